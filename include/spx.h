@@ -1,0 +1,267 @@
+/*
+ * spx.h — C-ABI of libspx.so, the B200 (sm_100a) implementation of the per-iteration
+ * registration hot path of fateshelled/sycl_points.
+ *
+ * The reference is a header-only C++20/SYCL library with no FFI of its own;
+ * this ABI replaces its SYCL queue / USM layer (I/utils/sycl_utils.hpp) and the kernels behind
+ * its public C++ entry points.  Each function cites the reference interface it stands in for:
+ *     I/ = cpp/include/sycl_points/     (paths inside fateshelled/sycl_points)
+ *
+ * Conventions
+ *  - every function returns 0 (SPX_OK) or a negative spx_status; spx_last_error() gives the
+ *    thread-local message.  CUDA errors are surfaced, never swallowed.
+ *  - all array arguments are DEVICE pointers obtained from spx_malloc (or any CUDA device
+ *    pointer on the queue's device) unless the name ends in _host.
+ *  - points / normals: float[n][4] (xyz1 / xyz0, I/points/types.hpp:11-13)
+ *    covariances:      float[n][16], column-major 4x4 with zero 4th row/col (types.hpp:12)
+ *    transforms:       float[16] HOST memory, column-major (Eigen::Matrix4f::data() order)
+ *    KNN result:       int32 idx[nq][k], float dist[nq][k] squared distances, ascending by
+ *                      (dist, idx); unfilled = -1 / FLT_MAX (I/algorithms/knn/result.hpp:12-34)
+ *  - work is enqueued on the queue's CUDA stream; functions that return values to the host
+ *    synchronise that stream, the others are asynchronous (call spx_queue_sync).
+ *  - a queue and the handles created from it are single-threaded, like the reference's
+ *    Registration / VoxelGrid / KDTree instances; distinct queues may run concurrently.
+ */
+#ifndef SPX_H_
+#define SPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SPX_API __attribute__((visibility("default")))
+#else
+#define SPX_API
+#endif
+
+typedef enum spx_status {
+    SPX_OK = 0,
+    SPX_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument / std::runtime_error in the reference */
+    SPX_ERR_CUDA = -2,
+    SPX_ERR_UNSUPPORTED = -3,
+    SPX_ERR_INTERNAL = -4
+} spx_status;
+
+/* I/algorithms/registration/factor.hpp:18-32 (same numeric values) */
+typedef enum spx_reg_type {
+    SPX_REG_POINT_TO_POINT = 0,
+    SPX_REG_POINT_TO_PLANE = 1,
+    SPX_REG_POINT_TO_DISTRIBUTION = 2, /* not built yet: SPX_ERR_UNSUPPORTED */
+    SPX_REG_GICP = 3,
+    SPX_REG_GENZ = 4 /* not built yet: SPX_ERR_UNSUPPORTED */
+} spx_reg_type;
+
+/* I/algorithms/robust/robust.hpp:14-20 */
+typedef enum spx_robust_loss {
+    SPX_LOSS_NONE = 0,
+    SPX_LOSS_HUBER = 1,
+    SPX_LOSS_TUKEY = 2,
+    SPX_LOSS_CAUCHY = 3,
+    SPX_LOSS_GEMAN_MCCLURE = 4
+} spx_robust_loss;
+
+/* I/algorithms/registration/registration_params.hpp:17-21 */
+typedef enum spx_optimization_method {
+    SPX_OPT_GAUSS_NEWTON = 0,
+    SPX_OPT_LEVENBERG_MARQUARDT = 1,
+    SPX_OPT_POWELL_DOGLEG = 2
+} spx_optimization_method;
+
+typedef struct spx_queue_s* spx_queue_t;               /* sycl_utils::DeviceQueue, sycl_utils.hpp:491-626 */
+typedef struct spx_event_s* spx_event_t;               /* sycl_utils::events,      sycl_utils.hpp:234-280 */
+typedef struct spx_index_s* spx_index_t;               /* knn::KDTree (as a KNNBase), kdtree.hpp:142-280 */
+typedef struct spx_registration_s* spx_registration_t; /* registration::Registration, registration.hpp:88-965 */
+
+/* RegistrationParams, I/algorithms/registration/registration_params.hpp:41-114 (defaults there). */
+typedef struct spx_registration_params {
+    int32_t reg_type;           /* spx_reg_type, default GICP */
+    int32_t robust_loss;        /* spx_robust_loss, default NONE */
+    int32_t optimization_method;/* spx_optimization_method, default GN */
+    int32_t max_iterations;     /* 20 */
+    float max_correspondence_distance; /* 2.0 */
+    float robust_default_scale; /* 10.0 */
+    float criteria_translation; /* 1e-3 m */
+    float criteria_rotation;    /* 1e-3 rad */
+    float gn_lambda;            /* 1.0 */
+    int32_t lm_max_inner_iterations; /* 10 */
+    float lm_lambda_factor;     /* 2 */
+    float lm_init_lambda;       /* 1 */
+    float lm_max_lambda;        /* 1e3 */
+    float lm_min_lambda;        /* 1e-6 */
+    float dogleg_initial_trust_region_radius; /* 1 */
+    float dogleg_min_trust_region_radius;     /* 1e-4 */
+    float dogleg_max_trust_region_radius;     /* 10 */
+    float dogleg_eta1;          /* .25 */
+    float dogleg_eta2;          /* .75 */
+    float dogleg_gamma_decrease;/* .25 */
+    float dogleg_gamma_increase;/* 2 */
+    int32_t reserved[8];        /* must be zero */
+} spx_registration_params;
+
+/* RegistrationResult, I/algorithms/registration/result.hpp:13-28.  `iterations` keeps the
+ * reference's meaning: the 0-based index of the last iteration run (registration.hpp:815). */
+typedef struct spx_registration_result {
+    float T[16];       /* column-major */
+    int32_t converged;
+    int32_t iterations;
+    float H[36];
+    float b[6];
+    float error;
+    float H_raw[36];
+    float b_raw[6];
+    float error_raw;
+    uint32_t inlier;
+} spx_registration_result;
+
+/* ------------------------------------------------------------------ runtime (replaces sycl_utils.hpp) */
+SPX_API const char* spx_last_error(void);
+SPX_API int spx_abi_version(void);
+SPX_API int spx_device_count(int* count);
+/* name: >= 256 bytes; sm = major*10+minor (100 on B200) */
+SPX_API int spx_device_info(int device, char* name, int* sm, int* sm_count, size_t* global_mem_bytes, int* l2_bytes);
+
+/* DeviceQueue(device) — sycl_utils.hpp:491-529.  Owns one in-order CUDA stream + scratch arena. */
+SPX_API int spx_queue_create(int device, spx_queue_t* out);
+/* Same, on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
+SPX_API int spx_queue_create_on_stream(int device, void* cuda_stream, spx_queue_t* out);
+SPX_API int spx_queue_destroy(spx_queue_t q);
+SPX_API int spx_queue_sync(spx_queue_t q); /* events.wait_and_throw(), sycl_utils.hpp:262-270 */
+SPX_API int spx_queue_device(spx_queue_t q, int* device);
+/* Kernels launched by this library since load (all queues): bench.py's `gpu_launches`. */
+SPX_API uint64_t spx_kernel_launch_count(void);
+
+/* shared_vector<T> storage — sycl_utils.hpp:630-635 (USM shared -> explicit device memory) */
+SPX_API int spx_malloc(spx_queue_t q, size_t bytes, void** out);
+SPX_API int spx_free(spx_queue_t q, void* ptr);
+SPX_API int spx_malloc_host(size_t bytes, void** out); /* pinned */
+SPX_API int spx_free_host(void* ptr);
+SPX_API int spx_memcpy_h2d(spx_queue_t q, void* dst, const void* src_host, size_t bytes); /* async on the stream */
+SPX_API int spx_memcpy_d2h(spx_queue_t q, void* dst_host, const void* src, size_t bytes); /* async on the stream */
+SPX_API int spx_memcpy_d2d(spx_queue_t q, void* dst, const void* src, size_t bytes);
+SPX_API int spx_memset(spx_queue_t q, void* dst, int value, size_t bytes);
+
+SPX_API int spx_event_create(spx_event_t* out);
+SPX_API int spx_event_destroy(spx_event_t e);
+SPX_API int spx_event_record(spx_queue_t q, spx_event_t e);
+SPX_API int spx_event_elapsed_ms(spx_event_t start, spx_event_t stop, float* ms); /* synchronises on stop */
+
+/* ------------------------------------------------------------------ KNN
+ * knn_search_bruteforce(queue, queries, targets, k) — I/algorithms/knn/bruteforce.hpp:24-96.
+ * Tile scan of all targets; dist = fma(dz,dz,fma(dy,dy,dx*dx)); result ordered by (dist, idx).
+ * T_host (nullable, 16 floats): transform applied to each query first — the reference's
+ * brute force takes none (pass NULL); KNNBase::knn_search_async does (knn.hpp:22-24).
+ * 1 <= k <= 128. */
+SPX_API int spx_knn_bruteforce(spx_queue_t q, const float* queries, size_t nq, const float* targets, size_t nt, int k,
+                       const float* T_host, int32_t* idx, float* dist);
+
+/* KDTree::build(queue, cloud, leaf) — kdtree.hpp:165-180,292-413.  Builds a GPU-resident exact
+ * index (uniform cell grid, counting-sorted on device) over `targets`; cell_size <= 0 picks one
+ * from the point density.  The index keeps its own sorted copy; `targets` may be freed after. */
+SPX_API int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_size, spx_index_t* out);
+SPX_API int spx_index_destroy(spx_index_t index);
+/* KNNBase::knn_search_async(queries, k, result, depends, transT) — knn.hpp:22-24,
+ * kdtree.hpp:203-224,424-562.  Exact: identical to spx_knn_bruteforce on the same inputs
+ * (ring search with a proven stop bound, brute-force pass for queries the rings cannot bound).
+ * 1 <= k <= 128 (the reference throws above 100, kdtree.hpp:221-223).  Asynchronous. */
+SPX_API int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, const float* T_host, int32_t* idx,
+                  float* dist);
+/* introspection for tests / DESIGN.md: cell size, grid dims[3], occupied cells, points */
+SPX_API int spx_index_info(spx_index_t index, float* cell_size, int32_t* dims3, int64_t* occupied_cells, int64_t* n_points);
+
+/* ------------------------------------------------------------------ features
+ * covariance::estimate_async(queue, neighbors, points, covs) — I/algorithms/feature/covariance.hpp:16-47,260-292 */
+SPX_API int spx_covariance(spx_queue_t q, const float* points, size_t n, const int32_t* knn_idx, int k, float* covs);
+/* covariance::estimate_normals_async(neighbors, points) — covariance.hpp:49-65,417-445 */
+SPX_API int spx_normals(spx_queue_t q, const float* points, size_t n, const int32_t* knn_idx, int k, float* normals);
+/* covariance::extract_normals_async(points) — covariance.hpp:467-495 */
+SPX_API int spx_normals_from_covs(spx_queue_t q, const float* points, const float* covs, size_t n, float* normals);
+
+/* ------------------------------------------------------------------ filters
+ * filter::VoxelGrid::downsampling(points, result) — I/algorithms/filter/voxel_downsampling.hpp:50-62,
+ * key = I/algorithms/common/voxel_constants.hpp:36-62.  Device radix sort by (key, index), fp32
+ * running sum per voxel in that order, mean = sum / sum.w, voxels with sum.w < min_voxel_count
+ * dropped, output ascending key.  out_points must hold n points; *m_host receives the count
+ * (synchronises).  voxel_size <= 0 -> SPX_ERR_INVALID_ARGUMENT (voxel_downsampling.hpp:23-25). */
+SPX_API int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n, float voxel_size, size_t min_voxel_count,
+                         float* out_points, size_t* m_host);
+/* PreprocessFilter::box_filter(cloud, min, max) — preprocess_operator/box_filter_operator.hpp:19-54,
+ * common.hpp:15-25, common/filter_by_flags.hpp:43-49 (order-preserving).  Synchronises. */
+SPX_API int spx_box_filter(spx_queue_t q, const float* points, size_t n, float min_distance, float max_distance,
+                   float* out_points, size_t* m_host);
+
+/* ------------------------------------------------------------------ registration
+ * Registration::compute_linearized_result / linearize — registration.hpp:312-331,513-676:
+ * per source i: skip if dist[i] > max_corr_sq; factor (factor.hpp:130-278) on
+ * (src[i], tgt[idx[i]]); robust weight/rho (robust.hpp:56-114); sum to 6x6 H, 6 b, error,
+ * inlier.  src_covs/tgt_covs NULL -> identity, tgt_normals NULL -> zero (registration.hpp:589-592).
+ * Outputs are HOST pointers (H 36 floats, symmetric); synchronises like the reference (:674). */
+SPX_API int spx_linearize(spx_queue_t q, int reg_type, int robust_loss, const float* src_points, const float* src_covs,
+                  size_t ns, const float* tgt_points, const float* tgt_covs, const float* tgt_normals,
+                  const int32_t* nn_idx, const float* nn_dist, const float* T_host, float max_corr_sq,
+                  float robust_scale, float* H_host, float* b_host, float* error_host, uint32_t* inlier_host);
+/* Registration::compute_error_frozen / compute_error — registration.hpp:350-359,678-789 */
+SPX_API int spx_error(spx_queue_t q, int reg_type, int robust_loss, const float* src_points, const float* src_covs, size_t ns,
+              const float* tgt_points, const float* tgt_covs, const float* tgt_normals, const int32_t* nn_idx,
+              const float* nn_dist, const float* T_host, float max_corr_sq, float robust_scale, float* error_host,
+              uint32_t* inlier_host);
+/* Registration::compute_icp_robust_weights — registration.hpp:279-294,412-462; weights[ns] device. */
+SPX_API int spx_robust_weights(spx_queue_t q, int reg_type, int robust_loss, const float* src_points, const float* src_covs,
+                       size_t ns, const float* tgt_points, const float* tgt_covs, const float* tgt_normals,
+                       const int32_t* nn_idx, const float* nn_dist, const float* T_host, float max_corr_sq,
+                       float robust_scale, float* weights);
+
+/* host-side pieces of the optimiser, exported so a caller that injects its own KNN (the
+ * reference's tests subclass KNNBase) can drive the loop: registration.hpp:791-801 (LDLT solve
+ * of (H + lambda I) delta = -b, fp64 inside), eigen_utils.hpp:909-943 (se3_exp, column-major
+ * out), dogleg_step.hpp:34-102. */
+SPX_API void spx_default_registration_params(spx_registration_params* p);
+SPX_API int spx_solve_6x6(const float* H_host, const float* b_host, float lambda, float* delta_host, int* success);
+SPX_API int spx_se3_exp(const float* twist6_host, float* T_host);
+SPX_API int spx_dogleg_step(const float* H_host, const float* g_host, float radius, float* p_host, float* step_norm,
+                    float* predicted_reduction);
+
+/* Registration(queue, params) — registration.hpp:105-114 */
+SPX_API int spx_registration_create(spx_queue_t q, const spx_registration_params* params, spx_registration_t* out);
+SPX_API int spx_registration_destroy(spx_registration_t reg);
+SPX_API int spx_registration_set_params(spx_registration_t reg, const spx_registration_params* params);
+
+/* Registration::align(source, target, target_knn, initial_guess, options) — registration.hpp:201-276
+ * with the target's spx_index as the KNNBase.  GN runs as a device-resident loop (nearest
+ * neighbour + linearise + reduce + 6x6 solve + pose update in one kernel per iteration, no host
+ * round trip until the end); LM / dog-leg take one host decision per trial step (:830-964).
+ * robust_scale <= 0 selects params.robust_default_scale (:217-218).  Missing inputs raise the
+ * reference's validate_params errors (:129-193).  T_trace_host (nullable): max_iterations*16
+ * floats, pose after each outer iteration.  Synchronises. */
+SPX_API int spx_registration_align(spx_registration_t reg, const float* src_points, const float* src_covs, size_t ns,
+                           const float* tgt_points, const float* tgt_covs, const float* tgt_normals, size_t nt,
+                           spx_index_t target_index, const float* T_init_host, float robust_scale,
+                           spx_registration_result* result_host, float* T_trace_host);
+/* neighbours cached by the last align / linearise on this handle (registration.hpp:365), device
+ * pointers valid until the next call: used by compute_error_frozen-style callers */
+SPX_API int spx_registration_neighbors(spx_registration_t reg, const int32_t** nn_idx, const float** nn_dist, size_t* n);
+
+/* ------------------------------------------------------------------ multi-GPU building blocks
+ * Source points are sharded across ranks, the target + index replicated.
+ * One outer GN iteration on a shard = nearest neighbour + linearise + block reduce into
+ * sums_dev[SPX_SUMS_LEN] doubles (21 upper-triangle H terms, 6 b, error, inlier count, 3 pad) with
+ * NO host sync; the caller all-reduces sums_dev (NCCL, same stream) and then calls
+ * spx_registration_shard_update on every rank, which solves and advances the device-resident
+ * pose identically everywhere. */
+#define SPX_SUMS_LEN 32
+SPX_API int spx_registration_shard_begin(spx_registration_t reg, const float* src_points, const float* src_covs, size_t ns,
+                                 const float* tgt_points, const float* tgt_covs, const float* tgt_normals, size_t nt,
+                                 spx_index_t target_index, const float* T_init_host, float robust_scale);
+SPX_API int spx_registration_shard_linearize(spx_registration_t reg, double* sums_dev);
+SPX_API int spx_registration_shard_update(spx_registration_t reg, const double* sums_dev);
+SPX_API int spx_registration_shard_finish(spx_registration_t reg, spx_registration_result* result_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPX_H_ */

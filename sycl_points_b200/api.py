@@ -1,0 +1,959 @@
+"""Host-side mirror of the reference's C++ interface for the hot path, on top of the C-ABI.
+
+Names, argument meaning and error behaviour follow the reference (I/ = cpp/include/sycl_points/):
+DeviceQueue (I/utils/sycl_utils.hpp:491), PointCloudShared (I/points/point_cloud.hpp:73),
+knn.KNNResult / KNNBase / KDTree / knn_search_bruteforce (I/algorithms/knn/),
+covariance.estimate / estimate_normals / extract_normals (I/algorithms/feature/covariance.hpp),
+filter.VoxelGrid / PreprocessFilter.box_filter (I/algorithms/filter/),
+registration.Registration / RegistrationParams / RegistrationResult / RegistrationPipeline
+(I/algorithms/registration/).  numpy arrays are host data; every compute call runs on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import RegistrationParamsC, RegistrationResultC, SpxError, SpxInvalidArgument, check
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def _hostf(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _T16(T) -> np.ndarray | None:
+    """4x4 (row-major numpy) -> 16 floats column-major, the layout of Eigen::Matrix4f::data()."""
+    if T is None:
+        return None
+    T = np.asarray(T, dtype=np.float32).reshape(4, 4)
+    return np.ascontiguousarray(T.T).reshape(16)
+
+
+def _T_from16(t16) -> np.ndarray:
+    return np.array(t16, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+# ------------------------------------------------------------------ runtime
+class DeviceQueue:
+    """sycl_utils::DeviceQueue (sycl_utils.hpp:491-626): one in-order CUDA stream on one device."""
+
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+        L = _lib.lib()
+        h = C.c_void_p()
+        if cuda_stream is None:
+            check(L.spx_queue_create(device, C.byref(h)))
+        else:
+            check(L.spx_queue_create_on_stream(device, C.c_void_p(cuda_stream), C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().spx_queue_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def wait(self):
+        """events.wait_and_throw()"""
+        check(_lib.lib().spx_queue_sync(self._h))
+
+    def is_cpu(self) -> bool:
+        return False
+
+    def is_gpu(self) -> bool:
+        return True
+
+    def is_nvidia(self) -> bool:
+        return True
+
+    def device_info(self) -> dict:
+        name = C.create_string_buffer(256)
+        sm, smc, l2 = C.c_int(), C.c_int(), C.c_int()
+        mem = C.c_size_t()
+        check(_lib.lib().spx_device_info(self.device, name, C.byref(sm), C.byref(smc), C.byref(mem), C.byref(l2)))
+        return dict(name=name.value.decode(), sm=sm.value, sm_count=smc.value, global_mem=mem.value, l2=l2.value)
+
+
+def device_count() -> int:
+    n = C.c_int()
+    check(_lib.lib().spx_device_count(C.byref(n)))
+    return n.value
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.lib().spx_kernel_launch_count())
+
+
+class Event:
+    def __init__(self):
+        h = C.c_void_p()
+        check(_lib.lib().spx_event_create(C.byref(h)))
+        self._h = h
+
+    def record(self, queue: DeviceQueue):
+        check(_lib.lib().spx_event_record(queue.handle, self._h))
+        return self
+
+    def elapsed_ms(self, later: "Event") -> float:
+        ms = C.c_float()
+        check(_lib.lib().spx_event_elapsed_ms(self._h, later._h, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().spx_event_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """Pinned host staging buffer (cudaMallocHost) viewed as a numpy array."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.shape = tuple(shape) if not isinstance(shape, int) else (shape,)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(_lib.lib().spx_malloc_host(max(nbytes, 1), C.byref(p)))
+        self._p = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.array = None
+                _lib.lib().spx_free_host(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+class DeviceArray:
+    """shared_vector<T> (sycl_utils.hpp:630-635) as explicit device memory + host copies on demand."""
+
+    def __init__(self, queue: DeviceQueue, shape, dtype=np.float32):
+        self.queue = queue
+        self.shape = tuple(shape) if not isinstance(shape, int) else (shape,)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(_lib.lib().spx_malloc(queue.handle, self.nbytes, C.byref(p)))
+        self._p = p
+
+    @classmethod
+    def from_host(cls, queue: DeviceQueue, a: np.ndarray) -> "DeviceArray":
+        a = np.ascontiguousarray(a)
+        d = cls(queue, a.shape, a.dtype)
+        d.upload(a)
+        return d
+
+    @property
+    def ptr(self):
+        return self._p
+
+    def __len__(self):
+        return self.shape[0] if self.shape else 0
+
+    def upload(self, a: np.ndarray, sync: bool = True):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        if self.nbytes:
+            check(_lib.lib().spx_memcpy_h2d(self.queue.handle, self._p, a.ctypes.data_as(C.c_void_p), self.nbytes))
+            if sync:
+                self.queue.wait()  # pageable source: keep it alive until the copy has run
+
+    def download(self, count: int | None = None) -> np.ndarray:
+        shape = self.shape if count is None else (count,) + self.shape[1:]
+        out = np.empty(shape, self.dtype)
+        if out.nbytes:
+            check(_lib.lib().spx_memcpy_d2h(self.queue.handle, out.ctypes.data_as(C.c_void_p), self._p, out.nbytes))
+        self.queue.wait()
+        return out
+
+    def free(self):
+        if getattr(self, "_p", None) and self._p:
+            _lib.lib().spx_free(self.queue.handle, self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _ptr(a: DeviceArray | None):
+    return None if a is None else a.ptr
+
+
+# ------------------------------------------------------------------ containers
+class PointCloudShared:
+    """PointCloudShared (point_cloud.hpp:73-476): per-attribute arrays on the device.
+    points (n,4) xyz1; covs (n,4,4) symmetric, zero 4th row/col; normals (n,4) xyz0."""
+
+    def __init__(self, queue: DeviceQueue, points: np.ndarray | None = None, covs: np.ndarray | None = None,
+                 normals: np.ndarray | None = None):
+        self.queue = queue
+        self.points: DeviceArray | None = None
+        self.covs: DeviceArray | None = None
+        self.normals: DeviceArray | None = None
+        self._n = 0
+        if points is not None:
+            self.set_points(points)
+        if covs is not None:
+            self.set_covs(covs)
+        if normals is not None:
+            self.set_normals(normals)
+
+    def size(self) -> int:
+        return self._n
+
+    def __len__(self):
+        return self._n
+
+    def has_cov(self) -> bool:
+        return self.covs is not None and len(self.covs) == self._n
+
+    def has_normal(self) -> bool:
+        return self.normals is not None and len(self.normals) == self._n
+
+    def set_points(self, points: np.ndarray):
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        if p.ndim != 2 or p.shape[1] != 4:
+            raise ValueError("points must be (n, 4) float32 (xyz1)")
+        self.points = DeviceArray.from_host(self.queue, p)
+        self._n = len(p)
+
+    def set_covs(self, covs: np.ndarray):
+        c = np.asarray(covs, dtype=np.float32).reshape(-1, 4, 4)
+        # host convention: row-major numpy; device/reference convention: column-major Matrix4f
+        self.covs = DeviceArray.from_host(self.queue, np.ascontiguousarray(c.transpose(0, 2, 1)).reshape(-1, 16))
+
+    def set_normals(self, normals: np.ndarray):
+        self.normals = DeviceArray.from_host(self.queue, np.ascontiguousarray(normals, dtype=np.float32))
+
+    def adopt_points(self, dev: DeviceArray, n: int):
+        self.points = dev
+        self._n = n
+
+    def points_host(self) -> np.ndarray:
+        return self.points.download(self._n) if self._n else np.zeros((0, 4), np.float32)
+
+    def covs_host(self) -> np.ndarray:
+        return self.covs.download(self._n).reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+    def normals_host(self) -> np.ndarray:
+        return self.normals.download(self._n)
+
+
+# ------------------------------------------------------------------ KNN
+class KNNResult:
+    """knn::KNNResult (result.hpp:12-34): indices int32 [q][k], squared distances float [q][k]."""
+
+    def __init__(self):
+        self.indices: DeviceArray | None = None
+        self.distances: DeviceArray | None = None
+        self.query_size = 0
+        self.k = 0
+
+    def allocate(self, queue: DeviceQueue, query_size: int = 0, k: int = 0):
+        self.query_size, self.k = query_size, k
+        self.indices = DeviceArray(queue, (query_size, k), np.int32)
+        self.distances = DeviceArray(queue, (query_size, k), np.float32)
+
+    def indices_host(self) -> np.ndarray:
+        return self.indices.download() if self.query_size * self.k else np.zeros((self.query_size, self.k), np.int32)
+
+    def distances_host(self) -> np.ndarray:
+        return self.distances.download() if self.query_size * self.k else np.zeros((self.query_size, self.k),
+                                                                                    np.float32)
+
+
+class KNNBase:
+    """knn::KNNBase (knn.hpp:14-61).  Subclass and implement knn_search_async to inject a KNN."""
+
+    def knn_search_async(self, queries: PointCloudShared, k: int, result: KNNResult, depends=None, transT=None):
+        raise NotImplementedError
+
+    def knn_search(self, queries: PointCloudShared, k: int, depends=None, transT=None) -> KNNResult:
+        result = KNNResult()
+        self.knn_search_async(queries, k, result, depends, transT)
+        queries.queue.wait()
+        return result
+
+    def nearest_neighbor_search_async(self, queries, result, depends=None, transT=None):
+        return self.knn_search_async(queries, 1, result, depends, transT)
+
+    def nearest_neighbor_search(self, queries, result, depends=None, transT=None):
+        self.nearest_neighbor_search_async(queries, result, depends, transT)
+        queries.queue.wait()
+
+
+def knn_search_bruteforce(queue: DeviceQueue, queries: PointCloudShared, targets: PointCloudShared, k: int,
+                          transT=None) -> KNNResult:
+    """knn::knn_search_bruteforce (bruteforce.hpp:24-96); synchronous like the reference (:93)."""
+    result = KNNResult()
+    result.allocate(queue, queries.size(), k)
+    t16 = _T16(transT)
+    check(_lib.lib().spx_knn_bruteforce(queue.handle, _ptr(queries.points), queries.size(), _ptr(targets.points),
+                                        targets.size(), k, _hostf(t16), result.indices.ptr, result.distances.ptr))
+    queue.wait()
+    return result
+
+
+class KDTree(KNNBase):
+    """knn::KDTree (kdtree.hpp:142-280) — same interface, GPU-resident exact cell-grid index inside."""
+
+    def __init__(self, queue: DeviceQueue):
+        self.queue = queue
+        self._h = None
+        self._n = 0
+
+    @staticmethod
+    def build(queue: DeviceQueue, cloud: PointCloudShared, leaf_threshold: int = 16, cell_size: float = 0.0):
+        # leaf_threshold is the reference's KD-tree knob; it has no meaning for the grid (accepted, ignored)
+        t = KDTree(queue)
+        h = C.c_void_p()
+        check(_lib.lib().spx_index_build(queue.handle, _ptr(cloud.points), cloud.size(), float(cell_size),
+                                         C.byref(h)))
+        t._h = h
+        t._n = cloud.size()
+        return t
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> dict:
+        cell = C.c_float()
+        dims = (C.c_int32 * 3)()
+        occ, npts = C.c_int64(), C.c_int64()
+        check(_lib.lib().spx_index_info(self._h, C.byref(cell), dims, C.byref(occ), C.byref(npts)))
+        return dict(cell_size=cell.value, dims=tuple(dims), occupied_cells=occ.value, n_points=npts.value)
+
+    def knn_search_async(self, queries: PointCloudShared, k: int, result: KNNResult, depends=None, transT=None):
+        if k > 128:
+            raise SpxInvalidArgument(-1, "[KDTree::knn_search_async] `k` is too large. not support.")
+        nq = queries.size()
+        if result.indices is None or result.query_size != nq or result.k != k:
+            result.allocate(self.queue, nq, k if nq else 0)  # kdtree.hpp:429-450
+        if nq == 0:
+            return
+        t16 = _T16(transT)
+        check(_lib.lib().spx_index_knn(self._h, _ptr(queries.points), nq, k, _hostf(t16), result.indices.ptr,
+                                       result.distances.ptr))
+
+    def close(self):
+        if self._h:
+            _lib.lib().spx_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ features
+class covariance:  # namespace sycl_points::algorithms::covariance
+    @staticmethod
+    def estimate(neighbors: KNNResult, points: PointCloudShared):
+        """covariance::estimate_async(neighbors, points) (covariance.hpp:260-302)"""
+        n = points.size()
+        if points.covs is None or len(points.covs) != n:
+            points.covs = DeviceArray(points.queue, (n, 16), np.float32)
+        check(_lib.lib().spx_covariance(points.queue.handle, _ptr(points.points), n, _ptr(neighbors.indices),
+                                        neighbors.k, points.covs.ptr))
+
+    @staticmethod
+    def estimate_knn(knn: KNNBase, points: PointCloudShared, k_correspondences: int):
+        """covariance::estimate_async(knn, points, k) (covariance.hpp:304-311)"""
+        neighbors = KNNResult()
+        knn.knn_search_async(points, k_correspondences, neighbors)
+        covariance.estimate(neighbors, points)
+
+    @staticmethod
+    def estimate_normals(neighbors: KNNResult, points: PointCloudShared):
+        """covariance::estimate_normals_async (covariance.hpp:417-445)"""
+        n = points.size()
+        if points.normals is None or len(points.normals) != n:
+            points.normals = DeviceArray(points.queue, (n, 4), np.float32)
+        check(_lib.lib().spx_normals(points.queue.handle, _ptr(points.points), n, _ptr(neighbors.indices),
+                                     neighbors.k, points.normals.ptr))
+
+    @staticmethod
+    def extract_normals(points: PointCloudShared):
+        """covariance::extract_normals (covariance.hpp:467-503)"""
+        if not points.has_cov():
+            raise SpxInvalidArgument(-1, "[covariance::extract_normals_async] covariances not computed")
+        n = points.size()
+        if points.normals is None or len(points.normals) != n:
+            points.normals = DeviceArray(points.queue, (n, 4), np.float32)
+        check(_lib.lib().spx_normals_from_covs(points.queue.handle, _ptr(points.points), points.covs.ptr, n,
+                                               points.normals.ptr))
+
+
+# ------------------------------------------------------------------ filters
+class VoxelGrid:
+    """filter::VoxelGrid (voxel_downsampling.hpp:14-79)."""
+
+    def __init__(self, queue: DeviceQueue, voxel_size: float):
+        if voxel_size <= 0.0:
+            raise ValueError("voxel_size must be positive")  # std::invalid_argument, :23-25
+        self.queue = queue
+        self._voxel_size = float(voxel_size)
+        self._min_voxel_count = 1
+
+    def set_voxel_size(self, voxel_size: float):
+        if voxel_size <= 0.0:
+            raise ValueError("voxel_size must be positive")
+        self._voxel_size = float(voxel_size)
+
+    def get_voxel_size(self) -> float:
+        return self._voxel_size
+
+    def set_min_voxel_count(self, n: int):
+        self._min_voxel_count = int(n)
+
+    def downsampling(self, cloud: PointCloudShared, result: PointCloudShared | None = None) -> PointCloudShared:
+        result = result if result is not None else PointCloudShared(self.queue)
+        n = cloud.size()
+        if n == 0:
+            result.adopt_points(DeviceArray(self.queue, (0, 4), np.float32), 0)
+            return result
+        out = DeviceArray(self.queue, (n, 4), np.float32)
+        m = C.c_size_t()
+        check(_lib.lib().spx_voxel_downsample(self.queue.handle, cloud.points.ptr, n, self._voxel_size,
+                                              self._min_voxel_count, out.ptr, C.byref(m)))
+        result.adopt_points(out, int(m.value))
+        result.covs = None
+        result.normals = None
+        return result
+
+
+class PreprocessFilter:
+    """filter::PreprocessFilter — only box_filter is on the path (preprocess_filter.hpp, box_filter_operator.hpp)."""
+
+    def __init__(self, queue: DeviceQueue):
+        self.queue = queue
+
+    def box_filter(self, cloud: PointCloudShared, min_distance: float = 1.0, max_distance: float = FLT_MAX,
+                   output: PointCloudShared | None = None) -> PointCloudShared:
+        output = output if output is not None else cloud
+        n = cloud.size()
+        if n == 0:
+            return output
+        out = DeviceArray(self.queue, (n, 4), np.float32)
+        m = C.c_size_t()
+        check(_lib.lib().spx_box_filter(self.queue.handle, cloud.points.ptr, n, min_distance, max_distance, out.ptr,
+                                        C.byref(m)))
+        output.adopt_points(out, int(m.value))
+        output.covs = None
+        output.normals = None
+        return output
+
+
+# ------------------------------------------------------------------ registration
+class RegType(enum.IntEnum):  # factor.hpp:18-32
+    POINT_TO_POINT = 0
+    POINT_TO_PLANE = 1
+    POINT_TO_DISTRIBUTION = 2
+    GICP = 3
+    GENZ = 4
+
+
+class RobustLossType(enum.IntEnum):  # robust.hpp:14-20
+    NONE = 0
+    HUBER = 1
+    TUKEY = 2
+    CAUCHY = 3
+    GEMAN_MCCLURE = 4
+
+
+class OptimizationMethod(enum.IntEnum):  # registration_params.hpp:17-21
+    GAUSS_NEWTON = 0
+    LEVENBERG_MARQUARDT = 1
+    POWELL_DOGLEG = 2
+
+
+def RegType_from_string(s: str) -> RegType:  # factor.hpp:43-61
+    u = s.upper()
+    if u == "P2D":
+        return RegType.POINT_TO_DISTRIBUTION
+    try:
+        return RegType[u]
+    except KeyError:
+        raise RuntimeError(f"[RegType_from_string] Invalid RegType str '{s}'")
+
+
+def RobustLossType_from_string(s: str) -> RobustLossType:  # robust.hpp:30-48
+    try:
+        return RobustLossType[s.upper()]
+    except KeyError:
+        raise RuntimeError(f"[RobustLossType_from_string] Invalid RobustLossType str '{s}'")
+
+
+def OptimizationMethod_from_string(s: str) -> OptimizationMethod:  # registration_params.hpp:23-38
+    u = s.upper()
+    table = {"GN": 0, "GAUSS_NEWTON": 0, "LM": 1, "LEVENBERG_MARQUARDT": 1, "DOGLEG": 2, "POWELL_DOGLEG": 2}
+    if u not in table:
+        raise RuntimeError(f"[OptimizationMethod_from_string] Invalid OptimizationMethod str [{s}]")
+    return OptimizationMethod(table[u])
+
+
+@dataclass
+class RobustParams:
+    type: RobustLossType = RobustLossType.NONE
+    default_scale: float = 10.0
+
+
+@dataclass
+class Criteria:
+    translation: float = 1e-3
+    rotation: float = 1e-3
+
+
+@dataclass
+class GaussNewtonParams:
+    lambda_: float = 1.0
+
+
+@dataclass
+class LevenbergMarquardtParams:
+    max_inner_iterations: int = 10
+    lambda_factor: float = 2.0
+    init_lambda: float = 1.0
+    max_lambda: float = 1e3
+    min_lambda: float = 1e-6
+
+
+@dataclass
+class DoglegParams:
+    initial_trust_region_radius: float = 1.0
+    min_trust_region_radius: float = 1e-4
+    max_trust_region_radius: float = 10.0
+    eta1: float = 0.25
+    eta2: float = 0.75
+    gamma_decrease: float = 0.25
+    gamma_increase: float = 2.0
+
+
+@dataclass
+class RegistrationParams:
+    """RegistrationParams (registration_params.hpp:41-114), same defaults."""
+    reg_type: RegType = RegType.GICP
+    max_correspondence_distance: float = 2.0
+    robust: RobustParams = field(default_factory=RobustParams)
+    verbose: bool = False
+    gn: GaussNewtonParams = field(default_factory=GaussNewtonParams)
+    lm: LevenbergMarquardtParams = field(default_factory=LevenbergMarquardtParams)
+    dogleg: DoglegParams = field(default_factory=DoglegParams)
+    optimization_method: OptimizationMethod = OptimizationMethod.GAUSS_NEWTON
+    max_iterations: int = 20
+    criteria: Criteria = field(default_factory=Criteria)
+
+    def to_c(self) -> RegistrationParamsC:
+        P = RegistrationParamsC()
+        _lib.lib().spx_default_registration_params(C.byref(P))
+        P.reg_type = int(self.reg_type)
+        P.robust_loss = int(self.robust.type)
+        P.optimization_method = int(self.optimization_method)
+        P.max_iterations = int(self.max_iterations)
+        P.max_correspondence_distance = self.max_correspondence_distance
+        P.robust_default_scale = self.robust.default_scale
+        P.criteria_translation = self.criteria.translation
+        P.criteria_rotation = self.criteria.rotation
+        P.gn_lambda = self.gn.lambda_
+        P.lm_max_inner_iterations = self.lm.max_inner_iterations
+        P.lm_lambda_factor = self.lm.lambda_factor
+        P.lm_init_lambda = self.lm.init_lambda
+        P.lm_max_lambda = self.lm.max_lambda
+        P.lm_min_lambda = self.lm.min_lambda
+        P.dogleg_initial_trust_region_radius = self.dogleg.initial_trust_region_radius
+        P.dogleg_min_trust_region_radius = self.dogleg.min_trust_region_radius
+        P.dogleg_max_trust_region_radius = self.dogleg.max_trust_region_radius
+        P.dogleg_eta1 = self.dogleg.eta1
+        P.dogleg_eta2 = self.dogleg.eta2
+        P.dogleg_gamma_decrease = self.dogleg.gamma_decrease
+        P.dogleg_gamma_increase = self.dogleg.gamma_increase
+        return P
+
+
+@dataclass
+class RegistrationResult:
+    """RegistrationResult (result.hpp:13-28)."""
+    T: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    converged: bool = False
+    iterations: int = 0
+    H: np.ndarray = field(default_factory=lambda: np.zeros((6, 6), np.float32))
+    b: np.ndarray = field(default_factory=lambda: np.zeros(6, np.float32))
+    error: float = FLT_MAX
+    H_raw: np.ndarray = field(default_factory=lambda: np.zeros((6, 6), np.float32))
+    b_raw: np.ndarray = field(default_factory=lambda: np.zeros(6, np.float32))
+    error_raw: float = FLT_MAX
+    inlier: int = 0
+    trace: np.ndarray | None = None  # pose after every outer iteration (parity tests)
+
+    @staticmethod
+    def from_c(R: RegistrationResultC) -> "RegistrationResult":
+        return RegistrationResult(T=_T_from16(R.T), converged=bool(R.converged), iterations=int(R.iterations),
+                                  H=np.array(R.H, np.float32).reshape(6, 6), b=np.array(R.b, np.float32),
+                                  error=float(R.error), H_raw=np.array(R.H_raw, np.float32).reshape(6, 6),
+                                  b_raw=np.array(R.b_raw, np.float32), error_raw=float(R.error_raw),
+                                  inlier=int(R.inlier))
+
+
+@dataclass
+class LinearizedResult:
+    """LinearizedResult (linearized_result.hpp:12-23)."""
+    H: np.ndarray
+    b: np.ndarray
+    error: float
+    inlier: int
+
+
+@dataclass
+class ExecutionOptions:
+    """Registration::ExecutionOptions (registration.hpp:92-100)."""
+    robust_scale: float = -1.0
+    rotation_robust_scale: float = -1.0
+    dt: float = 0.1
+    prev_pose: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+
+
+def se3_exp(twist) -> np.ndarray:
+    tw = np.ascontiguousarray(twist, np.float32)
+    out = np.empty(16, np.float32)
+    check(_lib.lib().spx_se3_exp(_hostf(tw), _hostf(out)))
+    return _T_from16(out)
+
+
+def solve_6x6(H, b, lam: float):
+    H = np.ascontiguousarray(H, np.float32).reshape(36)
+    b = np.ascontiguousarray(b, np.float32)
+    d = np.empty(6, np.float32)
+    ok = C.c_int()
+    check(_lib.lib().spx_solve_6x6(_hostf(H), _hostf(b), lam, _hostf(d), C.byref(ok)))
+    return bool(ok.value), d
+
+
+def dogleg_step(H, g, radius: float):
+    H = np.ascontiguousarray(H, np.float32).reshape(36)
+    g = np.ascontiguousarray(g, np.float32)
+    p = np.empty(6, np.float32)
+    sn, pr = C.c_float(), C.c_float()
+    check(_lib.lib().spx_dogleg_step(_hostf(H), _hostf(g), radius, _hostf(p), C.byref(sn), C.byref(pr)))
+    return p, sn.value, pr.value
+
+
+class Registration:
+    """registration::Registration (registration.hpp:88-965)."""
+
+    def __init__(self, queue: DeviceQueue, params: RegistrationParams | None = None):
+        self.queue = queue
+        self.params = params if params is not None else RegistrationParams()
+        h = C.c_void_p()
+        Pc = self.params.to_c()
+        check(_lib.lib().spx_registration_create(queue.handle, C.byref(Pc), C.byref(h)))
+        self._h = h
+        self._neighbors = KNNResult()  # registration.hpp:365 (used with injected KNNs)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().spx_registration_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _scale(self, options: ExecutionOptions | None) -> float:
+        s = options.robust_scale if options is not None else -1.0
+        return s if s > 0.0 else self.params.robust.default_scale  # registration.hpp:217-218
+
+    def _loss(self) -> int:
+        if self.params.robust.type != RobustLossType.NONE and self.params.robust.default_scale <= 0.0:
+            print("[Caution] `robust.default_scale` must be greater than zero. Disable robust loss.")
+            self.params.robust.type = RobustLossType.NONE  # registration.hpp:186-192
+        return int(self.params.robust.type)
+
+    def _validate(self, source: PointCloudShared, target: PointCloudShared):
+        # registration.hpp:129-193
+        if self.params.reg_type == RegType.POINT_TO_PLANE and not target.has_normal():
+            if not target.has_cov():
+                raise RuntimeError("[Registration::validate_params] Normal vector or covariance matrices of target "
+                                   "must be pre-computed before performing Point-to-Plane ICP matching.")
+            print("[Caution] Normal vectors for Point-to-Plane ICP are not provided. ")
+            print("          Attempting to derive them from pre-computed covariance matrices.")
+            covariance.extract_normals(target)
+        if self.params.reg_type == RegType.GICP and (not source.has_cov() or not target.has_cov()):
+            raise RuntimeError("[Registration::validate_params] Covariance matrices of source and target must be "
+                               "pre-computed before performing GICP matching.")
+
+    def align(self, source: PointCloudShared, target: PointCloudShared, target_knn: KNNBase, initial_guess=None,
+              options: ExecutionOptions | None = None, trace: bool = False) -> RegistrationResult:
+        """Registration::align (registration.hpp:201-276)."""
+        T0 = np.eye(4, dtype=np.float32) if initial_guess is None else np.asarray(initial_guess, np.float32)
+        if source.size() == 0:
+            return RegistrationResult(T=T0.copy())
+        self._validate(source, target)
+        self._loss()
+        if not isinstance(target_knn, KDTree):
+            return self._align_injected_knn(source, target, target_knn, T0, options, trace)
+        Pc = self.params.to_c()
+        check(_lib.lib().spx_registration_set_params(self._h, C.byref(Pc)))
+        R = RegistrationResultC()
+        t16 = _T16(T0)
+        tr = np.zeros((max(self.params.max_iterations, 1), 16), np.float32) if trace else None
+        scale = options.robust_scale if options is not None else -1.0
+        check(_lib.lib().spx_registration_align(
+            self._h, source.points.ptr, _ptr(source.covs) if source.has_cov() else None, source.size(),
+            target.points.ptr, _ptr(target.covs) if target.has_cov() else None,
+            _ptr(target.normals) if target.has_normal() else None, target.size(), target_knn.handle, _hostf(t16),
+            float(scale), C.byref(R), _hostf(tr)))
+        out = RegistrationResult.from_c(R)
+        if trace:
+            out.trace = np.stack([_T_from16(t) for t in tr])
+        return out
+
+    # -- pieces usable with any KNNBase (the reference's tests inject host KNNs)
+    def _linearize(self, source, target, nn: KNNResult, T, scale) -> LinearizedResult:
+        H = np.empty(36, np.float32)
+        b = np.empty(6, np.float32)
+        err, inl = C.c_float(), C.c_uint32()
+        mc = np.float32(self.params.max_correspondence_distance)
+        t16 = _T16(T)
+        check(_lib.lib().spx_linearize(
+            self.queue.handle, int(self.params.reg_type), self._loss(), source.points.ptr,
+            _ptr(source.covs) if source.has_cov() else None, source.size(), target.points.ptr,
+            _ptr(target.covs) if target.has_cov() else None, _ptr(target.normals) if target.has_normal() else None,
+            nn.indices.ptr, nn.distances.ptr, _hostf(t16), float(mc * mc), float(scale), _hostf(H), _hostf(b),
+            C.byref(err), C.byref(inl)))
+        return LinearizedResult(H.reshape(6, 6), b, err.value, inl.value)
+
+    def _error(self, source, target, nn: KNNResult, T, scale):
+        err, inl = C.c_float(), C.c_uint32()
+        mc = np.float32(self.params.max_correspondence_distance)
+        t16 = _T16(T)
+        check(_lib.lib().spx_error(
+            self.queue.handle, int(self.params.reg_type), self._loss(), source.points.ptr,
+            _ptr(source.covs) if source.has_cov() else None, source.size(), target.points.ptr,
+            _ptr(target.covs) if target.has_cov() else None, _ptr(target.normals) if target.has_normal() else None,
+            nn.indices.ptr, nn.distances.ptr, _hostf(t16), float(mc * mc), float(scale), C.byref(err),
+            C.byref(inl)))
+        return err.value, inl.value
+
+    def compute_linearized_result(self, source, target, target_knn: KNNBase, pose,
+                                  options: ExecutionOptions | None = None) -> LinearizedResult:
+        """Registration::compute_linearized_result (registration.hpp:312-331)."""
+        target_knn.nearest_neighbor_search_async(source, self._neighbors, None, pose)
+        return self._linearize(source, target, self._neighbors, pose, self._scale(options))
+
+    def compute_error_frozen(self, source, target, pose, options: ExecutionOptions | None = None):
+        """Registration::compute_error_frozen (registration.hpp:350-359)."""
+        return self._error(source, target, self._neighbors, pose, self._scale(options))
+
+    def compute_icp_robust_weights(self, source, target, target_knn: KNNBase, pose, robust_scale: float) -> np.ndarray:
+        """Registration::compute_icp_robust_weights (registration.hpp:279-294)."""
+        n = source.size()
+        if n == 0:
+            return np.zeros(0, np.float32)
+        target_knn.nearest_neighbor_search_async(source, self._neighbors, None, pose)
+        w = DeviceArray(self.queue, (n,), np.float32)
+        mc = np.float32(self.params.max_correspondence_distance)
+        t16 = _T16(pose)
+        check(_lib.lib().spx_robust_weights(
+            self.queue.handle, int(self.params.reg_type), self._loss(), source.points.ptr,
+            _ptr(source.covs) if source.has_cov() else None, n, target.points.ptr,
+            _ptr(target.covs) if target.has_cov() else None, _ptr(target.normals) if target.has_normal() else None,
+            self._neighbors.indices.ptr, self._neighbors.distances.ptr, _hostf(t16), float(mc * mc),
+            float(robust_scale), w.ptr))
+        return w.download()
+
+    def _align_injected_knn(self, source, target, knn: KNNBase, T0, options, trace) -> RegistrationResult:
+        """The reference loop (registration.hpp:227-272, 803-964) with a user KNNBase: correspondences
+        come from the injected object, linearise / error run on the GPU, the 6x6 step on the host."""
+        P = self.params
+        res = RegistrationResult(T=T0.copy())
+        scale = self._scale(options)
+        lam = P.lm.init_lambda
+        radius = P.dogleg.initial_trust_region_radius
+        conv = lambda d: (np.linalg.norm(d[:3]) < P.criteria.rotation and  # noqa: E731
+                          np.linalg.norm(d[3:]) < P.criteria.translation)
+        clampr = lambda r: min(max(r, P.dogleg.min_trust_region_radius), P.dogleg.max_trust_region_radius)  # noqa
+        poses = []
+        for it in range(P.max_iterations):
+            knn.nearest_neighbor_search_async(source, self._neighbors, None, res.T)
+            lin = self._linearize(source, target, self._neighbors, res.T, scale)
+            res.H_raw, res.b_raw, res.error_raw = lin.H, lin.b, lin.error
+            if P.optimization_method == OptimizationMethod.GAUSS_NEWTON:
+                ok, d = solve_6x6(lin.H, lin.b, P.gn.lambda_)
+                res.converged = bool(ok and conv(d))
+                res.T = (res.T @ se3_exp(d)).astype(np.float32)
+                res.iterations, res.H, res.b, res.error, res.inlier = it, lin.H, lin.b, lin.error, lin.inlier
+            elif P.optimization_method == OptimizationMethod.LEVENBERG_MARQUARDT:
+                last = FLT_MAX
+                for _ in range(P.lm.max_inner_iterations):
+                    ok, d = solve_6x6(lin.H, lin.b, lam)
+                    res.converged = bool(ok and conv(d))
+                    Tn = (res.T @ se3_exp(d)).astype(np.float32)
+                    ne, ni = self._error(source, target, self._neighbors, Tn, scale)
+                    if ne <= lin.error:
+                        res.converged, res.T, res.error, res.inlier = bool(conv(d)), Tn, ne, ni
+                        lam = min(max(lam / P.lm.lambda_factor, P.lm.min_lambda), P.lm.max_lambda)
+                        break
+                    elif abs(ne - last) <= 1e-6:
+                        res.converged, res.T, res.error, res.inlier = bool(conv(d)), Tn, ne, ni
+                        break
+                    else:
+                        lam = min(max(lam * P.lm.lambda_factor, P.lm.min_lambda), P.lm.max_lambda)
+                    last = ne
+                res.iterations, res.H, res.b = it, lin.H, lin.b
+            else:
+                res.H, res.b, res.error, res.inlier, res.iterations = lin.H, lin.b, lin.error, lin.inlier, it
+                radius = clampr(radius)
+                p, step_norm, pred = dogleg_step(lin.H, lin.b, radius)
+                if pred <= 0.0:
+                    radius = clampr(radius * P.dogleg.gamma_decrease)
+                else:
+                    Tn = (res.T @ se3_exp(p)).astype(np.float32)
+                    ne, ni = self._error(source, target, self._neighbors, Tn, scale)
+                    rho = (lin.error - ne) / pred
+                    if rho < P.dogleg.eta1:
+                        radius = clampr(radius * P.dogleg.gamma_decrease)
+                    else:
+                        res.converged, res.T, res.error, res.inlier = bool(conv(p)), Tn, ne, ni
+                        if rho > P.dogleg.eta2 and step_norm >= radius * 0.99:
+                            radius = clampr(radius * P.dogleg.gamma_increase)
+            poses.append(res.T.copy())
+            if res.converged:
+                break
+        if trace:
+            while len(poses) < max(P.max_iterations, 1):
+                poses.append(poses[-1] if poses else res.T.copy())
+            res.trace = np.stack(poses)
+        return res
+
+
+# ------------------------------------------------------------------ pipeline wrappers
+@dataclass
+class RandomSamplingParams:  # registration_pipeline_params.hpp:11-16
+    enable: bool = True
+    num: int = 1000
+    use_intensities: bool = False
+    weighted_ratio: float = 0.8
+
+
+@dataclass
+class RobustScheduleParams:  # registration_pipeline_params.hpp:18-25
+    auto_scale: bool = False
+    init_scale: float = 10.0
+    min_scale: float = 0.5
+    rotation_init_scale: float = 10.0
+    rotation_min_scale: float = 0.5
+    auto_scaling_iter: int = 4
+
+
+@dataclass
+class RegistrationPipelineParams:  # registration_pipeline_params.hpp:32-41
+    registration: RegistrationParams = field(default_factory=RegistrationParams)
+    random_sampling: RandomSamplingParams = field(default_factory=RandomSamplingParams)
+    robust: RobustScheduleParams = field(default_factory=RobustScheduleParams)
+
+
+def robust_scale_schedule(init_scale: float, min_scale: float, levels: int) -> list[float]:
+    """pipeline/robust.hpp:84-87,106-110: s_{l+1} = s_l * (min/init)^(1/(L-1)), in fp32 like the reference."""
+    f = np.float32(1.0)
+    if levels > 1:
+        f = np.float32(np.power(np.float32(min_scale) / np.float32(init_scale),
+                                np.float32(1.0) / np.float32(levels - 1), dtype=np.float32))
+    out, s = [], np.float32(init_scale)
+    for _ in range(levels):
+        out.append(float(s))
+        s = np.float32(s * f)
+    return out
+
+
+class RegistrationPipeline:
+    """registration::RegistrationPipeline (registration_pipeline.hpp:17-151) with the robust-scale
+    annealing wrapper (pipeline/robust.hpp:42-114).  `aligner` may be any callable with the
+    RegistrationAligner signature (pipeline/aligner.hpp:13-15) — the reference's tests pass lambdas.
+    Random sampling (default on in the reference, registration_pipeline.hpp:127-140) needs the
+    libstdc++ mt19937 stream and is a "next" row; enable=True raises until built."""
+
+    def __init__(self, queue_or_aligner, pipeline_params: RegistrationPipelineParams | None = None):
+        self.pipeline_params = pipeline_params if pipeline_params is not None else RegistrationPipelineParams()
+        if callable(queue_or_aligner):
+            self.registration = None
+            self._aligner = queue_or_aligner
+        else:
+            self.registration = Registration(queue_or_aligner, self.pipeline_params.registration)
+            self._aligner = self.registration.align
+        self._input = None
+
+    def get_registration_input_point_cloud(self):
+        return self._input
+
+    def align(self, source, target, target_knn, initial_guess=None, options: ExecutionOptions | None = None):
+        rs = self.pipeline_params.random_sampling
+        if rs.enable and source.size() > rs.num:
+            raise SpxError(-3, "[RegistrationPipeline::align] random_sampling is not built yet (SURVEY §8(f) rank 1); "
+                               "set random_sampling.enable = False")
+        self._input = source
+        options = options if options is not None else ExecutionOptions()
+        T0 = np.eye(4, dtype=np.float32) if initial_guess is None else np.asarray(initial_guess, np.float32)
+        if not self.pipeline_params.robust.auto_scale:  # registration_pipeline.hpp:118-121
+            return self._aligner(source, target, target_knn, T0, options)
+        return self._robust_align(source, target, target_knn, T0, options)
+
+    def _robust_align(self, source, target, target_knn, T0, options):
+        # pipeline/robust.hpp:42-114
+        pp = self.pipeline_params.robust
+        reg = self.pipeline_params.registration
+        result = RegistrationResult(T=T0.copy())
+        if source.size() == 0:
+            return result
+        fixed = options.robust_scale > 0.0 or options.rotation_robust_scale > 0.0
+        auto = (not fixed) and reg.robust.type != RobustLossType.NONE and pp.auto_scale
+        if auto and (pp.min_scale <= 0.0 or pp.min_scale >= pp.init_scale):
+            print("[Caution] `pipeline.robust.min_scale` must be greater than zero and less than "
+                  "`pipeline.robust.init_scale`.")
+            auto = False
+        if auto and pp.auto_scaling_iter == 0:
+            print("[Caution] `pipeline.robust.auto_scaling_iter` must be greater than zero. Disable auto scaling.")
+            auto = False
+        levels = max(1, pp.auto_scaling_iter) if auto else 1
+        if options.robust_scale > 0.0:
+            scales = [options.robust_scale] * levels
+        elif auto:
+            scales = robust_scale_schedule(pp.init_scale, pp.min_scale, levels)
+        else:
+            scales = [reg.robust.default_scale]
+        rot = robust_scale_schedule(pp.rotation_init_scale, pp.rotation_min_scale, levels) if auto else \
+            [options.rotation_robust_scale if options.rotation_robust_scale > 0 else 10.0] * levels
+        for lvl in range(levels):
+            o = ExecutionOptions(robust_scale=scales[lvl], rotation_robust_scale=rot[lvl], dt=options.dt,
+                                 prev_pose=options.prev_pose)
+            result = self._aligner(source, target, target_knn, result.T, o)
+        return result

@@ -1,0 +1,173 @@
+// Shared internals of libspx: error plumbing, the queue (one in-order CUDA stream + a scratch
+// arena), launch accounting and the exact-arithmetic device helpers every kernel uses.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cfloat>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/spx.h"
+
+namespace spx {
+
+// ------------------------------------------------------------------ errors
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define SPX_CUDA(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            throw ::spx::Error(SPX_ERR_CUDA, std::string("[CUDA] ") + cudaGetErrorString(_e) + " at " +     \
+                                                 __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")"); \
+    } while (0)
+
+#define SPX_REQUIRE(cond, msg)                                              \
+    do {                                                                    \
+        if (!(cond)) throw ::spx::Error(SPX_ERR_INVALID_ARGUMENT, (msg));   \
+    } while (0)
+
+// Every extern "C" entry point is `return guard([&]{ ... });`
+template <typename F>
+inline int guard(F&& f) {
+    try {
+        f();
+        return SPX_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return SPX_ERR_INTERNAL;
+    } catch (...) {
+        set_last_error("unknown exception");
+        return SPX_ERR_INTERNAL;
+    }
+}
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Checks the launch itself (configuration errors); execution errors surface at the next sync.
+#define SPX_LAUNCH_CHECK()            \
+    do {                              \
+        ::spx::count_launch();        \
+        SPX_CUDA(cudaGetLastError()); \
+    } while (0)
+
+}  // namespace spx
+
+// ------------------------------------------------------------------ queue
+struct spx_queue_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = true;
+    int sm_count = 148;
+    // scratch arena: grows monotonically, bump-allocated per API call (no cudaMalloc on the hot path)
+    char* arena = nullptr;
+    size_t arena_cap = 0;
+    size_t arena_off = 0;
+    std::vector<void*> retired;  // old arenas kept alive until the stream is known idle
+    // pinned staging for small host<->device scalars
+    char* pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    void arena_reset() { arena_off = 0; }
+    // Reserve the total a call needs BEFORE taking pointers: growing invalidates nothing in flight
+    // (the old block is retired, not freed) but earlier pointers of this call would go stale.
+    void arena_reserve(size_t bytes);
+    void* arena_take(size_t bytes);
+    template <typename T>
+    T* take(size_t count) {
+        return static_cast<T*>(arena_take(count * sizeof(T)));
+    }
+    void* pinned_get(size_t bytes);
+    void sync();
+};
+
+struct spx_event_s {
+    cudaEvent_t ev = nullptr;
+};
+
+namespace spx {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        SPX_CUDA(cudaGetDevice(&prev));
+        if (prev != dev) SPX_CUDA(cudaSetDevice(dev));
+        cur = dev;
+    }
+    ~DeviceGuard() {
+        if (prev != cur) cudaSetDevice(prev);
+    }
+    int cur = 0;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int div_up(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+// 4x4 transform passed to kernels by value, row-major rows as float4 (the reference hands its
+// kernels std::array<sycl::float4,4> rows: eigen_utils.hpp:701-708)
+struct Xform {
+    float4 r0, r1, r2, r3;
+};
+inline Xform xform_from_colmajor(const float* T) {
+    Xform x;
+    x.r0 = make_float4(T[0], T[4], T[8], T[12]);
+    x.r1 = make_float4(T[1], T[5], T[9], T[13]);
+    x.r2 = make_float4(T[2], T[6], T[10], T[14]);
+    x.r3 = make_float4(T[3], T[7], T[11], T[15]);
+    return x;
+}
+inline Xform xform_identity() {
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    return xform_from_colmajor(I);
+}
+
+#ifdef __CUDACC__
+// transform_point: row i = fma(T(i,3),p3, fma(T(i,2),p2, fma(T(i,1),p1, fma(T(i,0),p0, 0))))
+// (I/algorithms/common/transform.hpp:32-37 via eigen_utils.hpp:113-127).  __fmaf_rn/__fmul_rn are
+// never re-associated or contracted by nvcc, so the result is bit-identical to the fma chain.
+__device__ __forceinline__ float row_dot(const float4 r, const float4 p) {
+    return __fmaf_rn(r.w, p.w, __fmaf_rn(r.z, p.z, __fmaf_rn(r.y, p.y, __fmul_rn(r.x, p.x))));
+}
+__device__ __forceinline__ float4 transform_point(const Xform& T, const float4 p) {
+    return make_float4(row_dot(T.r0, p), row_dot(T.r1, p), row_dot(T.r2, p), row_dot(T.r3, p));
+}
+// squared distance exactly as kdtree.hpp:509-511 evaluates dot<4>(q-p, q-p) with w-difference 0:
+// fma(dz,dz,fma(dy,dy,dx*dx)).  (The 4th term fma(0,0,s) == s.)
+__device__ __forceinline__ float dist_sq(const float qx, const float qy, const float qz, const float px,
+                                         const float py, const float pz) {
+    const float dx = __fsub_rn(qx, px);
+    const float dy = __fsub_rn(qy, py);
+    const float dz = __fsub_rn(qz, pz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+// (dist, idx) lexicographic "a before b"; idx < 0 marks an empty slot (always last)
+__device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) {
+    return da < db || (da == db && (ib < 0 || ia < ib));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+}  // namespace spx

@@ -1,0 +1,1257 @@
+// Registration hot loop on the device: nearest neighbour -> per-point factor -> robust weight ->
+// block reduction to the 21 unique H terms, 6 b terms, error and inlier count -> 6x6 solve and
+// pose update.  Reference: I/algorithms/registration/registration.hpp:201-276 (align loop),
+// :513-676 (linearise + sycl::reduction), :678-789 (error pass), :803-964 (GN / LM / dog-leg),
+// factors I/algorithms/registration/factor.hpp:63-278, robust kernels I/algorithms/robust/robust.hpp.
+//
+// What is different from the reference by design (results stay within the stated tolerances):
+//  * GICP's plane regularisation of both covariances (2 eigen-decompositions per point per
+//    iteration inside linearize_gicp, factor.hpp:250-255) is pose-independent, so align() hoists
+//    it into one pass per cloud and the iteration kernel reads 6 floats per covariance.
+//  * H is symmetric: 21 terms are reduced instead of 36 (registration.hpp:565-571 sums all 36).
+//  * sums: fp32 per thread, fp32 warp shuffles, fp64 from the block level up, folded in a fixed
+//    order by the last block to finish -> deterministic, and closer to the exact sum than any
+//    fp32 sycl::reduction order.
+//  * Gauss-Newton never returns to the host inside the loop: the last block also solves the 6x6
+//    system (fp64 LDL^T) and advances the pose that the next launch reads.
+#include <cmath>
+#include <cstring>
+
+#include "spx_grid.cuh"
+#include "spx_math.cuh"
+
+using namespace spx;
+
+namespace {
+
+constexpr int LIN_THREADS = 256;
+constexpr int LIN_WARPS = LIN_THREADS / 32;
+constexpr int N_H = 21;
+constexpr int S_B = 21, S_ERR = 27, S_INL = 28;
+constexpr int N_ACC = 28;  // float accumulators per thread (21 H + 6 b + error)
+
+// device-resident optimiser state (one per spx_registration)
+struct RegState {
+    float T[4][4];  // row-major current pose
+    int iterations;
+    int converged;
+    int stop;  // set once converged: later launches of the same align() return immediately
+    int solve_ok;
+    float H[36];
+    float b[6];
+    float error;
+    uint32_t inlier;
+    float delta[6];
+    float pad[2];
+};
+
+struct LinArgs {
+    // source
+    const float4* src_pts;
+    const float4* src_c0;  // regularised covariance xx xy xz yy
+    const float2* src_c1;  //                        yz zz
+    const float* src_cov16;  // raw reference layout (generic entry points)
+    uint32_t ns;
+    // target (original index order)
+    const float4* tgt_pts;
+    const float4* tgt_c0;
+    const float2* tgt_c1;
+    const float* tgt_cov16;
+    const float4* tgt_normals;
+    // correspondences
+    const int32_t* idx_in;
+    const float* dist_in;
+    int32_t* idx_out;
+    float* dist_out;
+    GridView grid;
+    // pose
+    RegState* state;
+    Xform T;
+    int use_state;
+    // gating / robust kernel
+    float max_corr;
+    float max_corr_sq;
+    float scale;
+    int loss;
+    // reduction
+    double* partials;  // [gridDim.x][32]
+    unsigned int* ticket;
+    double* sums_out;  // [32]
+    // fused Gauss-Newton step
+    float lambda, crit_rot, crit_trans;
+    int iter_index;
+    float* trace;  // [max_iterations][16] column-major poses, nullable
+    float* weights_out;  // compute_icp_robust_weights
+};
+
+// ------------------------------------------------------------------ robust kernels (robust.hpp:56-114)
+__device__ __forceinline__ float robust_weight(int loss, float r, float s) {
+    if (loss == SPX_LOSS_NONE) return 1.0f;
+    if (r <= 1e-8f) return 1.0f;
+    const float x = __fdiv_rn(r, s);
+    switch (loss) {
+        case SPX_LOSS_HUBER: return fminf(1.0f, __fdiv_rn(1.0f, x));
+        case SPX_LOSS_TUKEY: {
+            if (x >= 1.0f) return 0.0f;
+            const float f = __fsub_rn(1.0f, __fmul_rn(x, x));
+            return __fmul_rn(f, f);
+        }
+        case SPX_LOSS_CAUCHY: return __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(x, x)));
+        default: {
+            const float d = __fadd_rn(1.0f, __fmul_rn(x, x));
+            return __fdiv_rn(1.0f, __fmul_rn(d, d));
+        }
+    }
+}
+
+__device__ __forceinline__ float robust_error(int loss, float r, float s) {
+    const float r2 = __fmul_rn(r, r), s2 = __fmul_rn(s, s);
+    switch (loss) {
+        case SPX_LOSS_HUBER:
+            return r <= s ? __fmul_rn(__fmul_rn(0.5f, r), r) : __fmul_rn(s, __fsub_rn(r, __fmul_rn(0.5f, s)));
+        case SPX_LOSS_TUKEY:
+            return r <= s ? __fmul_rn(__fdiv_rn(s2, 6.0f), __fsub_rn(1.0f, powf(__fsub_rn(1.0f, __fdiv_rn(r2, s2)), 3.0f)))
+                          : __fdiv_rn(s2, 6.0f);
+        case SPX_LOSS_CAUCHY:
+            return __fmul_rn(__fmul_rn(__fmul_rn(0.5f, s), s), logf(__fadd_rn(1.0f, __fdiv_rn(r2, s2))));
+        case SPX_LOSS_GEMAN_MCCLURE:
+            return __fdiv_rn(__fmul_rn(0.5f, __fmul_rn(__fmul_rn(s2, r), r)), __fadd_rn(s2, r2));
+        default: return __fmul_rn(__fmul_rn(0.5f, r), r);
+    }
+}
+
+// ------------------------------------------------------------------ factors
+struct Jac {
+    float j[3][6];  // rows 0..2 of the 4x6 SE(3) Jacobian [R skew(p) | -R]; row 3 is zero
+};
+
+// compute_se3_jacobian — factor.hpp:69-84; the zero terms of skew() drop out of the fma chains
+__device__ __forceinline__ Jac se3_jacobian(const Xform& T, const float4 p) {
+    Jac J;
+    const float R[3][3] = {{T.r0.x, T.r0.y, T.r0.z}, {T.r1.x, T.r1.y, T.r1.z}, {T.r2.x, T.r2.y, T.r2.z}};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        J.j[i][0] = __fmaf_rn(R[i][2], -p.y, __fmul_rn(R[i][1], p.z));
+        J.j[i][1] = __fmaf_rn(R[i][2], p.x, __fmul_rn(R[i][0], -p.z));
+        J.j[i][2] = __fmaf_rn(R[i][1], -p.x, __fmul_rn(R[i][0], p.y));
+        J.j[i][3] = -R[i][0];
+        J.j[i][4] = -R[i][1];
+        J.j[i][5] = -R[i][2];
+    }
+    return J;
+}
+
+__device__ __forceinline__ float chain3(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+}
+
+__device__ __forceinline__ float sym_at(const Sym3& s, int i, int j) {
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    return a == 0 ? (b == 0 ? s.xx : (b == 1 ? s.xy : s.xz)) : (a == 1 ? (b == 1 ? s.yy : s.yz) : s.zz);
+}
+
+// compute_mahalanobis_covariance + inverse — factor.hpp:111-123, transform.hpp:14-22,
+// covariance.hpp:136-141, eigen_utils.hpp:403-423; cs / ct already plane-regularised
+__device__ __forceinline__ Sym3 gicp_minv(const Xform& T, const Sym3& cs, const Sym3& ct) {
+    const float R[3][3] = {{T.r0.x, T.r0.y, T.r0.z}, {T.r1.x, T.r1.y, T.r1.z}, {T.r2.x, T.r2.y, T.r2.z}};
+    float X[3][3];  // C R^T
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            X[k][j] = chain3(sym_at(cs, k, 0), R[j][0], sym_at(cs, k, 1), R[j][1], sym_at(cs, k, 2), R[j][2]);
+    auto rcr = [&](int i, int j) { return chain3(R[i][0], X[0][j], R[i][1], X[1][j], R[i][2], X[2][j]); };
+    Sym3 M;
+    M.xx = __fadd_rn(rcr(0, 0), ct.xx);
+    M.xy = __fadd_rn(rcr(0, 1), ct.xy);
+    M.xz = __fadd_rn(rcr(0, 2), ct.xz);
+    M.yy = __fadd_rn(rcr(1, 1), ct.yy);
+    M.yz = __fadd_rn(rcr(1, 2), ct.yz);
+    M.zz = __fadd_rn(rcr(2, 2), ct.zz);
+    return sym_inverse(M);
+}
+
+struct Terms {
+    float H[N_H];
+    float b[6];
+    float e2;
+    float rn;
+};
+
+template <int REG>
+__device__ __forceinline__ void point_terms(const Xform& T, const float4 ps, const Sym3& cs, const float4 pt,
+                                            const Sym3& ct, const float4 nrm, Terms& o) {
+    const float4 tp = transform_point(T, ps);
+    const float r0 = __fsub_rn(pt.x, tp.x), r1 = __fsub_rn(pt.y, tp.y), r2 = __fsub_rn(pt.z, tp.z);
+    const Jac J = se3_jacobian(T, ps);
+    if (REG == SPX_REG_POINT_TO_POINT) {  // factor.hpp:130-149
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+            for (int c = a; c < 6; ++c) o.H[t++] = chain3(J.j[0][a], J.j[0][c], J.j[1][a], J.j[1][c], J.j[2][a], J.j[2][c]);
+            o.b[a] = chain3(J.j[0][a], r0, J.j[1][a], r1, J.j[2][a], r2);
+        }
+        o.e2 = chain3(r0, r0, r1, r1, r2, r2);
+        o.rn = __fsqrt_rn(o.e2);
+    } else if (REG == SPX_REG_POINT_TO_PLANE) {  // factor.hpp:172-210
+        const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
+        const float n[3] = {nrm.x, nrm.y, nrm.z};
+        float row[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) row[c] = chain3(n[0], J.j[0][c], n[1], J.j[1][c], n[2], J.j[2][c]);
+        float Jp[3][6], pe[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            pe[i] = __fmul_rn(n[i], d);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) Jp[i][c] = __fmul_rn(n[i], row[c]);
+        }
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+            for (int c = a; c < 6; ++c) o.H[t++] = chain3(Jp[0][a], Jp[0][c], Jp[1][a], Jp[1][c], Jp[2][a], Jp[2][c]);
+            o.b[a] = chain3(Jp[0][a], pe[0], Jp[1][a], pe[1], Jp[2][a], pe[2]);
+        }
+        o.e2 = __fmul_rn(d, d);
+        o.rn = fabsf(d);
+    } else {  // GICP, factor.hpp:239-278
+        const Sym3 Mi = gicp_minv(T, cs, ct);
+        float JTM[6][3];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                JTM[a][j] = chain3(J.j[0][a], sym_at(Mi, 0, j), J.j[1][a], sym_at(Mi, 1, j), J.j[2][a], sym_at(Mi, 2, j));
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+            for (int c = a; c < 6; ++c) o.H[t++] = chain3(JTM[a][0], J.j[0][c], JTM[a][1], J.j[1][c], JTM[a][2], J.j[2][c]);
+            o.b[a] = chain3(JTM[a][0], r0, JTM[a][1], r1, JTM[a][2], r2);
+        }
+        const float m0 = chain3(Mi.xx, r0, Mi.xy, r1, Mi.xz, r2);
+        const float m1 = chain3(Mi.xy, r0, Mi.yy, r1, Mi.yz, r2);
+        const float m2 = chain3(Mi.xz, r0, Mi.yz, r1, Mi.zz, r2);
+        o.e2 = chain3(r0, m0, r1, m1, r2, m2);
+        o.rn = __fsqrt_rn(o.e2);
+    }
+}
+
+template <int REG>
+__device__ __forceinline__ float point_error(const Xform& T, const float4 ps, const Sym3& cs, const float4 pt,
+                                             const Sym3& ct, const float4 nrm) {
+    const float4 tp = transform_point(T, ps);
+    const float r0 = __fsub_rn(pt.x, tp.x), r1 = __fsub_rn(pt.y, tp.y), r2 = __fsub_rn(pt.z, tp.z);
+    if (REG == SPX_REG_POINT_TO_POINT) return chain3(r0, r0, r1, r1, r2, r2);  // factor.hpp:156-164
+    if (REG == SPX_REG_POINT_TO_PLANE) {                                       // factor.hpp:218-230
+        const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
+        return __fmul_rn(d, d);
+    }
+    const Sym3 Mi = gicp_minv(T, cs, ct);  // factor.hpp:287-306
+    const float m0 = chain3(Mi.xx, r0, Mi.xy, r1, Mi.xz, r2);
+    const float m1 = chain3(Mi.xy, r0, Mi.yy, r1, Mi.yz, r2);
+    const float m2 = chain3(Mi.xz, r0, Mi.yz, r1, Mi.zz, r2);
+    return chain3(r0, m0, r1, m1, r2, m2);
+}
+
+__device__ __forceinline__ Sym3 identity_sym() {
+    Sym3 s;
+    s.xx = s.yy = s.zz = 1.0f;
+    s.xy = s.xz = s.yz = 0.0f;
+    return s;
+}
+__device__ __forceinline__ Sym3 load_sym(const float4* c0, const float2* c1, size_t i) {
+    const float4 a = __ldg(c0 + i);
+    const float2 b = __ldg(c1 + i);
+    Sym3 s;
+    s.xx = a.x; s.xy = a.y; s.xz = a.z; s.yy = a.w; s.yz = b.x; s.zz = b.y;
+    return s;
+}
+
+// covariances for one correspondence.  Prepared (6-float, already regularised) arrays win; raw
+// 16-float reference covariances are regularised on the fly (what the reference does every
+// iteration); missing covariances are identity (registration.hpp:589-590) — and identity goes
+// through update_covariance_plane like any other matrix.
+template <int REG>
+__device__ __forceinline__ void load_covs(const LinArgs& a, uint32_t i, int ti, Sym3& cs, Sym3& ct) {
+    if (REG != SPX_REG_GICP) return;
+    if (a.src_c0) cs = load_sym(a.src_c0, a.src_c1, i);
+    else cs = plane_regularize(a.src_cov16 ? load_cov16(a.src_cov16 + (size_t)i * 16) : identity_sym());
+    if (a.tgt_c0) ct = load_sym(a.tgt_c0, a.tgt_c1, (size_t)ti);
+    else ct = plane_regularize(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : identity_sym());
+}
+
+__device__ __forceinline__ Xform state_xform(const RegState* s) {
+    Xform T;
+    T.r0 = make_float4(s->T[0][0], s->T[0][1], s->T[0][2], s->T[0][3]);
+    T.r1 = make_float4(s->T[1][0], s->T[1][1], s->T[1][2], s->T[1][3]);
+    T.r2 = make_float4(s->T[2][0], s->T[2][1], s->T[2][2], s->T[2][3]);
+    T.r3 = make_float4(s->T[3][0], s->T[3][1], s->T[3][2], s->T[3][3]);
+    return T;
+}
+
+// Gauss-Newton step on the reduced sums — registration.hpp:803-828 (+ :407-410, :791-801)
+__device__ void gn_update(RegState* st, const double* sums, float lambda, float crit_rot, float crit_trans,
+                          int iter_index, float* trace) {
+    float H[36], b[6];
+    int t = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int c = a; c < 6; ++c) {
+            const float v = (float)sums[t++];
+            H[a * 6 + c] = v;
+            H[c * 6 + a] = v;
+        }
+    for (int a = 0; a < 6; ++a) b[a] = (float)sums[S_B + a];
+    float delta[6];
+    const bool ok = solve_damped6(H, b, lambda, delta);
+    const bool conv = ok && norm3f(delta) < crit_rot && norm3f(delta + 3) < crit_trans;
+    float E[4][4], Tn[4][4];
+    se3_exp_rm(delta, E);
+    isometry_mul_rm(st->T, E, Tn);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) st->T[i][j] = Tn[i][j];
+    st->iterations = iter_index;
+    st->converged = conv ? 1 : 0;
+    st->stop = conv ? 1 : 0;
+    st->solve_ok = ok ? 1 : 0;
+    for (int i = 0; i < 36; ++i) st->H[i] = H[i];
+    for (int i = 0; i < 6; ++i) {
+        st->b[i] = b[i];
+        st->delta[i] = delta[i];
+    }
+    st->error = (float)sums[S_ERR];
+    st->inlier = (uint32_t)(sums[S_INL] + 0.5);
+    if (trace)
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) trace[(size_t)iter_index * 16 + j * 4 + i] = Tn[i][j];
+}
+
+// block reduction of `nv` (<= 29) per-thread values -> partials -> ordered fold by the last block.
+// Returns true in the last block, with the folded sums in `fold` (shared memory, 32 doubles).
+__device__ bool reduce_to_sums(const float* acc, int nacc, uint32_t inl, double* partials, unsigned int* ticket,
+                               double* sums_out, double (*fold)[32], float (*red)[32]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int v = 0; v < nacc; ++v) {
+        const float s = warp_sum(acc[v]);
+        if (lane == 0) red[warp][v] = s;
+    }
+    {
+        uint32_t c = inl;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) red[warp][31] = __uint_as_float(c);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        if ((int)threadIdx.x < nacc) {
+            for (int w = 0; w < LIN_WARPS; ++w) s += (double)red[w][threadIdx.x];
+        } else if (threadIdx.x == S_INL) {
+            for (int w = 0; w < LIN_WARPS; ++w) s += (double)__float_as_uint(red[w][31]);
+        }
+        // error-only passes keep the layout: error at S_ERR, inliers at S_INL
+        int slot = threadIdx.x;
+        if (nacc == 1 && threadIdx.x == 0) slot = S_ERR;
+        if (nacc == 1 && threadIdx.x == S_ERR) slot = 0;
+        __stcg(partials + (size_t)blockIdx.x * 32 + slot, s);
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    {
+        const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
+        double s = 0.0;
+        for (unsigned b = slice; b < gridDim.x; b += LIN_WARPS) s += __ldcg(partials + (size_t)b * 32 + v);
+        fold[slice][v] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int w = 0; w < LIN_WARPS; ++w) s += fold[w][threadIdx.x];
+        fold[0][threadIdx.x] = s;
+        if (sums_out) sums_out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch on this stream
+    __syncthreads();
+    return true;
+}
+
+// MODE 0: linearise from given correspondences.  MODE 1: nearest neighbour through the grid index
+// fused in front (writes idx/dist for the frozen-neighbour error passes).  SOLVE: the last block
+// also performs the Gauss-Newton update of the device-resident pose.
+template <int REG, int MODE, bool SOLVE>
+__global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs a) {
+    __shared__ double fold[LIN_WARPS][32];
+    __shared__ float red[LIN_WARPS][32];
+    Xform T = a.T;
+    if (a.use_state) {
+        if (a.state->stop) return;  // converged earlier in this align(): nothing left to do
+        T = state_xform(a.state);
+    }
+    float acc[N_ACC];
+#pragma unroll
+    for (int v = 0; v < N_ACC; ++v) acc[v] = 0.0f;
+    uint32_t inl = 0;
+
+    for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
+        const float4 ps = __ldg(a.src_pts + i);
+        float d;
+        int ti;
+        if (MODE == 1) {
+            const float4 q = transform_point(T, ps);
+            Best1 best;
+            best.init();
+            if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && a.grid.n > 0)
+                grid_search(a.grid, q.x, q.y, q.z, best, a.max_corr, 1 << 20);
+            d = best.d;
+            ti = best.i;
+            a.idx_out[i] = ti;
+            a.dist_out[i] = d;
+        } else {
+            d = __ldg(a.dist_in + i);
+            ti = __ldg(a.idx_in + i);
+        }
+        if (d > a.max_corr_sq || ti < 0) continue;  // registration.hpp:584 (+ guard for the -1 fill)
+        const float4 pt = __ldg(a.tgt_pts + ti);
+        const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        Sym3 cs, ct;
+        load_covs<REG>(a, i, ti, cs, ct);
+        Terms t;
+        point_terms<REG>(T, ps, cs, pt, ct, nrm, t);
+        const float w = robust_weight(a.loss, t.rn, a.scale);
+#pragma unroll
+        for (int v = 0; v < N_H; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(w, t.H[v]));
+#pragma unroll
+        for (int v = 0; v < 6; ++v) acc[S_B + v] = __fadd_rn(acc[S_B + v], __fmul_rn(w, t.b[v]));
+        acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(a.loss, t.rn, a.scale));
+        ++inl;
+    }
+    if (!reduce_to_sums(acc, N_ACC, inl, a.partials, a.ticket, a.sums_out, fold, red)) return;
+    if (SOLVE && threadIdx.x == 0)
+        gn_update(a.state, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, a.iter_index, a.trace);
+}
+
+// error-only pass with frozen neighbours — registration.hpp:678-777; WEIGHTS: per-point robust
+// weights instead of the sum (registration.hpp:412-462)
+template <int REG, bool WEIGHTS>
+__global__ void __launch_bounds__(LIN_THREADS, 2) error_kernel(const LinArgs a) {
+    __shared__ double fold[LIN_WARPS][32];
+    __shared__ float red[LIN_WARPS][32];
+    const Xform T = a.T;
+    float acc[1] = {0.0f};
+    uint32_t inl = 0;
+    for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
+        const float d = __ldg(a.dist_in + i);
+        const int ti = __ldg(a.idx_in + i);
+        float w = 0.0f;
+        if (!(d > a.max_corr_sq || ti < 0)) {
+            const float4 ps = __ldg(a.src_pts + i);
+            const float4 pt = __ldg(a.tgt_pts + ti);
+            const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
+                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            Sym3 cs, ct;
+            load_covs<REG>(a, i, ti, cs, ct);
+            const float rn = __fsqrt_rn(point_error<REG>(T, ps, cs, pt, ct, nrm));
+            if (WEIGHTS) {
+                w = robust_weight(a.loss, rn, a.scale);
+            } else {
+                acc[0] = __fadd_rn(acc[0], robust_error(a.loss, rn, a.scale));
+                ++inl;
+            }
+        }
+        if (WEIGHTS) a.weights_out[i] = w;
+    }
+    if (WEIGHTS) return;
+    reduce_to_sums(acc, 1, inl, a.partials, a.ticket, a.sums_out, fold, red);
+}
+
+// stand-alone update for the sharded path: sums were all-reduced across ranks by the caller
+__global__ void gn_update_kernel(RegState* st, const double* sums, float lambda, float crit_rot, float crit_trans,
+                                 int iter_index, float* trace) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->stop) return;
+    gn_update(st, sums, lambda, crit_rot, crit_trans, iter_index, trace);
+}
+
+// one pass per cloud: 16-float reference covariance -> plane-regularised 6 floats
+__global__ void __launch_bounds__(128) prepare_cov_kernel(const float* __restrict__ cov16, uint32_t n,
+                                                          float4* __restrict__ c0, float2* __restrict__ c1) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const Sym3 r = plane_regularize(cov16 ? load_cov16(cov16 + (size_t)i * 16) : identity_sym());
+    c0[i] = make_float4(r.xx, r.xy, r.xz, r.yy);
+    c1[i] = make_float2(r.yz, r.zz);
+}
+
+template <int MODE, bool SOLVE>
+void launch_linearize(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
+    switch (reg) {
+        case SPX_REG_POINT_TO_POINT:
+            linearize_kernel<SPX_REG_POINT_TO_POINT, MODE, SOLVE><<<blocks, LIN_THREADS, 0, st>>>(a);
+            break;
+        case SPX_REG_POINT_TO_PLANE:
+            linearize_kernel<SPX_REG_POINT_TO_PLANE, MODE, SOLVE><<<blocks, LIN_THREADS, 0, st>>>(a);
+            break;
+        default: linearize_kernel<SPX_REG_GICP, MODE, SOLVE><<<blocks, LIN_THREADS, 0, st>>>(a); break;
+    }
+    SPX_LAUNCH_CHECK();
+}
+
+template <bool WEIGHTS>
+void launch_error(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
+    switch (reg) {
+        case SPX_REG_POINT_TO_POINT: error_kernel<SPX_REG_POINT_TO_POINT, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
+        case SPX_REG_POINT_TO_PLANE: error_kernel<SPX_REG_POINT_TO_PLANE, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
+        default: error_kernel<SPX_REG_GICP, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
+    }
+    SPX_LAUNCH_CHECK();
+}
+
+void check_reg_loss(int reg, int loss, const char* where) {
+    if (reg == SPX_REG_POINT_TO_DISTRIBUTION || reg == SPX_REG_GENZ)
+        throw Error(SPX_ERR_UNSUPPORTED, std::string(where) + " RegType not built yet (POINT_TO_DISTRIBUTION / GENZ)");
+    if (!(reg == SPX_REG_POINT_TO_POINT || reg == SPX_REG_POINT_TO_PLANE || reg == SPX_REG_GICP))
+        throw Error(SPX_ERR_INVALID_ARGUMENT, "[Registration::dispatch] Combination not found in tags!");
+    if (loss < SPX_LOSS_NONE || loss > SPX_LOSS_GEMAN_MCCLURE)
+        throw Error(SPX_ERR_INVALID_ARGUMENT, "[Registration::dispatch] Combination not found in tags!");
+}
+
+unsigned lin_blocks(spx_queue_t q, size_t ns) {
+    const unsigned need = (unsigned)div_up(ns, LIN_THREADS);
+    const unsigned cap = (unsigned)q->sm_count * 4;  // grid-stride beyond 4 CTAs per SM
+    return std::max(1u, std::min(need, cap));
+}
+
+void sums_to_host(const double* s, float* H, float* b, float* err, uint32_t* inl) {
+    int t = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int c = a; c < 6; ++c) {
+            const float v = (float)s[t++];
+            H[a * 6 + c] = v;
+            H[c * 6 + a] = v;
+        }
+    for (int a = 0; a < 6; ++a) b[a] = (float)s[S_B + a];
+    *err = (float)s[S_ERR];
+    *inl = (uint32_t)(s[S_INL] + 0.5);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ handle
+struct spx_registration_s {
+    spx_queue_t q = nullptr;
+    spx_registration_params P{};
+    RegState* state = nullptr;       // device
+    double* partials = nullptr;      // device [max_blocks][32]
+    unsigned max_blocks = 0;
+    unsigned int* ticket = nullptr;  // device
+    double* sums = nullptr;          // device [32]
+    int32_t* nn_idx = nullptr;
+    float* nn_dist = nullptr;
+    size_t nn_cap = 0;
+    float4* src_c0 = nullptr;
+    float2* src_c1 = nullptr;
+    size_t src_cap = 0;
+    float4* tgt_c0 = nullptr;
+    float2* tgt_c1 = nullptr;
+    size_t tgt_cap = 0;
+    float* trace = nullptr;
+    size_t trace_cap = 0;
+    size_t nn_n = 0;
+    // sharded / staged context
+    LinArgs shard{};
+    int shard_reg = 0;
+    int shard_iter = 0;
+    bool shard_active = false;
+};
+
+namespace {
+
+void reg_free(spx_registration_t r) {
+    auto f = [](auto*& p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    };
+    f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist);
+    f(r->src_c0); f(r->src_c1); f(r->tgt_c0); f(r->tgt_c1); f(r->trace);
+}
+
+template <typename T>
+void ensure(T*& p, size_t& cap, size_t need, cudaStream_t st) {
+    if (need <= cap && p) return;
+    if (p) {
+        SPX_CUDA(cudaStreamSynchronize(st));
+        SPX_CUDA(cudaFree(p));
+        p = nullptr;
+    }
+    const size_t c = std::max<size_t>(need, 1024);
+    SPX_CUDA(cudaMalloc(&p, c * sizeof(T)));
+    cap = c;
+}
+
+// reference validate_params — registration.hpp:129-193
+void validate(const spx_registration_params& P, const float* src_covs, const float* tgt_covs,
+              const float* tgt_normals) {
+    if (P.reg_type == SPX_REG_POINT_TO_PLANE && !tgt_normals && !tgt_covs)
+        throw Error(SPX_ERR_INVALID_ARGUMENT,
+                    "[Registration::validate_params] Normal vector or covariance matrices of target must be "
+                    "pre-computed before performing Point-to-Plane ICP matching.");
+    if (P.reg_type == SPX_REG_GICP && (!src_covs || !tgt_covs))
+        throw Error(SPX_ERR_INVALID_ARGUMENT,
+                    "[Registration::validate_params] Covariance matrices of source and target must be pre-computed "
+                    "before performing GICP matching.");
+}
+
+struct AlignCtx {
+    LinArgs a;
+    int reg;
+    unsigned blocks;
+};
+
+// shared set-up of align / shard_begin: scratch, covariance preparation, initial state upload
+AlignCtx align_setup(spx_registration_t r, const float* src_points, const float* src_covs, size_t ns,
+                     const float* tgt_points, const float* tgt_covs, const float* tgt_normals, size_t nt,
+                     spx_index_t index, const float* T_init_host, float robust_scale, float4** derived_normals) {
+    spx_queue_t q = r->q;
+    cudaStream_t st = q->stream;
+    spx_registration_params& P = r->P;
+    SPX_REQUIRE(index, "[Registration::align] target_knn (spx_index) is null");
+    SPX_REQUIRE(index->q->device == q->device, "[Registration::align] index lives on another device");
+    SPX_REQUIRE(index->n_total == nt, "[Registration::align] target_knn was built on a different cloud size");
+    SPX_REQUIRE(ns < (1ull << 31) && nt < (1ull << 31), "[Registration::align] too many points");
+    check_reg_loss(P.reg_type, P.robust_loss, "[Registration::align]");
+    validate(P, src_covs, tgt_covs, tgt_normals);
+    int loss = P.robust_loss;
+    if (loss != SPX_LOSS_NONE && P.robust_default_scale <= 0.0f) loss = SPX_LOSS_NONE;  // registration.hpp:186-192
+
+    size_t cap_dummy = r->nn_cap;
+    ensure(r->nn_idx, cap_dummy, ns, st);
+    ensure(r->nn_dist, r->nn_cap, ns, st);
+    r->nn_n = ns;
+    size_t tcap = r->trace_cap;
+    ensure(r->trace, tcap, (size_t)std::max(P.max_iterations, 1) * 16, st);
+    r->trace_cap = tcap;
+
+    AlignCtx c;
+    c.reg = P.reg_type;
+    c.blocks = lin_blocks(q, ns);
+    if (c.blocks > r->max_blocks) {
+        if (r->partials) {
+            SPX_CUDA(cudaStreamSynchronize(st));
+            SPX_CUDA(cudaFree(r->partials));
+        }
+        r->max_blocks = std::max(c.blocks, (unsigned)q->sm_count * 4);
+        SPX_CUDA(cudaMalloc(&r->partials, (size_t)r->max_blocks * 32 * sizeof(double)));
+    }
+    LinArgs& a = c.a;
+    std::memset(&a, 0, sizeof(a));
+    a.src_pts = reinterpret_cast<const float4*>(src_points);
+    a.ns = (uint32_t)ns;
+    a.tgt_pts = reinterpret_cast<const float4*>(tgt_points);
+    a.tgt_normals = reinterpret_cast<const float4*>(tgt_normals);
+    if (P.reg_type == SPX_REG_GICP) {
+        size_t cap = r->src_cap;
+        ensure(r->src_c0, cap, ns, st);
+        ensure(r->src_c1, r->src_cap, ns, st);
+        cap = r->tgt_cap;
+        ensure(r->tgt_c0, cap, nt, st);
+        ensure(r->tgt_c1, r->tgt_cap, nt, st);
+        if (ns) {
+            prepare_cov_kernel<<<div_up(ns, 128), 128, 0, st>>>(src_covs, (uint32_t)ns, r->src_c0, r->src_c1);
+            SPX_LAUNCH_CHECK();
+        }
+        if (nt) {
+            prepare_cov_kernel<<<div_up(nt, 128), 128, 0, st>>>(tgt_covs, (uint32_t)nt, r->tgt_c0, r->tgt_c1);
+            SPX_LAUNCH_CHECK();
+        }
+        a.src_c0 = r->src_c0; a.src_c1 = r->src_c1;
+        a.tgt_c0 = r->tgt_c0; a.tgt_c1 = r->tgt_c1;
+    }
+    if (P.reg_type == SPX_REG_POINT_TO_PLANE && !tgt_normals) {
+        // registration.hpp:139-141: normals derived from the pre-computed covariances
+        fprintf(stdout, "[Caution] Normal vectors for Point-to-Plane ICP are not provided. \n"
+                        "          Attempting to derive them from pre-computed covariance matrices.\n");
+        float4* nrm = nullptr;
+        SPX_CUDA(cudaMalloc(&nrm, std::max<size_t>(nt, 1) * sizeof(float4)));
+        *derived_normals = nrm;
+        if (spx_normals_from_covs(q, tgt_points, tgt_covs, nt, reinterpret_cast<float*>(nrm)) != SPX_OK)
+            throw Error(SPX_ERR_INTERNAL, spx_last_error());
+        a.tgt_normals = nrm;
+    }
+    a.idx_in = r->nn_idx; a.dist_in = r->nn_dist;
+    a.idx_out = r->nn_idx; a.dist_out = r->nn_dist;
+    a.grid = index->view;
+    a.state = r->state;
+    a.use_state = 1;
+    a.T = xform_identity();
+    a.max_corr = P.max_correspondence_distance;
+    a.max_corr_sq = P.max_correspondence_distance * P.max_correspondence_distance;
+    a.scale = robust_scale > 0.0f ? robust_scale : P.robust_default_scale;  // registration.hpp:217-218
+    a.loss = loss;
+    a.partials = r->partials;
+    a.ticket = r->ticket;
+    a.sums_out = r->sums;
+    a.lambda = P.gn_lambda;
+    a.crit_rot = P.criteria_rotation;
+    a.crit_trans = P.criteria_translation;
+    a.trace = r->trace;
+
+    RegState* hs = static_cast<RegState*>(q->pinned_get(sizeof(RegState) + 64 + 32 * sizeof(double)));
+    std::memset(hs, 0, sizeof(RegState));
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) hs->T[i][j] = T_init_host ? T_init_host[j * 4 + i] : (i == j ? 1.0f : 0.0f);
+    hs->error = FLT_MAX;
+    SPX_CUDA(cudaMemcpyAsync(r->state, hs, sizeof(RegState), cudaMemcpyHostToDevice, st));
+    SPX_CUDA(cudaMemsetAsync(r->ticket, 0, sizeof(unsigned int), st));
+    return c;
+}
+
+void fill_result(const RegState& s, spx_registration_result* R) {
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) R->T[j * 4 + i] = s.T[i][j];
+    R->converged = s.converged;
+    R->iterations = s.iterations;
+    std::memcpy(R->H, s.H, sizeof(R->H));
+    std::memcpy(R->b, s.b, sizeof(R->b));
+    R->error = s.error;
+    std::memcpy(R->H_raw, s.H, sizeof(R->H));
+    std::memcpy(R->b_raw, s.b, sizeof(R->b));
+    R->error_raw = s.error;
+    R->inlier = s.inlier;
+}
+
+void host_T_to_xform(const float T[4][4], Xform& x) {
+    x.r0 = make_float4(T[0][0], T[0][1], T[0][2], T[0][3]);
+    x.r1 = make_float4(T[1][0], T[1][1], T[1][2], T[1][3]);
+    x.r2 = make_float4(T[2][0], T[2][1], T[2][2], T[2][3]);
+    x.r3 = make_float4(T[3][0], T[3][1], T[3][2], T[3][3]);
+}
+
+// dogleg_step.hpp:34-102 on the host (N = 6)
+void dogleg_host(const float* H, const float* g, float radius, float* p, float* step_norm, float* pred) {
+    float p_gn[6] = {0}, n_gn = 0.0f;
+    bool valid_gn = false;
+    {
+        double A[6][6], rhs[6], x[6];
+        for (int i = 0; i < 6; ++i) {
+            for (int j = 0; j < 6; ++j) A[i][j] = (double)H[i * 6 + j];
+            rhs[i] = -(double)g[i];
+        }
+        Ldlt6 f;
+        ldlt6_compute(A, f);
+        double mind = f.D[0];
+        for (int i = 1; i < 6; ++i) mind = std::min(mind, f.D[i]);
+        if (f.ok && mind > 0.0) {
+            ldlt6_solve(f, rhs, x);
+            float s = 0.0f;
+            for (int i = 0; i < 6; ++i) {
+                p_gn[i] = (float)x[i];
+                s += p_gn[i] * p_gn[i];
+            }
+            n_gn = std::sqrt(s);
+            valid_gn = std::isfinite(n_gn);
+        }
+    }
+    float g2 = 0.0f, Hg[6], gHg = 0.0f;
+    for (int i = 0; i < 6; ++i) g2 += g[i] * g[i];
+    for (int i = 0; i < 6; ++i) {
+        float s = 0.0f;
+        for (int j = 0; j < 6; ++j) s += H[i * 6 + j] * g[j];
+        Hg[i] = s;
+    }
+    for (int i = 0; i < 6; ++i) gHg += g[i] * Hg[i];
+    float p_sd[6];
+    for (int i = 0; i < 6; ++i) p_sd[i] = -g[i];
+    if (gHg > FLT_EPSILON) {
+        const float alpha = g2 / gHg;
+        if (std::isfinite(alpha))
+            for (int i = 0; i < 6; ++i) p_sd[i] = -alpha * g[i];
+    }
+    float n_sd2 = 0.0f;
+    for (int i = 0; i < 6; ++i) n_sd2 += p_sd[i] * p_sd[i];
+    const float n_sd = std::sqrt(n_sd2);
+    for (int i = 0; i < 6; ++i) p[i] = 0.0f;
+    if (valid_gn && n_gn <= radius) {
+        std::memcpy(p, p_gn, sizeof(p_gn));
+        *step_norm = n_gn;
+    } else if (n_sd >= radius) {
+        if (n_sd > FLT_EPSILON)
+            for (int i = 0; i < 6; ++i) p[i] = (radius / n_sd) * p_sd[i];
+        *step_norm = radius;
+    } else if (valid_gn) {
+        float diff[6], aq = 0.0f, bq = 0.0f;
+        for (int i = 0; i < 6; ++i) {
+            diff[i] = p_gn[i] - p_sd[i];
+            aq += diff[i] * diff[i];
+            bq += p_sd[i] * diff[i];
+        }
+        bq *= 2.0f;
+        const float cq = n_sd2 - radius * radius;
+        const float disc = std::max(bq * bq - 4.0f * aq * cq, 0.0f);
+        float tau = 0.0f;
+        if (aq > FLT_EPSILON) tau = (-bq + std::sqrt(disc)) / (2.0f * aq);
+        tau = std::min(std::max(tau, 0.0f), 1.0f);
+        float s = 0.0f;
+        for (int i = 0; i < 6; ++i) {
+            p[i] = p_sd[i] + tau * diff[i];
+            s += p[i] * p[i];
+        }
+        *step_norm = std::sqrt(s);
+    } else {
+        std::memcpy(p, p_sd, sizeof(p_sd));
+        if (n_sd > radius && n_sd > FLT_EPSILON) {
+            for (int i = 0; i < 6; ++i) p[i] *= radius / n_sd;
+            *step_norm = radius;
+        } else {
+            *step_norm = n_sd;
+        }
+    }
+    float gp = 0.0f, pHp = 0.0f;
+    for (int i = 0; i < 6; ++i) {
+        gp += g[i] * p[i];
+        float s = 0.0f;
+        for (int j = 0; j < 6; ++j) s += H[i * 6 + j] * p[j];
+        pHp += p[i] * s;
+    }
+    *pred = -(gp + 0.5f * pHp);
+}
+
+// generic (caller-supplied correspondences) argument block for spx_linearize / spx_error / weights
+LinArgs generic_args(spx_queue_t q, int loss, const float* src_points, const float* src_covs, size_t ns,
+                     const float* tgt_points, const float* tgt_covs, const float* tgt_normals, const int32_t* nn_idx,
+                     const float* nn_dist, const float* T_host, float max_corr_sq, float robust_scale, unsigned blocks) {
+    LinArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.src_pts = reinterpret_cast<const float4*>(src_points);
+    a.src_cov16 = src_covs;
+    a.ns = (uint32_t)ns;
+    a.tgt_pts = reinterpret_cast<const float4*>(tgt_points);
+    a.tgt_cov16 = tgt_covs;
+    a.tgt_normals = reinterpret_cast<const float4*>(tgt_normals);
+    a.idx_in = nn_idx;
+    a.dist_in = nn_dist;
+    a.T = T_host ? xform_from_colmajor(T_host) : xform_identity();
+    a.max_corr_sq = max_corr_sq;
+    a.max_corr = std::sqrt(std::max(max_corr_sq, 0.0f));
+    a.scale = robust_scale;
+    a.loss = loss;
+    q->arena_reset();
+    q->arena_reserve((size_t)blocks * 32 * sizeof(double) + 32 * sizeof(double) + 4096);
+    a.partials = q->take<double>((size_t)blocks * 32);
+    a.sums_out = q->take<double>(32);
+    a.ticket = q->take<unsigned int>(16);
+    SPX_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), q->stream));
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+void spx_default_registration_params(spx_registration_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->reg_type = SPX_REG_GICP;
+    p->robust_loss = SPX_LOSS_NONE;
+    p->optimization_method = SPX_OPT_GAUSS_NEWTON;
+    p->max_iterations = 20;
+    p->max_correspondence_distance = 2.0f;
+    p->robust_default_scale = 10.0f;
+    p->criteria_translation = 1e-3f;
+    p->criteria_rotation = 1e-3f;
+    p->gn_lambda = 1.0f;
+    p->lm_max_inner_iterations = 10;
+    p->lm_lambda_factor = 2.0f;
+    p->lm_init_lambda = 1.0f;
+    p->lm_max_lambda = 1e3f;
+    p->lm_min_lambda = 1e-6f;
+    p->dogleg_initial_trust_region_radius = 1.0f;
+    p->dogleg_min_trust_region_radius = 1e-4f;
+    p->dogleg_max_trust_region_radius = 10.0f;
+    p->dogleg_eta1 = 0.25f;
+    p->dogleg_eta2 = 0.75f;
+    p->dogleg_gamma_decrease = 0.25f;
+    p->dogleg_gamma_increase = 2.0f;
+}
+
+int spx_solve_6x6(const float* H_host, const float* b_host, float lambda, float* delta_host, int* success) {
+    return guard([&] {
+        SPX_REQUIRE(H_host && b_host && delta_host, "[spx_solve_6x6] null pointer");
+        const bool ok = solve_damped6(H_host, b_host, lambda, delta_host);
+        if (success) *success = ok ? 1 : 0;
+    });
+}
+
+int spx_se3_exp(const float* twist6_host, float* T_host) {
+    return guard([&] {
+        SPX_REQUIRE(twist6_host && T_host, "[spx_se3_exp] null pointer");
+        float E[4][4];
+        se3_exp_rm(twist6_host, E);
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) T_host[j * 4 + i] = E[i][j];
+    });
+}
+
+int spx_dogleg_step(const float* H_host, const float* g_host, float radius, float* p_host, float* step_norm,
+                    float* predicted_reduction) {
+    return guard([&] {
+        SPX_REQUIRE(H_host && g_host && p_host && step_norm && predicted_reduction, "[spx_dogleg_step] null pointer");
+        dogleg_host(H_host, g_host, radius, p_host, step_norm, predicted_reduction);
+    });
+}
+
+int spx_linearize(spx_queue_t q, int reg_type, int robust_loss, const float* src_points, const float* src_covs,
+                  size_t ns, const float* tgt_points, const float* tgt_covs, const float* tgt_normals,
+                  const int32_t* nn_idx, const float* nn_dist, const float* T_host, float max_corr_sq,
+                  float robust_scale, float* H_host, float* b_host, float* error_host, uint32_t* inlier_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && H_host && b_host && error_host && inlier_host, "[Registration::linearize] null argument");
+        check_reg_loss(reg_type, robust_loss, "[Registration::linearize]");
+        SPX_REQUIRE(ns < (1ull << 31), "[Registration::linearize] too many points");
+        std::memset(H_host, 0, 36 * sizeof(float));
+        std::memset(b_host, 0, 6 * sizeof(float));
+        *error_host = 0.0f;
+        *inlier_host = 0;
+        if (ns == 0) return;
+        SPX_REQUIRE(src_points && tgt_points && nn_idx && nn_dist, "[Registration::linearize] null pointer");
+        DeviceGuard g(q->device);
+        const unsigned blocks = lin_blocks(q, ns);
+        LinArgs a = generic_args(q, robust_loss, src_points, src_covs, ns, tgt_points, tgt_covs, tgt_normals, nn_idx,
+                                 nn_dist, T_host, max_corr_sq, robust_scale, blocks);
+        launch_linearize<0, false>(reg_type, a, blocks, q->stream);
+        double* hs = static_cast<double*>(q->pinned_get(32 * sizeof(double)));
+        SPX_CUDA(cudaMemcpyAsync(hs, a.sums_out, 32 * sizeof(double), cudaMemcpyDeviceToHost, q->stream));
+        q->sync();
+        sums_to_host(hs, H_host, b_host, error_host, inlier_host);
+    });
+}
+
+int spx_error(spx_queue_t q, int reg_type, int robust_loss, const float* src_points, const float* src_covs, size_t ns,
+              const float* tgt_points, const float* tgt_covs, const float* tgt_normals, const int32_t* nn_idx,
+              const float* nn_dist, const float* T_host, float max_corr_sq, float robust_scale, float* error_host,
+              uint32_t* inlier_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && error_host && inlier_host, "[Registration::compute_error] null argument");
+        check_reg_loss(reg_type, robust_loss, "[Registration::compute_error]");
+        SPX_REQUIRE(ns < (1ull << 31), "[Registration::compute_error] too many points");
+        *error_host = 0.0f;
+        *inlier_host = 0;
+        if (ns == 0) return;
+        SPX_REQUIRE(src_points && tgt_points && nn_idx && nn_dist, "[Registration::compute_error] null pointer");
+        DeviceGuard g(q->device);
+        const unsigned blocks = lin_blocks(q, ns);
+        LinArgs a = generic_args(q, robust_loss, src_points, src_covs, ns, tgt_points, tgt_covs, tgt_normals, nn_idx,
+                                 nn_dist, T_host, max_corr_sq, robust_scale, blocks);
+        launch_error<false>(reg_type, a, blocks, q->stream);
+        double* hs = static_cast<double*>(q->pinned_get(32 * sizeof(double)));
+        SPX_CUDA(cudaMemcpyAsync(hs, a.sums_out, 32 * sizeof(double), cudaMemcpyDeviceToHost, q->stream));
+        q->sync();
+        *error_host = (float)hs[S_ERR];
+        *inlier_host = (uint32_t)(hs[S_INL] + 0.5);
+    });
+}
+
+int spx_robust_weights(spx_queue_t q, int reg_type, int robust_loss, const float* src_points, const float* src_covs,
+                       size_t ns, const float* tgt_points, const float* tgt_covs, const float* tgt_normals,
+                       const int32_t* nn_idx, const float* nn_dist, const float* T_host, float max_corr_sq,
+                       float robust_scale, float* weights) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[Registration::compute_icp_robust_weights] null queue");
+        check_reg_loss(reg_type, robust_loss, "[Registration::compute_icp_robust_weights]");
+        SPX_REQUIRE(ns < (1ull << 31), "[Registration::compute_icp_robust_weights] too many points");
+        if (ns == 0) return;
+        SPX_REQUIRE(src_points && tgt_points && nn_idx && nn_dist && weights,
+                    "[Registration::compute_icp_robust_weights] null pointer");
+        DeviceGuard g(q->device);
+        const unsigned blocks = (unsigned)div_up(ns, LIN_THREADS);
+        LinArgs a = generic_args(q, robust_loss, src_points, src_covs, ns, tgt_points, tgt_covs, tgt_normals, nn_idx,
+                                 nn_dist, T_host, max_corr_sq, robust_scale, 1);
+        a.weights_out = weights;
+        launch_error<true>(reg_type, a, blocks, q->stream);
+    });
+}
+
+int spx_registration_create(spx_queue_t q, const spx_registration_params* params, spx_registration_t* out) {
+    return guard([&] {
+        SPX_REQUIRE(q && out, "[Registration::Registration] null argument");
+        DeviceGuard g(q->device);
+        auto* r = new spx_registration_s();
+        r->q = q;
+        if (params) r->P = *params;
+        else spx_default_registration_params(&r->P);
+        try {
+            SPX_CUDA(cudaMalloc(&r->state, sizeof(RegState)));
+            SPX_CUDA(cudaMalloc(&r->ticket, 64));
+            SPX_CUDA(cudaMalloc(&r->sums, 32 * sizeof(double)));
+            SPX_CUDA(cudaMemsetAsync(r->ticket, 0, 64, q->stream));
+            r->max_blocks = (unsigned)q->sm_count * 4;
+            SPX_CUDA(cudaMalloc(&r->partials, (size_t)r->max_blocks * 32 * sizeof(double)));
+        } catch (...) {
+            reg_free(r);
+            delete r;
+            throw;
+        }
+        *out = r;
+    });
+}
+
+int spx_registration_destroy(spx_registration_t reg) {
+    return guard([&] {
+        if (!reg) return;
+        DeviceGuard g(reg->q->device);
+        cudaStreamSynchronize(reg->q->stream);
+        reg_free(reg);
+        delete reg;
+    });
+}
+
+int spx_registration_set_params(spx_registration_t reg, const spx_registration_params* params) {
+    return guard([&] {
+        SPX_REQUIRE(reg && params, "[Registration::set_params] null argument");
+        reg->P = *params;
+    });
+}
+
+int spx_registration_neighbors(spx_registration_t reg, const int32_t** nn_idx, const float** nn_dist, size_t* n) {
+    return guard([&] {
+        SPX_REQUIRE(reg, "[Registration::neighbors] null handle");
+        if (nn_idx) *nn_idx = reg->nn_idx;
+        if (nn_dist) *nn_dist = reg->nn_dist;
+        if (n) *n = reg->nn_n;
+    });
+}
+
+int spx_registration_align(spx_registration_t reg, const float* src_points, const float* src_covs, size_t ns,
+                           const float* tgt_points, const float* tgt_covs, const float* tgt_normals, size_t nt,
+                           spx_index_t target_index, const float* T_init_host, float robust_scale,
+                           spx_registration_result* R, float* T_trace_host) {
+    float4* derived_normals = nullptr;
+    const int rc = guard([&] {
+        SPX_REQUIRE(reg && R, "[Registration::align] null argument");
+        spx_queue_t q = reg->q;
+        DeviceGuard g(q->device);
+        cudaStream_t st = q->stream;
+        const spx_registration_params P = reg->P;
+        // RegistrationResult defaults — result.hpp:16-25
+        std::memset(R, 0, sizeof(*R));
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) R->T[j * 4 + i] = T_init_host ? T_init_host[j * 4 + i] : (i == j ? 1.0f : 0.0f);
+        R->error = FLT_MAX;
+        R->error_raw = FLT_MAX;
+        if (ns == 0) return;  // registration.hpp:209-211
+        SPX_REQUIRE(src_points && (tgt_points || nt == 0), "[Registration::align] null points");
+        AlignCtx c = align_setup(reg, src_points, src_covs, ns, tgt_points, tgt_covs, tgt_normals, nt, target_index,
+                                 T_init_host, robust_scale, &derived_normals);
+        LinArgs& a = c.a;
+        RegState* hs = static_cast<RegState*>(q->pinned_get(sizeof(RegState) + 64 + 32 * sizeof(double)));
+        double* hsums = reinterpret_cast<double*>(reinterpret_cast<char*>(hs) + sizeof(RegState) + 64);
+        const int max_it = P.max_iterations;
+
+        if (P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
+            for (int it = 0; it < max_it; ++it) {
+                a.iter_index = it;
+                launch_linearize<1, true>(c.reg, a, c.blocks, st);
+            }
+            SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, st));
+            q->sync();
+            if (max_it > 0) fill_result(*hs, R);
+            if (T_trace_host && max_it > 0) {
+                // iterations never run (converged earlier) repeat the final pose
+                SPX_CUDA(cudaMemcpyAsync(T_trace_host, reg->trace, (size_t)(hs->iterations + 1) * 16 * sizeof(float),
+                                         cudaMemcpyDeviceToHost, st));
+                q->sync();
+                for (int it = hs->iterations + 1; it < max_it; ++it)
+                    std::memcpy(T_trace_host + (size_t)it * 16, T_trace_host + (size_t)hs->iterations * 16, 64);
+            }
+            return;
+        }
+
+        // LM / dog-leg: one host decision per trial step (registration.hpp:830-964)
+        float T[4][4];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) T[i][j] = R->T[j * 4 + i];
+        float lambda = P.lm_init_lambda;
+        float radius = P.dogleg_initial_trust_region_radius;
+        a.use_state = 0;
+        a.state = nullptr;
+        auto converged = [&](const float* d) {
+            return norm3f(d) < P.criteria_rotation && norm3f(d + 3) < P.criteria_translation;
+        };
+        auto trial_error = [&](const float Tn[4][4], float* err, uint32_t* inl) {
+            LinArgs e = a;
+            host_T_to_xform(Tn, e.T);
+            launch_error<false>(c.reg, e, c.blocks, st);
+            SPX_CUDA(cudaMemcpyAsync(hsums, reg->sums, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            q->sync();
+            *err = (float)hsums[S_ERR];
+            *inl = (uint32_t)(hsums[S_INL] + 0.5);
+        };
+        auto clampf = [](float v, float lo, float hi) { return std::min(std::max(v, lo), hi); };
+        for (int it = 0; it < max_it; ++it) {
+            host_T_to_xform(T, a.T);
+            launch_linearize<1, false>(c.reg, a, c.blocks, st);
+            SPX_CUDA(cudaMemcpyAsync(hsums, reg->sums, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            q->sync();
+            float H[36], b[6], err;
+            uint32_t inl;
+            sums_to_host(hsums, H, b, &err, &inl);
+            std::memcpy(R->H_raw, H, sizeof(H));
+            std::memcpy(R->b_raw, b, sizeof(b));
+            R->error_raw = err;
+            if (P.optimization_method == SPX_OPT_LEVENBERG_MARQUARDT) {
+                float last = FLT_MAX, d[6];
+                for (int in = 0; in < P.lm_max_inner_iterations; ++in) {
+                    const bool ok = solve_damped6(H, b, lambda, d);
+                    R->converged = ok ? converged(d) : 0;
+                    float E[4][4], Tn[4][4];
+                    se3_exp_rm(d, E);
+                    isometry_mul_rm(T, E, Tn);
+                    float ne;
+                    uint32_t ni;
+                    trial_error(Tn, &ne, &ni);
+                    if (ne <= err) {
+                        R->converged = converged(d);
+                        std::memcpy(T, Tn, sizeof(T));
+                        R->error = ne;
+                        R->inlier = ni;
+                        lambda = clampf(lambda / P.lm_lambda_factor, P.lm_min_lambda, P.lm_max_lambda);
+                        break;
+                    } else if (std::fabs(ne - last) <= 1e-6f) {
+                        R->converged = converged(d);
+                        std::memcpy(T, Tn, sizeof(T));
+                        R->error = ne;
+                        R->inlier = ni;
+                        break;
+                    } else {
+                        lambda = clampf(lambda * P.lm_lambda_factor, P.lm_min_lambda, P.lm_max_lambda);
+                    }
+                    last = ne;
+                }
+                R->iterations = it;
+                std::memcpy(R->H, H, sizeof(H));
+                std::memcpy(R->b, b, sizeof(b));
+            } else {
+                std::memcpy(R->H, H, sizeof(H));
+                std::memcpy(R->b, b, sizeof(b));
+                R->error = err;
+                R->inlier = inl;
+                R->iterations = it;
+                radius = clampf(radius, P.dogleg_min_trust_region_radius, P.dogleg_max_trust_region_radius);
+                float p[6], step_norm, pred;
+                dogleg_host(H, b, radius, p, &step_norm, &pred);
+                if (pred <= 0.0f) {
+                    radius = clampf(radius * P.dogleg_gamma_decrease, P.dogleg_min_trust_region_radius,
+                                    P.dogleg_max_trust_region_radius);
+                } else {
+                    float E[4][4], Tn[4][4];
+                    se3_exp_rm(p, E);
+                    isometry_mul_rm(T, E, Tn);
+                    float ne;
+                    uint32_t ni;
+                    trial_error(Tn, &ne, &ni);
+                    const float rho = (err - ne) / pred;
+                    if (rho < P.dogleg_eta1) {
+                        radius = clampf(radius * P.dogleg_gamma_decrease, P.dogleg_min_trust_region_radius,
+                                        P.dogleg_max_trust_region_radius);
+                    } else {
+                        R->converged = converged(p);
+                        std::memcpy(T, Tn, sizeof(T));
+                        R->error = ne;
+                        R->inlier = ni;
+                        if (rho > P.dogleg_eta2 && step_norm >= radius * 0.99f)
+                            radius = clampf(radius * P.dogleg_gamma_increase, P.dogleg_min_trust_region_radius,
+                                            P.dogleg_max_trust_region_radius);
+                    }
+                }
+            }
+            for (int j = 0; j < 4; ++j)
+                for (int i = 0; i < 4; ++i) R->T[j * 4 + i] = T[i][j];
+            if (T_trace_host) std::memcpy(T_trace_host + (size_t)it * 16, R->T, 64);
+            if (R->converged) {
+                if (T_trace_host)
+                    for (int k2 = it + 1; k2 < max_it; ++k2) std::memcpy(T_trace_host + (size_t)k2 * 16, R->T, 64);
+                break;
+            }
+        }
+    });
+    if (derived_normals) {
+        cudaStreamSynchronize(reg->q->stream);
+        cudaFree(derived_normals);
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------ sharded building blocks
+int spx_registration_shard_begin(spx_registration_t reg, const float* src_points, const float* src_covs, size_t ns,
+                                 const float* tgt_points, const float* tgt_covs, const float* tgt_normals, size_t nt,
+                                 spx_index_t target_index, const float* T_init_host, float robust_scale) {
+    return guard([&] {
+        SPX_REQUIRE(reg, "[Registration::shard_begin] null handle");
+        SPX_REQUIRE(reg->P.optimization_method == SPX_OPT_GAUSS_NEWTON,
+                    "[Registration::shard_begin] the sharded path is Gauss-Newton only");
+        if (reg->P.reg_type == SPX_REG_POINT_TO_PLANE)
+            SPX_REQUIRE(tgt_normals, "[Registration::shard_begin] Point-to-Plane needs target normals");
+        DeviceGuard g(reg->q->device);
+        float4* dn = nullptr;
+        AlignCtx c = align_setup(reg, src_points, src_covs, ns, tgt_points, tgt_covs, tgt_normals, nt, target_index,
+                                 T_init_host, robust_scale, &dn);
+        reg->shard = c.a;
+        reg->shard_reg = c.reg;
+        reg->shard_iter = 0;
+        reg->shard_active = true;
+    });
+}
+
+int spx_registration_shard_linearize(spx_registration_t reg, double* sums_dev) {
+    return guard([&] {
+        SPX_REQUIRE(reg && reg->shard_active && sums_dev, "[Registration::shard_linearize] no active shard");
+        DeviceGuard g(reg->q->device);
+        LinArgs a = reg->shard;
+        a.sums_out = sums_dev;
+        const unsigned blocks = lin_blocks(reg->q, a.ns);
+        if (a.ns == 0) {
+            // an empty shard still contributes zeros (and must not leave stale sums behind)
+            SPX_CUDA(cudaMemsetAsync(sums_dev, 0, 32 * sizeof(double), reg->q->stream));
+            return;
+        }
+        launch_linearize<1, false>(reg->shard_reg, a, blocks, reg->q->stream);
+    });
+}
+
+int spx_registration_shard_update(spx_registration_t reg, const double* sums_dev) {
+    return guard([&] {
+        SPX_REQUIRE(reg && reg->shard_active && sums_dev, "[Registration::shard_update] no active shard");
+        DeviceGuard g(reg->q->device);
+        const LinArgs& a = reg->shard;
+        gn_update_kernel<<<1, 32, 0, reg->q->stream>>>(reg->state, sums_dev, a.lambda, a.crit_rot, a.crit_trans,
+                                                      reg->shard_iter, reg->trace);
+        SPX_LAUNCH_CHECK();
+        ++reg->shard_iter;
+    });
+}
+
+int spx_registration_shard_finish(spx_registration_t reg, spx_registration_result* R) {
+    return guard([&] {
+        SPX_REQUIRE(reg && reg->shard_active && R, "[Registration::shard_finish] no active shard");
+        spx_queue_t q = reg->q;
+        DeviceGuard g(q->device);
+        RegState* hs = static_cast<RegState*>(q->pinned_get(sizeof(RegState) + 64 + 32 * sizeof(double)));
+        SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, q->stream));
+        q->sync();
+        std::memset(R, 0, sizeof(*R));
+        fill_result(*hs, R);
+        reg->shard_active = false;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// Runtime shim of libspx: replaces the reference's SYCL queue / USM / event layer
+// (I/utils/sycl_utils.hpp:234-280,491-635) with one in-order CUDA stream per queue, explicit
+// device memory and CUDA events.
+#include <cstring>
+
+#include "spx_common.cuh"
+
+namespace spx {
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+std::atomic<uint64_t> g_launches{0};
+
+}  // namespace spx
+
+using namespace spx;
+
+void spx_queue_s::arena_reserve(size_t bytes) {
+    bytes = align_up(bytes + 4096, 1 << 20);
+    if (bytes <= arena_cap) return;
+    size_t cap = arena_cap ? arena_cap : (size_t)(8 << 20);
+    while (cap < bytes) cap *= 2;
+    void* p = nullptr;
+    SPX_CUDA(cudaMalloc(&p, cap));
+    if (arena) retired.push_back(arena);
+    arena = static_cast<char*>(p);
+    arena_cap = cap;
+    arena_off = 0;
+}
+
+void* spx_queue_s::arena_take(size_t bytes) {
+    const size_t off = align_up(arena_off, 256);
+    if (off + bytes > arena_cap)
+        throw Error(SPX_ERR_INTERNAL, "[spx] scratch arena overflow (arena_reserve under-estimated)");
+    arena_off = off + bytes;
+    return arena + off;
+}
+
+void* spx_queue_s::pinned_get(size_t bytes) {
+    if (bytes < (64u << 10)) bytes = 64u << 10;  // one allocation serves every small staging use
+    if (bytes > pinned_cap) {
+        if (pinned) {
+            cudaStreamSynchronize(stream);  // nothing may still be copying through the old block
+            cudaFreeHost(pinned);
+        }
+        pinned = nullptr;
+        pinned_cap = 0;
+        void* p = nullptr;
+        SPX_CUDA(cudaMallocHost(&p, align_up(bytes, 4096)));
+        pinned = static_cast<char*>(p);
+        pinned_cap = align_up(bytes, 4096);
+    }
+    return pinned;
+}
+
+void spx_queue_s::sync() {
+    SPX_CUDA(cudaStreamSynchronize(stream));
+    for (void* p : retired) cudaFree(p);
+    retired.clear();
+}
+
+extern "C" {
+
+const char* spx_last_error(void) { return t_last_error.c_str(); }
+int spx_abi_version(void) { return SPX_ABI_VERSION; }
+uint64_t spx_kernel_launch_count(void) { return g_launches.load(); }
+
+int spx_device_count(int* count) {
+    return guard([&] {
+        SPX_REQUIRE(count, "[spx_device_count] null output");
+        SPX_CUDA(cudaGetDeviceCount(count));
+    });
+}
+
+int spx_device_info(int device, char* name, int* sm, int* sm_count, size_t* global_mem_bytes, int* l2_bytes) {
+    return guard([&] {
+        cudaDeviceProp p;
+        SPX_CUDA(cudaGetDeviceProperties(&p, device));
+        if (name) {
+            std::strncpy(name, p.name, 255);
+            name[255] = 0;
+        }
+        if (sm) *sm = p.major * 10 + p.minor;
+        if (sm_count) *sm_count = p.multiProcessorCount;
+        if (global_mem_bytes) *global_mem_bytes = p.totalGlobalMem;
+        if (l2_bytes) *l2_bytes = p.l2CacheSize;
+    });
+}
+
+static int queue_create(int device, void* stream, bool own, spx_queue_t* out) {
+    return guard([&] {
+        SPX_REQUIRE(out, "[DeviceQueue::DeviceQueue] null output");
+        int n = 0;
+        SPX_CUDA(cudaGetDeviceCount(&n));
+        SPX_REQUIRE(device >= 0 && device < n,
+                    "[DeviceQueue::DeviceQueue] device ordinal " + std::to_string(device) + " is not supported.");
+        DeviceGuard g(device);
+        auto* q = new spx_queue_s();
+        q->device = device;
+        q->owns_stream = own;
+        if (own) {
+            SPX_CUDA(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+        } else {
+            q->stream = static_cast<cudaStream_t>(stream);
+        }
+        SPX_CUDA(cudaDeviceGetAttribute(&q->sm_count, cudaDevAttrMultiProcessorCount, device));
+        q->arena_reserve(8 << 20);
+        *out = q;
+    });
+}
+
+int spx_queue_create(int device, spx_queue_t* out) { return queue_create(device, nullptr, true, out); }
+int spx_queue_create_on_stream(int device, void* cuda_stream, spx_queue_t* out) {
+    return queue_create(device, cuda_stream, false, out);
+}
+
+int spx_queue_destroy(spx_queue_t q) {
+    return guard([&] {
+        if (!q) return;
+        DeviceGuard g(q->device);
+        cudaStreamSynchronize(q->stream);
+        for (void* p : q->retired) cudaFree(p);
+        if (q->arena) cudaFree(q->arena);
+        if (q->pinned) cudaFreeHost(q->pinned);
+        if (q->owns_stream && q->stream) cudaStreamDestroy(q->stream);
+        delete q;
+    });
+}
+
+int spx_queue_sync(spx_queue_t q) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_queue_sync] null queue");
+        DeviceGuard g(q->device);
+        q->sync();
+    });
+}
+
+int spx_queue_device(spx_queue_t q, int* device) {
+    return guard([&] {
+        SPX_REQUIRE(q && device, "[spx_queue_device] null argument");
+        *device = q->device;
+    });
+}
+
+int spx_malloc(spx_queue_t q, size_t bytes, void** out) {
+    return guard([&] {
+        SPX_REQUIRE(q && out, "[spx_malloc] null argument");
+        DeviceGuard g(q->device);
+        *out = nullptr;
+        if (bytes == 0) return;
+        SPX_CUDA(cudaMalloc(out, bytes));
+    });
+}
+
+int spx_free(spx_queue_t q, void* ptr) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_free] null queue");
+        if (!ptr) return;
+        DeviceGuard g(q->device);
+        SPX_CUDA(cudaStreamSynchronize(q->stream));
+        SPX_CUDA(cudaFree(ptr));
+    });
+}
+
+int spx_malloc_host(size_t bytes, void** out) {
+    return guard([&] {
+        SPX_REQUIRE(out, "[spx_malloc_host] null output");
+        *out = nullptr;
+        if (bytes == 0) return;
+        SPX_CUDA(cudaMallocHost(out, bytes));
+    });
+}
+
+int spx_free_host(void* ptr) {
+    return guard([&] {
+        if (ptr) SPX_CUDA(cudaFreeHost(ptr));
+    });
+}
+
+int spx_memcpy_h2d(spx_queue_t q, void* dst, const void* src_host, size_t bytes) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_memcpy_h2d] null queue");
+        if (!bytes) return;
+        DeviceGuard g(q->device);
+        SPX_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, q->stream));
+    });
+}
+
+int spx_memcpy_d2h(spx_queue_t q, void* dst_host, const void* src, size_t bytes) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_memcpy_d2h] null queue");
+        if (!bytes) return;
+        DeviceGuard g(q->device);
+        SPX_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, q->stream));
+    });
+}
+
+int spx_memcpy_d2d(spx_queue_t q, void* dst, const void* src, size_t bytes) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_memcpy_d2d] null queue");
+        if (!bytes) return;
+        DeviceGuard g(q->device);
+        SPX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, q->stream));
+    });
+}
+
+int spx_memset(spx_queue_t q, void* dst, int value, size_t bytes) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_memset] null queue");
+        if (!bytes) return;
+        DeviceGuard g(q->device);
+        SPX_CUDA(cudaMemsetAsync(dst, value, bytes, q->stream));
+    });
+}
+
+int spx_event_create(spx_event_t* out) {
+    return guard([&] {
+        SPX_REQUIRE(out, "[spx_event_create] null output");
+        auto* e = new spx_event_s();
+        SPX_CUDA(cudaEventCreate(&e->ev));
+        *out = e;
+    });
+}
+
+int spx_event_destroy(spx_event_t e) {
+    return guard([&] {
+        if (!e) return;
+        cudaEventDestroy(e->ev);
+        delete e;
+    });
+}
+
+int spx_event_record(spx_queue_t q, spx_event_t e) {
+    return guard([&] {
+        SPX_REQUIRE(q && e, "[spx_event_record] null argument");
+        DeviceGuard g(q->device);
+        SPX_CUDA(cudaEventRecord(e->ev, q->stream));
+    });
+}
+
+int spx_event_elapsed_ms(spx_event_t start, spx_event_t stop, float* ms) {
+    return guard([&] {
+        SPX_REQUIRE(start && stop && ms, "[spx_event_elapsed_ms] null argument");
+        SPX_CUDA(cudaEventSynchronize(stop->ev));
+        SPX_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// Voxel-grid downsampling and the box filter on the device.
+//
+// Reference: filter::VoxelGrid::downsampling (I/algorithms/filter/voxel_downsampling.hpp:50-62) —
+// only the key computation runs on the device there (:114-144); the sort (:146-179, host std::sort)
+// and the per-voxel mean (:181-218, host sweep) are host code.  Here all three are kernels:
+//   1. voxel coordinates per point (voxel_constants.hpp:36-62) + their bounding box,
+//   2. an order-preserving compact key  ((z-zmin)·ny + (y-ymin))·nx + (x-xmin)  — same ordering as
+//      the reference's 63-bit key but only ceil(log2(nx·ny·nz)) significant bits, so the LSD radix
+//      sort needs 3-4 eight-bit passes instead of 8,
+//   3. a stable LSD radix sort of (key, original index) — stability gives the (key, index) order the
+//      oracle defines for the order the reference leaves to std::sort,
+//   4. one thread per voxel run: fp32 running sum in that order, mean = sum / sum.w, drop runs with
+//      sum.w < min_voxel_count (:204), stream-compact to ascending-key output.
+#include <cmath>
+
+#include "spx_scan.cuh"
+
+using namespace spx;
+
+namespace {
+
+constexpr int VX_THREADS = 256;
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;  // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+
+struct CoordAcc {
+    int mn[3];
+    int mx[3];
+    uint32_t valid;
+    uint32_t pad;
+};
+
+// compute_voxel_bit's coordinate part — voxel_constants.hpp:36-53.  Returns false for the points
+// the reference maps to invalid_coord (non-finite or outside the 21-bit range).
+__device__ __forceinline__ bool voxel_coords(const float4 p, float inv, int c[3]) {
+    if (!isfinite(p.x) || !isfinite(p.y) || !isfinite(p.z)) return false;
+    const float fx = floorf(__fmul_rn(p.x, inv));
+    const float fy = floorf(__fmul_rn(p.y, inv));
+    const float fz = floorf(__fmul_rn(p.z, inv));
+    const float lim = 1048576.0f;  // 2^20: coord + offset must land in [0, 2^21 - 1]
+    if (!(fx >= -lim && fx < lim && fy >= -lim && fy < lim && fz >= -lim && fz < lim)) return false;
+    c[0] = (int)fx + (1 << 20);
+    c[1] = (int)fy + (1 << 20);
+    c[2] = (int)fz + (1 << 20);
+    return true;
+}
+
+__global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __restrict__ pts, uint32_t n, float inv,
+                                                                CoordAcc* acc) {
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    uint32_t cnt = 0;
+    for (uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x; i < n; i += gridDim.x * VX_THREADS) {
+        int c[3];
+        if (voxel_coords(__ldg(pts + i), inv, c)) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = min(mn[a], c[a]);
+                mx[a] = max(mx[a], c[a]);
+            }
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&acc->mn[a], mn[a]);
+            atomicMax(&acc->mx[a], mx[a]);
+        }
+        atomicAdd(&acc->valid, cnt);
+    }
+}
+
+struct KeyGeom {
+    int mn[3];
+    unsigned long long nx, nxy;  // strides of the compact key
+    unsigned long long invalid;  // key given to dropped points (sorts after every valid key)
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(VX_THREADS) voxel_key_kernel(const float4* __restrict__ pts, uint32_t n, float inv,
+                                                               KeyGeom g, KeyT* __restrict__ keys) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    int c[3];
+    unsigned long long key = g.invalid;
+    if (voxel_coords(__ldg(pts + i), inv, c))
+        key = (unsigned long long)(c[2] - g.mn[2]) * g.nxy + (unsigned long long)(c[1] - g.mn[1]) * g.nx +
+              (unsigned long long)(c[0] - g.mn[0]);
+    keys[i] = (KeyT)key;
+}
+
+// ---- stable LSD radix sort, one 8-bit digit per pass: histogram -> scan -> scatter
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const KeyT* __restrict__ keys, uint32_t n, int shift,
+                                                                uint32_t nblocks, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t h[RADIX];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+        const uint32_t i = base + it * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    ghist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// Each warp owns a contiguous 256-key slice of the tile and walks it 32 keys at a time, so
+// "earlier in the input" == "earlier (warp, chunk, lane)".  __match_any_sync groups equal digits
+// inside a chunk; the per-warp digit counters give the rank inside the warp; a per-digit prefix
+// over the warps (seeded with the scanned global histogram) gives the final, stable position.
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* __restrict__ keys_in,
+                                                                   const uint32_t* __restrict__ vals_in,
+                                                                   KeyT* __restrict__ keys_out,
+                                                                   uint32_t* __restrict__ vals_out,
+                                                                   const uint32_t* __restrict__ goffs, uint32_t n,
+                                                                   int shift, uint32_t nblocks) {
+    __shared__ uint32_t wcnt[RS_WARPS][RADIX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < RS_WARPS * RADIX; t += RS_THREADS) (&wcnt[0][0])[t] = 0;
+    __syncthreads();
+
+    KeyT key[RS_ITEMS];
+    uint32_t val[RS_ITEMS], rank[RS_ITEMS];
+    const uint32_t wbase = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const uint32_t i = wbase + c * 32 + lane;
+        const bool live = i < n;
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        rank[c] = 0;
+        key[c] = 0;
+        val[c] = 0;
+        if (live) {
+            key[c] = keys_in[i];
+            val[c] = vals_in ? vals_in[i] : i;
+            const uint32_t digit = (uint32_t)(key[c] >> shift) & (RADIX - 1);
+            const unsigned peers = __match_any_sync(act, digit);
+            const uint32_t before = __popc(peers & ((1u << lane) - 1));
+            const uint32_t prev = wcnt[warp][digit];
+            __syncwarp(act);
+            if (before == 0) wcnt[warp][digit] = prev + __popc(peers);
+            __syncwarp(act);
+            rank[c] = prev + before;
+        }
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;  // RS_THREADS == RADIX
+        uint32_t run = goffs[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t t = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const uint32_t i = wbase + c * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (uint32_t)(key[c] >> shift) & (RADIX - 1);
+            const uint32_t dst = wcnt[warp][digit] + rank[c];
+            keys_out[dst] = key[c];
+            vals_out[dst] = val[c];
+        }
+    }
+}
+
+// ---- per-voxel mean
+template <typename KeyT>
+__global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __restrict__ pts,
+                                                                const KeyT* __restrict__ skeys,
+                                                                const uint32_t* __restrict__ svals, uint32_t n_valid,
+                                                                float min_count, uint32_t* __restrict__ flags,
+                                                                float4* __restrict__ means) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i >= n_valid) return;
+    const KeyT key = skeys[i];
+    uint32_t flag = 0;
+    if (i == 0 || skeys[i - 1] != key) {
+        // PointType point_sum = Zero; point_sum += points[idx] in sorted order — :193-201
+        float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+        for (uint32_t j = i; j < n_valid && skeys[j] == key; ++j) {
+            const float4 p = __ldg(pts + svals[j]);
+            sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
+        }
+        if (sw >= min_count) {  // :204
+            flag = 1;
+            means[i] = make_float4(__fdiv_rn(sx, sw), __fdiv_rn(sy, sw), __fdiv_rn(sz, sw), __fdiv_rn(sw, sw));
+        }
+    }
+    flags[i] = flag;
+}
+
+__global__ void __launch_bounds__(VX_THREADS) compact_float4_kernel(const float4* __restrict__ in,
+                                                                    const uint32_t* __restrict__ flags,
+                                                                    const uint32_t* __restrict__ pos, uint32_t n,
+                                                                    float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i]) out[pos[i]] = in[i];
+}
+
+// box_filter — preprocess_operator/box_filter_operator.hpp:36-44 + common.hpp:15-25
+__global__ void __launch_bounds__(VX_THREADS) box_flag_kernel(const float4* __restrict__ pts, uint32_t n, float mn,
+                                                              float mx, uint32_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pts + i);
+    uint32_t keep = 0;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(p.w)) {
+        const float linf = fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)));
+        keep = !(linf < mn || linf > mx);
+    }
+    flags[i] = keep;
+}
+
+int bits_for(unsigned long long v) {  // bits needed to represent values in [0, v]
+    int b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+
+template <typename KeyT>
+void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
+                     uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev) {
+    cudaStream_t st = q->stream;
+    const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
+    KeyT* keys_a = q->take<KeyT>(n);
+    KeyT* keys_b = q->take<KeyT>(n);
+    uint32_t* vals_a = q->take<uint32_t>(n);
+    uint32_t* vals_b = q->take<uint32_t>(n);
+    uint32_t* ghist = q->take<uint32_t>((size_t)RADIX * nblocks + 64);
+    uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems((size_t)RADIX * nblocks));
+    uint32_t* flags = q->take<uint32_t>(n);
+    uint32_t* pos = q->take<uint32_t>(n);
+    uint32_t* scan_tmp2 = q->take<uint32_t>(scan_scratch_elems(n));
+    float4* means = q->take<float4>(n);
+
+    voxel_key_kernel<KeyT><<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, inv, geom, keys_a);
+    SPX_LAUNCH_CHECK();
+    const int passes = std::max(1, (key_bits + RADIX_BITS - 1) / RADIX_BITS);
+    KeyT* kin = keys_a;
+    KeyT* kout = keys_b;
+    uint32_t* vin = nullptr;  // first pass: value = position
+    uint32_t* vout = vals_a;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * RADIX_BITS;
+        radix_hist_kernel<KeyT><<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, nblocks, ghist);
+        SPX_LAUNCH_CHECK();
+        exclusive_scan_u32(st, ghist, ghist, (size_t)RADIX * nblocks, scan_tmp, nullptr);
+        radix_scatter_kernel<KeyT><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, ghist, n, shift, nblocks);
+        SPX_LAUNCH_CHECK();
+        std::swap(kin, kout);
+        vin = vout;
+        vout = (vout == vals_a) ? vals_b : vals_a;
+    }
+    // kin / vin now hold the sorted (key, index) pairs; dropped points (invalid key) sit at the end
+    if (n_valid > 0) {
+        voxel_mean_kernel<KeyT><<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count,
+                                                                                  flags, means);
+        SPX_LAUNCH_CHECK();
+    }
+    exclusive_scan_u32(st, flags, pos, n_valid, scan_tmp2, total_dev);
+    if (n_valid > 0) {
+        compact_float4_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(means, flags, pos, n_valid, out);
+        SPX_LAUNCH_CHECK();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n_in, float voxel_size, size_t min_voxel_count,
+                         float* out_points, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && m_host, "[VoxelGrid::downsampling] null argument");
+        if (!(voxel_size > 0.0f)) throw Error(SPX_ERR_INVALID_ARGUMENT, "voxel_size must be positive");
+        SPX_REQUIRE(n_in < (1ull << 31), "[VoxelGrid::downsampling] too many points");
+        *m_host = 0;
+        if (n_in == 0) return;
+        SPX_REQUIRE(points && out_points, "[VoxelGrid::downsampling] null pointer");
+        DeviceGuard dg(q->device);
+        cudaStream_t st = q->stream;
+        const uint32_t n = (uint32_t)n_in;
+        const float inv = 1.0f / voxel_size;  // voxel_downsampling.hpp:27
+        const float4* pts = reinterpret_cast<const float4*>(points);
+        const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
+
+        q->arena_reset();
+        q->arena_reserve((size_t)n * (8 * 2 + 4 * 2 + 4 * 2 + 16) + ((size_t)RADIX * nblocks + 64) * 4 +
+                         (scan_scratch_elems((size_t)RADIX * nblocks) + scan_scratch_elems(n)) * 4 + 16 * 256 + 4096);
+        CoordAcc* acc = q->take<CoordAcc>(1);
+        uint32_t* total_dev = q->take<uint32_t>(16);
+        char* pin = static_cast<char*>(q->pinned_get(256));
+        CoordAcc* hacc = reinterpret_cast<CoordAcc*>(pin);
+        uint32_t* htotal = reinterpret_cast<uint32_t*>(pin + 128);
+        for (int a = 0; a < 3; ++a) {
+            hacc->mn[a] = INT_MAX;
+            hacc->mx[a] = INT_MIN;
+        }
+        hacc->valid = 0;
+        hacc->pad = 0;
+        SPX_CUDA(cudaMemcpyAsync(acc, hacc, sizeof(CoordAcc), cudaMemcpyHostToDevice, st));
+        voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
+        SPX_LAUNCH_CHECK();
+        SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(CoordAcc), cudaMemcpyDeviceToHost, st));
+        q->sync();
+        const CoordAcc bb = *hacc;
+        if (bb.valid == 0) return;
+
+        KeyGeom geom;
+        unsigned long long dim[3];
+        for (int a = 0; a < 3; ++a) {
+            geom.mn[a] = bb.mn[a];
+            dim[a] = (unsigned long long)(bb.mx[a] - bb.mn[a]) + 1ull;
+        }
+        geom.nx = dim[0];
+        geom.nxy = dim[0] * dim[1];
+        const unsigned long long max_key = dim[0] * dim[1] * dim[2] - 1ull;  // <= 2^63 - 1
+        const bool has_invalid = bb.valid != n;
+        geom.invalid = max_key + 1ull;
+        const int key_bits = bits_for(has_invalid ? geom.invalid : max_key);
+        const float min_count = (float)min_voxel_count;
+        float4* out = reinterpret_cast<float4*>(out_points);
+        if (key_bits <= 32)
+            sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev);
+        else
+            sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev);
+        SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
+        q->sync();
+        *m_host = *htotal;
+    });
+}
+
+int spx_box_filter(spx_queue_t q, const float* points, size_t n_in, float min_distance, float max_distance,
+                   float* out_points, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && m_host, "[PreprocessFilter::box_filter] null argument");
+        SPX_REQUIRE(n_in < (1ull << 31), "[PreprocessFilter::box_filter] too many points");
+        *m_host = 0;
+        if (n_in == 0) return;
+        SPX_REQUIRE(points && out_points, "[PreprocessFilter::box_filter] null pointer");
+        DeviceGuard dg(q->device);
+        cudaStream_t st = q->stream;
+        const uint32_t n = (uint32_t)n_in;
+        q->arena_reset();
+        q->arena_reserve((size_t)n * 8 + scan_scratch_elems(n) * 4 + 4096);
+        uint32_t* flags = q->take<uint32_t>(n);
+        uint32_t* pos = q->take<uint32_t>(n);
+        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(n));
+        uint32_t* total_dev = q->take<uint32_t>(16);
+        const float4* pts = reinterpret_cast<const float4*>(points);
+        box_flag_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, min_distance, max_distance, flags);
+        SPX_LAUNCH_CHECK();
+        exclusive_scan_u32(st, flags, pos, n, scan_tmp, total_dev);
+        compact_float4_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, flags, pos, n,
+                                                                           reinterpret_cast<float4*>(out_points));
+        SPX_LAUNCH_CHECK();
+        uint32_t* htotal = static_cast<uint32_t*>(q->pinned_get(64));
+        SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
+        q->sync();
+        *m_host = *htotal;
+    });
+}
+
+}  // extern "C"

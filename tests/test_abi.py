@@ -1,0 +1,138 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/spx.h
+declares, and the host-side pieces that need no GPU behave like the reference."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import sycl_points_b200 as spx
+from sycl_points_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = spx.declared_symbols()
+    assert len(names) >= 45
+    raw = C.CDLL(_lib.SO_PATH)
+    missing = [n for n in names if not hasattr(raw, n)]
+    assert not missing, missing
+    assert spx.lib().spx_abi_version() == 1
+
+
+def test_header_cites_reference_lines():
+    text = open(os.path.join(ROOT, "include", "spx.h")).read()
+    for needle in ("bruteforce.hpp:24-96", "kdtree.hpp", "covariance.hpp:16-47", "voxel_downsampling.hpp:50-62",
+                   "registration.hpp:201-276", "registration.hpp:312-331,513-676", "sycl_utils.hpp:491"):
+        assert needle in text, needle
+
+
+def test_param_struct_defaults_match_reference():
+    # registration_params.hpp:41-114
+    P = spx.RegistrationParams().to_c()
+    assert (P.reg_type, P.robust_loss, P.optimization_method, P.max_iterations) == (3, 0, 0, 20)
+    assert P.max_correspondence_distance == 2.0 and P.robust_default_scale == 10.0
+    assert abs(P.criteria_translation - 1e-3) < 1e-9 and abs(P.criteria_rotation - 1e-3) < 1e-9
+    assert P.gn_lambda == 1.0 and P.lm_max_inner_iterations == 10 and P.lm_lambda_factor == 2.0
+    assert P.lm_init_lambda == 1.0 and P.lm_max_lambda == 1e3 and abs(P.lm_min_lambda - 1e-6) < 1e-12
+    assert P.dogleg_initial_trust_region_radius == 1.0 and P.dogleg_max_trust_region_radius == 10.0
+    assert (P.dogleg_eta1, P.dogleg_eta2, P.dogleg_gamma_decrease, P.dogleg_gamma_increase) == (0.25, 0.75, 0.25, 2.0)
+    # the oracle's struct carries the same defaults
+    O = oracle.default_params()
+    assert (O.reg_type, O.loss, O.opt_method, O.max_iterations) == (3, 0, 0, 20)
+    assert C.sizeof(_lib.RegistrationResultC) == C.sizeof(oracle.RegResult)
+
+
+def test_enum_strings():
+    # factor.hpp:43-61, robust.hpp:30-48, registration_params.hpp:23-38
+    assert spx.api.RegType_from_string("gicp") == spx.RegType.GICP
+    assert spx.api.RegType_from_string("P2D") == spx.RegType.POINT_TO_DISTRIBUTION
+    assert spx.api.RobustLossType_from_string("geman_mcclure") == spx.RobustLossType.GEMAN_MCCLURE
+    assert spx.api.OptimizationMethod_from_string("lm") == spx.OptimizationMethod.LEVENBERG_MARQUARDT
+    assert spx.api.OptimizationMethod_from_string("dogleg") == spx.OptimizationMethod.POWELL_DOGLEG
+    with pytest.raises(RuntimeError, match="Invalid RegType"):
+        spx.api.RegType_from_string("nope")
+
+
+def test_host_solver_pieces_match_oracle():
+    """spx_solve_6x6 / spx_se3_exp / spx_dogleg_step are host code: comparable without a GPU."""
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        A = rng.normal(size=(6, 8))
+        H = (A @ A.T * rng.uniform(1, 1e4)).astype(np.float32)
+        b = (rng.normal(size=6) * 100).astype(np.float32)
+        ok_s, d_s = spx.api.solve_6x6(H, b, 1.0)
+        ok_o, d_o = oracle.solve6(H, b, 1.0)
+        assert ok_s and ok_o
+        assert np.allclose(d_s, d_o, rtol=1e-6, atol=1e-9)
+        tw = rng.uniform(-1, 1, 6).astype(np.float32) * rng.choice([1e-4, 1e-2, 1.0])
+        assert np.allclose(spx.api.se3_exp(tw), oracle.se3_exp(tw), rtol=0, atol=3e-7)
+        p_s, sn_s, pr_s = spx.api.dogleg_step(H, b, 0.3)
+        p_o, sn_o, pr_o = oracle.dogleg_step(H, b, 0.3)
+        assert np.allclose(p_s, p_o, rtol=1e-5, atol=1e-8) and abs(sn_s - sn_o) <= 1e-6 * max(1, sn_o)
+        assert abs(pr_s - pr_o) <= 1e-4 * max(1.0, abs(pr_o))
+    assert np.array_equal(spx.api.se3_exp(np.zeros(6)), np.eye(4, dtype=np.float32))
+
+
+def test_robust_scale_schedule_reference_values():
+    # T/test_registration_pipeline.cpp:360-409
+    s = spx.robust_scale_schedule(6.0, 2.0, 3)
+    assert s[0] == 6.0 and abs(s[1] - np.sqrt(12.0)) <= 1e-5 and abs(s[2] - 2.0) <= 1e-5
+    r = spx.robust_scale_schedule(9.0, 3.0, 3)
+    assert r[0] == 9.0 and abs(r[1] - np.sqrt(27.0)) <= 1e-5 and abs(r[2] - 3.0) <= 1e-5
+    assert np.allclose(s, oracle.robust_schedule(6.0, 2.0, 3), rtol=1e-6)
+
+
+def test_pipeline_forwards_scales_like_reference():
+    """RobustAlignerLeavesScaleUnsetWhenAutoScalingDisabledAndAnnealsWhenEnabled
+    (T/test_registration_pipeline.cpp:360-409) with a lambda aligner — no GPU involved."""
+
+    class Cloud:
+        def size(self):
+            return 3
+
+    params = spx.RegistrationPipelineParams()
+    params.registration.robust.type = spx.RobustLossType.HUBER
+    params.registration.robust.default_scale = 8.0
+    seen = []
+
+    def aligner(src, tgt, knn, T, options):
+        seen.append((options.robust_scale, options.rotation_robust_scale))
+        return spx.RegistrationResult()
+
+    spx.RegistrationPipeline(aligner, params).align(Cloud(), Cloud(), None)
+    assert len(seen) == 1 and seen[0][0] == -1.0
+    params.robust.auto_scale = True
+    params.robust.init_scale, params.robust.min_scale = 6.0, 2.0
+    params.robust.rotation_init_scale, params.robust.rotation_min_scale = 9.0, 3.0
+    params.robust.auto_scaling_iter = 3
+    seen.clear()
+    spx.RegistrationPipeline(aligner, params).align(Cloud(), Cloud(), None)
+    assert len(seen) == 3
+    assert seen[0] == (6.0, 9.0)
+    assert abs(seen[1][0] - np.sqrt(12.0)) <= 1e-5 and abs(seen[1][1] - np.sqrt(27.0)) <= 1e-5
+    assert abs(seen[2][0] - 2.0) <= 1e-5 and abs(seen[2][1] - 3.0) <= 1e-5
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device every compute entry point must raise, never silently compute."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(spx.SpxError):
+        spx.DeviceQueue(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sycl_points_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "oracle/" not in text and "liborc" not in text, f

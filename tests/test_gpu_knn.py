@@ -1,0 +1,174 @@
+"""GPU parity: KNN through the C-ABI vs the oracle.  Bit-exact indices and distances, ties by
+index (north star).  Mirrors T/test_kdtree.cpp."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+FMAX = np.finfo(np.float32).max
+
+
+@pytest.fixture(scope="module")
+def q(spx):
+    return spx.DeviceQueue(0)
+
+
+def gpu_bf(spx, q, qry, tgt, k, T=None):
+    r = spx.knn_search_bruteforce(q, spx.PointCloudShared(q, qry), spx.PointCloudShared(q, tgt), k, T)
+    return r.indices_host(), r.distances_host()
+
+
+def gpu_index(spx, q, qry, tgt, k, T=None, cell=0.0):
+    tree = spx.KDTree.build(q, spx.PointCloudShared(q, tgt), cell_size=cell)
+    r = tree.knn_search(spx.PointCloudShared(q, qry), k, transT=T)
+    return r.indices_host(), r.distances_host(), tree
+
+
+def assert_same(a, b):
+    assert np.array_equal(a[0], b[0]), f"indices differ at {np.argwhere(a[0] != b[0])[:5]}"
+    assert np.array_equal(a[1], b[1]), "distances differ"
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 10, 20])
+def test_fixture_distribution(spx, q, k):
+    # T/test_kdtree.cpp:301-317,392-408: seed 1234, 1000 targets, 100 queries, range 10
+    g = oracle.Rng(1234)
+    tgt, qry = g.uniform_points(1000, 10.0), g.uniform_points(100, 10.0)
+    want = oracle.knn_bruteforce(qry, tgt, k)
+    assert_same(gpu_bf(spx, q, qry, tgt, k), want)
+    assert_same(gpu_index(spx, q, qry, tgt, k)[:2], want)
+
+
+def test_various_sizes(spx, q):
+    # T/test_kdtree.cpp:320-355
+    g = oracle.Rng(1234)
+    for nt in (10, 100, 500):
+        for nq in (5, 20):
+            tgt, qry = g.uniform_points(nt, 10.0), g.uniform_points(nq, 10.0)
+            want = oracle.knn_bruteforce(qry, tgt, 3)
+            assert_same(gpu_bf(spx, q, qry, tgt, 3), want)
+            assert_same(gpu_index(spx, q, qry, tgt, 3)[:2], want)
+
+
+def test_single_point_known_answer(spx, q):
+    # T/test_kdtree.cpp:358-389
+    tgt = np.array([[0, 0, 0, 1]], np.float32)
+    qry = np.array([[1, 1, 1, 1]], np.float32)
+    for idx, dist in (gpu_bf(spx, q, qry, tgt, 1), gpu_index(spx, q, qry, tgt, 1)[:2]):
+        assert idx[0, 0] == 0 and abs(dist[0, 0] - 3.0) <= 1e-6
+
+
+def test_self_search(spx, q):
+    # T/test_kdtree.cpp:467-476
+    tgt = oracle.Rng(1234).uniform_points(1000, 10.0)
+    idx, dist, _ = gpu_index(spx, q, tgt, tgt, 10)
+    assert np.array_equal(idx[:, 0], np.arange(1000)) and (dist[:, 0] == 0).all()
+    assert (np.diff(dist, axis=1) >= 0).all()
+
+
+def test_ties_resolve_to_lowest_index(spx, q):
+    rng = np.random.default_rng(5)
+    base = rng.integers(-3, 4, (60, 3)).astype(np.float32)  # integer lattice: many exact distance ties
+    tgt = np.c_[np.repeat(base, 4, axis=0), np.ones(240, np.float32)].astype(np.float32)  # + exact duplicates
+    tgt = tgt[rng.permutation(len(tgt))]
+    qry = np.c_[rng.integers(-3, 4, (80, 3)).astype(np.float32), np.ones(80, np.float32)].astype(np.float32)
+    for k in (1, 4, 7, 20):
+        want = oracle.knn_bruteforce(qry, tgt, k)
+        assert_same(gpu_bf(spx, q, qry, tgt, k), want)
+        assert_same(gpu_index(spx, q, qry, tgt, k)[:2], want)
+        assert_same(gpu_index(spx, q, qry, tgt, k, cell=0.7)[:2], want)
+
+
+def test_k_larger_than_targets_and_empty(spx, q):
+    tgt = oracle.Rng(7).uniform_points(3, 1.0)
+    want = oracle.knn_bruteforce(tgt, tgt, 5)
+    got = gpu_bf(spx, q, tgt, tgt, 5)
+    assert_same(got, want)
+    assert (got[0][:, 3:] == -1).all() and (got[1][:, 3:] == FMAX).all()  # result.hpp:21-27
+    assert_same(gpu_index(spx, q, tgt, tgt, 5)[:2], want)
+    # empty query -> empty result (kdtree.hpp:429-436); empty target -> all unfilled
+    tree = spx.KDTree.build(q, spx.PointCloudShared(q, tgt))
+    r = tree.knn_search(spx.PointCloudShared(q, np.zeros((0, 4), np.float32)), 3)
+    assert r.query_size == 0
+    empty = spx.KDTree.build(q, spx.PointCloudShared(q, np.zeros((0, 4), np.float32)))
+    r = empty.knn_search(spx.PointCloudShared(q, tgt), 2)
+    assert (r.indices_host() == -1).all() and (r.distances_host() == FMAX).all()
+
+
+def test_k_limit(spx, q):
+    tgt = oracle.Rng(7).uniform_points(8, 1.0)
+    tree = spx.KDTree.build(q, spx.PointCloudShared(q, tgt))
+    with pytest.raises(spx.SpxInvalidArgument, match="too large"):  # kdtree.hpp:221-223
+        tree.knn_search(spx.PointCloudShared(q, tgt), 200)
+
+
+def test_transform_inside_search(spx, q):
+    # KNNBase::knn_search_async transforms queries by transT inside the search (kdtree.hpp:470)
+    g = oracle.Rng(99)
+    tgt, qry = g.uniform_points(5000, 10.0), g.uniform_points(700, 10.0)
+    T = oracle.se3_exp(np.array([0.1, -0.2, 0.3, 1.0, -2.0, 0.5], np.float32))
+    want = oracle.knn_bruteforce(qry, tgt, 6, T)
+    assert_same(gpu_bf(spx, q, qry, tgt, 6, T), want)
+    assert_same(gpu_index(spx, q, qry, tgt, 6, T)[:2], want)
+    assert_same(oracle.KDTree(tgt).knn(qry, 6, T, mode=0), want)
+
+
+def test_queries_far_outside_and_nonfinite(spx, q):
+    g = oracle.Rng(3)
+    tgt = g.uniform_points(3000, 5.0)
+    qry = g.uniform_points(64, 5.0)
+    qry[:16, :3] *= 100.0  # far outside the grid: ring search gives up -> full-scan fallback
+    qry[16:20, :3] += 40.0
+    tgt2 = tgt.copy()
+    tgt2[5, 0] = np.nan  # non-finite targets are never neighbours
+    tgt2[6, 1] = np.inf
+    for k in (1, 5):
+        want = oracle.knn_bruteforce(qry, tgt2, k)
+        assert_same(gpu_bf(spx, q, qry, tgt2, k), want)
+        assert_same(gpu_index(spx, q, qry, tgt2, k)[:2], want)
+    qn = qry.copy()
+    qn[0, 2] = np.nan
+    idx, dist, _ = gpu_index(spx, q, qn, tgt2, 3)
+    assert (idx[0] == -1).all() and (dist[0] == FMAX).all()
+
+
+def test_bundled_pair_k10_and_nn(spx, q, bundled, bundled_golden):
+    src, tgt = bundled["source_ds"], bundled["target_ds"]
+    want = oracle.KDTree(tgt).knn(tgt, 10)
+    got = gpu_index(spx, q, tgt, tgt, 10)
+    assert_same(got[:2], want)
+    assert np.array_equal(got[0][:256], bundled_golden["idx_t_head"])
+    nn = gpu_index(spx, q, src, tgt, 1)
+    assert np.array_equal(nn[0].reshape(-1), bundled_golden["nn_idx"])
+    assert np.array_equal(nn[1].reshape(-1), bundled_golden["nn_dist"])
+    info = got[2].info()
+    assert info["n_points"] == len(tgt) and 1.0 <= len(tgt) / info["occupied_cells"] <= 40.0
+
+
+def test_clustered_and_planar_clouds(spx, q):
+    rng = np.random.default_rng(11)
+    plane = np.c_[rng.uniform(-50, 50, (20000, 2)), np.zeros(20000)]
+    blob = rng.normal(0, 0.05, (5000, 3)) + [10, 10, 2]
+    line = np.c_[np.linspace(-30, 30, 3000), np.full(3000, 7.0), np.full(3000, 1.0)]
+    tgt = np.c_[np.concatenate([plane, blob, line]), np.ones(28000)].astype(np.float32)
+    qry = tgt[rng.choice(len(tgt), 3000, replace=False)].copy()
+    qry[:, :3] += rng.normal(0, 0.2, (3000, 3)).astype(np.float32)
+    for k in (1, 10, 20):
+        want = oracle.KDTree(tgt).knn(qry, k)
+        assert_same(gpu_index(spx, q, qry, tgt, k)[:2], want)
+    assert_same(gpu_bf(spx, q, qry[:500], tgt, 10), oracle.knn_bruteforce(qry[:500], tgt, 10))
+
+
+def test_large_100k_k10(spx, q):
+    # the reference's own timing case (T/test_kdtree.cpp:411-457): 100k x 100k, k = 10, uniform
+    g = oracle.Rng(1234)
+    tgt, qry = g.uniform_points(100000, 10.0), g.uniform_points(100000, 10.0)
+    want = oracle.KDTree(tgt).knn(qry, 10)
+    assert_same(gpu_index(spx, q, qry, tgt, 10)[:2], want)
+    sub = np.arange(0, 100000, 50)
+    got = gpu_bf(spx, q, qry[sub], tgt, 10)
+    assert np.array_equal(got[0], want[0][sub]) and np.array_equal(got[1], want[1][sub])
+    # 2-queries-per-thread variant of the tile scan (taken when nq is large)
+    got = gpu_bf(spx, q, qry, tgt[:4096], 20)
+    assert_same(got, oracle.knn_bruteforce(qry, tgt[:4096], 20))
