@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — the registration hot path on BASELINE.json config 2.
+
+A "step" is one pass of the whole per-pair hot path over one synthetic LiDAR-shaped scan pair
+(2.0 M raw points per cloud -> ~120 k points after the 0.25 m voxel grid):
+
+    voxel-grid downsample (both clouds) -> exact KNN index build (both) -> KNN k=10 (both)
+    -> covariance from 10 neighbours (both) -> GICP align (Gauss-Newton, Huber scale 10,
+    max_correspondence_distance 2.0, <= 20 iterations, criteria 1e-3 / 1e-3, initial guess I)
+
+metric `value`  = scan pairs per second, whole job (all ranks), raw clouds resident in HBM;
+`e2e`           = the same through the public API from pinned HOST buffers: H2D of both raw clouds
+                  and D2H of the registration result inside the timed region;
+`ms_per_iter`   = GICP align milliseconds per executed ICP iteration (the other half of the metric);
+`roofline`      = the fused nearest-neighbour + linearise + reduce (+ solve) kernel: algorithmic bytes
+                  192*N_s + 16*N_t per launch / its CUDA-event time per launch;
+`cpu_baseline`  = the oracle port of the reference's CPU path on the same pair, all host threads.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+N > 1: every rank aligns its own independent pair on its own GPU (no data-path collective: weak
+scaling of batched pairs); max over ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import synthetic  # noqa: E402
+
+VOXEL = 0.25
+K_COV = 10
+WORKLOAD = ("synthetic KITTI-shaped pair (16 accumulated 64-beam sweeps, ~2.0M raw pts/cloud), 0.25 m voxel -> "
+            "~120k pts, KNN k=10 covariances, GICP GN Huber(10) max_corr 2.0 <=20 iters")
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ the step (GPU arm)
+class PairPipeline:
+    def __init__(self, spx, q, n_src_raw, n_tgt_raw):
+        self.spx, self.q = spx, q
+        self.vg = spx.VoxelGrid(q, VOXEL)
+        params = spx.RegistrationParams()  # GICP, GN, max_corr 2.0, max_iter 20, criteria 1e-3 (reference defaults)
+        params.robust.type = spx.RobustLossType.HUBER
+        params.robust.default_scale = 10.0
+        self.reg = spx.Registration(q, params)
+        self.raw_src = spx.PointCloudShared(q)
+        self.raw_tgt = spx.PointCloudShared(q)
+        self.raw_src.adopt_points(spx.DeviceArray(q, (n_src_raw, 4), np.float32), n_src_raw)
+        self.raw_tgt.adopt_points(spx.DeviceArray(q, (n_tgt_raw, 4), np.float32), n_tgt_raw)
+        self.nn_s, self.nn_t = spx.KNNResult(), spx.KNNResult()
+        self.last = None
+
+    def upload(self, src_host, tgt_host, sync=True):
+        self.raw_src.points.upload(src_host, sync=False)
+        self.raw_tgt.points.upload(tgt_host, sync=False)
+        if sync:
+            self.q.wait()
+
+    def run(self):
+        spx, q = self.spx, self.q
+        src = self.vg.downsampling(self.raw_src)
+        tgt = self.vg.downsampling(self.raw_tgt)
+        tree_s = spx.KDTree.build(q, src)
+        tree_t = spx.KDTree.build(q, tgt)
+        tree_s.knn_search_async(src, K_COV, self.nn_s)
+        tree_t.knn_search_async(tgt, K_COV, self.nn_t)
+        spx.covariance.estimate(self.nn_s, src)
+        spx.covariance.estimate(self.nn_t, tgt)
+        res = self.reg.align(src, tgt, tree_t)  # synchronises (result comes back to the host)
+        self.last = (src, tgt, tree_t, res)
+        tree_s.close()
+        return res
+
+
+def cpu_pair(oracle, src_raw, tgt_raw):
+    """The reference's CPU path for one pair, restated (oracle port): std::sort voxel grid, host
+    KD-tree build, KD-tree KNN k=10, covariance, KD-tree NN + GICP linearise per iteration."""
+    src = oracle.voxel_downsample(src_raw, VOXEL, 1, unstable=True)
+    tgt = oracle.voxel_downsample(tgt_raw, VOXEL, 1, unstable=True)
+    ts, tt = oracle.KDTree(src), oracle.KDTree(tgt)
+    idx_s, _ = ts.knn(src, K_COV, mode=1)
+    idx_t, _ = tt.knn(tgt, K_COV, mode=1)
+    cs, ct = oracle.covariance(src, idx_s), oracle.covariance(tgt, idx_t)
+    P = oracle.default_params(reg_type=3, loss=1, opt_method=0, max_iterations=20, robust_default_scale=10.0,
+                              sum_mode=1, knn_mode=1)
+    return oracle.align(P, src, cs, tgt, ct, None, tt), len(src), len(tgt)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The SYCL build is
+    not possible in this image (no SYCL compiler, no Eigen: DESIGN.md), so this is the oracle port
+    with every host thread, on the same pair and settings; rank 0 alone runs it."""
+    if rank != 0:
+        return
+    import oracle
+    tgt_raw, src_raw, _ = synthetic.kitti_pair(42)
+    cores = oracle.num_threads()
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        cpu_pair(oracle, src_raw, tgt_raw)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps):
+        r, ns, nt = cpu_pair(oracle, src_raw, tgt_raw)
+        iters += r["iterations"] + 1
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "gicp_scan_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_src": ns, "n_tgt": nt, "icp_iterations_per_pair": iters / args.steps},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} whole pairs (full pipeline) on {cores} host threads"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_iter": 1e3 * dt / max(iters, 1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="spx", choices=["spx", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import sycl_points_b200 as spx  # fails loudly if libspx.so is missing / cannot be built
+
+    q = spx.DeviceQueue(local)
+    info = q.device_info()
+    tgt_raw, src_raw, T_gt = synthetic.kitti_pair(42 + rank)
+    pipe = PairPipeline(spx, q, len(src_raw), len(tgt_raw))
+    pin_src, pin_tgt = spx.PinnedArray(src_raw.shape), spx.PinnedArray(tgt_raw.shape)
+    pin_src.array[...] = src_raw
+    pin_tgt.array[...] = tgt_raw
+    pipe.upload(pin_src.array, pin_tgt.array)
+    flush = spx.DeviceArray(q, (256 << 20,), np.uint8)  # > 126 MB L2
+
+    def l2_flush():
+        spx._lib.check(spx.lib().spx_memset(q.handle, flush.ptr, 0, flush.nbytes))
+
+    def barrier():
+        q.wait()
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        res = pipe.run()
+    # ---------------- device-resident timing
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(spx.Event(), spx.Event()) for _ in range(args.steps)]
+    loop_ms, launches, iters_done, align_ms = [], 0, 0, []
+    barrier()
+    launches0 = spx.kernel_launch_count()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        l2_flush()
+        ev[s][0].record(q)
+        res = pipe.run()
+        ev[s][1].record(q)
+        t = pipe.reg.last_timing()
+        loop_ms.append(t["loop_ms"])
+        launches += t["launches"]
+        iters_done += t["iterations"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    gpu_launches = spx.kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_ms(b) for a, b in ev]
+    total_ms = float(np.sum(step_ms))
+    # ---------------- end to end from host buffers
+    for _ in range(2):
+        pipe.upload(pin_src.array, pin_tgt.array, sync=False)
+        pipe.run()
+    ev2 = [(spx.Event(), spx.Event()) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        l2_flush()
+        ev2[s][0].record(q)
+        pipe.upload(pin_src.array, pin_tgt.array, sync=False)  # H2D of this step's inputs (pinned)
+        res = pipe.run()                                        # result struct D2H + sync inside
+        ev2[s][1].record(q)
+    barrier()
+    e2e_ms = float(np.sum([a.elapsed_ms(b) for a, b in ev2]))
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = t.tolist()
+        c = torch.tensor([float(gpu_launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        gpu_launches = int(c.item())
+
+    src_ds, tgt_ds, _, res = pipe.last
+    ns, nt = src_ds.size(), tgt_ds.size()
+    value = world * args.steps / (total_ms * 1e-3)
+    e2e = world * args.steps / (e2e_ms * 1e-3)
+    alg_bytes = 192 * ns + 16 * nt
+    kern_ms = float(np.sum(loop_ms)) / max(iters_done, 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    dT = np.linalg.inv(T_gt.astype(np.float64)) @ res.T.astype(np.float64)
+
+    line = {
+        "metric": "gicp_scan_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_src_raw": int(len(src_raw)), "n_tgt_raw": int(len(tgt_raw)), "n_src": ns,
+                   "n_tgt": nt, "icp_iterations_per_pair": iters_done / args.steps,
+                   "l2": "flushed before every step (256 MiB memset outside the per-step events)",
+                   "gpu": info["name"], "sm_count": info["sm_count"],
+                   "pose_error_vs_gt_m": float(np.linalg.norm(dT[:3, 3]))},
+        "ms_per_iter": kern_ms,
+        "align_loop_ms": float(np.mean(loop_ms)),
+        "wall_s": wall,
+        "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(src_raw.nbytes + tgt_raw.nbytes),
+                "d2h_bytes_per_step": 428 + 2 * 8 + 4 * 8,
+                "note": "result struct + voxel/box counts + index-build scalars come back every step"},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "linearize_kernel<GICP, fused NN, solve>", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms,
+                     "note": "120k working set is L2-resident (SURVEY fact 3); per-launch time = event time of "
+                             "the iteration launches / iterations that did work"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        t0 = time.perf_counter()
+        n_cpu = 0
+        cores = oracle.num_threads()
+        while n_cpu < 1 or (time.perf_counter() - t0 < 10.0 and n_cpu < 4):
+            r, _, _ = cpu_pair(oracle, src_raw, tgt_raw)
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_cpu} whole pair(s), full pipeline, oracle port on {cores} threads",
+                                "ms_per_pair": 1e3 * dt / n_cpu, "icp_iterations": r['iterations'] + 1}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

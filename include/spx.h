@@ -242,6 +242,10 @@ SPX_API int spx_registration_align(spx_registration_t reg, const float* src_poin
                            const float* tgt_points, const float* tgt_covs, const float* tgt_normals, size_t nt,
                            spx_index_t target_index, const float* T_init_host, float robust_scale,
                            spx_registration_result* result_host, float* T_trace_host);
+/* CUDA-event time of the iteration kernels of the last align on this handle (from just before the
+ * first iteration launch to just after the last), the number of iteration kernels launched and
+ * the number of outer iterations that did work: bench.py's live per-launch duration. */
+SPX_API int spx_registration_last_timing(spx_registration_t reg, float* loop_ms, int32_t* launches, int32_t* iterations);
 /* neighbours cached by the last align / linearise on this handle (registration.hpp:365), device
  * pointers valid until the next call: used by compute_error_frozen-style callers */
 SPX_API int spx_registration_neighbors(spx_registration_t reg, const int32_t** nn_idx, const float** nn_dist, size_t* n);

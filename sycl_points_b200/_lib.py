@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
         "spx_registration_set_params": (C.c_int, [vp, C.POINTER(RegistrationParamsC)]),
         "spx_registration_align": (C.c_int, [vp, f32p, f32p, sz, f32p, f32p, f32p, sz, vp, hostf, C.c_float,
                                              C.POINTER(RegistrationResultC), hostf]),
+        "spx_registration_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                                                   C.POINTER(C.c_int32)]),
         "spx_registration_neighbors": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "spx_registration_shard_begin": (C.c_int, [vp, f32p, f32p, sz, f32p, f32p, f32p, sz, vp, hostf, C.c_float]),
         "spx_registration_shard_linearize": (C.c_int, [vp, vp]),

@@ -737,6 +737,12 @@ class Registration:
             out.trace = np.stack([_T_from16(t) for t in tr])
         return out
 
+    def last_timing(self) -> dict:
+        """CUDA-event time of the iteration kernels of the last Gauss-Newton align (bench.py)."""
+        ms, launches, iters = C.c_float(), C.c_int32(), C.c_int32()
+        check(_lib.lib().spx_registration_last_timing(self._h, C.byref(ms), C.byref(launches), C.byref(iters)))
+        return dict(loop_ms=ms.value, launches=launches.value, iterations=iters.value)
+
     # -- pieces usable with any KNNBase (the reference's tests inject host KNNs)
     def _linearize(self, source, target, nn: KNNResult, T, scale) -> LinearizedResult:
         H = np.empty(36, np.float32)

@@ -423,9 +423,9 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         ix->ncells = ncells;
         ix->occupied = (int64_t)occupied;
 
-        SPX_CUDA(cudaMalloc(&start_dev, (ncells + 1) * 4));
+        SPX_CUDA(cudaMallocAsync(&start_dev, (ncells + 1) * 4, st));
         ix->start = start_dev;
-        SPX_CUDA(cudaMalloc(&ix->sorted, (size_t)std::max<uint32_t>(bb.finite, 1) * sizeof(float4)));
+        SPX_CUDA(cudaMallocAsync(&ix->sorted, (size_t)std::max<uint32_t>(bb.finite, 1) * sizeof(float4), st));
         exclusive_scan_u32(st, counts, start_dev, ncells + 1, scan_tmp, nullptr);
         SPX_CUDA(cudaMemsetAsync(counts, 0, (ncells + 1) * 4, st));  // reuse as per-cell cursor
         cell_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, cell_id, start_dev, counts, ix->sorted);
@@ -442,9 +442,8 @@ int spx_index_destroy(spx_index_t index) {
     return guard([&] {
         if (!index) return;
         DeviceGuard g(index->q->device);
-        cudaStreamSynchronize(index->q->stream);
-        if (index->sorted) cudaFree(index->sorted);
-        if (index->start) cudaFree(index->start);
+        if (index->sorted) cudaFreeAsync(index->sorted, index->q->stream);
+        if (index->start) cudaFreeAsync(index->start, index->q->stream);
         delete index;
     });
 }

@@ -573,6 +573,11 @@ struct spx_registration_s {
     int shard_reg = 0;
     int shard_iter = 0;
     bool shard_active = false;
+    // live timing of the iteration kernels (bench.py roofline)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    int last_iterations = 0;
+    bool timed = false;
 };
 
 namespace {
@@ -584,6 +589,9 @@ void reg_free(spx_registration_t r) {
     };
     f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist);
     f(r->src_c0); f(r->src_c1); f(r->tgt_c0); f(r->tgt_c1); f(r->trace);
+    if (r->ev0) cudaEventDestroy(r->ev0);
+    if (r->ev1) cudaEventDestroy(r->ev1);
+    r->ev0 = r->ev1 = nullptr;
 }
 
 template <typename T>
@@ -996,6 +1004,8 @@ int spx_registration_create(spx_queue_t q, const spx_registration_params* params
             SPX_CUDA(cudaMemsetAsync(r->ticket, 0, 64, q->stream));
             r->max_blocks = (unsigned)q->sm_count * 4;
             SPX_CUDA(cudaMalloc(&r->partials, (size_t)r->max_blocks * 32 * sizeof(double)));
+            SPX_CUDA(cudaEventCreate(&r->ev0));
+            SPX_CUDA(cudaEventCreate(&r->ev1));
         } catch (...) {
             reg_free(r);
             delete r;
@@ -1019,6 +1029,19 @@ int spx_registration_set_params(spx_registration_t reg, const spx_registration_p
     return guard([&] {
         SPX_REQUIRE(reg && params, "[Registration::set_params] null argument");
         reg->P = *params;
+    });
+}
+
+int spx_registration_last_timing(spx_registration_t reg, float* loop_ms, int32_t* launches, int32_t* iterations) {
+    return guard([&] {
+        SPX_REQUIRE(reg, "[Registration::last_timing] null handle");
+        SPX_REQUIRE(reg->timed, "[Registration::last_timing] no timed Gauss-Newton align on this handle yet");
+        DeviceGuard g(reg->q->device);
+        float ms = 0.0f;
+        SPX_CUDA(cudaEventElapsedTime(&ms, reg->ev0, reg->ev1));
+        if (loop_ms) *loop_ms = ms;
+        if (launches) *launches = reg->last_launches;
+        if (iterations) *iterations = reg->last_iterations;
     });
 }
 
@@ -1057,14 +1080,20 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         double* hsums = reinterpret_cast<double*>(reinterpret_cast<char*>(hs) + sizeof(RegState) + 64);
         const int max_it = P.max_iterations;
 
+        reg->timed = false;
         if (P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
+            SPX_CUDA(cudaEventRecord(reg->ev0, st));
             for (int it = 0; it < max_it; ++it) {
                 a.iter_index = it;
                 launch_linearize<1, true>(c.reg, a, c.blocks, st);
             }
+            SPX_CUDA(cudaEventRecord(reg->ev1, st));
             SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, st));
             q->sync();
             if (max_it > 0) fill_result(*hs, R);
+            reg->timed = max_it > 0;
+            reg->last_launches = max_it;
+            reg->last_iterations = max_it > 0 ? hs->iterations + 1 : 0;
             if (T_trace_host && max_it > 0) {
                 // iterations never run (converged earlier) repeat the final pose
                 SPX_CUDA(cudaMemcpyAsync(T_trace_host, reg->trace, (size_t)(hs->iterations + 1) * 16 * sizeof(float),

@@ -104,6 +104,12 @@ static int queue_create(int device, void* stream, bool own, spx_queue_t* out) {
             q->stream = static_cast<cudaStream_t>(stream);
         }
         SPX_CUDA(cudaDeviceGetAttribute(&q->sm_count, cudaDevAttrMultiProcessorCount, device));
+        // spx_malloc / spx_free are stream-ordered pool allocations: keep freed blocks cached so a
+        // per-scan alloc/free cycle never reaches the driver
+        cudaMemPool_t pool;
+        SPX_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        SPX_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         q->arena_reserve(8 << 20);
         *out = q;
     });
@@ -148,7 +154,7 @@ int spx_malloc(spx_queue_t q, size_t bytes, void** out) {
         DeviceGuard g(q->device);
         *out = nullptr;
         if (bytes == 0) return;
-        SPX_CUDA(cudaMalloc(out, bytes));
+        SPX_CUDA(cudaMallocAsync(out, bytes, q->stream));
     });
 }
 
@@ -157,8 +163,7 @@ int spx_free(spx_queue_t q, void* ptr) {
         SPX_REQUIRE(q, "[spx_free] null queue");
         if (!ptr) return;
         DeviceGuard g(q->device);
-        SPX_CUDA(cudaStreamSynchronize(q->stream));
-        SPX_CUDA(cudaFree(ptr));
+        SPX_CUDA(cudaFreeAsync(ptr, q->stream));  // ordered after everything already enqueued
     });
 }
 

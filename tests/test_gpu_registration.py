@@ -37,8 +37,10 @@ def pair(spx, q, bundled):
 
 def pose_delta(Ta, Tb):
     d = np.linalg.inv(Ta.astype(np.float64)) @ Tb.astype(np.float64)
-    ang = np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1))
-    return np.linalg.norm(d[:3, 3]), ang
+    # sin(angle) from the skew part: accurate for the tiny angles compared here (arccos of the
+    # trace loses half the digits near identity)
+    w = 0.5 * np.array([d[2, 1] - d[1, 2], d[0, 2] - d[2, 0], d[1, 0] - d[0, 1]])
+    return np.linalg.norm(d[:3, 3]), float(np.arcsin(min(1.0, np.linalg.norm(w))))
 
 
 def rel(a, b):
