@@ -167,12 +167,18 @@ SPX_API int spx_index_build(spx_queue_t q, const float* targets, size_t nt, floa
 SPX_API int spx_index_destroy(spx_index_t index);
 /* KNNBase::knn_search_async(queries, k, result, depends, transT) — knn.hpp:22-24,
  * kdtree.hpp:203-224,424-562.  Exact: identical to spx_knn_bruteforce on the same inputs
- * (ring search with a proven stop bound, brute-force pass for queries the rings cannot bound).
+ * (ring search with a proven stop bound over a hierarchy of grids).
  * 1 <= k <= 128 (the reference throws above 100, kdtree.hpp:221-223).  Asynchronous. */
 SPX_API int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, const float* T_host, int32_t* idx,
                   float* dist);
 /* introspection for tests / DESIGN.md: cell size, grid dims[3], occupied cells, points */
 SPX_API int spx_index_info(spx_index_t index, float* cell_size, int32_t* dims3, int64_t* occupied_cells, int64_t* n_points);
+/* tuning aid: per-query work counters of the k = 1 search, stats4[q] = {segments, candidate points,
+ * shells, last level}; max_radius <= 0 = unbounded */
+SPX_API int spx_index_nn_stats(spx_index_t index, const float* queries, size_t nq, const float* T_host, float max_radius,
+                       uint32_t* stats4);
+/* number of grid levels (each 8x coarser than the previous) the index keeps */
+SPX_API int spx_index_levels(spx_index_t index, int32_t* n_levels);
 
 /* ------------------------------------------------------------------ features
  * covariance::estimate_async(queue, neighbors, points, covs) — I/algorithms/feature/covariance.hpp:16-47,260-292 */

@@ -347,7 +347,10 @@ class KDTree(KNNBase):
         dims = (C.c_int32 * 3)()
         occ, npts = C.c_int64(), C.c_int64()
         check(_lib.lib().spx_index_info(self._h, C.byref(cell), dims, C.byref(occ), C.byref(npts)))
-        return dict(cell_size=cell.value, dims=tuple(dims), occupied_cells=occ.value, n_points=npts.value)
+        lv = C.c_int32()
+        check(_lib.lib().spx_index_levels(self._h, C.byref(lv)))
+        return dict(cell_size=cell.value, dims=tuple(dims), occupied_cells=occ.value, n_points=npts.value,
+                    levels=lv.value)
 
     def knn_search_async(self, queries: PointCloudShared, k: int, result: KNNResult, depends=None, transT=None):
         if k > 128:

@@ -15,7 +15,7 @@ constexpr int FEAT_THREADS = 128;
 __device__ __forceinline__ bool estimate_cov(const float4* __restrict__ pts, const int32_t* __restrict__ row, int k,
                                              Sym3& C) {
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    float oxx = 0.f, oxy = 0.f, oxz = 0.f, oyx = 0.f, oyy = 0.f, oyz = 0.f, ozx = 0.f, ozy = 0.f, ozz = 0.f;
+    float oxx = 0.f, oxy = 0.f, oxz = 0.f, oyy = 0.f, oyz = 0.f, ozz = 0.f;
     int cnt = 0;
     for (int j = 0; j < k; ++j) {
         const int id = __ldg(row + j);
@@ -31,7 +31,6 @@ __device__ __forceinline__ bool estimate_cov(const float4* __restrict__ pts, con
         ozz = __fadd_rn(ozz, __fmul_rn(p.z, p.z));
         ++cnt;
     }
-    (void)oyx; (void)ozx; (void)ozy;
     if (cnt < 4) {
         C.xx = C.yy = C.zz = 1.0f;
         C.xy = C.xz = C.yz = 0.0f;

@@ -18,6 +18,12 @@
 
 namespace spx {
 
+constexpr int GRID_MAX_LEVELS = 6;
+constexpr int GRID_LEVEL_FACTOR = 4;   // cell edge ratio between consecutive levels
+constexpr int GRID_LEVEL_RINGS = 2;    // shells (beyond the query's own cell) searched on a level before moving
+                                       // to the next coarser one: empty space is crossed in coarse steps, so a
+                                       // query with nothing nearby costs a few dozen row look-ups per level
+
 struct GridView {
     float ox, oy, oz;    // grid origin (bbox min of the indexed points)
     float cell, inv;     // cell edge and its reciprocal
@@ -26,6 +32,18 @@ struct GridView {
     const uint32_t* __restrict__ start;  // [dx*dy*dz + 1] first sorted position of each cell
     const float4* __restrict__ pts;      // sorted points, w = original index (int bits)
     uint32_t n;                          // indexed (finite) points
+};
+
+// LiDAR clouds span three orders of magnitude in density (ground rings metres apart at range,
+// centimetres near the sensor), so one cell size cannot serve every query: the index keeps up to
+// GRID_MAX_LEVELS independent grids over the same points, each GRID_LEVEL_FACTOR coarser than the
+// previous one.  A query runs the ring search on the finest level for a few shells and, if the stop
+// bound has not been met, starts over on the next level (the candidate list carries over; re-offered
+// points are recognised by their index).  The coarsest level is searched until its whole grid has
+// been seen, so every query terminates with the exact answer and no brute-force pass is needed.
+struct GridLevels {
+    int n_levels;
+    GridView lv[GRID_MAX_LEVELS];
 };
 
 #ifdef __CUDACC__
@@ -66,98 +84,156 @@ struct Best1 {
 };
 
 struct BestK {
-    float* d;   // [k]
-    int* i;     // [k]
+    float* d;   // element j at d[j * stride]
+    int* i;
     int k;
-    float wd;   // cached d[k-1]
-    int wi;     // cached i[k-1]
+    int stride;
+    float wd;   // cached k-th best
+    int wi;
     __device__ __forceinline__ void init() {
-        for (int j = 0; j < k; ++j) { d[j] = FLT_MAX; i[j] = -1; }
+        for (int j = 0; j < k; ++j) { d[j * stride] = FLT_MAX; i[j * stride] = -1; }
         wd = FLT_MAX; wi = -1;
     }
     __device__ __forceinline__ float worst() const { return wd; }
     __device__ __forceinline__ void offer(float ds, int idx, uint32_t) {
         if (!lex_less(ds, idx, wd, wi)) return;
         int pos = k - 1;
-        while (pos > 0 && lex_less(ds, idx, d[pos - 1], i[pos - 1])) {
-            d[pos] = d[pos - 1];
-            i[pos] = i[pos - 1];
-            --pos;
+        while (pos > 0 && lex_less(ds, idx, d[(pos - 1) * stride], i[(pos - 1) * stride])) --pos;
+        // the same point offered again by a coarser level lands right behind its own entry
+        if (pos > 0 && i[(pos - 1) * stride] == idx) return;
+        for (int j = k - 1; j > pos; --j) {
+            d[j * stride] = d[(j - 1) * stride];
+            i[j * stride] = i[(j - 1) * stride];
         }
-        d[pos] = ds;
-        i[pos] = idx;
-        wd = d[k - 1];
-        wi = i[k - 1];
+        d[pos * stride] = ds;
+        i[pos * stride] = idx;
+        wd = d[(k - 1) * stride];
+        wi = i[(k - 1) * stride];
     }
 };
 
-constexpr int GRID_SEG_CHUNK = 8;
+constexpr int GRID_SEG_CHUNK = 9;  // the merged first pass (3x3 rows) fits one chunk
+constexpr int GRID_BATCH = 4;  // candidate loads in flight per thread
+
+// optional per-query work counters (spx_index_knn_stats, used to tune the index); the default
+// policy compiles to nothing
+struct NoStats {
+    __device__ __forceinline__ void segment(uint32_t) {}
+    __device__ __forceinline__ void shell() {}
+    __device__ __forceinline__ void level(int) {}
+};
+struct CountStats {
+    uint32_t segs = 0, cands = 0, shells = 0, last_level = 0;
+    __device__ __forceinline__ void segment(uint32_t n) { ++segs; cands += n; }
+    __device__ __forceinline__ void shell() { ++shells; }
+    __device__ __forceinline__ void level(int l) { last_level = l; }
+};
 
 // Ring search.  max_radius: stop expanding once every point within it has been seen (ICP use:
 // correspondences farther than max_correspondence_distance are rejected anyway,
 // registration.hpp:584); pass +inf for an unbounded exact search.  r_max: shells after which an
 // unbounded search gives up (returns false -> caller falls back to a full scan).
-template <typename Best>
-__device__ inline bool grid_search(const GridView& g, float qx, float qy, float qz, Best& best, float max_radius,
-                                   int r_max) {
+template <typename Best, typename Stats = NoStats>
+__device__ __noinline__ bool grid_search(const GridView& g, float qx, float qy, float qz, Best& best, float max_radius,
+                                         int r_begin, int r_max, Stats* stats = nullptr) {
     const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
     const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
     const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
     const float INF = __int_as_float(0x7f800000);
     // rounding allowance: grid part (build) + the query's own magnitude (q - slab coordinate)
     const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+    // bounded searches never need anything beyond max_radius (+ allowance): prune against it too
+    const float reach = max_radius + margin;
+    const float reach2 = reach < 1.8e19f ? __fmul_rn(reach, reach) : INF;
 
     uint32_t seg_lo[GRID_SEG_CHUNK], seg_hi[GRID_SEG_CHUNK];
     int nseg = 0;
 
+    // Two-phase processing of up to GRID_SEG_CHUNK cell ranges: (1) all `start` look-ups are issued
+    // back to back, (2) the candidate points of ALL ranges are walked as one flat stream in batches
+    // of GRID_BATCH loads issued before any distance is evaluated.  A query's time is a chain of
+    // L2 round trips, so the number of dependent trips — not the arithmetic — is what is minimised.
     auto flush = [&]() {
-        uint32_t s[GRID_SEG_CHUNK], e[GRID_SEG_CHUNK];
+        uint32_t ls[GRID_SEG_CHUNK], le[GRID_SEG_CHUNK];
 #pragma unroll
         for (int t = 0; t < GRID_SEG_CHUNK; ++t) {
-            s[t] = 0; e[t] = 0;
+            uint32_t a = 0, b = 0;
             if (t < nseg) {
-                s[t] = __ldg(g.start + seg_lo[t]);
-                e[t] = __ldg(g.start + seg_hi[t] + 1);
+                a = __ldg(g.start + seg_lo[t]);
+                b = __ldg(g.start + seg_hi[t] + 1);
             }
+            ls[t] = a;
+            le[t] = b;
         }
+        int t = 0;
+        uint32_t j = ls[0], end = le[0];
+        if (stats)
+            for (int u = 0; u < nseg; ++u) stats->segment(le[u] - ls[u]);
+        while (t < nseg) {
+            uint32_t addr[GRID_BATCH];
+            float4 p[GRID_BATCH];
 #pragma unroll
-        for (int t = 0; t < GRID_SEG_CHUNK; ++t) {
-            if (t < nseg) {
-#pragma unroll 4
-                for (uint32_t j = s[t]; j < e[t]; ++j) {
-                    const float4 p = __ldg(g.pts + j);
-                    const float ds = dist_sq(qx, qy, qz, p.x, p.y, p.z);
-                    best.offer(ds, __float_as_int(p.w), j);
+            for (int u = 0; u < GRID_BATCH; ++u) {
+                while (t < nseg && j >= end) {
+                    ++t;
+                    if (t < nseg) {
+                        j = ls[t];
+                        end = le[t];
+                    }
                 }
+                addr[u] = 0xffffffffu;
+                if (t < nseg) addr[u] = j++;
             }
+#pragma unroll
+            for (int u = 0; u < GRID_BATCH; ++u)
+                if (addr[u] != 0xffffffffu) p[u] = __ldg(g.pts + addr[u]);
+#pragma unroll
+            for (int u = 0; u < GRID_BATCH; ++u)
+                if (addr[u] != 0xffffffffu)
+                    best.offer(dist_sq(qx, qy, qz, p[u].x, p[u].y, p[u].z), __float_as_int(p[u].w), addr[u]);
         }
         nseg = 0;
     };
 
-    for (int r = 0;; ++r) {
+    // The first pass covers shells 0 and 1 together (the 3x3 block of rows around the query's cell,
+    // each row one contiguous range of 3 cells): for the dense part of a cloud that is the whole
+    // search, with a fixed trip count and no pruning arithmetic.  Later passes add one shell each
+    // and prune rows / trim their x range against the best distance known so far.
+    for (int r = r_begin;; ++r) {
+        const bool merged = (r == 1);
         const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
         const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
         for (int zz = z0; zz <= z1; ++zz) {
-            const float gz = axis_gap(qz, g.oz, g.cell, zz);
             const bool ez = (zz - cz == r) || (cz - zz == r);
             for (int yy = y0; yy <= y1; ++yy) {
-                const float gy = axis_gap(qy, g.oy, g.cell, yy);
-                // prune rows that cannot hold anything better than the current k-th best
-                const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
-                if (__fmul_rn(gyz, gyz) > best.worst()) continue;
-                const bool edge = ez || (yy - cy == r) || (cy - yy == r);
+                const bool edge = merged || ez || (yy - cy == r) || (cy - yy == r);
+                int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
+                const float lim2 = fminf(best.worst(), reach2);
+                if (lim2 < 1.0e30f) {
+                    // prune rows that cannot hold anything better than the current k-th best, and
+                    // cells of the row farther along x than sqrt(lim2 - gap^2) (+ allowance)
+                    const float gz = axis_gap(qz, g.oz, g.cell, zz);
+                    const float gy = axis_gap(qy, g.oy, g.cell, yy);
+                    const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
+                    const float gyz2 = __fmul_rn(gyz, gyz);
+                    if (gyz2 > lim2) continue;
+                    const float w = sqrtf(lim2 - gyz2) + margin;
+                    xa = max(xa, grid_coord(qx - w, g.ox, g.inv, g.dx));
+                    xb = min(xb, grid_coord(qx + w, g.ox, g.inv, g.dx));
+                    if (xa > xb) continue;
+                }
                 const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
                 if (edge) {
-                    const int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
                     seg_lo[nseg] = row + xa;
                     seg_hi[nseg] = row + xb;
                     if (++nseg == GRID_SEG_CHUNK) flush();
                 } else {
-                    if (cx - r >= 0) {
+                    // interior row of a later shell: only the two end cells are new
+                    if (cx - r >= xa) {
                         seg_lo[nseg] = seg_hi[nseg] = row + (cx - r);
                         if (++nseg == GRID_SEG_CHUNK) flush();
                     }
-                    if (cx + r <= g.dx - 1) {
+                    if (cx + r <= xb) {
                         seg_lo[nseg] = seg_hi[nseg] = row + (cx + r);
                         if (++nseg == GRID_SEG_CHUNK) flush();
                     }
@@ -165,6 +241,7 @@ __device__ inline bool grid_search(const GridView& g, float qx, float qy, float 
             }
         }
         if (nseg) flush();
+        if (stats) stats->shell();
 
         const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, r, g.dx),
                                         shell_bound_axis(qy, g.oy, g.cell, cy, r, g.dy)),
@@ -177,6 +254,66 @@ __device__ inline bool grid_search(const GridView& g, float qx, float qy, float 
     }
 }
 
+// First pass on the finest level: the 3x3x3 block of cells around the query's cell, i.e. 9 rows of
+// 3 contiguous cells.  No pruning arithmetic, fixed trip counts, all 18 `start` look-ups issued at
+// once; for queries inside the dense part of a cloud this is the entire search.  Returns true when
+// the stop bound of shell 1 is already met.
+template <typename Best, typename Stats = NoStats>
+__device__ __forceinline__ bool grid_first_pass(const GridView& g, float qx, float qy, float qz, Best& best,
+                                                float max_radius, Stats* stats = nullptr) {
+    const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
+    const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
+    const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
+    const int xa = max(cx - 1, 0), xb = min(cx + 1, g.dx - 1);
+    uint32_t ls[9], le[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int zz = cz + (t / 3) - 1, yy = cy + (t % 3) - 1;
+        const bool ok = zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy;
+        const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
+        ls[t] = ok ? __ldg(g.start + row + xa) : 0u;
+        le[t] = ok ? __ldg(g.start + row + xb + 1) : 0u;
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        if (stats) stats->segment(le[t] - ls[t]);
+        for (uint32_t j = ls[t]; j < le[t]; j += 4) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j + u < le[t]) p[u] = __ldg(g.pts + j + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j + u < le[t])
+                    best.offer(dist_sq(qx, qy, qz, p[u].x, p[u].y, p[u].z), __float_as_int(p[u].w), j + u);
+        }
+    }
+    if (stats) stats->shell();
+    const float INF = __int_as_float(0x7f800000);
+    const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+    const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, 1, g.dx),
+                                    shell_bound_axis(qy, g.oy, g.cell, cy, 1, g.dy)),
+                              shell_bound_axis(qz, g.oz, g.cell, cz, 1, g.dz));
+    if (bound == INF) return true;
+    const float bs = bound - margin;
+    return (bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) || bs >= max_radius;
+}
+
+// Exact search over the level hierarchy (see GridLevels).  Always terminates with the full answer.
+template <typename Best, typename Stats = NoStats>
+__device__ __forceinline__ void grid_search_levels(const GridLevels& g, float qx, float qy, float qz, Best& best,
+                                                   float max_radius, Stats* stats = nullptr) {
+    if (stats) stats->level(0);
+    if (grid_first_pass(g.lv[0], qx, qy, qz, best, max_radius, stats)) return;
+    for (int l = 0; l < g.n_levels; ++l) {
+        const bool last = (l == g.n_levels - 1);
+        if (stats) stats->level(l);
+        if (grid_search(g.lv[l], qx, qy, qz, best, max_radius, l == 0 ? 2 : 1, last ? (1 << 20) : GRID_LEVEL_RINGS,
+                        stats))
+            return;
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace spx
@@ -186,9 +323,9 @@ struct spx_index_s {
     spx_queue_t q = nullptr;
     size_t n_total = 0;   // points given to build
     uint32_t n = 0;       // finite points indexed
-    float4* sorted = nullptr;
-    uint32_t* start = nullptr;
-    size_t ncells = 0;
-    int64_t occupied = 0;
-    spx::GridView view{};
+    float4* sorted[spx::GRID_MAX_LEVELS] = {};
+    uint32_t* start[spx::GRID_MAX_LEVELS] = {};
+    size_t ncells[spx::GRID_MAX_LEVELS] = {};
+    int64_t occupied = 0;  // occupied cells of the finest level
+    spx::GridLevels levels{};
 };

@@ -14,6 +14,8 @@
 //    fp32 sycl::reduction order.
 //  * Gauss-Newton never returns to the host inside the loop: the last block also solves the 6x6
 //    system (fp64 LDL^T) and advances the pose that the next launch reads.
+#include <cooperative_groups.h>
+
 #include <cmath>
 #include <cstring>
 
@@ -63,7 +65,7 @@ struct LinArgs {
     const float* dist_in;
     int32_t* idx_out;
     float* dist_out;
-    GridView grid;
+    GridLevels grid;
     // pose
     RegState* state;
     Xform T;
@@ -171,71 +173,70 @@ __device__ __forceinline__ Sym3 gicp_minv(const Xform& T, const Sym3& cs, const 
     return sym_inverse(M);
 }
 
-struct Terms {
-    float H[N_H];
-    float b[6];
-    float e2;
-    float rn;
-};
-
+// One correspondence: factor terms (factor.hpp:130-278), robust weight (robust.hpp:56-90), and
+// the weighted accumulation of registration.hpp:613-626,653-659.  The residual norm and weight are
+// formed first, then every H / b entry is computed and added straight into its accumulator, so no
+// 27-entry temporary is ever live (register pressure, not arithmetic, limits this kernel).
 template <int REG>
-__device__ __forceinline__ void point_terms(const Xform& T, const float4 ps, const Sym3& cs, const float4 pt,
-                                            const Sym3& ct, const float4 nrm, Terms& o) {
+__device__ __forceinline__ void accumulate_point(const Xform& T, const float4 ps, const Sym3& cs, const float4 pt,
+                                                 const Sym3& ct, const float4 nrm, int loss, float scale,
+                                                 float* acc) {
     const float4 tp = transform_point(T, ps);
     const float r0 = __fsub_rn(pt.x, tp.x), r1 = __fsub_rn(pt.y, tp.y), r2 = __fsub_rn(pt.z, tp.z);
     const Jac J = se3_jacobian(T, ps);
     if (REG == SPX_REG_POINT_TO_POINT) {  // factor.hpp:130-149
+        const float e2 = chain3(r0, r0, r1, r1, r2, r2);
+        const float rn = __fsqrt_rn(e2);
+        const float w = robust_weight(loss, rn, scale);
         int t = 0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
 #pragma unroll
-            for (int c = a; c < 6; ++c) o.H[t++] = chain3(J.j[0][a], J.j[0][c], J.j[1][a], J.j[1][c], J.j[2][a], J.j[2][c]);
-            o.b[a] = chain3(J.j[0][a], r0, J.j[1][a], r1, J.j[2][a], r2);
+            for (int c = a; c < 6; ++c, ++t)
+                acc[t] = __fadd_rn(acc[t], __fmul_rn(w, chain3(J.j[0][a], J.j[0][c], J.j[1][a], J.j[1][c], J.j[2][a], J.j[2][c])));
+            acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(J.j[0][a], r0, J.j[1][a], r1, J.j[2][a], r2)));
         }
-        o.e2 = chain3(r0, r0, r1, r1, r2, r2);
-        o.rn = __fsqrt_rn(o.e2);
+        acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
     } else if (REG == SPX_REG_POINT_TO_PLANE) {  // factor.hpp:172-210
         const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
+        const float rn = fabsf(d);
+        const float w = robust_weight(loss, rn, scale);
         const float n[3] = {nrm.x, nrm.y, nrm.z};
         float row[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) row[c] = chain3(n[0], J.j[0][c], n[1], J.j[1][c], n[2], J.j[2][c]);
-        float Jp[3][6], pe[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            pe[i] = __fmul_rn(n[i], d);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) Jp[i][c] = __fmul_rn(n[i], row[c]);
-        }
+        const float pe0 = __fmul_rn(n[0], d), pe1 = __fmul_rn(n[1], d), pe2 = __fmul_rn(n[2], d);
         int t = 0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
+            const float ja0 = __fmul_rn(n[0], row[a]), ja1 = __fmul_rn(n[1], row[a]), ja2 = __fmul_rn(n[2], row[a]);
 #pragma unroll
-            for (int c = a; c < 6; ++c) o.H[t++] = chain3(Jp[0][a], Jp[0][c], Jp[1][a], Jp[1][c], Jp[2][a], Jp[2][c]);
-            o.b[a] = chain3(Jp[0][a], pe[0], Jp[1][a], pe[1], Jp[2][a], pe[2]);
+            for (int c = a; c < 6; ++c, ++t)
+                acc[t] = __fadd_rn(acc[t], __fmul_rn(w, chain3(ja0, __fmul_rn(n[0], row[c]), ja1, __fmul_rn(n[1], row[c]),
+                                                             ja2, __fmul_rn(n[2], row[c]))));
+            acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(ja0, pe0, ja1, pe1, ja2, pe2)));
         }
-        o.e2 = __fmul_rn(d, d);
-        o.rn = fabsf(d);
+        acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
     } else {  // GICP, factor.hpp:239-278
         const Sym3 Mi = gicp_minv(T, cs, ct);
-        float JTM[6][3];
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                JTM[a][j] = chain3(J.j[0][a], sym_at(Mi, 0, j), J.j[1][a], sym_at(Mi, 1, j), J.j[2][a], sym_at(Mi, 2, j));
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-#pragma unroll
-            for (int c = a; c < 6; ++c) o.H[t++] = chain3(JTM[a][0], J.j[0][c], JTM[a][1], J.j[1][c], JTM[a][2], J.j[2][c]);
-            o.b[a] = chain3(JTM[a][0], r0, JTM[a][1], r1, JTM[a][2], r2);
-        }
         const float m0 = chain3(Mi.xx, r0, Mi.xy, r1, Mi.xz, r2);
         const float m1 = chain3(Mi.xy, r0, Mi.yy, r1, Mi.yz, r2);
         const float m2 = chain3(Mi.xz, r0, Mi.yz, r1, Mi.zz, r2);
-        o.e2 = chain3(r0, m0, r1, m1, r2, m2);
-        o.rn = __fsqrt_rn(o.e2);
+        const float e2 = chain3(r0, m0, r1, m1, r2, m2);
+        const float rn = __fsqrt_rn(e2);
+        const float w = robust_weight(loss, rn, scale);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const float q0 = chain3(J.j[0][a], Mi.xx, J.j[1][a], Mi.xy, J.j[2][a], Mi.xz);  // (J^T M^-1)(a, :)
+            const float q1 = chain3(J.j[0][a], Mi.xy, J.j[1][a], Mi.yy, J.j[2][a], Mi.yz);
+            const float q2 = chain3(J.j[0][a], Mi.xz, J.j[1][a], Mi.yz, J.j[2][a], Mi.zz);
+#pragma unroll
+            for (int c = a; c < 6; ++c, ++t)
+                acc[t] = __fadd_rn(acc[t], __fmul_rn(w, chain3(q0, J.j[0][c], q1, J.j[1][c], q2, J.j[2][c])));
+            acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(q0, r0, q1, r1, q2, r2)));
+        }
+        acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
     }
 }
 
@@ -385,9 +386,46 @@ __device__ bool reduce_to_sums(const float* acc, int nacc, uint32_t inl, double*
     return true;
 }
 
-// MODE 0: linearise from given correspondences.  MODE 1: nearest neighbour through the grid index
-// fused in front (writes idx/dist for the frozen-neighbour error passes).  SOLVE: the last block
-// also performs the Gauss-Newton update of the device-resident pose.
+// Per-thread accumulation over a grid-stride slice of the source points.
+// MODE 0: correspondences given.  MODE 1: nearest neighbour through the index fused in front
+// (bounded by max_correspondence_distance; writes idx/dist for the frozen-neighbour error passes).
+template <int REG, int MODE>
+__device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Xform& T, float* acc, uint32_t& inl) {
+    const int32_t* idx = a.idx_in;
+    const float* dist = a.dist_in;
+    if (MODE == 1) {
+        // phase 1: correspondences for this thread's points.  Kept apart from the factor arithmetic
+        // so that the 28 accumulators are not live across the index traversal (registers = max of the
+        // two phases instead of their sum); the thread re-reads its own writes in phase 2.
+        for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
+            const float4 q = transform_point(T, __ldg(a.src_pts + i));
+            Best1 best;
+            best.init();
+            if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && a.grid.lv[0].n > 0)
+                grid_search_levels(a.grid, q.x, q.y, q.z, best, a.max_corr);
+            a.idx_out[i] = best.i;
+            a.dist_out[i] = best.d;
+        }
+        idx = a.idx_out;
+        dist = a.dist_out;
+    }
+    for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
+        const float d = MODE == 1 ? __ldcg(dist + i) : __ldg(dist + i);
+        const int ti = MODE == 1 ? __ldcg(idx + i) : __ldg(idx + i);
+        if (d > a.max_corr_sq || ti < 0) continue;  // registration.hpp:584 (+ guard for the -1 fill)
+        const float4 ps = __ldg(a.src_pts + i);
+        const float4 pt = __ldg(a.tgt_pts + ti);
+        const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        Sym3 cs, ct;
+        load_covs<REG>(a, i, ti, cs, ct);
+        accumulate_point<REG>(T, ps, cs, pt, ct, nrm, a.loss, a.scale, acc);
+        ++inl;
+    }
+}
+
+// One launch = one linearisation.  SOLVE: the last block also performs the Gauss-Newton update of
+// the device-resident pose (used by callers that interleave their own work between iterations).
 template <int REG, int MODE, bool SOLVE>
 __global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs a) {
     __shared__ double fold[LIN_WARPS][32];
@@ -401,44 +439,78 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs
 #pragma unroll
     for (int v = 0; v < N_ACC; ++v) acc[v] = 0.0f;
     uint32_t inl = 0;
-
-    for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
-        const float4 ps = __ldg(a.src_pts + i);
-        float d;
-        int ti;
-        if (MODE == 1) {
-            const float4 q = transform_point(T, ps);
-            Best1 best;
-            best.init();
-            if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && a.grid.n > 0)
-                grid_search(a.grid, q.x, q.y, q.z, best, a.max_corr, 1 << 20);
-            d = best.d;
-            ti = best.i;
-            a.idx_out[i] = ti;
-            a.dist_out[i] = d;
-        } else {
-            d = __ldg(a.dist_in + i);
-            ti = __ldg(a.idx_in + i);
-        }
-        if (d > a.max_corr_sq || ti < 0) continue;  // registration.hpp:584 (+ guard for the -1 fill)
-        const float4 pt = __ldg(a.tgt_pts + ti);
-        const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
-                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        Sym3 cs, ct;
-        load_covs<REG>(a, i, ti, cs, ct);
-        Terms t;
-        point_terms<REG>(T, ps, cs, pt, ct, nrm, t);
-        const float w = robust_weight(a.loss, t.rn, a.scale);
-#pragma unroll
-        for (int v = 0; v < N_H; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(w, t.H[v]));
-#pragma unroll
-        for (int v = 0; v < 6; ++v) acc[S_B + v] = __fadd_rn(acc[S_B + v], __fmul_rn(w, t.b[v]));
-        acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(a.loss, t.rn, a.scale));
-        ++inl;
-    }
+    lin_accumulate<REG, MODE>(a, T, acc, inl);
     if (!reduce_to_sums(acc, N_ACC, inl, a.partials, a.ticket, a.sums_out, fold, red)) return;
     if (SOLVE && threadIdx.x == 0)
         gn_update(a.state, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, a.iter_index, a.trace);
+}
+
+// The whole Gauss-Newton align() as ONE cooperative launch (registration.hpp:227-272 + :803-828):
+// every iteration is nearest neighbour + linearise + block reduce, one grid-wide barrier, then
+// every block folds the per-block partials in the same fixed order and solves the same 6x6 system
+// (bitwise identical results, so no second barrier and no broadcast), advances its copy of the
+// pose and goes on.  Block 0 records the state for the host.  Partials are double-buffered by
+// iteration parity so a block that races ahead never overwrites what a slower block still reads.
+template <int REG>
+__global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs a, int max_iterations) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double fold[LIN_WARPS][32];
+    __shared__ float red[LIN_WARPS][32];
+    __shared__ RegState st;
+    if (threadIdx.x == 0) st = *a.state;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int it = 0; it < max_iterations; ++it) {
+        const Xform T = state_xform(&st);
+        float acc[N_ACC];
+#pragma unroll
+        for (int v = 0; v < N_ACC; ++v) acc[v] = 0.0f;
+        uint32_t inl = 0;
+        lin_accumulate<REG, 1>(a, T, acc, inl);
+        // block reduce -> this block's partial row
+        for (int v = 0; v < N_ACC; ++v) {
+            const float s = warp_sum(acc[v]);
+            if (lane == 0) red[warp][v] = s;
+        }
+        {
+            uint32_t c = inl;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) red[warp][31] = __uint_as_float(c);
+        }
+        __syncthreads();
+        double* part = a.partials + (size_t)(it & 1) * gridDim.x * 32;
+        if (threadIdx.x < 32) {
+            double s = 0.0;
+            if (threadIdx.x < N_ACC) {
+                for (int w = 0; w < LIN_WARPS; ++w) s += (double)red[w][threadIdx.x];
+            } else if (threadIdx.x == S_INL) {
+                for (int w = 0; w < LIN_WARPS; ++w) s += (double)__float_as_uint(red[w][31]);
+            }
+            __stcg(part + (size_t)blockIdx.x * 32 + threadIdx.x, s);
+        }
+        __threadfence();
+        grid.sync();
+        {
+            const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
+            double s = 0.0;
+            for (unsigned b = slice; b < gridDim.x; b += LIN_WARPS) s += __ldcg(part + (size_t)b * 32 + v);
+            fold[slice][v] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double s = 0.0;
+            for (int w = 0; w < LIN_WARPS; ++w) s += fold[w][threadIdx.x];
+            fold[0][threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            gn_update(&st, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, it, blockIdx.x == 0 ? a.trace : nullptr);
+        __syncthreads();
+        if (st.stop) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.state = st;
 }
 
 // error-only pass with frozen neighbours — registration.hpp:678-777; WEIGHTS: per-point robust
@@ -517,6 +589,13 @@ void launch_error(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
     SPX_LAUNCH_CHECK();
 }
 
+template <int REG>
+unsigned coop_blocks(int device_sm_count) {
+    int per_sm = 0;
+    SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_gn_kernel<REG>, LIN_THREADS, 0));
+    return (unsigned)std::max(per_sm, 1) * (unsigned)device_sm_count;
+}
+
 void check_reg_loss(int reg, int loss, const char* where) {
     if (reg == SPX_REG_POINT_TO_DISTRIBUTION || reg == SPX_REG_GENZ)
         throw Error(SPX_ERR_UNSUPPORTED, std::string(where) + " RegType not built yet (POINT_TO_DISTRIBUTION / GENZ)");
@@ -528,7 +607,7 @@ void check_reg_loss(int reg, int loss, const char* where) {
 
 unsigned lin_blocks(spx_queue_t q, size_t ns) {
     const unsigned need = (unsigned)div_up(ns, LIN_THREADS);
-    const unsigned cap = (unsigned)q->sm_count * 4;  // grid-stride beyond 4 CTAs per SM
+    const unsigned cap = (unsigned)q->sm_count * 2;  // one resident wave (2 CTAs per SM), grid-stride beyond
     return std::max(1u, std::min(need, cap));
 }
 
@@ -698,7 +777,7 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     }
     a.idx_in = r->nn_idx; a.dist_in = r->nn_dist;
     a.idx_out = r->nn_idx; a.dist_out = r->nn_dist;
-    a.grid = index->view;
+    a.grid = index->levels;
     a.state = r->state;
     a.use_state = 1;
     a.T = xform_identity();
@@ -832,6 +911,36 @@ void dogleg_host(const float* H, const float* g, float radius, float* p, float* 
         pHp += p[i] * s;
     }
     *pred = -(gp + 0.5f * pHp);
+}
+
+void launch_align_gn(int reg_type, LinArgs& a, int max_it, spx_queue_t q, spx_registration_t reg) {
+    unsigned resident;
+    const void* fn;
+    switch (reg_type) {
+        case SPX_REG_POINT_TO_POINT:
+            resident = coop_blocks<SPX_REG_POINT_TO_POINT>(q->sm_count);
+            fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_POINT>;
+            break;
+        case SPX_REG_POINT_TO_PLANE:
+            resident = coop_blocks<SPX_REG_POINT_TO_PLANE>(q->sm_count);
+            fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_PLANE>;
+            break;
+        default:
+            resident = coop_blocks<SPX_REG_GICP>(q->sm_count);
+            fn = (const void*)align_gn_kernel<SPX_REG_GICP>;
+            break;
+    }
+    const unsigned blocks = std::max(1u, std::min((unsigned)div_up(a.ns, LIN_THREADS), resident));
+    if (2 * blocks > reg->max_blocks) {
+        SPX_CUDA(cudaStreamSynchronize(q->stream));
+        if (reg->partials) SPX_CUDA(cudaFree(reg->partials));
+        reg->max_blocks = 2 * blocks;
+        SPX_CUDA(cudaMalloc(&reg->partials, (size_t)reg->max_blocks * 32 * sizeof(double)));
+        a.partials = reg->partials;
+    }
+    void* args[] = {(void*)&a, (void*)&max_it};
+    SPX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(LIN_THREADS), args, 0, q->stream));
+    SPX_LAUNCH_CHECK();
 }
 
 // generic (caller-supplied correspondences) argument block for spx_linearize / spx_error / weights
@@ -1083,16 +1192,13 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         reg->timed = false;
         if (P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
             SPX_CUDA(cudaEventRecord(reg->ev0, st));
-            for (int it = 0; it < max_it; ++it) {
-                a.iter_index = it;
-                launch_linearize<1, true>(c.reg, a, c.blocks, st);
-            }
+            if (max_it > 0) launch_align_gn(c.reg, a, max_it, q, reg);
             SPX_CUDA(cudaEventRecord(reg->ev1, st));
             SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, st));
             q->sync();
             if (max_it > 0) fill_result(*hs, R);
             reg->timed = max_it > 0;
-            reg->last_launches = max_it;
+            reg->last_launches = max_it > 0 ? 1 : 0;
             reg->last_iterations = max_it > 0 ? hs->iterations + 1 : 0;
             if (T_trace_host && max_it > 0) {
                 // iterations never run (converged earlier) repeat the final pose
