@@ -101,7 +101,7 @@ typedef struct spx_registration_params {
     float dogleg_eta2;          /* .75 */
     float dogleg_gamma_decrease;/* .25 */
     float dogleg_gamma_increase;/* 2 */
-    int32_t reserved[8];        /* must be zero */
+    int32_t reserved[8];        /* [0]: cap on the align kernel's persistent grid (blocks, 0 = auto); rest must be zero */
 } spx_registration_params;
 
 /* RegistrationResult, I/algorithms/registration/result.hpp:13-28.  `iterations` keeps the
@@ -270,6 +270,38 @@ SPX_API int spx_registration_shard_begin(spx_registration_t reg, const float* sr
 SPX_API int spx_registration_shard_linearize(spx_registration_t reg, double* sums_dev);
 SPX_API int spx_registration_shard_update(spx_registration_t reg, const double* sums_dev);
 SPX_API int spx_registration_shard_finish(spx_registration_t reg, spx_registration_result* result_host);
+
+/* ------------------------------------------------------------------ multi-GPU: fused linearise + exchange
+ * The same sharding (source split, target + index replicated), but the exchange of the sums row
+ * happens INSIDE the iteration kernel over NVLink peer memory instead of a separate NCCL call:
+ * every rank's align kernel stores its 32-double partial row into every peer's mailbox, waits for
+ * the peers' rows, folds them in rank order (bitwise identical everywhere) and takes the same
+ * Gauss-Newton step — one cooperative launch per align per GPU, no host round trip, no collective
+ * launch per iteration.  The reference has no multi-device path; this is the
+ * B200-native replacement of what would be an all-reduce after registration.hpp:576-661.
+ *
+ * One communicator per rank.  Two ways to wire the mailboxes:
+ *  - one process per GPU (torch.distributed): spx_comm_ipc_handle on every rank, all-gather the
+ *    64-byte handles with any host-side transport, spx_comm_connect_ipc, then a host barrier;
+ *  - one process driving several GPUs: spx_comm_connect_local on the array of communicators. */
+typedef struct spx_comm_s* spx_comm_t;
+#define SPX_IPC_HANDLE_BYTES 64
+#define SPX_MAX_WORLD 8
+SPX_API int spx_comm_create(spx_queue_t q, int rank, int world, spx_comm_t* out);
+SPX_API int spx_comm_destroy(spx_comm_t comm);
+SPX_API int spx_comm_ipc_handle(spx_comm_t comm, uint8_t* handle64_host);
+/* handles_host: world * SPX_IPC_HANDLE_BYTES bytes, rank-major (own entry ignored) */
+SPX_API int spx_comm_connect_ipc(spx_comm_t comm, const uint8_t* handles_host);
+SPX_API int spx_comm_connect_local(spx_comm_t* comms, int world);
+/* Gauss-Newton align of this rank's source shard against the replicated target; every rank must
+ * call launch (asynchronous) with the same params / initial guess, then finish (synchronises,
+ * result identical on every rank; H, b, error, inlier are the GLOBAL sums).  A peer that does not
+ * answer within ~5 s aborts the kernel and finish returns SPX_ERR_INTERNAL. */
+SPX_API int spx_registration_align_sharded_launch(spx_registration_t reg, spx_comm_t comm, const float* src_points,
+                                          const float* src_covs, size_t ns, const float* tgt_points,
+                                          const float* tgt_covs, const float* tgt_normals, size_t nt,
+                                          spx_index_t target_index, const float* T_init_host, float robust_scale);
+SPX_API int spx_registration_align_sharded_finish(spx_registration_t reg, spx_registration_result* result_host);
 
 #ifdef __cplusplus
 }

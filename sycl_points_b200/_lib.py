@@ -136,6 +136,14 @@ def lib() -> C.CDLL:
         "spx_registration_shard_linearize": (C.c_int, [vp, vp]),
         "spx_registration_shard_update": (C.c_int, [vp, vp]),
         "spx_registration_shard_finish": (C.c_int, [vp, C.POINTER(RegistrationResultC)]),
+        "spx_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "spx_comm_destroy": (C.c_int, [vp]),
+        "spx_comm_ipc_handle": (C.c_int, [vp, C.c_char_p]),
+        "spx_comm_connect_ipc": (C.c_int, [vp, C.c_char_p]),
+        "spx_comm_connect_local": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "spx_registration_align_sharded_launch": (C.c_int, [vp, vp, f32p, f32p, sz, f32p, f32p, f32p, sz, vp, hostf,
+                                                            C.c_float]),
+        "spx_registration_align_sharded_finish": (C.c_int, [vp, C.POINTER(RegistrationResultC)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header/library mismatch: fail loudly

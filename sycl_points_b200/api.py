@@ -573,6 +573,7 @@ class RegistrationParams:
     optimization_method: OptimizationMethod = OptimizationMethod.GAUSS_NEWTON
     max_iterations: int = 20
     criteria: Criteria = field(default_factory=Criteria)
+    max_blocks: int = 0  # spx extension: cap on the align kernel's persistent grid (0 = one full wave)
 
     def to_c(self) -> RegistrationParamsC:
         P = RegistrationParamsC()
@@ -598,6 +599,7 @@ class RegistrationParams:
         P.dogleg_eta2 = self.dogleg.eta2
         P.dogleg_gamma_decrease = self.dogleg.gamma_decrease
         P.dogleg_gamma_increase = self.dogleg.gamma_increase
+        P.reserved[0] = int(self.max_blocks)
         return P
 
 

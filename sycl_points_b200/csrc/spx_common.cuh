@@ -99,6 +99,30 @@ struct spx_event_s {
     cudaEvent_t ev = nullptr;
 };
 
+// Multi-GPU exchange of the per-iteration sums row over NVLink peer memory.
+// Every rank owns one mailbox (cudaMalloc, exported by CUDA IPC or mapped by peer access):
+//   rows  [2 parities][SPX_MAX_RANKS][32] doubles — rank r's partial sums, written BY rank r
+//   flags [2][SPX_MAX_RANKS] u64                  — sequence number of the row that has landed
+//   gsum  [2][32] doubles, ready [2] u64          — the folded sums, published to the local grid
+//   error u32                                     — set when a peer did not answer in time
+constexpr int SPX_MAX_RANKS = 8;
+constexpr size_t SPX_MBOX_ROWS = 0;
+constexpr size_t SPX_MBOX_FLAGS = SPX_MBOX_ROWS + 2 * SPX_MAX_RANKS * 32 * sizeof(double);
+constexpr size_t SPX_MBOX_GSUM = SPX_MBOX_FLAGS + 2 * SPX_MAX_RANKS * sizeof(unsigned long long);
+constexpr size_t SPX_MBOX_READY = SPX_MBOX_GSUM + 2 * 32 * sizeof(double);
+constexpr size_t SPX_MBOX_ERROR = SPX_MBOX_READY + 2 * sizeof(unsigned long long);
+constexpr size_t SPX_MBOX_BYTES = 8192;
+
+struct spx_comm_s {
+    spx_queue_t q = nullptr;
+    int rank = 0, world = 1;
+    char* local = nullptr;                  // this rank's mailbox
+    char* peer[SPX_MAX_RANKS] = {};         // every rank's mailbox as mapped here (peer[rank] == local)
+    bool ipc_opened[SPX_MAX_RANKS] = {};    // mapped through cudaIpcOpenMemHandle (to be closed)
+    bool connected = false;
+    unsigned long long seq = 1;             // next row sequence number; advances identically on every rank
+};
+
 namespace spx {
 
 struct DeviceGuard {

@@ -47,6 +47,17 @@ struct RegState {
     float pad[2];
 };
 
+// view of the NVLink mailboxes handed to the sharded align kernel (spx_comm_s)
+struct PeerX {
+    int world, rank;
+    double* rows[SPX_MAX_RANKS];               // rows[p]: rank p's mailbox rows [2][SPX_MAX_RANKS][32]
+    unsigned long long* flags[SPX_MAX_RANKS];  // flags[p]: rank p's arrival flags [2][SPX_MAX_RANKS]
+    double* gsum;                              // local [2][32]
+    unsigned long long* ready;                 // local [2]
+    unsigned int* error;                       // local
+    unsigned long long seq0;                   // sequence number of iteration 0 of this align
+};
+
 struct LinArgs {
     // source
     const float4* src_pts;
@@ -84,6 +95,7 @@ struct LinArgs {
     int iter_index;
     float* trace;  // [max_iterations][16] column-major poses, nullable
     float* weights_out;  // compute_icp_robust_weights
+    PeerX px;            // sharded align only
 };
 
 // ------------------------------------------------------------------ robust kernels (robust.hpp:56-114)
@@ -445,13 +457,44 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs
         gn_update(a.state, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, a.iter_index, a.trace);
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long PEER_TIMEOUT_NS = 5000000000ull;
+
 // The whole Gauss-Newton align() as ONE cooperative launch (registration.hpp:227-272 + :803-828):
 // every iteration is nearest neighbour + linearise + block reduce, one grid-wide barrier, then
 // every block folds the per-block partials in the same fixed order and solves the same 6x6 system
 // (bitwise identical results, so no second barrier and no broadcast), advances its copy of the
 // pose and goes on.  Block 0 records the state for the host.  Partials are double-buffered by
 // iteration parity so a block that races ahead never overwrites what a slower block still reads.
-template <int REG>
+//
+// SHARDED: this GPU holds one shard of the source.  After the barrier block 0 folds the local
+// partial rows, stores the result into every rank's mailbox over NVLink (its own included), raises
+// the per-rank arrival flag (release, system scope), waits for every peer's flag (acquire), folds
+// the rows in rank order and publishes the global sums to the other blocks of this grid through a
+// local flag.  Every rank folds the same rows in the same order, so all poses stay bitwise equal
+// and converge at the same iteration.  Mailbox rows and flags are double-buffered by iteration
+// parity: a rank can be at most one exchange ahead of the slowest peer.
+template <int REG, bool SHARDED>
 __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs a, int max_iterations) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -492,19 +535,64 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs 
         }
         __threadfence();
         grid.sync();
-        {
+        if (!SHARDED || blockIdx.x == 0) {
             const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
             double s = 0.0;
             for (unsigned b = slice; b < gridDim.x; b += LIN_WARPS) s += __ldcg(part + (size_t)b * 32 + v);
             fold[slice][v] = s;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                double t = 0.0;
+                for (int w = 0; w < LIN_WARPS; ++w) t += fold[w][threadIdx.x];
+                fold[0][threadIdx.x] = t;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            double s = 0.0;
-            for (int w = 0; w < LIN_WARPS; ++w) s += fold[w][threadIdx.x];
-            fold[0][threadIdx.x] = s;
+        if (SHARDED) {
+            const PeerX& x = a.px;
+            const int par = it & 1;
+            const unsigned long long seq = x.seq0 + (unsigned long long)it;
+            if (blockIdx.x == 0) {
+                if (threadIdx.x < 32) {
+                    const double v = fold[0][threadIdx.x];
+                    for (int p = 0; p < x.world; ++p)
+                        __stcg(x.rows[p] + ((size_t)par * SPX_MAX_RANKS + x.rank) * 32 + threadIdx.x, v);
+                }
+                __threadfence_system();
+                __syncthreads();
+                if ((int)threadIdx.x < x.world) {
+                    st_release_sys(x.flags[threadIdx.x] + par * SPX_MAX_RANKS + x.rank, seq);
+                    const unsigned long long* f = x.flags[x.rank] + par * SPX_MAX_RANKS + threadIdx.x;
+                    const unsigned long long t0 = global_ns();
+                    while (ld_acquire_sys(f) < seq) {
+                        if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+                            atomicExch(x.error, 1u);
+                            break;
+                        }
+                    }
+                    __threadfence_system();
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    double t = 0.0;
+                    for (int r = 0; r < x.world; ++r)
+                        t += __ldcg(x.rows[x.rank] + ((size_t)par * SPX_MAX_RANKS + r) * 32 + threadIdx.x);
+                    fold[0][threadIdx.x] = t;
+                    __stcg(x.gsum + par * 32 + threadIdx.x, t);
+                }
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) st_release_gpu(x.ready + par, seq);
+            } else {
+                if (threadIdx.x == 0)
+                    while (ld_acquire_gpu(x.ready + par) < seq) {
+                    }
+                __syncthreads();
+                if (threadIdx.x < 32) fold[0][threadIdx.x] = __ldcg(x.gsum + par * 32 + threadIdx.x);
+                __syncthreads();
+            }
+            if (__ldcg(x.error)) break;  // a peer went silent: every block leaves, the host reports it
         }
-        __syncthreads();
         if (threadIdx.x == 0)
             gn_update(&st, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, it, blockIdx.x == 0 ? a.trace : nullptr);
         __syncthreads();
@@ -589,10 +677,10 @@ void launch_error(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
     SPX_LAUNCH_CHECK();
 }
 
-template <int REG>
+template <int REG, bool SHARDED>
 unsigned coop_blocks(int device_sm_count) {
     int per_sm = 0;
-    SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_gn_kernel<REG>, LIN_THREADS, 0));
+    SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_gn_kernel<REG, SHARDED>, LIN_THREADS, 0));
     return (unsigned)std::max(per_sm, 1) * (unsigned)device_sm_count;
 }
 
@@ -652,6 +740,9 @@ struct spx_registration_s {
     int shard_reg = 0;
     int shard_iter = 0;
     bool shard_active = false;
+    spx_comm_t shard_comm = nullptr;  // fused (mailbox) sharded align in flight
+    float4* shard_derived_normals = nullptr;
+    int shard_max_it = 0;
     // live timing of the iteration kernels (bench.py roofline)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0;
@@ -913,24 +1004,28 @@ void dogleg_host(const float* H, const float* g, float radius, float* p, float* 
     *pred = -(gp + 0.5f * pHp);
 }
 
+template <bool SHARDED>
 void launch_align_gn(int reg_type, LinArgs& a, int max_it, spx_queue_t q, spx_registration_t reg) {
     unsigned resident;
     const void* fn;
     switch (reg_type) {
         case SPX_REG_POINT_TO_POINT:
-            resident = coop_blocks<SPX_REG_POINT_TO_POINT>(q->sm_count);
-            fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_POINT>;
+            resident = coop_blocks<SPX_REG_POINT_TO_POINT, SHARDED>(q->sm_count);
+            fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_POINT, SHARDED>;
             break;
         case SPX_REG_POINT_TO_PLANE:
-            resident = coop_blocks<SPX_REG_POINT_TO_PLANE>(q->sm_count);
-            fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_PLANE>;
+            resident = coop_blocks<SPX_REG_POINT_TO_PLANE, SHARDED>(q->sm_count);
+            fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_PLANE, SHARDED>;
             break;
         default:
-            resident = coop_blocks<SPX_REG_GICP>(q->sm_count);
-            fn = (const void*)align_gn_kernel<SPX_REG_GICP>;
+            resident = coop_blocks<SPX_REG_GICP, SHARDED>(q->sm_count);
+            fn = (const void*)align_gn_kernel<SPX_REG_GICP, SHARDED>;
             break;
     }
-    const unsigned blocks = std::max(1u, std::min((unsigned)div_up(a.ns, LIN_THREADS), resident));
+    unsigned blocks = std::max(1u, std::min((unsigned)div_up(a.ns, LIN_THREADS), resident));
+    // reserved[0] = cap on the persistent grid (0 = one full wave).  Lets several aligns share one
+    // GPU (concurrent queues; two ranks of the exchange protocol on one device in the tests).
+    if (reg->P.reserved[0] > 0) blocks = std::min(blocks, (unsigned)reg->P.reserved[0]);
     if (2 * blocks > reg->max_blocks) {
         SPX_CUDA(cudaStreamSynchronize(q->stream));
         if (reg->partials) SPX_CUDA(cudaFree(reg->partials));
@@ -1192,7 +1287,7 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         reg->timed = false;
         if (P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
             SPX_CUDA(cudaEventRecord(reg->ev0, st));
-            if (max_it > 0) launch_align_gn(c.reg, a, max_it, q, reg);
+            if (max_it > 0) launch_align_gn<false>(c.reg, a, max_it, q, reg);
             SPX_CUDA(cudaEventRecord(reg->ev1, st));
             SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, st));
             q->sync();
@@ -1387,6 +1482,92 @@ int spx_registration_shard_finish(spx_registration_t reg, spx_registration_resul
         fill_result(*hs, R);
         reg->shard_active = false;
     });
+}
+
+// ------------------------------------------------------------------ fused linearise + NVLink exchange
+int spx_registration_align_sharded_launch(spx_registration_t reg, spx_comm_t comm, const float* src_points,
+                                          const float* src_covs, size_t ns, const float* tgt_points,
+                                          const float* tgt_covs, const float* tgt_normals, size_t nt,
+                                          spx_index_t target_index, const float* T_init_host, float robust_scale) {
+    return guard([&] {
+        SPX_REQUIRE(reg && comm, "[Registration::align_sharded] null argument");
+        SPX_REQUIRE(comm->connected, "[Registration::align_sharded] communicator is not connected");
+        SPX_REQUIRE(comm->q->device == reg->q->device, "[Registration::align_sharded] communicator lives on another device");
+        SPX_REQUIRE(reg->P.optimization_method == SPX_OPT_GAUSS_NEWTON,
+                    "[Registration::align_sharded] the sharded path is Gauss-Newton only");
+        SPX_REQUIRE(!reg->shard_comm, "[Registration::align_sharded] previous sharded align not finished");
+        SPX_REQUIRE(tgt_points || nt == 0, "[Registration::align_sharded] null target");
+        SPX_REQUIRE(src_points || ns == 0, "[Registration::align_sharded] null source");
+        spx_queue_t q = reg->q;
+        DeviceGuard g(q->device);
+        cudaStream_t st = q->stream;
+        // an empty shard still takes part in every exchange: one block, no points
+        float4* dn = nullptr;
+        AlignCtx c = align_setup(reg, ns ? src_points : tgt_points, ns ? src_covs : tgt_covs, ns, tgt_points, tgt_covs,
+                                 tgt_normals, nt, target_index, T_init_host, robust_scale, &dn);
+        reg->shard_derived_normals = dn;
+        LinArgs& a = c.a;
+        PeerX& x = a.px;
+        x.world = comm->world;
+        x.rank = comm->rank;
+        for (int r = 0; r < comm->world; ++r) {
+            SPX_REQUIRE(comm->peer[r], "[Registration::align_sharded] peer mailbox not mapped");
+            x.rows[r] = reinterpret_cast<double*>(comm->peer[r] + SPX_MBOX_ROWS);
+            x.flags[r] = reinterpret_cast<unsigned long long*>(comm->peer[r] + SPX_MBOX_FLAGS);
+        }
+        x.gsum = reinterpret_cast<double*>(comm->local + SPX_MBOX_GSUM);
+        x.ready = reinterpret_cast<unsigned long long*>(comm->local + SPX_MBOX_READY);
+        x.error = reinterpret_cast<unsigned int*>(comm->local + SPX_MBOX_ERROR);
+        const int max_it = std::max(reg->P.max_iterations, 0);
+        x.seq0 = comm->seq;
+        comm->seq += (unsigned long long)std::max(max_it, 1);
+        SPX_CUDA(cudaMemsetAsync(x.error, 0, sizeof(unsigned int), st));
+        reg->timed = false;
+        SPX_CUDA(cudaEventRecord(reg->ev0, st));
+        if (max_it > 0) launch_align_gn<true>(c.reg, a, max_it, q, reg);
+        SPX_CUDA(cudaEventRecord(reg->ev1, st));
+        reg->shard_comm = comm;
+        reg->shard_max_it = max_it;
+    });
+}
+
+int spx_registration_align_sharded_finish(spx_registration_t reg, spx_registration_result* R) {
+    float4* dn = nullptr;
+    const int rc = guard([&] {
+        SPX_REQUIRE(reg && R, "[Registration::align_sharded] null argument");
+        SPX_REQUIRE(reg->shard_comm, "[Registration::align_sharded] no sharded align in flight");
+        spx_queue_t q = reg->q;
+        DeviceGuard g(q->device);
+        spx_comm_t comm = reg->shard_comm;
+        reg->shard_comm = nullptr;
+        dn = reg->shard_derived_normals;
+        reg->shard_derived_normals = nullptr;
+        char* pin = static_cast<char*>(q->pinned_get(sizeof(RegState) + 64 + 32 * sizeof(double)));
+        RegState* hs = reinterpret_cast<RegState*>(pin);
+        unsigned int* herr = reinterpret_cast<unsigned int*>(pin + sizeof(RegState));
+        SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, q->stream));
+        SPX_CUDA(cudaMemcpyAsync(herr, comm->local + SPX_MBOX_ERROR, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                                 q->stream));
+        q->sync();
+        if (*herr) throw Error(SPX_ERR_INTERNAL, "[Registration::align_sharded] a peer rank did not answer (timeout)");
+        if (reg->shard_max_it > 0) {
+            fill_result(*hs, R);
+            reg->timed = true;
+            reg->last_launches = 1;
+            reg->last_iterations = hs->iterations + 1;
+        } else {
+            std::memset(R, 0, sizeof(*R));
+            for (int j = 0; j < 4; ++j)
+                for (int i = 0; i < 4; ++i) R->T[j * 4 + i] = hs->T[i][j];
+            R->error = FLT_MAX;
+            R->error_raw = FLT_MAX;
+        }
+    });
+    if (dn) {
+        cudaStreamSynchronize(reg->q->stream);
+        cudaFree(dn);
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -251,4 +251,99 @@ int spx_event_elapsed_ms(spx_event_t start, spx_event_t stop, float* ms) {
     });
 }
 
+// ------------------------------------------------------------------ multi-GPU mailboxes
+int spx_comm_create(spx_queue_t q, int rank, int world, spx_comm_t* out) {
+    return guard([&] {
+        SPX_REQUIRE(q && out, "[spx_comm_create] null argument");
+        SPX_REQUIRE(world >= 1 && world <= SPX_MAX_RANKS && rank >= 0 && rank < world,
+                    "[spx_comm_create] need 0 <= rank < world <= 8");
+        DeviceGuard g(q->device);
+        auto* c = new spx_comm_s();
+        c->q = q;
+        c->rank = rank;
+        c->world = world;
+        void* p = nullptr;
+        // plain cudaMalloc: pool (cudaMallocAsync) memory cannot be exported through CUDA IPC
+        cudaError_t e = cudaMalloc(&p, SPX_MBOX_BYTES);
+        if (e != cudaSuccess) {
+            delete c;
+            throw Error(SPX_ERR_CUDA, std::string("[spx_comm_create] cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        c->local = static_cast<char*>(p);
+        c->peer[rank] = c->local;
+        SPX_CUDA(cudaMemsetAsync(p, 0, SPX_MBOX_BYTES, q->stream));
+        SPX_CUDA(cudaStreamSynchronize(q->stream));
+        c->connected = (world == 1);
+        *out = c;
+    });
+}
+
+int spx_comm_destroy(spx_comm_t c) {
+    return guard([&] {
+        if (!c) return;
+        DeviceGuard g(c->q->device);
+        cudaStreamSynchronize(c->q->stream);
+        for (int r = 0; r < c->world; ++r)
+            if (c->ipc_opened[r] && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+        if (c->local) cudaFree(c->local);
+        delete c;
+    });
+}
+
+int spx_comm_ipc_handle(spx_comm_t c, uint8_t* handle64_host) {
+    return guard([&] {
+        SPX_REQUIRE(c && handle64_host, "[spx_comm_ipc_handle] null argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == SPX_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+        DeviceGuard g(c->q->device);
+        cudaIpcMemHandle_t h;
+        SPX_CUDA(cudaIpcGetMemHandle(&h, c->local));
+        std::memcpy(handle64_host, &h, sizeof(h));
+    });
+}
+
+int spx_comm_connect_ipc(spx_comm_t c, const uint8_t* handles_host) {
+    return guard([&] {
+        SPX_REQUIRE(c && handles_host, "[spx_comm_connect_ipc] null argument");
+        DeviceGuard g(c->q->device);
+        for (int r = 0; r < c->world; ++r) {
+            if (r == c->rank || c->peer[r]) continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles_host + (size_t)r * SPX_IPC_HANDLE_BYTES, sizeof(h));
+            void* p = nullptr;
+            SPX_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peer[r] = static_cast<char*>(p);
+            c->ipc_opened[r] = true;
+        }
+        c->connected = true;
+    });
+}
+
+int spx_comm_connect_local(spx_comm_t* comms, int world) {
+    return guard([&] {
+        SPX_REQUIRE(comms && world >= 1 && world <= SPX_MAX_RANKS, "[spx_comm_connect_local] bad arguments");
+        for (int a = 0; a < world; ++a) {
+            SPX_REQUIRE(comms[a] && comms[a]->world == world && comms[a]->rank == a,
+                        "[spx_comm_connect_local] communicator a must have rank a of `world`");
+        }
+        for (int a = 0; a < world; ++a) {
+            DeviceGuard g(comms[a]->q->device);
+            for (int b = 0; b < world; ++b) {
+                if (a == b) continue;
+                const int da = comms[a]->q->device, db = comms[b]->q->device;
+                if (da != db) {
+                    int can = 0;
+                    SPX_CUDA(cudaDeviceCanAccessPeer(&can, da, db));
+                    SPX_REQUIRE(can, "[spx_comm_connect_local] devices " + std::to_string(da) + " and " +
+                                         std::to_string(db) + " have no peer access");
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SPX_CUDA(e);
+                    (void)cudaGetLastError();
+                }
+                comms[a]->peer[b] = comms[b]->local;
+            }
+            comms[a]->connected = true;
+        }
+    });
+}
+
 }  // extern "C"

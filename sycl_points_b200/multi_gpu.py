@@ -1,0 +1,222 @@
+"""Multi-GPU registration: one process per GPU (torch.distributed), source points sharded, target
+cloud + index replicated on every rank.
+
+Two exchange paths for the per-iteration sums row (21 H terms, 6 b terms, error, inlier count):
+
+  mode="p2p"   the product path — spx_registration_align_sharded_*: ONE cooperative kernel per
+               align per GPU; the row is stored into every peer's mailbox over NVLink from inside
+               the kernel and folded in rank order (no collective launch, no host round trip);
+  mode="nccl"  the baseline — shard_linearize -> torch.distributed.all_reduce -> shard_update, one
+               collective per iteration on the queue's stream.
+
+Both leave the identical pose on every rank.  The reference has no multi-device path at all
+(SURVEY.md §2.2); what is mirrored here is Registration::align's contract
+(I/algorithms/registration/registration.hpp:201-276) on a sharded source.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import RegistrationResultC, check
+from .api import (DeviceQueue, ExecutionOptions, KDTree, PointCloudShared, Registration, RegistrationParams,
+                  RegistrationResult, OptimizationMethod, _T16, _hostf, _ptr)
+
+SUMS_LEN = _lib.SPX_SUMS_LEN
+S_B, S_ERR, S_INL = 21, 27, 28  # layout of the sums row (include/spx.h, SPX_SUMS_LEN)
+
+
+def shard_bounds(n: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous ceil(n / world) ranges; trailing ranks may be short or empty."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    step = -(-n // world) if n > 0 else 0
+    return [(min(r * step, n), min((r + 1) * step, n)) for r in range(world)]
+
+
+def shard_of(n: int, rank: int, world: int) -> tuple[int, int]:
+    return shard_bounds(n, world)[rank]
+
+
+def sums_to_Hb(s) -> tuple[np.ndarray, np.ndarray, float, int]:
+    """Unpack a sums row into the symmetric 6x6 H, b, error, inlier count (float32 like the reference)."""
+    s = np.asarray(s, np.float64)
+    H = np.zeros((6, 6), np.float32)
+    t = 0
+    for a in range(6):
+        for c in range(a, 6):
+            H[a, c] = H[c, a] = np.float32(s[t])
+            t += 1
+    return H, s[S_B:S_B + 6].astype(np.float32), float(np.float32(s[S_ERR])), int(s[S_INL] + 0.5)
+
+
+class Communicator:
+    """spx_comm: this rank's NVLink mailbox, wired to the peers' through CUDA IPC handles that are
+    all-gathered over the given torch.distributed group (any backend)."""
+
+    def __init__(self, queue: DeviceQueue, rank: int | None = None, world: int | None = None, group=None):
+        import torch.distributed as dist
+        self.queue = queue
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        h = C.c_void_p()
+        check(_lib.lib().spx_comm_create(queue.handle, self.rank, self.world, C.byref(h)))
+        self._h = h
+        if self.world > 1:
+            buf = C.create_string_buffer(64)
+            check(_lib.lib().spx_comm_ipc_handle(self._h, buf))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(buf.raw), group=group)
+            check(_lib.lib().spx_comm_connect_ipc(self._h, b"".join(handles)))
+            dist.barrier(group=group)  # nobody launches before every mailbox is mapped everywhere
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().spx_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LocalCommunicators:
+    """One process driving several GPUs: a communicator per queue, wired by peer access."""
+
+    def __init__(self, queues: list[DeviceQueue]):
+        self.queues = queues
+        self.handles = []
+        for r, q in enumerate(queues):
+            h = C.c_void_p()
+            check(_lib.lib().spx_comm_create(q.handle, r, len(queues), C.byref(h)))
+            self.handles.append(h)
+        arr = (C.c_void_p * len(queues))(*[h.value for h in self.handles])
+        check(_lib.lib().spx_comm_connect_local(arr, len(queues)))
+
+    def close(self):
+        for h in self.handles:
+            _lib.lib().spx_comm_destroy(h)
+        self.handles = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedAlignLoop:
+    """The reduce-then-identical-update protocol of the sharded Gauss-Newton align, independent of
+    where the per-shard sums come from (hooks).  `all_reduce(row)` must sum the row over ranks in
+    place.  Every rank runs the same loop on the same reduced sums, so no pose broadcast is needed.
+    Mirrors registration.hpp:227-272 with optimize_gauss_newton (:803-828)."""
+
+    def __init__(self, max_iterations: int, all_reduce):
+        self.max_iterations = max_iterations
+        self.all_reduce = all_reduce
+
+    # hooks -----------------------------------------------------------------
+    def begin(self):
+        raise NotImplementedError
+
+    def linearize_shard(self):
+        """-> the rank's partial sums row (anything all_reduce accepts)"""
+        raise NotImplementedError
+
+    def update(self, row) -> bool | None:
+        """apply the GN step from the reduced row; return True to stop early (None = unknown: the
+        device-resident variants keep launching and later launches no-op)"""
+        raise NotImplementedError
+
+    def finish(self):
+        raise NotImplementedError
+
+    def run(self):
+        self.begin()
+        for _ in range(self.max_iterations):
+            row = self.linearize_shard()
+            self.all_reduce(row)
+            if self.update(row):
+                break
+        return self.finish()
+
+
+class ShardedRegistration:
+    """Registration over a source sharded across the ranks of a process group."""
+
+    def __init__(self, queue: DeviceQueue, params: RegistrationParams | None = None, comm: Communicator | None = None,
+                 mode: str = "p2p", group=None):
+        if mode not in ("p2p", "nccl"):
+            raise ValueError("mode must be 'p2p' or 'nccl'")
+        self.queue = queue
+        self.params = params if params is not None else RegistrationParams()
+        if self.params.optimization_method != OptimizationMethod.GAUSS_NEWTON:
+            raise RuntimeError("[ShardedRegistration] the sharded path is Gauss-Newton only")
+        self.mode = mode
+        self.group = group
+        self.comm = comm
+        if mode == "p2p" and comm is None:
+            self.comm = Communicator(queue, group=group)
+        self.reg = Registration(queue, self.params)
+        self._sums = None
+
+    def _common_args(self, source: PointCloudShared, target: PointCloudShared, tree: KDTree, T0, options):
+        scale = options.robust_scale if options is not None else -1.0
+        t16 = _T16(T0)
+        return (source.points.ptr if source.size() else None, _ptr(source.covs) if source.has_cov() else None,
+                source.size(), target.points.ptr, _ptr(target.covs) if target.has_cov() else None,
+                _ptr(target.normals) if target.has_normal() else None, target.size(), tree.handle, _hostf(t16),
+                float(scale)), t16
+
+    def align(self, source_shard: PointCloudShared, target: PointCloudShared, target_knn: KDTree, initial_guess=None,
+              options: ExecutionOptions | None = None) -> RegistrationResult:
+        T0 = np.eye(4, dtype=np.float32) if initial_guess is None else np.asarray(initial_guess, np.float32)
+        self.reg._loss()
+        Pc = self.params.to_c()
+        L = _lib.lib()
+        check(L.spx_registration_set_params(self.reg._h, C.byref(Pc)))
+        args, keep = self._common_args(source_shard, target, target_knn, T0, options)
+        R = RegistrationResultC()
+        if self.mode == "p2p":
+            check(L.spx_registration_align_sharded_launch(self.reg._h, self.comm.handle, *args))
+            check(L.spx_registration_align_sharded_finish(self.reg._h, C.byref(R)))
+            return RegistrationResult.from_c(R)
+        # NCCL baseline: the sums row lives in a torch tensor so that all_reduce can take it; the
+        # queue must have been created on torch's current stream (DeviceQueue(dev, cuda_stream=...)).
+        import torch
+        import torch.distributed as dist
+        if self._sums is None:
+            self._sums = torch.zeros(SUMS_LEN, dtype=torch.float64, device=torch.device("cuda", self.queue.device))
+        sums = self._sums
+        reg_h = self.reg._h
+        outer = self
+
+        class _Loop(ShardedAlignLoop):
+            def begin(self):
+                check(L.spx_registration_shard_begin(reg_h, *args))
+
+            def linearize_shard(self):
+                check(L.spx_registration_shard_linearize(reg_h, C.c_void_p(sums.data_ptr())))
+                return sums
+
+            def update(self, row):
+                check(L.spx_registration_shard_update(reg_h, C.c_void_p(row.data_ptr())))
+                return None
+
+            def finish(self):
+                check(L.spx_registration_shard_finish(reg_h, C.byref(R)))
+                return RegistrationResult.from_c(R)
+
+        return _Loop(self.params.max_iterations, lambda t: dist.all_reduce(t, group=outer.group)).run()
+
+    def last_timing(self) -> dict:
+        return self.reg.last_timing()

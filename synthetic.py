@@ -154,3 +154,10 @@ def kitti_pair(seed: int = 42, sweeps: int = 16, beams: int = 64, azimuth_steps:
     tgt = accumulated_cloud(np.eye(4), boxes, cyl, sweeps, beams, azimuth_steps, spacing, seed * 2 + 1)
     src = accumulated_cloud(T_gt, boxes, cyl, sweeps, beams, azimuth_steps, spacing, seed * 2 + 2)
     return tgt, src, T_gt.astype(np.float32)
+
+
+def dense_pair(seed: int = 42, n_points: int = 2_000_000):
+    """BASELINE config 4 shape: a dense scan pair (8 sweeps x 256 beams x 4096 azimuth steps, ~8.2 M raw
+    points per cloud) meant for a 0.05 m voxel grid, which leaves ~1.9 M points per cloud; callers trim
+    to `n_points`.  (target_raw, source_raw, T_gt)."""
+    return kitti_pair(seed, sweeps=8, beams=256, azimuth_steps=4096, spacing=8.0)

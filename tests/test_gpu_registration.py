@@ -286,3 +286,100 @@ def test_sharded_sums_match_single(spx, q, pair):
     dt, da = pose_delta(ref.T, outs[0].T)
     assert dt < 1e-6 and da < 1e-6
     assert outs[0].inlier == ref.inlier
+
+
+def _sharded_launch(spx, reg, comm_handle, cl, tgt, tree, t16):
+    import ctypes as C
+    spx._lib.check(spx.lib().spx_registration_align_sharded_launch(
+        reg._h, comm_handle, cl.points.ptr if cl.size() else None, cl.covs.ptr if cl.size() else None, cl.size(),
+        tgt.points.ptr, tgt.covs.ptr, None, tgt.size(), tree.handle, t16.ctypes.data_as(C.POINTER(C.c_float)), -1.0))
+
+
+def _sharded_finish(spx, reg):
+    import ctypes as C
+    R = spx._lib.RegistrationResultC()
+    spx._lib.check(spx.lib().spx_registration_align_sharded_finish(reg._h, C.byref(R)))
+    return spx.RegistrationResult.from_c(R)
+
+
+def test_fused_exchange_world1_equals_plain_align(spx, q, pair):
+    """The NVLink-mailbox align kernel with a single rank: the self-exchange must leave the sums, and
+    therefore every pose, bit-identical to the plain cooperative align."""
+    from sycl_points_b200.multi_gpu import LocalCommunicators
+    params = spx.RegistrationParams()
+    params.robust.type = spx.RobustLossType.HUBER
+    ref = spx.Registration(q, params).align(pair["src"], pair["tgt"], pair["tree"])
+    comms = LocalCommunicators([q])
+    reg = spx.Registration(q, params)
+    spx._lib.check(spx.lib().spx_registration_set_params(reg._h, params.to_c()))
+    t16 = np.ascontiguousarray(np.eye(4, dtype=np.float32).T).reshape(16)
+    for _ in range(2):  # twice: the sequence numbers keep advancing across aligns
+        _sharded_launch(spx, reg, comms.handles[0], pair["src"], pair["tgt"], pair["tree"], t16)
+        out = _sharded_finish(spx, reg)
+        assert np.array_equal(out.T, ref.T) and out.iterations == ref.iterations and out.converged == ref.converged
+        assert out.inlier == ref.inlier and np.array_equal(out.H, ref.H) and np.array_equal(out.b, ref.b)
+    comms.close()
+
+
+@pytest.mark.parametrize("split", ["half", "empty_tail"])
+def test_fused_exchange_two_ranks_on_one_gpu(spx, pair, split):
+    """Two ranks of the exchange protocol co-resident on ONE device (two queues, the persistent
+    grids capped so that both fit): both end with the identical pose, equal to the unsharded align."""
+    from sycl_points_b200.multi_gpu import LocalCommunicators
+    qa, qb = spx.DeviceQueue(0), spx.DeviceQueue(0)
+    params = spx.RegistrationParams()
+    params.robust.type = spx.RobustLossType.HUBER
+    ref = spx.Registration(qa, params).align(pair["src"], pair["tgt"], pair["tree"])
+    params.max_blocks = 64
+    ns = pair["src"].size()
+    cut = ns // 2 + 7 if split == "half" else ns
+    tgt_a, tgt_b = pair["tgt"], spx.PointCloudShared(qb, pair["tgt_h"], pair["cov_t"])
+    tree_b = spx.KDTree.build(qb, tgt_b)
+    shards = [spx.PointCloudShared(qa, pair["src_h"][:cut], pair["cov_s"][:cut]),
+              spx.PointCloudShared(qb, pair["src_h"][cut:], pair["cov_s"][cut:]) if cut < ns else spx.PointCloudShared(qb)]
+    regs = [spx.Registration(qa, params), spx.Registration(qb, params)]
+    for r in regs:
+        spx._lib.check(spx.lib().spx_registration_set_params(r._h, params.to_c()))
+    comms = LocalCommunicators([qa, qb])
+    qa.wait()
+    qb.wait()
+    t16 = np.ascontiguousarray(np.eye(4, dtype=np.float32).T).reshape(16)
+    _sharded_launch(spx, regs[0], comms.handles[0], shards[0], tgt_a, pair["tree"], t16)
+    _sharded_launch(spx, regs[1], comms.handles[1], shards[1], tgt_b, tree_b, t16)
+    outs = [_sharded_finish(spx, r) for r in regs]
+    assert np.array_equal(outs[0].T, outs[1].T)
+    assert outs[0].iterations == outs[1].iterations == ref.iterations and outs[0].converged == ref.converged
+    dt, da = pose_delta(ref.T, outs[0].T)
+    assert dt < 1e-6 and da < 1e-6
+    assert outs[0].inlier == ref.inlier
+    comms.close()
+
+
+def test_fused_exchange_across_two_gpus(spx, pair):
+    """The same protocol with the ranks on two devices (peer access over NVLink); skipped on a
+    single-GPU box (the two-ranks-on-one-GPU test covers the protocol there)."""
+    from sycl_points_b200.multi_gpu import LocalCommunicators, shard_bounds
+    if spx.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    qs = [spx.DeviceQueue(0), spx.DeviceQueue(1)]
+    params = spx.RegistrationParams()
+    params.robust.type = spx.RobustLossType.HUBER
+    ref = spx.Registration(qs[0], params).align(pair["src"], pair["tgt"], pair["tree"])
+    bounds = shard_bounds(pair["src"].size(), 2)
+    tgts = [spx.PointCloudShared(qq, pair["tgt_h"], pair["cov_t"]) for qq in qs]
+    trees = [spx.KDTree.build(qq, t) for qq, t in zip(qs, tgts)]
+    shards = [spx.PointCloudShared(qq, pair["src_h"][lo:hi], pair["cov_s"][lo:hi]) for qq, (lo, hi) in zip(qs, bounds)]
+    regs = [spx.Registration(qq, params) for qq in qs]
+    for r in regs:
+        spx._lib.check(spx.lib().spx_registration_set_params(r._h, params.to_c()))
+    comms = LocalCommunicators(qs)
+    for qq in qs:
+        qq.wait()
+    t16 = np.ascontiguousarray(np.eye(4, dtype=np.float32).T).reshape(16)
+    for r, h, s, t, tr in zip(regs, comms.handles, shards, tgts, trees):
+        _sharded_launch(spx, r, h, s, t, tr, t16)
+    outs = [_sharded_finish(spx, r) for r in regs]
+    assert np.array_equal(outs[0].T, outs[1].T)
+    dt, da = pose_delta(ref.T, outs[0].T)
+    assert dt < 1e-6 and da < 1e-6 and outs[0].inlier == ref.inlier
+    comms.close()
