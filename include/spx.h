@@ -146,6 +146,12 @@ SPX_API int spx_memcpy_d2h(spx_queue_t q, void* dst_host, const void* src, size_
 SPX_API int spx_memcpy_d2d(spx_queue_t q, void* dst, const void* src, size_t bytes);
 SPX_API int spx_memset(spx_queue_t q, void* dst, int value, size_t bytes);
 
+/* USM *shared* semantics for the C++ facade's shared_vector<T> (host-dereferenceable, device-usable):
+ * CUDA managed memory + explicit prefetch (the reference's mem_advise hints, sycl_utils.hpp:283-364). */
+SPX_API int spx_malloc_managed(size_t bytes, void** out);
+SPX_API int spx_free_managed(void* ptr);
+SPX_API int spx_prefetch(spx_queue_t q, const void* ptr, size_t bytes, int to_device); /* to_device 0 = to host */
+
 SPX_API int spx_event_create(spx_event_t* out);
 SPX_API int spx_event_destroy(spx_event_t e);
 SPX_API int spx_event_record(spx_queue_t q, spx_event_t e);
@@ -196,10 +202,31 @@ SPX_API int spx_normals_from_covs(spx_queue_t q, const float* points, const floa
  * (synchronises).  voxel_size <= 0 -> SPX_ERR_INVALID_ARGUMENT (voxel_downsampling.hpp:23-25). */
 SPX_API int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n, float voxel_size, size_t min_voxel_count,
                          float* out_points, size_t* m_host);
+/* filter::VoxelGrid::downsampling(cloud, result) — voxel_downsampling.hpp:64-79,220-288: the cloud
+ * overload also aggregates per-point attributes over each voxel in the same order: mean RGBA
+ * (float[n][4]), MEDIAN intensity (float[n], :82-98), mean timestamp offset (float[n]).  Any
+ * attribute input may be NULL (then its output is ignored). */
+SPX_API int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n, float voxel_size,
+                               size_t min_voxel_count, const float* rgb, const float* intensity,
+                               const float* timestamps, float* out_points, float* out_rgb, float* out_intensity,
+                               float* out_timestamps, size_t* m_host);
 /* PreprocessFilter::box_filter(cloud, min, max) — preprocess_operator/box_filter_operator.hpp:19-54,
  * common.hpp:15-25, common/filter_by_flags.hpp:43-49 (order-preserving).  Synchronises. */
 SPX_API int spx_box_filter(spx_queue_t q, const float* points, size_t n, float min_distance, float max_distance,
                    float* out_points, size_t* m_host);
+
+/* PreprocessFilter::random_sampling(source, output, n) — preprocess_operator/random_sampling_operator.hpp:15-58:
+ * partial Fisher-Yates over 0..n-1 with a persistent std::mt19937 (seed 1234) and
+ * std::uniform_int_distribution<size_t>(i, n-1) (libstdc++), then ORDER-PRESERVING compaction.
+ * spx_random_sampling writes the m = min(n, sampling_num) selected indices in ascending order to
+ * idx_out (device, int32[m]); spx_gather applies them to any per-point attribute (elem_bytes a
+ * multiple of 4: 16 = points/normals, 64 = covariances, 4 = intensities). */
+typedef struct spx_rng_s* spx_rng_t;
+SPX_API int spx_rng_create(uint32_t seed, spx_rng_t* out);
+SPX_API int spx_rng_seed(spx_rng_t rng, uint32_t seed);
+SPX_API int spx_rng_destroy(spx_rng_t rng);
+SPX_API int spx_random_sampling(spx_queue_t q, spx_rng_t rng, size_t n, size_t sampling_num, int32_t* idx_out, size_t* m_host);
+SPX_API int spx_gather(spx_queue_t q, const void* src, size_t elem_bytes, const int32_t* idx, size_t m, void* dst);
 
 /* ------------------------------------------------------------------ registration
  * Registration::compute_linearized_result / linearize — registration.hpp:312-331,513-676:

@@ -1,0 +1,112 @@
+// filter::PreprocessFilter — the two operators that feed the registration path:
+//   box_filter       I/algorithms/filter/preprocess_operator/box_filter_operator.hpp:19-54 (+ common.hpp:15-25)
+//   random_sampling  I/algorithms/filter/preprocess_operator/random_sampling_operator.hpp:15-58
+// Both compact on the device and preserve source order.  The sensor-specific operators of the
+// reference class (polar grid, FPS, angle incidence, intensity ...) are out of scope.
+#pragma once
+
+#include <limits>
+#include <memory>
+
+#include "sycl_points/points/point_cloud.hpp"
+
+namespace sycl_points {
+namespace algorithms {
+namespace filter {
+
+class PreprocessFilter {
+public:
+    using Ptr = std::shared_ptr<PreprocessFilter>;
+
+    PreprocessFilter(const sycl_utils::DeviceQueue& queue) : queue_(queue) {
+        detail::spx_check(spx_rng_create(1234u, &rng_));  // random_sampling_operator.hpp:20
+    }
+    ~PreprocessFilter() {
+        if (rng_) spx_rng_destroy(rng_);
+    }
+    PreprocessFilter(const PreprocessFilter&) = delete;
+    PreprocessFilter& operator=(const PreprocessFilter&) = delete;
+
+    void set_random_seed(uint_fast32_t seed) { detail::spx_check(spx_rng_seed(rng_, (uint32_t)seed)); }
+
+    /// in place
+    void box_filter(PointCloudShared& data, float min_distance = 1.0f,
+                    float max_distance = std::numeric_limits<float>::max()) {
+        this->box_filter(data, data, min_distance, max_distance);
+    }
+    /// keep points whose L-infinity range lies in [min_distance, max_distance]; attributes other
+    /// than the points are dropped (the path filters raw scans, which carry none it needs)
+    void box_filter(const PointCloudShared& source, PointCloudShared& output, float min_distance = 1.0f,
+                    float max_distance = std::numeric_limits<float>::max()) {
+        const size_t N = source.size();
+        if (N == 0) {
+            if (&source != &output) output.clear();
+            return;
+        }
+        PointContainerShared out(N);
+        this->queue_.set_accessed_by_device(source.points_ptr(), N);
+        this->queue_.set_accessed_by_device(out.data(), N);
+        size_t m = 0;
+        detail::spx_check(spx_box_filter(this->queue_.handle(), reinterpret_cast<const float*>(source.points_ptr()), N,
+                                         min_distance, max_distance, reinterpret_cast<float*>(out.data()), &m));
+        out.resize(m);
+        output.points->swap(out);
+        output.covs->clear();
+        output.normals->clear();
+        output.rgb->clear();
+        output.intensities->clear();
+        output.timestamp_offsets->clear();
+    }
+
+    /// in place
+    void random_sampling(PointCloudShared& data, size_t sampling_num) {
+        PointCloudShared out(this->queue_);
+        this->random_sampling(data, out, sampling_num);
+        data = out;
+    }
+    /// partial Fisher-Yates with the persistent mt19937, order-preserving compaction of points,
+    /// covariances, normals and intensities
+    void random_sampling(const PointCloudShared& source, PointCloudShared& output, size_t sampling_num) {
+        const size_t N = source.size();
+        if (N <= sampling_num) {  // keep everything (random_sampling_operator.hpp:26-30)
+            output = source;
+            return;
+        }
+        shared_vector<int32_t> idx(sampling_num);
+        this->queue_.set_accessed_by_device(idx.data(), sampling_num);
+        size_t m = 0;
+        detail::spx_check(spx_random_sampling(this->queue_.handle(), rng_, N, sampling_num, idx.data(), &m));
+        PointCloudShared out(this->queue_);
+        gather(*source.points, *out.points, idx, m, true);
+        gather(*source.covs, *out.covs, idx, m, source.has_cov());
+        gather(*source.normals, *out.normals, idx, m, source.has_normal());
+        gather(*source.intensities, *out.intensities, idx, m, source.has_intensity());
+        detail::spx_check(spx_queue_sync(this->queue_.handle()));
+        out.start_time_ms = source.start_time_ms;
+        out.end_time_ms = source.end_time_ms;
+        output.points.swap(out.points);
+        output.covs.swap(out.covs);
+        output.normals.swap(out.normals);
+        output.intensities.swap(out.intensities);
+        output.rgb->clear();
+        output.timestamp_offsets->clear();
+    }
+
+private:
+    template <typename V>
+    void gather(const V& src, V& dst, const shared_vector<int32_t>& idx, size_t m, bool enable) const {
+        dst.resize(enable ? m : 0);
+        if (!enable || m == 0) return;
+        this->queue_.set_accessed_by_device(src.data(), src.size());
+        this->queue_.set_accessed_by_device(dst.data(), m);
+        detail::spx_check(spx_gather(this->queue_.handle(), src.data(), sizeof(typename V::value_type), idx.data(), m,
+                                     dst.data()));
+    }
+
+    sycl_utils::DeviceQueue queue_;
+    spx_rng_t rng_ = nullptr;
+};
+
+}  // namespace filter
+}  // namespace algorithms
+}  // namespace sycl_points

@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
         "spx_normals": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals_from_covs": (C.c_int, [vp, f32p, f32p, sz, f32p]),
         "spx_voxel_downsample": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, C.POINTER(C.c_size_t)]),
+        "spx_voxel_downsample_attrs": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                                                 C.POINTER(C.c_size_t)]),
         "spx_box_filter": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, f32p, C.POINTER(C.c_size_t)]),
         "spx_linearize": (C.c_int, [vp, C.c_int, C.c_int, f32p, f32p, sz, f32p, f32p, f32p, i32p, f32p, hostf,
                                     C.c_float, C.c_float, hostf, hostf, C.POINTER(C.c_float),
@@ -136,6 +138,14 @@ def lib() -> C.CDLL:
         "spx_registration_shard_linearize": (C.c_int, [vp, vp]),
         "spx_registration_shard_update": (C.c_int, [vp, vp]),
         "spx_registration_shard_finish": (C.c_int, [vp, C.POINTER(RegistrationResultC)]),
+        "spx_malloc_managed": (C.c_int, [sz, C.POINTER(vp)]),
+        "spx_free_managed": (C.c_int, [vp]),
+        "spx_prefetch": (C.c_int, [vp, vp, sz, C.c_int]),
+        "spx_rng_create": (C.c_int, [C.c_uint32, C.POINTER(vp)]),
+        "spx_rng_seed": (C.c_int, [vp, C.c_uint32]),
+        "spx_rng_destroy": (C.c_int, [vp]),
+        "spx_random_sampling": (C.c_int, [vp, vp, sz, sz, i32p, C.POINTER(C.c_size_t)]),
+        "spx_gather": (C.c_int, [vp, vp, sz, i32p, sz, vp]),
         "spx_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
         "spx_comm_destroy": (C.c_int, [vp]),
         "spx_comm_ipc_handle": (C.c_int, [vp, C.c_char_p]),

@@ -215,6 +215,9 @@ class PointCloudShared:
         self.points: DeviceArray | None = None
         self.covs: DeviceArray | None = None
         self.normals: DeviceArray | None = None
+        self.rgb: DeviceArray | None = None          # (n, 4) RGBA in [0, 1]  (types.hpp:14-17)
+        self.intensities: DeviceArray | None = None  # (n,)
+        self.timestamp_offsets: DeviceArray | None = None  # (n,) ms relative to the first measurement
         self._n = 0
         if points is not None:
             self.set_points(points)
@@ -249,6 +252,25 @@ class PointCloudShared:
 
     def set_normals(self, normals: np.ndarray):
         self.normals = DeviceArray.from_host(self.queue, np.ascontiguousarray(normals, dtype=np.float32))
+
+    def has_rgb(self) -> bool:
+        return self.rgb is not None and len(self.rgb) == self._n and self._n > 0
+
+    def has_intensity(self) -> bool:
+        return self.intensities is not None and len(self.intensities) == self._n and self._n > 0
+
+    def has_timestamps(self) -> bool:
+        return self.timestamp_offsets is not None and len(self.timestamp_offsets) == self._n and self._n > 0
+
+    def set_rgb(self, rgb: np.ndarray):
+        self.rgb = DeviceArray.from_host(self.queue, np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 4))
+
+    def set_intensities(self, v: np.ndarray):
+        self.intensities = DeviceArray.from_host(self.queue, np.ascontiguousarray(v, dtype=np.float32).reshape(-1))
+
+    def set_timestamp_offsets(self, v: np.ndarray):
+        self.timestamp_offsets = DeviceArray.from_host(self.queue,
+                                                       np.ascontiguousarray(v, dtype=np.float32).reshape(-1))
 
     def adopt_points(self, dev: DeviceArray, n: int):
         self.points = dev
@@ -438,19 +460,46 @@ class VoxelGrid:
         self._min_voxel_count = int(n)
 
     def downsampling(self, cloud: PointCloudShared, result: PointCloudShared | None = None) -> PointCloudShared:
+        """voxel_downsampling.hpp:64-79 (+ :220-288 when the cloud carries RGB / intensity / timestamps)."""
         result = result if result is not None else PointCloudShared(self.queue)
         n = cloud.size()
         if n == 0:
             result.adopt_points(DeviceArray(self.queue, (0, 4), np.float32), 0)
+            result.covs = result.normals = result.rgb = result.intensities = result.timestamp_offsets = None
             return result
         out = DeviceArray(self.queue, (n, 4), np.float32)
         m = C.c_size_t()
-        check(_lib.lib().spx_voxel_downsample(self.queue.handle, cloud.points.ptr, n, self._voxel_size,
-                                              self._min_voxel_count, out.ptr, C.byref(m)))
-        result.adopt_points(out, int(m.value))
+        rgb, inten, ts = cloud.has_rgb(), cloud.has_intensity(), cloud.has_timestamps()
+        if not (rgb or inten or ts):
+            check(_lib.lib().spx_voxel_downsample(self.queue.handle, cloud.points.ptr, n, self._voxel_size,
+                                                  self._min_voxel_count, out.ptr, C.byref(m)))
+            o_rgb = o_int = o_ts = None
+        else:
+            o_rgb = DeviceArray(self.queue, (n, 4), np.float32) if rgb else None
+            o_int = DeviceArray(self.queue, (n,), np.float32) if inten else None
+            o_ts = DeviceArray(self.queue, (n,), np.float32) if ts else None
+            check(_lib.lib().spx_voxel_downsample_attrs(
+                self.queue.handle, cloud.points.ptr, n, self._voxel_size, self._min_voxel_count,
+                cloud.rgb.ptr if rgb else None, cloud.intensities.ptr if inten else None,
+                cloud.timestamp_offsets.ptr if ts else None, out.ptr, _ptr(o_rgb), _ptr(o_int), _ptr(o_ts),
+                C.byref(m)))
+        mm = int(m.value)
+        result.adopt_points(out, mm)
         result.covs = None
         result.normals = None
+        result.rgb = _trim(o_rgb, mm)
+        result.intensities = _trim(o_int, mm)
+        result.timestamp_offsets = _trim(o_ts, mm)
         return result
+
+
+def _trim(a: DeviceArray | None, m: int):
+    """view the first m rows of an over-allocated output array (no copy)"""
+    if a is None:
+        return None
+    a.shape = (m,) + a.shape[1:]
+    a.nbytes = int(np.prod(a.shape)) * a.dtype.itemsize
+    return a
 
 
 class PreprocessFilter:
@@ -458,6 +507,54 @@ class PreprocessFilter:
 
     def __init__(self, queue: DeviceQueue):
         self.queue = queue
+        h = C.c_void_p()
+        check(_lib.lib().spx_rng_create(1234, C.byref(h)))  # random_sampling_operator.hpp:20
+        self._rng = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_rng", None):
+                _lib.lib().spx_rng_destroy(self._rng)
+                self._rng = None
+        except Exception:
+            pass
+
+    def set_random_seed(self, seed: int):
+        check(_lib.lib().spx_rng_seed(self._rng, int(seed)))
+
+    def random_sampling(self, cloud: PointCloudShared, sampling_num: int,
+                        output: PointCloudShared | None = None) -> PointCloudShared:
+        """PreprocessFilter::random_sampling (random_sampling_operator.hpp:24-52): partial Fisher-Yates
+        with the persistent mt19937, order-preserving compaction of every per-point attribute."""
+        n = cloud.size()
+        if n <= sampling_num:
+            if output is None or output is cloud:
+                return cloud
+            for name in ("points", "covs", "normals", "rgb", "intensities", "timestamp_offsets"):
+                setattr(output, name, getattr(cloud, name))
+            output._n = n
+            return output
+        idx = DeviceArray(self.queue, (sampling_num,), np.int32)
+        m = C.c_size_t()
+        check(_lib.lib().spx_random_sampling(self.queue.handle, self._rng, n, sampling_num, idx.ptr, C.byref(m)))
+        mm = int(m.value)
+
+        def take(a: DeviceArray | None, enable: bool):
+            if not enable:
+                return None
+            row = int(np.prod(a.shape[1:])) if len(a.shape) > 1 else 1
+            out = DeviceArray(self.queue, (mm,) + a.shape[1:], a.dtype)
+            check(_lib.lib().spx_gather(self.queue.handle, a.ptr, row * a.dtype.itemsize, idx.ptr, mm, out.ptr))
+            return out
+
+        res = (take(cloud.points, True), take(cloud.covs, cloud.has_cov()), take(cloud.normals, cloud.has_normal()),
+               take(cloud.rgb, cloud.has_rgb()), take(cloud.intensities, cloud.has_intensity()),
+               take(cloud.timestamp_offsets, cloud.has_timestamps()))
+        output = output if output is not None else PointCloudShared(self.queue)
+        (output.points, output.covs, output.normals, output.rgb, output.intensities, output.timestamp_offsets) = res
+        output._n = mm
+        self._last_indices = idx
+        return output
 
     def box_filter(self, cloud: PointCloudShared, min_distance: float = 1.0, max_distance: float = FLT_MAX,
                    output: PointCloudShared | None = None) -> PointCloudShared:
@@ -910,8 +1007,8 @@ class RegistrationPipeline:
     """registration::RegistrationPipeline (registration_pipeline.hpp:17-151) with the robust-scale
     annealing wrapper (pipeline/robust.hpp:42-114).  `aligner` may be any callable with the
     RegistrationAligner signature (pipeline/aligner.hpp:13-15) — the reference's tests pass lambdas.
-    Random sampling (default on in the reference, registration_pipeline.hpp:127-140) needs the
-    libstdc++ mt19937 stream and is a "next" row; enable=True raises until built."""
+    Random sampling (default ON in the reference, 1000 points, registration_pipeline.hpp:127-140) draws
+    from the library's persistent std::mt19937(1234) exactly as the reference does."""
 
     def __init__(self, queue_or_aligner, pipeline_params: RegistrationPipelineParams | None = None):
         self.pipeline_params = pipeline_params if pipeline_params is not None else RegistrationPipelineParams()
@@ -922,6 +1019,7 @@ class RegistrationPipeline:
             self.registration = Registration(queue_or_aligner, self.pipeline_params.registration)
             self._aligner = self.registration.align
         self._input = None
+        self._filter = None
 
     def get_registration_input_point_cloud(self):
         return self._input
@@ -929,8 +1027,11 @@ class RegistrationPipeline:
     def align(self, source, target, target_knn, initial_guess=None, options: ExecutionOptions | None = None):
         rs = self.pipeline_params.random_sampling
         if rs.enable and source.size() > rs.num:
-            raise SpxError(-3, "[RegistrationPipeline::align] random_sampling is not built yet (SURVEY §8(f) rank 1); "
-                               "set random_sampling.enable = False")
+            if rs.use_intensities:
+                raise SpxError(-3, "[RegistrationPipeline::align] intensity-weighted sampling is not built")
+            if self._filter is None:
+                self._filter = PreprocessFilter(source.queue)
+            source = self._filter.random_sampling(source, rs.num, PointCloudShared(source.queue))
         self._input = source
         options = options if options is not None else ExecutionOptions()
         T0 = np.eye(4, dtype=np.float32) if initial_guess is None else np.asarray(initial_guess, np.float32)

@@ -1,7 +1,10 @@
 // Runtime shim of libspx: replaces the reference's SYCL queue / USM / event layer
 // (I/utils/sycl_utils.hpp:234-280,491-635) with one in-order CUDA stream per queue, explicit
 // device memory and CUDA events.
+#include <algorithm>
 #include <cstring>
+#include <numeric>
+#include <random>
 
 #include "spx_common.cuh"
 
@@ -218,6 +221,35 @@ int spx_memset(spx_queue_t q, void* dst, int value, size_t bytes) {
     });
 }
 
+int spx_malloc_managed(size_t bytes, void** out) {
+    return guard([&] {
+        SPX_REQUIRE(out, "[spx_malloc_managed] null output");
+        *out = nullptr;
+        if (bytes == 0) return;
+        SPX_CUDA(cudaMallocManaged(out, bytes, cudaMemAttachGlobal));
+    });
+}
+
+int spx_free_managed(void* ptr) {
+    return guard([&] {
+        if (ptr) SPX_CUDA(cudaFree(ptr));
+    });
+}
+
+int spx_prefetch(spx_queue_t q, const void* ptr, size_t bytes, int to_device) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_prefetch] null queue");
+        if (!ptr || !bytes) return;
+        DeviceGuard g(q->device);
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type != cudaMemoryTypeManaged) {
+            (void)cudaGetLastError();
+            return;  // plain device / host memory: nothing to migrate
+        }
+        SPX_CUDA(cudaMemPrefetchAsync(ptr, bytes, to_device ? q->device : cudaCpuDeviceId, q->stream));
+    });
+}
+
 int spx_event_create(spx_event_t* out) {
     return guard([&] {
         SPX_REQUIRE(out, "[spx_event_create] null output");
@@ -248,6 +280,62 @@ int spx_event_elapsed_ms(spx_event_t start, spx_event_t stop, float* ms) {
         SPX_REQUIRE(start && stop && ms, "[spx_event_elapsed_ms] null argument");
         SPX_CUDA(cudaEventSynchronize(stop->ev));
         SPX_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+    });
+}
+
+// ------------------------------------------------------------------ random sampling (host RNG, like the reference)
+struct spx_rng_s {
+    std::mt19937 mt;
+};
+
+int spx_rng_create(uint32_t seed, spx_rng_t* out) {
+    return guard([&] {
+        SPX_REQUIRE(out, "[spx_rng_create] null output");
+        auto* r = new spx_rng_s();
+        r->mt.seed(seed);
+        *out = r;
+    });
+}
+int spx_rng_seed(spx_rng_t rng, uint32_t seed) {
+    return guard([&] {
+        SPX_REQUIRE(rng, "[spx_rng_seed] null rng");
+        rng->mt.seed(seed);
+    });
+}
+int spx_rng_destroy(spx_rng_t rng) {
+    return guard([&] { delete rng; });
+}
+
+// random_sampling_operator.hpp:24-52: the draw order (and therefore the RNG stream carried over to
+// the next call) is the reference's; the compaction keeps source order, so ascending indices.
+int spx_random_sampling(spx_queue_t q, spx_rng_t rng, size_t n, size_t sampling_num, int32_t* idx_out, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && rng && m_host, "[PreprocessFilter::random_sampling] null argument");
+        SPX_REQUIRE(n < (1ull << 31), "[PreprocessFilter::random_sampling] too many points");
+        std::vector<int32_t> sel;
+        if (n <= sampling_num) {  // keep everything, no draw
+            sel.resize(n);
+            std::iota(sel.begin(), sel.end(), 0);
+        } else {
+            std::vector<size_t> indices(n);
+            std::iota(indices.begin(), indices.end(), (size_t)0);
+            for (size_t i = 0; i < sampling_num; ++i) {
+                std::uniform_int_distribution<size_t> dist(i, n - 1);
+                const size_t j = dist(rng->mt);
+                std::swap(indices[i], indices[j]);
+            }
+            sel.resize(sampling_num);
+            for (size_t i = 0; i < sampling_num; ++i) sel[i] = (int32_t)indices[i];
+            std::sort(sel.begin(), sel.end());
+        }
+        *m_host = sel.size();
+        if (sel.empty()) return;
+        SPX_REQUIRE(idx_out, "[PreprocessFilter::random_sampling] null output");
+        DeviceGuard g(q->device);
+        int32_t* pin = static_cast<int32_t*>(q->pinned_get(sel.size() * sizeof(int32_t)));
+        std::memcpy(pin, sel.data(), sel.size() * sizeof(int32_t));
+        SPX_CUDA(cudaMemcpyAsync(idx_out, pin, sel.size() * sizeof(int32_t), cudaMemcpyDefault, q->stream));
+        q->sync();  // the pinned staging block is reused by the next call
     });
 }
 

@@ -184,12 +184,52 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* _
 }
 
 // ---- per-voxel mean
+// optional per-point attributes aggregated with the points (voxel_downsampling.hpp:220-288): mean
+// RGBA, median intensity (:82-98), mean timestamp offset — all over the voxel's points in the same
+// stable (key, index) order
+struct VoxAttrs {
+    const float4* rgb;
+    const float* intensity;
+    const float* timestamps;
+    float4* rgb_mean;    // per sorted position (run head), compacted afterwards
+    float* intensity_med;
+    float* ts_mean;
+};
+
+__device__ __forceinline__ uint32_t float_key(float f) {  // order-preserving float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// rank-th smallest (0-based) intensity of the run [j0, j1) by radix selection on the ordered bits:
+// 32 passes over the run, no scratch, exact for any run length (what nth_element returns)
+__device__ float run_select(const float* __restrict__ v, const uint32_t* __restrict__ svals, uint32_t j0, uint32_t j1,
+                            uint32_t rank) {
+    uint32_t prefix = 0, mask = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t b = 1u << bit;
+        uint32_t zeros = 0;
+        for (uint32_t j = j0; j < j1; ++j) {
+            const uint32_t k = float_key(__ldg(v + svals[j]));
+            zeros += ((k & mask) == prefix) && !(k & b);
+        }
+        if (rank >= zeros) {
+            rank -= zeros;
+            prefix |= b;
+        }
+        mask |= b;
+    }
+    return key_float(prefix);
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __restrict__ pts,
                                                                 const KeyT* __restrict__ skeys,
                                                                 const uint32_t* __restrict__ svals, uint32_t n_valid,
                                                                 float min_count, uint32_t* __restrict__ flags,
-                                                                float4* __restrict__ means) {
+                                                                float4* __restrict__ means, VoxAttrs at) {
     const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
     if (i >= n_valid) return;
     const KeyT key = skeys[i];
@@ -197,16 +237,45 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __
     if (i == 0 || skeys[i - 1] != key) {
         // PointType point_sum = Zero; point_sum += points[idx] in sorted order — :193-201
         float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
-        for (uint32_t j = i; j < n_valid && skeys[j] == key; ++j) {
+        uint32_t j = i;
+        for (; j < n_valid && skeys[j] == key; ++j) {
             const float4 p = __ldg(pts + svals[j]);
             sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
         }
         if (sw >= min_count) {  // :204
             flag = 1;
             means[i] = make_float4(__fdiv_rn(sx, sw), __fdiv_rn(sy, sw), __fdiv_rn(sz, sw), __fdiv_rn(sw, sw));
+            if (at.rgb) {
+                float r = 0.f, g = 0.f, b = 0.f, a = 0.f;
+                for (uint32_t t = i; t < j; ++t) {
+                    const float4 c = __ldg(at.rgb + svals[t]);
+                    r = __fadd_rn(r, c.x); g = __fadd_rn(g, c.y); b = __fadd_rn(b, c.z); a = __fadd_rn(a, c.w);
+                }
+                at.rgb_mean[i] = make_float4(__fdiv_rn(r, sw), __fdiv_rn(g, sw), __fdiv_rn(b, sw), __fdiv_rn(a, sw));
+            }
+            if (at.timestamps) {
+                float ts = 0.f;
+                for (uint32_t t = i; t < j; ++t) ts = __fadd_rn(ts, __ldg(at.timestamps + svals[t]));
+                at.ts_mean[i] = __fdiv_rn(ts, sw);
+            }
+            if (at.intensity) {
+                const uint32_t len = j - i, mid = len / 2;
+                const float up = run_select(at.intensity, svals, i, j, mid);
+                at.intensity_med[i] = (len & 1u) ? up
+                                                 : __fmul_rn(0.5f, __fadd_rn(run_select(at.intensity, svals, i, j, mid - 1), up));
+            }
         }
     }
     flags[i] = flag;
+}
+
+__global__ void __launch_bounds__(VX_THREADS) compact_float_kernel(const float* __restrict__ in,
+                                                                   const uint32_t* __restrict__ flags,
+                                                                   const uint32_t* __restrict__ pos, uint32_t n,
+                                                                   float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i]) out[pos[i]] = in[i];
 }
 
 __global__ void __launch_bounds__(VX_THREADS) compact_float4_kernel(const float4* __restrict__ in,
@@ -232,6 +301,26 @@ __global__ void __launch_bounds__(VX_THREADS) box_flag_kernel(const float4* __re
     flags[i] = keep;
 }
 
+// order given by idx: dst[j] = src[idx[j]], in 4-byte words (points 4 words, covariances 16)
+__global__ void __launch_bounds__(VX_THREADS) gather_words_kernel(const uint32_t* __restrict__ src, int words,
+                                                                  const int32_t* __restrict__ idx, size_t total,
+                                                                  uint32_t* __restrict__ dst) {
+    const size_t t = (size_t)blockIdx.x * VX_THREADS + threadIdx.x;
+    if (t >= total) return;
+    const size_t j = t / words;
+    const int w = (int)(t - j * words);
+    dst[t] = __ldg(src + (size_t)__ldg(idx + j) * words + w);
+}
+__global__ void __launch_bounds__(VX_THREADS) gather_vec4_kernel(const uint4* __restrict__ src, int vecs,
+                                                                 const int32_t* __restrict__ idx, size_t total,
+                                                                 uint4* __restrict__ dst) {
+    const size_t t = (size_t)blockIdx.x * VX_THREADS + threadIdx.x;
+    if (t >= total) return;
+    const size_t j = t / vecs;
+    const int w = (int)(t - j * vecs);
+    dst[t] = __ldg(src + (size_t)__ldg(idx + j) * vecs + w);
+}
+
 int bits_for(unsigned long long v) {  // bits needed to represent values in [0, v]
     int b = 0;
     while (v) {
@@ -241,9 +330,18 @@ int bits_for(unsigned long long v) {  // bits needed to represent values in [0, 
     return b;
 }
 
+struct VoxAttrIO {
+    const float4* rgb = nullptr;
+    const float* intensity = nullptr;
+    const float* timestamps = nullptr;
+    float4* out_rgb = nullptr;
+    float* out_intensity = nullptr;
+    float* out_timestamps = nullptr;
+};
+
 template <typename KeyT>
 void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
-                     uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev) {
+                     uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev, const VoxAttrIO& io) {
     cudaStream_t st = q->stream;
     const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
     KeyT* keys_a = q->take<KeyT>(n);
@@ -256,6 +354,13 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     uint32_t* pos = q->take<uint32_t>(n);
     uint32_t* scan_tmp2 = q->take<uint32_t>(scan_scratch_elems(n));
     float4* means = q->take<float4>(n);
+    VoxAttrs at{};
+    at.rgb = io.rgb;
+    at.intensity = io.intensity;
+    at.timestamps = io.timestamps;
+    if (io.rgb) at.rgb_mean = q->take<float4>(n);
+    if (io.intensity) at.intensity_med = q->take<float>(n);
+    if (io.timestamps) at.ts_mean = q->take<float>(n);
 
     voxel_key_kernel<KeyT><<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, inv, geom, keys_a);
     SPX_LAUNCH_CHECK();
@@ -278,13 +383,28 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     // kin / vin now hold the sorted (key, index) pairs; dropped points (invalid key) sit at the end
     if (n_valid > 0) {
         voxel_mean_kernel<KeyT><<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count,
-                                                                                  flags, means);
+                                                                                  flags, means, at);
         SPX_LAUNCH_CHECK();
     }
     exclusive_scan_u32(st, flags, pos, n_valid, scan_tmp2, total_dev);
     if (n_valid > 0) {
         compact_float4_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(means, flags, pos, n_valid, out);
         SPX_LAUNCH_CHECK();
+        if (io.rgb) {
+            compact_float4_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(at.rgb_mean, flags, pos, n_valid,
+                                                                                     io.out_rgb);
+            SPX_LAUNCH_CHECK();
+        }
+        if (io.intensity) {
+            compact_float_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(at.intensity_med, flags, pos,
+                                                                                    n_valid, io.out_intensity);
+            SPX_LAUNCH_CHECK();
+        }
+        if (io.timestamps) {
+            compact_float_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(at.ts_mean, flags, pos, n_valid,
+                                                                                    io.out_timestamps);
+            SPX_LAUNCH_CHECK();
+        }
     }
 }
 
@@ -292,8 +412,10 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
 
 extern "C" {
 
-int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n_in, float voxel_size, size_t min_voxel_count,
-                         float* out_points, size_t* m_host) {
+int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, float voxel_size,
+                               size_t min_voxel_count, const float* rgb, const float* intensity,
+                               const float* timestamps, float* out_points, float* out_rgb, float* out_intensity,
+                               float* out_timestamps, size_t* m_host) {
     return guard([&] {
         SPX_REQUIRE(q && m_host, "[VoxelGrid::downsampling] null argument");
         if (!(voxel_size > 0.0f)) throw Error(SPX_ERR_INVALID_ARGUMENT, "voxel_size must be positive");
@@ -301,6 +423,8 @@ int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n_in, float 
         *m_host = 0;
         if (n_in == 0) return;
         SPX_REQUIRE(points && out_points, "[VoxelGrid::downsampling] null pointer");
+        SPX_REQUIRE((!rgb || out_rgb) && (!intensity || out_intensity) && (!timestamps || out_timestamps),
+                    "[VoxelGrid::downsampling] attribute given without its output array");
         DeviceGuard dg(q->device);
         cudaStream_t st = q->stream;
         const uint32_t n = (uint32_t)n_in;
@@ -309,8 +433,8 @@ int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n_in, float 
         const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
 
         q->arena_reset();
-        q->arena_reserve((size_t)n * (8 * 2 + 4 * 2 + 4 * 2 + 16) + ((size_t)RADIX * nblocks + 64) * 4 +
-                         (scan_scratch_elems((size_t)RADIX * nblocks) + scan_scratch_elems(n)) * 4 + 16 * 256 + 4096);
+        q->arena_reserve((size_t)n * (8 * 2 + 4 * 2 + 4 * 2 + 16 + 16 + 4 + 4) + ((size_t)RADIX * nblocks + 64) * 4 +
+                         (scan_scratch_elems((size_t)RADIX * nblocks) + scan_scratch_elems(n)) * 4 + 16 * 256 + 8192);
         CoordAcc* acc = q->take<CoordAcc>(1);
         uint32_t* total_dev = q->take<uint32_t>(16);
         char* pin = static_cast<char*>(q->pinned_get(256));
@@ -344,14 +468,27 @@ int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n_in, float 
         const int key_bits = bits_for(has_invalid ? geom.invalid : max_key);
         const float min_count = (float)min_voxel_count;
         float4* out = reinterpret_cast<float4*>(out_points);
+        VoxAttrIO io;
+        io.rgb = reinterpret_cast<const float4*>(rgb);
+        io.intensity = intensity;
+        io.timestamps = timestamps;
+        io.out_rgb = reinterpret_cast<float4*>(out_rgb);
+        io.out_intensity = out_intensity;
+        io.out_timestamps = out_timestamps;
         if (key_bits <= 32)
-            sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev);
+            sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, io);
         else
-            sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev);
+            sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, io);
         SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
         q->sync();
         *m_host = *htotal;
     });
+}
+
+int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n_in, float voxel_size, size_t min_voxel_count,
+                         float* out_points, size_t* m_host) {
+    return spx_voxel_downsample_attrs(q, points, n_in, voxel_size, min_voxel_count, nullptr, nullptr, nullptr,
+                                      out_points, nullptr, nullptr, nullptr, m_host);
 }
 
 int spx_box_filter(spx_queue_t q, const float* points, size_t n_in, float min_distance, float max_distance,
@@ -382,6 +519,28 @@ int spx_box_filter(spx_queue_t q, const float* points, size_t n_in, float min_di
         SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
         q->sync();
         *m_host = *htotal;
+    });
+}
+
+int spx_gather(spx_queue_t q, const void* src, size_t elem_bytes, const int32_t* idx, size_t m, void* dst) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_gather] null queue");
+        SPX_REQUIRE(elem_bytes > 0 && elem_bytes % 4 == 0, "[spx_gather] elem_bytes must be a positive multiple of 4");
+        if (m == 0) return;
+        SPX_REQUIRE(src && idx && dst, "[spx_gather] null pointer");
+        DeviceGuard dg(q->device);
+        const bool vec = elem_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(src) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+        if (vec) {
+            const size_t total = m * (elem_bytes / 16);
+            gather_vec4_kernel<<<div_up(total, VX_THREADS), VX_THREADS, 0, q->stream>>>(
+                static_cast<const uint4*>(src), (int)(elem_bytes / 16), idx, total, static_cast<uint4*>(dst));
+        } else {
+            const size_t total = m * (elem_bytes / 4);
+            gather_words_kernel<<<div_up(total, VX_THREADS), VX_THREADS, 0, q->stream>>>(
+                static_cast<const uint32_t*>(src), (int)(elem_bytes / 4), idx, total, static_cast<uint32_t*>(dst));
+        }
+        SPX_LAUNCH_CHECK();
     });
 }
 

@@ -129,3 +129,75 @@ def test_box_filter(spx, q, bundled):
     cloud = spx.PointCloudShared(q, raw)
     spx.PreprocessFilter(q).box_filter(cloud, 0.5, 50.0)
     assert np.array_equal(cloud.points_host(), oracle.box_filter(raw, 0.5, 50.0))
+
+
+def test_voxel_attributes_vs_oracle(spx, q, bundled):
+    """Cloud overload (voxel_downsampling.hpp:220-288): mean RGB, MEDIAN intensity, mean timestamp per
+    voxel in the stable order — bit-exact vs the oracle, incl. even / odd run lengths and ties."""
+    pts = bundled["source_raw_head"]
+    rs = np.random.RandomState(3)
+    n = len(pts)
+    rgb = rs.uniform(0, 1, (n, 4)).astype(np.float32)
+    inten = np.round(rs.uniform(0, 255, n)).astype(np.float32)  # many ties
+    ts = rs.uniform(0, 100, n).astype(np.float32)
+    for voxel, minc in ((0.5, 1), (1.0, 2), (3.0, 1)):
+        cloud = spx.PointCloudShared(q, pts)
+        cloud.set_rgb(rgb)
+        cloud.set_intensities(inten)
+        cloud.set_timestamp_offsets(ts)
+        vg = spx.VoxelGrid(q, voxel)
+        vg.set_min_voxel_count(minc)
+        out = vg.downsampling(cloud)
+        o_p, o_rgb, o_int, o_ts = oracle.voxel_downsample_attrs(pts, voxel, minc, rgb, inten, ts)
+        assert out.size() == len(o_p)
+        assert np.array_equal(out.points_host(), o_p)
+        assert np.array_equal(out.rgb.download(), o_rgb)
+        assert np.array_equal(out.intensities.download(), o_int)
+        assert np.array_equal(out.timestamp_offsets.download(), o_ts)
+    # subset of attributes
+    cloud = spx.PointCloudShared(q, pts)
+    cloud.set_intensities(inten)
+    out = spx.VoxelGrid(q, 1.0).downsampling(cloud)
+    o_p, _, o_int, _ = oracle.voxel_downsample_attrs(pts, 1.0, 1, None, inten, None)
+    assert np.array_equal(out.points_host(), o_p) and np.array_equal(out.intensities.download(), o_int)
+    assert not out.has_rgb() and not out.has_timestamps()
+
+
+def test_voxel_reference_attribute_known_answer(spx, q):
+    """T/test_downsampling_filters.cpp:27-88 through the C-ABI."""
+    pts = np.array([[0.10, 0, 0, 1], [0.40, 0, 0, 1], [1.10, 0, 0, 1], [1.40, 0, 0, 1], [0.20, 0, 0, 1]], np.float32)
+    cloud = spx.PointCloudShared(q, pts)
+    cloud.set_rgb(np.array([[10, 20, 30, 1], [20, 40, 60, 1], [30, 60, 90, 1], [50, 70, 90, 1], [70, 80, 90, 1]], np.float32))
+    cloud.set_intensities(np.array([1, 3, 5, 7, 100], np.float32))
+    cloud.set_timestamp_offsets(np.array([0, 2, 4, 6, 8], np.float32))
+    vg = spx.VoxelGrid(q, 1.0)
+    vg.set_min_voxel_count(2)
+    out = vg.downsampling(cloud)
+    assert out.size() == 2 and out.has_rgb() and out.has_intensity() and out.has_timestamps()
+    p = out.points_host()
+    first = int(np.argmin(np.abs(p[:, 0] - 0.233333)))
+    assert abs(p[first, 0] - 0.233333) < 1e-5
+    assert abs(out.intensities.download()[first] - 3.0) < 1e-5
+    assert abs(out.timestamp_offsets.download()[first] - 3.333333) < 1e-5
+    assert np.allclose(out.rgb.download()[first, :3], [33.333333, 46.666667, 60.0], atol=1e-5)
+
+
+def test_random_sampling_matches_reference_rng_stream(spx, q, bundled):
+    """PreprocessFilter::random_sampling: the selected set equals the oracle's (libstdc++ mt19937(1234) +
+    uniform_int_distribution<size_t>), the RNG state carries over between calls, order is preserved."""
+    pts = bundled["source_ds"]
+    n = len(pts)
+    cloud = spx.PointCloudShared(q, pts)
+    cloud.set_intensities(np.arange(n, dtype=np.float32))
+    f = spx.PreprocessFilter(q)
+    rng = oracle.Rng(1234)
+    for num in (1000, 1000, 17):
+        out = f.random_sampling(cloud, num)
+        keep = rng.random_sampling_flags(n, num).astype(bool)
+        assert out.size() == num
+        assert np.array_equal(out.points_host(), pts[keep])
+        assert np.array_equal(out.intensities.download(), np.arange(n, dtype=np.float32)[keep])
+    assert f.random_sampling(cloud, n + 5) is cloud  # nothing drawn when the request covers the cloud
+    f.set_random_seed(99)
+    out = f.random_sampling(cloud, 50)
+    assert np.array_equal(out.points_host(), pts[oracle.Rng(99).random_sampling_flags(n, 50).astype(bool)])

@@ -383,3 +383,28 @@ def test_fused_exchange_across_two_gpus(spx, pair):
     dt, da = pose_delta(ref.T, outs[0].T)
     assert dt < 1e-6 and da < 1e-6 and outs[0].inlier == ref.inlier
     comms.close()
+
+
+def test_example_registration_pipeline_with_random_sampling(spx, q, pair, bundled):
+    """E/example_registration.cpp as shipped (SURVEY §8(d) cfg 1 (i)): the pipeline's default random
+    sampling draws 1000 source points from mt19937(1234); same subset as the oracle, same pose."""
+    pp = spx.RegistrationPipelineParams()
+    pp.registration.max_iterations = 10
+    pp.registration.optimization_method = spx.OptimizationMethod.LEVENBERG_MARQUARDT
+    pp.registration.robust.type = spx.RobustLossType.GEMAN_MCCLURE
+    pp.robust.auto_scale = True
+    pp.robust.init_scale, pp.robust.min_scale, pp.robust.auto_scaling_iter = 10.0, 2.5, 3
+    assert pp.random_sampling.enable and pp.random_sampling.num == 1000  # reference defaults
+    pipe = spx.RegistrationPipeline(q, pp)
+    res = pipe.align(pair["src"], pair["tgt"], pair["tree"], np.eye(4))
+    keep = oracle.Rng(1234).random_sampling_flags(len(pair["src_h"]), 1000).astype(bool)
+    inp = pipe.get_registration_input_point_cloud()
+    assert inp.size() == 1000 and np.array_equal(inp.points_host(), pair["src_h"][keep])
+    assert np.array_equal(inp.covs_host(), pair["cov_s"][keep])
+    P = oracle.default_params(reg_type=3, loss=4, opt_method=1, max_iterations=10)
+    ores = oracle.align_robust(P, pair["src_h"][keep], pair["cov_s"][keep], pair["tgt_h"], pair["cov_t"], None,
+                               pair["otree"], np.eye(4), 10.0, 2.5, 3)
+    dt, da = pose_delta(ores["T"], res.T)
+    assert dt < 1e-5 and da < 1e-5 and res.iterations == ores["iterations"]
+    dt, da = pose_delta(bundled["T_target_source"], res.T)
+    assert dt < 0.10 and np.degrees(da) < 0.5
