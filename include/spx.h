@@ -279,6 +279,11 @@ SPX_API int spx_registration_align(spx_registration_t reg, const float* src_poin
  * first iteration launch to just after the last), the number of iteration kernels launched and
  * the number of outer iterations that did work: bench.py's live per-launch duration. */
 SPX_API int spx_registration_last_timing(spx_registration_t reg, float* loop_ms, int32_t* launches, int32_t* iterations);
+/* tuning aid: per-iteration phase timestamps of the cooperative align kernel (globaltimer ns, latest
+ * block to reach each phase): times_host[it][8] = {start, first-pass search done, cooperative search done,
+ * accumulate done, partials written, grid barrier passed, fold done, solve done}.  enable != 0 allocates the buffer (affects later
+ * aligns on this handle), enable == 0 frees it; times_host nullable. */
+SPX_API int spx_registration_phase_times(spx_registration_t reg, int enable, uint64_t* times_host, int max_iterations);
 /* neighbours cached by the last align / linearise on this handle (registration.hpp:365), device
  * pointers valid until the next call: used by compute_error_frozen-style callers */
 SPX_API int spx_registration_neighbors(spx_registration_t reg, const int32_t** nn_idx, const float** nn_dist, size_t* n);

@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
                                              C.POINTER(RegistrationResultC), hostf]),
         "spx_registration_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                                    C.POINTER(C.c_int32)]),
+        "spx_registration_phase_times": (C.c_int, [vp, C.c_int, vp, C.c_int]),
         "spx_registration_neighbors": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "spx_registration_shard_begin": (C.c_int, [vp, f32p, f32p, sz, f32p, f32p, f32p, sz, vp, hostf, C.c_float]),
         "spx_registration_shard_linearize": (C.c_int, [vp, vp]),

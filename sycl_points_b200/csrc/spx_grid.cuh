@@ -112,6 +112,38 @@ struct BestK {
     }
 };
 
+// Small k (<= K): the sorted candidate list lives in REGISTERS as packed 64-bit keys
+//   key = ((dist bits) << 32 | index) + 1          (dist >= 0, so its bits order like the value;
+//                                                   the index in the low word breaks ties -> (dist, index))
+// and an insertion is K predicated compare-exchanges — no memory traffic, no data-dependent loop, so
+// lanes of a warp never diverge inside it.  Lists shorter than K are padded at the FRONT with key 0
+// (below every real key), which keeps the k-th best in the fixed register key[K-1].
+template <int K>
+struct BestR {
+    unsigned long long key[K];
+    static constexpr unsigned long long EMPTY = ((0x7f7fffffull << 32) | 0xffffffffull) + 1ull;  // FLT_MAX, -1
+    __device__ __forceinline__ void init(int k) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) key[j] = (j < K - k) ? 0ull : EMPTY;
+    }
+    __device__ __forceinline__ float worst() const { return __uint_as_float((uint32_t)((key[K - 1] - 1ull) >> 32)); }
+    __device__ __forceinline__ void offer(float ds, int idx, uint32_t) {
+        unsigned long long c = (((unsigned long long)__float_as_uint(ds) << 32) | (unsigned long long)(uint32_t)idx) + 1ull;
+        if (c >= key[K - 1]) return;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            // the same point re-offered by a coarser level: drop it (it sinks off the end as "infinity")
+            if (c == key[j]) c = ~0ull;
+            const unsigned long long lo = c < key[j] ? c : key[j];
+            const unsigned long long hi = c < key[j] ? key[j] : c;
+            key[j] = lo;
+            c = hi;
+        }
+    }
+    __device__ __forceinline__ float dist_at(int j) const { return __uint_as_float((uint32_t)((key[j] - 1ull) >> 32)); }
+    __device__ __forceinline__ int idx_at(int j) const { return (int)(uint32_t)((key[j] - 1ull) & 0xffffffffull); }
+};
+
 constexpr int GRID_SEG_CHUNK = 9;  // the merged first pass (3x3 rows) fits one chunk
 constexpr int GRID_BATCH = 4;  // candidate loads in flight per thread
 
@@ -314,6 +346,233 @@ __device__ __forceinline__ void grid_search_levels(const GridLevels& g, float qx
     }
 }
 
+// ------------------------------------------------------------------ ICP nearest neighbour
+// k = 1 search of the registration loop (kdtree.hpp:463-553 with k = 1, bounded by
+// max_correspondence_distance: registration.hpp:584 rejects anything farther).  Same exactness
+// argument as grid_search; three additions that matter for the iteration kernel:
+//  * warm start: the previous iteration's correspondence is offered first.  It is a real target
+//    point, so it only tightens the pruning bound — the answer is unchanged — and after the first
+//    iteration most queries touch one or two cells instead of 27;
+//  * first pass = the 3x3 rows around the query's cell, rows and x-ranges pruned against the bound,
+//    every `start` look-up issued at once: a typical query is 3-4 dependent L2 round trips;
+//  * queries the first pass cannot finish (nothing nearby: scan edges, sparse far range; ~8 % of a
+//    LiDAR scan, and spatially clustered, i.e. concentrated in a few warps) are NOT continued by
+//    their lane.  The iteration kernel appends them to a work list and, after a grid barrier, all
+//    warps of the grid drain it: one query per warp at a time, shell rows and candidates scanned 32
+//    wide (load-balanced by a prefix sum over the rows' candidate counts).  The tail the whole grid
+//    used to wait for — one warp owning dozens of expensive queries — is spread over every SM.
+
+__device__ __forceinline__ unsigned long long best_key(float d, int i) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)i;  // i = -1 sorts last
+}
+
+// returns true when `best` is final
+__device__ __forceinline__ bool icp_first_pass(const GridView& g, float qx, float qy, float qz, Best1& best,
+                                               float max_radius) {
+    const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
+    const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
+    const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
+    const float INF = __int_as_float(0x7f800000);
+    const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+    const float reach = max_radius + margin;
+    const float reach2 = reach < 1.8e19f ? __fmul_rn(reach, reach) : INF;
+    const float lim2 = fminf(best.d, reach2);
+    // Row (y, z) can hold something better than the bound only if its distance g_yz to the query
+    // satisfies g_yz <= sqrt(lim2) + margin =: L, and then only in cells within
+    // w = sqrt(L^2 - g_yz^2) + margin of the query along x (w is never smaller than grid_search's
+    // sqrt(lim2 - (g_yz - margin)^2) + margin: 2 margin (sqrt(lim2) + margin - g_yz) >= 0).  Pruning
+    // arithmetic only pays when the bound is tighter than the block being looked at.
+    const bool prune = lim2 < __fmul_rn(4.0f, __fmul_rn(g.cell, g.cell));
+    const float L = prune ? sqrtf(lim2) + margin : INF;
+    const float L2 = prune ? __fmul_rn(L, L) : INF;
+    float gy2[3], gz2[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const float a = prune ? axis_gap(qy, g.oy, g.cell, cy + v - 1) : 0.0f;
+        const float b = prune ? axis_gap(qz, g.oz, g.cell, cz + v - 1) : 0.0f;
+        gy2[v] = __fmul_rn(a, a);
+        gz2[v] = __fmul_rn(b, b);
+    }
+    uint32_t ls[9], le[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int zz = cz + (t / 3) - 1, yy = cy + (t % 3) - 1;
+        bool ok = zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy;
+        int xa = max(cx - 1, 0), xb = min(cx + 1, g.dx - 1);
+        if (prune) {
+            const float g2 = __fadd_rn(gy2[t % 3], gz2[t / 3]);
+            ok = ok && g2 <= L2;
+            if (ok) {
+                const float w = sqrtf(fmaxf(L2 - g2, 0.0f)) + margin;
+                xa = max(xa, grid_coord(qx - w, g.ox, g.inv, g.dx));
+                xb = min(xb, grid_coord(qx + w, g.ox, g.inv, g.dx));
+                ok = xa <= xb;
+            }
+        }
+        const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
+        ls[t] = ok ? __ldg(g.start + row + xa) : 0u;
+        le[t] = ok ? __ldg(g.start + row + xb + 1) : 0u;
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        for (uint32_t j = ls[t]; j < le[t]; j += 4) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j + u < le[t]) p[u] = __ldg(g.pts + j + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j + u < le[t])
+                    best.offer(dist_sq(qx, qy, qz, p[u].x, p[u].y, p[u].z), __float_as_int(p[u].w), j + u);
+        }
+    }
+    const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, 1, g.dx),
+                                    shell_bound_axis(qy, g.oy, g.cell, cy, 1, g.dy)),
+                              shell_bound_axis(qz, g.oz, g.cell, cz, 1, g.dz));
+    if (bound == INF) return true;
+    const float bs = bound - margin;
+    return (bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) || bs >= max_radius;
+}
+
+// Warp-cooperative continuation for ONE query (all arguments warp-uniform, every lane calls it):
+// shells r = 2.. on the finest level, then r = 1.. on each coarser level, rows of a shell spread
+// over the lanes, candidates of all rows scanned 32 wide.  `best` is warp-uniform on entry and exit.
+static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float qx, float qy, float qz, Best1& best,
+                                                    float max_radius, uint32_t* dbg = nullptr) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float INF = __int_as_float(0x7f800000);
+    for (int l = 0; l < gl.n_levels; ++l) {
+        const GridView& g = gl.lv[l];
+        const bool last = (l == gl.n_levels - 1);
+        const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
+        const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
+        const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
+        const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+        const float reach = max_radius + margin;
+        const float reach2 = reach < 1.8e19f ? __fmul_rn(reach, reach) : INF;
+        const int r_begin = (l == 0) ? 2 : 1;
+        const int r_max = last ? (1 << 20) : GRID_LEVEL_RINGS;
+        for (int r = r_begin;; ++r) {
+            const bool merged = (r == 1);  // first shell on a coarser level: the whole 3x3x3 block
+            const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
+            const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
+            const int ny = y1 - y0 + 1;
+            const int nrows = (z1 - z0 + 1) * ny;
+            Best1 mine = best;  // per-lane candidate, merged after the shell
+            const float lim2 = fminf(best.d, reach2);
+            if (dbg) {
+                dbg[1] += 1;
+                dbg[2] += (uint32_t)nrows;
+            }
+            for (int base = 0; base < nrows; base += 32) {
+                const int t = base + lane;
+                uint32_t sA = 0, eA = 0, sB = 0, eB = 0;
+                if (t < nrows) {
+                    const int zz = z0 + t / ny, yy = y0 + t % ny;
+                    const bool edge = merged || (zz - cz == r) || (cz - zz == r) || (yy - cy == r) || (cy - yy == r);
+                    int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
+                    bool ok = true;
+                    if (lim2 < 1.0e30f) {
+                        const float gz = axis_gap(qz, g.oz, g.cell, zz);
+                        const float gy = axis_gap(qy, g.oy, g.cell, yy);
+                        const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
+                        const float gyz2 = __fmul_rn(gyz, gyz);
+                        ok = gyz2 <= lim2;
+                        const float w = sqrtf(fmaxf(lim2 - gyz2, 0.0f)) + margin;
+                        xa = max(xa, grid_coord(qx - w, g.ox, g.inv, g.dx));
+                        xb = min(xb, grid_coord(qx + w, g.ox, g.inv, g.dx));
+                        ok = ok && xa <= xb;
+                    }
+                    if (ok) {
+                        const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
+                        if (edge) {
+                            sA = __ldg(g.start + row + xa);
+                            eA = __ldg(g.start + row + xb + 1);
+                        } else {  // interior row of a later shell: only the two end cells are new
+                            if (cx - r >= xa) {
+                                sA = __ldg(g.start + row + (cx - r));
+                                eA = __ldg(g.start + row + (cx - r) + 1);
+                            }
+                            if (cx + r <= xb) {
+                                sB = __ldg(g.start + row + (cx + r));
+                                eB = __ldg(g.start + row + (cx + r) + 1);
+                            }
+                        }
+                    }
+                }
+                const uint32_t cA = eA - sA, cnt = cA + (eB - sB);
+                uint32_t inc = cnt;  // inclusive prefix sum of the candidate counts over the lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const uint32_t total = __shfl_sync(FULL, inc, 31);
+                if (dbg) dbg[3] += total;
+                for (uint32_t cb = 0; cb < total; cb += 32) {
+                    const uint32_t kk = cb + lane;
+                    const bool live = kk < total;
+                    const uint32_t key = live ? kk : 0u;
+                    int owner = 0;  // number of lanes whose inclusive sum is <= key
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) {
+                        const uint32_t v = __shfl_sync(FULL, inc, owner + sft - 1);
+                        if (v <= key) owner += sft;
+                    }
+                    owner = min(owner, 31);
+                    const uint32_t o_inc = __shfl_sync(FULL, inc, owner);
+                    const uint32_t o_cnt = __shfl_sync(FULL, cnt, owner);
+                    const uint32_t o_cA = __shfl_sync(FULL, cA, owner);
+                    const uint32_t o_sA = __shfl_sync(FULL, sA, owner);
+                    const uint32_t o_sB = __shfl_sync(FULL, sB, owner);
+                    if (live) {
+                        const uint32_t jj = key - (o_inc - o_cnt);
+                        const uint32_t pos = jj < o_cA ? o_sA + jj : o_sB + (jj - o_cA);
+                        const float4 p = __ldg(g.pts + pos);
+                        mine.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), pos);
+                    }
+                }
+            }
+            // merge the lanes' candidates: minimum by (dist, index)
+            unsigned long long k = best_key(mine.d, mine.i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long v = __shfl_xor_sync(FULL, k, o);
+                k = v < k ? v : k;
+            }
+            const unsigned win = __ballot_sync(FULL, best_key(mine.d, mine.i) == k);
+            const int wl = __ffs(win) - 1;
+            best.d = __shfl_sync(FULL, mine.d, wl);
+            best.i = __shfl_sync(FULL, mine.i, wl);
+            best.p = __shfl_sync(FULL, mine.p, wl);
+
+            const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, r, g.dx),
+                                            shell_bound_axis(qy, g.oy, g.cell, cy, r, g.dy)),
+                                      shell_bound_axis(qz, g.oz, g.cell, cz, r, g.dz));
+            if (bound == INF) return;  // whole grid visited
+            const float bs = bound - margin;
+            if (bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) return;
+            if (bs >= max_radius) return;  // everything within max_radius has been seen
+            if (r >= r_max) break;         // next (coarser) level
+        }
+    }
+}
+
+// Per-lane part of the search: warm start (warm_pos != 0xffffffff offers that sorted position
+// first) + pruned first pass.  Returns true when `best` is final; otherwise `best` holds the bound
+// reached so far and the query goes to the cooperative continuation.
+__device__ __forceinline__ bool icp_fast(const GridLevels& gl, float qx, float qy, float qz, uint32_t warm_pos,
+                                         float max_radius, Best1& best) {
+    const GridView& g = gl.lv[0];
+    best.init();
+    if (warm_pos != 0xffffffffu) {
+        const float4 p = __ldg(g.pts + warm_pos);
+        best.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), warm_pos);
+    }
+    return icp_first_pass(g, qx, qy, qz, best, max_radius);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace spx
@@ -326,6 +585,6 @@ struct spx_index_s {
     float4* sorted[spx::GRID_MAX_LEVELS] = {};
     uint32_t* start[spx::GRID_MAX_LEVELS] = {};
     size_t ncells[spx::GRID_MAX_LEVELS] = {};
-    int64_t occupied = 0;  // occupied cells of the finest level
+    unsigned long long* occ_dev = nullptr;  // occupied cells of the finest level (device counter)
     spx::GridLevels levels{};
 };

@@ -2,6 +2,7 @@
 // GPU-resident exact index that stands in for knn::KDTree (kdtree.hpp:142-562) behind the same
 // KNNBase contract (knn.hpp:14-61).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "spx_grid.cuh"
@@ -17,15 +18,44 @@ constexpr int BF_TILE = 2048;  // float4 targets staged per step (32 KB of share
 
 // One thread owns QPT queries and streams every target tile out of shared memory (one broadcast
 // LDS.128 per target feeds QPT distance evaluations).  Candidate lists live in the thread's rows of
-// the output arrays; only the k-th best is cached in registers, so the steady-state inner loop is
-// 3 sub + 1 mul + 2 fma + 1 compare per (query, target) pair.  Targets are scanned in index order
-// with a strict '<', which yields exactly the (dist, index) order of bruteforce.hpp:71-83.
-template <int QPT>
+// the output arrays; only the k-th best is cached in registers.  Targets are tested BF_BATCH at a
+// time with no branch per pair: the steady state is 3 sub + 1 mul + 2 fma + 1 predicated compare
+// per (query, target) pair and one branch per BF_BATCH x QPT pairs; a batch with a hit (rare once the
+// lists are warm: ~k ln(N/k) inserts per query in total) replays its pairs in index order with a
+// strict '<', which yields exactly the (dist, index) order of bruteforce.hpp:71-83.
+// PACKED: two queries share one packed-FP32 instruction stream (sm_100 FADD2 / FMUL2 / FFMA2 via
+// sub/mul/fma.rn.f32x2 — IEEE round-to-nearest per element, so results stay bit-identical).
+constexpr int BF_BATCH = 4;
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// fma(dz,dz,fma(dy,dy,dx*dx)) for two queries at once against one target
+__device__ __forceinline__ unsigned long long dist_sq2(unsigned long long qx, unsigned long long qy, unsigned long long qz,
+                                                       float px, float py, float pz) {
+    const unsigned long long PX = pack2(px, px), PY = pack2(py, py), PZ = pack2(pz, pz);
+    unsigned long long dx, dy, dz, r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(qx), "l"(PX));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(qy), "l"(PY));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(qz), "l"(PZ));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(dx));
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(dy), "l"(r));
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(dz), "l"(r));
+    return r;
+}
+
+template <int QPT, bool PACKED>
 __global__ void __launch_bounds__(BF_THREADS) knn_bruteforce_kernel(const float4* __restrict__ queries, uint32_t nq,
                                                                     const float4* __restrict__ targets, uint32_t nt,
                                                                     int k, Xform T, int has_T,
                                                                     int32_t* __restrict__ idx,
                                                                     float* __restrict__ dist) {
+    static_assert(!PACKED || QPT % 2 == 0, "packed variant pairs queries");
     __shared__ float4 tile[BF_TILE];
     const uint32_t first = (blockIdx.x * BF_THREADS + threadIdx.x) * QPT;
 
@@ -48,6 +78,15 @@ __global__ void __launch_bounds__(BF_THREADS) knn_bruteforce_kernel(const float4
             wd[u] = -1.0f;  // nothing compares below it: the slot never inserts
         }
     }
+    unsigned long long qx2[QPT / 2 + 1], qy2[QPT / 2 + 1], qz2[QPT / 2 + 1];
+    if (PACKED) {
+#pragma unroll
+        for (int u = 0; u < QPT / 2; ++u) {
+            qx2[u] = pack2(qx[2 * u], qx[2 * u + 1]);
+            qy2[u] = pack2(qy[2 * u], qy[2 * u + 1]);
+            qz2[u] = pack2(qz[2 * u], qz[2 * u + 1]);
+        }
+    }
 
     for (uint32_t base = 0; base < nt; base += BF_TILE) {
         __syncthreads();
@@ -59,25 +98,45 @@ __global__ void __launch_bounds__(BF_THREADS) knn_bruteforce_kernel(const float4
         }
         __syncthreads();
         const int lim = min((uint32_t)BF_TILE, nt - base);
-        const int lim4 = (lim + 3) & ~3;  // sentinels cover the padding
-#pragma unroll 4
-        for (int t = 0; t < lim4; ++t) {
-            const float4 p = tile[t];
+        const int limb = (lim + BF_BATCH - 1) / BF_BATCH * BF_BATCH;  // sentinels cover the padding
+#pragma unroll 2
+        for (int t = 0; t < limb; t += BF_BATCH) {
+            float ds[BF_BATCH][QPT];
+            bool any = false;
 #pragma unroll
-            for (int u = 0; u < QPT; ++u) {
-                const float ds = dist_sq(qx[u], qy[u], qz[u], p.x, p.y, p.z);
-                if (ds < wd[u]) {
-                    float* d = drow[u];
-                    int32_t* id = irow[u];
-                    int pos = k - 1;
-                    while (pos > 0 && ds < d[pos - 1]) {
-                        d[pos] = d[pos - 1];
-                        id[pos] = id[pos - 1];
-                        --pos;
+            for (int v = 0; v < BF_BATCH; ++v) {
+                const float4 p = tile[t + v];
+                if (PACKED) {
+#pragma unroll
+                    for (int u = 0; u < QPT / 2; ++u)
+                        unpack2(dist_sq2(qx2[u], qy2[u], qz2[u], p.x, p.y, p.z), ds[v][2 * u], ds[v][2 * u + 1]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < QPT; ++u) ds[v][u] = dist_sq(qx[u], qy[u], qz[u], p.x, p.y, p.z);
+                }
+#pragma unroll
+                for (int u = 0; u < QPT; ++u) any |= ds[v][u] < wd[u];
+            }
+            if (any) {
+#pragma unroll
+                for (int u = 0; u < QPT; ++u) {
+#pragma unroll
+                    for (int v = 0; v < BF_BATCH; ++v) {
+                        const float d1 = ds[v][u];
+                        if (d1 < wd[u]) {
+                            float* d = drow[u];
+                            int32_t* id = irow[u];
+                            int pos = k - 1;
+                            while (pos > 0 && d1 < d[pos - 1]) {
+                                d[pos] = d[pos - 1];
+                                id[pos] = id[pos - 1];
+                                --pos;
+                            }
+                            d[pos] = d1;
+                            id[pos] = (int)(base + t + v);
+                            wd[u] = d[k - 1];
+                        }
                     }
-                    d[pos] = ds;
-                    id[pos] = (int)(base + t);
-                    wd[u] = d[k - 1];
                 }
             }
         }
@@ -167,6 +226,85 @@ __global__ void occupied_kernel(const uint32_t* __restrict__ counts, size_t ncel
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(occupied, c);
 }
 
+// ---- cell-size selection without a host round trip per attempt
+// The finest cell edge is chosen so that an occupied cell holds ~2 points.  Occupancy as a function
+// of the cell edge is measured for OCC_CANDS candidate edges in ONE pass: every point sets one bit
+// per candidate in a hashed bitmap of M bits, and the number of occupied cells follows from the
+// fraction of zero bits (linear counting: n_occ ~ -M ln(zeros / M), within ~1 % at the loads used).
+constexpr int OCC_CANDS = 8;
+__constant__ float OCC_FACTOR[OCC_CANDS] = {0.35f, 0.5f, 0.7071f, 1.0f, 1.4142f, 2.0f, 2.8284f, 4.0f};
+
+struct OccPlan {     // written by occ_plan_kernel, read by occ_mark_kernel and by the host
+    float lo[3];
+    float c0;        // volume-heuristic cell edge the candidates are multiples of
+    float ext[3];
+    float max_abs;
+};
+
+__global__ void occ_plan_kernel(const BBoxAcc* __restrict__ acc, OccPlan* __restrict__ plan) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float lo[3], ext[3], max_ext = 0.0f, max_abs = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+        const int ol = acc->mn[a], oh = acc->mx[a];
+        lo[a] = __int_as_float(ol ^ ((ol >> 31) & 0x7fffffff));
+        const float hi = __int_as_float(oh ^ ((oh >> 31) & 0x7fffffff));
+        ext[a] = hi - lo[a];
+        max_ext = fmaxf(max_ext, ext[a]);
+        max_abs = fmaxf(max_abs, fmaxf(fabsf(lo[a]), fabsf(hi)));
+    }
+    if (!(max_ext > 0.0f)) max_ext = 1.0f;
+    double vol = 1.0;
+    for (int a = 0; a < 3; ++a) vol *= (double)fmaxf(ext[a], 0.02f * max_ext);
+    float c0 = (float)cbrt(vol / (2.0 * (double)max(acc->finite, 1u)));
+    c0 = fmaxf(c0, 1e-6f * fmaxf(max_abs, 1.0f));
+    for (int a = 0; a < 3; ++a) {
+        plan->lo[a] = lo[a];
+        plan->ext[a] = ext[a];
+    }
+    plan->c0 = c0;
+    plan->max_abs = max_abs;
+}
+
+__global__ void occ_mark_kernel(const float4* __restrict__ pts, uint32_t n, const OccPlan* __restrict__ plan,
+                                uint32_t* __restrict__ bitmaps, uint32_t words_per_map) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pts + i);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) return;
+    const float rx = p.x - plan->lo[0], ry = p.y - plan->lo[1], rz = p.z - plan->lo[2];
+    const float c0 = plan->c0;
+    const uint32_t mask = words_per_map * 32u - 1u;
+#pragma unroll
+    for (int j = 0; j < OCC_CANDS; ++j) {
+        const float inv = 1.0f / (c0 * OCC_FACTOR[j]);
+        const uint32_t ix = (uint32_t)fminf(rx * inv, 4.0e9f), iy = (uint32_t)fminf(ry * inv, 4.0e9f),
+                       iz = (uint32_t)fminf(rz * inv, 4.0e9f);
+        uint32_t h = ix * 73856093u ^ iy * 19349663u ^ iz * 83492791u;
+        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+        h &= mask;
+        atomicOr(bitmaps + (size_t)j * words_per_map + (h >> 5), 1u << (h & 31u));
+    }
+}
+
+__global__ void occ_count_kernel(const uint32_t* __restrict__ bitmaps, uint32_t words_per_map,
+                                 unsigned int* __restrict__ ones) {
+    const int j = blockIdx.y;
+    unsigned int c = 0;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words_per_map; w += gridDim.x * blockDim.x)
+        c += __popc(bitmaps[(size_t)j * words_per_map + w]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(ones + j, c);
+}
+
+// occupied cells of a finished level = cells whose range in `start` is not empty
+__global__ void occupied_from_start_kernel(const uint32_t* __restrict__ start, size_t ncells, unsigned long long* occupied) {
+    unsigned long long c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (size_t)gridDim.x * blockDim.x)
+        c += start[i + 1] != start[i];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(occupied, c);
+}
+
 // Stable scatter: a point's slot inside its cell is its rank among the cell's points in ORIGINAL
 // index order, so the sorted copy (and therefore the visiting order) is deterministic run to run.
 // Rank = number of earlier points of the same cell; computed with one atomic per point on a
@@ -250,6 +388,43 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_kernel(const GridLevels
     }
 }
 
+// 1 < k <= K: register-resident lists (BestR); the block stages its [queries][k] tile in shared
+// memory and writes it out cooperatively so the global stores coalesce.
+template <int K>
+__global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_kernel(const GridLevels g, const float4* __restrict__ queries,
+                                                                     uint32_t nq, int k, Xform T, int has_T,
+                                                                     int32_t* __restrict__ idx, float* __restrict__ dist) {
+    __shared__ float sd[K * GRID_THREADS];
+    __shared__ int si[K * GRID_THREADS];
+    const uint32_t q0 = blockIdx.x * GRID_THREADS;
+    const uint32_t qi = q0 + threadIdx.x;
+    const float INF = __int_as_float(0x7f800000);
+    float4 q = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (qi < nq) {
+        q = __ldg(queries + qi);
+        if (has_T) q = transform_point(T, q);
+    }
+    BestR<K> best;
+    best.init(k);
+    if (qi < nq && isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && g.lv[0].n > 0)
+        grid_search_levels(g, q.x, q.y, q.z, best, INF);
+    // slots K-k .. K-1 hold the k results in ascending order; row layout [j][thread] is conflict-free
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j >= K - k) {
+            sd[(j - (K - k)) * GRID_THREADS + threadIdx.x] = best.dist_at(j);
+            si[(j - (K - k)) * GRID_THREADS + threadIdx.x] = best.idx_at(j);
+        }
+    }
+    __syncthreads();
+    const uint32_t live = min((uint32_t)GRID_THREADS, nq - q0);
+    for (uint32_t e = threadIdx.x; e < live * (uint32_t)k; e += GRID_THREADS) {
+        const uint32_t ql = e / (uint32_t)k, j = e - ql * (uint32_t)k;
+        dist[(size_t)q0 * k + e] = sd[j * GRID_THREADS + ql];
+        idx[(size_t)q0 * k + e] = si[j * GRID_THREADS + ql];
+    }
+}
+
 // work counters of the k = 1 search (tuning aid): stats[q] = {segments, candidates, shells, last level}
 __global__ void __launch_bounds__(GRID_THREADS) grid_nn_stats_kernel(const GridLevels g, const float4* __restrict__ queries,
                                                                       uint32_t nq, Xform T, int has_T, float max_radius,
@@ -269,14 +444,24 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_nn_stats_kernel(const GridL
 void launch_bruteforce(spx_queue_t q, const float4* queries, uint32_t nq, const float4* targets, uint32_t nt, int k,
                        const Xform& T, int has_T, int32_t* idx, float* dist) {
     if (nq == 0) return;
-    // 2 queries per thread halves the shared-memory traffic per pair; small batches keep 1 so
-    // the grid still covers the SMs
-    const bool two = nq >= (uint32_t)q->sm_count * BF_THREADS * 4;
-    const unsigned blocks = (unsigned)div_up(nq, (size_t)BF_THREADS * (two ? 2 : 1));
-    if (two)
-        knn_bruteforce_kernel<2><<<blocks, BF_THREADS, 0, q->stream>>>(queries, nq, targets, nt, k, T, has_T, idx, dist);
-    else
-        knn_bruteforce_kernel<1><<<blocks, BF_THREADS, 0, q->stream>>>(queries, nq, targets, nt, k, T, has_T, idx, dist);
+    // more queries per thread = fewer shared-memory reads per pair; small batches keep 1 so the grid
+    // still covers the SMs.  SPX_BF_VARIANT (tuning): "q1", "q2", "q4", "p2", "p4" force a variant.
+    int qpt = nq >= (uint32_t)q->sm_count * BF_THREADS * 8 ? 4 : (nq >= (uint32_t)q->sm_count * BF_THREADS * 4 ? 2 : 1);
+    bool packed = qpt >= 2;
+    if (const char* e = std::getenv("SPX_BF_VARIANT")) {
+        packed = e[0] == 'p';
+        qpt = e[1] == '4' ? 4 : (e[1] == '2' ? 2 : 1);
+        if (qpt == 1) packed = false;
+    }
+    const unsigned blocks = (unsigned)div_up(nq, (size_t)BF_THREADS * qpt);
+#define SPX_BF_LAUNCH(Q, P) \
+    knn_bruteforce_kernel<Q, P><<<blocks, BF_THREADS, 0, q->stream>>>(queries, nq, targets, nt, k, T, has_T, idx, dist)
+    if (qpt == 4 && packed) SPX_BF_LAUNCH(4, true);
+    else if (qpt == 4) SPX_BF_LAUNCH(4, false);
+    else if (qpt == 2 && packed) SPX_BF_LAUNCH(2, true);
+    else if (qpt == 2) SPX_BF_LAUNCH(2, false);
+    else SPX_BF_LAUNCH(1, false);
+#undef SPX_BF_LAUNCH
     SPX_LAUNCH_CHECK();
 }
 
@@ -322,40 +507,63 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         const uint32_t n = (uint32_t)nt;
         cudaStream_t st = q->stream;
 
+        // scratch: bbox accumulator, occupancy plan + bitmaps + counters, per-point cell ids, per-cell counts
+        uint32_t map_bits = 1u << 16;
+        while (map_bits < 8u * n && map_bits < (1u << 30)) map_bits <<= 1;
+        const uint32_t words_per_map = map_bits / 32u;
         q->arena_reset();
-        q->arena_reserve(sizeof(BBoxAcc) + 256 + (size_t)n * 4 + 2 * (MAX_CELLS + 64) * 4 +
-                         scan_scratch_elems(MAX_CELLS + 1) * 4 + 4096);
+        q->arena_reserve(sizeof(BBoxAcc) + sizeof(OccPlan) + 1024 + (size_t)OCC_CANDS * words_per_map * 4 + (size_t)n * 4 +
+                         2 * (MAX_CELLS + 64) * 4 + scan_scratch_elems(MAX_CELLS + 1) * 4 + 8192);
         BBoxAcc* acc = q->take<BBoxAcc>(1);
-        unsigned long long* occ_dev = q->take<unsigned long long>(1);
+        OccPlan* plan = q->take<OccPlan>(1);
+        unsigned int* ones = q->take<unsigned int>(OCC_CANDS);
+        uint32_t* bitmaps = q->take<uint32_t>((size_t)OCC_CANDS * words_per_map);
         uint32_t* cell_id = q->take<uint32_t>(n);
         uint32_t* counts = q->take<uint32_t>(MAX_CELLS + 64);
         uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(MAX_CELLS + 1));
 
-        BBoxAcc* hacc = static_cast<BBoxAcc*>(q->pinned_get(sizeof(BBoxAcc) + 64));
+        char* pin = static_cast<char*>(q->pinned_get(1024));
+        BBoxAcc* hacc = reinterpret_cast<BBoxAcc*>(pin);
+        OccPlan* hplan = reinterpret_cast<OccPlan*>(pin + 128);
+        unsigned int* hones = reinterpret_cast<unsigned int*>(pin + 256);
         for (int a = 0; a < 3; ++a) {
             hacc->mn[a] = INT_MAX;
             hacc->mx[a] = INT_MIN;
         }
         hacc->finite = 0;
         hacc->pad = 0;
+        const bool adaptive = !(cell_size > 0.0f);
         SPX_CUDA(cudaMemcpyAsync(acc, hacc, sizeof(BBoxAcc), cudaMemcpyHostToDevice, st));
         bbox_kernel<<<std::min(div_up(n, 256), q->sm_count * 8), 256, 0, st>>>(pts, n, acc);
         SPX_LAUNCH_CHECK();
+        occ_plan_kernel<<<1, 32, 0, st>>>(acc, plan);
+        SPX_LAUNCH_CHECK();
+        if (adaptive) {
+            SPX_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)OCC_CANDS * words_per_map * 4, st));
+            SPX_CUDA(cudaMemsetAsync(ones, 0, OCC_CANDS * sizeof(unsigned int), st));
+            occ_mark_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, plan, bitmaps, words_per_map);
+            SPX_LAUNCH_CHECK();
+            occ_count_kernel<<<dim3(std::min(div_up(words_per_map, 256), 64), OCC_CANDS), 256, 0, st>>>(bitmaps, words_per_map,
+                                                                                                       ones);
+            SPX_LAUNCH_CHECK();
+            SPX_CUDA(cudaMemcpyAsync(hones, ones, OCC_CANDS * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        }
         SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, st));
-        q->sync();
+        SPX_CUDA(cudaMemcpyAsync(hplan, plan, sizeof(OccPlan), cudaMemcpyDeviceToHost, st));
+        q->sync();  // the only host round trip of the build: grid dimensions size the allocations
         const BBoxAcc bb = *hacc;
+        const OccPlan pl = *hplan;
         ix->n = bb.finite;
         L.lv[0].n = bb.finite;
         if (bb.finite == 0) return;
 
         float lo[3], ext[3];
-        float max_ext = 0.0f, max_abs = 0.0f;
+        float max_ext = 0.0f;
+        const float max_abs = pl.max_abs;
         for (int a = 0; a < 3; ++a) {
-            lo[a] = float_from_ordered(bb.mn[a]);
-            const float hi = float_from_ordered(bb.mx[a]);
-            ext[a] = hi - lo[a];
+            lo[a] = pl.lo[a];
+            ext[a] = pl.ext[a];
             max_ext = std::max(max_ext, ext[a]);
-            max_abs = std::max(max_abs, std::max(std::fabs(lo[a]), std::fabs(hi)));
         }
         if (!(max_ext > 0.0f)) max_ext = 1.0f;
 
@@ -398,51 +606,52 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
             ix->ncells[level] = ncells;
         };
 
-        // finest level: ~2 cells per point over the (thickened) bounding box to start with, then
-        // adapted to the measured occupancy (LiDAR clouds are surfaces; volume heuristics are off)
+        // finest level: the cell edge at which an occupied cell holds ~2 points (the points a query
+        // looks at grow with the square of the edge on a surface, the row look-ups do not), read
+        // off the measured occupancy curve by log-log interpolation between the candidates
         float cell = cell_size;
-        const bool adaptive = !(cell_size > 0.0f);
         if (adaptive) {
-            double vol = 1.0;
-            for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 0.02f * max_ext);
-            cell = (float)std::cbrt(vol / (2.0 * (double)bb.finite));
+            double avg[OCC_CANDS];
+            for (int j = 0; j < OCC_CANDS; ++j) {
+                const double zeros = (double)map_bits - (double)hones[j];
+                const double occ = zeros >= 1.0 ? -(double)map_bits * std::log(zeros / (double)map_bits)
+                                                : (double)map_bits * std::log((double)map_bits);
+                avg[j] = (double)bb.finite / std::max(occ, 1.0);
+            }
+            static const double F[OCC_CANDS] = {0.35, 0.5, 0.7071, 1.0, 1.4142, 2.0, 2.8284, 4.0};
+            const double want = 2.0;
+            double f = F[OCC_CANDS - 1];
+            if (avg[0] >= want) {
+                f = F[0];
+            } else {
+                for (int j = 0; j + 1 < OCC_CANDS; ++j)
+                    if (avg[j] < want && avg[j + 1] >= want) {
+                        const double t = (std::log(want) - std::log(avg[j])) / std::max(std::log(avg[j + 1]) - std::log(avg[j]), 1e-9);
+                        f = std::exp(std::log(F[j]) + t * (std::log(F[j + 1]) - std::log(F[j])));
+                        break;
+                    }
+            }
+            if (bb.finite <= 8) f = 1.0;
+            cell = (float)(pl.c0 * f);
             cell = std::max(cell, 1e-6f * std::max(max_abs, 1.0f));
         }
         int dims[3];
         size_t ncells = 0;
-        unsigned long long occupied = 0;
-        for (int attempt = 0; attempt < 5; ++attempt) {
-            for (;;) {  // respect the dense-grid budget
-                const double nc = dims_for(cell, dims);
-                if (nc <= (double)MAX_CELLS) {
-                    ncells = (size_t)dims[0] * dims[1] * dims[2];
-                    break;
-                }
-                cell *= (float)std::cbrt(nc / (double)MAX_CELLS) * 1.02f;
-            }
-            count_level(cell, dims, ncells);
-            if (!adaptive) break;
-            SPX_CUDA(cudaMemsetAsync(occ_dev, 0, 8, st));
-            occupied_kernel<<<std::min(div_up(ncells, 256), q->sm_count * 8), 256, 0, st>>>(counts, ncells, occ_dev);
-            SPX_LAUNCH_CHECK();
-            unsigned long long* hocc = reinterpret_cast<unsigned long long*>(q->pinned_get(64));
-            SPX_CUDA(cudaMemcpyAsync(hocc, occ_dev, 8, cudaMemcpyDeviceToHost, st));
-            q->sync();
-            occupied = *hocc;
-            if (attempt == 4) break;
-            const double avg = (double)bb.finite / (double)std::max<unsigned long long>(occupied, 1);
-            // aim for ~2 points per occupied cell: the points a query has to look at grow with the
-            // square of the cell edge on a surface, the row look-ups do not
-            if (avg < 1.3 && bb.finite > 8) {
-                cell *= (float)std::min(3.0, std::max(1.25, std::sqrt(2.0 / avg)));
-            } else if (avg > 3.5) {
-                cell *= (float)std::max(0.3, std::min(0.8, std::sqrt(2.0 / avg)));
-            } else {
+        for (;;) {  // respect the dense-grid budget
+            const double nc = dims_for(cell, dims);
+            if (nc <= (double)MAX_CELLS) {
+                ncells = (size_t)dims[0] * dims[1] * dims[2];
                 break;
             }
+            cell *= (float)std::cbrt(nc / (double)MAX_CELLS) * 1.02f;
         }
-        ix->occupied = (int64_t)occupied;
+        count_level(cell, dims, ncells);
         finish_level(0, cell, dims, ncells, true);
+        SPX_CUDA(cudaMallocAsync(&ix->occ_dev, sizeof(unsigned long long), st));
+        SPX_CUDA(cudaMemsetAsync(ix->occ_dev, 0, sizeof(unsigned long long), st));
+        occupied_from_start_kernel<<<std::min(div_up(ncells, 256), q->sm_count * 8), 256, 0, st>>>(ix->start[0], ncells,
+                                                                                                 ix->occ_dev);
+        SPX_LAUNCH_CHECK();
 
         // coarser levels until the coarsest grid is only a few cells wide
         int level = 0;
@@ -455,7 +664,7 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
             finish_level(level, cell, dims, ncells, false);
         }
         L.n_levels = level + 1;
-        q->sync();
+        // no final sync: everything above is ordered on the queue's stream, and so is every search
     });
 }
 
@@ -467,6 +676,7 @@ int spx_index_destroy(spx_index_t index) {
             if (index->sorted[l]) cudaFreeAsync(index->sorted[l], index->q->stream);
             if (index->start[l]) cudaFreeAsync(index->start[l], index->q->stream);
         }
+        if (index->occ_dev) cudaFreeAsync(index->occ_dev, index->q->stream);
         delete index;
     });
 }
@@ -481,7 +691,17 @@ int spx_index_info(spx_index_t index, float* cell_size, int32_t* dims3, int64_t*
             dims3[1] = v.dy;
             dims3[2] = v.dz;
         }
-        if (occupied_cells) *occupied_cells = index->occupied;
+        if (occupied_cells) {
+            *occupied_cells = 0;
+            if (index->occ_dev) {  // counted on the device at build time, fetched on demand
+                spx_queue_t q = index->q;
+                DeviceGuard g(q->device);
+                unsigned long long* h = static_cast<unsigned long long*>(q->pinned_get(64));
+                SPX_CUDA(cudaMemcpyAsync(h, index->occ_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q->stream));
+                q->sync();
+                *occupied_cells = (int64_t)*h;
+            }
+        }
         if (n_points) *n_points = index->n;
     });
 }
@@ -525,6 +745,15 @@ int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, con
         if (k == 1) {
             grid_knn_kernel<true><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
                                                                          idx, dist);
+        } else if (k <= 5) {
+            grid_knn_reg_kernel<5><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
+                                                                          idx, dist);
+        } else if (k <= 10) {
+            grid_knn_reg_kernel<10><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
+                                                                           idx, dist);
+        } else if (k <= 20) {
+            grid_knn_reg_kernel<20><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
+                                                                           idx, dist);
         } else {
             const size_t smem = (size_t)k * GRID_THREADS * 8;
             static bool attr_set = false;

@@ -76,6 +76,10 @@ struct LinArgs {
     const float* dist_in;
     int32_t* idx_out;
     float* dist_out;
+    uint32_t* pos_out;   // sorted position of the correspondence in the index: next iteration's warm start
+    int warm_start;      // idx_out / pos_out hold a previous iteration's result (per-launch kernels)
+    uint32_t* worklist;          // [ns] source indices whose search the first pass could not finish
+    unsigned int* wl_counters;   // [2 parities][count, cursor]
     GridLevels grid;
     // pose
     RegState* state;
@@ -96,7 +100,37 @@ struct LinArgs {
     float* trace;  // [max_iterations][16] column-major poses, nullable
     float* weights_out;  // compute_icp_robust_weights
     PeerX px;            // sharded align only
+    // optional phase timestamps (tuning aid, spx_registration_phase_times): [iteration][PH_N] ns,
+    // entry p = latest time any block reached phase p of that iteration
+    unsigned long long* phase;
 };
+constexpr int PH_START = 0, PH_NN = 1, PH_COOP = 2, PH_ACC = 3, PH_PART = 4, PH_SYNC = 5, PH_FOLD = 6, PH_SOLVE = 7, PH_N = 8;
+constexpr int PH_MAX_ITERS = 64;
+constexpr int PH_MAX_WARPS = 8192;
+constexpr size_t PH_WORDS = (size_t)PH_MAX_ITERS * PH_N + (size_t)PH_MAX_WARPS * 5;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long PEER_TIMEOUT_NS = 5000000000ull;
 
 // ------------------------------------------------------------------ robust kernels (robust.hpp:56-114)
 __device__ __forceinline__ float robust_weight(int loss, float r, float s) {
@@ -318,7 +352,7 @@ __device__ void gn_update(RegState* st, const double* sums, float lambda, float 
         }
     for (int a = 0; a < 6; ++a) b[a] = (float)sums[S_B + a];
     float delta[6];
-    const bool ok = solve_damped6(H, b, lambda, delta);
+    const bool ok = solve_damped6_device(H, b, lambda, delta);
     const bool conv = ok && norm3f(delta) < crit_rot && norm3f(delta + 3) < crit_trans;
     float E[4][4], Tn[4][4];
     se3_exp_rm(delta, E);
@@ -401,26 +435,86 @@ __device__ bool reduce_to_sums(const float* acc, int nacc, uint32_t inl, double*
 // Per-thread accumulation over a grid-stride slice of the source points.
 // MODE 0: correspondences given.  MODE 1: nearest neighbour through the index fused in front
 // (bounded by max_correspondence_distance; writes idx/dist for the frozen-neighbour error passes).
-template <int REG, int MODE>
-__device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Xform& T, float* acc, uint32_t& inl) {
-    const int32_t* idx = a.idx_in;
-    const float* dist = a.dist_in;
-    if (MODE == 1) {
-        // phase 1: correspondences for this thread's points.  Kept apart from the factor arithmetic
-        // so that the 28 accumulators are not live across the index traversal (registers = max of the
-        // two phases instead of their sum); the thread re-reads its own writes in phase 2.
-        for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
-            const float4 q = transform_point(T, __ldg(a.src_pts + i));
+__device__ __forceinline__ void phase_mark(unsigned long long* phase, int it, int p) {
+    if (phase && threadIdx.x == 0 && it < PH_MAX_ITERS) atomicMax(phase + it * PH_N + p, global_ns());
+}
+
+// Correspondence search of one iteration over the whole grid (MODE 1).  Three steps separated by
+// grid barriers (the kernels that call this are cooperative launches):
+//   1. every lane: warm start + pruned first pass for its own source points; finished queries write
+//      their result, unfinished ones write the bound reached and are appended to the work list;
+//   2. every warp of the grid pulls unfinished queries off the list (one atomic per grab) and
+//      completes them cooperatively — the expensive queries cluster in space, i.e. in a few warps,
+//      and this is what spreads them over all SMs;
+//   3. (caller) factor evaluation reads the finished idx / dist arrays.
+// Work-list counters are double-buffered by `par` and the other pair is cleared in step 2, so no
+// extra barrier or host memset is needed between iterations.
+__device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T, int it, cooperative_groups::grid_group& grid) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool warm = it > 0 || a.warm_start;
+    const int par = it & 1;
+    unsigned int* wl_count = a.wl_counters + par * 2;
+    unsigned int* wl_cursor = a.wl_counters + par * 2 + 1;
+    for (uint32_t base = blockIdx.x * LIN_THREADS; base < a.ns; base += gridDim.x * LIN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        bool pending = false;
+        if (i < a.ns) {
             Best1 best;
             best.init();
-            if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && a.grid.lv[0].n > 0)
-                grid_search_levels(a.grid, q.x, q.y, q.z, best, a.max_corr);
+            const float4 q = transform_point(T, __ldg(a.src_pts + i));
+            if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
+                uint32_t wp = 0xffffffffu;
+                if (warm && __ldcg(a.idx_out + i) >= 0) wp = __ldcg(a.pos_out + i);
+                pending = !icp_fast(a.grid, q.x, q.y, q.z, wp, a.max_corr, best);
+            }
             a.idx_out[i] = best.i;
             a.dist_out[i] = best.d;
+            a.pos_out[i] = best.p;
         }
-        idx = a.idx_out;
-        dist = a.dist_out;
+        // warp-aggregated append
+        const unsigned m = __ballot_sync(FULL, pending);
+        if (m) {
+            unsigned int slot = 0;
+            if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
+            slot = __shfl_sync(FULL, slot, __ffs(m) - 1);
+            if (pending) a.worklist[slot + __popc(m & ((1u << lane) - 1u))] = i;
+        }
     }
+    phase_mark(a.phase, it, PH_NN);
+    __threadfence();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the other parity's counters: idle until the next iteration
+        a.wl_counters[(par ^ 1) * 2] = 0;
+        a.wl_counters[(par ^ 1) * 2 + 1] = 0;
+    }
+    const unsigned int n_slow = __ldcg(wl_count);
+    for (;;) {
+        unsigned int k = 0;
+        if (lane == 0) k = atomicAdd(wl_cursor, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_slow) break;
+        const uint32_t i = __ldcg(a.worklist + k);
+        const float4 q = transform_point(T, __ldg(a.src_pts + i));
+        Best1 best;
+        best.i = __ldcg(a.idx_out + i);
+        best.d = __ldcg(a.dist_out + i);
+        best.p = __ldcg(a.pos_out + i);
+        icp_coop_search(a.grid, q.x, q.y, q.z, best, a.max_corr);
+        if (lane == 0) {
+            a.idx_out[i] = best.i;
+            a.dist_out[i] = best.d;
+            a.pos_out[i] = best.p;
+        }
+    }
+    __threadfence();
+    grid.sync();
+}
+
+template <int REG, int MODE>
+__device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Xform& T, float* acc, uint32_t& inl) {
+    const int32_t* idx = MODE == 1 ? a.idx_out : a.idx_in;
+    const float* dist = MODE == 1 ? a.dist_out : a.dist_in;
     for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
         const float d = MODE == 1 ? __ldcg(dist + i) : __ldg(dist + i);
         const int ti = MODE == 1 ? __ldcg(idx + i) : __ldg(idx + i);
@@ -444,8 +538,12 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs
     __shared__ float red[LIN_WARPS][32];
     Xform T = a.T;
     if (a.use_state) {
-        if (a.state->stop) return;  // converged earlier in this align(): nothing left to do
+        if (a.state->stop) return;  // converged earlier in this align(): nothing left to do (whole grid)
         T = state_xform(a.state);
+    }
+    if (MODE == 1) {  // cooperative launch: the correspondence search has grid barriers inside
+        cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+        nn_search_grid(a, T, a.iter_index, grid);
     }
     float acc[N_ACC];
 #pragma unroll
@@ -456,29 +554,6 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs
     if (SOLVE && threadIdx.x == 0)
         gn_update(a.state, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, a.iter_index, a.trace);
 }
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-constexpr unsigned long long PEER_TIMEOUT_NS = 5000000000ull;
 
 // The whole Gauss-Newton align() as ONE cooperative launch (registration.hpp:227-272 + :803-828):
 // every iteration is nearest neighbour + linearise + block reduce, one grid-wide barrier, then
@@ -510,7 +585,14 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs 
 #pragma unroll
         for (int v = 0; v < N_ACC; ++v) acc[v] = 0.0f;
         uint32_t inl = 0;
+        phase_mark(a.phase, it, PH_START);
+        nn_search_grid(a, T, it, grid);
+        phase_mark(a.phase, it, PH_COOP);
         lin_accumulate<REG, 1>(a, T, acc, inl);
+        if (a.phase) {
+            __syncthreads();
+            phase_mark(a.phase, it, PH_ACC);
+        }
         // block reduce -> this block's partial row
         for (int v = 0; v < N_ACC; ++v) {
             const float s = warp_sum(acc[v]);
@@ -534,7 +616,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs 
             __stcg(part + (size_t)blockIdx.x * 32 + threadIdx.x, s);
         }
         __threadfence();
+        phase_mark(a.phase, it, PH_PART);
         grid.sync();
+        phase_mark(a.phase, it, PH_SYNC);
         if (!SHARDED || blockIdx.x == 0) {
             const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
             double s = 0.0;
@@ -593,9 +677,11 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs 
             }
             if (__ldcg(x.error)) break;  // a peer went silent: every block leaves, the host reports it
         }
+        phase_mark(a.phase, it, PH_FOLD);
         if (threadIdx.x == 0)
             gn_update(&st, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, it, blockIdx.x == 0 ? a.trace : nullptr);
         __syncthreads();
+        phase_mark(a.phase, it, PH_SOLVE);
         if (st.stop) break;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.state = st;
@@ -653,16 +739,27 @@ __global__ void __launch_bounds__(128) prepare_cov_kernel(const float* __restric
     c1[i] = make_float2(r.yz, r.zz);
 }
 
+template <int REG, int MODE, bool SOLVE>
+void launch_linearize_one(const LinArgs& a, unsigned blocks, cudaStream_t st, int sm_count) {
+    if (MODE == 1) {
+        // the fused correspondence search synchronises the grid: cooperative launch, one resident wave
+        int per_sm = 0;
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linearize_kernel<REG, MODE, SOLVE>, LIN_THREADS, 0));
+        blocks = std::max(1u, std::min(blocks, (unsigned)std::max(per_sm, 1) * (unsigned)sm_count));
+        void* args[] = {(void*)&a};
+        SPX_CUDA(cudaLaunchCooperativeKernel((const void*)linearize_kernel<REG, MODE, SOLVE>, dim3(blocks), dim3(LIN_THREADS),
+                                             args, 0, st));
+    } else {
+        linearize_kernel<REG, MODE, SOLVE><<<blocks, LIN_THREADS, 0, st>>>(a);
+    }
+}
+
 template <int MODE, bool SOLVE>
-void launch_linearize(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
+void launch_linearize(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st, int sm_count = 148) {
     switch (reg) {
-        case SPX_REG_POINT_TO_POINT:
-            linearize_kernel<SPX_REG_POINT_TO_POINT, MODE, SOLVE><<<blocks, LIN_THREADS, 0, st>>>(a);
-            break;
-        case SPX_REG_POINT_TO_PLANE:
-            linearize_kernel<SPX_REG_POINT_TO_PLANE, MODE, SOLVE><<<blocks, LIN_THREADS, 0, st>>>(a);
-            break;
-        default: linearize_kernel<SPX_REG_GICP, MODE, SOLVE><<<blocks, LIN_THREADS, 0, st>>>(a); break;
+        case SPX_REG_POINT_TO_POINT: launch_linearize_one<SPX_REG_POINT_TO_POINT, MODE, SOLVE>(a, blocks, st, sm_count); break;
+        case SPX_REG_POINT_TO_PLANE: launch_linearize_one<SPX_REG_POINT_TO_PLANE, MODE, SOLVE>(a, blocks, st, sm_count); break;
+        default: launch_linearize_one<SPX_REG_GICP, MODE, SOLVE>(a, blocks, st, sm_count); break;
     }
     SPX_LAUNCH_CHECK();
 }
@@ -725,6 +822,9 @@ struct spx_registration_s {
     double* sums = nullptr;          // device [32]
     int32_t* nn_idx = nullptr;
     float* nn_dist = nullptr;
+    uint32_t* nn_pos = nullptr;
+    uint32_t* worklist = nullptr;
+    unsigned int* wl_counters = nullptr;
     size_t nn_cap = 0;
     float4* src_c0 = nullptr;
     float2* src_c1 = nullptr;
@@ -740,6 +840,7 @@ struct spx_registration_s {
     int shard_reg = 0;
     int shard_iter = 0;
     bool shard_active = false;
+    unsigned long long* phase = nullptr;  // [PH_MAX_ITERS][PH_N], allocated by spx_registration_phase_times(enable)
     spx_comm_t shard_comm = nullptr;  // fused (mailbox) sharded align in flight
     float4* shard_derived_normals = nullptr;
     int shard_max_it = 0;
@@ -757,8 +858,8 @@ void reg_free(spx_registration_t r) {
         if (p) cudaFree(p);
         p = nullptr;
     };
-    f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist);
-    f(r->src_c0); f(r->src_c1); f(r->tgt_c0); f(r->tgt_c1); f(r->trace);
+    f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist); f(r->nn_pos); f(r->worklist); f(r->wl_counters);
+    f(r->src_c0); f(r->src_c1); f(r->tgt_c0); f(r->tgt_c1); f(r->trace); f(r->phase);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     r->ev0 = r->ev1 = nullptr;
@@ -814,6 +915,10 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
 
     size_t cap_dummy = r->nn_cap;
     ensure(r->nn_idx, cap_dummy, ns, st);
+    cap_dummy = r->nn_cap;
+    ensure(r->nn_pos, cap_dummy, ns, st);
+    cap_dummy = r->nn_cap;
+    ensure(r->worklist, cap_dummy, ns, st);
     ensure(r->nn_dist, r->nn_cap, ns, st);
     r->nn_n = ns;
     size_t tcap = r->trace_cap;
@@ -868,6 +973,11 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     }
     a.idx_in = r->nn_idx; a.dist_in = r->nn_dist;
     a.idx_out = r->nn_idx; a.dist_out = r->nn_dist;
+    a.pos_out = r->nn_pos;
+    a.warm_start = 0;
+    a.worklist = r->worklist;
+    a.wl_counters = r->wl_counters;
+    SPX_CUDA(cudaMemsetAsync(r->wl_counters, 0, 4 * sizeof(unsigned int), st));
     a.grid = index->levels;
     a.state = r->state;
     a.use_state = 1;
@@ -883,6 +993,8 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     a.crit_rot = P.criteria_rotation;
     a.crit_trans = P.criteria_translation;
     a.trace = r->trace;
+    a.phase = r->phase;
+    if (r->phase) SPX_CUDA(cudaMemsetAsync(r->phase, 0, PH_WORDS * sizeof(unsigned long long), st));
 
     RegState* hs = static_cast<RegState*>(q->pinned_get(sizeof(RegState) + 64 + 32 * sizeof(double)));
     std::memset(hs, 0, sizeof(RegState));
@@ -1204,6 +1316,7 @@ int spx_registration_create(spx_queue_t q, const spx_registration_params* params
         try {
             SPX_CUDA(cudaMalloc(&r->state, sizeof(RegState)));
             SPX_CUDA(cudaMalloc(&r->ticket, 64));
+            SPX_CUDA(cudaMalloc(&r->wl_counters, 64));
             SPX_CUDA(cudaMalloc(&r->sums, 32 * sizeof(double)));
             SPX_CUDA(cudaMemsetAsync(r->ticket, 0, 64, q->stream));
             r->max_blocks = (unsigned)q->sm_count * 4;
@@ -1246,6 +1359,30 @@ int spx_registration_last_timing(spx_registration_t reg, float* loop_ms, int32_t
         if (loop_ms) *loop_ms = ms;
         if (launches) *launches = reg->last_launches;
         if (iterations) *iterations = reg->last_iterations;
+    });
+}
+
+int spx_registration_phase_times(spx_registration_t reg, int enable, uint64_t* times_host, int max_iterations) {
+    return guard([&] {
+        SPX_REQUIRE(reg, "[Registration::phase_times] null handle");
+        DeviceGuard g(reg->q->device);
+        if (enable && !reg->phase) {
+            SPX_CUDA(cudaMalloc(&reg->phase, PH_WORDS * sizeof(unsigned long long)));
+            SPX_CUDA(cudaMemsetAsync(reg->phase, 0, PH_WORDS * sizeof(unsigned long long), reg->q->stream));
+        }
+        if (!enable && reg->phase) {
+            SPX_CUDA(cudaStreamSynchronize(reg->q->stream));
+            SPX_CUDA(cudaFree(reg->phase));
+            reg->phase = nullptr;
+        }
+        if (times_host && reg->phase) {
+            // max_iterations < 0: the whole buffer (phase table + per-warp records of iteration 1)
+            const size_t words = max_iterations < 0 ? PH_WORDS
+                                                    : (size_t)std::min(max_iterations, PH_MAX_ITERS) * PH_N;
+            SPX_CUDA(cudaMemcpyAsync(times_host, reg->phase, words * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, reg->q->stream));
+            reg->q->sync();
+        }
     });
 }
 
@@ -1329,7 +1466,9 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         auto clampf = [](float v, float lo, float hi) { return std::min(std::max(v, lo), hi); };
         for (int it = 0; it < max_it; ++it) {
             host_T_to_xform(T, a.T);
-            launch_linearize<1, false>(c.reg, a, c.blocks, st);
+            a.warm_start = it > 0;
+            a.iter_index = it;
+            launch_linearize<1, false>(c.reg, a, c.blocks, st, q->sm_count);
             SPX_CUDA(cudaMemcpyAsync(hsums, reg->sums, 32 * sizeof(double), cudaMemcpyDeviceToHost, st));
             q->sync();
             float H[36], b[6], err;
@@ -1448,13 +1587,15 @@ int spx_registration_shard_linearize(spx_registration_t reg, double* sums_dev) {
         DeviceGuard g(reg->q->device);
         LinArgs a = reg->shard;
         a.sums_out = sums_dev;
+        a.warm_start = reg->shard_iter > 0;
+        a.iter_index = reg->shard_iter;
         const unsigned blocks = lin_blocks(reg->q, a.ns);
         if (a.ns == 0) {
             // an empty shard still contributes zeros (and must not leave stale sums behind)
             SPX_CUDA(cudaMemsetAsync(sums_dev, 0, 32 * sizeof(double), reg->q->stream));
             return;
         }
-        launch_linearize<1, false>(reg->shard_reg, a, blocks, reg->q->stream);
+        launch_linearize<1, false>(reg->shard_reg, a, blocks, reg->q->stream, reg->q->sm_count);
     });
 }
 

@@ -40,6 +40,17 @@ def shard_of(n: int, rank: int, world: int) -> tuple[int, int]:
     return shard_bounds(n, world)[rank]
 
 
+def shard_indices(n: int, rank: int, world: int, block: int = 1024) -> np.ndarray:
+    """Block-cyclic shard: blocks of `block` consecutive points dealt round-robin to the ranks.  Voxel-
+    ordered clouds put dense ground and sparse walls in different contiguous ranges, so contiguous
+    shards (shard_bounds) can be badly unbalanced in work; block-cyclic shards are not.  The sum over
+    ranks is the same set of points either way."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    i = np.arange(n, dtype=np.int64)
+    return i[(i // block) % world == rank]
+
+
 def sums_to_Hb(s) -> tuple[np.ndarray, np.ndarray, float, int]:
     """Unpack a sums row into the symmetric 6x6 H, b, error, inlier count (float32 like the reference)."""
     s = np.asarray(s, np.float64)

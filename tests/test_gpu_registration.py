@@ -408,3 +408,37 @@ def test_example_registration_pipeline_with_random_sampling(spx, q, pair, bundle
     assert dt < 1e-5 and da < 1e-5 and res.iterations == ores["iterations"]
     dt, da = pose_delta(bundled["T_target_source"], res.T)
     assert dt < 0.10 and np.degrees(da) < 0.5
+
+
+@pytest.mark.parametrize("max_corr,shift", [(2.0, 0.0), (2.0, 1.5), (0.5, 0.3), (6.0, 4.0)])
+@pytest.mark.parametrize("opt", ["GN", "LM"])
+def test_align_correspondences_exact_with_warm_start(spx, q, pair, max_corr, shift, opt):
+    """The fused nearest-neighbour search of the iteration kernels (warm start from the previous
+    iteration, pruned first pass, warp-cooperative continuation): after 3 iterations the cached
+    correspondences must be the exact brute-force answer at the pose the last iteration linearised
+    at — bit-exact index and distance for everything within max_correspondence_distance."""
+    import ctypes as C
+    params = spx.RegistrationParams(max_iterations=3)
+    params.max_correspondence_distance = max_corr
+    params.optimization_method = spx.OptimizationMethod.GAUSS_NEWTON if opt == "GN" else \
+        spx.OptimizationMethod.LEVENBERG_MARQUARDT
+    params.criteria.translation = params.criteria.rotation = 0.0
+    T0 = np.eye(4, dtype=np.float32)
+    T0[:3, 3] = [shift, -0.5 * shift, 0.1 * shift]
+    reg = spx.Registration(q, params)
+    res = reg.align(pair["src"], pair["tgt"], pair["tree"], T0, trace=True)
+    ip, dp, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+    spx._lib.check(spx.lib().spx_registration_neighbors(reg._h, C.byref(ip), C.byref(dp), C.byref(n)))
+    assert n.value == pair["src"].size()
+    idx = np.empty(n.value, np.int32)
+    dist = np.empty(n.value, np.float32)
+    spx._lib.check(spx.lib().spx_memcpy_d2h(q.handle, idx.ctypes.data_as(C.c_void_p), ip, idx.nbytes))
+    spx._lib.check(spx.lib().spx_memcpy_d2h(q.handle, dist.ctypes.data_as(C.c_void_p), dp, dist.nbytes))
+    q.wait()
+    T_lin = res.trace[1]  # pose after 2 updates = the pose the 3rd iteration searched at
+    oi, od = oracle.knn_bruteforce(pair["src_h"], pair["tgt_h"], 1, T_lin)
+    oi, od = oi.reshape(-1), od.reshape(-1)
+    within = od <= np.float32(max_corr) ** 2
+    assert within.sum() > 100
+    assert np.array_equal(idx[within], oi[within]) and np.array_equal(dist[within], od[within])
+    assert (dist[~within] > np.float32(max_corr) ** 2).all()

@@ -139,3 +139,15 @@ def test_bench_reference_arm_under_torchrun_rank0_only():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r1.returncode == 0 and r1.stdout.strip() == "", (r1.stdout, r1.stderr[-500:])
+
+
+def test_block_cyclic_shards_partition_the_cloud():
+    from sycl_points_b200.multi_gpu import shard_indices
+    for n in (0, 1, 1023, 1024, 5000, 114045):
+        for w in (1, 2, 3, 8):
+            parts = [shard_indices(n, r, w) for r in range(w)]
+            allidx = np.sort(np.concatenate(parts)) if parts else np.zeros(0)
+            assert np.array_equal(allidx, np.arange(n))
+            if n >= 8 * 1024 * w:
+                sizes = [len(p) for p in parts]
+                assert max(sizes) - min(sizes) <= 1024

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="config-2 sized pair (quick check)")
     ap.add_argument("--single-only", action="store_true", help="only the plain single-GPU align (ncu captures)")
     ap.add_argument("--factors", default="POINT_TO_PLANE,GICP")
+    ap.add_argument("--contiguous", action="store_true", help="contiguous ceil(N/G) shards instead of block-cyclic")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     import torch
@@ -45,7 +46,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import sycl_points_b200 as spx
-    from sycl_points_b200.multi_gpu import Communicator, ShardedRegistration, shard_of
+    from sycl_points_b200.multi_gpu import Communicator, ShardedRegistration, shard_indices, shard_of
 
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
@@ -70,10 +71,11 @@ def main():
         ts.close()
         ns, nt = src.size(), tgt.size()
         lo, hi = shard_of(ns, rank, world)
+        sel = np.arange(lo, hi) if args.contiguous else shard_indices(ns, rank, world)
         cov_s = src.covs_host()
-        shard = spx.PointCloudShared(q, src_full[lo:hi], cov_s[lo:hi])
+        shard = spx.PointCloudShared(q, src_full[sel], cov_s[sel])
         if rank == 0:
-            print(f"# setup {time.time() - t0:.1f} s: N_s={ns} N_t={nt} world={world} shard0=[{lo},{hi}) index={tt.info()}",
+            print(f"# setup {time.time() - t0:.1f} s: N_s={ns} N_t={nt} world={world} shard0={len(sel)} pts ({'contiguous' if args.contiguous else 'block-cyclic'}) index={tt.info()}",
                   file=sys.stderr)
         comm = Communicator(q, rank, world) if world > 1 else Communicator(q, 0, 1)
         peak = 6546.6
