@@ -156,6 +156,8 @@ SPX_API int spx_event_create(spx_event_t* out);
 SPX_API int spx_event_destroy(spx_event_t e);
 SPX_API int spx_event_record(spx_queue_t q, spx_event_t e);
 SPX_API int spx_event_elapsed_ms(spx_event_t start, spx_event_t stop, float* ms); /* synchronises on stop */
+/* work enqueued on q after this call starts only once e has completed (handler::depends_on across queues) */
+SPX_API int spx_queue_wait_event(spx_queue_t q, spx_event_t e);
 
 /* ------------------------------------------------------------------ KNN
  * knn_search_bruteforce(queue, queries, targets, k) — I/algorithms/knn/bruteforce.hpp:24-96.

@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "spx_event_create": (C.c_int, [C.POINTER(vp)]),
         "spx_event_destroy": (C.c_int, [vp]),
         "spx_event_record": (C.c_int, [vp, vp]),
+        "spx_queue_wait_event": (C.c_int, [vp, vp]),
         "spx_event_elapsed_ms": (C.c_int, [vp, vp, C.POINTER(C.c_float)]),
         "spx_knn_bruteforce": (C.c_int, [vp, f32p, sz, f32p, sz, C.c_int, hostf, i32p, f32p]),
         "spx_index_build": (C.c_int, [vp, f32p, sz, C.c_float, C.POINTER(vp)]),

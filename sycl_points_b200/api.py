@@ -72,6 +72,10 @@ class DeviceQueue:
         """events.wait_and_throw()"""
         check(_lib.lib().spx_queue_sync(self._h))
 
+    def wait_event(self, event: "Event"):
+        """later work on this queue starts only after `event` (recorded on any queue) has completed"""
+        check(_lib.lib().spx_queue_wait_event(self._h, event._h))
+
     def is_cpu(self) -> bool:
         return False
 

@@ -362,13 +362,18 @@ __device__ __forceinline__ void grid_search_levels(const GridLevels& g, float qx
 //    wide (load-balanced by a prefix sum over the rows' candidate counts).  The tail the whole grid
 //    used to wait for — one warp owning dozens of expensive queries — is spread over every SM.
 
+constexpr uint32_t ICP_LANE_CANDS = 64;  // most candidates a single lane scans on a coarser level
+
 __device__ __forceinline__ unsigned long long best_key(float d, int i) {
     return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)i;  // i = -1 sorts last
 }
 
-// returns true when `best` is final
-__device__ __forceinline__ bool icp_first_pass(const GridView& g, float qx, float qy, float qz, Best1& best,
-                                               float max_radius) {
+// One pruned pass over the 3x3x3 block of `g` around the query.  Valid on ANY level (every level
+// indexes all points): afterwards every point closer than min(bound, current best) has been seen.
+// Returns 1 when `best` is final, 0 when not proven, -1 when the rows hold more than max_cands
+// candidates (nothing scanned: the caller leaves dense blocks to the cooperative search).
+__device__ __forceinline__ int icp_first_pass(const GridView& g, float qx, float qy, float qz, Best1& best,
+                                              float max_radius, uint32_t max_cands = 0xffffffffu) {
     const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
     const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
     const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
@@ -413,6 +418,12 @@ __device__ __forceinline__ bool icp_first_pass(const GridView& g, float qx, floa
         ls[t] = ok ? __ldg(g.start + row + xa) : 0u;
         le[t] = ok ? __ldg(g.start + row + xb + 1) : 0u;
     }
+    if (max_cands != 0xffffffffu) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) total += le[t] - ls[t];
+        if (total > max_cands) return -1;
+    }
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
         for (uint32_t j = ls[t]; j < le[t]; j += 4) {
@@ -429,9 +440,9 @@ __device__ __forceinline__ bool icp_first_pass(const GridView& g, float qx, floa
     const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, 1, g.dx),
                                     shell_bound_axis(qy, g.oy, g.cell, cy, 1, g.dy)),
                               shell_bound_axis(qz, g.oz, g.cell, cz, 1, g.dz));
-    if (bound == INF) return true;
+    if (bound == INF) return 1;
     const float bs = bound - margin;
-    return (bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) || bs >= max_radius;
+    return ((bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) || bs >= max_radius) ? 1 : 0;
 }
 
 // Warp-cooperative continuation for ONE query (all arguments warp-uniform, every lane calls it):
@@ -570,7 +581,10 @@ __device__ __forceinline__ bool icp_fast(const GridLevels& gl, float qx, float q
         const float4 p = __ldg(g.pts + warm_pos);
         best.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), warm_pos);
     }
-    return icp_first_pass(g, qx, qy, qz, best, max_radius);
+    // (A per-lane pass on the next coarser level for the unproven, sparse-neighbourhood queries was
+    // measured: it halves the cooperative phase but doubles this one — those queries cluster in the
+    // same warps — for a net loss; icp_first_pass keeps its max_cands hook for that experiment.)
+    return icp_first_pass(g, qx, qy, qz, best, max_radius) == 1;
 }
 
 #endif  // __CUDACC__

@@ -183,13 +183,33 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, uint32_t n, BBoxAcc*
         }
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one set of atomics per BLOCK (per-warp atomics on seven shared addresses serialise)
+    __shared__ int smn[3], smx[3];
+    __shared__ uint32_t scnt;
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) {
+            smn[a] = INT_MAX;
+            smx[a] = INT_MIN;
+        }
+        scnt = 0;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && cnt) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&acc->mn[a], mn[a]);
-            atomicMax(&acc->mx[a], mx[a]);
+            atomicMin(&smn[a], mn[a]);
+            atomicMax(&smx[a], mx[a]);
         }
-        atomicAdd(&acc->finite, cnt);
+        atomicAdd(&scnt, cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && scnt) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&acc->mn[a], smn[a]);
+            atomicMax(&acc->mx[a], smx[a]);
+        }
+        atomicAdd(&acc->finite, scnt);
     }
 }
 
@@ -205,17 +225,21 @@ __device__ __forceinline__ uint32_t cell_of(const GridGeom& g, const float4 p) {
     return ((uint32_t)cz * (uint32_t)g.dy + (uint32_t)cy) * (uint32_t)g.dx + (uint32_t)cx;
 }
 
+// Points arrive spatially sorted (voxel order), so the lanes of a warp mostly share a handful of
+// cells — on the coarse levels a single one.  One atomic per distinct cell per warp instead of one
+// per point (120 k atomics on six addresses took 30 us per coarse level).
 __global__ void cell_count_kernel(const float4* __restrict__ pts, uint32_t n, GridGeom g, uint32_t* __restrict__ cell_id,
                                   uint32_t* __restrict__ counts) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 p = __ldg(pts + i);
+    const int lane = threadIdx.x & 31;
     uint32_t c = 0xffffffffu;
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-        c = cell_of(g, p);
-        atomicAdd(counts + c, 1u);
+    if (i < n) {
+        const float4 p = __ldg(pts + i);
+        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) c = cell_of(g, p);
+        cell_id[i] = c;
     }
-    cell_id[i] = c;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (c != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(counts + c, (uint32_t)__popc(peers));
 }
 
 __global__ void occupied_kernel(const uint32_t* __restrict__ counts, size_t ncells, unsigned long long* occupied) {
@@ -227,7 +251,7 @@ __global__ void occupied_kernel(const uint32_t* __restrict__ counts, size_t ncel
 }
 
 // ---- cell-size selection without a host round trip per attempt
-// The finest cell edge is chosen so that an occupied cell holds ~2 points.  Occupancy as a function
+// The finest cell edge is chosen so that an occupied cell holds ~3 points.  Occupancy as a function
 // of the cell edge is measured for OCC_CANDS candidate edges in ONE pass: every point sets one bit
 // per candidate in a hashed bitmap of M bits, and the number of occupied cells follows from the
 // fraction of zero bits (linear counting: n_occ ~ -M ln(zeros / M), within ~1 % at the loads used).
@@ -314,10 +338,15 @@ __global__ void cell_scatter_kernel(const float4* __restrict__ pts, uint32_t n, 
                                     const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
                                     float4* __restrict__ sorted) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t c = cell_id[i];
+    const int lane = threadIdx.x & 31;
+    const uint32_t c = i < n ? cell_id[i] : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (c != 0xffffffffu && lane == leader) base = __ldg(start + c) + atomicAdd(cursor + c, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
     if (c == 0xffffffffu) return;
-    const uint32_t pos = start[c] + atomicAdd(cursor + c, 1u);
+    const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
     const float4 p = __ldg(pts + i);
     sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float((int)i));
 }
@@ -384,6 +413,67 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_kernel(const GridLevels
             const uint32_t ql = e / (uint32_t)k, j = e - ql * (uint32_t)k;
             dist[(size_t)q0 * k + e] = sd[j * GRID_THREADS + ql];
             idx[(size_t)q0 * k + e] = si[j * GRID_THREADS + ql];
+        }
+    }
+}
+
+// k == 1, two passes (same split as the registration kernels, spx_registration.cu nn_search_grid):
+// pass 1, one lane per query: first pass over the 3x3x3 block; unfinished queries go to a work list.
+// pass 2, one warp per listed query: cooperative continuation over shells and coarser levels.
+__global__ void __launch_bounds__(GRID_THREADS) grid_nn1_fast_kernel(const GridLevels g, const float4* __restrict__ queries,
+                                                                     uint32_t nq, Xform T, int has_T, float max_radius,
+                                                                     int32_t* __restrict__ idx, float* __restrict__ dist,
+                                                                     uint32_t* __restrict__ pos,
+                                                                     uint32_t* __restrict__ worklist,
+                                                                     unsigned int* __restrict__ wl_count) {
+    const uint32_t qi = blockIdx.x * GRID_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool pending = false;
+    if (qi < nq) {
+        float4 q = __ldg(queries + qi);
+        if (has_T) q = transform_point(T, q);
+        Best1 best;
+        best.init();
+        if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && g.lv[0].n > 0)
+            pending = !icp_fast(g, q.x, q.y, q.z, 0xffffffffu, max_radius, best);
+        idx[qi] = best.i;
+        dist[qi] = best.d;
+        pos[qi] = best.p;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pending);
+    if (m) {
+        unsigned int slot = 0;
+        if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+        if (pending) worklist[slot + __popc(m & ((1u << lane) - 1u))] = qi;
+    }
+}
+
+__global__ void __launch_bounds__(GRID_THREADS) grid_nn1_coop_kernel(const GridLevels g, const float4* __restrict__ queries,
+                                                                     Xform T, int has_T, float max_radius,
+                                                                     int32_t* __restrict__ idx, float* __restrict__ dist,
+                                                                     const uint32_t* __restrict__ pos,
+                                                                     const uint32_t* __restrict__ worklist,
+                                                                     const unsigned int* __restrict__ wl_count,
+                                                                     unsigned int* __restrict__ wl_cursor) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_slow = *wl_count;
+    for (;;) {
+        unsigned int k = 0;
+        if (lane == 0) k = atomicAdd(wl_cursor, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_slow) break;
+        const uint32_t qi = worklist[k];
+        float4 q = __ldg(queries + qi);
+        if (has_T) q = transform_point(T, q);
+        Best1 best;
+        best.i = idx[qi];
+        best.d = dist[qi];
+        best.p = pos[qi];
+        icp_coop_search(g, q.x, q.y, q.z, best, max_radius);
+        if (lane == 0) {
+            idx[qi] = best.i;
+            dist[qi] = best.d;
         }
     }
 }
@@ -606,9 +696,10 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
             ix->ncells[level] = ncells;
         };
 
-        // finest level: the cell edge at which an occupied cell holds ~2 points (the points a query
-        // looks at grow with the square of the edge on a surface, the row look-ups do not), read
-        // off the measured occupancy curve by log-log interpolation between the candidates
+        // finest level: the cell edge at which an occupied cell holds ~3 points (measured optimum on
+        // LiDAR-shaped clouds for both the k = 10 and the warm-started k = 1 searches: smaller cells
+        // send more queries past the first pass, larger ones add candidates to every query), read off
+        // the measured occupancy curve by log-log interpolation between the candidates
         float cell = cell_size;
         if (adaptive) {
             double avg[OCC_CANDS];
@@ -619,7 +710,8 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
                 avg[j] = (double)bb.finite / std::max(occ, 1.0);
             }
             static const double F[OCC_CANDS] = {0.35, 0.5, 0.7071, 1.0, 1.4142, 2.0, 2.8284, 4.0};
-            const double want = 2.0;
+            double want = 3.0;
+            if (const char* e = std::getenv("SPX_CELL_TARGET")) want = std::max(0.5, std::atof(e));  // tuning aid
             double f = F[OCC_CANDS - 1];
             if (avg[0] >= want) {
                 f = F[0];
@@ -743,8 +835,18 @@ int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, con
         const unsigned blocks = (unsigned)div_up(nq, GRID_THREADS);
         const float4* qs = reinterpret_cast<const float4*>(queries);
         if (k == 1) {
-            grid_knn_kernel<true><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
-                                                                         idx, dist);
+            q->arena_reset();
+            q->arena_reserve(nq * 8 + 4096);
+            uint32_t* pos = q->take<uint32_t>(nq);
+            uint32_t* worklist = q->take<uint32_t>(nq);
+            unsigned int* counters = q->take<unsigned int>(16);
+            SPX_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), q->stream));
+            grid_nn1_fast_kernel<<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, T, has_T, INFINITY,
+                                                                        idx, dist, pos, worklist, counters);
+            SPX_LAUNCH_CHECK();
+            // the drain kernel sizes itself to the device, not to the (unknown on the host) list length
+            grid_nn1_coop_kernel<<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(index->levels, qs, T, has_T, INFINITY, idx,
+                                                                                 dist, pos, worklist, counters, counters + 1);
         } else if (k <= 5) {
             grid_knn_reg_kernel<5><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
                                                                           idx, dist);

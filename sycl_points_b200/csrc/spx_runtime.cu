@@ -275,6 +275,14 @@ int spx_event_record(spx_queue_t q, spx_event_t e) {
     });
 }
 
+int spx_queue_wait_event(spx_queue_t q, spx_event_t e) {
+    return guard([&] {
+        SPX_REQUIRE(q && e, "[spx_queue_wait_event] null argument");
+        DeviceGuard g(q->device);
+        SPX_CUDA(cudaStreamWaitEvent(q->stream, e->ev, 0));
+    });
+}
+
 int spx_event_elapsed_ms(spx_event_t start, spx_event_t stop, float* ms) {
     return guard([&] {
         SPX_REQUIRE(start && stop && ms, "[spx_event_elapsed_ms] null argument");

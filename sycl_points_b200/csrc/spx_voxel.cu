@@ -73,13 +73,33 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __
         }
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
+    // one set of global atomics per block: per-warp atomics on seven shared addresses serialise
+    __shared__ int smn[3], smx[3];
+    __shared__ uint32_t scnt;
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) {
+            smn[a] = INT_MAX;
+            smx[a] = INT_MIN;
+        }
+        scnt = 0;
+    }
+    __syncthreads();
     if ((threadIdx.x & 31) == 0 && cnt) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&acc->mn[a], mn[a]);
-            atomicMax(&acc->mx[a], mx[a]);
+            atomicMin(&smn[a], mn[a]);
+            atomicMax(&smx[a], mx[a]);
         }
-        atomicAdd(&acc->valid, cnt);
+        atomicAdd(&scnt, cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && scnt) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&acc->mn[a], smn[a]);
+            atomicMax(&acc->mx[a], smx[a]);
+        }
+        atomicAdd(&acc->valid, scnt);
     }
 }
 
@@ -224,6 +244,15 @@ __device__ float run_select(const float* __restrict__ v, const uint32_t* __restr
     return key_float(prefix);
 }
 
+// points into sorted (key, index) order: every thread one 16-byte gather, coalesced store — the
+// per-voxel sums then read contiguous runs instead of one random line per addend
+__global__ void __launch_bounds__(VX_THREADS) gather_points_kernel(const float4* __restrict__ pts,
+                                                                   const uint32_t* __restrict__ svals, uint32_t n_valid,
+                                                                   float4* __restrict__ sorted) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i < n_valid) sorted[i] = __ldg(pts + __ldg(svals + i));
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __restrict__ pts,
                                                                 const KeyT* __restrict__ skeys,
@@ -239,7 +268,7 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __
         float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
         uint32_t j = i;
         for (; j < n_valid && skeys[j] == key; ++j) {
-            const float4 p = __ldg(pts + svals[j]);
+            const float4 p = __ldg(pts + j);  // `pts` is the gathered (sorted-order) copy
             sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
         }
         if (sw >= min_count) {  // :204
@@ -354,6 +383,7 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     uint32_t* pos = q->take<uint32_t>(n);
     uint32_t* scan_tmp2 = q->take<uint32_t>(scan_scratch_elems(n));
     float4* means = q->take<float4>(n);
+    float4* gathered = q->take<float4>(n);
     VoxAttrs at{};
     at.rgb = io.rgb;
     at.intensity = io.intensity;
@@ -382,7 +412,9 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     }
     // kin / vin now hold the sorted (key, index) pairs; dropped points (invalid key) sit at the end
     if (n_valid > 0) {
-        voxel_mean_kernel<KeyT><<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count,
+        gather_points_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(pts, vin, n_valid, gathered);
+        SPX_LAUNCH_CHECK();
+        voxel_mean_kernel<KeyT><<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(gathered, kin, vin, n_valid, min_count,
                                                                                   flags, means, at);
         SPX_LAUNCH_CHECK();
     }
@@ -433,7 +465,7 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
 
         q->arena_reset();
-        q->arena_reserve((size_t)n * (8 * 2 + 4 * 2 + 4 * 2 + 16 + 16 + 4 + 4) + ((size_t)RADIX * nblocks + 64) * 4 +
+        q->arena_reserve((size_t)n * (8 * 2 + 4 * 2 + 4 * 2 + 16 + 16 + 16 + 4 + 4) + ((size_t)RADIX * nblocks + 64) * 4 +
                          (scan_scratch_elems((size_t)RADIX * nblocks) + scan_scratch_elems(n)) * 4 + 16 * 256 + 8192);
         CoordAcc* acc = q->take<CoordAcc>(1);
         uint32_t* total_dev = q->take<uint32_t>(16);
