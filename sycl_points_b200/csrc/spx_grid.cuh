@@ -166,7 +166,7 @@ struct CountStats {
 // registration.hpp:584); pass +inf for an unbounded exact search.  r_max: shells after which an
 // unbounded search gives up (returns false -> caller falls back to a full scan).
 template <typename Best, typename Stats = NoStats>
-__device__ __noinline__ bool grid_search(const GridView& g, float qx, float qy, float qz, Best& best, float max_radius,
+__device__ __forceinline__ bool grid_search(const GridView& g, float qx, float qy, float qz, Best& best, float max_radius,
                                          int r_begin, int r_max, Stats* stats = nullptr) {
     const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
     const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
@@ -464,6 +464,9 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
         const float reach2 = reach < 1.8e19f ? __fmul_rn(reach, reach) : INF;
         const int r_begin = (l == 0) ? 2 : 1;
         const int r_max = last ? (1 << 20) : GRID_LEVEL_RINGS;
+        // (Skipping a level whose last shell cannot certify the current candidate was tried and is a
+        // large loss: the candidate is often NOT the answer — a wall one metre away is found by the
+        // next fine shell for a handful of candidates, but costs thousands on the coarser level.)
         for (int r = r_begin;; ++r) {
             const bool merged = (r == 1);  // first shell on a coarser level: the whole 3x3x3 block
             const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "spx_grid.cuh"
@@ -509,6 +510,77 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
     }
     __threadfence();
     grid.sync();
+}
+
+// ---- the same search as three ordinary launches per iteration (large clouds)
+// The cooperative kernels carry the factor arithmetic's register budget (128/thread -> 16 warps per
+// SM) through the search, which is latency-bound and wants warps in flight.  Above a few hundred
+// thousand source points launch overhead no longer matters, so the search gets kernels of its own
+// (64 registers -> 4x the resident warps) and the factor pass runs as linearize_kernel<REG, 0, SOLVE>.
+constexpr int NN_THREADS = 128;
+
+__global__ void __launch_bounds__(NN_THREADS, 8) icp_fast_kernel(const LinArgs a) {
+    if (a.state->stop) return;
+    const Xform T = state_xform(a.state);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool warm = a.iter_index > 0 || a.warm_start;
+    const int par = a.iter_index & 1;
+    unsigned int* wl_count = a.wl_counters + par * 2;
+    const uint32_t i = blockIdx.x * NN_THREADS + threadIdx.x;
+    bool pending = false;
+    if (i < a.ns) {
+        Best1 best;
+        best.init();
+        const float4 q = transform_point(T, __ldg(a.src_pts + i));
+        if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
+            uint32_t wp = 0xffffffffu;
+            if (warm && a.idx_out[i] >= 0) wp = a.pos_out[i];
+            pending = !icp_fast(a.grid, q.x, q.y, q.z, wp, a.max_corr, best);
+        }
+        a.idx_out[i] = best.i;
+        a.dist_out[i] = best.d;
+        a.pos_out[i] = best.p;
+    }
+    const unsigned m = __ballot_sync(FULL, pending);
+    if (m) {
+        unsigned int slot = 0;
+        if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
+        slot = __shfl_sync(FULL, slot, __ffs(m) - 1);
+        if (pending) a.worklist[slot + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+}
+
+__global__ void __launch_bounds__(NN_THREADS, 8) icp_coop_kernel(const LinArgs a) {
+    if (a.state->stop) return;
+    const Xform T = state_xform(a.state);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int par = a.iter_index & 1;
+    const unsigned int n_slow = a.wl_counters[par * 2];
+    unsigned int* wl_cursor = a.wl_counters + par * 2 + 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // next iteration's counters (idle during this launch)
+        a.wl_counters[(par ^ 1) * 2] = 0;
+        a.wl_counters[(par ^ 1) * 2 + 1] = 0;
+    }
+    for (;;) {
+        unsigned int k = 0;
+        if (lane == 0) k = atomicAdd(wl_cursor, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_slow) break;
+        const uint32_t i = a.worklist[k];
+        const float4 q = transform_point(T, __ldg(a.src_pts + i));
+        Best1 best;
+        best.i = a.idx_out[i];
+        best.d = a.dist_out[i];
+        best.p = a.pos_out[i];
+        icp_coop_search(a.grid, q.x, q.y, q.z, best, a.max_corr);
+        if (lane == 0) {
+            a.idx_out[i] = best.i;
+            a.dist_out[i] = best.d;
+            a.pos_out[i] = best.p;
+        }
+    }
 }
 
 template <int REG, int MODE>
@@ -1423,14 +1495,43 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
 
         reg->timed = false;
         if (P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
+            // small clouds: one cooperative launch for the whole loop.  Large clouds: three ordinary
+            // launches per iteration (search kernels with their own register budget), converged-state
+            // polled every SPLIT_POLL iterations; launches after convergence return immediately.
+            size_t split_min = 400000;
+            if (const char* e = std::getenv("SPX_SPLIT_MIN")) split_min = (size_t)std::atoll(e);  // tuning aid
+            const bool split = ns >= split_min;
+            int launches = 0;
             SPX_CUDA(cudaEventRecord(reg->ev0, st));
-            if (max_it > 0) launch_align_gn<false>(c.reg, a, max_it, q, reg);
+            if (max_it > 0 && !split) {
+                launch_align_gn<false>(c.reg, a, max_it, q, reg);
+                launches = 1;
+            } else if (max_it > 0) {
+                constexpr int SPLIT_POLL = 4;
+                LinArgs f = a;  // factor pass: correspondences given, fused solve
+                f.idx_in = reg->nn_idx;
+                f.dist_in = reg->nn_dist;
+                for (int it = 0; it < max_it; ++it) {
+                    a.iter_index = f.iter_index = it;
+                    icp_fast_kernel<<<div_up(ns, NN_THREADS), NN_THREADS, 0, st>>>(a);
+                    SPX_LAUNCH_CHECK();
+                    icp_coop_kernel<<<q->sm_count * 16, NN_THREADS, 0, st>>>(a);
+                    SPX_LAUNCH_CHECK();
+                    launch_linearize<0, true>(c.reg, f, c.blocks, st, q->sm_count);
+                    launches += 3;
+                    if ((it + 1) % SPLIT_POLL == 0 && it + 1 < max_it) {
+                        SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, st));
+                        q->sync();
+                        if (hs->stop) break;
+                    }
+                }
+            }
             SPX_CUDA(cudaEventRecord(reg->ev1, st));
             SPX_CUDA(cudaMemcpyAsync(hs, reg->state, sizeof(RegState), cudaMemcpyDeviceToHost, st));
             q->sync();
             if (max_it > 0) fill_result(*hs, R);
             reg->timed = max_it > 0;
-            reg->last_launches = max_it > 0 ? 1 : 0;
+            reg->last_launches = launches;
             reg->last_iterations = max_it > 0 ? hs->iterations + 1 : 0;
             if (T_trace_host && max_it > 0) {
                 // iterations never run (converged earlier) repeat the final pose

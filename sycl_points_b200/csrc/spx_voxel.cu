@@ -259,16 +259,33 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __
                                                                 const uint32_t* __restrict__ svals, uint32_t n_valid,
                                                                 float min_count, uint32_t* __restrict__ flags,
                                                                 float4* __restrict__ means, VoxAttrs at) {
-    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
-    if (i >= n_valid) return;
-    const KeyT key = skeys[i];
+    // the block's tile of (key, point) is staged in shared memory with coalesced loads; the thread at
+    // the head of a voxel run then walks the run out of shared memory (a run that leaves the tile
+    // continues in global memory).  The sum stays strictly sequential in (key, index) order.
+    __shared__ KeyT sk[VX_THREADS];
+    __shared__ float4 sp[VX_THREADS];
+    const uint32_t base = blockIdx.x * VX_THREADS;
+    const uint32_t i = base + threadIdx.x;
+    const bool live = i < n_valid;
+    KeyT key = 0;
+    if (live) {
+        key = skeys[i];
+        sk[threadIdx.x] = key;
+        sp[threadIdx.x] = __ldg(pts + i);  // `pts` is the gathered (sorted-order) copy
+    }
+    __syncthreads();
+    if (!live) return;
     uint32_t flag = 0;
-    if (i == 0 || skeys[i - 1] != key) {
+    const bool head = i == 0 || (threadIdx.x > 0 ? sk[threadIdx.x - 1] : skeys[i - 1]) != key;
+    if (head) {
         // PointType point_sum = Zero; point_sum += points[idx] in sorted order — :193-201
         float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
         uint32_t j = i;
-        for (; j < n_valid && skeys[j] == key; ++j) {
-            const float4 p = __ldg(pts + j);  // `pts` is the gathered (sorted-order) copy
+        for (; j < n_valid; ++j) {
+            const uint32_t l = j - base;
+            const bool in_tile = l < VX_THREADS;
+            if ((in_tile ? sk[l] : skeys[j]) != key) break;
+            const float4 p = in_tile ? sp[l] : __ldg(pts + j);
             sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
         }
         if (sw >= min_count) {  // :204

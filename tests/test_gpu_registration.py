@@ -442,3 +442,23 @@ def test_align_correspondences_exact_with_warm_start(spx, q, pair, max_corr, shi
     assert within.sum() > 100
     assert np.array_equal(idx[within], oi[within]) and np.array_equal(dist[within], od[within])
     assert (dist[~within] > np.float32(max_corr) ** 2).all()
+
+
+@pytest.mark.parametrize("reg", REGS)
+def test_split_kernel_path_equals_fused(spx, q, pair, reg, monkeypatch):
+    """Large clouds run the Gauss-Newton loop as three launches per iteration (search kernels with
+    their own register budget) instead of one cooperative launch; forced here on the small pair:
+    identical correspondences, identical sums, hence bit-identical poses, iterations and inliers."""
+    params = spx.RegistrationParams(reg_type=spx.RegType[reg], max_iterations=7)
+    params.robust.type = spx.RobustLossType.HUBER
+    T0 = np.eye(4, dtype=np.float32)
+    T0[:3, 3] = [0.3, -0.2, 0.05]
+    fused = spx.Registration(q, params).align(pair["src"], pair["tgt"], pair["tree"], T0, trace=True)
+    monkeypatch.setenv("SPX_SPLIT_MIN", "0")
+    r = spx.Registration(q, params)
+    split = r.align(pair["src"], pair["tgt"], pair["tree"], T0, trace=True)
+    assert r.last_timing()["launches"] >= 3
+    monkeypatch.delenv("SPX_SPLIT_MIN")
+    assert split.iterations == fused.iterations and split.converged == fused.converged
+    assert split.inlier == fused.inlier
+    assert np.array_equal(split.trace, fused.trace) and np.array_equal(split.T, fused.T)
