@@ -230,8 +230,14 @@ def main():
 
     q = spx.DeviceQueue(local)
     info = q.device_info()
+    # every rank drives two queues from two host threads; when that oversubscribes the host's cores
+    # the queues wait on an OS primitive instead of spinning (SPX_BENCH_SYNC=spin|block overrides)
+    sync_mode = os.environ.get("SPX_BENCH_SYNC", "block" if 2 * world > (os.cpu_count() or 1) // 2 else "spin")
     tgt_raw, src_raw, T_gt = synthetic.kitti_pair(42 + rank)
     pipe = PairPipeline(spx, q, len(src_raw), len(tgt_raw))
+    if sync_mode == "block":
+        q.set_blocking_sync(True)
+        pipe.q2.set_blocking_sync(True)
     pin_src, pin_tgt = spx.PinnedArray(src_raw.shape), spx.PinnedArray(tgt_raw.shape)
     pin_src.array[...] = src_raw
     pin_tgt.array[...] = tgt_raw
@@ -254,7 +260,8 @@ def main():
         res = pipe.run()
     # ---------------- device-resident timing
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # one sampler per job: the JSON line reports rank 0's GPU
+        sampler.start()
     ev = [(spx.Event(), spx.Event()) for _ in range(args.steps)]
     loop_ms, launches, iters_done, align_ms = [], 0, 0, []
     barrier()
@@ -327,7 +334,8 @@ def main():
         "config": {"workload": WORKLOAD, "n_src_raw": int(len(src_raw)), "n_tgt_raw": int(len(tgt_raw)), "n_src": ns,
                    "n_tgt": nt, "icp_iterations_per_pair": iters_done / args.steps,
                    "l2": "flushed before every step (256 MiB memset outside the per-step events)",
-                   "gpu": info["name"], "sm_count": info["sm_count"],
+                   "gpu": info["name"], "sm_count": info["sm_count"], "host_sync": sync_mode,
+                   "host_cores": os.cpu_count(),
                    "pose_error_vs_gt_m": float(np.linalg.norm(dT[:3, 3]))},
         "ms_per_iter": kern_ms,
         "align_loop_ms": float(np.mean(loop_ms)),

@@ -133,6 +133,9 @@ SPX_API int spx_queue_create_on_stream(int device, void* cuda_stream, spx_queue_
 SPX_API int spx_queue_destroy(spx_queue_t q);
 SPX_API int spx_queue_sync(spx_queue_t q); /* events.wait_and_throw(), sycl_utils.hpp:262-270 */
 SPX_API int spx_queue_device(spx_queue_t q, int* device);
+/* how spx_queue_sync (and every call that returns values to the host) waits: 0 = spin (lowest
+ * latency, default), 1 = block on an OS primitive (frees the core: many queues / ranks per host) */
+SPX_API int spx_queue_set_blocking_sync(spx_queue_t q, int blocking);
 /* Kernels launched by this library since load (all queues): bench.py's `gpu_launches`. */
 SPX_API uint64_t spx_kernel_launch_count(void);
 

@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
         "spx_queue_create_on_stream": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
         "spx_queue_destroy": (C.c_int, [vp]),
         "spx_queue_sync": (C.c_int, [vp]),
+        "spx_queue_set_blocking_sync": (C.c_int, [vp, C.c_int]),
         "spx_queue_device": (C.c_int, [vp, C.POINTER(C.c_int)]),
         "spx_kernel_launch_count": (C.c_uint64, []),
         "spx_malloc": (C.c_int, [vp, sz, C.POINTER(vp)]),

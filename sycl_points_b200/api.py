@@ -72,6 +72,10 @@ class DeviceQueue:
         """events.wait_and_throw()"""
         check(_lib.lib().spx_queue_sync(self._h))
 
+    def set_blocking_sync(self, blocking: bool = True):
+        """wait on an OS primitive instead of spinning (frees the core when many queues share a host)"""
+        check(_lib.lib().spx_queue_set_blocking_sync(self._h, 1 if blocking else 0))
+
     def wait_event(self, event: "Event"):
         """later work on this queue starts only after `event` (recorded on any queue) has completed"""
         check(_lib.lib().spx_queue_wait_event(self._h, event._h))

@@ -81,6 +81,8 @@ struct spx_queue_s {
     // pinned staging for small host<->device scalars
     char* pinned = nullptr;
     size_t pinned_cap = 0;
+    // optional blocking wait (cudaEventBlockingSync) instead of the default spin
+    cudaEvent_t block_ev = nullptr;
 
     void arena_reset() { arena_off = 0; }
     // Reserve the total a call needs BEFORE taking pointers: growing invalidates nothing in flight

@@ -57,7 +57,12 @@ void* spx_queue_s::pinned_get(size_t bytes) {
 }
 
 void spx_queue_s::sync() {
-    SPX_CUDA(cudaStreamSynchronize(stream));
+    if (block_ev) {
+        SPX_CUDA(cudaEventRecord(block_ev, stream));
+        SPX_CUDA(cudaEventSynchronize(block_ev));
+    } else {
+        SPX_CUDA(cudaStreamSynchronize(stream));
+    }
     for (void* p : retired) cudaFree(p);
     retired.clear();
 }
@@ -131,6 +136,7 @@ int spx_queue_destroy(spx_queue_t q) {
         for (void* p : q->retired) cudaFree(p);
         if (q->arena) cudaFree(q->arena);
         if (q->pinned) cudaFreeHost(q->pinned);
+        if (q->block_ev) cudaEventDestroy(q->block_ev);
         if (q->owns_stream && q->stream) cudaStreamDestroy(q->stream);
         delete q;
     });
@@ -141,6 +147,18 @@ int spx_queue_sync(spx_queue_t q) {
         SPX_REQUIRE(q, "[spx_queue_sync] null queue");
         DeviceGuard g(q->device);
         q->sync();
+    });
+}
+
+int spx_queue_set_blocking_sync(spx_queue_t q, int blocking) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[spx_queue_set_blocking_sync] null queue");
+        DeviceGuard g(q->device);
+        if (blocking && !q->block_ev) SPX_CUDA(cudaEventCreateWithFlags(&q->block_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+        if (!blocking && q->block_ev) {
+            cudaEventDestroy(q->block_ev);
+            q->block_ev = nullptr;
+        }
     });
 }
 
