@@ -121,21 +121,29 @@ struct BestK {
 template <int K>
 struct BestR {
     unsigned long long key[K];
+    bool dedup;  // a coarser level re-offers points the finer one has already seen
     static constexpr unsigned long long EMPTY = ((0x7f7fffffull << 32) | 0xffffffffull) + 1ull;  // FLT_MAX, -1
     __device__ __forceinline__ void init(int k) {
 #pragma unroll
         for (int j = 0; j < K; ++j) key[j] = (j < K - k) ? 0ull : EMPTY;
+        dedup = false;
     }
     __device__ __forceinline__ float worst() const { return __uint_as_float((uint32_t)((key[K - 1] - 1ull) >> 32)); }
     __device__ __forceinline__ void offer(float ds, int idx, uint32_t) {
         unsigned long long c = (((unsigned long long)__float_as_uint(ds) << 32) | (unsigned long long)(uint32_t)idx) + 1ull;
         if (c >= key[K - 1]) return;
+        if (dedup) {  // rare path (levels >= 1): is this exact (dist, index) already listed?
+            bool seen = false;
+#pragma unroll
+            for (int j = 0; j < K; ++j) seen |= (c == key[j]);
+            if (seen) return;
+        }
+        // K compare-exchanges, 2 ISETP + 4 SEL each: the new key sinks to its place, the old k-th falls off
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            // the same point re-offered by a coarser level: drop it (it sinks off the end as "infinity")
-            if (c == key[j]) c = ~0ull;
-            const unsigned long long lo = c < key[j] ? c : key[j];
-            const unsigned long long hi = c < key[j] ? key[j] : c;
+            const bool lt = c < key[j];
+            const unsigned long long lo = lt ? c : key[j];
+            const unsigned long long hi = lt ? key[j] : c;
             key[j] = lo;
             c = hi;
         }
@@ -143,6 +151,11 @@ struct BestR {
     __device__ __forceinline__ float dist_at(int j) const { return __uint_as_float((uint32_t)((key[j] - 1ull) >> 32)); }
     __device__ __forceinline__ int idx_at(int j) const { return (int)(uint32_t)((key[j] - 1ull) & 0xffffffffull); }
 };
+
+template <typename Best>
+__device__ __forceinline__ void best_set_dedup(Best&, bool) {}
+template <int K>
+__device__ __forceinline__ void best_set_dedup(BestR<K>& b, bool v) { b.dedup = v; }
 
 constexpr int GRID_SEG_CHUNK = 9;  // the merged first pass (3x3 rows) fits one chunk
 constexpr int GRID_BATCH = 4;  // candidate loads in flight per thread
@@ -298,13 +311,17 @@ __device__ __forceinline__ bool grid_first_pass(const GridView& g, float qx, flo
     const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
     const int xa = max(cx - 1, 0), xb = min(cx + 1, g.dx - 1);
     uint32_t ls[9], le[9];
+    // rows in order of proximity (the query's own row, the four edge neighbours, the four corners):
+    // the k-th best tightens early and most later candidates are rejected by one compare
+    constexpr int ORDER[9] = {4, 1, 3, 5, 7, 0, 2, 6, 8};
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
+    for (int s = 0; s < 9; ++s) {
+        const int t = ORDER[s];
         const int zz = cz + (t / 3) - 1, yy = cy + (t % 3) - 1;
         const bool ok = zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy;
         const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
-        ls[t] = ok ? __ldg(g.start + row + xa) : 0u;
-        le[t] = ok ? __ldg(g.start + row + xb + 1) : 0u;
+        ls[s] = ok ? __ldg(g.start + row + xa) : 0u;
+        le[s] = ok ? __ldg(g.start + row + xb + 1) : 0u;
     }
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -339,6 +356,7 @@ __device__ __forceinline__ void grid_search_levels(const GridLevels& g, float qx
     if (grid_first_pass(g.lv[0], qx, qy, qz, best, max_radius, stats)) return;
     for (int l = 0; l < g.n_levels; ++l) {
         const bool last = (l == g.n_levels - 1);
+        if (l == 1) best_set_dedup(best, true);
         if (stats) stats->level(l);
         if (grid_search(g.lv[l], qx, qy, qz, best, max_radius, l == 0 ? 2 : 1, last ? (1 << 20) : GRID_LEVEL_RINGS,
                         stats))

@@ -515,6 +515,97 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_kernel(const GridLe
     }
 }
 
+// 1 < k <= K in two launches, the split the k = 1 search and the registration kernels use: queries
+// the first pass cannot certify (not enough neighbours inside the 3x3x3 block: sparse regions,
+// clustered in a few blocks) go to a work list and are searched again — from scratch, registers
+// only — by a second kernel whose warps take 32 listed queries at a time, so the expensive queries
+// are packed densely into warps (no idle lanes next to them) and spread over every SM.
+template <int K>
+__global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_first_kernel(const GridLevels g, const float4* __restrict__ queries,
+                                                                           uint32_t nq, int k, Xform T, int has_T,
+                                                                           int32_t* __restrict__ idx, float* __restrict__ dist,
+                                                                           uint32_t* __restrict__ worklist,
+                                                                           unsigned int* __restrict__ wl_count) {
+    const uint32_t qi = blockIdx.x * GRID_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const float INF = __int_as_float(0x7f800000);
+    bool pending = false;
+    if (qi < nq) {
+        float4 q = __ldg(queries + qi);
+        if (has_T) q = transform_point(T, q);
+        BestR<K> best;
+        best.init(k);
+        if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && g.lv[0].n > 0)
+            pending = !grid_first_pass(g.lv[0], q.x, q.y, q.z, best, INF);
+        if (!pending) {
+            int32_t* irow = idx + (size_t)qi * k;
+            float* drow = dist + (size_t)qi * k;
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (j >= K - k) {
+                    irow[j - (K - k)] = best.idx_at(j);
+                    drow[j - (K - k)] = best.dist_at(j);
+                }
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pending);
+    if (m) {
+        unsigned int slot = 0;
+        if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+        if (pending) worklist[slot + __popc(m & ((1u << lane) - 1u))] = qi;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_list_kernel(const GridLevels g, const float4* __restrict__ queries,
+                                                                          int k, Xform T, int has_T,
+                                                                          int32_t* __restrict__ idx, float* __restrict__ dist,
+                                                                          const uint32_t* __restrict__ worklist,
+                                                                          const unsigned int* __restrict__ wl_count,
+                                                                          unsigned int* __restrict__ wl_cursor) {
+    const int lane = threadIdx.x & 31;
+    const float INF = __int_as_float(0x7f800000);
+    const unsigned int n_slow = *wl_count;
+    for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(wl_cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_slow) break;
+        if (base + lane < n_slow) {
+            const uint32_t qi = worklist[base + lane];
+            float4 q = __ldg(queries + qi);
+            if (has_T) q = transform_point(T, q);
+            BestR<K> best;
+            best.init(k);
+            grid_search_levels(g, q.x, q.y, q.z, best, INF);
+            int32_t* irow = idx + (size_t)qi * k;
+            float* drow = dist + (size_t)qi * k;
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (j >= K - k) {
+                    irow[j - (K - k)] = best.idx_at(j);
+                    drow[j - (K - k)] = best.dist_at(j);
+                }
+        }
+    }
+}
+
+template <int K>
+void launch_knn_reg(spx_index_t index, spx_queue_t q, const float4* qs, uint32_t nq, int k, const Xform& T, int has_T,
+                    int32_t* idx, float* dist) {
+    q->arena_reset();
+    q->arena_reserve((size_t)nq * 4 + 4096);
+    uint32_t* worklist = q->take<uint32_t>(nq);
+    unsigned int* counters = q->take<unsigned int>(16);
+    SPX_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), q->stream));
+    grid_knn_reg_first_kernel<K><<<div_up(nq, GRID_THREADS), GRID_THREADS, 0, q->stream>>>(index->levels, qs, nq, k, T, has_T, idx,
+                                                                                         dist, worklist, counters);
+    SPX_LAUNCH_CHECK();
+    grid_knn_reg_list_kernel<K><<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(index->levels, qs, k, T, has_T, idx, dist,
+                                                                                worklist, counters, counters + 1);
+}
+
 // work counters of the k = 1 search (tuning aid): stats[q] = {segments, candidates, shells, last level}
 __global__ void __launch_bounds__(GRID_THREADS) grid_nn_stats_kernel(const GridLevels g, const float4* __restrict__ queries,
                                                                       uint32_t nq, Xform T, int has_T, float max_radius,
@@ -856,15 +947,19 @@ int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, con
             // the drain kernel sizes itself to the device, not to the (unknown on the host) list length
             grid_nn1_coop_kernel<<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(index->levels, qs, T, has_T, INFINITY, idx,
                                                                                  dist, pos, worklist, counters, counters + 1);
+        } else if (k <= 20 && std::getenv("SPX_KNN_ONEPASS")) {  // tuning aid: the single-launch variant
+            if (k <= 5)
+                grid_knn_reg_kernel<5><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T, idx, dist);
+            else if (k <= 10)
+                grid_knn_reg_kernel<10><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T, idx, dist);
+            else
+                grid_knn_reg_kernel<20><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T, idx, dist);
         } else if (k <= 5) {
-            grid_knn_reg_kernel<5><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
-                                                                          idx, dist);
+            launch_knn_reg<5>(index, q, qs, (uint32_t)nq, k, T, has_T, idx, dist);
         } else if (k <= 10) {
-            grid_knn_reg_kernel<10><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
-                                                                           idx, dist);
+            launch_knn_reg<10>(index, q, qs, (uint32_t)nq, k, T, has_T, idx, dist);
         } else if (k <= 20) {
-            grid_knn_reg_kernel<20><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T,
-                                                                           idx, dist);
+            launch_knn_reg<20>(index, q, qs, (uint32_t)nq, k, T, has_T, idx, dist);
         } else {
             const size_t smem = (size_t)k * GRID_THREADS * 8;
             static bool attr_set = false;
