@@ -801,6 +801,20 @@ __global__ void gn_update_kernel(RegState* st, const double* sums, float lambda,
     gn_update(st, sums, lambda, crit_rot, crit_trans, iter_index, trace);
 }
 
+// optimiser state at the start of an align, written on the device (a small H2D copy would queue
+// behind another queue's bulk upload on the copy engine)
+__global__ void state_init_kernel(RegState* st, Xform T) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    RegState s;
+    memset(&s, 0, sizeof(s));
+    const float4 r[4] = {T.r0, T.r1, T.r2, T.r3};
+    for (int i = 0; i < 4; ++i) {
+        s.T[i][0] = r[i].x; s.T[i][1] = r[i].y; s.T[i][2] = r[i].z; s.T[i][3] = r[i].w;
+    }
+    s.error = FLT_MAX;
+    *st = s;
+}
+
 // one pass per cloud: 16-float reference covariance -> plane-regularised 6 floats
 __global__ void __launch_bounds__(128) prepare_cov_kernel(const float* __restrict__ cov16, uint32_t n,
                                                           float4* __restrict__ c0, float2* __restrict__ c1) {
@@ -1068,12 +1082,11 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     a.phase = r->phase;
     if (r->phase) SPX_CUDA(cudaMemsetAsync(r->phase, 0, PH_WORDS * sizeof(unsigned long long), st));
 
-    RegState* hs = static_cast<RegState*>(q->pinned_get(sizeof(RegState) + 64 + 32 * sizeof(double)));
-    std::memset(hs, 0, sizeof(RegState));
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) hs->T[i][j] = T_init_host ? T_init_host[j * 4 + i] : (i == j ? 1.0f : 0.0f);
-    hs->error = FLT_MAX;
-    SPX_CUDA(cudaMemcpyAsync(r->state, hs, sizeof(RegState), cudaMemcpyHostToDevice, st));
+    {
+        const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        state_init_kernel<<<1, 32, 0, st>>>(r->state, xform_from_colmajor(T_init_host ? T_init_host : I16));
+        SPX_LAUNCH_CHECK();
+    }
     SPX_CUDA(cudaMemsetAsync(r->ticket, 0, sizeof(unsigned int), st));
     return c;
 }

@@ -49,6 +49,18 @@ __device__ __forceinline__ bool voxel_coords(const float4 p, float inv, int c[3]
     return true;
 }
 
+// initialised on the device: a small H2D copy would queue behind another queue's bulk upload
+__global__ void coord_acc_init_kernel(CoordAcc* acc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) {
+            acc->mn[a] = INT_MAX;
+            acc->mx[a] = INT_MIN;
+        }
+        acc->valid = 0;
+        acc->pad = 0;
+    }
+}
+
 __global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __restrict__ pts, uint32_t n, float inv,
                                                                 CoordAcc* acc) {
     int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
@@ -281,12 +293,35 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __
         // PointType point_sum = Zero; point_sum += points[idx] in sorted order — :193-201
         float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
         uint32_t j = i;
-        for (; j < n_valid; ++j) {
+        const uint32_t tile_end = min(base + VX_THREADS, n_valid);
+        for (; j < tile_end; ++j) {
             const uint32_t l = j - base;
-            const bool in_tile = l < VX_THREADS;
-            if ((in_tile ? sk[l] : skeys[j]) != key) break;
-            const float4 p = in_tile ? sp[l] : __ldg(pts + j);
+            if (sk[l] != key) break;
+            const float4 p = sp[l];
             sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
+        }
+        // a run that leaves the tile (voxels next to the sensor hold hundreds of points) continues in
+        // global memory, 8 independent loads in flight per step; the adds stay in (key, index) order
+        bool open = (j == tile_end);
+        while (open && j < n_valid) {
+            KeyT kb[8];
+            float4 pb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t jj = min(j + u, n_valid - 1);
+                kb[u] = skeys[jj];
+                pb[u] = __ldg(pts + jj);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (open && j < n_valid && kb[u] == key) {
+                    sx = __fadd_rn(sx, pb[u].x); sy = __fadd_rn(sy, pb[u].y); sz = __fadd_rn(sz, pb[u].z);
+                    sw = __fadd_rn(sw, pb[u].w);
+                    ++j;
+                } else {
+                    open = false;
+                }
+            }
         }
         if (sw >= min_count) {  // :204
             flag = 1;
@@ -495,7 +530,8 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         }
         hacc->valid = 0;
         hacc->pad = 0;
-        SPX_CUDA(cudaMemcpyAsync(acc, hacc, sizeof(CoordAcc), cudaMemcpyHostToDevice, st));
+        coord_acc_init_kernel<<<1, 32, 0, st>>>(acc);
+        SPX_LAUNCH_CHECK();
         voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
         SPX_LAUNCH_CHECK();
         SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(CoordAcc), cudaMemcpyDeviceToHost, st));
