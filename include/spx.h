@@ -152,7 +152,8 @@ SPX_API int spx_memset(spx_queue_t q, void* dst, int value, size_t bytes);
 /* USM *shared* semantics for the C++ facade's shared_vector<T> (host-dereferenceable, device-usable):
  * CUDA managed memory + explicit prefetch (the reference's mem_advise hints, sycl_utils.hpp:283-364). */
 SPX_API int spx_malloc_managed(size_t bytes, void** out);
-SPX_API int spx_free_managed(void* ptr);
+SPX_API int spx_free_managed(void* ptr); /* returns the block to a size-class cache (no device sync) */
+SPX_API int spx_managed_trim(void);      /* releases every cached idle block */
 SPX_API int spx_prefetch(spx_queue_t q, const void* ptr, size_t bytes, int to_device); /* to_device 0 = to host */
 
 SPX_API int spx_event_create(spx_event_t* out);

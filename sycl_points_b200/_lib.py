@@ -143,6 +143,7 @@ def lib() -> C.CDLL:
         "spx_registration_shard_finish": (C.c_int, [vp, C.POINTER(RegistrationResultC)]),
         "spx_malloc_managed": (C.c_int, [sz, C.POINTER(vp)]),
         "spx_free_managed": (C.c_int, [vp]),
+        "spx_managed_trim": (C.c_int, []),
         "spx_prefetch": (C.c_int, [vp, vp, sz, C.c_int]),
         "spx_rng_create": (C.c_int, [C.c_uint32, C.POINTER(vp)]),
         "spx_rng_seed": (C.c_int, [vp, C.c_uint32]),
