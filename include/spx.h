@@ -200,6 +200,11 @@ SPX_API int spx_normals(spx_queue_t q, const float* points, size_t n, const int3
 /* covariance::extract_normals_async(points) — covariance.hpp:467-495 */
 SPX_API int spx_normals_from_covs(spx_queue_t q, const float* points, const float* covs, size_t n, float* normals);
 
+/* transform::transform_async(cloud, trans) — I/algorithms/common/transform.hpp:45-104: in place,
+ * points T p, covariances T C T^T (nullable), normals T n (nullable; not re-normalised, as the
+ * reference's kernel).  Asynchronous. */
+SPX_API int spx_transform(spx_queue_t q, float* points, float* covs, float* normals, size_t n, const float* T_host);
+
 /* ------------------------------------------------------------------ filters
  * filter::VoxelGrid::downsampling(points, result) — I/algorithms/filter/voxel_downsampling.hpp:50-62,
  * key = I/algorithms/common/voxel_constants.hpp:36-62.  Device radix sort by (key, index), fp32

@@ -150,6 +150,22 @@ def transform_points(T, pts) -> np.ndarray:
     return out
 
 
+def transform_cloud(T, pts, covs=None, normals=None):
+    """transform::transform (transform.hpp:45-104): returns (points, covs | None, normals | None)."""
+    pts = _pts(pts)
+    n = len(pts)
+    cv = None if covs is None else _covs_cm(covs)
+    nr = None if normals is None else _pts(normals)
+    o_p = np.empty_like(pts)
+    o_c = None if cv is None else np.empty((n, 16), np.float32)
+    o_n = None if nr is None else np.empty((n, 4), np.float32)
+    t = _T(T)
+    lib().orc_transform_cloud(_f(t), _f(pts), _f(cv), _f(nr), C.c_size_t(n), _f(o_p), _f(o_c), _f(o_n))
+    if o_c is not None:
+        o_c = np.ascontiguousarray(o_c.reshape(n, 4, 4).transpose(0, 2, 1))  # column-major -> row-major numpy
+    return o_p, o_c, o_n
+
+
 def knn_bruteforce(queries, targets, k: int, T=None):
     q, t = _pts(queries), _pts(targets)
     idx = np.empty((len(q), k), np.int32)

@@ -978,6 +978,28 @@ void orc_transform_points(const float* T16, const float* pts, size_t n, float* o
     }
 }
 
+// transform::transform_async — I/algorithms/common/transform.hpp:45-94: covariances T C T^T (:14-22),
+// normals T n (:24-30; the kernel's normalize<4>() result is DISCARDED there, so the reference's device
+// path leaves normals un-normalised — restated as is), points T p (:32-37).  Any of covs / normals
+// may be NULL.  Column-major 4x4 covariances.
+void orc_transform_cloud(const float* T16, const float* pts, const float* covs, const float* normals, size_t n,
+                         float* out_pts, float* out_covs, float* out_normals) {
+    const M4 T = load_T(T16);
+    for (size_t i = 0; i < n; ++i) {
+        if (covs) {
+            const M4 r = transform_cov(load_cov(covs + 16 * i), T);
+            for (int j = 0; j < 4; ++j)
+                for (int a = 0; a < 4; ++a) out_covs[16 * i + j * 4 + a] = r(a, j);
+        }
+        if (normals) {
+            const V4 r = mul<4, 4>(T, load_p(normals + 4 * i));
+            for (int a = 0; a < 4; ++a) out_normals[4 * i + a] = r(a);
+        }
+        const V4 r = transform_point(T, load_p(pts + 4 * i));
+        for (int a = 0; a < 4; ++a) out_pts[4 * i + a] = r(a);
+    }
+}
+
 // I/algorithms/knn/bruteforce.hpp:24-96 with the oracle's fixed distance formula (the
 // reference's sycl::dot leaves contraction to the SYCL implementation):
 // dist = fma(dz,dz,fma(dy,dy,dx*dx)) on the transformed query, order (dist, index).

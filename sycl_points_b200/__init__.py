@@ -10,4 +10,4 @@ from .api import (DeviceArray, DeviceQueue, Event, ExecutionOptions, KDTree, KNN
                   LinearizedResult, OptimizationMethod, PinnedArray, PointCloudShared, PreprocessFilter, RegType,
                   Registration, RegistrationParams, RegistrationPipeline, RegistrationPipelineParams,
                   RegistrationResult, RobustLossType, VoxelGrid, covariance, device_count, kernel_launch_count,
-                  knn_search_bruteforce, robust_scale_schedule)
+                  knn_search_bruteforce, robust_scale_schedule, transform)

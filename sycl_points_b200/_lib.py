@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "spx_covariance": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals_from_covs": (C.c_int, [vp, f32p, f32p, sz, f32p]),
+        "spx_transform": (C.c_int, [vp, f32p, f32p, f32p, sz, hostf]),
         "spx_voxel_downsample": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, C.POINTER(C.c_size_t)]),
         "spx_voxel_downsample_attrs": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                                  C.POINTER(C.c_size_t)]),

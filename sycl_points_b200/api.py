@@ -580,6 +580,42 @@ class PreprocessFilter:
         return output
 
 
+class transform:  # namespace sycl_points::algorithms::transform (common/transform.hpp:45-136)
+    @staticmethod
+    def transform(cloud: PointCloudShared, trans) -> None:
+        """in place: points T p, covariances T C T^T, normals T n"""
+        if cloud.size() == 0:
+            return
+        t16 = _T16(trans)
+        check(_lib.lib().spx_transform(cloud.queue.handle, cloud.points.ptr,
+                                       _ptr(cloud.covs) if cloud.has_cov() else None,
+                                       _ptr(cloud.normals) if cloud.has_normal() else None, cloud.size(), _hostf(t16)))
+
+    transform_async = transform
+
+    @staticmethod
+    def transform_copy(cloud: PointCloudShared, trans) -> PointCloudShared:
+        out = PointCloudShared(cloud.queue)
+        n = cloud.size()
+
+        def dup(a: DeviceArray | None, enable: bool):
+            if not enable:
+                return None
+            b = DeviceArray(cloud.queue, a.shape, a.dtype)
+            check(_lib.lib().spx_memcpy_d2d(cloud.queue.handle, b.ptr, a.ptr, a.nbytes))
+            return b
+
+        out.points = dup(cloud.points, n > 0) if n else DeviceArray(cloud.queue, (0, 4), np.float32)
+        out._n = n
+        out.covs = dup(cloud.covs, cloud.has_cov())
+        out.normals = dup(cloud.normals, cloud.has_normal())
+        out.rgb = dup(cloud.rgb, cloud.has_rgb())
+        out.intensities = dup(cloud.intensities, cloud.has_intensity())
+        out.timestamp_offsets = dup(cloud.timestamp_offsets, cloud.has_timestamps())
+        transform.transform(out, trans)
+        return out
+
+
 # ------------------------------------------------------------------ registration
 class RegType(enum.IntEnum):  # factor.hpp:18-32
     POINT_TO_POINT = 0

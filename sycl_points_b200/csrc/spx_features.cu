@@ -96,6 +96,65 @@ __global__ void __launch_bounds__(FEAT_THREADS) normals_from_covs_kernel(const f
 
 }  // namespace
 
+// ------------------------------------------------------------------ cloud transform
+// transform::transform_async — I/algorithms/common/transform.hpp:45-94, in place.  Same fma chains
+// as eigen_utils::multiply (eigen_utils.hpp:88-127): covariance = T (C T^T) with the 4x4 products
+// written out (terms with an exact zero factor — the 4th row / column of C — are no-ops and are
+// skipped), normal = T n (NOT re-normalised: the reference discards normalize<4>()'s result,
+// transform.hpp:24-30), point = T p.  One kernel for all three attributes.
+namespace {
+__global__ void __launch_bounds__(FEAT_THREADS) transform_cloud_kernel(float4* __restrict__ pts, float* __restrict__ covs,
+                                                                       float4* __restrict__ normals, uint32_t n, Xform T) {
+    const uint32_t i = blockIdx.x * FEAT_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 rows[4] = {T.r0, T.r1, T.r2, T.r3};
+    if (covs) {
+        float4* c = reinterpret_cast<float4*>(covs + (size_t)i * 16);  // column-major: c[j] = column j
+        const float4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+        const float Cm[4][4] = {{c0.x, c1.x, c2.x, c3.x}, {c0.y, c1.y, c2.y, c3.y}, {c0.z, c1.z, c2.z, c3.z},
+                                {c0.w, c1.w, c2.w, c3.w}};  // Cm[row][col]
+        const float Tm[4][4] = {{rows[0].x, rows[0].y, rows[0].z, rows[0].w}, {rows[1].x, rows[1].y, rows[1].z, rows[1].w},
+                                {rows[2].x, rows[2].y, rows[2].z, rows[2].w}, {rows[3].x, rows[3].y, rows[3].z, rows[3].w}};
+        float X[4][4], R[4][4];
+        // X = C * T^T : X(i,j) = fma chain over k of C(i,k) * T(j,k), k ascending, starting from 0
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = __fmaf_rn(Cm[a][k], Tm[b][k], acc);
+                X[a][b] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = __fmaf_rn(Tm[a][k], X[k][b], acc);
+                R[a][b] = acc;
+            }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[b] = make_float4(R[0][b], R[1][b], R[2][b], R[3][b]);
+    }
+    if (normals) {
+        const float4 v = normals[i];
+        float o[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            o[a] = __fmaf_rn(rows[a].w, v.w, __fmaf_rn(rows[a].z, v.z, __fmaf_rn(rows[a].y, v.y, __fmaf_rn(rows[a].x, v.x, 0.0f))));
+        normals[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    const float4 p = pts[i];
+    float o[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        o[a] = __fmaf_rn(rows[a].w, p.w, __fmaf_rn(rows[a].z, p.z, __fmaf_rn(rows[a].y, p.y, __fmaf_rn(rows[a].x, p.x, 0.0f))));
+    pts[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+}  // namespace
+
 extern "C" {
 
 int spx_covariance(spx_queue_t q, const float* points, size_t n, const int32_t* knn_idx, int k, float* covs) {
@@ -135,6 +194,20 @@ int spx_normals_from_covs(spx_queue_t q, const float* points, const float* covs,
         DeviceGuard g(q->device);
         normals_from_covs_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
             reinterpret_cast<const float4*>(points), covs, (uint32_t)n, reinterpret_cast<float4*>(normals));
+        SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_transform(spx_queue_t q, float* points, float* covs, float* normals, size_t n, const float* T_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && T_host, "[transform::transform] null argument");
+        SPX_REQUIRE(n < (1ull << 31), "[transform::transform] too many points");
+        if (n == 0) return;
+        SPX_REQUIRE(points, "[transform::transform] null points");
+        DeviceGuard g(q->device);
+        transform_cloud_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
+            reinterpret_cast<float4*>(points), covs, reinterpret_cast<float4*>(normals), (uint32_t)n,
+            xform_from_colmajor(T_host));
         SPX_LAUNCH_CHECK();
     });
 }

@@ -463,12 +463,13 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
         if (i < a.ns) {
             Best1 best;
             best.init();
-            const float4 q = transform_point(T, __ldg(a.src_pts + i));
-            if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
-                uint32_t wp = 0xffffffffu;
-                if (warm && __ldcg(a.idx_out + i) >= 0) wp = __ldcg(a.pos_out + i);
-                pending = !icp_fast(a.grid, q.x, q.y, q.z, wp, a.max_corr, best);
-            }
+            // the three loads are independent: issued together, one round trip instead of three
+            const float4 ps = __ldg(a.src_pts + i);
+            const int prev_i = warm ? __ldcg(a.idx_out + i) : -1;
+            const uint32_t prev_p = warm ? __ldcg(a.pos_out + i) : 0xffffffffu;
+            const float4 q = transform_point(T, ps);
+            if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
+                pending = !icp_fast(a.grid, q.x, q.y, q.z, prev_i >= 0 ? prev_p : 0xffffffffu, a.max_corr, best);
             a.idx_out[i] = best.i;
             a.dist_out[i] = best.d;
             a.pos_out[i] = best.p;
@@ -532,12 +533,12 @@ __global__ void __launch_bounds__(NN_THREADS, 8) icp_fast_kernel(const LinArgs a
     if (i < a.ns) {
         Best1 best;
         best.init();
-        const float4 q = transform_point(T, __ldg(a.src_pts + i));
-        if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
-            uint32_t wp = 0xffffffffu;
-            if (warm && a.idx_out[i] >= 0) wp = a.pos_out[i];
-            pending = !icp_fast(a.grid, q.x, q.y, q.z, wp, a.max_corr, best);
-        }
+        const float4 ps = __ldg(a.src_pts + i);
+        const int prev_i = warm ? a.idx_out[i] : -1;
+        const uint32_t prev_p = warm ? a.pos_out[i] : 0xffffffffu;
+        const float4 q = transform_point(T, ps);
+        if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
+            pending = !icp_fast(a.grid, q.x, q.y, q.z, prev_i >= 0 ? prev_p : 0xffffffffu, a.max_corr, best);
         a.idx_out[i] = best.i;
         a.dist_out[i] = best.d;
         a.pos_out[i] = best.p;

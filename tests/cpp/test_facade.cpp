@@ -10,6 +10,7 @@
 #include <set>
 #include <vector>
 
+#include "sycl_points/algorithms/common/transform.hpp"
 #include "sycl_points/algorithms/feature/covariance.hpp"
 #include "sycl_points/algorithms/filter/preprocess_filter.hpp"
 #include "sycl_points/algorithms/filter/voxel_downsampling.hpp"
@@ -299,6 +300,21 @@ static void test_align(const sycl_utils::DeviceQueue& queue) {
     covariance::estimate_async(*tree_s, source, 10).wait_and_throw();
     covariance::estimate_normals_async(*tree_t, target, 10).wait_and_throw();
     CHECK(target.has_cov() && source.has_cov() && target.has_normal());
+
+    {  // transform::transform_copy (device) vs transform_cpu_copy (host loop): T * source == target
+        auto moved = transform::transform_copy(source, T);
+        auto moved_cpu = transform::transform_cpu_copy(source, T);
+        queue.ptr->wait();
+        float worst = 0.f, worst_cov = 0.f;
+        for (size_t i = 0; i < moved.size(); ++i) {
+            worst = std::max(worst, ((*moved.points)[i] - (*target.points)[i]).norm());
+            worst = std::max(worst, ((*moved.points)[i] - (*moved_cpu.points)[i]).norm());
+            worst_cov = std::max(worst_cov, ((*moved.covs)[i] - (*moved_cpu.covs)[i]).norm());
+        }
+        CHECK(moved.size() == source.size() && moved.has_cov());
+        CHECK(worst < 1e-4f);
+        CHECK(worst_cov < 1e-5f);
+    }
 
     struct Wrap : knn::KNNBase {  // hides the KDTree type: forces the generic (injected) path
         const knn::KDTree& t;

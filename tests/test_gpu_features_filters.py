@@ -201,3 +201,26 @@ def test_random_sampling_matches_reference_rng_stream(spx, q, bundled):
     f.set_random_seed(99)
     out = f.random_sampling(cloud, 50)
     assert np.array_equal(out.points_host(), pts[oracle.Rng(99).random_sampling_flags(n, 50).astype(bool)])
+
+
+def test_cloud_transform_bit_exact(spx, q, bundled):
+    """transform::transform (transform.hpp:45-104): points, covariances (T C T^T) and normals in one
+    in-place kernel, same fma chains as the reference's eigen_utils::multiply -> bit-exact vs the oracle."""
+    tgt = bundled["target_ds"]
+    cloud = spx.PointCloudShared(q, tgt)
+    nn = spx.KDTree.build(q, cloud).knn_search(cloud, 10)
+    spx.covariance.estimate(nn, cloud)
+    spx.covariance.estimate_normals(nn, cloud)
+    covs, nrm = cloud.covs_host(), cloud.normals_host()
+    T = oracle.se3_exp(np.array([0.3, -0.2, 0.5, 1.5, -2.0, 0.25], np.float32))
+    o_p, o_c, o_n = oracle.transform_cloud(T, tgt, covs, nrm)
+    moved = spx.transform.transform_copy(cloud, T)
+    assert np.array_equal(moved.points_host(), o_p)
+    assert np.array_equal(moved.covs_host(), o_c)
+    assert np.array_equal(moved.normals_host(), o_n)
+    assert np.array_equal(cloud.points_host(), tgt)  # the copy left the original alone
+    spx.transform.transform(cloud, T)  # in place
+    assert np.array_equal(cloud.points_host(), o_p) and np.array_equal(cloud.covs_host(), o_c)
+    bare = spx.PointCloudShared(q, tgt)
+    spx.transform.transform(bare, T)
+    assert np.array_equal(bare.points_host(), o_p) and not bare.has_cov()
