@@ -52,9 +52,9 @@ typedef enum spx_status {
 typedef enum spx_reg_type {
     SPX_REG_POINT_TO_POINT = 0,
     SPX_REG_POINT_TO_PLANE = 1,
-    SPX_REG_POINT_TO_DISTRIBUTION = 2, /* not built yet: SPX_ERR_UNSUPPORTED */
+    SPX_REG_POINT_TO_DISTRIBUTION = 2,
     SPX_REG_GICP = 3,
-    SPX_REG_GENZ = 4 /* not built yet: SPX_ERR_UNSUPPORTED */
+    SPX_REG_GENZ = 4 /* not built: SPX_ERR_UNSUPPORTED */
 } spx_reg_type;
 
 /* I/algorithms/robust/robust.hpp:14-20 */

@@ -185,6 +185,10 @@ private:
             throw std::runtime_error(
                 "[Registration::validate_params] Covariance matrices of source and target must be pre-computed "
                 "before performing GICP matching.");
+        if (this->params_.reg_type == RegType::POINT_TO_DISTRIBUTION && !target.has_cov())
+            throw std::runtime_error(
+                "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
+                "performing Point-to-Distribution ICP matching.");
         if (this->params_.robust.type != robust::RobustLossType::NONE && this->params_.robust.default_scale <= 0.0f) {
             std::cout << "[Caution] `robust.default_scale` must be greater than zero. Disable robust loss." << std::endl;
             this->params_.robust.type = robust::RobustLossType::NONE;

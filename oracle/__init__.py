@@ -50,7 +50,7 @@ class RegResult(C.Structure):
     ]
 
 
-REG = {"POINT_TO_POINT": 0, "POINT_TO_PLANE": 1, "GICP": 3}
+REG = {"POINT_TO_POINT": 0, "POINT_TO_PLANE": 1, "POINT_TO_DISTRIBUTION": 2, "GICP": 3}
 LOSS = {"NONE": 0, "HUBER": 1, "TUKEY": 2, "CAUCHY": 3, "GEMAN_MCCLURE": 4}
 OPT = {"GN": 0, "LM": 1, "DOGLEG": 2}
 

@@ -526,7 +526,30 @@ inline PointTerm lin_gicp(const M4& T, const V4& ps, const M4& cs, const V4& pt,
     return o;
 }
 
-// I/algorithms/registration/factor.hpp:156-164, 218-230, 287-306
+// I/algorithms/registration/factor.hpp:311-317: Mahalanobis = inverse of the RAW target covariance
+inline M4 p2d_mahalanobis(const M4& ct) {
+    const M3 inv = inverse(block3(ct));
+    M4 out = M4::zero();
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) out(i, j) = inv(i, j);
+    return out;
+}
+
+// I/algorithms/registration/factor.hpp:326-354 (identity-weighted Jacobian = the plain SE(3) Jacobian)
+inline PointTerm lin_p2d(const M4& T, const V4& ps, const V4& pt, const M4& ct) {
+    const V4 r = residual_of(T, ps, pt);
+    const M4 Minv = p2d_mahalanobis(ct);
+    const Mat<4, 6> J = se3_jacobian(T, ps);
+    const Mat<6, 4> JTM = mul<6, 4, 4>(transpose(J), Minv);
+    PointTerm o;
+    o.H = ensure_symmetric<6>(mul<6, 4, 6>(JTM, J));
+    o.b = mul<6, 4>(JTM, r);
+    o.sq_err = dot<4>(r, mul<4, 4>(Minv, r));
+    o.res_norm = std::sqrt(o.sq_err);
+    return o;
+}
+
+// I/algorithms/registration/factor.hpp:156-164, 218-230, 287-306, 362-373
 inline float err_only(int reg, const M4& T, const V4& ps, const M4& cs, const V4& pt, const M4& ct, const V4& nrm) {
     const V4 r = residual_of(T, ps, pt);
     if (reg == R_P2P) return dot<4>(r, r);
@@ -539,7 +562,7 @@ inline float err_only(int reg, const M4& T, const V4& ps, const M4& cs, const V4
         const float d = dot<3>(n, r3);
         return d * d;
     }
-    const M4 Minv = gicp_mahalanobis_inv(cs, ct, T);
+    const M4 Minv = reg == R_P2D ? p2d_mahalanobis(ct) : gicp_mahalanobis_inv(cs, ct, T);
     return dot<4>(r, mul<4, 4>(Minv, r));
 }
 
@@ -580,6 +603,8 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
                 t = lin_p2p(T, ps, pt);
             } else if (reg == R_P2PLANE) {
                 t = lin_p2plane(T, ps, pt, c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
+            } else if (reg == R_P2D) {
+                t = lin_p2d(T, ps, pt, c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);
             } else {
                 t = lin_gicp(T, ps, c.src_covs ? load_cov(c.src_covs + 16 * i) : ident, pt,
                              c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);
@@ -616,6 +641,8 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
                 t = lin_p2p(T, ps, pt);
             } else if (reg == R_P2PLANE) {
                 t = lin_p2plane(T, ps, pt, c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
+            } else if (reg == R_P2D) {
+                t = lin_p2d(T, ps, pt, c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);
             } else {
                 t = lin_gicp(T, ps, c.src_covs ? load_cov(c.src_covs + 16 * i) : ident, pt,
                              c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);

@@ -856,6 +856,9 @@ class Registration:
         if self.params.reg_type == RegType.GICP and (not source.has_cov() or not target.has_cov()):
             raise RuntimeError("[Registration::validate_params] Covariance matrices of source and target must be "
                                "pre-computed before performing GICP matching.")
+        if self.params.reg_type == RegType.POINT_TO_DISTRIBUTION and not target.has_cov():
+            raise RuntimeError("[Registration::validate_params] Covariance matrices of target must be pre-computed "
+                               "before performing Point-to-Distribution ICP matching.")
 
     def align(self, source: PointCloudShared, target: PointCloudShared, target_knn: KNNBase, initial_guess=None,
               options: ExecutionOptions | None = None, trace: bool = False) -> RegistrationResult:

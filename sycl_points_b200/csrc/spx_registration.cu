@@ -264,8 +264,8 @@ __device__ __forceinline__ void accumulate_point(const Xform& T, const float4 ps
             acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(ja0, pe0, ja1, pe1, ja2, pe2)));
         }
         acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
-    } else {  // GICP, factor.hpp:239-278
-        const Sym3 Mi = gicp_minv(T, cs, ct);
+    } else {  // GICP, factor.hpp:239-278; point-to-distribution, :326-354 (ct already holds inverse(C_t))
+        const Sym3 Mi = (REG == SPX_REG_POINT_TO_DISTRIBUTION) ? ct : gicp_minv(T, cs, ct);
         const float m0 = chain3(Mi.xx, r0, Mi.xy, r1, Mi.xz, r2);
         const float m1 = chain3(Mi.xy, r0, Mi.yy, r1, Mi.yz, r2);
         const float m2 = chain3(Mi.xz, r0, Mi.yz, r1, Mi.zz, r2);
@@ -297,7 +297,7 @@ __device__ __forceinline__ float point_error(const Xform& T, const float4 ps, co
         const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
         return __fmul_rn(d, d);
     }
-    const Sym3 Mi = gicp_minv(T, cs, ct);  // factor.hpp:287-306
+    const Sym3 Mi = (REG == SPX_REG_POINT_TO_DISTRIBUTION) ? ct : gicp_minv(T, cs, ct);  // factor.hpp:287-306, 362-373
     const float m0 = chain3(Mi.xx, r0, Mi.xy, r1, Mi.xz, r2);
     const float m1 = chain3(Mi.xy, r0, Mi.yy, r1, Mi.yz, r2);
     const float m2 = chain3(Mi.xz, r0, Mi.yz, r1, Mi.zz, r2);
@@ -324,6 +324,13 @@ __device__ __forceinline__ Sym3 load_sym(const float4* c0, const float2* c1, siz
 // through update_covariance_plane like any other matrix.
 template <int REG>
 __device__ __forceinline__ void load_covs(const LinArgs& a, uint32_t i, int ti, Sym3& cs, Sym3& ct) {
+    if (REG == SPX_REG_POINT_TO_DISTRIBUTION) {
+        // only the target covariance matters: prepared = inverse(C_t) (compute_target_mahalanobis,
+        // factor.hpp:311-317 — the RAW covariance, no plane regularisation); missing -> identity
+        if (a.tgt_c0) ct = load_sym(a.tgt_c0, a.tgt_c1, (size_t)ti);
+        else ct = sym_inverse(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : identity_sym());
+        return;
+    }
     if (REG != SPX_REG_GICP) return;
     if (a.src_c0) cs = load_sym(a.src_c0, a.src_c1, i);
     else cs = plane_regularize(a.src_cov16 ? load_cov16(a.src_cov16 + (size_t)i * 16) : identity_sym());
@@ -818,10 +825,11 @@ __global__ void state_init_kernel(RegState* st, Xform T) {
 
 // one pass per cloud: 16-float reference covariance -> plane-regularised 6 floats
 __global__ void __launch_bounds__(128) prepare_cov_kernel(const float* __restrict__ cov16, uint32_t n,
-                                                          float4* __restrict__ c0, float2* __restrict__ c1) {
+                                                          float4* __restrict__ c0, float2* __restrict__ c1, int invert) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
-    const Sym3 r = plane_regularize(cov16 ? load_cov16(cov16 + (size_t)i * 16) : identity_sym());
+    const Sym3 raw = cov16 ? load_cov16(cov16 + (size_t)i * 16) : identity_sym();
+    const Sym3 r = invert ? sym_inverse(raw) : plane_regularize(raw);  // invert: point-to-distribution
     c0[i] = make_float4(r.xx, r.xy, r.xz, r.yy);
     c1[i] = make_float2(r.yz, r.zz);
 }
@@ -846,6 +854,9 @@ void launch_linearize(int reg, const LinArgs& a, unsigned blocks, cudaStream_t s
     switch (reg) {
         case SPX_REG_POINT_TO_POINT: launch_linearize_one<SPX_REG_POINT_TO_POINT, MODE, SOLVE>(a, blocks, st, sm_count); break;
         case SPX_REG_POINT_TO_PLANE: launch_linearize_one<SPX_REG_POINT_TO_PLANE, MODE, SOLVE>(a, blocks, st, sm_count); break;
+        case SPX_REG_POINT_TO_DISTRIBUTION:
+            launch_linearize_one<SPX_REG_POINT_TO_DISTRIBUTION, MODE, SOLVE>(a, blocks, st, sm_count);
+            break;
         default: launch_linearize_one<SPX_REG_GICP, MODE, SOLVE>(a, blocks, st, sm_count); break;
     }
     SPX_LAUNCH_CHECK();
@@ -856,6 +867,9 @@ void launch_error(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
     switch (reg) {
         case SPX_REG_POINT_TO_POINT: error_kernel<SPX_REG_POINT_TO_POINT, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
         case SPX_REG_POINT_TO_PLANE: error_kernel<SPX_REG_POINT_TO_PLANE, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
+        case SPX_REG_POINT_TO_DISTRIBUTION:
+            error_kernel<SPX_REG_POINT_TO_DISTRIBUTION, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a);
+            break;
         default: error_kernel<SPX_REG_GICP, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
     }
     SPX_LAUNCH_CHECK();
@@ -869,9 +883,9 @@ unsigned coop_blocks(int device_sm_count) {
 }
 
 void check_reg_loss(int reg, int loss, const char* where) {
-    if (reg == SPX_REG_POINT_TO_DISTRIBUTION || reg == SPX_REG_GENZ)
-        throw Error(SPX_ERR_UNSUPPORTED, std::string(where) + " RegType not built yet (POINT_TO_DISTRIBUTION / GENZ)");
-    if (!(reg == SPX_REG_POINT_TO_POINT || reg == SPX_REG_POINT_TO_PLANE || reg == SPX_REG_GICP))
+    if (reg == SPX_REG_GENZ) throw Error(SPX_ERR_UNSUPPORTED, std::string(where) + " RegType GENZ is not built");
+    if (!(reg == SPX_REG_POINT_TO_POINT || reg == SPX_REG_POINT_TO_PLANE || reg == SPX_REG_GICP ||
+          reg == SPX_REG_POINT_TO_DISTRIBUTION))
         throw Error(SPX_ERR_INVALID_ARGUMENT, "[Registration::dispatch] Combination not found in tags!");
     if (loss < SPX_LOSS_NONE || loss > SPX_LOSS_GEMAN_MCCLURE)
         throw Error(SPX_ERR_INVALID_ARGUMENT, "[Registration::dispatch] Combination not found in tags!");
@@ -976,6 +990,10 @@ void validate(const spx_registration_params& P, const float* src_covs, const flo
         throw Error(SPX_ERR_INVALID_ARGUMENT,
                     "[Registration::validate_params] Covariance matrices of source and target must be pre-computed "
                     "before performing GICP matching.");
+    if (P.reg_type == SPX_REG_POINT_TO_DISTRIBUTION && !tgt_covs)
+        throw Error(SPX_ERR_INVALID_ARGUMENT,
+                    "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
+                    "performing Point-to-Distribution ICP matching.");
 }
 
 struct AlignCtx {
@@ -1029,22 +1047,30 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     a.ns = (uint32_t)ns;
     a.tgt_pts = reinterpret_cast<const float4*>(tgt_points);
     a.tgt_normals = reinterpret_cast<const float4*>(tgt_normals);
-    if (P.reg_type == SPX_REG_GICP) {
+    if (P.reg_type == SPX_REG_GICP || P.reg_type == SPX_REG_POINT_TO_DISTRIBUTION) {
+        // pose-independent per-point matrices, prepared once per align: GICP = plane-regularised
+        // covariances of both clouds; point-to-distribution = inverse of the raw target covariance
+        const bool gicp = P.reg_type == SPX_REG_GICP;
         size_t cap = r->src_cap;
-        ensure(r->src_c0, cap, ns, st);
-        ensure(r->src_c1, r->src_cap, ns, st);
+        if (gicp) {
+            ensure(r->src_c0, cap, ns, st);
+            ensure(r->src_c1, r->src_cap, ns, st);
+        }
         cap = r->tgt_cap;
         ensure(r->tgt_c0, cap, nt, st);
         ensure(r->tgt_c1, r->tgt_cap, nt, st);
-        if (ns) {
-            prepare_cov_kernel<<<div_up(ns, 128), 128, 0, st>>>(src_covs, (uint32_t)ns, r->src_c0, r->src_c1);
+        if (ns && gicp) {
+            prepare_cov_kernel<<<div_up(ns, 128), 128, 0, st>>>(src_covs, (uint32_t)ns, r->src_c0, r->src_c1, 0);
             SPX_LAUNCH_CHECK();
         }
         if (nt) {
-            prepare_cov_kernel<<<div_up(nt, 128), 128, 0, st>>>(tgt_covs, (uint32_t)nt, r->tgt_c0, r->tgt_c1);
+            prepare_cov_kernel<<<div_up(nt, 128), 128, 0, st>>>(tgt_covs, (uint32_t)nt, r->tgt_c0, r->tgt_c1, gicp ? 0 : 1);
             SPX_LAUNCH_CHECK();
         }
-        a.src_c0 = r->src_c0; a.src_c1 = r->src_c1;
+        if (gicp) {
+            a.src_c0 = r->src_c0;
+            a.src_c1 = r->src_c1;
+        }
         a.tgt_c0 = r->tgt_c0; a.tgt_c1 = r->tgt_c1;
     }
     if (P.reg_type == SPX_REG_POINT_TO_PLANE && !tgt_normals) {
@@ -1214,6 +1240,10 @@ void launch_align_gn(int reg_type, LinArgs& a, int max_it, spx_queue_t q, spx_re
         case SPX_REG_POINT_TO_PLANE:
             resident = coop_blocks<SPX_REG_POINT_TO_PLANE, SHARDED>(q->sm_count);
             fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_PLANE, SHARDED>;
+            break;
+        case SPX_REG_POINT_TO_DISTRIBUTION:
+            resident = coop_blocks<SPX_REG_POINT_TO_DISTRIBUTION, SHARDED>(q->sm_count);
+            fn = (const void*)align_gn_kernel<SPX_REG_POINT_TO_DISTRIBUTION, SHARDED>;
             break;
         default:
             resident = coop_blocks<SPX_REG_GICP, SHARDED>(q->sm_count);

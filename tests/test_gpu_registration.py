@@ -12,7 +12,7 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 LOSSES = ["NONE", "HUBER", "TUKEY", "CAUCHY", "GEMAN_MCCLURE"]
-REGS = ["POINT_TO_POINT", "POINT_TO_PLANE", "GICP"]
+REGS = ["POINT_TO_POINT", "POINT_TO_PLANE", "GICP", "POINT_TO_DISTRIBUTION"]
 
 
 @pytest.fixture(scope="module")
@@ -33,6 +33,22 @@ def pair(spx, q, bundled):
     otree = oracle.KDTree(tgt_h)
     return dict(src=src, tgt=tgt, tree=tt, src_h=src_h, tgt_h=tgt_h, cov_s=src.covs_host(), cov_t=tgt.covs_host(),
                 nrm_t=tgt.normals_host(), otree=otree)
+
+
+def clouds_for(spx, q, pair, reg):
+    """(target cloud, its host covariances) to use with factor `reg`.  Point-to-distribution inverts
+    the RAW target covariance (factor.hpp:311-317); the 10-neighbour covariances of a planar LiDAR
+    patch are near-singular in fp32, the inverse is then indefinite and the reference's own formula
+    yields NaN residual norms (reproduced identically by oracle and GPU).  The parity comparison
+    uses what a P2D user would: covariances with a 1 cm^2 isotropic floor."""
+    if reg != "POINT_TO_DISTRIBUTION":
+        return pair["tgt"], pair["cov_t"]
+    if "tgt_p2d" not in pair:
+        cov = pair["cov_t"].copy()
+        cov[:, :3, :3] += np.float32(1e-2) * np.eye(3, dtype=np.float32)
+        pair["tgt_p2d"] = spx.PointCloudShared(q, pair["tgt_h"], cov, pair["nrm_t"])
+        pair["cov_t_p2d"] = cov
+    return pair["tgt_p2d"], pair["cov_t_p2d"]
 
 
 def pose_delta(Ta, Tb):
@@ -56,18 +72,19 @@ def test_linearize_and_error_vs_oracle(spx, q, pair, reg, loss):
     params.robust.type = spx.RobustLossType[loss]
     params.robust.default_scale = 0.7
     reg_obj = spx.Registration(q, params)
-    lin = reg_obj.compute_linearized_result(pair["src"], pair["tgt"], pair["tree"], T)
+    tgt, cov_t = clouds_for(spx, q, pair, reg)
+    lin = reg_obj.compute_linearized_result(pair["src"], tgt, pair["tree"], T)
     H, b, e, inl = oracle.linearize(oracle.REG[reg], oracle.LOSS[loss], pair["src_h"], pair["cov_s"], pair["tgt_h"],
-                                    pair["cov_t"], pair["nrm_t"], nn_idx, nn_dist, T, 4.0, 0.7, mode=1)
-    tol = 2e-4 if reg == "GICP" else 1e-5
+                                    cov_t, pair["nrm_t"], nn_idx, nn_dist, T, 4.0, 0.7, mode=1)
+    tol = 2e-4 if reg in ("GICP", "POINT_TO_DISTRIBUTION") else 1e-5
     assert lin.inlier == inl
     assert rel(lin.H, H) <= tol and rel(lin.b, b) <= tol and abs(lin.error - e) <= tol * abs(e)
     assert np.array_equal(lin.H, lin.H.T)
     # frozen-neighbour error at a trial pose (registration.hpp:350-359)
     T2 = (T @ oracle.se3_exp(np.array([1e-3, 2e-3, -1e-3, 0.01, -0.02, 0.005], np.float32))).astype(np.float32)
-    ge, gi = reg_obj.compute_error_frozen(pair["src"], pair["tgt"], T2)
+    ge, gi = reg_obj.compute_error_frozen(pair["src"], tgt, T2)
     oe, oi = oracle.error(oracle.REG[reg], oracle.LOSS[loss], pair["src_h"], pair["cov_s"], pair["tgt_h"],
-                          pair["cov_t"], pair["nrm_t"], nn_idx, nn_dist, T2, 4.0, 0.7, mode=1)
+                          cov_t, pair["nrm_t"], nn_idx, nn_dist, T2, 4.0, 0.7, mode=1)
     assert gi == oi and abs(ge - oe) <= tol * abs(oe)
 
 
@@ -175,10 +192,11 @@ def test_align_matches_oracle_iteration_by_iteration(spx, q, pair, reg, opt):
     params.optimization_method = spx.OptimizationMethod({"GN": 0, "LM": 1, "DOGLEG": 2}[opt])
     params.criteria.translation = 0.0
     params.criteria.rotation = 0.0
-    res = spx.Registration(q, params).align(pair["src"], pair["tgt"], pair["tree"], trace=True)
+    tgt, cov_t = clouds_for(spx, q, pair, reg)
+    res = spx.Registration(q, params).align(pair["src"], tgt, pair["tree"], trace=True)
     P = oracle.default_params(reg_type=oracle.REG[reg], loss=1, opt_method=oracle.OPT[opt], max_iterations=iters,
                               robust_default_scale=1.0, crit_translation=0.0, crit_rotation=0.0)
-    ores = oracle.align(P, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"], pair["nrm_t"], pair["otree"],
+    ores = oracle.align(P, pair["src_h"], pair["cov_s"], pair["tgt_h"], cov_t, pair["nrm_t"], pair["otree"],
                         trace=True)
     tol = 1e-5
     for it in range(iters):
@@ -453,10 +471,11 @@ def test_split_kernel_path_equals_fused(spx, q, pair, reg, monkeypatch):
     params.robust.type = spx.RobustLossType.HUBER
     T0 = np.eye(4, dtype=np.float32)
     T0[:3, 3] = [0.3, -0.2, 0.05]
-    fused = spx.Registration(q, params).align(pair["src"], pair["tgt"], pair["tree"], T0, trace=True)
+    tgt, _ = clouds_for(spx, q, pair, reg)
+    fused = spx.Registration(q, params).align(pair["src"], tgt, pair["tree"], T0, trace=True)
     monkeypatch.setenv("SPX_SPLIT_MIN", "0")
     r = spx.Registration(q, params)
-    split = r.align(pair["src"], pair["tgt"], pair["tree"], T0, trace=True)
+    split = r.align(pair["src"], tgt, pair["tree"], T0, trace=True)
     assert r.last_timing()["launches"] >= 3
     monkeypatch.delenv("SPX_SPLIT_MIN")
     assert split.iterations == fused.iterations and split.converged == fused.converged
