@@ -58,12 +58,29 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_totals_kernel(c
     if (threadIdx.x == 0) totals[blockIdx.x] = total;
 }
 
-// phase 3 (also the whole job when n fits one tile): scan inside the tile + tile offset
+// phase 3 (also the whole job when n fits one tile): scan inside the tile + tile offset.
+// RAW_TOTALS: `tile_offsets` holds the un-scanned per-tile totals and every block sums its
+// predecessors itself (a few KB of L2 reads) — saves the middle launch for up to SCAN_TILE tiles.
+template <bool RAW_TOTALS>
 static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_apply_kernel(const uint32_t* __restrict__ in, size_t n,
                                                                        const uint32_t* __restrict__ tile_offsets,
                                                                        uint32_t* __restrict__ out,
                                                                        uint32_t* __restrict__ grand_total) {
     __shared__ uint32_t sw[33];
+    __shared__ uint32_t tile_off;
+    uint32_t my_off = 0;
+    if (RAW_TOTALS) {
+        uint32_t part = 0;
+        for (uint32_t t = threadIdx.x; t < blockIdx.x; t += SCAN_THREADS) part += tile_offsets[t];
+        uint32_t tot;
+        block_exclusive_scan(part, sw, &tot);
+        if (threadIdx.x == 0) tile_off = tot;
+        __syncthreads();
+        my_off = tile_off;
+        __syncthreads();  // sw is reused below
+    } else if (tile_offsets) {
+        my_off = tile_offsets[blockIdx.x];
+    }
     const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t s = 0;
@@ -74,15 +91,14 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_apply_kernel(co
         s += v[i];
     }
     uint32_t total;
-    uint32_t run = block_exclusive_scan(s, sw, &total) + (tile_offsets ? tile_offsets[blockIdx.x] : 0u);
+    uint32_t run = block_exclusive_scan(s, sw, &total) + my_off;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         const size_t j = base + i;
         if (j < n) out[j] = run;
         run += v[i];
     }
-    if (grand_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
-        *grand_total = (tile_offsets ? tile_offsets[blockIdx.x] : 0u) + total;
+    if (grand_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *grand_total = my_off + total;
 }
 
 inline size_t scan_scratch_elems(size_t n) {
@@ -103,15 +119,20 @@ inline void exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* ou
     }
     const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (tiles == 1) {
-        scan_tile_apply_kernel<<<1, SCAN_THREADS, 0, st>>>(in, n, nullptr, out, grand_total);
+        scan_tile_apply_kernel<false><<<1, SCAN_THREADS, 0, st>>>(in, n, nullptr, out, grand_total);
         SPX_LAUNCH_CHECK();
         return;
     }
     uint32_t* totals = scratch;
     scan_tile_totals_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, totals);
     SPX_LAUNCH_CHECK();
+    if (tiles <= (size_t)SCAN_TILE) {  // two launches: each apply block sums its predecessors' totals itself
+        scan_tile_apply_kernel<true><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, totals, out, grand_total);
+        SPX_LAUNCH_CHECK();
+        return;
+    }
     exclusive_scan_u32(st, totals, totals, tiles, scratch + align_up(tiles, 64), nullptr);
-    scan_tile_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, totals, out, grand_total);
+    scan_tile_apply_kernel<false><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, totals, out, grand_total);
     SPX_LAUNCH_CHECK();
 }
 
