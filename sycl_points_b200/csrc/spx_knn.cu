@@ -577,7 +577,9 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_list_kernel(const G
                                                                           int32_t* __restrict__ idx, float* __restrict__ dist,
                                                                           const uint32_t* __restrict__ worklist,
                                                                           const unsigned int* __restrict__ wl_count,
-                                                                          unsigned int* __restrict__ wl_cursor) {
+                                                                          unsigned int* __restrict__ wl_cursor,
+                                                                          uint32_t* __restrict__ far_list,
+                                                                          unsigned int* __restrict__ far_count) {
     const int lane = threadIdx.x & 31;
     const float INF = __int_as_float(0x7f800000);
     const unsigned int n_slow = *wl_count;
@@ -592,16 +594,41 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_list_kernel(const G
             if (has_T) q = transform_point(T, q);
             BestR<K> best;
             best.init(k);
-            grid_search_levels(g, q.x, q.y, q.z, best, INF);
-            int32_t* irow = idx + (size_t)qi * k;
-            float* drow = dist + (size_t)qi * k;
+            // the two finest levels per lane; a query still open after that has its k-th neighbour
+            // several coarse cells away and goes to the warp-cooperative kernel
+            if (grid_search_levels(g, q.x, q.y, q.z, best, INF, (NoStats*)nullptr, 2)) {
+                int32_t* irow = idx + (size_t)qi * k;
+                float* drow = dist + (size_t)qi * k;
 #pragma unroll
-            for (int j = 0; j < K; ++j)
-                if (j >= K - k) {
-                    irow[j - (K - k)] = best.idx_at(j);
-                    drow[j - (K - k)] = best.dist_at(j);
-                }
+                for (int j = 0; j < K; ++j)
+                    if (j >= K - k) {
+                        irow[j - (K - k)] = best.idx_at(j);
+                        drow[j - (K - k)] = best.dist_at(j);
+                    }
+            } else {
+                far_list[atomicAdd(far_count, 1u)] = qi;
+            }
         }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(GRID_THREADS) grid_knn_far_kernel(const GridLevels g, const float4* __restrict__ queries, int k,
+                                                                    Xform T, int has_T, int32_t* __restrict__ idx,
+                                                                    float* __restrict__ dist, const uint32_t* __restrict__ far_list,
+                                                                    const unsigned int* __restrict__ far_count,
+                                                                    unsigned int* __restrict__ far_cursor) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_far = *far_count;
+    for (;;) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(far_cursor, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_far) break;
+        const uint32_t qi = far_list[t];
+        float4 q = __ldg(queries + qi);
+        if (has_T) q = transform_point(T, q);
+        knn_coop_search<K>(g, q.x, q.y, q.z, k, idx + (size_t)qi * k, dist + (size_t)qi * k);
     }
 }
 
@@ -609,15 +636,20 @@ template <int K>
 void launch_knn_reg(spx_index_t index, spx_queue_t q, const float4* qs, uint32_t nq, int k, const Xform& T, int has_T,
                     int32_t* idx, float* dist) {
     q->arena_reset();
-    q->arena_reserve((size_t)nq * 4 + 4096);
+    q->arena_reserve((size_t)nq * 8 + 4096);
     uint32_t* worklist = q->take<uint32_t>(nq);
-    unsigned int* counters = q->take<unsigned int>(16);
-    SPX_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), q->stream));
+    uint32_t* far_list = q->take<uint32_t>(nq);
+    unsigned int* counters = q->take<unsigned int>(16);  // {list count, list cursor, far count, far cursor}
+    SPX_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), q->stream));
     grid_knn_reg_first_kernel<K><<<div_up(nq, GRID_THREADS), GRID_THREADS, 0, q->stream>>>(index->levels, qs, nq, k, T, has_T, idx,
                                                                                          dist, worklist, counters);
     SPX_LAUNCH_CHECK();
     grid_knn_reg_list_kernel<K><<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(index->levels, qs, k, T, has_T, idx, dist,
-                                                                                worklist, counters, counters + 1);
+                                                                                worklist, counters, counters + 1, far_list,
+                                                                                counters + 2);
+    SPX_LAUNCH_CHECK();
+    grid_knn_far_kernel<K><<<q->sm_count, GRID_THREADS, 0, q->stream>>>(index->levels, qs, k, T, has_T, idx, dist, far_list,
+                                                                       counters + 2, counters + 3);
 }
 
 // work counters of the k = 1 search (tuning aid): stats[q] = {segments, candidates, shells, last level}
