@@ -148,13 +148,6 @@ __device__ __forceinline__ int float_ordered(float f) {
     const int i = __float_as_int(f);
     return i ^ ((i >> 31) & 0x7fffffff);
 }
-inline float float_from_ordered(int o) {
-    const int i = o ^ ((o >> 31) & 0x7fffffff);
-    float f;
-    std::memcpy(&f, &i, 4);
-    return f;
-}
-
 struct BBoxAcc {
     int mn[3];
     int mx[3];
@@ -239,31 +232,6 @@ __device__ __forceinline__ uint32_t cell_of(const GridGeom& g, const float4 p) {
     return ((uint32_t)cz * (uint32_t)g.dy + (uint32_t)cy) * (uint32_t)g.dx + (uint32_t)cx;
 }
 
-// Points arrive spatially sorted (voxel order), so the lanes of a warp mostly share a handful of
-// cells — on the coarse levels a single one.  One atomic per distinct cell per warp instead of one
-// per point (120 k atomics on six addresses took 30 us per coarse level).
-__global__ void cell_count_kernel(const float4* __restrict__ pts, uint32_t n, GridGeom g, uint32_t* __restrict__ cell_id,
-                                  uint32_t* __restrict__ counts) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    uint32_t c = 0xffffffffu;
-    if (i < n) {
-        const float4 p = __ldg(pts + i);
-        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) c = cell_of(g, p);
-        cell_id[i] = c;
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    if (c != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(counts + c, (uint32_t)__popc(peers));
-}
-
-__global__ void occupied_kernel(const uint32_t* __restrict__ counts, size_t ncells, unsigned long long* occupied) {
-    unsigned long long c = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (size_t)gridDim.x * blockDim.x)
-        c += counts[i] != 0;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(occupied, c);
-}
-
 // ---- cell-size selection without a host round trip per attempt
 // The finest cell edge is chosen so that an occupied cell holds ~3 points.  Occupancy as a function
 // of the cell edge is measured for OCC_CANDS candidate edges in ONE pass: every point sets one bit
@@ -343,26 +311,62 @@ __global__ void occupied_from_start_kernel(const uint32_t* __restrict__ start, s
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(occupied, c);
 }
 
-// Stable scatter: a point's slot inside its cell is its rank among the cell's points in ORIGINAL
-// index order, so the sorted copy (and therefore the visiting order) is deterministic run to run.
-// Rank = number of earlier points of the same cell; computed with one atomic per point on a
-// per-cell cursor would be order-dependent, so instead each cell's points are written in any order
-// and then ordered by original index in a second pass (cells are tiny).
-__global__ void cell_scatter_kernel(const float4* __restrict__ pts, uint32_t n, const uint32_t* __restrict__ cell_id,
-                                    const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
-                                    float4* __restrict__ sorted) {
+// Stable order: a point's slot inside its cell must be its rank among the cell's points in ORIGINAL
+// index order, so that the sorted copy (and therefore the visiting order) is deterministic run to
+// run.  The scatter below hands out slots with atomics (arrival order); each cell's slice of the
+// finest level is then ordered by original index in a second pass (cells are tiny).  Points arrive
+// spatially sorted (voxel order), so the lanes of a warp mostly share a handful of cells — on the
+// coarse levels a single one: one atomic per distinct cell per warp (__match_any_sync) instead of one
+// per point (120 k atomics on six addresses took 30 us per coarse level).
+// ---- all levels in one pass
+// The levels are independent counting sorts of the same points, so they share launches: one count
+// kernel, ONE scan over the concatenated per-level count arrays, one scatter kernel.  Level l's
+// counts start at cell_base[l]; every level sums to n, so the scanned value of level l's cell c is
+// l*n + (position inside the level): the levels' sorted copies are laid out back to back in one
+// array and `start` values index it directly (GridView::pts is the common base pointer).
+struct LevelSet {
+    int n_levels;
+    GridGeom geom[GRID_MAX_LEVELS];
+    uint32_t cell_base[GRID_MAX_LEVELS + 1];
+};
+
+__global__ void levels_count_kernel(const float4* __restrict__ pts, uint32_t n, LevelSet ls, uint32_t* __restrict__ counts) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const uint32_t c = i < n ? cell_id[i] : 0xffffffffu;
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (c != 0xffffffffu && lane == leader) base = __ldg(start + c) + atomicAdd(cursor + c, (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (c == 0xffffffffu) return;
-    const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
-    const float4 p = __ldg(pts + i);
-    sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float((int)i));
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = false;
+    if (i < n) {
+        p = __ldg(pts + i);
+        ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    }
+    for (int l = 0; l < ls.n_levels; ++l) {
+        const uint32_t c = ok ? ls.cell_base[l] + cell_of(ls.geom[l], p) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (ok && lane == __ffs(peers) - 1) atomicAdd(counts + c, (uint32_t)__popc(peers));
+    }
+}
+
+__global__ void levels_scatter_kernel(const float4* __restrict__ pts, uint32_t n, LevelSet ls,
+                                      const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                      float4* __restrict__ sorted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = false;
+    if (i < n) {
+        p = __ldg(pts + i);
+        ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    }
+    const float4 rec = make_float4(p.x, p.y, p.z, __int_as_float((int)i));
+    for (int l = 0; l < ls.n_levels; ++l) {
+        const uint32_t c = ok ? ls.cell_base[l] + cell_of(ls.geom[l], p) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (ok && lane == leader) base = __ldg(start + c) + atomicAdd(cursor + c, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) sorted[base + __popc(peers & ((1u << lane) - 1u))] = rec;
+    }
 }
 
 // insertion sort of each cell's slice by original index (one thread per cell)
@@ -747,16 +751,14 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         while (map_bits < 8u * n && map_bits < (1u << 30)) map_bits <<= 1;
         const uint32_t words_per_map = map_bits / 32u;
         q->arena_reset();
-        q->arena_reserve(sizeof(BBoxAcc) + sizeof(OccPlan) + 1024 + (size_t)OCC_CANDS * words_per_map * 4 + (size_t)n * 4 +
-                         2 * (MAX_CELLS + 64) * 4 + scan_scratch_elems(MAX_CELLS + 1) * 4 + 8192);
-        // (MAX_CELLS is the per-call budget below)
+        q->arena_reserve(sizeof(BBoxAcc) + sizeof(OccPlan) + 1024 + (size_t)OCC_CANDS * words_per_map * 4 +
+                         2 * (MAX_CELLS + MAX_CELLS / 32 + 128) * 4 + scan_scratch_elems(MAX_CELLS + MAX_CELLS / 32 + 128) * 4 + 8192);
         BBoxAcc* acc = q->take<BBoxAcc>(1);
         OccPlan* plan = q->take<OccPlan>(1);
         unsigned int* ones = q->take<unsigned int>(OCC_CANDS);
         uint32_t* bitmaps = q->take<uint32_t>((size_t)OCC_CANDS * words_per_map);
-        uint32_t* cell_id = q->take<uint32_t>(n);
-        uint32_t* counts = q->take<uint32_t>(MAX_CELLS + 64);
-        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(MAX_CELLS + 1));
+        uint32_t* counts = q->take<uint32_t>(MAX_CELLS + MAX_CELLS / 32 + 128);
+        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(MAX_CELLS + MAX_CELLS / 32 + 128));
 
         char* pin = static_cast<char*>(q->pinned_get(1024));
         BBoxAcc* hacc = reinterpret_cast<BBoxAcc*>(pin);
@@ -813,36 +815,6 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
             }
             return nc;
         };
-        auto count_level = [&](float cell, const int dims[3], size_t ncells) {
-            GridGeom geom{lo[0], lo[1], lo[2], 1.0f / cell, dims[0], dims[1], dims[2]};
-            SPX_CUDA(cudaMemsetAsync(counts, 0, (ncells + 1) * 4, st));
-            cell_count_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, geom, cell_id, counts);
-            SPX_LAUNCH_CHECK();
-        };
-        auto finish_level = [&](int level, float cell, const int dims[3], size_t ncells, bool order) {
-            SPX_CUDA(cudaMallocAsync(&ix->start[level], (ncells + 1) * 4, st));
-            SPX_CUDA(cudaMallocAsync(&ix->sorted[level], (size_t)bb.finite * sizeof(float4), st));
-            exclusive_scan_u32(st, counts, ix->start[level], ncells + 1, scan_tmp, nullptr);
-            SPX_CUDA(cudaMemsetAsync(counts, 0, (ncells + 1) * 4, st));  // reuse as per-cell cursor
-            cell_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, cell_id, ix->start[level], counts,
-                                                               ix->sorted[level]);
-            SPX_LAUNCH_CHECK();
-            if (order) {
-                cell_order_kernel<<<div_up(ncells, 256), 256, 0, st>>>(ix->start[level], ncells, ix->sorted[level]);
-                SPX_LAUNCH_CHECK();
-            }
-            GridView& v = L.lv[level];
-            v.ox = lo[0]; v.oy = lo[1]; v.oz = lo[2];
-            v.cell = cell;
-            v.inv = 1.0f / cell;
-            v.dx = dims[0]; v.dy = dims[1]; v.dz = dims[2];
-            v.margin = 1e-3f * cell + 2e-6f * (max_abs + max_ext);
-            v.start = ix->start[level];
-            v.pts = ix->sorted[level];
-            v.n = bb.finite;
-            ix->ncells[level] = ncells;
-        };
-
         // finest level: the cell edge at which an occupied cell holds ~3 points (measured optimum on
         // LiDAR-shaped clouds for both the k = 10 and the warm-started k = 1 searches: smaller cells
         // send more queries past the first pass, larger ones add candidates to every query), read off
@@ -875,33 +847,61 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
             cell = std::max(cell, 1e-6f * std::max(max_abs, 1.0f));
         }
         int dims[3];
-        size_t ncells = 0;
         for (;;) {  // respect the dense-grid budget
             const double nc = dims_for(cell, dims);
-            if (nc <= (double)MAX_CELLS) {
-                ncells = (size_t)dims[0] * dims[1] * dims[2];
-                break;
-            }
+            if (nc <= (double)MAX_CELLS) break;
             cell *= (float)std::cbrt(nc / (double)MAX_CELLS) * 1.02f;
         }
-        count_level(cell, dims, ncells);
-        finish_level(0, cell, dims, ncells, true);
-        SPX_CUDA(cudaMallocAsync(&ix->occ_dev, sizeof(unsigned long long), st));
-        SPX_CUDA(cudaMemsetAsync(ix->occ_dev, 0, sizeof(unsigned long long), st));
-        occupied_from_start_kernel<<<std::min(div_up(ncells, 256), q->sm_count * 8), 256, 0, st>>>(ix->start[0], ncells,
-                                                                                                 ix->occ_dev);
-        SPX_LAUNCH_CHECK();
-
-        // coarser levels until the coarsest grid is only a few cells wide
+        // level geometry: the finest grid, then grids GRID_LEVEL_FACTOR x coarser until only a few cells wide
+        LevelSet ls{};
+        float cells[GRID_MAX_LEVELS];
         int level = 0;
-        while (level + 1 < GRID_MAX_LEVELS && std::max(dims[0], std::max(dims[1], dims[2])) > 4) {
+        size_t total_cells = 0;
+        for (;;) {
+            ls.geom[level] = GridGeom{lo[0], lo[1], lo[2], 1.0f / cell, dims[0], dims[1], dims[2]};
+            ls.cell_base[level] = (uint32_t)total_cells;
+            cells[level] = cell;
+            ix->ncells[level] = (size_t)dims[0] * dims[1] * dims[2];
+            total_cells += ix->ncells[level];
+            if (level + 1 >= GRID_MAX_LEVELS || std::max(dims[0], std::max(dims[1], dims[2])) <= 4) break;
             ++level;
             cell *= (float)GRID_LEVEL_FACTOR;
             dims_for(cell, dims);
-            ncells = (size_t)dims[0] * dims[1] * dims[2];
-            count_level(cell, dims, ncells);
-            finish_level(level, cell, dims, ncells, false);
         }
+        ls.n_levels = level + 1;
+        ls.cell_base[ls.n_levels] = (uint32_t)total_cells;
+        SPX_REQUIRE((unsigned long long)ls.n_levels * bb.finite < (1ull << 32) && total_cells + 1 < (1ull << 32),
+                    "[KDTree::build] cloud too large for 32-bit index positions");
+        // (counts / scan scratch were sized for MAX_CELLS of the finest level + the coarser ones: <= 1/63 more)
+        SPX_REQUIRE(total_cells + 1 <= MAX_CELLS + MAX_CELLS / 32 + 64, "[KDTree::build] internal: cell budget exceeded");
+
+        SPX_CUDA(cudaMallocAsync(&ix->start[0], (total_cells + 1) * 4, st));
+        SPX_CUDA(cudaMallocAsync(&ix->sorted[0], (size_t)ls.n_levels * bb.finite * sizeof(float4), st));
+        SPX_CUDA(cudaMemsetAsync(counts, 0, (total_cells + 1) * 4, st));
+        levels_count_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, counts);
+        SPX_LAUNCH_CHECK();
+        exclusive_scan_u32(st, counts, ix->start[0], total_cells + 1, scan_tmp, nullptr);
+        SPX_CUDA(cudaMemsetAsync(counts, 0, (total_cells + 1) * 4, st));  // reuse as per-cell cursor
+        levels_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, ix->start[0], counts, ix->sorted[0]);
+        SPX_LAUNCH_CHECK();
+        cell_order_kernel<<<div_up(ix->ncells[0], 256), 256, 0, st>>>(ix->start[0], ix->ncells[0], ix->sorted[0]);
+        SPX_LAUNCH_CHECK();
+        for (int l = 0; l < ls.n_levels; ++l) {
+            GridView& v = L.lv[l];
+            v.ox = lo[0]; v.oy = lo[1]; v.oz = lo[2];
+            v.cell = cells[l];
+            v.inv = ls.geom[l].inv;
+            v.dx = ls.geom[l].dx; v.dy = ls.geom[l].dy; v.dz = ls.geom[l].dz;
+            v.margin = 1e-3f * cells[l] + 2e-6f * (max_abs + max_ext);
+            v.start = ix->start[0] + ls.cell_base[l];
+            v.pts = ix->sorted[0];  // common base: `start` values of level l already include l * n
+            v.n = bb.finite;
+        }
+        SPX_CUDA(cudaMallocAsync(&ix->occ_dev, sizeof(unsigned long long), st));
+        SPX_CUDA(cudaMemsetAsync(ix->occ_dev, 0, sizeof(unsigned long long), st));
+        occupied_from_start_kernel<<<std::min(div_up(ix->ncells[0], 256), q->sm_count * 8), 256, 0, st>>>(
+            ix->start[0], ix->ncells[0], ix->occ_dev);
+        SPX_LAUNCH_CHECK();
         L.n_levels = level + 1;
         // no final sync: everything above is ordered on the queue's stream, and so is every search
     });

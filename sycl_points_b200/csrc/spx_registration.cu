@@ -29,7 +29,6 @@ namespace {
 
 constexpr int LIN_THREADS = 256;
 constexpr int LIN_WARPS = LIN_THREADS / 32;
-constexpr int N_H = 21;
 constexpr int S_B = 21, S_ERR = 27, S_INL = 28;
 constexpr int N_ACC = 28;  // float accumulators per thread (21 H + 6 b + error)
 
@@ -838,8 +837,9 @@ template <int REG, int MODE, bool SOLVE>
 void launch_linearize_one(const LinArgs& a, unsigned blocks, cudaStream_t st, int sm_count) {
     if (MODE == 1) {
         // the fused correspondence search synchronises the grid: cooperative launch, one resident wave
-        int per_sm = 0;
-        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linearize_kernel<REG, MODE, SOLVE>, LIN_THREADS, 0));
+        static int per_sm = 0;  // queried once per variant
+        if (per_sm == 0)
+            SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linearize_kernel<REG, MODE, SOLVE>, LIN_THREADS, 0));
         blocks = std::max(1u, std::min(blocks, (unsigned)std::max(per_sm, 1) * (unsigned)sm_count));
         void* args[] = {(void*)&a};
         SPX_CUDA(cudaLaunchCooperativeKernel((const void*)linearize_kernel<REG, MODE, SOLVE>, dim3(blocks), dim3(LIN_THREADS),
@@ -877,8 +877,9 @@ void launch_error(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
 
 template <int REG, bool SHARDED>
 unsigned coop_blocks(int device_sm_count) {
-    int per_sm = 0;
-    SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_gn_kernel<REG, SHARDED>, LIN_THREADS, 0));
+    static int per_sm = 0;  // same on every device this library targets (sm_100a); queried once per variant
+    if (per_sm == 0)
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_gn_kernel<REG, SHARDED>, LIN_THREADS, 0));
     return (unsigned)std::max(per_sm, 1) * (unsigned)device_sm_count;
 }
 
