@@ -497,11 +497,17 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
         a.wl_counters[(par ^ 1) * 2 + 1] = 0;
     }
     const unsigned int n_slow = __ldcg(wl_count);
+    // tuning aid (phase buffer attached, iteration 2): per-warp {ns in this loop, queries, slowest query ns, list size}
+    const bool rec = a.phase != nullptr && it == 2;
+    const unsigned long long t_loop = rec ? global_ns() : 0ull;
+    unsigned long long t_worst = 0;
+    unsigned int n_done = 0;
     for (;;) {
         unsigned int k = 0;
         if (lane == 0) k = atomicAdd(wl_cursor, 1u);
         k = __shfl_sync(FULL, k, 0);
         if (k >= n_slow) break;
+        const unsigned long long t_q = rec ? global_ns() : 0ull;
         const uint32_t i = __ldcg(a.worklist + k);
         const float4 q = transform_point(T, __ldg(a.src_pts + i));
         Best1 best;
@@ -514,6 +520,18 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
             a.dist_out[i] = best.d;
             a.pos_out[i] = best.p;
         }
+        if (rec) {
+            t_worst = max(t_worst, global_ns() - t_q);
+            ++n_done;
+        }
+    }
+    if (rec && lane == 0) {
+        unsigned long long* w = a.phase + PH_MAX_ITERS * PH_N + (size_t)(blockIdx.x * LIN_WARPS + (threadIdx.x >> 5)) * 5;
+        w[0] = global_ns() - t_loop;
+        w[1] = n_done;
+        w[2] = t_worst;
+        w[3] = n_slow;
+        w[4] = 1;
     }
     __threadfence();
     grid.sync();
