@@ -215,6 +215,159 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const KeyT* _
     }
 }
 
+// ---- the same sort as ONE kernel per digit ("onesweep": chained scan with decoupled look-back).
+// The digit histograms of every pass come out of the key kernel; a pass then needs no separate
+// histogram and no device-wide scan: a tile publishes its per-digit counts in `status`, walks back
+// over its predecessors' entries until it meets an inclusive one, and scatters.  Tiles are taken by
+// ticket, so a tile only ever waits for tiles that already run.  Used while counts fit the 30 value
+// bits of a status word; above that the three-kernel passes above take over.
+constexpr uint32_t OS_LOCAL = 1u << 30;  // status word = flag | count
+constexpr uint32_t OS_INCL = 2u << 30;
+constexpr uint32_t OS_VALUE = OS_LOCAL - 1u;
+constexpr int OS_MAX_PASSES = 8;
+template <typename KeyT>
+struct OsItems {
+    static constexpr int value = sizeof(KeyT) == 4 ? 16 : 8;  // keys per thread (tile staged in 32 / 24 KB of smem)
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4* __restrict__ pts, uint32_t n,
+                                                                    float inv, KeyGeom g, KeyT* __restrict__ keys,
+                                                                    int passes, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t h[OS_MAX_PASSES * RADIX];
+    for (int t = threadIdx.x; t < passes * RADIX; t += VX_THREADS) h[t] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x; i < n; i += gridDim.x * VX_THREADS) {
+        int c[3];
+        unsigned long long key = g.invalid;
+        if (voxel_coords(__ldg(pts + i), inv, c))
+            key = (unsigned long long)(c[2] - g.mn[2]) * g.nxy + (unsigned long long)(c[1] - g.mn[1]) * g.nx +
+                  (unsigned long long)(c[0] - g.mn[0]);
+        keys[i] = (KeyT)key;
+        for (int p = 0; p < passes; ++p) atomicAdd(&h[p * RADIX + ((uint32_t)(key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < passes * RADIX; t += VX_THREADS)
+        if (h[t]) atomicAdd(ghist + t, h[t]);
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const KeyT* __restrict__ keys_in,
+                                                              const uint32_t* __restrict__ vals_in,
+                                                              KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                              const uint32_t* __restrict__ ghist /*[RADIX], this pass*/,
+                                                              uint32_t* status /*[tiles][RADIX], zeroed*/,
+                                                              uint32_t* ticket /*zeroed*/, uint32_t n, int shift) {
+    constexpr int ITEMS = OsItems<KeyT>::value;
+    constexpr uint32_t TILE = RS_THREADS * ITEMS;
+    __shared__ uint32_t wcnt[RS_WARPS][RADIX];
+    __shared__ uint32_t dig_excl[RADIX];  // first tile-sorted position of each digit
+    __shared__ uint32_t gbase[RADIX];     // global position of tile-sorted element e of digit d = gbase[d] + e
+    __shared__ uint32_t sw_a[33], sw_b[33];
+    __shared__ uint32_t s_tile;
+    __shared__ KeyT skey[TILE];
+    __shared__ uint32_t sval[TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int t = threadIdx.x; t < RS_WARPS * RADIX; t += RS_THREADS) (&wcnt[0][0])[t] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tbase = tile * TILE;
+
+    KeyT key[ITEMS];
+    uint32_t val[ITEMS], rank[ITEMS];
+    const uint32_t wbase = tbase + warp * (32 * ITEMS);
+#pragma unroll
+    for (int c = 0; c < ITEMS; ++c) {  // loads first: all ITEMS requests of a thread are in flight together
+        const uint32_t i = wbase + c * 32 + lane;
+        key[c] = 0;
+        if (i < n) key[c] = keys_in[i];
+    }
+#pragma unroll
+    for (int c = 0; c < ITEMS; ++c) {  // stable rank inside the warp's slice, as in radix_scatter_kernel
+        const uint32_t i = wbase + c * 32 + lane;
+        const bool live = i < n;
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        rank[c] = 0;
+        if (live) {
+            const uint32_t digit = (uint32_t)(key[c] >> shift) & (RADIX - 1);
+            const unsigned peers = __match_any_sync(act, digit);
+            const uint32_t before = __popc(peers & ((1u << lane) - 1));
+            const uint32_t prev = wcnt[warp][digit];
+            __syncwarp(act);
+            if (before == 0) wcnt[warp][digit] = prev + __popc(peers);
+            __syncwarp(act);
+            rank[c] = prev + before;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < ITEMS; ++c) {  // the payload is fetched while the look-back below waits
+        const uint32_t i = wbase + c * 32 + lane;
+        val[c] = i;
+        if (vals_in && i < n) val[c] = vals_in[i];
+    }
+    {
+        const int d = threadIdx.x;  // RS_THREADS == RADIX: one digit per thread
+        uint32_t count = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t t = wcnt[w][d];
+            wcnt[w][d] = count;
+            count += t;
+        }
+        volatile uint32_t* my = status + (size_t)tile * RADIX + d;
+        *my = (tile == 0 ? OS_INCL : OS_LOCAL) | count;
+        const uint32_t excl = block_exclusive_scan(count, sw_a, nullptr);
+        const uint32_t gstart = block_exclusive_scan(ghist[d], sw_b, nullptr);
+        uint32_t prev = 0;
+        if (tile > 0) {
+            // walk back over the predecessors' entries, OS_LOOK of them in flight at a time (the walk is a
+            // chain of L2 round trips: when every tile of a one-wave launch publishes at once it is
+            // ~sqrt(2 tiles) steps long); entries are consumed strictly in order, an unpublished one
+            // (flag 0: that tile runs, tickets are ordered) restarts the batch at its position
+            constexpr int OS_LOOK = 8;
+            int p = (int)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t v[OS_LOOK];
+#pragma unroll
+                for (int u = 0; u < OS_LOOK; ++u)
+                    v[u] = *(volatile const uint32_t*)(status + (size_t)max(p - u, 0) * RADIX + d);
+#pragma unroll
+                for (int u = 0; u < OS_LOOK; ++u) {
+                    if (done || (v[u] >> 30) == 0) break;
+                    prev += v[u] & OS_VALUE;
+                    done = (v[u] & OS_INCL) != 0;
+                    --p;
+                }
+            }
+            *my = OS_INCL | (prev + count);
+        }
+        dig_excl[d] = excl;
+        gbase[d] = gstart + prev - excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < ITEMS; ++c) {
+        const uint32_t i = wbase + c * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (uint32_t)(key[c] >> shift) & (RADIX - 1);
+            const uint32_t pos = dig_excl[digit] + wcnt[warp][digit] + rank[c];
+            skey[pos] = key[c];
+            sval[pos] = val[c];
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = min(TILE, n - tbase);
+    for (uint32_t e = threadIdx.x; e < cnt; e += RS_THREADS) {  // digit runs leave as contiguous stores
+        const KeyT k = skey[e];
+        const uint32_t dst = gbase[(uint32_t)(k >> shift) & (RADIX - 1)] + e;
+        keys_out[dst] = k;
+        vals_out[dst] = sval[e];
+    }
+}
+
 // ---- per-voxel mean
 // optional per-point attributes aggregated with the points (voxel_downsampling.hpp:220-288): mean
 // RGBA, median intensity (:82-98), mean timestamp offset — all over the voxel's points in the same
@@ -256,107 +409,224 @@ __device__ float run_select(const float* __restrict__ v, const uint32_t* __restr
     return key_float(prefix);
 }
 
-// points into sorted (key, index) order: every thread one 16-byte gather, coalesced store — the
-// per-voxel sums then read contiguous runs instead of one random line per addend
-__global__ void __launch_bounds__(VX_THREADS) gather_points_kernel(const float4* __restrict__ pts,
-                                                                   const uint32_t* __restrict__ svals, uint32_t n_valid,
-                                                                   float4* __restrict__ sorted) {
-    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
-    if (i < n_valid) sorted[i] = __ldg(pts + __ldg(svals + i));
+// ---- per-voxel mean + stream compaction in one kernel.
+// A tile of the sorted (key, index) list is staged in shared memory — keys and indices with
+// coalesced loads, the points gathered through the indices — and the heads of the voxel runs are
+// compacted so that CONSECUTIVE threads walk consecutive runs (one thread per element left ~4 of
+// 32 lanes busy and made the kernel issue-bound).  The sum over a run stays strictly sequential in
+// (key, index) order; a run that leaves the tile continues in global memory.  Kept voxels are
+// counted per tile, the tile's output offset comes from a decoupled look-back over the tiles'
+// counts (tiles taken by ticket), and the means go straight to their final, ascending-key place.
+constexpr int VR_THREADS = 256;
+constexpr unsigned long long LB_LOCAL = 1ull << 62, LB_INCL = 1ull << 63, LB_VALUE = LB_LOCAL - 1ull;
+
+// exclusive prefix of `count` over the tiles before `tile`; called by all 32 lanes of one warp
+__device__ __forceinline__ unsigned long long warp_lookback(volatile unsigned long long* status, uint32_t tile,
+                                                            unsigned long long count, int lane) {
+    if (lane == 0) status[tile] = (tile == 0 ? LB_INCL : LB_LOCAL) | count;
+    unsigned long long prev = 0;
+    if (tile > 0) {
+        long long p = (long long)tile - 1;
+        for (;;) {  // 32 predecessors per round trip
+            const long long idx = p - lane;
+            unsigned long long v = LB_INCL;  // before the first tile: an inclusive zero
+            if (idx >= 0) v = status[idx];
+            const unsigned incl = __ballot_sync(0xffffffffu, (v & LB_INCL) != 0);
+            const unsigned ready = __ballot_sync(0xffffffffu, (v >> 62) != 0);
+            const int f = incl ? __ffs(incl) - 1 : 32;       // nearest inclusive entry
+            const int c = ~ready ? __ffs(~ready) - 1 : 32;   // entries published without a gap
+            if (!(f < 32 ? c > f : c == 32)) continue;       // a needed tile has not published yet (it runs)
+            unsigned long long x = lane <= min(f, 31) ? (v & LB_VALUE) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            prev += x;
+            if (f < 32) break;
+            p -= 32;
+        }
+        if (lane == 0) status[tile] = LB_INCL | (prev + count);
+    }
+    return prev;
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const float4* __restrict__ pts,
-                                                                const KeyT* __restrict__ skeys,
-                                                                const uint32_t* __restrict__ svals, uint32_t n_valid,
-                                                                float min_count, uint32_t* __restrict__ flags,
-                                                                float4* __restrict__ means, VoxAttrs at) {
-    // the block's tile of (key, point) is staged in shared memory with coalesced loads; the thread at
-    // the head of a voxel run then walks the run out of shared memory (a run that leaves the tile
-    // continues in global memory).  The sum stays strictly sequential in (key, index) order.
-    __shared__ KeyT sk[VX_THREADS];
-    __shared__ float4 sp[VX_THREADS];
-    const uint32_t base = blockIdx.x * VX_THREADS;
-    const uint32_t i = base + threadIdx.x;
-    const bool live = i < n_valid;
-    KeyT key = 0;
-    if (live) {
-        key = skeys[i];
-        sk[threadIdx.x] = key;
-        sp[threadIdx.x] = __ldg(pts + i);  // `pts` is the gathered (sorted-order) copy
+struct VrTile {
+    static constexpr int value = sizeof(KeyT) == 4 ? 1024 : 512;
+};
+constexpr int VR_HALO = 256;  // elements staged past the tile so that its last run rarely leaves shared memory
+
+// one run: strictly sequential fp32 sum over [l, ...) while the key matches — voxel_downsampling.hpp:193-201.
+// Returns the global end of the run; sum.w is the divisor of every mean of this voxel.
+template <typename KeyT>
+__device__ __forceinline__ uint32_t walk_run(const KeyT* sk, const float4* sp, uint32_t l, uint32_t staged, uint32_t base,
+                                             const float4* __restrict__ pts, const KeyT* __restrict__ skeys,
+                                             const uint32_t* __restrict__ svals, uint32_t n_valid, float4& sum) {
+    const KeyT key = sk[l];
+    float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+    for (; l < staged; ++l) {
+        if (sk[l] != key) break;
+        const float4 p = sp[l];
+        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
+    }
+    // a run longer than the halo goes on in global memory: 8 independent loads in flight per step,
+    // the adds stay in (key, index) order
+    uint32_t j = base + l;
+    bool open = (l == staged);
+    while (open && j < n_valid) {
+        KeyT kb[8];
+        float4 pb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t jj = min(j + u, n_valid - 1);
+            kb[u] = skeys[jj];
+            pb[u] = __ldg(pts + svals[jj]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (open && j < n_valid && kb[u] == key) {
+                sx = __fadd_rn(sx, pb[u].x); sy = __fadd_rn(sy, pb[u].y); sz = __fadd_rn(sz, pb[u].z);
+                sw = __fadd_rn(sw, pb[u].w);
+                ++j;
+            } else {
+                open = false;
+            }
+        }
+    }
+    sum = make_float4(sx, sy, sz, sw);
+    return j;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* __restrict__ pts,
+                                                                  const KeyT* __restrict__ skeys,
+                                                                  const uint32_t* __restrict__ svals, uint32_t n_valid,
+                                                                  float min_count, unsigned long long* status,
+                                                                  uint32_t* ticket, float4* __restrict__ out,
+                                                                  uint32_t* __restrict__ total_out, VoxAttrs at) {
+    constexpr int TILE = VrTile<KeyT>::value;
+    constexpr int RPT = TILE / VR_THREADS;
+    constexpr int WARPS = VR_THREADS / 32;
+    __shared__ KeyT sk[TILE + VR_HALO];
+    __shared__ float4 sp[TILE + VR_HALO];  // the points; a finished run leaves its mean at its head
+    __shared__ uint16_t heads[TILE];       // tile-local start of run r
+    __shared__ uint16_t ranks[TILE];       // rank of run r among the tile's kept runs
+    __shared__ uint8_t keepf[TILE];
+    __shared__ uint32_t sw[33];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_off;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * (uint32_t)TILE;
+    const uint32_t cnt = min((uint32_t)TILE, n_valid - base);                 // elements owned by the tile
+    const uint32_t staged = min((uint32_t)(TILE + VR_HALO), n_valid - base);  // elements in shared memory
+    for (uint32_t l = t; l < staged; l += VR_THREADS) {
+        sk[l] = skeys[base + l];
+        sp[l] = __ldg(pts + svals[base + l]);
     }
     __syncthreads();
-    if (!live) return;
-    uint32_t flag = 0;
-    const bool head = i == 0 || (threadIdx.x > 0 ? sk[threadIdx.x - 1] : skeys[i - 1]) != key;
-    if (head) {
-        // PointType point_sum = Zero; point_sum += points[idx] in sorted order — :193-201
-        float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
-        uint32_t j = i;
-        const uint32_t tile_end = min(base + VX_THREADS, n_valid);
-        for (; j < tile_end; ++j) {
-            const uint32_t l = j - base;
-            if (sk[l] != key) break;
-            const float4 p = sp[l];
-            sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
-        }
-        // a run that leaves the tile (voxels next to the sensor hold hundreds of points) continues in
-        // global memory, 8 independent loads in flight per step; the adds stay in (key, index) order
-        bool open = (j == tile_end);
-        while (open && j < n_valid) {
-            KeyT kb[8];
-            float4 pb[8];
+
+    // heads of the runs that start in this tile, in order: thread t owns elements RPT*t .. RPT*t + RPT-1
+    uint32_t hmask = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t jj = min(j + u, n_valid - 1);
-                kb[u] = skeys[jj];
-                pb[u] = __ldg(pts + jj);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (open && j < n_valid && kb[u] == key) {
-                    sx = __fadd_rn(sx, pb[u].x); sy = __fadd_rn(sy, pb[u].y); sz = __fadd_rn(sz, pb[u].z);
-                    sw = __fadd_rn(sw, pb[u].w);
-                    ++j;
-                } else {
-                    open = false;
-                }
-            }
+    for (int u = 0; u < RPT; ++u) {
+        const uint32_t l = (uint32_t)t * RPT + u;
+        if (l < cnt) {
+            const bool head = l > 0 ? sk[l - 1] != sk[l] : (base == 0 || skeys[base - 1] != sk[0]);
+            hmask |= (head ? 1u : 0u) << u;
         }
-        if (sw >= min_count) {  // :204
-            flag = 1;
-            means[i] = make_float4(__fdiv_rn(sx, sw), __fdiv_rn(sy, sw), __fdiv_rn(sz, sw), __fdiv_rn(sw, sw));
+    }
+    uint32_t n_heads;
+    uint32_t hpos = block_exclusive_scan(__popc(hmask), sw, &n_heads);
+#pragma unroll
+    for (int u = 0; u < RPT; ++u)
+        if (hmask >> u & 1u) heads[hpos++] = (uint16_t)(t * RPT + u);
+    __syncthreads();
+
+    // the runs are dealt to the warps in slices of m consecutive lanes: packed enough that the walk is
+    // not issue-bound, spread enough that every warp takes part and the longest run in a warp is short
+    const uint32_t m = min(32u, max(1u, (n_heads + WARPS - 1) / WARPS));
+    for (uint32_t r0 = 0; r0 < n_heads; r0 += WARPS * m) {
+        const uint32_t r = r0 + warp * m + lane;
+        if ((uint32_t)lane < m && r < n_heads) {
+            const uint32_t l = heads[r];
+            float4 sum;
+            walk_run<KeyT>(sk, sp, l, staged, base, pts, skeys, svals, n_valid, sum);
+            const bool kept = sum.w >= min_count;  // :204
+            keepf[r] = kept ? 1 : 0;
+            // only this run's walker ever reads the run's elements, so its head can take the result
+            if (kept)
+                sp[l] = make_float4(__fdiv_rn(sum.x, sum.w), __fdiv_rn(sum.y, sum.w), __fdiv_rn(sum.z, sum.w),
+                                    __fdiv_rn(sum.w, sum.w));
+        }
+    }
+    __syncthreads();
+    uint32_t mine = 0;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const uint32_t r = (uint32_t)t * RPT + u;
+        if (r < n_heads) mine += keepf[r];
+    }
+    uint32_t n_keep;
+    uint32_t rank = block_exclusive_scan(mine, sw, &n_keep);
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const uint32_t r = (uint32_t)t * RPT + u;
+        if (r < n_heads) {
+            ranks[r] = (uint16_t)rank;
+            rank += keepf[r];
+        }
+    }
+    if (t < 32) {
+        const unsigned long long off = warp_lookback(status, tile, n_keep, lane);
+        if (lane == 0) {
+            s_off = off;
+            if (base + cnt == n_valid) *total_out = (uint32_t)(off + n_keep);
+        }
+    }
+    __syncthreads();
+    const unsigned long long off = s_off;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const uint32_t r = (uint32_t)t * RPT + u;
+        if (r < n_heads && keepf[r]) out[off + ranks[r]] = sp[heads[r]];
+    }
+    if (at.rgb || at.intensity || at.timestamps) {
+        // optional attributes over the same runs, written at the same output position
+        for (uint32_t r = t; r < n_heads; r += VR_THREADS) {
+            if (!keepf[r]) continue;
+            const size_t o = off + ranks[r];
+            const uint32_t l = heads[r];
+            const uint32_t i = base + l;
+            uint32_t j = i + 1;  // extent and divisor again, in the same order (the head's point is gone)
+            float wsum = __ldg(pts + svals[i]).w;
+            wsum = __fadd_rn(0.f, wsum);
+            const KeyT key = sk[l];
+            while (j < n_valid && skeys[j] == key) {
+                wsum = __fadd_rn(wsum, __ldg(pts + svals[j]).w);
+                ++j;
+            }
             if (at.rgb) {
-                float r = 0.f, g = 0.f, b = 0.f, a = 0.f;
-                for (uint32_t t = i; t < j; ++t) {
-                    const float4 c = __ldg(at.rgb + svals[t]);
-                    r = __fadd_rn(r, c.x); g = __fadd_rn(g, c.y); b = __fadd_rn(b, c.z); a = __fadd_rn(a, c.w);
+                float rr = 0.f, g = 0.f, b = 0.f, a = 0.f;
+                for (uint32_t e = i; e < j; ++e) {
+                    const float4 c = __ldg(at.rgb + svals[e]);
+                    rr = __fadd_rn(rr, c.x); g = __fadd_rn(g, c.y); b = __fadd_rn(b, c.z); a = __fadd_rn(a, c.w);
                 }
-                at.rgb_mean[i] = make_float4(__fdiv_rn(r, sw), __fdiv_rn(g, sw), __fdiv_rn(b, sw), __fdiv_rn(a, sw));
+                at.rgb_mean[o] = make_float4(__fdiv_rn(rr, wsum), __fdiv_rn(g, wsum), __fdiv_rn(b, wsum), __fdiv_rn(a, wsum));
             }
             if (at.timestamps) {
                 float ts = 0.f;
-                for (uint32_t t = i; t < j; ++t) ts = __fadd_rn(ts, __ldg(at.timestamps + svals[t]));
-                at.ts_mean[i] = __fdiv_rn(ts, sw);
+                for (uint32_t e = i; e < j; ++e) ts = __fadd_rn(ts, __ldg(at.timestamps + svals[e]));
+                at.ts_mean[o] = __fdiv_rn(ts, wsum);
             }
             if (at.intensity) {
                 const uint32_t len = j - i, mid = len / 2;
                 const float up = run_select(at.intensity, svals, i, j, mid);
-                at.intensity_med[i] = (len & 1u) ? up
+                at.intensity_med[o] = (len & 1u) ? up
                                                  : __fmul_rn(0.5f, __fadd_rn(run_select(at.intensity, svals, i, j, mid - 1), up));
             }
         }
     }
-    flags[i] = flag;
-}
-
-__global__ void __launch_bounds__(VX_THREADS) compact_float_kernel(const float* __restrict__ in,
-                                                                   const uint32_t* __restrict__ flags,
-                                                                   const uint32_t* __restrict__ pos, uint32_t n,
-                                                                   float* __restrict__ out) {
-    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
-    if (i >= n) return;
-    if (flags[i]) out[pos[i]] = in[i];
 }
 
 __global__ void __launch_bounds__(VX_THREADS) compact_float4_kernel(const float4* __restrict__ in,
@@ -424,71 +694,74 @@ template <typename KeyT>
 void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
                      uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev, const VoxAttrIO& io) {
     cudaStream_t st = q->stream;
-    const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
     KeyT* keys_a = q->take<KeyT>(n);
     KeyT* keys_b = q->take<KeyT>(n);
     uint32_t* vals_a = q->take<uint32_t>(n);
     uint32_t* vals_b = q->take<uint32_t>(n);
-    uint32_t* ghist = q->take<uint32_t>((size_t)RADIX * nblocks + 64);
-    uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems((size_t)RADIX * nblocks));
-    uint32_t* flags = q->take<uint32_t>(n);
-    uint32_t* pos = q->take<uint32_t>(n);
-    uint32_t* scan_tmp2 = q->take<uint32_t>(scan_scratch_elems(n));
-    float4* means = q->take<float4>(n);
-    float4* gathered = q->take<float4>(n);
     VoxAttrs at{};
     at.rgb = io.rgb;
     at.intensity = io.intensity;
     at.timestamps = io.timestamps;
-    if (io.rgb) at.rgb_mean = q->take<float4>(n);
-    if (io.intensity) at.intensity_med = q->take<float>(n);
-    if (io.timestamps) at.ts_mean = q->take<float>(n);
 
-    voxel_key_kernel<KeyT><<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, inv, geom, keys_a);
-    SPX_LAUNCH_CHECK();
     const int passes = std::max(1, (key_bits + RADIX_BITS - 1) / RADIX_BITS);
+    const bool onesweep = n < OS_LOCAL;
+    // one zeroed block for everything the look-backs need:
+    // [digit histograms 8 x 256][sort tickets 64][sort status passes x tiles x 256][reduce ticket 2][reduce status 2 x tiles]
+    const uint32_t os_tiles = onesweep ? (uint32_t)div_up(n, RS_THREADS * OsItems<KeyT>::value) : 0u;
+    const uint32_t vr_tiles = (uint32_t)div_up(std::max(n_valid, 1u), VrTile<KeyT>::value);
+    const size_t os_words = (size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)passes * os_tiles * RADIX;
+    const size_t words = os_words + 2 + 2 * (size_t)vr_tiles;
+    uint32_t* os = q->take<uint32_t>(words);
+    uint32_t* lb_ticket = os + os_words;
+    unsigned long long* lb_status = reinterpret_cast<unsigned long long*>(os + os_words + 2);
+    SPX_CUDA(cudaMemsetAsync(os, 0, words * sizeof(uint32_t), st));
+
     KeyT* kin = keys_a;
     KeyT* kout = keys_b;
     uint32_t* vin = nullptr;  // first pass: value = position
     uint32_t* vout = vals_a;
-    for (int p = 0; p < passes; ++p) {
-        const int shift = p * RADIX_BITS;
-        radix_hist_kernel<KeyT><<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, nblocks, ghist);
+    if (onesweep) {
+        // one kernel per digit: histograms of all passes from the key kernel, look-back instead of scans
+        voxel_key_hist_kernel<KeyT><<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(
+            pts, n, inv, geom, keys_a, passes, os);
         SPX_LAUNCH_CHECK();
-        exclusive_scan_u32(st, ghist, ghist, (size_t)RADIX * nblocks, scan_tmp, nullptr);
-        radix_scatter_kernel<KeyT><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, ghist, n, shift, nblocks);
+        for (int p = 0; p < passes; ++p) {
+            onesweep_kernel<KeyT><<<os_tiles, RS_THREADS, 0, st>>>(
+                kin, vin, kout, vout, os + p * RADIX, os + OS_MAX_PASSES * RADIX + 64 + (size_t)p * os_tiles * RADIX,
+                os + OS_MAX_PASSES * RADIX + p, n, p * RADIX_BITS);
+            SPX_LAUNCH_CHECK();
+            std::swap(kin, kout);
+            vin = vout;
+            vout = (vout == vals_a) ? vals_b : vals_a;
+        }
+    } else {
+        const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
+        uint32_t* ghist = q->take<uint32_t>((size_t)RADIX * nblocks + 64);
+        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems((size_t)RADIX * nblocks));
+        voxel_key_kernel<KeyT><<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, inv, geom, keys_a);
         SPX_LAUNCH_CHECK();
-        std::swap(kin, kout);
-        vin = vout;
-        vout = (vout == vals_a) ? vals_b : vals_a;
+        for (int p = 0; p < passes; ++p) {
+            const int shift = p * RADIX_BITS;
+            radix_hist_kernel<KeyT><<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, nblocks, ghist);
+            SPX_LAUNCH_CHECK();
+            exclusive_scan_u32(st, ghist, ghist, (size_t)RADIX * nblocks, scan_tmp, nullptr);
+            radix_scatter_kernel<KeyT><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, ghist, n, shift, nblocks);
+            SPX_LAUNCH_CHECK();
+            std::swap(kin, kout);
+            vin = vout;
+            vout = (vout == vals_a) ? vals_b : vals_a;
+        }
     }
     // kin / vin now hold the sorted (key, index) pairs; dropped points (invalid key) sit at the end
     if (n_valid > 0) {
-        gather_points_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(pts, vin, n_valid, gathered);
+        at.rgb_mean = io.out_rgb;
+        at.intensity_med = io.out_intensity;
+        at.ts_mean = io.out_timestamps;
+        voxel_reduce_kernel<KeyT><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status, lb_ticket, out,
+                                                               total_dev, at);
         SPX_LAUNCH_CHECK();
-        voxel_mean_kernel<KeyT><<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(gathered, kin, vin, n_valid, min_count,
-                                                                                  flags, means, at);
-        SPX_LAUNCH_CHECK();
-    }
-    exclusive_scan_u32(st, flags, pos, n_valid, scan_tmp2, total_dev);
-    if (n_valid > 0) {
-        compact_float4_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(means, flags, pos, n_valid, out);
-        SPX_LAUNCH_CHECK();
-        if (io.rgb) {
-            compact_float4_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(at.rgb_mean, flags, pos, n_valid,
-                                                                                     io.out_rgb);
-            SPX_LAUNCH_CHECK();
-        }
-        if (io.intensity) {
-            compact_float_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(at.intensity_med, flags, pos,
-                                                                                    n_valid, io.out_intensity);
-            SPX_LAUNCH_CHECK();
-        }
-        if (io.timestamps) {
-            compact_float_kernel<<<div_up(n_valid, VX_THREADS), VX_THREADS, 0, st>>>(at.ts_mean, flags, pos, n_valid,
-                                                                                    io.out_timestamps);
-            SPX_LAUNCH_CHECK();
-        }
+    } else {
+        SPX_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), st));
     }
 }
 
@@ -517,8 +790,11 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
 
         q->arena_reset();
-        q->arena_reserve((size_t)n * (8 * 2 + 4 * 2 + 4 * 2 + 16 + 16 + 16 + 4 + 4) + ((size_t)RADIX * nblocks + 64) * 4 +
-                         (scan_scratch_elems((size_t)RADIX * nblocks) + scan_scratch_elems(n)) * 4 + 16 * 256 + 8192);
+        // two key and two index buffers, then either the look-back tables or the histogram + scan scratch
+        q->arena_reserve((size_t)n * (8 * 2 + 4 * 2) + ((size_t)RADIX * nblocks + 64) * 4 +
+                         scan_scratch_elems((size_t)RADIX * nblocks) * 4 +
+                         ((size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)OS_MAX_PASSES * (div_up(n, RS_TILE) + 1) * RADIX) * 4 +
+                         (2 + 2 * (div_up(n, 512) + 1)) * 4 + 16 * 256 + 8192);
         CoordAcc* acc = q->take<CoordAcc>(1);
         uint32_t* total_dev = q->take<uint32_t>(16);
         char* pin = static_cast<char*>(q->pinned_get(256));
