@@ -237,14 +237,24 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4
     __shared__ uint32_t h[OS_MAX_PASSES * RADIX];
     for (int t = threadIdx.x; t < passes * RADIX; t += VX_THREADS) h[t] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x; i < n; i += gridDim.x * VX_THREADS) {
-        int c[3];
-        unsigned long long key = g.invalid;
-        if (voxel_coords(__ldg(pts + i), inv, c))
-            key = (unsigned long long)(c[2] - g.mn[2]) * g.nxy + (unsigned long long)(c[1] - g.mn[1]) * g.nx +
-                  (unsigned long long)(c[0] - g.mn[0]);
-        keys[i] = (KeyT)key;
-        for (int p = 0; p < passes; ++p) atomicAdd(&h[p * RADIX + ((uint32_t)(key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+    constexpr int KH = 4;  // points per thread and step, their loads in flight together
+    for (uint32_t i0 = blockIdx.x * (VX_THREADS * KH) + threadIdx.x; i0 < n; i0 += gridDim.x * (VX_THREADS * KH)) {
+        float4 pt[KH];
+#pragma unroll
+        for (int u = 0; u < KH; ++u) pt[u] = __ldg(pts + min(i0 + u * VX_THREADS, n - 1));
+#pragma unroll
+        for (int u = 0; u < KH; ++u) {
+            const uint32_t i = i0 + u * VX_THREADS;
+            if (i >= n) break;
+            int c[3];
+            unsigned long long key = g.invalid;
+            if (voxel_coords(pt[u], inv, c))
+                key = (unsigned long long)(c[2] - g.mn[2]) * g.nxy + (unsigned long long)(c[1] - g.mn[1]) * g.nx +
+                      (unsigned long long)(c[0] - g.mn[0]);
+            keys[i] = (KeyT)key;
+            for (int p = 0; p < passes; ++p)
+                atomicAdd(&h[p * RADIX + ((uint32_t)(key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < passes * RADIX; t += VX_THREADS)
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const KeyT* __r
         val[c] = i;
         if (vals_in && i < n) val[c] = vals_in[i];
     }
+    uint32_t my_count, my_excl;
     {
         const int d = threadIdx.x;  // RS_THREADS == RADIX: one digit per thread
         uint32_t count = 0;
@@ -316,17 +327,33 @@ __global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const KeyT* __r
             wcnt[w][d] = count;
             count += t;
         }
-        volatile uint32_t* my = status + (size_t)tile * RADIX + d;
-        *my = (tile == 0 ? OS_INCL : OS_LOCAL) | count;
-        const uint32_t excl = block_exclusive_scan(count, sw_a, nullptr);
+        my_count = count;
+        *(volatile uint32_t*)(status + (size_t)tile * RADIX + d) = (tile == 0 ? OS_INCL : OS_LOCAL) | count;
+        my_excl = block_exclusive_scan(count, sw_a, nullptr);
+        dig_excl[d] = my_excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < ITEMS; ++c) {  // the tile in digit order, in shared memory
+        const uint32_t i = wbase + c * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (uint32_t)(key[c] >> shift) & (RADIX - 1);
+            const uint32_t pos = dig_excl[digit] + wcnt[warp][digit] + rank[c];
+            skey[pos] = key[c];
+            sval[pos] = val[c];
+        }
+    }
+    {
+        // look-back, now that the registers of the tile are free: thread d walks back over the
+        // predecessors' entries of digit d, OS_LOOK of them in flight per round trip (when every tile of a
+        // one-wave launch publishes at once the walk is long: it is a chain of L2 latencies).  Entries are
+        // consumed strictly in order; an unpublished one (flag 0: that tile runs, tickets are ordered)
+        // restarts the batch at its position.
+        const int d = threadIdx.x;
         const uint32_t gstart = block_exclusive_scan(ghist[d], sw_b, nullptr);
         uint32_t prev = 0;
         if (tile > 0) {
-            // walk back over the predecessors' entries, OS_LOOK of them in flight at a time (the walk is a
-            // chain of L2 round trips: when every tile of a one-wave launch publishes at once it is
-            // ~sqrt(2 tiles) steps long); entries are consumed strictly in order, an unpublished one
-            // (flag 0: that tile runs, tickets are ordered) restarts the batch at its position
-            constexpr int OS_LOOK = 8;
+            constexpr int OS_LOOK = 32;
             int p = (int)tile - 1;
             bool done = false;
             while (!done) {
@@ -342,21 +369,9 @@ __global__ void __launch_bounds__(RS_THREADS, 4) onesweep_kernel(const KeyT* __r
                     --p;
                 }
             }
-            *my = OS_INCL | (prev + count);
+            *(volatile uint32_t*)(status + (size_t)tile * RADIX + d) = OS_INCL | (prev + my_count);
         }
-        dig_excl[d] = excl;
-        gbase[d] = gstart + prev - excl;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < ITEMS; ++c) {
-        const uint32_t i = wbase + c * 32 + lane;
-        if (i < n) {
-            const uint32_t digit = (uint32_t)(key[c] >> shift) & (RADIX - 1);
-            const uint32_t pos = dig_excl[digit] + wcnt[warp][digit] + rank[c];
-            skey[pos] = key[c];
-            sval[pos] = val[c];
-        }
+        gbase[d] = gstart + prev - my_excl;
     }
     __syncthreads();
     const uint32_t cnt = min(TILE, n - tbase);
@@ -420,31 +435,63 @@ __device__ float run_select(const float* __restrict__ v, const uint32_t* __restr
 constexpr int VR_THREADS = 256;
 constexpr unsigned long long LB_LOCAL = 1ull << 62, LB_INCL = 1ull << 63, LB_VALUE = LB_LOCAL - 1ull;
 
-// exclusive prefix of `count` over the tiles before `tile`; called by all 32 lanes of one warp
-__device__ __forceinline__ unsigned long long warp_lookback(volatile unsigned long long* status, uint32_t tile,
-                                                            unsigned long long count, int lane) {
-    if (lane == 0) status[tile] = (tile == 0 ? LB_INCL : LB_LOCAL) | count;
+// Exclusive prefix of `count` over the tiles before `tile`; called by every thread of the block.
+// Each round reads the LB_WIN nearest predecessors not yet accounted for, all at once: when a whole
+// wave of tiles publishes together, hardly any of them is inclusive yet and the walk is long — with
+// one warp's 32 entries per L2 round trip it was the largest part of the kernel.
+constexpr int LB_PER = 4;
+constexpr uint32_t LB_WIN = VR_THREADS * LB_PER;
+__device__ __forceinline__ void lookback_publish(volatile unsigned long long* status, uint32_t tile,
+                                                 unsigned long long count) {
+    if (threadIdx.x == 0) status[tile] = (tile == 0 ? LB_INCL : LB_LOCAL) | count;
+}
+__device__ __forceinline__ unsigned long long block_lookback(volatile unsigned long long* status, uint32_t tile,
+                                                             unsigned long long count, uint32_t* s_min /*[2]*/,
+                                                             unsigned long long* s_sum) {
+    const uint32_t t = threadIdx.x;
+    if (tile == 0) return 0ull;
     unsigned long long prev = 0;
-    if (tile > 0) {
-        long long p = (long long)tile - 1;
-        for (;;) {  // 32 predecessors per round trip
-            const long long idx = p - lane;
-            unsigned long long v = LB_INCL;  // before the first tile: an inclusive zero
-            if (idx >= 0) v = status[idx];
-            const unsigned incl = __ballot_sync(0xffffffffu, (v & LB_INCL) != 0);
-            const unsigned ready = __ballot_sync(0xffffffffu, (v >> 62) != 0);
-            const int f = incl ? __ffs(incl) - 1 : 32;       // nearest inclusive entry
-            const int c = ~ready ? __ffs(~ready) - 1 : 32;   // entries published without a gap
-            if (!(f < 32 ? c > f : c == 32)) continue;       // a needed tile has not published yet (it runs)
-            unsigned long long x = lane <= min(f, 31) ? (v & LB_VALUE) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            prev += x;
-            if (f < 32) break;
-            p -= 32;
+    long long p = (long long)tile - 1;
+    for (;;) {
+        __syncthreads();
+        if (t == 0) {
+            s_min[0] = LB_WIN;  // nearest inclusive entry of the window
+            s_min[1] = LB_WIN;  // nearest entry not published yet
+            *s_sum = 0ull;
         }
-        if (lane == 0) status[tile] = LB_INCL | (prev + count);
+        __syncthreads();
+        unsigned long long v[LB_PER];
+#pragma unroll
+        for (int u = 0; u < LB_PER; ++u) {  // entry e of the window is tile p - e
+            const long long idx = p - (long long)(u * VR_THREADS + t);
+            v[u] = LB_INCL;  // before the first tile: an inclusive zero
+            if (idx >= 0) v[u] = status[idx];
+        }
+        uint32_t f = LB_WIN, un = LB_WIN;
+#pragma unroll
+        for (int u = LB_PER - 1; u >= 0; --u) {
+            const uint32_t e = u * VR_THREADS + t;
+            if (v[u] & LB_INCL) f = e;
+            if ((v[u] >> 62) == 0) un = e;
+        }
+        if (f < LB_WIN) atomicMin(&s_min[0], f);
+        if (un < LB_WIN) atomicMin(&s_min[1], un);
+        __syncthreads();
+        const uint32_t F = s_min[0], U = s_min[1];
+        if (U < F) continue;  // a tile the sum needs has not published yet (it runs: tickets are ordered)
+        unsigned long long x = 0;
+#pragma unroll
+        for (int u = 0; u < LB_PER; ++u)
+            if ((uint32_t)(u * VR_THREADS + t) <= F) x += v[u] & LB_VALUE;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((t & 31) == 0 && x) atomicAdd(s_sum, x);
+        __syncthreads();
+        prev += *s_sum;
+        if (F < LB_WIN) break;
+        p -= LB_WIN;
     }
+    if (t == 0) status[tile] = LB_INCL | (prev + count);
     return prev;
 }
 
@@ -462,15 +509,33 @@ __device__ __forceinline__ uint32_t walk_run(const KeyT* sk, const float4* sp, u
                                              const uint32_t* __restrict__ svals, uint32_t n_valid, float4& sum) {
     const KeyT key = sk[l];
     float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
-    for (; l < staged; ++l) {
-        if (sk[l] != key) break;
-        const float4 p = sp[l];
-        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); sw = __fadd_rn(sw, p.w);
+    // four elements per step, their shared-memory loads issued together and ahead of the key tests: one
+    // element at a time is a chain of two dependent loads, a compare and a branch (~100 cycles each)
+    bool open = true;
+    while (open && l < staged) {
+        KeyT kq[4];
+        float4 pq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t ll = min(l + u, staged - 1);
+            kq[u] = sk[ll];
+            pq[u] = sp[ll];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (open && l < staged && kq[u] == key) {
+                sx = __fadd_rn(sx, pq[u].x); sy = __fadd_rn(sy, pq[u].y); sz = __fadd_rn(sz, pq[u].z);
+                sw = __fadd_rn(sw, pq[u].w);
+                ++l;
+            } else {
+                open = false;
+            }
+        }
     }
     // a run longer than the halo goes on in global memory: 8 independent loads in flight per step,
     // the adds stay in (key, index) order
     uint32_t j = base + l;
-    bool open = (l == staged);
+    open = (l == staged);
     while (open && j < n_valid) {
         KeyT kb[8];
         float4 pb[8];
@@ -495,13 +560,22 @@ __device__ __forceinline__ uint32_t walk_run(const KeyT* sk, const float4* sp, u
     return j;
 }
 
-template <typename KeyT>
+// EARLY: the tile publishes its number of RUNS as soon as it knows them, before the walks, and every
+// run is written at its run rank.  The look-back after the walks then never waits (a tile that has
+// to wait for the slowest tile before it keeps its slot on the SM: publishing after the walks made a
+// wave of tiles last as long as its slowest one, 10 of 22 us per tile).  A run that fails the
+// min_voxel_count test cannot be compacted away in this mode: it is counted in `dropped`, and the
+// host runs the kernel again with EARLY = false (counts published after the walks, only kept runs
+// ranked).  With min_voxel_count <= 1 and w == 1 — the reference's homogeneous points — nothing is
+// ever dropped.
+template <typename KeyT, bool EARLY>
 __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* __restrict__ pts,
                                                                   const KeyT* __restrict__ skeys,
                                                                   const uint32_t* __restrict__ svals, uint32_t n_valid,
                                                                   float min_count, unsigned long long* status,
                                                                   uint32_t* ticket, float4* __restrict__ out,
-                                                                  uint32_t* __restrict__ total_out, VoxAttrs at) {
+                                                                  uint32_t* __restrict__ total_out /*[0] total, [1] dropped*/,
+                                                                  VoxAttrs at) {
     constexpr int TILE = VrTile<KeyT>::value;
     constexpr int RPT = TILE / VR_THREADS;
     constexpr int WARPS = VR_THREADS / 32;
@@ -511,8 +585,9 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* 
     __shared__ uint16_t ranks[TILE];       // rank of run r among the tile's kept runs
     __shared__ uint8_t keepf[TILE];
     __shared__ uint32_t sw[33];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_off;
+    __shared__ uint32_t s_tile, s_min[2];
+    __shared__ unsigned long long s_sum;
+    __shared__ KeyT s_prev_key;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -520,9 +595,34 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* 
     const uint32_t base = tile * (uint32_t)TILE;
     const uint32_t cnt = min((uint32_t)TILE, n_valid - base);                 // elements owned by the tile
     const uint32_t staged = min((uint32_t)(TILE + VR_HALO), n_valid - base);  // elements in shared memory
-    for (uint32_t l = t; l < staged; l += VR_THREADS) {
-        sk[l] = skeys[base + l];
-        sp[l] = __ldg(pts + svals[base + l]);
+    {
+        // index loads first, then every gather of the thread in flight together (two round trips per tile
+        // instead of two per element)
+        constexpr int SPT = (TILE + VR_HALO) / VR_THREADS;
+        uint32_t si[SPT];
+        KeyT kk[SPT];
+        float4 pp[SPT];
+        if (t == 0) s_prev_key = base > 0 ? skeys[base - 1] : (KeyT)0;
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const uint32_t l = u * VR_THREADS + t;
+            si[u] = 0;
+            kk[u] = 0;
+            if (l < staged) {
+                si[u] = svals[base + l];
+                kk[u] = skeys[base + l];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) pp[u] = __ldg(pts + si[u]);
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const uint32_t l = u * VR_THREADS + t;
+            if (l < staged) {
+                sk[l] = kk[u];
+                sp[l] = pp[u];
+            }
+        }
     }
     __syncthreads();
 
@@ -532,7 +632,7 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* 
     for (int u = 0; u < RPT; ++u) {
         const uint32_t l = (uint32_t)t * RPT + u;
         if (l < cnt) {
-            const bool head = l > 0 ? sk[l - 1] != sk[l] : (base == 0 || skeys[base - 1] != sk[0]);
+            const bool head = l > 0 ? sk[l - 1] != sk[l] : (base == 0 || s_prev_key != sk[0]);
             hmask |= (head ? 1u : 0u) << u;
         }
     }
@@ -541,6 +641,7 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* 
 #pragma unroll
     for (int u = 0; u < RPT; ++u)
         if (hmask >> u & 1u) heads[hpos++] = (uint16_t)(t * RPT + u);
+    if (EARLY) lookback_publish(status, tile, n_heads);
     __syncthreads();
 
     // the runs are dealt to the warps in slices of m consecutive lanes: packed enough that the walk is
@@ -561,31 +662,38 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* 
         }
     }
     __syncthreads();
-    uint32_t mine = 0;
+    uint32_t n_keep = n_heads;
+    if (!EARLY) {
+        uint32_t mine = 0;
 #pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-        const uint32_t r = (uint32_t)t * RPT + u;
-        if (r < n_heads) mine += keepf[r];
-    }
-    uint32_t n_keep;
-    uint32_t rank = block_exclusive_scan(mine, sw, &n_keep);
+        for (int u = 0; u < RPT; ++u) {
+            const uint32_t r = (uint32_t)t * RPT + u;
+            if (r < n_heads) mine += keepf[r];
+        }
+        uint32_t rank = block_exclusive_scan(mine, sw, &n_keep);
 #pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-        const uint32_t r = (uint32_t)t * RPT + u;
-        if (r < n_heads) {
-            ranks[r] = (uint16_t)rank;
-            rank += keepf[r];
+        for (int u = 0; u < RPT; ++u) {
+            const uint32_t r = (uint32_t)t * RPT + u;
+            if (r < n_heads) {
+                ranks[r] = (uint16_t)rank;
+                rank += keepf[r];
+            }
         }
-    }
-    if (t < 32) {
-        const unsigned long long off = warp_lookback(status, tile, n_keep, lane);
-        if (lane == 0) {
-            s_off = off;
-            if (base + cnt == n_valid) *total_out = (uint32_t)(off + n_keep);
+        lookback_publish(status, tile, n_keep);
+    } else {
+        uint32_t lost = 0;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const uint32_t r = (uint32_t)t * RPT + u;
+            if (r < n_heads) {
+                ranks[r] = (uint16_t)r;
+                lost += keepf[r] ? 0u : 1u;
+            }
         }
+        if (lost) atomicAdd(total_out + 1, lost);
     }
-    __syncthreads();
-    const unsigned long long off = s_off;
+    const unsigned long long off = block_lookback(status, tile, n_keep, s_min, &s_sum);
+    if (t == 0 && base + cnt == n_valid) *total_out = (uint32_t)(off + n_keep);
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
         const uint32_t r = (uint32_t)t * RPT + u;
@@ -692,7 +800,8 @@ struct VoxAttrIO {
 
 template <typename KeyT>
 void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
-                     uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev, const VoxAttrIO& io) {
+                     uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev, uint32_t* htotal,
+                     const VoxAttrIO& io) {
     cudaStream_t st = q->stream;
     KeyT* keys_a = q->take<KeyT>(n);
     KeyT* keys_b = q->take<KeyT>(n);
@@ -722,7 +831,7 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     uint32_t* vout = vals_a;
     if (onesweep) {
         // one kernel per digit: histograms of all passes from the key kernel, look-back instead of scans
-        voxel_key_hist_kernel<KeyT><<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(
+        voxel_key_hist_kernel<KeyT><<<std::min(div_up(n, VX_THREADS * 4), q->sm_count * 8), VX_THREADS, 0, st>>>(
             pts, n, inv, geom, keys_a, passes, os);
         SPX_LAUNCH_CHECK();
         for (int p = 0; p < passes; ++p) {
@@ -753,15 +862,33 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
         }
     }
     // kin / vin now hold the sorted (key, index) pairs; dropped points (invalid key) sit at the end
-    if (n_valid > 0) {
-        at.rgb_mean = io.out_rgb;
-        at.intensity_med = io.out_intensity;
-        at.ts_mean = io.out_timestamps;
-        voxel_reduce_kernel<KeyT><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status, lb_ticket, out,
-                                                               total_dev, at);
+    SPX_CUDA(cudaMemsetAsync(total_dev, 0, 2 * sizeof(uint32_t), st));
+    if (n_valid == 0) {
+        htotal[0] = 0;
+        return;
+    }
+    at.rgb_mean = io.out_rgb;
+    at.intensity_med = io.out_intensity;
+    at.ts_mean = io.out_timestamps;
+    const bool early = min_count <= 1.0f;
+    if (early)
+        voxel_reduce_kernel<KeyT, true><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status,
+                                                                        lb_ticket, out, total_dev, at);
+    else
+        voxel_reduce_kernel<KeyT, false><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status,
+                                                                         lb_ticket, out, total_dev, at);
+    SPX_LAUNCH_CHECK();
+    SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    q->sync();
+    if (early && htotal[1] != 0) {
+        // some voxel failed the min_voxel_count test (points with w < 1): again, ranking only the kept runs
+        SPX_CUDA(cudaMemsetAsync(lb_ticket, 0, (2 + 2 * (size_t)vr_tiles) * sizeof(uint32_t), st));
+        SPX_CUDA(cudaMemsetAsync(total_dev, 0, 2 * sizeof(uint32_t), st));
+        voxel_reduce_kernel<KeyT, false><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status,
+                                                                         lb_ticket, out, total_dev, at);
         SPX_LAUNCH_CHECK();
-    } else {
-        SPX_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), st));
+        SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        q->sync();
     }
 }
 
@@ -837,12 +964,11 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         io.out_intensity = out_intensity;
         io.out_timestamps = out_timestamps;
         if (key_bits <= 32)
-            sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, io);
+            sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, htotal, io);
         else
-            sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, io);
-        SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
-        q->sync();
-        *m_host = *htotal;
+            sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, htotal,
+                                                io);
+        *m_host = htotal[0];
     });
 }
 

@@ -97,6 +97,13 @@ def test_voxel_invalid_points_and_wide_keys(spx, q):
     assert np.array_equal(got, oracle.voxel_downsample(wide, 0.02))
     allbad = np.full((10, 4), np.nan, np.float32)
     assert spx.VoxelGrid(q, 0.5).downsampling(spx.PointCloudShared(q, allbad)).size() == 0
+    # w != 1: a voxel whose w sum stays below min_voxel_count = 1 is dropped (voxel_downsampling.hpp:204);
+    # the kernel ranks every run first and is run again ranking only the kept ones
+    light = pts[np.isfinite(pts).all(axis=1)][:30000].copy()
+    light[::3, 3] = np.float32(0.25)
+    got = spx.VoxelGrid(q, 0.25).downsampling(spx.PointCloudShared(q, light)).points_host()
+    want = oracle.voxel_downsample(light, 0.25)
+    assert 0 < len(want) < 30000 and np.array_equal(got, want)
 
 
 def test_voxel_idempotent_and_sorted_large(spx, q):
