@@ -131,6 +131,7 @@ class PairPipeline:
         self.raw_tgt.adopt_points(spx.DeviceArray(q, (n_tgt_raw, 4), np.float32), n_tgt_raw)
         self.nn_s, self.nn_t = spx.KNNResult(), spx.KNNResult()
         self.pool = ThreadPoolExecutor(max_workers=1)
+        self.src_done = spx.Event()
         self.last = None
         # end-to-end (streaming) mode: a copy queue and two sets of raw buffers, so that the upload of
         # scan pair s+1 overlaps the processing of pair s (what a LiDAR front end does with its frames)
@@ -148,7 +149,7 @@ class PairPipeline:
         self.q2.wait()
         self.q.wait()
 
-    def _chain(self, q, vg, raw, nn, host=None, after=None):
+    def _chain(self, q, vg, raw, nn, host=None, after=None, done=None):
         spx = self.spx
         if after is not None:
             q.wait_event(after)  # nothing of this chain starts before the step's start event
@@ -158,6 +159,8 @@ class PairPipeline:
         tree = spx.KDTree.build(q, cloud)
         tree.knn_search_async(cloud, K_COV, nn)
         spx.covariance.estimate(nn, cloud)
+        if done is not None:
+            done.record(q)  # the other queue waits for this on the device, the host does not
         return cloud, tree
 
     def stream_upload(self, slot, src_host, tgt_host):
@@ -170,20 +173,23 @@ class PairPipeline:
     def run_streamed(self, slot):
         """process the pair in buffer set `slot` once its upload has landed"""
         rs, rt, ev = self.stream_raw[slot]
-        fut = self.pool.submit(self._chain, self.q2, self.vg2, rs, self.nn_s, None, ev)
+        fut = self.pool.submit(self._chain, self.q2, self.vg2, rs, self.nn_s, None, ev, self.src_done)
         tgt, tree_t = self._chain(self.q, self.vg, rt, self.nn_t, None, ev)
         src, tree_s = fut.result()
-        self.q2.wait()
+        self.q.wait_event(self.src_done)
         res = self.reg.align(src, tgt, tree_t)
         self.last = (src, tgt, tree_t, res)
         tree_s.close()
         return res
 
     def run(self, start_event=None, src_host=None, tgt_host=None):
-        fut = self.pool.submit(self._chain, self.q2, self.vg2, self.raw_src, self.nn_s, src_host, start_event)
+        fut = self.pool.submit(self._chain, self.q2, self.vg2, self.raw_src, self.nn_s, src_host, start_event,
+                               self.src_done)
         tgt, tree_t = self._chain(self.q, self.vg, self.raw_tgt, self.nn_t, tgt_host)
         src, tree_s = fut.result()
-        self.q2.wait()  # the source chain's last kernels (covariances) must be done before the align reads them
+        # the source chain's last kernels (covariances) must be done before the align reads them: a
+        # device-side wait, so that the align's set-up launches queue up behind the running chains
+        self.q.wait_event(self.src_done)
         res = self.reg.align(src, tgt, tree_t)  # synchronises (result comes back to the host)
         self.last = (src, tgt, tree_t, res)
         tree_s.close()

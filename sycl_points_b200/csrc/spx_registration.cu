@@ -826,25 +826,52 @@ __global__ void gn_update_kernel(RegState* st, const double* sums, float lambda,
     gn_update(st, sums, lambda, crit_rot, crit_trans, iter_index, trace);
 }
 
-// optimiser state at the start of an align, written on the device (a small H2D copy would queue
-// behind another queue's bulk upload on the copy engine)
-__global__ void state_init_kernel(RegState* st, Xform T) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    RegState s;
-    memset(&s, 0, sizeof(s));
-    const float4 r[4] = {T.r0, T.r1, T.r2, T.r3};
-    for (int i = 0; i < 4; ++i) {
-        s.T[i][0] = r[i].x; s.T[i][1] = r[i].y; s.T[i][2] = r[i].z; s.T[i][3] = r[i].w;
+// Everything an align needs before its first iteration, in ONE launch: the pose-independent
+// per-point matrices of both clouds (16-float reference covariance -> plane-regularised 6 floats, or
+// the inverse for point-to-distribution), the optimiser state, and the zeroed work-list counters and
+// ticket.  Written on the device — a small H2D copy would queue behind another queue's bulk upload on
+// the copy engine, and five separate stream operations cost ~20 us of launch gaps per align.
+struct PrepArgs {
+    const float* src_cov16;
+    uint32_t ns;  // 0: the source needs no matrices
+    float4* src_c0;
+    float2* src_c1;
+    const float* tgt_cov16;
+    uint32_t nt;  // 0: the target needs no matrices
+    float4* tgt_c0;
+    float2* tgt_c1;
+    int invert_tgt;
+    RegState* state;
+    Xform T;
+    unsigned int* wl_counters;
+    unsigned int* ticket;
+};
+__global__ void __launch_bounds__(128) align_prepare_kernel(PrepArgs p) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        RegState s;
+        memset(&s, 0, sizeof(s));
+        const float4 r[4] = {p.T.r0, p.T.r1, p.T.r2, p.T.r3};
+        for (int i = 0; i < 4; ++i) {
+            s.T[i][0] = r[i].x; s.T[i][1] = r[i].y; s.T[i][2] = r[i].z; s.T[i][3] = r[i].w;
+        }
+        s.error = FLT_MAX;
+        *p.state = s;
+        for (int i = 0; i < 4; ++i) p.wl_counters[i] = 0u;
+        *p.ticket = 0u;
     }
-    s.error = FLT_MAX;
-    *st = s;
-}
-
-// one pass per cloud: 16-float reference covariance -> plane-regularised 6 floats
-__global__ void __launch_bounds__(128) prepare_cov_kernel(const float* __restrict__ cov16, uint32_t n,
-                                                          float4* __restrict__ c0, float2* __restrict__ c1, int invert) {
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= n) return;
+    uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    const float* cov16 = p.src_cov16;
+    float4* c0 = p.src_c0;
+    float2* c1 = p.src_c1;
+    bool invert = false;
+    if (i >= p.ns) {
+        i -= p.ns;
+        if (i >= p.nt) return;
+        cov16 = p.tgt_cov16;
+        c0 = p.tgt_c0;
+        c1 = p.tgt_c1;
+        invert = p.invert_tgt != 0;
+    }
     const Sym3 raw = cov16 ? load_cov16(cov16 + (size_t)i * 16) : identity_sym();
     const Sym3 r = invert ? sym_inverse(raw) : plane_regularize(raw);  // invert: point-to-distribution
     c0[i] = make_float4(r.xx, r.xy, r.xz, r.yy);
@@ -1062,6 +1089,8 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     }
     LinArgs& a = c.a;
     std::memset(&a, 0, sizeof(a));
+    PrepArgs prep;
+    std::memset(&prep, 0, sizeof(prep));
     a.src_pts = reinterpret_cast<const float4*>(src_points);
     a.ns = (uint32_t)ns;
     a.tgt_pts = reinterpret_cast<const float4*>(tgt_points);
@@ -1078,14 +1107,15 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
         cap = r->tgt_cap;
         ensure(r->tgt_c0, cap, nt, st);
         ensure(r->tgt_c1, r->tgt_cap, nt, st);
-        if (ns && gicp) {
-            prepare_cov_kernel<<<div_up(ns, 128), 128, 0, st>>>(src_covs, (uint32_t)ns, r->src_c0, r->src_c1, 0);
-            SPX_LAUNCH_CHECK();
-        }
-        if (nt) {
-            prepare_cov_kernel<<<div_up(nt, 128), 128, 0, st>>>(tgt_covs, (uint32_t)nt, r->tgt_c0, r->tgt_c1, gicp ? 0 : 1);
-            SPX_LAUNCH_CHECK();
-        }
+        prep.src_cov16 = src_covs;
+        prep.ns = gicp ? (uint32_t)ns : 0u;
+        prep.src_c0 = r->src_c0;
+        prep.src_c1 = r->src_c1;
+        prep.tgt_cov16 = tgt_covs;
+        prep.nt = (uint32_t)nt;
+        prep.tgt_c0 = r->tgt_c0;
+        prep.tgt_c1 = r->tgt_c1;
+        prep.invert_tgt = gicp ? 0 : 1;
         if (gicp) {
             a.src_c0 = r->src_c0;
             a.src_c1 = r->src_c1;
@@ -1109,7 +1139,6 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     a.warm_start = 0;
     a.worklist = r->worklist;
     a.wl_counters = r->wl_counters;
-    SPX_CUDA(cudaMemsetAsync(r->wl_counters, 0, 4 * sizeof(unsigned int), st));
     a.grid = index->levels;
     a.state = r->state;
     a.use_state = 1;
@@ -1130,10 +1159,13 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
 
     {
         const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-        state_init_kernel<<<1, 32, 0, st>>>(r->state, xform_from_colmajor(T_init_host ? T_init_host : I16));
+        prep.state = r->state;
+        prep.T = xform_from_colmajor(T_init_host ? T_init_host : I16);
+        prep.wl_counters = r->wl_counters;
+        prep.ticket = r->ticket;
+        align_prepare_kernel<<<std::max<unsigned>(1u, (unsigned)div_up((size_t)prep.ns + prep.nt, 128)), 128, 0, st>>>(prep);
         SPX_LAUNCH_CHECK();
     }
-    SPX_CUDA(cudaMemsetAsync(r->ticket, 0, sizeof(unsigned int), st));
     return c;
 }
 

@@ -41,7 +41,7 @@ for rep in range(6):
     tgt, tt = chain(q, pipe.vg, pipe.raw_tgt, pipe.nn_t, start, mt, ht)
     src, ts = fut.result()
     t_join = time.perf_counter()
-    pipe.q2.wait()
+    q.wait_event(ms[-1][1])  # device-side join, as bench.py does
     a0 = spx.Event().record(q)
     res = pipe.reg.align(src, tgt, tt)
     a1 = spx.Event().record(q)
