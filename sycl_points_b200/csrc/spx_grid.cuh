@@ -354,16 +354,18 @@ __device__ __forceinline__ bool grid_first_pass(const GridView& g, float qx, flo
 template <typename Best, typename Stats = NoStats>
 __device__ __forceinline__ bool grid_search_levels(const GridLevels& g, float qx, float qy, float qz, Best& best,
                                                    float max_radius, Stats* stats = nullptr,
-                                                   int level_limit = GRID_MAX_LEVELS) {
+                                                   int level_limit = GRID_MAX_LEVELS, bool first_pass_done = false,
+                                                   int rings0 = GRID_LEVEL_RINGS) {
     if (stats) stats->level(0);
-    if (grid_first_pass(g.lv[0], qx, qy, qz, best, max_radius, stats)) return true;
+    // first_pass_done: `best` already holds the outcome of an unsuccessful first pass (another kernel ran it)
+    if (!first_pass_done && grid_first_pass(g.lv[0], qx, qy, qz, best, max_radius, stats)) return true;
     const int nl = min(g.n_levels, level_limit);
     for (int l = 0; l < nl; ++l) {
         const bool last = (l == g.n_levels - 1);
         if (l == 1) best_set_dedup(best, true);
         if (stats) stats->level(l);
-        if (grid_search(g.lv[l], qx, qy, qz, best, max_radius, l == 0 ? 2 : 1, last ? (1 << 20) : GRID_LEVEL_RINGS,
-                        stats))
+        if (grid_search(g.lv[l], qx, qy, qz, best, max_radius, l == 0 ? 2 : 1,
+                        last ? (1 << 20) : (l == 0 ? rings0 : GRID_LEVEL_RINGS), stats))
             return true;
     }
     return false;

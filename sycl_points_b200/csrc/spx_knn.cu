@@ -543,16 +543,17 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_first_kernel(const 
                                                                            uint32_t nq, int k, Xform T, int has_T,
                                                                            int32_t* __restrict__ idx, float* __restrict__ dist,
                                                                            uint32_t* __restrict__ worklist,
-                                                                           unsigned int* __restrict__ wl_count) {
+                                                                           unsigned int* __restrict__ wl_count,
+                                                                           unsigned long long* __restrict__ carry) {
     const uint32_t qi = blockIdx.x * GRID_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const float INF = __int_as_float(0x7f800000);
     bool pending = false;
+    BestR<K> best;
+    best.init(k);
     if (qi < nq) {
         float4 q = __ldg(queries + qi);
         if (has_T) q = transform_point(T, q);
-        BestR<K> best;
-        best.init(k);
         if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && g.lv[0].n > 0)
             pending = !grid_first_pass(g.lv[0], q.x, q.y, q.z, best, INF);
         if (!pending) {
@@ -571,19 +572,27 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_first_kernel(const 
         unsigned int slot = 0;
         if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
         slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
-        if (pending) worklist[slot + __popc(m & ((1u << lane) - 1u))] = qi;
+        if (pending) {
+            // the list kernel resumes from this state instead of repeating the first pass
+            const unsigned int w = slot + __popc(m & ((1u << lane) - 1u));
+            worklist[w] = qi;
+#pragma unroll
+            for (int j = 0; j < K; ++j) carry[(size_t)j * nq + w] = best.key[j];
+        }
     }
 }
 
 template <int K>
 __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_list_kernel(const GridLevels g, const float4* __restrict__ queries,
-                                                                          int k, Xform T, int has_T,
+                                                                          uint32_t nq, int k, Xform T, int has_T,
                                                                           int32_t* __restrict__ idx, float* __restrict__ dist,
                                                                           const uint32_t* __restrict__ worklist,
                                                                           const unsigned int* __restrict__ wl_count,
                                                                           unsigned int* __restrict__ wl_cursor,
                                                                           uint32_t* __restrict__ far_list,
-                                                                          unsigned int* __restrict__ far_count) {
+                                                                          unsigned int* __restrict__ far_count,
+                                                                          const unsigned long long* __restrict__ carry,
+                                                                          int list_levels, int list_rings0) {
     const int lane = threadIdx.x & 31;
     const float INF = __int_as_float(0x7f800000);
     const unsigned int n_slow = *wl_count;
@@ -593,14 +602,18 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_list_kernel(const G
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_slow) break;
         if (base + lane < n_slow) {
-            const uint32_t qi = worklist[base + lane];
+            const uint32_t w = base + lane;
+            const uint32_t qi = worklist[w];
             float4 q = __ldg(queries + qi);
             if (has_T) q = transform_point(T, q);
             BestR<K> best;
-            best.init(k);
-            // the two finest levels per lane; a query still open after that has its k-th neighbour
-            // several coarse cells away and goes to the warp-cooperative kernel
-            if (grid_search_levels(g, q.x, q.y, q.z, best, INF, (NoStats*)nullptr, 2)) {
+            best.dedup = false;
+#pragma unroll
+            for (int j = 0; j < K; ++j) best.key[j] = carry[(size_t)j * nq + w];
+            // per lane, from where the earlier stages stopped, up to level `list_levels`; a query still
+            // open after that has its k-th neighbour several coarse cells away and goes to the
+            // warp-cooperative kernel
+            if (grid_search_levels(g, q.x, q.y, q.z, best, INF, (NoStats*)nullptr, list_levels, true, list_rings0)) {
                 int32_t* irow = idx + (size_t)qi * k;
                 float* drow = dist + (size_t)qi * k;
 #pragma unroll
@@ -640,17 +653,21 @@ template <int K>
 void launch_knn_reg(spx_index_t index, spx_queue_t q, const float4* qs, uint32_t nq, int k, const Xform& T, int has_T,
                     int32_t* idx, float* dist) {
     q->arena_reset();
-    q->arena_reserve((size_t)nq * 8 + 4096);
+    q->arena_reserve((size_t)nq * (8 + 8 * K) + 8192);
     uint32_t* worklist = q->take<uint32_t>(nq);
     uint32_t* far_list = q->take<uint32_t>(nq);
+    unsigned long long* carry = q->take<unsigned long long>((size_t)nq * K);  // [K][nq]: first-pass lists of the pending
+    int list_levels = 2, list_rings0 = GRID_LEVEL_RINGS;  // tuning aids
+    if (const char* e = std::getenv("SPX_KNN_LIST_LEVELS")) list_levels = std::atoi(e);
+    if (const char* e = std::getenv("SPX_KNN_LIST_RINGS0")) list_rings0 = std::atoi(e);
     unsigned int* counters = q->take<unsigned int>(16);  // {list count, list cursor, far count, far cursor}
     SPX_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), q->stream));
     grid_knn_reg_first_kernel<K><<<div_up(nq, GRID_THREADS), GRID_THREADS, 0, q->stream>>>(index->levels, qs, nq, k, T, has_T, idx,
-                                                                                         dist, worklist, counters);
+                                                                                         dist, worklist, counters, carry);
     SPX_LAUNCH_CHECK();
-    grid_knn_reg_list_kernel<K><<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(index->levels, qs, k, T, has_T, idx, dist,
-                                                                                worklist, counters, counters + 1, far_list,
-                                                                                counters + 2);
+    grid_knn_reg_list_kernel<K><<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(
+        index->levels, qs, nq, k, T, has_T, idx, dist, worklist, counters, counters + 1, far_list, counters + 2, carry,
+        list_levels, list_rings0);
     SPX_LAUNCH_CHECK();
     grid_knn_far_kernel<K><<<q->sm_count, GRID_THREADS, 0, q->stream>>>(index->levels, qs, k, T, has_T, idx, dist, far_list,
                                                                        counters + 2, counters + 3);
