@@ -429,51 +429,80 @@ static __device__ __noinline__ void knn_coop_search(const GridLevels& gl, float 
         const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
         const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
         const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
-        const int r_max = last ? (1 << 20) : GRID_LEVEL_RINGS;
+        // more shells per level than the per-lane searches take: a shell here costs one or two round trips
+        // when it is empty, while the next level's first block scans every point of 27 cells 4x the size
+        const int r_max = last ? (1 << 20) : 4;
         for (int r = 1;; ++r) {
             const bool merged = (r == 1);
             const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
             const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
-            for (int zz = z0; zz <= z1; ++zz)
-                for (int yy = y0; yy <= y1; ++yy) {
+            // 32 rows (z, y) of the shell at a time: every lane prunes ONE row and looks up its cell
+            // range(s), all in one round trip; the warp then strides the candidates of the rows that
+            // hold any.  Around an isolated query whole shells are empty: one trip each instead of one
+            // per row (25 rows x 2 shells x every level was most of this kernel's time).
+            const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+            for (int row0 = 0; row0 < nrows; row0 += 32) {
+                uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+                const int ri = row0 + lane;
+                if (ri < nrows) {
+                    const int zz = z0 + ri / ny, yy = y0 + ri % ny;
                     const bool edge = merged || (zz - cz == r) || (cz - zz == r) || (yy - cy == r) || (cy - yy == r);
                     int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
+                    bool ok = true;
                     if (kth_d < 1.0e30f) {
                         const float gz = axis_gap(qz, g.oz, g.cell, zz);
                         const float gy = axis_gap(qy, g.oy, g.cell, yy);
                         const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
                         const float gyz2 = __fmul_rn(gyz, gyz);
-                        if (gyz2 > kth_d) continue;
-                        const float w = sqrtf(kth_d - gyz2) + margin;
-                        xa = max(xa, grid_coord(qx - w, g.ox, g.inv, g.dx));
-                        xb = min(xb, grid_coord(qx + w, g.ox, g.inv, g.dx));
-                        if (xa > xb) continue;
-                    }
-                    const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
-                    // up to two ranges: the whole row on the shell's faces, its two end cells otherwise
-                    uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
-                    if (edge) {
-                        s0 = __ldg(g.start + row + xa);
-                        e0 = __ldg(g.start + row + xb + 1);
-                    } else {
-                        if (cx - r >= xa) {
-                            s0 = __ldg(g.start + row + (cx - r));
-                            e0 = __ldg(g.start + row + (cx - r) + 1);
-                        }
-                        if (cx + r <= xb) {
-                            s1 = __ldg(g.start + row + (cx + r));
-                            e1 = __ldg(g.start + row + (cx + r) + 1);
+                        ok = !(gyz2 > kth_d);
+                        if (ok) {
+                            const float w = sqrtf(kth_d - gyz2) + margin;
+                            xa = max(xa, grid_coord(qx - w, g.ox, g.inv, g.dx));
+                            xb = min(xb, grid_coord(qx + w, g.ox, g.inv, g.dx));
+                            ok = xa <= xb;
                         }
                     }
-                    for (uint32_t j = s0 + lane; j < e0; j += 32) {
-                        const float4 p = __ldg(g.pts + j);
-                        mine.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), j);
+                    if (ok) {
+                        const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
+                        // up to two ranges: the whole row on the shell's faces, its two end cells otherwise
+                        if (edge) {
+                            s0 = __ldg(g.start + row + xa);
+                            e0 = __ldg(g.start + row + xb + 1);
+                        } else {
+                            if (cx - r >= xa) {
+                                s0 = __ldg(g.start + row + (cx - r));
+                                e0 = __ldg(g.start + row + (cx - r) + 1);
+                            }
+                            if (cx + r <= xb) {
+                                s1 = __ldg(g.start + row + (cx + r));
+                                e1 = __ldg(g.start + row + (cx + r) + 1);
+                            }
+                        }
                     }
-                    for (uint32_t j = s1 + lane; j < e1; j += 32) {
+                }
+                unsigned m = __ballot_sync(0xffffffffu, e0 > s0 || e1 > s1);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t a0 = __shfl_sync(0xffffffffu, s0, src), b0 = __shfl_sync(0xffffffffu, e0, src);
+                    const uint32_t a1 = __shfl_sync(0xffffffffu, s1, src), b1 = __shfl_sync(0xffffffffu, e1, src);
+                    // 8 loads in flight per lane: on a coarse level a row holds thousands of points
+                    for (uint32_t j = a0 + lane; j < b0; j += 32 * 8) {
+                        float4 p[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (j + 32 * u < b0) p[u] = __ldg(g.pts + j + 32 * u);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (j + 32 * u < b0)
+                                mine.offer(dist_sq(qx, qy, qz, p[u].x, p[u].y, p[u].z), __float_as_int(p[u].w), j + 32 * u);
+                    }
+                    for (uint32_t j = a1 + lane; j < b1; j += 32) {
                         const float4 p = __ldg(g.pts + j);
                         mine.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), j);
                     }
                 }
+            }
             const unsigned long long kth = warp_merge_topk<K>(mine, k, nullptr);
             kth_d = __uint_as_float((uint32_t)((kth - 1ull) >> 32));
             const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, r, g.dx),
