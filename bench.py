@@ -238,7 +238,30 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_iter": 1e3 * dt / max(iters, 1),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded later write there too (NCCL prints its
+    version banner on fd 1), so fd 1 is pointed at stderr for the whole run and the line goes out
+    through a saved duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -249,6 +272,7 @@ def main():
     ap.add_argument("--impl", default="spx", choices=["spx", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
     if args.impl == "reference":
@@ -419,7 +443,7 @@ def main():
                                 "sample": f"{n_cpu} whole pair(s), full pipeline, oracle port on {cores} threads",
                                 "ms_per_pair": 1e3 * dt / n_cpu, "icp_iterations": r['iterations'] + 1}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
