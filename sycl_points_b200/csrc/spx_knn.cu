@@ -152,24 +152,41 @@ struct BBoxAcc {
     int mn[3];
     int mx[3];
     uint32_t finite;
-    uint32_t pad;
+    uint32_t done_blocks;  // ticket: the last block of bbox_kernel derives the occupancy plan
 };
+struct OccPlan {
+    float lo[3];
+    float c0;        // volume-heuristic cell edge the candidates are multiples of
+    float ext[3];
+    float max_abs;
+};
+constexpr int OCC_CANDS = 8;
+// everything the host reads back from the first phase of the build, contiguous: ONE device-to-host copy
+struct BuildHead {
+    BBoxAcc acc;
+    OccPlan plan;
+    unsigned int ones[OCC_CANDS];
+};
+__device__ void occ_plan(const volatile BBoxAcc* acc, OccPlan* plan);
 
 // accumulators are initialised by a kernel, not by a host-to-device copy: a small H2D copy queues
 // behind whatever bulk upload another queue has in flight on the same copy engine (measured: the
 // streamed end-to-end step lost 0.6 ms to exactly that)
-__global__ void bbox_init_kernel(BBoxAcc* acc) {
+__global__ void bbox_init_kernel(BuildHead* head) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        BBoxAcc* acc = &head->acc;
         for (int a = 0; a < 3; ++a) {
             acc->mn[a] = INT_MAX;
             acc->mx[a] = INT_MIN;
         }
         acc->finite = 0;
-        acc->pad = 0;
+        acc->done_blocks = 0;
+        for (int j = 0; j < OCC_CANDS; ++j) head->ones[j] = 0u;
     }
 }
 
-__global__ void bbox_kernel(const float4* __restrict__ pts, uint32_t n, BBoxAcc* acc) {
+__global__ void bbox_kernel(const float4* __restrict__ pts, uint32_t n, BuildHead* head) {
+    BBoxAcc* acc = &head->acc;
     int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
     uint32_t cnt = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -218,6 +235,13 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, uint32_t n, BBoxAcc*
         }
         atomicAdd(&acc->finite, scnt);
     }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&acc->done_blocks, 1u) == gridDim.x - 1) {
+            __threadfence();
+            occ_plan(acc, &head->plan);
+        }
+    }
 }
 
 struct GridGeom {
@@ -237,18 +261,10 @@ __device__ __forceinline__ uint32_t cell_of(const GridGeom& g, const float4 p) {
 // of the cell edge is measured for OCC_CANDS candidate edges in ONE pass: every point sets one bit
 // per candidate in a hashed bitmap of M bits, and the number of occupied cells follows from the
 // fraction of zero bits (linear counting: n_occ ~ -M ln(zeros / M), within ~1 % at the loads used).
-constexpr int OCC_CANDS = 8;
 __constant__ float OCC_FACTOR[OCC_CANDS] = {0.35f, 0.5f, 0.7071f, 1.0f, 1.4142f, 2.0f, 2.8284f, 4.0f};
 
-struct OccPlan {     // written by occ_plan_kernel, read by occ_mark_kernel and by the host
-    float lo[3];
-    float c0;        // volume-heuristic cell edge the candidates are multiples of
-    float ext[3];
-    float max_abs;
-};
-
-__global__ void occ_plan_kernel(const BBoxAcc* __restrict__ acc, OccPlan* __restrict__ plan) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// written by the last block of bbox_kernel, read by occ_mark_kernel and by the host
+__device__ void occ_plan(const volatile BBoxAcc* acc, OccPlan* plan) {
     float lo[3], ext[3], max_ext = 0.0f, max_abs = 0.0f;
     for (int a = 0; a < 3; ++a) {
         const int ol = acc->mn[a], oh = acc->mx[a];
@@ -261,7 +277,7 @@ __global__ void occ_plan_kernel(const BBoxAcc* __restrict__ acc, OccPlan* __rest
     if (!(max_ext > 0.0f)) max_ext = 1.0f;
     double vol = 1.0;
     for (int a = 0; a < 3; ++a) vol *= (double)fmaxf(ext[a], 0.02f * max_ext);
-    float c0 = (float)cbrt(vol / (2.0 * (double)max(acc->finite, 1u)));
+    float c0 = (float)cbrt(vol / (2.0 * (double)max((uint32_t)acc->finite, 1u)));
     c0 = fmaxf(c0, 1e-6f * fmaxf(max_abs, 1.0f));
     for (int a = 0; a < 3; ++a) {
         plan->lo[a] = lo[a];
@@ -768,47 +784,36 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         while (map_bits < 8u * n && map_bits < (1u << 30)) map_bits <<= 1;
         const uint32_t words_per_map = map_bits / 32u;
         q->arena_reset();
-        q->arena_reserve(sizeof(BBoxAcc) + sizeof(OccPlan) + 1024 + (size_t)OCC_CANDS * words_per_map * 4 +
+        q->arena_reserve(sizeof(BuildHead) + 1024 + (size_t)OCC_CANDS * words_per_map * 4 +
                          2 * (MAX_CELLS + MAX_CELLS / 32 + 128) * 4 + scan_scratch_elems(MAX_CELLS + MAX_CELLS / 32 + 128) * 4 + 8192);
-        BBoxAcc* acc = q->take<BBoxAcc>(1);
-        OccPlan* plan = q->take<OccPlan>(1);
-        unsigned int* ones = q->take<unsigned int>(OCC_CANDS);
+        BuildHead* head = q->take<BuildHead>(1);
+        OccPlan* plan = &head->plan;
+        unsigned int* ones = head->ones;
         uint32_t* bitmaps = q->take<uint32_t>((size_t)OCC_CANDS * words_per_map);
         uint32_t* counts = q->take<uint32_t>(MAX_CELLS + MAX_CELLS / 32 + 128);
         uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(MAX_CELLS + MAX_CELLS / 32 + 128));
 
-        char* pin = static_cast<char*>(q->pinned_get(1024));
-        BBoxAcc* hacc = reinterpret_cast<BBoxAcc*>(pin);
-        OccPlan* hplan = reinterpret_cast<OccPlan*>(pin + 128);
-        unsigned int* hones = reinterpret_cast<unsigned int*>(pin + 256);
-        for (int a = 0; a < 3; ++a) {
-            hacc->mn[a] = INT_MAX;
-            hacc->mx[a] = INT_MIN;
-        }
-        hacc->finite = 0;
-        hacc->pad = 0;
+        BuildHead* hhead = static_cast<BuildHead*>(q->pinned_get(1024));
+        unsigned int* hones = hhead->ones;
         const bool adaptive = !(cell_size > 0.0f);
-        bbox_init_kernel<<<1, 32, 0, st>>>(acc);
+        // accumulators, ticket and counters initialised on the device; the bounding-box kernel's last
+        // block derives the occupancy plan from the box
+        bbox_init_kernel<<<1, 32, 0, st>>>(head);
         SPX_LAUNCH_CHECK();
-        bbox_kernel<<<std::min(div_up(n, 256), q->sm_count * 8), 256, 0, st>>>(pts, n, acc);
-        SPX_LAUNCH_CHECK();
-        occ_plan_kernel<<<1, 32, 0, st>>>(acc, plan);
+        bbox_kernel<<<std::min(div_up(n, 256), q->sm_count * 8), 256, 0, st>>>(pts, n, head);
         SPX_LAUNCH_CHECK();
         if (adaptive) {
             SPX_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)OCC_CANDS * words_per_map * 4, st));
-            SPX_CUDA(cudaMemsetAsync(ones, 0, OCC_CANDS * sizeof(unsigned int), st));
             occ_mark_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, plan, bitmaps, words_per_map);
             SPX_LAUNCH_CHECK();
             occ_count_kernel<<<dim3(std::min(div_up(words_per_map, 256), 64), OCC_CANDS), 256, 0, st>>>(bitmaps, words_per_map,
                                                                                                        ones);
             SPX_LAUNCH_CHECK();
-            SPX_CUDA(cudaMemcpyAsync(hones, ones, OCC_CANDS * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         }
-        SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, st));
-        SPX_CUDA(cudaMemcpyAsync(hplan, plan, sizeof(OccPlan), cudaMemcpyDeviceToHost, st));
+        SPX_CUDA(cudaMemcpyAsync(hhead, head, sizeof(BuildHead), cudaMemcpyDeviceToHost, st));
         q->sync();  // the only host round trip of the build: grid dimensions size the allocations
-        const BBoxAcc bb = *hacc;
-        const OccPlan pl = *hplan;
+        const BBoxAcc bb = hhead->acc;
+        const OccPlan pl = hhead->plan;
         ix->n = bb.finite;
         L.lv[0].n = bb.finite;
         if (bb.finite == 0) return;
