@@ -363,8 +363,11 @@ __global__ void levels_count_kernel(const float4* __restrict__ pts, uint32_t n, 
 }
 
 __global__ void levels_scatter_kernel(const float4* __restrict__ pts, uint32_t n, LevelSet ls,
-                                      const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                      const uint32_t* __restrict__ start, uint32_t* __restrict__ remaining,
                                       float4* __restrict__ sorted) {
+    // `remaining` holds the per-cell counts of levels_count_kernel: a warp's group of points takes its
+    // slots off the END of the cell's range (no second zeroed cursor array); the finest level's cells
+    // are put into index order afterwards, on the coarser levels the order inside a cell is free
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -379,7 +382,10 @@ __global__ void levels_scatter_kernel(const float4* __restrict__ pts, uint32_t n
         const unsigned peers = __match_any_sync(0xffffffffu, c);
         const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
-        if (ok && lane == leader) base = __ldg(start + c) + atomicAdd(cursor + c, (uint32_t)__popc(peers));
+        if (ok && lane == leader) {
+            const uint32_t g = (uint32_t)__popc(peers);
+            base = __ldg(start + c) + atomicSub(remaining + c, g) - g;
+        }
         base = __shfl_sync(0xffffffffu, base, leader);
         if (ok) sorted[base + __popc(peers & ((1u << lane) - 1u))] = rec;
     }
@@ -903,7 +909,6 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         levels_count_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, counts);
         SPX_LAUNCH_CHECK();
         exclusive_scan_u32(st, counts, ix->start[0], total_cells + 1, scan_tmp, nullptr);
-        SPX_CUDA(cudaMemsetAsync(counts, 0, (total_cells + 1) * 4, st));  // reuse as per-cell cursor
         levels_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, ix->start[0], counts, ix->sorted[0]);
         SPX_LAUNCH_CHECK();
         cell_order_kernel<<<div_up(ix->ncells[0], 256), 256, 0, st>>>(ix->start[0], ix->ncells[0], ix->sorted[0]);
@@ -919,11 +924,6 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
             v.pts = ix->sorted[0];  // common base: `start` values of level l already include l * n
             v.n = bb.finite;
         }
-        SPX_CUDA(cudaMallocAsync(&ix->occ_dev, sizeof(unsigned long long), st));
-        SPX_CUDA(cudaMemsetAsync(ix->occ_dev, 0, sizeof(unsigned long long), st));
-        occupied_from_start_kernel<<<std::min(div_up(ix->ncells[0], 256), q->sm_count * 8), 256, 0, st>>>(
-            ix->start[0], ix->ncells[0], ix->occ_dev);
-        SPX_LAUNCH_CHECK();
         L.n_levels = level + 1;
         // no final sync: everything above is ordered on the queue's stream, and so is every search
     });
@@ -954,9 +954,16 @@ int spx_index_info(spx_index_t index, float* cell_size, int32_t* dims3, int64_t*
         }
         if (occupied_cells) {
             *occupied_cells = 0;
-            if (index->occ_dev) {  // counted on the device at build time, fetched on demand
+            if (index->start[0] && index->n > 0) {  // counted on demand: nothing on the search path needs it
                 spx_queue_t q = index->q;
                 DeviceGuard g(q->device);
+                if (!index->occ_dev) {
+                    SPX_CUDA(cudaMallocAsync(&index->occ_dev, sizeof(unsigned long long), q->stream));
+                    SPX_CUDA(cudaMemsetAsync(index->occ_dev, 0, sizeof(unsigned long long), q->stream));
+                    occupied_from_start_kernel<<<std::min(div_up(index->ncells[0], 256), q->sm_count * 8), 256, 0, q->stream>>>(
+                        index->start[0], index->ncells[0], index->occ_dev);
+                    SPX_LAUNCH_CHECK();
+                }
                 unsigned long long* h = static_cast<unsigned long long*>(q->pinned_get(64));
                 SPX_CUDA(cudaMemcpyAsync(h, index->occ_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q->stream));
                 q->sync();
