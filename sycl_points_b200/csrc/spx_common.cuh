@@ -83,6 +83,14 @@ struct spx_queue_s {
     size_t pinned_cap = 0;
     // optional blocking wait (cudaEventBlockingSync) instead of the default spin
     cudaEvent_t block_ev = nullptr;
+    // voxel-grid key geometry of the previous down-sampling on this queue (spx_voxel.cu: lets the next
+    // call of the same voxel size start its sort without waiting for its own bounding box)
+    struct {
+        bool valid = false;
+        float voxel = 0.0f;
+        int mn[3] = {0, 0, 0};
+        int mx[3] = {0, 0, 0};
+    } voxel_geom;
 
     void arena_reset() { arena_off = 0; }
     // Reserve the total a call needs BEFORE taking pointers: growing invalidates nothing in flight

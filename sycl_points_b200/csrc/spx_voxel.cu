@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __
 
 struct KeyGeom {
     int mn[3];
+    int mx[3];                   // last voxel coordinate the key covers (checked when the box was guessed)
     unsigned long long nx, nxy;  // strides of the compact key
     unsigned long long invalid;  // key given to dropped points (sorts after every valid key)
 };
@@ -233,7 +234,8 @@ struct OsItems {
 template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4* __restrict__ pts, uint32_t n,
                                                                     float inv, KeyGeom g, KeyT* __restrict__ keys,
-                                                                    int passes, uint32_t* __restrict__ ghist) {
+                                                                    int passes, uint32_t* __restrict__ ghist,
+                                                                    uint32_t* __restrict__ outside) {
     __shared__ uint32_t h[OS_MAX_PASSES * RADIX];
     for (int t = threadIdx.x; t < passes * RADIX; t += VX_THREADS) h[t] = 0;
     __syncthreads();
@@ -248,9 +250,13 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4
             if (i >= n) break;
             int c[3];
             unsigned long long key = g.invalid;
-            if (voxel_coords(pt[u], inv, c))
-                key = (unsigned long long)(c[2] - g.mn[2]) * g.nxy + (unsigned long long)(c[1] - g.mn[1]) * g.nx +
-                      (unsigned long long)(c[0] - g.mn[0]);
+            if (voxel_coords(pt[u], inv, c)) {
+                if (c[0] < g.mn[0] || c[0] > g.mx[0] || c[1] < g.mn[1] || c[1] > g.mx[1] || c[2] < g.mn[2] || c[2] > g.mx[2])
+                    *outside = 1u;  // only possible with a guessed box: the host starts over with the exact one
+                else
+                    key = (unsigned long long)(c[2] - g.mn[2]) * g.nxy + (unsigned long long)(c[1] - g.mn[1]) * g.nx +
+                          (unsigned long long)(c[0] - g.mn[0]);
+            }
             keys[i] = (KeyT)key;
             for (int p = 0; p < passes; ++p)
                 atomicAdd(&h[p * RADIX + ((uint32_t)(key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
@@ -571,11 +577,15 @@ __device__ __forceinline__ uint32_t walk_run(const KeyT* sk, const float4* sp, u
 template <typename KeyT, bool EARLY>
 __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* __restrict__ pts,
                                                                   const KeyT* __restrict__ skeys,
-                                                                  const uint32_t* __restrict__ svals, uint32_t n_valid,
+                                                                  const uint32_t* __restrict__ svals, uint32_t n_valid_arg,
+                                                                  const uint32_t* __restrict__ n_valid_dev,
                                                                   float min_count, unsigned long long* status,
                                                                   uint32_t* ticket, float4* __restrict__ out,
                                                                   uint32_t* __restrict__ total_out /*[0] total, [1] dropped*/,
                                                                   VoxAttrs at) {
+    // n_valid_dev: the host launched before it knew how many points are valid (guessed key geometry):
+    // the grid covers all points and the tiles past the valid ones leave at once
+    const uint32_t n_valid = n_valid_dev ? *n_valid_dev : n_valid_arg;
     constexpr int TILE = VrTile<KeyT>::value;
     constexpr int RPT = TILE / VR_THREADS;
     constexpr int WARPS = VR_THREADS / 32;
@@ -593,6 +603,7 @@ __global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const float4* 
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t base = tile * (uint32_t)TILE;
+    if (base >= n_valid) return;
     const uint32_t cnt = min((uint32_t)TILE, n_valid - base);                 // elements owned by the tile
     const uint32_t staged = min((uint32_t)(TILE + VR_HALO), n_valid - base);  // elements in shared memory
     {
@@ -799,9 +810,12 @@ struct VoxAttrIO {
 };
 
 template <typename KeyT>
-void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
+// guessed: the key geometry comes from the previous call (the bounding box of THIS cloud is still on its
+// way to the host in `hacc`): the number of valid points is read on the device, and a point outside the
+// guessed box raises total_dev[2] — the function then returns false and the caller starts over.
+bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
                      uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev, uint32_t* htotal,
-                     const VoxAttrIO& io) {
+                     const VoxAttrIO& io, bool guessed, const CoordAcc* acc, CoordAcc* hacc) {
     cudaStream_t st = q->stream;
     KeyT* keys_a = q->take<KeyT>(n);
     KeyT* keys_b = q->take<KeyT>(n);
@@ -817,13 +831,14 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     // one zeroed block for everything the look-backs need:
     // [digit histograms 8 x 256][sort tickets 64][sort status passes x tiles x 256][reduce ticket 2][reduce status 2 x tiles]
     const uint32_t os_tiles = onesweep ? (uint32_t)div_up(n, RS_THREADS * OsItems<KeyT>::value) : 0u;
-    const uint32_t vr_tiles = (uint32_t)div_up(std::max(n_valid, 1u), VrTile<KeyT>::value);
+    const uint32_t vr_tiles = (uint32_t)div_up(guessed ? n : std::max(n_valid, 1u), VrTile<KeyT>::value);
     const size_t os_words = (size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)passes * os_tiles * RADIX;
     const size_t words = os_words + 2 + 2 * (size_t)vr_tiles;
     uint32_t* os = q->take<uint32_t>(words);
     uint32_t* lb_ticket = os + os_words;
     unsigned long long* lb_status = reinterpret_cast<unsigned long long*>(os + os_words + 2);
     SPX_CUDA(cudaMemsetAsync(os, 0, words * sizeof(uint32_t), st));
+    SPX_CUDA(cudaMemsetAsync(total_dev, 0, 4 * sizeof(uint32_t), st));  // {voxels kept, runs dropped, point outside the box}
 
     KeyT* kin = keys_a;
     KeyT* kout = keys_b;
@@ -832,7 +847,7 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     if (onesweep) {
         // one kernel per digit: histograms of all passes from the key kernel, look-back instead of scans
         voxel_key_hist_kernel<KeyT><<<std::min(div_up(n, VX_THREADS * 4), q->sm_count * 8), VX_THREADS, 0, st>>>(
-            pts, n, inv, geom, keys_a, passes, os);
+            pts, n, inv, geom, keys_a, passes, os, total_dev + 2);
         SPX_LAUNCH_CHECK();
         for (int p = 0; p < passes; ++p) {
             onesweep_kernel<KeyT><<<os_tiles, RS_THREADS, 0, st>>>(
@@ -862,34 +877,37 @@ void sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
         }
     }
     // kin / vin now hold the sorted (key, index) pairs; dropped points (invalid key) sit at the end
-    SPX_CUDA(cudaMemsetAsync(total_dev, 0, 2 * sizeof(uint32_t), st));
-    if (n_valid == 0) {
+    if (!guessed && n_valid == 0) {
         htotal[0] = 0;
-        return;
+        return true;
     }
     at.rgb_mean = io.out_rgb;
     at.intensity_med = io.out_intensity;
     at.ts_mean = io.out_timestamps;
+    const uint32_t* n_valid_dev = guessed ? &acc->valid : nullptr;
     const bool early = min_count <= 1.0f;
     if (early)
-        voxel_reduce_kernel<KeyT, true><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status,
-                                                                        lb_ticket, out, total_dev, at);
+        voxel_reduce_kernel<KeyT, true><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, n_valid_dev, min_count,
+                                                                        lb_status, lb_ticket, out, total_dev, at);
     else
-        voxel_reduce_kernel<KeyT, false><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status,
-                                                                         lb_ticket, out, total_dev, at);
+        voxel_reduce_kernel<KeyT, false><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, n_valid_dev, min_count,
+                                                                         lb_status, lb_ticket, out, total_dev, at);
     SPX_LAUNCH_CHECK();
-    SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (guessed) SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(CoordAcc), cudaMemcpyDeviceToHost, st));
     q->sync();
+    if (guessed && htotal[2] != 0) return false;
     if (early && htotal[1] != 0) {
         // some voxel failed the min_voxel_count test (points with w < 1): again, ranking only the kept runs
         SPX_CUDA(cudaMemsetAsync(lb_ticket, 0, (2 + 2 * (size_t)vr_tiles) * sizeof(uint32_t), st));
         SPX_CUDA(cudaMemsetAsync(total_dev, 0, 2 * sizeof(uint32_t), st));
-        voxel_reduce_kernel<KeyT, false><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, min_count, lb_status,
-                                                                         lb_ticket, out, total_dev, at);
+        voxel_reduce_kernel<KeyT, false><<<vr_tiles, VR_THREADS, 0, st>>>(pts, kin, vin, n_valid, n_valid_dev, min_count,
+                                                                         lb_status, lb_ticket, out, total_dev, at);
         SPX_LAUNCH_CHECK();
         SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         q->sync();
     }
+    return true;
 }
 
 }  // namespace
@@ -922,38 +940,6 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
                          scan_scratch_elems((size_t)RADIX * nblocks) * 4 +
                          ((size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)OS_MAX_PASSES * (div_up(n, RS_TILE) + 1) * RADIX) * 4 +
                          (2 + 2 * (div_up(n, 512) + 1)) * 4 + 16 * 256 + 8192);
-        CoordAcc* acc = q->take<CoordAcc>(1);
-        uint32_t* total_dev = q->take<uint32_t>(16);
-        char* pin = static_cast<char*>(q->pinned_get(256));
-        CoordAcc* hacc = reinterpret_cast<CoordAcc*>(pin);
-        uint32_t* htotal = reinterpret_cast<uint32_t*>(pin + 128);
-        for (int a = 0; a < 3; ++a) {
-            hacc->mn[a] = INT_MAX;
-            hacc->mx[a] = INT_MIN;
-        }
-        hacc->valid = 0;
-        hacc->pad = 0;
-        coord_acc_init_kernel<<<1, 32, 0, st>>>(acc);
-        SPX_LAUNCH_CHECK();
-        voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
-        SPX_LAUNCH_CHECK();
-        SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(CoordAcc), cudaMemcpyDeviceToHost, st));
-        q->sync();
-        const CoordAcc bb = *hacc;
-        if (bb.valid == 0) return;
-
-        KeyGeom geom;
-        unsigned long long dim[3];
-        for (int a = 0; a < 3; ++a) {
-            geom.mn[a] = bb.mn[a];
-            dim[a] = (unsigned long long)(bb.mx[a] - bb.mn[a]) + 1ull;
-        }
-        geom.nx = dim[0];
-        geom.nxy = dim[0] * dim[1];
-        const unsigned long long max_key = dim[0] * dim[1] * dim[2] - 1ull;  // <= 2^63 - 1
-        const bool has_invalid = bb.valid != n;
-        geom.invalid = max_key + 1ull;
-        const int key_bits = bits_for(has_invalid ? geom.invalid : max_key);
         const float min_count = (float)min_voxel_count;
         float4* out = reinterpret_cast<float4*>(out_points);
         VoxAttrIO io;
@@ -963,11 +949,103 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         io.out_rgb = reinterpret_cast<float4*>(out_rgb);
         io.out_intensity = out_intensity;
         io.out_timestamps = out_timestamps;
-        if (key_bits <= 32)
-            sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, htotal, io);
-        else
-            sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, bb.valid, min_count, out, total_dev, htotal,
-                                                io);
+        char* pin = static_cast<char*>(q->pinned_get(256));
+        CoordAcc* hacc = reinterpret_cast<CoordAcc*>(pin);
+        uint32_t* htotal = reinterpret_cast<uint32_t*>(pin + 128);
+
+        // Key geometry.  The exact one needs this cloud's voxel bounding box on the host — a round trip
+        // in the middle of the chain.  When the previous call on this queue used the same voxel size
+        // (consecutive scans of one sensor), its box, padded, is used instead and the sort starts at
+        // once; the box of THIS cloud is still computed, comes back with the result, and the key kernel
+        // checks every point against the guess: one point outside and the call starts over, exactly.
+        // The compact key is order-preserving for any box that contains the points, so the output does
+        // not depend on which box was used.
+        auto& cache = q->voxel_geom;
+        bool guessed = cache.valid && cache.voxel == voxel_size && n < OS_LOCAL && !std::getenv("SPX_VOXEL_EXACT_BOX");
+        bool have_box = false;  // a failed guess leaves this cloud's own box in hacc
+        for (;;) {
+            CoordAcc* acc = q->take<CoordAcc>(1);
+            uint32_t* total_dev = q->take<uint32_t>(16);
+            if (!have_box) {
+                coord_acc_init_kernel<<<1, 32, 0, st>>>(acc);
+                SPX_LAUNCH_CHECK();
+                voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
+                SPX_LAUNCH_CHECK();
+            }
+            int box_mn[3], box_mx[3];
+            uint32_t n_valid = 0;
+            bool has_invalid = true;
+            if (!guessed) {
+                if (!have_box) {
+                    SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(CoordAcc), cudaMemcpyDeviceToHost, st));
+                    q->sync();
+                }
+                if (hacc->valid == 0) {
+                    cache.valid = false;
+                    return;
+                }
+                for (int a = 0; a < 3; ++a) {
+                    box_mn[a] = hacc->mn[a];
+                    box_mx[a] = hacc->mx[a];
+                }
+                n_valid = hacc->valid;
+                has_invalid = n_valid != n;
+            } else {
+                // pad by 1/16 of the extent (at least 4 voxels) unless that costs a radix pass
+                auto bits_with_pad = [&](int shift, int floor_pad) {
+                    unsigned long long cells = 1;
+                    for (int a = 0; a < 3; ++a) {
+                        const long long d = (long long)cache.mx[a] - cache.mn[a] + 1;
+                        const long long pad = shift >= 0 ? std::max<long long>(floor_pad, d >> shift) : 0;
+                        const long long lo = std::max<long long>(0, cache.mn[a] - pad);
+                        const long long hi = std::min<long long>((1ll << 21) - 1, cache.mx[a] + pad);
+                        cells *= (unsigned long long)(hi - lo + 1);
+                    }
+                    return bits_for(cells);
+                };
+                const int exact_passes = (bits_with_pad(-1, 0) + RADIX_BITS - 1) / RADIX_BITS;
+                int shift = 4, floor_pad = 4;
+                if ((bits_with_pad(4, 4) + RADIX_BITS - 1) / RADIX_BITS > exact_passes) {
+                    shift = 31;  // d >> 31 == 0
+                    floor_pad = (bits_with_pad(31, 2) + RADIX_BITS - 1) / RADIX_BITS > exact_passes ? 0 : 2;
+                }
+                for (int a = 0; a < 3; ++a) {
+                    const long long d = (long long)cache.mx[a] - cache.mn[a] + 1;
+                    const long long pad = std::max<long long>(floor_pad, d >> shift);
+                    box_mn[a] = (int)std::max<long long>(0, cache.mn[a] - pad);
+                    box_mx[a] = (int)std::min<long long>((1ll << 21) - 1, cache.mx[a] + pad);
+                }
+            }
+            KeyGeom geom;
+            unsigned long long dim[3];
+            for (int a = 0; a < 3; ++a) {
+                geom.mn[a] = box_mn[a];
+                geom.mx[a] = box_mx[a];
+                dim[a] = (unsigned long long)(box_mx[a] - box_mn[a]) + 1ull;
+            }
+            geom.nx = dim[0];
+            geom.nxy = dim[0] * dim[1];
+            const unsigned long long max_key = dim[0] * dim[1] * dim[2] - 1ull;  // <= 2^63 - 1
+            geom.invalid = max_key + 1ull;
+            const int key_bits = bits_for(has_invalid ? geom.invalid : max_key);
+            const bool ok = key_bits <= 32 ? sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, n_valid, min_count, out,
+                                                                      total_dev, htotal, io, guessed, acc, hacc)
+                                           : sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, n_valid,
+                                                                                min_count, out, total_dev, htotal, io,
+                                                                                guessed, acc, hacc);
+            if (ok) break;
+            guessed = false;  // a point fell outside the guessed box: once more with this cloud's own box
+            have_box = true;
+            q->arena_reset();
+        }
+        // hacc holds this cloud's box either way: it is the next call's guess
+        cache.valid = hacc->valid > 0;
+        cache.voxel = voxel_size;
+        for (int a = 0; a < 3; ++a) {
+            cache.mn[a] = hacc->mn[a];
+            cache.mx[a] = hacc->mx[a];
+        }
+        if (guessed && hacc->valid == 0) htotal[0] = 0;
         *m_host = htotal[0];
     });
 }
