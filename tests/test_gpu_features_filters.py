@@ -106,6 +106,31 @@ def test_voxel_invalid_points_and_wide_keys(spx, q):
     assert 0 < len(want) < 30000 and np.array_equal(got, want)
 
 
+def test_voxel_guessed_key_box_hit_miss_and_size_change(spx, q):
+    """The key geometry of a call is guessed from the previous call's box on the same queue (checked on
+    the device; exact retry when a point falls outside).  Same output whichever box was used."""
+    rng = np.random.default_rng(21)
+    small = np.c_[rng.uniform(-10, 10, (40000, 3)), np.ones(40000)].astype(np.float32)
+    big = np.c_[rng.uniform(-55, 55, (60000, 3)), np.ones(60000)].astype(np.float32)
+    big[::211, 0] = np.nan
+    want_small, want_big = oracle.voxel_downsample(small, 0.25), oracle.voxel_downsample(big, 0.25)
+    vg = spx.VoxelGrid(q, 0.25)
+    first = vg.downsampling(spx.PointCloudShared(q, small)).points_host()   # no guess yet (or a stale one)
+    again = vg.downsampling(spx.PointCloudShared(q, small)).points_host()   # guess hits
+    assert np.array_equal(first, want_small) and np.array_equal(again, want_small)
+    assert np.array_equal(vg.downsampling(spx.PointCloudShared(q, big)).points_host(), want_big)      # guess misses
+    assert np.array_equal(vg.downsampling(spx.PointCloudShared(q, small)).points_host(), want_small)  # wider box, same keys order
+    assert np.array_equal(spx.VoxelGrid(q, 0.5).downsampling(spx.PointCloudShared(q, big)).points_host(),
+                          oracle.voxel_downsample(big, 0.5))                                          # other voxel size: exact box
+    shifted = small + np.float32([300, -200, 40, 0])                                                  # disjoint from every earlier box
+    assert np.array_equal(spx.VoxelGrid(q, 0.5).downsampling(spx.PointCloudShared(q, shifted)).points_host(),
+                          oracle.voxel_downsample(shifted, 0.5))
+    allbad = np.full((64, 4), np.nan, np.float32)
+    assert spx.VoxelGrid(q, 0.5).downsampling(spx.PointCloudShared(q, allbad)).size() == 0            # guessed, nothing valid
+    assert np.array_equal(spx.VoxelGrid(q, 0.5).downsampling(spx.PointCloudShared(q, small)).points_host(),
+                          oracle.voxel_downsample(small, 0.5))
+
+
 def test_voxel_idempotent_and_sorted_large(spx, q):
     """Size-independent properties at a BASELINE-like size: output keys strictly ascending, one
     point per voxel, and down-sampling the output again at the same size is a fixed point."""
