@@ -172,3 +172,44 @@ def test_large_100k_k10(spx, q):
     # 2-queries-per-thread variant of the tile scan (taken when nq is large)
     got = gpu_bf(spx, q, qry, tgt[:4096], 20)
     assert_same(got, oracle.knn_bruteforce(qry, tgt[:4096], 20))
+
+
+def _self_knn(spx, q, pts, k):
+    cloud = spx.PointCloudShared(q, pts)
+    tree = spx.KDTree.build(q, cloud)
+    r = tree.knn_search(cloud, k)  # the indexed array itself (covariance estimation's call)
+    return (r.indices_host(), r.distances_host()), cloud, tree
+
+
+@pytest.mark.parametrize("k", [2, 5, 10, 20])
+def test_self_search_mixed_density_with_nonfinite(spx, q, k):
+    """k-NN of the indexed cloud itself on a scan-like cloud: a plane, a wall, a blob far denser than the
+    rest, isolated points hundreds of metres out (the far-query kernel), NaN coordinates."""
+    rng = np.random.default_rng(31)
+    plane = np.c_[rng.uniform(-40, 40, (30000, 2)), rng.normal(0, 0.02, 30000)]
+    wall = np.c_[np.full(6000, 12.0), rng.uniform(-20, 20, 6000), rng.uniform(0, 6, 6000)]
+    blob = rng.normal(0, 0.03, (3000, 3)) + [5, -7, 1]
+    far = rng.uniform(-300, 300, (40, 3))
+    pts = np.c_[np.concatenate([plane, wall, blob, far]), np.ones(39040)].astype(np.float32)
+    pts[::997, 1] = np.nan
+    pts = pts[rng.permutation(len(pts))]
+    got, _, _ = _self_knn(spx, q, pts, k)
+    want = oracle.knn_bruteforce(pts, pts, k)  # (a KD-tree built over NaN coordinates is not a reference)
+    assert_same(got, want)
+
+
+def test_self_search_after_the_points_moved(spx, q):
+    """Same array, new content after build: queries are searched where they are NOW (the index keeps the
+    old positions as targets): moved points, points that became finite / non-finite."""
+    rng = np.random.default_rng(32)
+    pts = np.c_[rng.uniform(-20, 20, (20000, 2)), rng.normal(0, 0.05, 20000), np.ones(20000)].astype(np.float32)
+    pts[::500, 0] = np.nan
+    (_, _), cloud, tree = _self_knn(spx, q, pts, 10)
+    moved = pts.copy()
+    moved[1::7, :3] += rng.normal(0, 1.5, (len(moved[1::7]), 3)).astype(np.float32)   # into other cells
+    moved[::1000, 0] = rng.uniform(-20, 20, len(moved[::1000])).astype(np.float32)    # half of the NaNs become finite
+    moved[3::900, 2] = np.inf                                                          # some become non-finite
+    cloud.points.upload(moved)
+    r = tree.knn_search(cloud, 10)
+    want = oracle.knn_bruteforce(moved, pts, 10)
+    assert_same((r.indices_host(), r.distances_host()), want)
