@@ -366,8 +366,7 @@ __global__ void levels_scatter_kernel(const float4* __restrict__ pts, uint32_t n
                                       const uint32_t* __restrict__ start, uint32_t* __restrict__ remaining,
                                       float4* __restrict__ sorted) {
     // `remaining` holds the per-cell counts of levels_count_kernel: a warp's group of points takes its
-    // slots off the END of the cell's range (no second zeroed cursor array); the finest level's cells
-    // are put into index order afterwards, on the coarser levels the order inside a cell is free
+    // slots off the END of the cell's range (no second zeroed cursor array); the order inside a cell is free
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -391,23 +390,6 @@ __global__ void levels_scatter_kernel(const float4* __restrict__ pts, uint32_t n
     }
 }
 
-// insertion sort of each cell's slice by original index (one thread per cell)
-__global__ void cell_order_kernel(const uint32_t* __restrict__ start, size_t ncells, float4* __restrict__ sorted) {
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
-    const uint32_t s = start[c], e = start[c + 1];
-    if (e - s > 64) return;  // pathological cells stay in arrival order (results are order-independent)
-    for (uint32_t a = s + 1; a < e; ++a) {
-        const float4 v = sorted[a];
-        const int key = __float_as_int(v.w);
-        uint32_t b = a;
-        while (b > s && __float_as_int(sorted[b - 1].w) > key) {
-            sorted[b] = sorted[b - 1];
-            --b;
-        }
-        sorted[b] = v;
-    }
-}
 
 // ------------------------------------------------------------------ index search
 constexpr int GRID_THREADS = 128;
@@ -911,8 +893,8 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         exclusive_scan_u32(st, counts, ix->start[0], total_cells + 1, scan_tmp, nullptr);
         levels_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, ix->start[0], counts, ix->sorted[0]);
         SPX_LAUNCH_CHECK();
-        cell_order_kernel<<<div_up(ix->ncells[0], 256), 256, 0, st>>>(ix->start[0], ix->ncells[0], ix->sorted[0]);
-        SPX_LAUNCH_CHECK();
+        // (the points of a cell stay in the order the scatter's atomics handed out: every search orders its
+        // candidates by (distance, original index), so no result depends on it)
         for (int l = 0; l < ls.n_levels; ++l) {
             GridView& v = L.lv[l];
             v.ox = lo[0]; v.oy = lo[1]; v.oz = lo[2];
