@@ -773,13 +773,12 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         const uint32_t words_per_map = map_bits / 32u;
         q->arena_reset();
         q->arena_reserve(sizeof(BuildHead) + 1024 + (size_t)OCC_CANDS * words_per_map * 4 +
-                         2 * (MAX_CELLS + MAX_CELLS / 32 + 128) * 4 + scan_scratch_elems(MAX_CELLS + MAX_CELLS / 32 + 128) * 4 + 8192);
+                         (MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384) * 4 + 8192);
         BuildHead* head = q->take<BuildHead>(1);
         OccPlan* plan = &head->plan;
         unsigned int* ones = head->ones;
         uint32_t* bitmaps = q->take<uint32_t>((size_t)OCC_CANDS * words_per_map);
-        uint32_t* counts = q->take<uint32_t>(MAX_CELLS + MAX_CELLS / 32 + 128);
-        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(MAX_CELLS + MAX_CELLS / 32 + 128));
+        uint32_t* counts = q->take<uint32_t>(MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384);
 
         BuildHead* hhead = static_cast<BuildHead*>(q->pinned_get(1024));
         unsigned int* hones = hhead->ones;
@@ -887,10 +886,14 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
 
         SPX_CUDA(cudaMallocAsync(&ix->start[0], (total_cells + 1) * 4, st));
         SPX_CUDA(cudaMallocAsync(&ix->sorted[0], (size_t)ls.n_levels * bb.finite * sizeof(float4), st));
-        SPX_CUDA(cudaMemsetAsync(counts, 0, (total_cells + 1) * 4, st));
+        // per-cell counts and, right behind them, the zeroed ticket + status words of the one-launch scan
+        const size_t scan_at = align_up(total_cells + 1, 2);
+        SPX_REQUIRE(scan_at + scan_lookback_words(total_cells + 1) <= MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384,
+                    "[KDTree::build] internal: count buffer too small");
+        SPX_CUDA(cudaMemsetAsync(counts, 0, (scan_at + scan_lookback_words(total_cells + 1)) * 4, st));
         levels_count_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, counts);
         SPX_LAUNCH_CHECK();
-        exclusive_scan_u32(st, counts, ix->start[0], total_cells + 1, scan_tmp, nullptr);
+        exclusive_scan_u32_onepass(st, counts, ix->start[0], total_cells + 1, counts + scan_at, nullptr);
         levels_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, ix->start[0], counts, ix->sorted[0]);
         SPX_LAUNCH_CHECK();
         // (the points of a cell stay in the order the scatter's atomics handed out: every search orders its

@@ -438,69 +438,7 @@ __device__ float run_select(const float* __restrict__ v, const uint32_t* __restr
 // (key, index) order; a run that leaves the tile continues in global memory.  Kept voxels are
 // counted per tile, the tile's output offset comes from a decoupled look-back over the tiles'
 // counts (tiles taken by ticket), and the means go straight to their final, ascending-key place.
-constexpr int VR_THREADS = 256;
-constexpr unsigned long long LB_LOCAL = 1ull << 62, LB_INCL = 1ull << 63, LB_VALUE = LB_LOCAL - 1ull;
-
-// Exclusive prefix of `count` over the tiles before `tile`; called by every thread of the block.
-// Each round reads the LB_WIN nearest predecessors not yet accounted for, all at once: when a whole
-// wave of tiles publishes together, hardly any of them is inclusive yet and the walk is long — with
-// one warp's 32 entries per L2 round trip it was the largest part of the kernel.
-constexpr int LB_PER = 4;
-constexpr uint32_t LB_WIN = VR_THREADS * LB_PER;
-__device__ __forceinline__ void lookback_publish(volatile unsigned long long* status, uint32_t tile,
-                                                 unsigned long long count) {
-    if (threadIdx.x == 0) status[tile] = (tile == 0 ? LB_INCL : LB_LOCAL) | count;
-}
-__device__ __forceinline__ unsigned long long block_lookback(volatile unsigned long long* status, uint32_t tile,
-                                                             unsigned long long count, uint32_t* s_min /*[2]*/,
-                                                             unsigned long long* s_sum) {
-    const uint32_t t = threadIdx.x;
-    if (tile == 0) return 0ull;
-    unsigned long long prev = 0;
-    long long p = (long long)tile - 1;
-    for (;;) {
-        __syncthreads();
-        if (t == 0) {
-            s_min[0] = LB_WIN;  // nearest inclusive entry of the window
-            s_min[1] = LB_WIN;  // nearest entry not published yet
-            *s_sum = 0ull;
-        }
-        __syncthreads();
-        unsigned long long v[LB_PER];
-#pragma unroll
-        for (int u = 0; u < LB_PER; ++u) {  // entry e of the window is tile p - e
-            const long long idx = p - (long long)(u * VR_THREADS + t);
-            v[u] = LB_INCL;  // before the first tile: an inclusive zero
-            if (idx >= 0) v[u] = status[idx];
-        }
-        uint32_t f = LB_WIN, un = LB_WIN;
-#pragma unroll
-        for (int u = LB_PER - 1; u >= 0; --u) {
-            const uint32_t e = u * VR_THREADS + t;
-            if (v[u] & LB_INCL) f = e;
-            if ((v[u] >> 62) == 0) un = e;
-        }
-        if (f < LB_WIN) atomicMin(&s_min[0], f);
-        if (un < LB_WIN) atomicMin(&s_min[1], un);
-        __syncthreads();
-        const uint32_t F = s_min[0], U = s_min[1];
-        if (U < F) continue;  // a tile the sum needs has not published yet (it runs: tickets are ordered)
-        unsigned long long x = 0;
-#pragma unroll
-        for (int u = 0; u < LB_PER; ++u)
-            if ((uint32_t)(u * VR_THREADS + t) <= F) x += v[u] & LB_VALUE;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((t & 31) == 0 && x) atomicAdd(s_sum, x);
-        __syncthreads();
-        prev += *s_sum;
-        if (F < LB_WIN) break;
-        p -= LB_WIN;
-    }
-    if (t == 0) status[tile] = LB_INCL | (prev + count);
-    return prev;
-}
-
+constexpr int VR_THREADS = LB_THREADS;
 template <typename KeyT>
 struct VrTile {
     static constexpr int value = sizeof(KeyT) == 4 ? 1024 : 512;
