@@ -61,21 +61,9 @@ __global__ void coord_acc_init_kernel(CoordAcc* acc) {
     }
 }
 
-__global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __restrict__ pts, uint32_t n, float inv,
-                                                                CoordAcc* acc) {
-    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
-    uint32_t cnt = 0;
-    for (uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x; i < n; i += gridDim.x * VX_THREADS) {
-        int c[3];
-        if (voxel_coords(__ldg(pts + i), inv, c)) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                mn[a] = min(mn[a], c[a]);
-                mx[a] = max(mx[a], c[a]);
-            }
-            ++cnt;
-        }
-    }
+// per-thread box + count of valid points -> the block's -> the cloud's (one set of global atomics per
+// block: per-warp atomics on seven shared addresses serialise).  Called by every thread of the block.
+__device__ __forceinline__ void coord_acc_commit(int mn[3], int mx[3], uint32_t cnt, CoordAcc* acc) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -85,7 +73,6 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __
         }
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    // one set of global atomics per block: per-warp atomics on seven shared addresses serialise
     __shared__ int smn[3], smx[3];
     __shared__ uint32_t scnt;
     if (threadIdx.x == 0) {
@@ -113,6 +100,24 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __
         }
         atomicAdd(&acc->valid, scnt);
     }
+}
+
+__global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __restrict__ pts, uint32_t n, float inv,
+                                                                CoordAcc* acc) {
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    uint32_t cnt = 0;
+    for (uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x; i < n; i += gridDim.x * VX_THREADS) {
+        int c[3];
+        if (voxel_coords(__ldg(pts + i), inv, c)) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = min(mn[a], c[a]);
+                mx[a] = max(mx[a], c[a]);
+            }
+            ++cnt;
+        }
+    }
+    coord_acc_commit(mn, mx, cnt, acc);
 }
 
 struct KeyGeom {
@@ -235,7 +240,11 @@ template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4* __restrict__ pts, uint32_t n,
                                                                     float inv, KeyGeom g, KeyT* __restrict__ keys,
                                                                     int passes, uint32_t* __restrict__ ghist,
-                                                                    uint32_t* __restrict__ outside) {
+                                                                    uint32_t* __restrict__ outside, CoordAcc* acc) {
+    // acc != null (the box in `g` is a guess): this cloud's own box and valid count are accumulated here,
+    // in the same read of the points, instead of by voxel_bbox_kernel
+    int bmn[3] = {INT_MAX, INT_MAX, INT_MAX}, bmx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    uint32_t bcnt = 0;
     __shared__ uint32_t h[OS_MAX_PASSES * RADIX];
     for (int t = threadIdx.x; t < passes * RADIX; t += VX_THREADS) h[t] = 0;
     __syncthreads();
@@ -251,6 +260,12 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4
             int c[3];
             unsigned long long key = g.invalid;
             if (voxel_coords(pt[u], inv, c)) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    bmn[a] = min(bmn[a], c[a]);
+                    bmx[a] = max(bmx[a], c[a]);
+                }
+                ++bcnt;
                 if (c[0] < g.mn[0] || c[0] > g.mx[0] || c[1] < g.mn[1] || c[1] > g.mx[1] || c[2] < g.mn[2] || c[2] > g.mx[2])
                     *outside = 1u;  // only possible with a guessed box: the host starts over with the exact one
                 else
@@ -265,6 +280,7 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4
     __syncthreads();
     for (int t = threadIdx.x; t < passes * RADIX; t += VX_THREADS)
         if (h[t]) atomicAdd(ghist + t, h[t]);
+    if (acc) coord_acc_commit(bmn, bmx, bcnt, acc);
 }
 
 template <typename KeyT>
@@ -785,7 +801,7 @@ bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     if (onesweep) {
         // one kernel per digit: histograms of all passes from the key kernel, look-back instead of scans
         voxel_key_hist_kernel<KeyT><<<std::min(div_up(n, VX_THREADS * 4), q->sm_count * 8), VX_THREADS, 0, st>>>(
-            pts, n, inv, geom, keys_a, passes, os, total_dev + 2);
+            pts, n, inv, geom, keys_a, passes, os, total_dev + 2, guessed ? const_cast<CoordAcc*>(acc) : nullptr);
         SPX_LAUNCH_CHECK();
         for (int p = 0; p < passes; ++p) {
             onesweep_kernel<KeyT><<<os_tiles, RS_THREADS, 0, st>>>(
@@ -907,8 +923,10 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
             if (!have_box) {
                 coord_acc_init_kernel<<<1, 32, 0, st>>>(acc);
                 SPX_LAUNCH_CHECK();
-                voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
-                SPX_LAUNCH_CHECK();
+                if (!guessed) {  // (with a guessed box the key kernel accumulates this cloud's box as it goes)
+                    voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
+                    SPX_LAUNCH_CHECK();
+                }
             }
             int box_mn[3], box_mx[3];
             uint32_t n_valid = 0;
