@@ -1,6 +1,7 @@
 // KNN on the device: the brute-force tile scan (I/algorithms/knn/bruteforce.hpp:24-96) and the
 // GPU-resident exact index that stands in for knn::KDTree (kdtree.hpp:142-562) behind the same
 // KNNBase contract (knn.hpp:14-61).
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1023,11 +1024,13 @@ int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, con
             launch_knn_reg<20>(index, q, qs, (uint32_t)nq, k, T, has_T, idx, dist);
         } else {
             const size_t smem = (size_t)k * GRID_THREADS * 8;
-            static bool attr_set = false;
-            if (!attr_set) {
+            // the attribute belongs to the (function, device) pair: one process may drive several GPUs
+            static std::atomic<unsigned long long> attr_set{0ull};
+            const unsigned long long bit = 1ull << (q->device & 63);
+            if (!(attr_set.load(std::memory_order_acquire) & bit)) {
                 SPX_CUDA(cudaFuncSetAttribute(grid_knn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               128 * GRID_THREADS * 8));
-                attr_set = true;
+                attr_set.fetch_or(bit, std::memory_order_release);
             }
             grid_knn_kernel<false><<<blocks, GRID_THREADS, smem, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T,
                                                                              has_T, idx, dist);
