@@ -587,6 +587,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_first_kernel(const 
     }
 }
 
+constexpr int LIST_LANES = 16;
 template <int K>
 __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_list_kernel(const GridLevels g, const float4* __restrict__ queries,
                                                                           uint32_t nq, int k, Xform T, int has_T,
@@ -602,11 +603,13 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_list_kernel(const G
     const float INF = __int_as_float(0x7f800000);
     const unsigned int n_slow = *wl_count;
     for (;;) {
+        // LIST_LANES queries per warp and turn: fewer than 32 because a warp lasts as long as its slowest
+        // lane and the list is short (a third of the queries) — more, shorter warps fill the machine better
         unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(wl_cursor, 32u);
+        if (lane == 0) base = atomicAdd(wl_cursor, (unsigned int)LIST_LANES);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_slow) break;
-        if (base + lane < n_slow) {
+        if (lane < LIST_LANES && base + lane < n_slow) {
             const uint32_t w = base + lane;
             const uint32_t qi = worklist[w];
             float4 q = __ldg(queries + qi);
@@ -670,7 +673,7 @@ void launch_knn_reg(spx_index_t index, spx_queue_t q, const float4* qs, uint32_t
     grid_knn_reg_first_kernel<K><<<div_up(nq, GRID_THREADS), GRID_THREADS, 0, q->stream>>>(index->levels, qs, nq, k, T, has_T, idx,
                                                                                          dist, worklist, counters, carry);
     SPX_LAUNCH_CHECK();
-    grid_knn_reg_list_kernel<K><<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(
+    grid_knn_reg_list_kernel<K><<<q->sm_count * 16, GRID_THREADS, 0, q->stream>>>(
         index->levels, qs, nq, k, T, has_T, idx, dist, worklist, counters, counters + 1, far_list, counters + 2, carry,
         list_levels, list_rings0);
     SPX_LAUNCH_CHECK();
