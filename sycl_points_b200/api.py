@@ -761,11 +761,14 @@ class RegistrationResult:
 
     @staticmethod
     def from_c(R: RegistrationResultC) -> "RegistrationResult":
-        return RegistrationResult(T=_T_from16(R.T), converged=bool(R.converged), iterations=int(R.iterations),
-                                  H=np.array(R.H, np.float32).reshape(6, 6), b=np.array(R.b, np.float32),
-                                  error=float(R.error), H_raw=np.array(R.H_raw, np.float32).reshape(6, 6),
-                                  b_raw=np.array(R.b_raw, np.float32), error_raw=float(R.error_raw),
-                                  inlier=int(R.inlier))
+        # one copy of the struct's 104 words, sliced by field offset (words): T 0, converged 16, iterations 17,
+        # H 18, b 54, error 60, H_raw 61, b_raw 97, error_raw 103, inlier 104 — the call sits between the
+        # align's last kernel and the caller, so it is kept short
+        w = np.frombuffer(R, np.float32).copy()
+        return RegistrationResult(T=w[0:16].reshape(4, 4).T.copy(), converged=bool(R.converged),
+                                  iterations=int(R.iterations), H=w[18:54].reshape(6, 6), b=w[54:60],
+                                  error=float(w[60]), H_raw=w[61:97].reshape(6, 6), b_raw=w[97:103],
+                                  error_raw=float(w[103]), inlier=int(R.inlier))
 
 
 @dataclass
