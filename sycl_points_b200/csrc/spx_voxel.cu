@@ -49,15 +49,14 @@ __device__ __forceinline__ bool voxel_coords(const float4 p, float inv, int c[3]
     return true;
 }
 
-// initialised on the device: a small H2D copy would queue behind another queue's bulk upload
-__global__ void coord_acc_init_kernel(CoordAcc* acc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        for (int a = 0; a < 3; ++a) {
-            acc->mn[a] = INT_MAX;
-            acc->mx[a] = INT_MIN;
-        }
-        acc->valid = 0;
-        acc->pad = 0;
+// On the device the box is accumulated with atomicMax only, in an encoding whose empty state is all zero
+// bits (so the accumulator is initialised by the memset that zeroes the rest of the scratch, not by a kernel):
+// mn[a] holds max(2^21 - c), mx[a] holds max(c + 1) over the valid points' voxel coordinates c in [0, 2^21).
+// coord_acc_decode turns the copy that reached the host back into plain min / max.
+inline void coord_acc_decode(CoordAcc* h) {
+    for (int a = 0; a < 3; ++a) {
+        h->mn[a] = h->valid ? (1 << 21) - h->mn[a] : INT_MAX;
+        h->mx[a] = h->valid ? h->mx[a] - 1 : INT_MIN;
     }
 }
 
@@ -76,18 +75,15 @@ __device__ __forceinline__ void coord_acc_commit(int mn[3], int mx[3], uint32_t 
     __shared__ int smn[3], smx[3];
     __shared__ uint32_t scnt;
     if (threadIdx.x == 0) {
-        for (int a = 0; a < 3; ++a) {
-            smn[a] = INT_MAX;
-            smx[a] = INT_MIN;
-        }
+        for (int a = 0; a < 3; ++a) smn[a] = smx[a] = 0;
         scnt = 0;
     }
     __syncthreads();
     if ((threadIdx.x & 31) == 0 && cnt) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&smn[a], mn[a]);
-            atomicMax(&smx[a], mx[a]);
+            atomicMax(&smn[a], (1 << 21) - mn[a]);
+            atomicMax(&smx[a], mx[a] + 1);
         }
         atomicAdd(&scnt, cnt);
     }
@@ -95,7 +91,7 @@ __device__ __forceinline__ void coord_acc_commit(int mn[3], int mx[3], uint32_t 
     if (threadIdx.x == 0 && scnt) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&acc->mn[a], smn[a]);
+            atomicMax(&acc->mn[a], smn[a]);
             atomicMax(&acc->mx[a], smx[a]);
         }
         atomicAdd(&acc->valid, scnt);
@@ -769,7 +765,7 @@ template <typename KeyT>
 // guessed box raises total_dev[2] — the function then returns false and the caller starts over.
 bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
                      uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev, uint32_t* htotal,
-                     const VoxAttrIO& io, bool guessed, const CoordAcc* acc, CoordAcc* hacc) {
+                     const VoxAttrIO& io, bool guessed, CoordAcc* acc, CoordAcc* hacc) {
     cudaStream_t st = q->stream;
     KeyT* keys_a = q->take<KeyT>(n);
     KeyT* keys_b = q->take<KeyT>(n);
@@ -787,10 +783,11 @@ bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     const uint32_t os_tiles = onesweep ? (uint32_t)div_up(n, RS_THREADS * OsItems<KeyT>::value) : 0u;
     const uint32_t vr_tiles = (uint32_t)div_up(guessed ? n : std::max(n_valid, 1u), VrTile<KeyT>::value);
     const size_t os_words = (size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)passes * os_tiles * RADIX;
-    const size_t words = os_words + 2 + 2 * (size_t)vr_tiles;
+    const size_t words = os_words + 2 + 2 * (size_t)vr_tiles + 8;  // ... [box accumulator 8]
     uint32_t* os = q->take<uint32_t>(words);
     uint32_t* lb_ticket = os + os_words;
     unsigned long long* lb_status = reinterpret_cast<unsigned long long*>(os + os_words + 2);
+    if (guessed) acc = reinterpret_cast<CoordAcc*>(os + os_words + 2 + 2 * (size_t)vr_tiles);  // zeroed with the rest
     SPX_CUDA(cudaMemsetAsync(os, 0, words * sizeof(uint32_t), st));
     SPX_CUDA(cudaMemsetAsync(total_dev, 0, 4 * sizeof(uint32_t), st));  // {voxels kept, runs dropped, point outside the box}
 
@@ -801,7 +798,7 @@ bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     if (onesweep) {
         // one kernel per digit: histograms of all passes from the key kernel, look-back instead of scans
         voxel_key_hist_kernel<KeyT><<<std::min(div_up(n, VX_THREADS * 4), q->sm_count * 8), VX_THREADS, 0, st>>>(
-            pts, n, inv, geom, keys_a, passes, os, total_dev + 2, guessed ? const_cast<CoordAcc*>(acc) : nullptr);
+            pts, n, inv, geom, keys_a, passes, os, total_dev + 2, guessed ? acc : nullptr);
         SPX_LAUNCH_CHECK();
         for (int p = 0; p < passes; ++p) {
             onesweep_kernel<KeyT><<<os_tiles, RS_THREADS, 0, st>>>(
@@ -893,7 +890,7 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         q->arena_reserve((size_t)n * (8 * 2 + 4 * 2) + ((size_t)RADIX * nblocks + 64) * 4 +
                          scan_scratch_elems((size_t)RADIX * nblocks) * 4 +
                          ((size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)OS_MAX_PASSES * (div_up(n, RS_TILE) + 1) * RADIX) * 4 +
-                         (2 + 2 * (div_up(n, 512) + 1)) * 4 + 16 * 256 + 8192);
+                         (2 + 2 * (div_up(n, 512) + 1) + 8) * 4 + 16 * 256 + 8192);
         const float min_count = (float)min_voxel_count;
         float4* out = reinterpret_cast<float4*>(out_points);
         VoxAttrIO io;
@@ -918,15 +915,13 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         bool guessed = cache.valid && cache.voxel == voxel_size && n < OS_LOCAL && !std::getenv("SPX_VOXEL_EXACT_BOX");
         bool have_box = false;  // a failed guess leaves this cloud's own box in hacc
         for (;;) {
-            CoordAcc* acc = q->take<CoordAcc>(1);
+            CoordAcc* acc = nullptr;  // guessed: lives in sort_and_reduce's zeroed scratch, filled by the key kernel
             uint32_t* total_dev = q->take<uint32_t>(16);
-            if (!have_box) {
-                coord_acc_init_kernel<<<1, 32, 0, st>>>(acc);
+            if (!have_box && !guessed) {
+                acc = q->take<CoordAcc>(1);
+                SPX_CUDA(cudaMemsetAsync(acc, 0, sizeof(CoordAcc), st));
+                voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
                 SPX_LAUNCH_CHECK();
-                if (!guessed) {  // (with a guessed box the key kernel accumulates this cloud's box as it goes)
-                    voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
-                    SPX_LAUNCH_CHECK();
-                }
             }
             int box_mn[3], box_mx[3];
             uint32_t n_valid = 0;
@@ -935,6 +930,7 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
                 if (!have_box) {
                     SPX_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(CoordAcc), cudaMemcpyDeviceToHost, st));
                     q->sync();
+                    coord_acc_decode(hacc);
                 }
                 if (hacc->valid == 0) {
                     cache.valid = false;
@@ -989,6 +985,7 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
                                            : sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, n_valid,
                                                                                 min_count, out, total_dev, htotal, io,
                                                                                 guessed, acc, hacc);
+            if (guessed) coord_acc_decode(hacc);  // this cloud's own box came back with the result
             if (ok) break;
             guessed = false;  // a point fell outside the guessed box: once more with this cloud's own box
             have_box = true;
