@@ -149,9 +149,12 @@ __device__ __forceinline__ int float_ordered(float f) {
     const int i = __float_as_int(f);
     return i ^ ((i >> 31) & 0x7fffffff);
 }
+// The box is accumulated with atomicMax only, in an encoding whose empty state is all zero bits (the head is
+// initialised by the memset that clears the occupancy bitmaps, not by a kernel): with u(x) = the
+// order-preserving unsigned image of a finite float, mx[a] = max u(x) and mn[a] = max ~u(x).
 struct BBoxAcc {
-    int mn[3];
-    int mx[3];
+    uint32_t mn[3];
+    uint32_t mx[3];
     uint32_t finite;
     uint32_t done_blocks;  // ticket: the last block of bbox_kernel derives the occupancy plan
 };
@@ -173,19 +176,6 @@ __device__ void occ_plan(const volatile BBoxAcc* acc, OccPlan* plan);
 // accumulators are initialised by a kernel, not by a host-to-device copy: a small H2D copy queues
 // behind whatever bulk upload another queue has in flight on the same copy engine (measured: the
 // streamed end-to-end step lost 0.6 ms to exactly that)
-__global__ void bbox_init_kernel(BuildHead* head) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        BBoxAcc* acc = &head->acc;
-        for (int a = 0; a < 3; ++a) {
-            acc->mn[a] = INT_MAX;
-            acc->mx[a] = INT_MIN;
-        }
-        acc->finite = 0;
-        acc->done_blocks = 0;
-        for (int j = 0; j < OCC_CANDS; ++j) head->ones[j] = 0u;
-    }
-}
-
 __global__ void bbox_kernel(const float4* __restrict__ pts, uint32_t n, BuildHead* head) {
     BBoxAcc* acc = &head->acc;
     int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
@@ -209,21 +199,18 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, uint32_t n, BuildHea
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     // one set of atomics per BLOCK (per-warp atomics on seven shared addresses serialise)
-    __shared__ int smn[3], smx[3];
+    __shared__ uint32_t smn[3], smx[3];
     __shared__ uint32_t scnt;
     if (threadIdx.x == 0) {
-        for (int a = 0; a < 3; ++a) {
-            smn[a] = INT_MAX;
-            smx[a] = INT_MIN;
-        }
+        for (int a = 0; a < 3; ++a) smn[a] = smx[a] = 0u;
         scnt = 0;
     }
     __syncthreads();
     if ((threadIdx.x & 31) == 0 && cnt) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&smn[a], mn[a]);
-            atomicMax(&smx[a], mx[a]);
+            atomicMax(&smn[a], ~((uint32_t)mn[a] ^ 0x80000000u));
+            atomicMax(&smx[a], (uint32_t)mx[a] ^ 0x80000000u);
         }
         atomicAdd(&scnt, cnt);
     }
@@ -231,7 +218,7 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, uint32_t n, BuildHea
     if (threadIdx.x == 0 && scnt) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&acc->mn[a], smn[a]);
+            atomicMax(&acc->mn[a], smn[a]);
             atomicMax(&acc->mx[a], smx[a]);
         }
         atomicAdd(&acc->finite, scnt);
@@ -268,7 +255,7 @@ __constant__ float OCC_FACTOR[OCC_CANDS] = {0.35f, 0.5f, 0.7071f, 1.0f, 1.4142f,
 __device__ void occ_plan(const volatile BBoxAcc* acc, OccPlan* plan) {
     float lo[3], ext[3], max_ext = 0.0f, max_abs = 0.0f;
     for (int a = 0; a < 3; ++a) {
-        const int ol = acc->mn[a], oh = acc->mx[a];
+        const int ol = (int)(~acc->mn[a] ^ 0x80000000u), oh = (int)(acc->mx[a] ^ 0x80000000u);
         lo[a] = __int_as_float(ol ^ ((ol >> 31) & 0x7fffffff));
         const float hi = __int_as_float(oh ^ ((oh >> 31) & 0x7fffffff));
         ext[a] = hi - lo[a];
@@ -787,14 +774,16 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         BuildHead* hhead = static_cast<BuildHead*>(q->pinned_get(1024));
         unsigned int* hones = hhead->ones;
         const bool adaptive = !(cell_size > 0.0f);
-        // accumulators, ticket and counters initialised on the device; the bounding-box kernel's last
-        // block derives the occupancy plan from the box
-        bbox_init_kernel<<<1, 32, 0, st>>>(head);
-        SPX_LAUNCH_CHECK();
+        // accumulators, ticket and counters start as zero bits: one memset clears them together with the
+        // occupancy bitmaps behind them; the bounding-box kernel's last block derives the occupancy plan
+        SPX_CUDA(cudaMemsetAsync(head, 0,
+                                 adaptive ? (size_t)(reinterpret_cast<char*>(bitmaps + (size_t)OCC_CANDS * words_per_map) -
+                                                     reinterpret_cast<char*>(head))
+                                          : sizeof(BuildHead),
+                                 st));
         bbox_kernel<<<std::min(div_up(n, 256), q->sm_count * 8), 256, 0, st>>>(pts, n, head);
         SPX_LAUNCH_CHECK();
         if (adaptive) {
-            SPX_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)OCC_CANDS * words_per_map * 4, st));
             occ_mark_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, plan, bitmaps, words_per_map);
             SPX_LAUNCH_CHECK();
             occ_count_kernel<<<dim3(std::min(div_up(words_per_map, 256), 64), OCC_CANDS), 256, 0, st>>>(bitmaps, words_per_map,
