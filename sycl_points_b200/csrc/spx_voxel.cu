@@ -764,8 +764,8 @@ template <typename KeyT>
 // way to the host in `hacc`): the number of valid points is read on the device, and a point outside the
 // guessed box raises total_dev[2] — the function then returns false and the caller starts over.
 bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
-                     uint32_t n_valid, float min_count, float4* out, uint32_t* total_dev, uint32_t* htotal,
-                     const VoxAttrIO& io, bool guessed, CoordAcc* acc, CoordAcc* hacc) {
+                     uint32_t n_valid, float min_count, float4* out, uint32_t* htotal, const VoxAttrIO& io, bool guessed,
+                     CoordAcc* acc, CoordAcc* hacc) {
     cudaStream_t st = q->stream;
     KeyT* keys_a = q->take<KeyT>(n);
     KeyT* keys_b = q->take<KeyT>(n);
@@ -783,13 +783,13 @@ bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     const uint32_t os_tiles = onesweep ? (uint32_t)div_up(n, RS_THREADS * OsItems<KeyT>::value) : 0u;
     const uint32_t vr_tiles = (uint32_t)div_up(guessed ? n : std::max(n_valid, 1u), VrTile<KeyT>::value);
     const size_t os_words = (size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)passes * os_tiles * RADIX;
-    const size_t words = os_words + 2 + 2 * (size_t)vr_tiles + 8;  // ... [box accumulator 8]
+    const size_t words = os_words + 2 + 2 * (size_t)vr_tiles + 8 + 4;  // ... [box accumulator 8][result counters 4]
     uint32_t* os = q->take<uint32_t>(words);
     uint32_t* lb_ticket = os + os_words;
     unsigned long long* lb_status = reinterpret_cast<unsigned long long*>(os + os_words + 2);
     if (guessed) acc = reinterpret_cast<CoordAcc*>(os + os_words + 2 + 2 * (size_t)vr_tiles);  // zeroed with the rest
+    uint32_t* total_dev = os + os_words + 2 + 2 * (size_t)vr_tiles + 8;  // {voxels kept, runs dropped, point outside the box}
     SPX_CUDA(cudaMemsetAsync(os, 0, words * sizeof(uint32_t), st));
-    SPX_CUDA(cudaMemsetAsync(total_dev, 0, 4 * sizeof(uint32_t), st));  // {voxels kept, runs dropped, point outside the box}
 
     KeyT* kin = keys_a;
     KeyT* kout = keys_b;
@@ -890,7 +890,7 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         q->arena_reserve((size_t)n * (8 * 2 + 4 * 2) + ((size_t)RADIX * nblocks + 64) * 4 +
                          scan_scratch_elems((size_t)RADIX * nblocks) * 4 +
                          ((size_t)OS_MAX_PASSES * RADIX + 64 + (size_t)OS_MAX_PASSES * (div_up(n, RS_TILE) + 1) * RADIX) * 4 +
-                         (2 + 2 * (div_up(n, 512) + 1) + 8) * 4 + 16 * 256 + 8192);
+                         (2 + 2 * (div_up(n, 512) + 1) + 12) * 4 + 16 * 256 + 8192);
         const float min_count = (float)min_voxel_count;
         float4* out = reinterpret_cast<float4*>(out_points);
         VoxAttrIO io;
@@ -916,7 +916,6 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         bool have_box = false;  // a failed guess leaves this cloud's own box in hacc
         for (;;) {
             CoordAcc* acc = nullptr;  // guessed: lives in sort_and_reduce's zeroed scratch, filled by the key kernel
-            uint32_t* total_dev = q->take<uint32_t>(16);
             if (!have_box && !guessed) {
                 acc = q->take<CoordAcc>(1);
                 SPX_CUDA(cudaMemsetAsync(acc, 0, sizeof(CoordAcc), st));
@@ -981,10 +980,10 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
             geom.invalid = max_key + 1ull;
             const int key_bits = bits_for(has_invalid ? geom.invalid : max_key);
             const bool ok = key_bits <= 32 ? sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, n_valid, min_count, out,
-                                                                      total_dev, htotal, io, guessed, acc, hacc)
+                                                                      htotal, io, guessed, acc, hacc)
                                            : sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, n_valid,
-                                                                                min_count, out, total_dev, htotal, io,
-                                                                                guessed, acc, hacc);
+                                                                                min_count, out, htotal, io, guessed, acc,
+                                                                                hacc);
             if (guessed) coord_acc_decode(hacc);  // this cloud's own box came back with the result
             if (ok) break;
             guessed = false;  // a point fell outside the guessed box: once more with this cloud's own box
