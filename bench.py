@@ -119,7 +119,9 @@ class PairPipeline:
     def __init__(self, spx, q, n_src_raw, n_tgt_raw):
         from concurrent.futures import ThreadPoolExecutor
         self.spx, self.q = spx, q
-        self.q2 = spx.DeviceQueue(q.device)
+        # the source chain starts later (worker thread) and its k-NN is the longer one: it gets the more urgent
+        # stream so that both chains are done at the same time (SPX_BENCH_Q2_PRIORITY=0 to compare)
+        self.q2 = spx.DeviceQueue(q.device, priority=int(os.environ.get("SPX_BENCH_Q2_PRIORITY", "1")))
         self.vg, self.vg2 = spx.VoxelGrid(q, VOXEL), spx.VoxelGrid(self.q2, VOXEL)
         params = spx.RegistrationParams()  # GICP, GN, max_corr 2.0, max_iter 20, criteria 1e-3 (reference defaults)
         params.robust.type = spx.RobustLossType.HUBER

@@ -128,6 +128,10 @@ SPX_API int spx_device_info(int device, char* name, int* sm, int* sm_count, size
 
 /* DeviceQueue(device) — sycl_utils.hpp:491-529.  Owns one in-order CUDA stream + scratch arena. */
 SPX_API int spx_queue_create(int device, spx_queue_t* out);
+/* The same with a scheduling hint (sycl::ext::oneapi::property::queue::priority_high / _low in the reference's
+ * runtime): priority > 0 = the device's most urgent stream priority, < 0 = the least urgent, 0 = default.  When
+ * two queues have work pending, the blocks of the more urgent one are placed first. */
+SPX_API int spx_queue_create_with_priority(int device, int priority, spx_queue_t* out);
 /* Same, on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
 SPX_API int spx_queue_create_on_stream(int device, void* cuda_stream, spx_queue_t* out);
 SPX_API int spx_queue_destroy(spx_queue_t q);

@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         "spx_device_info": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
         "spx_queue_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "spx_queue_create_with_priority": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
         "spx_queue_create_on_stream": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
         "spx_queue_destroy": (C.c_int, [vp]),
         "spx_queue_sync": (C.c_int, [vp]),

@@ -43,10 +43,12 @@ def _T_from16(t16) -> np.ndarray:
 class DeviceQueue:
     """sycl_utils::DeviceQueue (sycl_utils.hpp:491-626): one in-order CUDA stream on one device."""
 
-    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+    def __init__(self, device: int = 0, cuda_stream: int | None = None, priority: int = 0):
         L = _lib.lib()
         h = C.c_void_p()
-        if cuda_stream is None:
+        if cuda_stream is None and priority != 0:
+            check(L.spx_queue_create_with_priority(device, int(priority), C.byref(h)))
+        elif cuda_stream is None:
             check(L.spx_queue_create(device, C.byref(h)))
         else:
             check(L.spx_queue_create_on_stream(device, C.c_void_p(cuda_stream), C.byref(h)))

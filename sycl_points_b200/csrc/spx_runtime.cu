@@ -98,7 +98,7 @@ int spx_device_info(int device, char* name, int* sm, int* sm_count, size_t* glob
     });
 }
 
-static int queue_create(int device, void* stream, bool own, spx_queue_t* out) {
+static int queue_create(int device, void* stream, bool own, spx_queue_t* out, int priority = 0) {
     return guard([&] {
         SPX_REQUIRE(out, "[DeviceQueue::DeviceQueue] null output");
         int n = 0;
@@ -110,7 +110,10 @@ static int queue_create(int device, void* stream, bool own, spx_queue_t* out) {
         q->device = device;
         q->owns_stream = own;
         if (own) {
-            SPX_CUDA(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+            int lo = 0, hi = 0;  // numerically: hi <= lo, lower = more urgent
+            SPX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            const int pr = priority > 0 ? hi : (priority < 0 ? lo : 0);
+            SPX_CUDA(cudaStreamCreateWithPriority(&q->stream, cudaStreamNonBlocking, pr));
         } else {
             q->stream = static_cast<cudaStream_t>(stream);
         }
@@ -127,6 +130,9 @@ static int queue_create(int device, void* stream, bool own, spx_queue_t* out) {
 }
 
 int spx_queue_create(int device, spx_queue_t* out) { return queue_create(device, nullptr, true, out); }
+int spx_queue_create_with_priority(int device, int priority, spx_queue_t* out) {
+    return queue_create(device, nullptr, true, out, priority);
+}
 int spx_queue_create_on_stream(int device, void* cuda_stream, spx_queue_t* out) {
     return queue_create(device, cuda_stream, false, out);
 }
