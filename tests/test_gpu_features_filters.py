@@ -256,3 +256,14 @@ def test_cloud_transform_bit_exact(spx, q, bundled):
     bare = spx.PointCloudShared(q, tgt)
     spx.transform.transform(bare, T)
     assert np.array_equal(bare.points_host(), o_p) and not bare.has_cov()
+
+
+@pytest.mark.parametrize("priority", [1, -1])
+def test_queue_with_priority_runs_the_same_path(spx, priority):
+    """spx_queue_create_with_priority: a scheduling hint only — same results on such a queue."""
+    qp = spx.DeviceQueue(0, priority=priority)
+    rng = np.random.default_rng(5)
+    pts = np.c_[rng.uniform(-20, 20, (30000, 3)), np.ones(30000)].astype(np.float32)
+    got = spx.VoxelGrid(qp, 0.5).downsampling(spx.PointCloudShared(qp, pts)).points_host()
+    assert np.array_equal(got, oracle.voxel_downsample(pts, 0.5))
+    qp.close()
