@@ -990,12 +990,28 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
             have_box = true;
             q->arena_reset();
         }
-        // hacc holds this cloud's box either way: it is the next call's guess
-        cache.valid = hacc->valid > 0;
-        cache.voxel = voxel_size;
-        for (int a = 0; a < 3; ++a) {
-            cache.mn[a] = hacc->mn[a];
-            cache.mx[a] = hacc->mx[a];
+        // hacc holds this cloud's box either way: it is the next call's guess — joined with the previous guess
+        // when that costs no radix pass (a queue that alternates between two clouds, source and target of a
+        // pair, would otherwise miss on every larger one)
+        if (hacc->valid > 0) {
+            int mn[3], mx[3];
+            bool join = cache.valid && cache.voxel == voxel_size;
+            unsigned long long own = 1, both = 1;
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = join ? std::min(cache.mn[a], hacc->mn[a]) : hacc->mn[a];
+                mx[a] = join ? std::max(cache.mx[a], hacc->mx[a]) : hacc->mx[a];
+                own *= (unsigned long long)(hacc->mx[a] - hacc->mn[a]) + 1ull;
+                both *= (unsigned long long)(mx[a] - mn[a]) + 1ull;
+            }
+            join = join && (bits_for(both) + RADIX_BITS - 1) / RADIX_BITS == (bits_for(own) + RADIX_BITS - 1) / RADIX_BITS;
+            for (int a = 0; a < 3; ++a) {
+                cache.mn[a] = join ? mn[a] : hacc->mn[a];
+                cache.mx[a] = join ? mx[a] : hacc->mx[a];
+            }
+            cache.valid = true;
+            cache.voxel = voxel_size;
+        } else {
+            cache.valid = false;
         }
         if (guessed && hacc->valid == 0) htotal[0] = 0;
         *m_host = htotal[0];
