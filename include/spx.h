@@ -204,6 +204,16 @@ SPX_API int spx_normals(spx_queue_t q, const float* points, size_t n, const int3
 /* covariance::extract_normals_async(points) — covariance.hpp:467-495 */
 SPX_API int spx_normals_from_covs(spx_queue_t q, const float* points, const float* covs, size_t n, float* normals);
 
+/* eigen_utils::symmetric_eigen_decomposition_3x3 — I/utils/eigen_utils.hpp:443-562 — applied to the
+ * upper-left 3x3 of n stored covariances (which must be symmetric, as covariance::estimate writes
+ * them: the upper triangle is read).  evals[n][3] ascending; evecs[n][9] row-major 3x3 whose column
+ * k is eigenvector k.  cos / acos / cbrt are correctly rounded.  Asynchronous. */
+SPX_API int spx_eigen3(spx_queue_t q, const float* covs, size_t n, float* evals, float* evecs);
+/* covariance::kernel::update_covariance_plane — covariance.hpp:67-74 — C <- V diag(1e-3, 1, 1) V^T,
+ * in place on n covariances: the per-point GICP regularisation (factor.hpp:250-255) that
+ * spx_registration_align applies once per cloud per align.  Asynchronous. */
+SPX_API int spx_covariance_update_plane(spx_queue_t q, float* covs, size_t n);
+
 /* transform::transform_async(cloud, trans) — I/algorithms/common/transform.hpp:45-104: in place,
  * points T p, covariances T C T^T (nullable), normals T n (nullable; not re-normalised, as the
  * reference's kernel).  Asynchronous. */

@@ -21,6 +21,16 @@
 
 namespace orc {
 
+// Transcendentals: the reference's sycl::cos / acos / cbrt / sin / log / pow are implementation-
+// defined; the oracle fixes them as the CORRECTLY ROUNDED fp32 value (fp64
+// evaluation, one rounding) — the same contract as the CUDA side (spx_math.cuh cr_*).
+inline float cr_cos(float x) { return (float)std::cos((double)x); }
+inline float cr_sin(float x) { return (float)std::sin((double)x); }
+inline float cr_acos(float x) { return (float)std::acos((double)x); }
+inline float cr_cbrt(float x) { return (float)std::cbrt((double)x); }
+inline float cr_log(float x) { return (float)std::log((double)x); }
+inline float cr_cube(float x) { const double d = (double)x; return (float)(d * d * d); }
+
 template <int M, int N>
 struct Mat {
     float v[M][N];
@@ -207,17 +217,17 @@ inline void eigen3(const M3& A, V3& evals, M3& evecs) {
     const float disc = 4.0f * p * p * p + 27.0f * q * q;
 
     if (std::fabs(disc) <= EPS) {
-        const float u = q >= 0 ? -std::cbrt(q / 2.0f) : std::cbrt(-q / 2.0f);
+        const float u = q >= 0 ? -cr_cbrt(q / 2.0f) : cr_cbrt(-q / 2.0f);
         evals(0) = 2.0f * u - c2 / 3.0f;
         evals(1) = evals(2) = -u - c2 / 3.0f;
     } else {
         const float sp = std::sqrt(-p / 3.0f);
         const float cs = std::max(-1.0f, std::min(1.0f, -q / (2.0f * sp * sp * sp)));
-        float phi = std::fabs(p) < EPS ? 0.0f : std::acos(cs);
+        float phi = std::fabs(p) < EPS ? 0.0f : cr_acos(cs);
         if (phi < 0.0f) phi += PI;
-        evals(0) = std::fma(2.0f * sp, std::cos(phi / 3.0f), -c2 / 3.0f);
-        evals(2) = std::fma(2.0f * sp, std::cos((phi + 4.0f * PI) / 3.0f), -c2 / 3.0f);
-        evals(1) = std::fma(2.0f * sp, std::cos((phi + 2.0f * PI) / 3.0f), -c2 / 3.0f);
+        evals(0) = std::fma(2.0f * sp, cr_cos(phi / 3.0f), -c2 / 3.0f);
+        evals(2) = std::fma(2.0f * sp, cr_cos((phi + 4.0f * PI) / 3.0f), -c2 / 3.0f);
+        evals(1) = std::fma(2.0f * sp, cr_cos((phi + 2.0f * PI) / 3.0f), -c2 / 3.0f);
     }
     if (evals(0) > evals(1)) std::swap(evals(0), evals(1));
     if (evals(1) > evals(2)) std::swap(evals(1), evals(2));
@@ -306,8 +316,8 @@ inline V4 so3_exp(const V3& om) {
     } else {
         const float th = std::sqrt(th2);
         const float h = 0.5f * th;
-        imag = std::sin(h) / th;
-        real = std::cos(h);
+        imag = cr_sin(h) / th;
+        real = cr_cos(h);
     }
     V4 q;
     q(0) = imag * om(0); q(1) = imag * om(1); q(2) = imag * om(2); q(3) = real;
@@ -330,8 +340,8 @@ inline M4 se3_exp(const V6& a) {
     } else {
         const M3 Om = skew(om(0), om(1), om(2));
         const M3 Om2 = mul<3, 3, 3>(Om, Om);
-        const float A = (1.0f - std::cos(th)) / th2;
-        const float B = (th - std::sin(th)) / (th2 * th);
+        const float A = (1.0f - cr_cos(th)) / th2;
+        const float B = (th - cr_sin(th)) / (th2 * th);
         const M3 V = add(M3::identity(), add(scale(Om, A), scale(Om2, B)));
         t = mul<3, 3>(V, tv);
     }

@@ -412,8 +412,8 @@ inline float robust_error(int loss, float r, float s) {
         case L_NONE: return 0.5f * r * r;
         case L_HUBER: return r <= s ? 0.5f * r * r : s * (r - 0.5f * s);
         case L_TUKEY:
-            return r <= s ? (s * s / 6.0f) * (1.0f - std::pow(1.0f - ((r * r) / (s * s)), 3.0f)) : s * s / 6.0f;
-        case L_CAUCHY: return 0.5f * s * s * std::log(1.0f + ((r * r) / (s * s)));
+            return r <= s ? (s * s / 6.0f) * (1.0f - cr_cube(1.0f - ((r * r) / (s * s)))) : s * s / 6.0f;
+        case L_CAUCHY: return 0.5f * s * s * cr_log(1.0f + ((r * r) / (s * s)));
         case L_GM: return 0.5f * (s * s * r * r) / (s * s + r * r);
     }
     return 0.5f * r * r;

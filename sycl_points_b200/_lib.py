@@ -114,6 +114,8 @@ def lib() -> C.CDLL:
         "spx_covariance": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals_from_covs": (C.c_int, [vp, f32p, f32p, sz, f32p]),
+        "spx_eigen3": (C.c_int, [vp, f32p, sz, f32p, f32p]),
+        "spx_covariance_update_plane": (C.c_int, [vp, f32p, sz]),
         "spx_transform": (C.c_int, [vp, f32p, f32p, f32p, sz, hostf]),
         "spx_voxel_downsample": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, C.POINTER(C.c_size_t)]),
         "spx_voxel_downsample_attrs": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, f32p, f32p, f32p, f32p, f32p, f32p,

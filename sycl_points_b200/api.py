@@ -447,6 +447,29 @@ class covariance:  # namespace sycl_points::algorithms::covariance
                                                points.normals.ptr))
 
 
+    @staticmethod
+    def update_covariance_plane(points: PointCloudShared):
+        """kernel::update_covariance_plane over a cloud's covariances, in place (covariance.hpp:67-74)"""
+        if not points.has_cov():
+            raise SpxInvalidArgument(-1, "[covariance::update_covariance_plane] covariances not computed")
+        check(_lib.lib().spx_covariance_update_plane(points.queue.handle, points.covs.ptr, points.size()))
+
+
+def symmetric_eigen_decomposition_3x3(queue: "DeviceQueue", covs) -> tuple[np.ndarray, np.ndarray]:
+    """eigen_utils::symmetric_eigen_decomposition_3x3 (eigen_utils.hpp:443-562) of n symmetric 3x3
+    matrices given as (n, 3, 3) or the (n, 4, 4) covariance layout; returns (evals (n,3) ascending,
+    evecs (n,3,3) with eigenvectors in columns)."""
+    a = np.asarray(covs, np.float32)
+    n = a.shape[0]
+    c44 = np.zeros((n, 4, 4), np.float32)
+    c44[:, :3, :3] = a[:, :3, :3]
+    d = DeviceArray(queue, (n, 16), np.float32)
+    d.upload(np.ascontiguousarray(c44.transpose(0, 2, 1)).reshape(n, 16))  # column-major 4x4
+    ev, V = DeviceArray(queue, (n, 3), np.float32), DeviceArray(queue, (n, 9), np.float32)
+    check(_lib.lib().spx_eigen3(queue.handle, d.ptr, n, ev.ptr, V.ptr))
+    return ev.download(), V.download().reshape(n, 3, 3)
+
+
 # ------------------------------------------------------------------ filters
 class VoxelGrid:
     """filter::VoxelGrid (voxel_downsampling.hpp:14-79)."""

@@ -94,6 +94,27 @@ __global__ void __launch_bounds__(FEAT_THREADS) normals_from_covs_kernel(const f
     normals[i] = normal_of(__ldg(pts + i), load_cov16(covs + (size_t)i * 16));
 }
 
+// eigen_utils::symmetric_eigen_decomposition_3x3 on stored covariances (eigen_utils.hpp:443-562):
+// evals ascending, evecs 3x3 ROW-major (column k = eigenvector k)
+__global__ void __launch_bounds__(FEAT_THREADS) eigen3_kernel(const float* __restrict__ covs, uint32_t n,
+                                                              float* __restrict__ evals, float* __restrict__ evecs) {
+    const uint32_t i = blockIdx.x * FEAT_THREADS + threadIdx.x;
+    if (i >= n) return;
+    float ev[3], V[3][3];
+    sym_eigen3(load_cov16(covs + (size_t)i * 16), ev, V);
+    for (int a = 0; a < 3; ++a) {
+        evals[(size_t)i * 3 + a] = ev[a];
+        for (int b = 0; b < 3; ++b) evecs[(size_t)i * 9 + a * 3 + b] = V[a][b];
+    }
+}
+
+// kernel::update_covariance_plane — covariance.hpp:67-74, in place on the 4x4 layout
+__global__ void __launch_bounds__(FEAT_THREADS) update_plane_kernel(float* __restrict__ covs, uint32_t n) {
+    const uint32_t i = blockIdx.x * FEAT_THREADS + threadIdx.x;
+    if (i >= n) return;
+    store_cov16(covs + (size_t)i * 16, plane_regularize(load_cov16(covs + (size_t)i * 16)));
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ cloud transform
@@ -194,6 +215,30 @@ int spx_normals_from_covs(spx_queue_t q, const float* points, const float* covs,
         DeviceGuard g(q->device);
         normals_from_covs_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
             reinterpret_cast<const float4*>(points), covs, (uint32_t)n, reinterpret_cast<float4*>(normals));
+        SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_eigen3(spx_queue_t q, const float* covs, size_t n, float* evals, float* evecs) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[eigen_utils::symmetric_eigen_decomposition_3x3] null queue");
+        SPX_REQUIRE(n < (1ull << 31), "[eigen_utils::symmetric_eigen_decomposition_3x3] too many matrices");
+        if (n == 0) return;
+        SPX_REQUIRE(covs && evals && evecs, "[eigen_utils::symmetric_eigen_decomposition_3x3] null pointer");
+        DeviceGuard g(q->device);
+        eigen3_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(covs, (uint32_t)n, evals, evecs);
+        SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_covariance_update_plane(spx_queue_t q, float* covs, size_t n) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[covariance::update_covariance_plane] null queue");
+        SPX_REQUIRE(n < (1ull << 31), "[covariance::update_covariance_plane] too many matrices");
+        if (n == 0) return;
+        SPX_REQUIRE(covs, "[covariance::update_covariance_plane] null pointer");
+        DeviceGuard g(q->device);
+        update_plane_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(covs, (uint32_t)n);
         SPX_LAUNCH_CHECK();
     });
 }

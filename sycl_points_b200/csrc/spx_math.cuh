@@ -26,6 +26,23 @@
 
 namespace spx {
 
+// Transcendentals.  The reference calls sycl::cos / acos / cbrt / sin / log / pow, whose rounding is
+// implementation-defined (unpinned).  The contract here and in the oracle is the
+// CORRECTLY ROUNDED fp32 value, obtained by evaluating in fp64 and rounding once: CUDA's and glibc's
+// fp64 routines are both < 2 ulp(fp64), so the two sides round to the same float except when the
+// exact value lies within ~1e-16 relative of a rounding boundary (probability ~1e-8 per call).
+// None of these sit on a per-iteration hot loop (plane regularisation and normals run once per
+// point per align; se3_exp once per iteration on one thread).
+SPX_HD float cr_cosf(float x) { return (float)cos((double)x); }
+SPX_HD float cr_sinf(float x) { return (float)sin((double)x); }
+SPX_HD float cr_acosf(float x) { return (float)acos((double)x); }
+SPX_HD float cr_cbrtf(float x) { return (float)cbrt((double)x); }
+SPX_HD float cr_logf(float x) { return (float)log((double)x); }
+SPX_HD float cr_cubef(float x) {  // pow(x, 3.0f)
+    const double d = (double)x;
+    return (float)(d * d * d);
+}
+
 // symmetric 3x3: xx xy xz yy yz zz
 struct Sym3 {
     float xx, xy, xz, yy, yz, zz;
@@ -95,18 +112,18 @@ __device__ inline void sym_eigen3(const Sym3& A, float ev[3], float V[3][3]) {
     const float disc = __fadd_rn(__fmul_rn(__fmul_rn(__fmul_rn(4.0f, p), p), p), __fmul_rn(__fmul_rn(27.0f, q), q));
     const float c2_3 = __fdiv_rn(c2, 3.0f);
     if (fabsf(disc) <= EPS) {
-        const float u = q >= 0 ? -cbrtf(__fdiv_rn(q, 2.0f)) : cbrtf(__fdiv_rn(-q, 2.0f));
+        const float u = q >= 0 ? -cr_cbrtf(__fdiv_rn(q, 2.0f)) : cr_cbrtf(__fdiv_rn(-q, 2.0f));
         ev[0] = __fsub_rn(__fmul_rn(2.0f, u), c2_3);
         ev[1] = ev[2] = __fsub_rn(-u, c2_3);
     } else {
         const float sp = __fsqrt_rn(__fdiv_rn(-p, 3.0f));
         const float den = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, sp), sp), sp);
         const float cs = fmaxf(-1.0f, fminf(1.0f, __fdiv_rn(-q, den)));
-        const float phi = fabsf(p) < EPS ? 0.0f : acosf(cs);
+        const float phi = fabsf(p) < EPS ? 0.0f : cr_acosf(cs);
         const float two_sp = __fmul_rn(2.0f, sp);
-        ev[0] = __fmaf_rn(two_sp, cosf(__fdiv_rn(phi, 3.0f)), -c2_3);
-        ev[2] = __fmaf_rn(two_sp, cosf(__fdiv_rn(__fadd_rn(phi, __fmul_rn(4.0f, PI)), 3.0f)), -c2_3);
-        ev[1] = __fmaf_rn(two_sp, cosf(__fdiv_rn(__fadd_rn(phi, __fmul_rn(2.0f, PI)), 3.0f)), -c2_3);
+        ev[0] = __fmaf_rn(two_sp, cr_cosf(__fdiv_rn(phi, 3.0f)), -c2_3);
+        ev[2] = __fmaf_rn(two_sp, cr_cosf(__fdiv_rn(__fadd_rn(phi, __fmul_rn(4.0f, PI)), 3.0f)), -c2_3);
+        ev[1] = __fmaf_rn(two_sp, cr_cosf(__fdiv_rn(__fadd_rn(phi, __fmul_rn(2.0f, PI)), 3.0f)), -c2_3);
     }
     float t;
     if (ev[0] > ev[1]) { t = ev[0]; ev[0] = ev[1]; ev[1] = t; }
@@ -198,8 +215,8 @@ SPX_HD void se3_exp_rm(const float a[6], float T[4][4]) {
     } else {
         const float th = sqrtf(th2);
         const float h = SPX_MUL(0.5f, th);
-        imag = SPX_DIV(sinf(h), th);
-        real = cosf(h);
+        imag = SPX_DIV(cr_sinf(h), th);
+        real = cr_cosf(h);
     }
     const float x = SPX_MUL(imag, ox), y = SPX_MUL(imag, oy), z = SPX_MUL(imag, oz), w = real;
     const float x2 = SPX_MUL(x, x), y2 = SPX_MUL(y, y), z2 = SPX_MUL(z, z);
@@ -234,8 +251,8 @@ SPX_HD void se3_exp_rm(const float a[6], float T[4][4]) {
                 for (int k = 0; k < 3; ++k) s = SPX_FMA(Om[i][k], Om[k][j], s);
                 Om2[i][j] = s;
             }
-        const float A = SPX_DIV(SPX_SUB(1.0f, cosf(th)), th2);
-        const float B = SPX_DIV(SPX_SUB(th, sinf(th)), SPX_MUL(th2, th));
+        const float A = SPX_DIV(SPX_SUB(1.0f, cr_cosf(th)), th2);
+        const float B = SPX_DIV(SPX_SUB(th, cr_sinf(th)), SPX_MUL(th2, th));
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j)
                 Vm[i][j] = SPX_ADD((i == j) ? 1.0f : 0.0f, SPX_ADD(SPX_MUL(Om[i][j], A), SPX_MUL(Om2[i][j], B)));

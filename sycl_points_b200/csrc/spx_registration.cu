@@ -158,10 +158,10 @@ __device__ __forceinline__ float robust_error(int loss, float r, float s) {
         case SPX_LOSS_HUBER:
             return r <= s ? __fmul_rn(__fmul_rn(0.5f, r), r) : __fmul_rn(s, __fsub_rn(r, __fmul_rn(0.5f, s)));
         case SPX_LOSS_TUKEY:
-            return r <= s ? __fmul_rn(__fdiv_rn(s2, 6.0f), __fsub_rn(1.0f, powf(__fsub_rn(1.0f, __fdiv_rn(r2, s2)), 3.0f)))
+            return r <= s ? __fmul_rn(__fdiv_rn(s2, 6.0f), __fsub_rn(1.0f, cr_cubef(__fsub_rn(1.0f, __fdiv_rn(r2, s2)))))
                           : __fdiv_rn(s2, 6.0f);
         case SPX_LOSS_CAUCHY:
-            return __fmul_rn(__fmul_rn(__fmul_rn(0.5f, s), s), logf(__fadd_rn(1.0f, __fdiv_rn(r2, s2))));
+            return __fmul_rn(__fmul_rn(__fmul_rn(0.5f, s), s), cr_logf(__fadd_rn(1.0f, __fdiv_rn(r2, s2))));
         case SPX_LOSS_GEMAN_MCCLURE:
             return __fdiv_rn(__fmul_rn(0.5f, __fmul_rn(__fmul_rn(s2, r), r)), __fadd_rn(s2, r2));
         default: return __fmul_rn(__fmul_rn(0.5f, r), r);

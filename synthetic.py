@@ -161,3 +161,28 @@ def dense_pair(seed: int = 42, n_points: int = 2_000_000):
     points per cloud) meant for a 0.05 m voxel grid, which leaves ~1.9 M points per cloud; callers trim
     to `n_points`.  (target_raw, source_raw, T_gt)."""
     return kitti_pair(seed, sweeps=8, beams=256, azimuth_steps=4096, spacing=8.0)
+
+
+def mt19937_uniform_box(n: int, seed: int, lo, hi) -> np.ndarray:
+    """(n, 4) float32 xyz1 with every coordinate drawn as C++'s
+    `std::uniform_real_distribution<float>(lo[a], hi[a])(std::mt19937(seed))`, x then y then z per
+    point (queries seed 1234, targets seed 4321).  numpy's legacy
+    RandomState(seed) is the same init_genrand-seeded MT19937 and its full-range uint32 draws are the
+    raw 32-bit outputs; libstdc++'s generate_canonical<float, 24> uses one output per value:
+    u = float(x) / 2^32, clamped below 1."""
+    rs = np.random.RandomState(seed)
+    raw = rs.randint(0, 2**32, size=3 * n, dtype=np.uint64).astype(np.uint32)
+    u = raw.astype(np.float32) / np.float32(4294967296.0)
+    u = np.minimum(u, np.nextafter(np.float32(1.0), np.float32(0.0)))
+    u = u.reshape(n, 3)
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    p = np.empty((n, 4), np.float32)
+    p[:, :3] = (hi - lo) * u + lo
+    p[:, 3] = 1.0
+    return p
+
+
+def knn_config3(n_queries: int = 1_000_000, n_targets: int = 1_000_000):
+    """BASELINE config 3 clouds: i.i.d. uniform in [-50, 50]^2 x [-3, 10], mt19937(1234) / (4321)."""
+    lo, hi = (-50.0, -50.0, -3.0), (50.0, 50.0, 10.0)
+    return mt19937_uniform_box(n_queries, 1234, lo, hi), mt19937_uniform_box(n_targets, 4321, lo, hi)
