@@ -48,19 +48,12 @@ __device__ __forceinline__ bool estimate_cov(const float4* __restrict__ pts, con
     return true;
 }
 
-__device__ __forceinline__ void store_cov16(float* __restrict__ out, const Sym3& C) {
-    float4* o = reinterpret_cast<float4*>(out);
-    o[0] = make_float4(C.xx, C.xy, C.xz, 0.f);
-    o[1] = make_float4(C.xy, C.yy, C.yz, 0.f);
-    o[2] = make_float4(C.xz, C.yz, C.zz, 0.f);
-    o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
 
 // extract_normal — covariance.hpp:49-65: eigenvector of the smallest eigenvalue, kept when
 // dot(n, p) <= 1.0 and negated otherwise (the reference's literal test), w = 0.
-__device__ __forceinline__ float4 normal_of(const float4 p, const Sym3& C) {
+__device__ __forceinline__ float4 normal_of(const float4 p, const Mat3& C) {
     float ev[3], V[3][3];
-    sym_eigen3(C, ev, V);
+    mat3_eigen(C, ev, V);
     const float nx = V[0][0], ny = V[1][0], nz = V[2][0];
     const float d = __fmaf_rn(nz, p.z, __fmaf_rn(ny, p.y, __fmul_rn(nx, p.x)));
     return d <= 1.0f ? make_float4(nx, ny, nz, 0.f) : make_float4(-nx, -ny, -nz, 0.f);
@@ -73,7 +66,7 @@ __global__ void __launch_bounds__(FEAT_THREADS) covariance_kernel(const float4* 
     if (i >= n) return;
     Sym3 C;
     estimate_cov(pts, idx + (size_t)i * k, k, C);
-    store_cov16(covs + (size_t)i * 16, C);
+    store_cov16(covs + (size_t)i * 16, mat3_from_sym(C));
 }
 
 __global__ void __launch_bounds__(FEAT_THREADS) normals_kernel(const float4* __restrict__ pts, uint32_t n,
@@ -83,7 +76,7 @@ __global__ void __launch_bounds__(FEAT_THREADS) normals_kernel(const float4* __r
     if (i >= n) return;
     Sym3 C;
     estimate_cov(pts, idx + (size_t)i * k, k, C);
-    normals[i] = normal_of(__ldg(pts + i), C);
+    normals[i] = normal_of(__ldg(pts + i), mat3_from_sym(C));
 }
 
 __global__ void __launch_bounds__(FEAT_THREADS) normals_from_covs_kernel(const float4* __restrict__ pts,
@@ -101,7 +94,7 @@ __global__ void __launch_bounds__(FEAT_THREADS) eigen3_kernel(const float* __res
     const uint32_t i = blockIdx.x * FEAT_THREADS + threadIdx.x;
     if (i >= n) return;
     float ev[3], V[3][3];
-    sym_eigen3(load_cov16(covs + (size_t)i * 16), ev, V);
+    mat3_eigen(load_cov16(covs + (size_t)i * 16), ev, V);
     for (int a = 0; a < 3; ++a) {
         evals[(size_t)i * 3 + a] = ev[a];
         for (int b = 0; b < 3; ++b) evecs[(size_t)i * 9 + a * 3 + b] = V[a][b];

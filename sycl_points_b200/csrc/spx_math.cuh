@@ -43,52 +43,79 @@ SPX_HD float cr_cubef(float x) {  // pow(x, 3.0f)
     return (float)(d * d * d);
 }
 
-// symmetric 3x3: xx xy xz yy yz zz
+// symmetric 3x3: xx xy xz yy yz zz (what covariance::estimate produces: exactly symmetric)
 struct Sym3 {
     float xx, xy, xz, yy, yz, zz;
 };
 
+// general 3x3, row-major m[i][j].  The reference's covariance arithmetic (update_covariance_plane,
+// transform_covs, inverse) runs on FULL matrices: V diag V^T, R C R^T and the adjugate are symmetric
+// only up to rounding, and with GICP's 1e-3 regularisation (condition ~1e3) an ulp of asymmetry is
+// 1e-4 relative in H.  Every consumer therefore carries all nine entries, like the reference.
 struct Mat3 {
     float m[3][3];
 };
 
+SPX_HD Mat3 mat3_from_sym(const Sym3& s) {
+    Mat3 r;
+    r.m[0][0] = s.xx; r.m[0][1] = s.xy; r.m[0][2] = s.xz;
+    r.m[1][0] = s.xy; r.m[1][1] = s.yy; r.m[1][2] = s.yz;
+    r.m[2][0] = s.xz; r.m[2][1] = s.yz; r.m[2][2] = s.zz;
+    return r;
+}
+SPX_HD Mat3 mat3_identity() {
+    Mat3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[i][j] = (i == j) ? 1.0f : 0.0f;
+    return r;
+}
+
 // a*b - c*d the way eigen_utils.hpp writes its 2x2 minors: fma(a, b, -(c*d))
 SPX_HD float minor2(float a, float b, float c, float d) { return SPX_FMA(a, b, -SPX_MUL(c, d)); }
 
-// determinant(A) — eigen_utils.hpp:303-307, A symmetric
-SPX_HD float sym_det(const Sym3& a) {
-    return SPX_FMA(a.xx, minor2(a.yy, a.zz, a.yz, a.yz),
-                   SPX_FMA(-a.xy, minor2(a.xy, a.zz, a.yz, a.xz), SPX_MUL(a.xz, minor2(a.xy, a.yz, a.yy, a.xz))));
+// determinant(A) — eigen_utils.hpp:303-307
+SPX_HD float mat3_det(const Mat3& A) {
+    return SPX_FMA(A.m[0][0], minor2(A.m[1][1], A.m[2][2], A.m[1][2], A.m[2][1]),
+                   SPX_FMA(-A.m[0][1], minor2(A.m[1][0], A.m[2][2], A.m[1][2], A.m[2][0]),
+                           SPX_MUL(A.m[0][2], minor2(A.m[1][0], A.m[2][1], A.m[1][1], A.m[2][0]))));
 }
 
 // inverse(A) — eigen_utils.hpp:403-423: adjugate / det, the ZERO matrix when |det| < 1e-6
-SPX_HD Sym3 sym_inverse(const Sym3& a) {
-    const float det = sym_det(a);
-    Sym3 r;
+SPX_HD Mat3 mat3_inverse(const Mat3& s) {
+    const float det = mat3_det(s);
+    Mat3 r;
     if (fabsf(det) < 1e-6f) {
-        r.xx = r.xy = r.xz = r.yy = r.yz = r.zz = 0.0f;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) r.m[i][j] = 0.0f;
         return r;
     }
     const float id = SPX_DIV(1.0f, det);
-    r.xx = SPX_MUL(minor2(a.yy, a.zz, a.yz, a.yz), id);  // (0,0)
-    r.xy = SPX_MUL(minor2(a.xz, a.yz, a.xy, a.zz), id);  // (0,1) = fma(s02, s21, -s01*s22)
-    r.xz = SPX_MUL(minor2(a.xy, a.yz, a.xz, a.yy), id);  // (0,2) = fma(s01, s12, -s02*s11)
-    r.yy = SPX_MUL(minor2(a.xx, a.zz, a.xz, a.xz), id);  // (1,1)
-    r.yz = SPX_MUL(minor2(a.xz, a.xy, a.xx, a.yz), id);  // (1,2) = fma(s02, s10, -s00*s12)
-    r.zz = SPX_MUL(minor2(a.xx, a.yy, a.xy, a.xy), id);  // (2,2)
+    r.m[0][0] = SPX_MUL(minor2(s.m[1][1], s.m[2][2], s.m[1][2], s.m[2][1]), id);
+    r.m[1][0] = SPX_MUL(minor2(s.m[1][2], s.m[2][0], s.m[1][0], s.m[2][2]), id);
+    r.m[2][0] = SPX_MUL(minor2(s.m[1][0], s.m[2][1], s.m[1][1], s.m[2][0]), id);
+    r.m[0][1] = SPX_MUL(minor2(s.m[0][2], s.m[2][1], s.m[0][1], s.m[2][2]), id);
+    r.m[1][1] = SPX_MUL(minor2(s.m[0][0], s.m[2][2], s.m[0][2], s.m[2][0]), id);
+    r.m[2][1] = SPX_MUL(minor2(s.m[0][1], s.m[2][0], s.m[0][0], s.m[2][1]), id);
+    r.m[0][2] = SPX_MUL(minor2(s.m[0][1], s.m[1][2], s.m[0][2], s.m[1][1]), id);
+    r.m[1][2] = SPX_MUL(minor2(s.m[0][2], s.m[1][0], s.m[0][0], s.m[1][2]), id);
+    r.m[2][2] = SPX_MUL(minor2(s.m[0][0], s.m[1][1], s.m[0][1], s.m[1][0]), id);
     return r;
 }
 
 #ifdef __CUDACC__
 // symmetric_eigen_decomposition_3x3 — eigen_utils.hpp:443-562 (scaled trigonometric Cardano,
-// eigenvalues ascending, eigenvector k = largest-norm column of adj(A - l_k I)).  Only the
-// eigenvectors V (columns) are returned scaled-matrix-exact; eigenvalues are rescaled at the end.
-__device__ inline void sym_eigen3(const Sym3& A, float ev[3], float V[3][3]) {
+// eigenvalues ascending, eigenvector k = largest-norm column of adj(A - l_k I)), on the full
+// matrix exactly as the reference indexes it (both triangles are read).  V holds the eigenvectors in
+// its columns; eigenvalues are rescaled at the end.
+__device__ inline void mat3_eigen(const Mat3& A, float ev[3], float V[3][3]) {
     constexpr float EPS = 1.1920929e-07f;
     constexpr float FMIN = 1.17549435e-38f;
     constexpr float PI = 3.14159265358979323846f;
-    float mx = fmaxf(fmaxf(fmaxf(fabsf(A.xx), fabsf(A.xy)), fmaxf(fabsf(A.xz), fabsf(A.yy))),
-                     fmaxf(fabsf(A.yz), fabsf(A.zz)));
+    float mx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mx = fmaxf(mx, fabsf(A.m[i][j]));
     if (mx < FMIN) {
         ev[0] = ev[1] = ev[2] = 0.0f;
         for (int i = 0; i < 3; ++i)
@@ -96,14 +123,17 @@ __device__ inline void sym_eigen3(const Sym3& A, float ev[3], float V[3][3]) {
         return;
     }
     const float si = __fdiv_rn(1.0f, mx);
-    Sym3 S;
-    S.xx = __fmul_rn(A.xx, si); S.xy = __fmul_rn(A.xy, si); S.xz = __fmul_rn(A.xz, si);
-    S.yy = __fmul_rn(A.yy, si); S.yz = __fmul_rn(A.yz, si); S.zz = __fmul_rn(A.zz, si);
+    Mat3 S;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) S.m[i][j] = __fmul_rn(A.m[i][j], si);
 
-    const float c2 = -__fadd_rn(__fadd_rn(__fadd_rn(0.0f, S.xx), S.yy), S.zz);
-    const float c1 = __fsub_rn(__fmaf_rn(S.xx, S.yy, __fmaf_rn(S.xx, S.zz, __fmul_rn(S.yy, S.zz))),
-                               __fmaf_rn(S.xy, S.xy, __fmaf_rn(S.xz, S.xz, __fmul_rn(S.yz, S.yz))));
-    const float c0 = -sym_det(S);
+    const float c2 = -__fadd_rn(__fadd_rn(__fadd_rn(0.0f, S.m[0][0]), S.m[1][1]), S.m[2][2]);
+    const float c1 = __fsub_rn(
+        __fmaf_rn(S.m[0][0], S.m[1][1], __fmaf_rn(S.m[0][0], S.m[2][2], __fmul_rn(S.m[1][1], S.m[2][2]))),
+        __fmaf_rn(S.m[0][1], S.m[1][0], __fmaf_rn(S.m[0][2], S.m[2][0], __fmul_rn(S.m[1][2], S.m[2][1]))));
+    const float c0 = -mat3_det(S);
 
     const float p = __fsub_rn(c1, __fdiv_rn(__fmul_rn(c2, c2), 3.0f));
     const float q = __fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.0f, c2), c2), c2), 27.0f),
@@ -132,25 +162,27 @@ __device__ inline void sym_eigen3(const Sym3& A, float ev[3], float V[3][3]) {
 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        Sym3 M = S;
-        M.xx = __fsub_rn(S.xx, ev[k]);
-        M.yy = __fsub_rn(S.yy, ev[k]);
-        M.zz = __fsub_rn(S.zz, ev[k]);
-        // cofactors (symmetric): m00 m01 m02 m11 m12 m22
-        const float m00 = minor2(M.yy, M.zz, M.yz, M.yz);
-        const float m01 = minor2(M.yz, M.xz, M.xy, M.zz);
-        const float m02 = minor2(M.xy, M.yz, M.yy, M.xz);
-        const float m11 = minor2(M.xx, M.zz, M.xz, M.xz);
-        const float m12 = minor2(M.xy, M.xz, M.xx, M.yz);
-        const float m22 = minor2(M.xx, M.yy, M.xy, M.xy);
-        const float s0 = __fmaf_rn(m00, m00, __fmaf_rn(m01, m01, __fmul_rn(m02, m02)));
-        const float s1 = __fmaf_rn(m01, m01, __fmaf_rn(m11, m11, __fmul_rn(m12, m12)));
+        Mat3 M = S;
+        M.m[0][0] = __fsub_rn(S.m[0][0], ev[k]);
+        M.m[1][1] = __fsub_rn(S.m[1][1], ev[k]);
+        M.m[2][2] = __fsub_rn(S.m[2][2], ev[k]);
+        const float m00 = minor2(M.m[1][1], M.m[2][2], M.m[1][2], M.m[2][1]);
+        const float m01 = minor2(M.m[1][2], M.m[2][0], M.m[1][0], M.m[2][2]);
+        const float m02 = minor2(M.m[1][0], M.m[2][1], M.m[1][1], M.m[2][0]);
+        const float m10 = minor2(M.m[0][2], M.m[2][1], M.m[0][1], M.m[2][2]);
+        const float m11 = minor2(M.m[0][0], M.m[2][2], M.m[0][2], M.m[2][0]);
+        const float m12 = minor2(M.m[0][1], M.m[2][0], M.m[0][0], M.m[2][1]);
+        const float m20 = minor2(M.m[0][1], M.m[1][2], M.m[0][2], M.m[1][1]);
+        const float m21 = minor2(M.m[0][2], M.m[1][0], M.m[0][0], M.m[1][2]);
+        const float m22 = minor2(M.m[0][0], M.m[1][1], M.m[0][1], M.m[1][0]);
+        const float s0 = __fmaf_rn(m00, m00, __fmaf_rn(m10, m10, __fmul_rn(m20, m20)));
+        const float s1 = __fmaf_rn(m01, m01, __fmaf_rn(m11, m11, __fmul_rn(m21, m21)));
         const float s2 = __fmaf_rn(m02, m02, __fmaf_rn(m12, m12, __fmul_rn(m22, m22)));
         float vx, vy, vz;
         if (s0 >= s1 && s0 >= s2) {
-            vx = m00; vy = m01; vz = m02;
+            vx = m00; vy = m10; vz = m20;
         } else if (s1 >= s0 && s1 >= s2) {
-            vx = m01; vy = m11; vz = m12;
+            vx = m01; vy = m11; vz = m21;
         } else {
             vx = m02; vy = m12; vz = m22;
         }
@@ -169,11 +201,12 @@ __device__ inline void sym_eigen3(const Sym3& A, float ev[3], float V[3][3]) {
     ev[2] = __fmul_rn(ev[2], mx);
 }
 
-// update_covariance_plane — I/algorithms/feature/covariance.hpp:67-74: C <- V diag(1e-3,1,1) V^T
-// (eigenvalues discarded).  Upper triangle of the reference's fma chains.
-__device__ inline Sym3 plane_regularize(const Sym3& C) {
+// update_covariance_plane — I/algorithms/feature/covariance.hpp:67-74: C <- (V diag(1e-3,1,1)) V^T
+// (eigenvalues discarded), all nine entries of the reference's fma chains: entry (i,j) and (j,i)
+// differ in the rounding of (V_i0 * 1e-3) * V_j0.
+__device__ inline Mat3 plane_regularize(const Mat3& C) {
     float ev[3], V[3][3];
-    sym_eigen3(C, ev, V);
+    mat3_eigen(C, ev, V);
     float VD[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -181,24 +214,32 @@ __device__ inline Sym3 plane_regularize(const Sym3& C) {
         VD[i][1] = V[i][1];
         VD[i][2] = V[i][2];
     }
-    auto e = [&](int i, int j) {
-        return __fmaf_rn(VD[i][2], V[j][2], __fmaf_rn(VD[i][1], V[j][1], __fmul_rn(VD[i][0], V[j][0])));
-    };
-    Sym3 r;
-    r.xx = e(0, 0); r.xy = e(0, 1); r.xz = e(0, 2);
-    r.yy = e(1, 1); r.yz = e(1, 2); r.zz = e(2, 2);
+    Mat3 r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r.m[i][j] = __fmaf_rn(VD[i][2], V[j][2], __fmaf_rn(VD[i][1], V[j][1], __fmul_rn(VD[i][0], V[j][0])));
     return r;
 }
 
-// covariance stored by the reference: float[16] column-major 4x4; upper 3x3 is symmetric
-__device__ __forceinline__ Sym3 load_cov16(const float* __restrict__ c) {
+// covariance stored by the reference: float[16] column-major 4x4 — all nine entries of the upper 3x3
+__device__ __forceinline__ Mat3 load_cov16(const float* __restrict__ c) {
     const float4 c0 = __ldg(reinterpret_cast<const float4*>(c));
     const float4 c1 = __ldg(reinterpret_cast<const float4*>(c) + 1);
     const float4 c2 = __ldg(reinterpret_cast<const float4*>(c) + 2);
-    Sym3 s;
-    s.xx = c0.x; s.xy = c1.x; s.xz = c2.x;
-    s.yy = c1.y; s.yz = c2.y; s.zz = c2.z;
+    Mat3 s;
+    s.m[0][0] = c0.x; s.m[1][0] = c0.y; s.m[2][0] = c0.z;
+    s.m[0][1] = c1.x; s.m[1][1] = c1.y; s.m[2][1] = c1.z;
+    s.m[0][2] = c2.x; s.m[1][2] = c2.y; s.m[2][2] = c2.z;
     return s;
+}
+__device__ __forceinline__ void store_cov16(float* __restrict__ out, const Mat3& C) {
+    float4* o = reinterpret_cast<float4*>(out);
+    o[0] = make_float4(C.m[0][0], C.m[1][0], C.m[2][0], 0.f);
+    o[1] = make_float4(C.m[0][1], C.m[1][1], C.m[2][1], 0.f);
+    o[2] = make_float4(C.m[0][2], C.m[1][2], C.m[2][2], 0.f);
+    o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 #endif  // __CUDACC__
 

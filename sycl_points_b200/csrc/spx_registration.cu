@@ -61,14 +61,12 @@ struct PeerX {
 struct LinArgs {
     // source
     const float4* src_pts;
-    const float4* src_c0;  // regularised covariance xx xy xz yy
-    const float2* src_c1;  //                        yz zz
+    const float4* src_cm;  // prepared (plane-regularised) covariance, 3 rows of the full 3x3 per point
     const float* src_cov16;  // raw reference layout (generic entry points)
     uint32_t ns;
     // target (original index order)
     const float4* tgt_pts;
-    const float4* tgt_c0;
-    const float2* tgt_c1;
+    const float4* tgt_cm;
     const float* tgt_cov16;
     const float4* tgt_normals;
     // correspondences
@@ -193,30 +191,25 @@ __device__ __forceinline__ float chain3(float a0, float b0, float a1, float b1, 
     return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
 }
 
-__device__ __forceinline__ float sym_at(const Sym3& s, int i, int j) {
-    const int a = i < j ? i : j, b = i < j ? j : i;
-    return a == 0 ? (b == 0 ? s.xx : (b == 1 ? s.xy : s.xz)) : (a == 1 ? (b == 1 ? s.yy : s.yz) : s.zz);
-}
-
-// compute_mahalanobis_covariance + inverse — factor.hpp:111-123, transform.hpp:14-22,
-// covariance.hpp:136-141, eigen_utils.hpp:403-423; cs / ct already plane-regularised
-__device__ __forceinline__ Sym3 gicp_minv(const Xform& T, const Sym3& cs, const Sym3& ct) {
+// compute_mahalanobis_covariance + inverse — factor.hpp:111-123, transform.hpp:14-22 (T (C T^T), the
+// 4x4 products' zero terms are exact no-ops), covariance.hpp:136-141, eigen_utils.hpp:403-423;
+// cs / ct already plane-regularised.  All nine entries, as the reference: R C R^T is symmetric only
+// up to rounding and the inverse amplifies the difference.
+__device__ __forceinline__ Mat3 gicp_minv(const Xform& T, const Mat3& cs, const Mat3& ct) {
     const float R[3][3] = {{T.r0.x, T.r0.y, T.r0.z}, {T.r1.x, T.r1.y, T.r1.z}, {T.r2.x, T.r2.y, T.r2.z}};
     float X[3][3];  // C R^T
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            X[k][j] = chain3(sym_at(cs, k, 0), R[j][0], sym_at(cs, k, 1), R[j][1], sym_at(cs, k, 2), R[j][2]);
-    auto rcr = [&](int i, int j) { return chain3(R[i][0], X[0][j], R[i][1], X[1][j], R[i][2], X[2][j]); };
-    Sym3 M;
-    M.xx = __fadd_rn(rcr(0, 0), ct.xx);
-    M.xy = __fadd_rn(rcr(0, 1), ct.xy);
-    M.xz = __fadd_rn(rcr(0, 2), ct.xz);
-    M.yy = __fadd_rn(rcr(1, 1), ct.yy);
-    M.yz = __fadd_rn(rcr(1, 2), ct.yz);
-    M.zz = __fadd_rn(rcr(2, 2), ct.zz);
-    return sym_inverse(M);
+            X[k][j] = chain3(cs.m[k][0], R[j][0], cs.m[k][1], R[j][1], cs.m[k][2], R[j][2]);
+    Mat3 M;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            M.m[i][j] = __fadd_rn(chain3(R[i][0], X[0][j], R[i][1], X[1][j], R[i][2], X[2][j]), ct.m[i][j]);
+    return mat3_inverse(M);
 }
 
 // One correspondence: factor terms (factor.hpp:130-278), robust weight (robust.hpp:56-90), and
@@ -224,8 +217,8 @@ __device__ __forceinline__ Sym3 gicp_minv(const Xform& T, const Sym3& cs, const 
 // formed first, then every H / b entry is computed and added straight into its accumulator, so no
 // 27-entry temporary is ever live (register pressure, not arithmetic, limits this kernel).
 template <int REG>
-__device__ __forceinline__ void accumulate_point(const Xform& T, const float4 ps, const Sym3& cs, const float4 pt,
-                                                 const Sym3& ct, const float4 nrm, int loss, float scale,
+__device__ __forceinline__ void accumulate_point(const Xform& T, const float4 ps, const Mat3& cs, const float4 pt,
+                                                 const Mat3& ct, const float4 nrm, int loss, float scale,
                                                  float* acc) {
     const float4 tp = transform_point(T, ps);
     const float r0 = __fsub_rn(pt.x, tp.x), r1 = __fsub_rn(pt.y, tp.y), r2 = __fsub_rn(pt.z, tp.z);
@@ -264,31 +257,42 @@ __device__ __forceinline__ void accumulate_point(const Xform& T, const float4 ps
         }
         acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
     } else {  // GICP, factor.hpp:239-278; point-to-distribution, :326-354 (ct already holds inverse(C_t))
-        const Sym3 Mi = (REG == SPX_REG_POINT_TO_DISTRIBUTION) ? ct : gicp_minv(T, cs, ct);
-        const float m0 = chain3(Mi.xx, r0, Mi.xy, r1, Mi.xz, r2);
-        const float m1 = chain3(Mi.xy, r0, Mi.yy, r1, Mi.yz, r2);
-        const float m2 = chain3(Mi.xz, r0, Mi.yz, r1, Mi.zz, r2);
+        const Mat3 Mi = (REG == SPX_REG_POINT_TO_DISTRIBUTION) ? ct : gicp_minv(T, cs, ct);
+        const float m0 = chain3(Mi.m[0][0], r0, Mi.m[0][1], r1, Mi.m[0][2], r2);  // M^-1 r, rows of the full inverse
+        const float m1 = chain3(Mi.m[1][0], r0, Mi.m[1][1], r1, Mi.m[1][2], r2);
+        const float m2 = chain3(Mi.m[2][0], r0, Mi.m[2][1], r1, Mi.m[2][2], r2);
         const float e2 = chain3(r0, m0, r1, m1, r2, m2);
         const float rn = __fsqrt_rn(e2);
         const float w = robust_weight(loss, rn, scale);
+        float q[6][3];  // J^T M^-1 : q[a][j] = sum_k J(k,a) Minv(k,j)
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                q[a][j] = chain3(J.j[0][a], Mi.m[0][j], J.j[1][a], Mi.m[1][j], J.j[2][a], Mi.m[2][j]);
         int t = 0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            const float q0 = chain3(J.j[0][a], Mi.xx, J.j[1][a], Mi.xy, J.j[2][a], Mi.xz);  // (J^T M^-1)(a, :)
-            const float q1 = chain3(J.j[0][a], Mi.xy, J.j[1][a], Mi.yy, J.j[2][a], Mi.yz);
-            const float q2 = chain3(J.j[0][a], Mi.xz, J.j[1][a], Mi.yz, J.j[2][a], Mi.zz);
 #pragma unroll
-            for (int c = a; c < 6; ++c, ++t)
-                acc[t] = __fadd_rn(acc[t], __fmul_rn(w, chain3(q0, J.j[0][c], q1, J.j[1][c], q2, J.j[2][c])));
-            acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(q0, r0, q1, r1, q2, r2)));
+            for (int c = a; c < 6; ++c, ++t) {
+                // ensure_symmetric(J^T M^-1 J) — eigen_utils.hpp:208-219: (H(a,c) + H(c,a)) * 0.5 off the diagonal
+                const float hac = chain3(q[a][0], J.j[0][c], q[a][1], J.j[1][c], q[a][2], J.j[2][c]);
+                float h = hac;
+                if (c != a) {
+                    const float hca = chain3(q[c][0], J.j[0][a], q[c][1], J.j[1][a], q[c][2], J.j[2][a]);
+                    h = __fmul_rn(__fadd_rn(hac, hca), 0.5f);
+                }
+                acc[t] = __fadd_rn(acc[t], __fmul_rn(w, h));
+            }
+            acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(q[a][0], r0, q[a][1], r1, q[a][2], r2)));
         }
         acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
     }
 }
 
 template <int REG>
-__device__ __forceinline__ float point_error(const Xform& T, const float4 ps, const Sym3& cs, const float4 pt,
-                                             const Sym3& ct, const float4 nrm) {
+__device__ __forceinline__ float point_error(const Xform& T, const float4 ps, const Mat3& cs, const float4 pt,
+                                             const Mat3& ct, const float4 nrm) {
     const float4 tp = transform_point(T, ps);
     const float r0 = __fsub_rn(pt.x, tp.x), r1 = __fsub_rn(pt.y, tp.y), r2 = __fsub_rn(pt.z, tp.z);
     if (REG == SPX_REG_POINT_TO_POINT) return chain3(r0, r0, r1, r1, r2, r2);  // factor.hpp:156-164
@@ -296,45 +300,46 @@ __device__ __forceinline__ float point_error(const Xform& T, const float4 ps, co
         const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
         return __fmul_rn(d, d);
     }
-    const Sym3 Mi = (REG == SPX_REG_POINT_TO_DISTRIBUTION) ? ct : gicp_minv(T, cs, ct);  // factor.hpp:287-306, 362-373
-    const float m0 = chain3(Mi.xx, r0, Mi.xy, r1, Mi.xz, r2);
-    const float m1 = chain3(Mi.xy, r0, Mi.yy, r1, Mi.yz, r2);
-    const float m2 = chain3(Mi.xz, r0, Mi.yz, r1, Mi.zz, r2);
+    const Mat3 Mi = (REG == SPX_REG_POINT_TO_DISTRIBUTION) ? ct : gicp_minv(T, cs, ct);  // factor.hpp:287-306, 362-373
+    const float m0 = chain3(Mi.m[0][0], r0, Mi.m[0][1], r1, Mi.m[0][2], r2);
+    const float m1 = chain3(Mi.m[1][0], r0, Mi.m[1][1], r1, Mi.m[1][2], r2);
+    const float m2 = chain3(Mi.m[2][0], r0, Mi.m[2][1], r1, Mi.m[2][2], r2);
     return chain3(r0, m0, r1, m1, r2, m2);
 }
 
-__device__ __forceinline__ Sym3 identity_sym() {
-    Sym3 s;
-    s.xx = s.yy = s.zz = 1.0f;
-    s.xy = s.xz = s.yz = 0.0f;
+// prepared matrices: three float4 rows per point (w unused), 48 B
+__device__ __forceinline__ Mat3 load_mat(const float4* cm, size_t i) {
+    const float4 a = __ldg(cm + 3 * i), b = __ldg(cm + 3 * i + 1), c = __ldg(cm + 3 * i + 2);
+    Mat3 s;
+    s.m[0][0] = a.x; s.m[0][1] = a.y; s.m[0][2] = a.z;
+    s.m[1][0] = b.x; s.m[1][1] = b.y; s.m[1][2] = b.z;
+    s.m[2][0] = c.x; s.m[2][1] = c.y; s.m[2][2] = c.z;
     return s;
 }
-__device__ __forceinline__ Sym3 load_sym(const float4* c0, const float2* c1, size_t i) {
-    const float4 a = __ldg(c0 + i);
-    const float2 b = __ldg(c1 + i);
-    Sym3 s;
-    s.xx = a.x; s.xy = a.y; s.xz = a.z; s.yy = a.w; s.yz = b.x; s.zz = b.y;
-    return s;
+__device__ __forceinline__ void store_mat(float4* cm, size_t i, const Mat3& s) {
+    cm[3 * i] = make_float4(s.m[0][0], s.m[0][1], s.m[0][2], 0.f);
+    cm[3 * i + 1] = make_float4(s.m[1][0], s.m[1][1], s.m[1][2], 0.f);
+    cm[3 * i + 2] = make_float4(s.m[2][0], s.m[2][1], s.m[2][2], 0.f);
 }
 
-// covariances for one correspondence.  Prepared (6-float, already regularised) arrays win; raw
-// 16-float reference covariances are regularised on the fly (what the reference does every
-// iteration); missing covariances are identity (registration.hpp:589-590) — and identity goes
-// through update_covariance_plane like any other matrix.
+// covariances for one correspondence.  Prepared (already regularised) arrays win; raw 16-float
+// reference covariances are regularised on the fly (what the reference does every iteration);
+// missing covariances are identity (registration.hpp:589-590) — and identity goes through
+// update_covariance_plane like any other matrix.
 template <int REG>
-__device__ __forceinline__ void load_covs(const LinArgs& a, uint32_t i, int ti, Sym3& cs, Sym3& ct) {
+__device__ __forceinline__ void load_covs(const LinArgs& a, uint32_t i, int ti, Mat3& cs, Mat3& ct) {
     if (REG == SPX_REG_POINT_TO_DISTRIBUTION) {
         // only the target covariance matters: prepared = inverse(C_t) (compute_target_mahalanobis,
         // factor.hpp:311-317 — the RAW covariance, no plane regularisation); missing -> identity
-        if (a.tgt_c0) ct = load_sym(a.tgt_c0, a.tgt_c1, (size_t)ti);
-        else ct = sym_inverse(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : identity_sym());
+        if (a.tgt_cm) ct = load_mat(a.tgt_cm, (size_t)ti);
+        else ct = mat3_inverse(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity());
         return;
     }
     if (REG != SPX_REG_GICP) return;
-    if (a.src_c0) cs = load_sym(a.src_c0, a.src_c1, i);
-    else cs = plane_regularize(a.src_cov16 ? load_cov16(a.src_cov16 + (size_t)i * 16) : identity_sym());
-    if (a.tgt_c0) ct = load_sym(a.tgt_c0, a.tgt_c1, (size_t)ti);
-    else ct = plane_regularize(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : identity_sym());
+    if (a.src_cm) cs = load_mat(a.src_cm, i);
+    else cs = plane_regularize(a.src_cov16 ? load_cov16(a.src_cov16 + (size_t)i * 16) : mat3_identity());
+    if (a.tgt_cm) ct = load_mat(a.tgt_cm, (size_t)ti);
+    else ct = plane_regularize(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity());
 }
 
 __device__ __forceinline__ Xform state_xform(const RegState* s) {
@@ -620,7 +625,7 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Xform& T,
         const float4 pt = __ldg(a.tgt_pts + ti);
         const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
                                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-        Sym3 cs, ct;
+        Mat3 cs, ct;
         load_covs<REG>(a, i, ti, cs, ct);
         accumulate_point<REG>(T, ps, cs, pt, ct, nrm, a.loss, a.scale, acc);
         ++inl;
@@ -802,7 +807,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) error_kernel(const LinArgs a) 
             const float4 pt = __ldg(a.tgt_pts + ti);
             const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
                                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            Sym3 cs, ct;
+            Mat3 cs, ct;
             load_covs<REG>(a, i, ti, cs, ct);
             const float rn = __fsqrt_rn(point_error<REG>(T, ps, cs, pt, ct, nrm));
             if (WEIGHTS) {
@@ -834,12 +839,10 @@ __global__ void gn_update_kernel(RegState* st, const double* sums, float lambda,
 struct PrepArgs {
     const float* src_cov16;
     uint32_t ns;  // 0: the source needs no matrices
-    float4* src_c0;
-    float2* src_c1;
+    float4* src_cm;
     const float* tgt_cov16;
     uint32_t nt;  // 0: the target needs no matrices
-    float4* tgt_c0;
-    float2* tgt_c1;
+    float4* tgt_cm;
     int invert_tgt;
     RegState* state;
     Xform T;
@@ -861,21 +864,17 @@ __global__ void __launch_bounds__(128) align_prepare_kernel(PrepArgs p) {
     }
     uint32_t i = blockIdx.x * 128 + threadIdx.x;
     const float* cov16 = p.src_cov16;
-    float4* c0 = p.src_c0;
-    float2* c1 = p.src_c1;
+    float4* cm = p.src_cm;
     bool invert = false;
     if (i >= p.ns) {
         i -= p.ns;
         if (i >= p.nt) return;
         cov16 = p.tgt_cov16;
-        c0 = p.tgt_c0;
-        c1 = p.tgt_c1;
+        cm = p.tgt_cm;
         invert = p.invert_tgt != 0;
     }
-    const Sym3 raw = cov16 ? load_cov16(cov16 + (size_t)i * 16) : identity_sym();
-    const Sym3 r = invert ? sym_inverse(raw) : plane_regularize(raw);  // invert: point-to-distribution
-    c0[i] = make_float4(r.xx, r.xy, r.xz, r.yy);
-    c1[i] = make_float2(r.yz, r.zz);
+    const Mat3 raw = cov16 ? load_cov16(cov16 + (size_t)i * 16) : mat3_identity();
+    store_mat(cm, i, invert ? mat3_inverse(raw) : plane_regularize(raw));  // invert: point-to-distribution
 }
 
 template <int REG, int MODE, bool SOLVE>
@@ -973,11 +972,9 @@ struct spx_registration_s {
     uint32_t* worklist = nullptr;
     unsigned int* wl_counters = nullptr;
     size_t nn_cap = 0;
-    float4* src_c0 = nullptr;
-    float2* src_c1 = nullptr;
+    float4* src_cm = nullptr;  // [3 * src_cap]
     size_t src_cap = 0;
-    float4* tgt_c0 = nullptr;
-    float2* tgt_c1 = nullptr;
+    float4* tgt_cm = nullptr;
     size_t tgt_cap = 0;
     float* trace = nullptr;
     size_t trace_cap = 0;
@@ -1006,7 +1003,7 @@ void reg_free(spx_registration_t r) {
         p = nullptr;
     };
     f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist); f(r->nn_pos); f(r->worklist); f(r->wl_counters);
-    f(r->src_c0); f(r->src_c1); f(r->tgt_c0); f(r->tgt_c1); f(r->trace); f(r->phase);
+    f(r->src_cm); f(r->tgt_cm); f(r->trace); f(r->phase);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     r->ev0 = r->ev1 = nullptr;
@@ -1022,6 +1019,19 @@ void ensure(T*& p, size_t& cap, size_t need, cudaStream_t st) {
     }
     const size_t c = std::max<size_t>(need, 1024);
     SPX_CUDA(cudaMalloc(&p, c * sizeof(T)));
+    cap = c;
+}
+
+// prepared matrices: 3 float4 per point
+void ensure3(float4*& p, size_t& cap, size_t need, cudaStream_t st) {
+    if (need <= cap && p) return;
+    if (p) {
+        SPX_CUDA(cudaStreamSynchronize(st));
+        SPX_CUDA(cudaFree(p));
+        p = nullptr;
+    }
+    const size_t c = std::max<size_t>(need, 1024);
+    SPX_CUDA(cudaMalloc(&p, c * 3 * sizeof(float4)));
     cap = c;
 }
 
@@ -1099,28 +1109,17 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
         // pose-independent per-point matrices, prepared once per align: GICP = plane-regularised
         // covariances of both clouds; point-to-distribution = inverse of the raw target covariance
         const bool gicp = P.reg_type == SPX_REG_GICP;
-        size_t cap = r->src_cap;
-        if (gicp) {
-            ensure(r->src_c0, cap, ns, st);
-            ensure(r->src_c1, r->src_cap, ns, st);
-        }
-        cap = r->tgt_cap;
-        ensure(r->tgt_c0, cap, nt, st);
-        ensure(r->tgt_c1, r->tgt_cap, nt, st);
+        if (gicp) ensure3(r->src_cm, r->src_cap, ns, st);
+        ensure3(r->tgt_cm, r->tgt_cap, nt, st);
         prep.src_cov16 = src_covs;
         prep.ns = gicp ? (uint32_t)ns : 0u;
-        prep.src_c0 = r->src_c0;
-        prep.src_c1 = r->src_c1;
+        prep.src_cm = r->src_cm;
         prep.tgt_cov16 = tgt_covs;
         prep.nt = (uint32_t)nt;
-        prep.tgt_c0 = r->tgt_c0;
-        prep.tgt_c1 = r->tgt_c1;
+        prep.tgt_cm = r->tgt_cm;
         prep.invert_tgt = gicp ? 0 : 1;
-        if (gicp) {
-            a.src_c0 = r->src_c0;
-            a.src_c1 = r->src_c1;
-        }
-        a.tgt_c0 = r->tgt_c0; a.tgt_c1 = r->tgt_c1;
+        if (gicp) a.src_cm = r->src_cm;
+        a.tgt_cm = r->tgt_cm;
     }
     if (P.reg_type == SPX_REG_POINT_TO_PLANE && !tgt_normals) {
         // registration.hpp:139-141: normals derived from the pre-computed covariances
