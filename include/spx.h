@@ -300,6 +300,27 @@ SPX_API int spx_registration_align(spx_registration_t reg, const float* src_poin
                            const float* tgt_points, const float* tgt_covs, const float* tgt_normals, size_t nt,
                            spx_index_t target_index, const float* T_init_host, float robust_scale,
                            spx_registration_result* result_host, float* T_trace_host);
+/* Batched Registration::align — BASELINE config 5 / SURVEY.md §8(b) `spx_align_batch`, §8(e) "all pairs share
+ * launches via a pair-id segment key": n_pairs independent (source, target, index, initial guess) tuples are
+ * aligned by ONE set-up launch and ONE persistent cooperative launch (Gauss-Newton; LM / dog-leg fall back to
+ * one align after the other).  Every pair's result is bit for bit what spx_registration_align returns for that
+ * pair alone (the per-pair sums are folded in an order that depends on the pair's own size only).  Reference
+ * semantics per pair: registration.hpp:201-276.  pairs_host / results_host are HOST arrays; the pointers inside
+ * a pair are device pointers as for spx_registration_align.  Synchronises once. */
+typedef struct spx_align_pair {
+    const float* src_points;
+    const float* src_covs;
+    size_t ns;
+    const float* tgt_points;
+    const float* tgt_covs;
+    const float* tgt_normals;
+    size_t nt;
+    spx_index_t target_index;
+    const float* T_init_host; /* 16 floats column-major, NULL = identity */
+    float robust_scale;       /* <= 0: params.robust_default_scale */
+} spx_align_pair;
+SPX_API int spx_registration_align_batch(spx_registration_t reg, size_t n_pairs, const spx_align_pair* pairs_host,
+                                 spx_registration_result* results_host);
 /* CUDA-event time of the iteration kernels of the last align on this handle (from just before the
  * first iteration launch to just after the last), the number of iteration kernels launched and
  * the number of outer iterations that did work: bench.py's live per-launch duration. */

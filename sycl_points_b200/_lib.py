@@ -49,6 +49,15 @@ class RegistrationResultC(C.Structure):
     ]
 
 
+class AlignPairC(C.Structure):
+    """struct spx_align_pair (include/spx.h)."""
+    _fields_ = [
+        ("src_points", C.c_void_p), ("src_covs", C.c_void_p), ("ns", C.c_size_t), ("tgt_points", C.c_void_p),
+        ("tgt_covs", C.c_void_p), ("tgt_normals", C.c_void_p), ("nt", C.c_size_t), ("target_index", C.c_void_p),
+        ("T_init_host", C.POINTER(C.c_float)), ("robust_scale", C.c_float),
+    ]
+
+
 def declared_symbols() -> list[str]:
     """Every function include/spx.h declares (the exported-symbol test walks this list)."""
     with open(HEADER) as f:
@@ -137,6 +146,7 @@ def lib() -> C.CDLL:
         "spx_registration_set_params": (C.c_int, [vp, C.POINTER(RegistrationParamsC)]),
         "spx_registration_align": (C.c_int, [vp, f32p, f32p, sz, f32p, f32p, f32p, sz, vp, hostf, C.c_float,
                                              C.POINTER(RegistrationResultC), hostf]),
+        "spx_registration_align_batch": (C.c_int, [vp, sz, C.POINTER(AlignPairC), C.POINTER(RegistrationResultC)]),
         "spx_registration_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                                    C.POINTER(C.c_int32)]),
         "spx_registration_phase_times": (C.c_int, [vp, C.c_int, vp, C.c_int]),

@@ -214,6 +214,13 @@ def _ptr(a: DeviceArray | None):
     return None if a is None else a.ptr
 
 
+def _addr(p):
+    """c_void_p / int / None -> value assignable to a c_void_p structure field"""
+    if p is None:
+        return None
+    return p.value if isinstance(p, C.c_void_p) else int(p)
+
+
 # ------------------------------------------------------------------ containers
 class PointCloudShared:
     """PointCloudShared (point_cloud.hpp:73-476): per-attribute arrays on the device.
@@ -913,6 +920,45 @@ class Registration:
         if trace:
             out.trace = np.stack([_T_from16(t) for t in tr])
         return out
+
+    def align_batch(self, pairs, options: ExecutionOptions | None = None) -> list:
+        """P independent aligns in one set-up launch + one persistent cooperative launch
+        (spx_registration_align_batch; BASELINE config 5).  pairs: sequence of
+        (source, target, target_knn[, initial_guess]).  Each result equals what align() returns for that
+        pair alone, bit for bit.  Reference semantics per pair: registration.hpp:201-276."""
+        pairs = list(pairs)
+        n = len(pairs)
+        if n == 0:
+            return []
+        self._loss()
+        Pc = self.params.to_c()
+        check(_lib.lib().spx_registration_set_params(self._h, C.byref(Pc)))
+        arr = (_lib.AlignPairC * n)()
+        keep = []
+        scale = options.robust_scale if options is not None else -1.0
+        for j, pr in enumerate(pairs):
+            source, target, knn = pr[0], pr[1], pr[2]
+            T0 = np.eye(4, dtype=np.float32) if len(pr) < 4 or pr[3] is None else np.asarray(pr[3], np.float32)
+            if source.size():
+                self._validate(source, target)
+                if not isinstance(knn, KDTree):
+                    raise SpxInvalidArgument(-1, "[Registration::align_batch] target_knn must be a KDTree (spx_index)")
+            t16 = _T16(T0)
+            keep.append(t16)
+            a = arr[j]
+            a.src_points = _addr(source.points.ptr) if source.size() else None
+            a.src_covs = _addr(_ptr(source.covs)) if source.has_cov() else None
+            a.ns = source.size()
+            a.tgt_points = _addr(target.points.ptr) if target.size() else None
+            a.tgt_covs = _addr(_ptr(target.covs)) if target.has_cov() else None
+            a.tgt_normals = _addr(_ptr(target.normals)) if target.has_normal() else None
+            a.nt = target.size()
+            a.target_index = _addr(knn.handle) if isinstance(knn, KDTree) else None
+            a.T_init_host = _hostf(t16)
+            a.robust_scale = float(scale)
+        R = (RegistrationResultC * n)()
+        check(_lib.lib().spx_registration_align_batch(self._h, n, arr, R))
+        return [RegistrationResult.from_c(R[j]) for j in range(n)]
 
     def last_timing(self) -> dict:
         """CUDA-event time of the iteration kernels of the last Gauss-Newton align (bench.py)."""

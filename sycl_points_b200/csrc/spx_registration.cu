@@ -789,6 +789,277 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs 
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.state = st;
 }
 
+// ------------------------------------------------------------------ batched Gauss-Newton align
+// ONE cooperative launch aligns P independent scan pairs (P = 1: Registration::align, registration.hpp:201-276;
+// P > 1: BASELINE config 5, SURVEY.md §8(e) "all pairs share launches via a pair-id segment key").
+// The source points of all pairs are cut into CHUNKs of LIN_THREADS consecutive points of ONE pair; chunk c
+// belongs to block c mod gridDim.x in every phase of every iteration.  A chunk's 28 sums are reduced by its
+// block (fp32 per lane and warp, fp64 across the warps) into the chunk's own partial row, and a pair's rows are
+// folded in chunk order: the sums of a pair — and therefore its poses, iteration counts and results — are a
+// function of that pair's data alone, bit for bit the same whether it is aligned alone or inside any batch
+// on any grid size.  Per-pair state (pose, flags) lives in global memory (RegState[P]); a pair that has
+// converged is skipped by every phase.  Per iteration: first-pass search -> barrier -> work-list drain ->
+// barrier -> factor pass + chunk rows -> barrier -> fold + 6x6 solve (P = 1: every block, redundantly, no
+// further barrier; P > 1: pair p by block p mod gridDim.x, then a barrier).
+constexpr int CHUNK = LIN_THREADS;
+
+struct PairDesc {
+    const float4* src_pts;
+    const float4* src_cm;  // prepared matrices (GICP), 3 float4 per point
+    const float4* tgt_pts;
+    const float4* tgt_cm;  // GICP: regularised covariance; point-to-distribution: inverse(C_t)
+    const float4* tgt_normals;
+    int32_t* idx;          // [ns] correspondences of the current iteration (and the next one's warm start)
+    float* dist;
+    uint32_t* pos;
+    RegState* state;
+    float* trace;          // [max_iterations][16] column-major poses, nullable
+    uint32_t ns;
+    uint32_t chunk0;       // first chunk of this pair
+    uint32_t nchunks;
+    float scale;           // robust scale of this pair (registration.hpp:217-218)
+    GridLevels grid;       // the target's index
+};
+
+struct BatchArgs {
+    const PairDesc* pairs;      // [n_pairs]
+    const uint32_t* chunk_end;  // [n_pairs] chunk0 + nchunks, ascending: chunk -> pair lookup
+    uint32_t n_pairs, total_chunks;
+    float4* wl_q;               // work list: transformed query xyz, w = bits of the source index
+    float4* wl_b;               //            best so far {dist, idx bits, pos bits}, w = bits of the pair id
+    unsigned int* wl_counters;  // [2 parities][count, cursor]
+    double* partials;           // [2 parities][total_chunks][32]
+    float max_corr, max_corr_sq;
+    int loss;
+    float lambda, crit_rot, crit_trans;
+    unsigned long long* phase;
+};
+
+__device__ __forceinline__ uint32_t pair_of_chunk(const BatchArgs& a, uint32_t c) {
+    uint32_t lo = 0, hi = a.n_pairs - 1;  // first pair whose chunk_end > c
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a.chunk_end + mid) > c) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+// pose of a pair: P = 1 keeps it in shared memory; P > 1 reads what the pair's owner block wrote before the
+// last grid barrier (L2: another SM's L1 may hold a stale line)
+__device__ __forceinline__ Xform pose_ldcg(const RegState* st) {
+    const float4* t = reinterpret_cast<const float4*>(&st->T[0][0]);
+    Xform T;
+    T.r0 = __ldcg(t);
+    T.r1 = __ldcg(t + 1);
+    T.r2 = __ldcg(t + 2);
+    T.r3 = __ldcg(t + 3);
+    return T;
+}
+
+template <int REG>
+__global__ void __launch_bounds__(LIN_THREADS, 2) align_batch_kernel(const BatchArgs a, int max_iterations) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double fold[LIN_WARPS][32];
+    __shared__ float red[LIN_WARPS][32];
+    __shared__ RegState st1;  // P = 1: this block's copy of the optimiser state
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool single = a.n_pairs == 1;
+    if (single) {
+        if (threadIdx.x == 0) st1 = *a.pairs[0].state;
+        __syncthreads();
+    }
+    for (int it = 0; it < max_iterations; ++it) {
+        const int par = it & 1;
+        const bool warm = it > 0;
+        unsigned int* wl_count = a.wl_counters + par * 2;
+        unsigned int* wl_cursor = a.wl_counters + par * 2 + 1;
+        phase_mark(a.phase, it, PH_START);
+        // ---- 1. first-pass search: one lane per source point
+        for (uint32_t c = blockIdx.x; c < a.total_chunks; c += gridDim.x) {
+            const uint32_t p = single ? 0u : pair_of_chunk(a, c);
+            const PairDesc* d = a.pairs + p;
+            const RegState* st = d->state;
+            if (!single && __ldcg(&st->stop)) continue;  // block-uniform
+            const Xform T = single ? state_xform(&st1) : pose_ldcg(st);
+            const uint32_t ns = __ldg(&d->ns);
+            const uint32_t i = (c - __ldg(&d->chunk0)) * CHUNK + threadIdx.x;
+            bool pending = false;
+            Best1 best;
+            best.init();
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < ns) {
+                int32_t* idx = d->idx;
+                float* dist = d->dist;
+                uint32_t* pos = d->pos;
+                // the three loads are independent: issued together, one round trip instead of three
+                const float4 ps = __ldg(d->src_pts + i);
+                const int prev_i = warm ? __ldcg(idx + i) : -1;
+                const uint32_t prev_p = warm ? __ldcg(pos + i) : 0xffffffffu;
+                q = transform_point(T, ps);
+                if (__ldg(&d->grid.lv[0].n) > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
+                    pending = !icp_fast(d->grid, q.x, q.y, q.z, prev_i >= 0 ? prev_p : 0xffffffffu, a.max_corr, best);
+                idx[i] = best.i;
+                dist[i] = best.d;
+                pos[i] = best.p;
+            }
+            const unsigned m = __ballot_sync(FULL, pending);  // warp-aggregated append
+            if (m) {
+                unsigned int slot = 0;
+                if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
+                slot = __shfl_sync(FULL, slot, __ffs(m) - 1);
+                if (pending) {
+                    const unsigned int w = slot + __popc(m & ((1u << lane) - 1u));
+                    a.wl_q[w] = make_float4(q.x, q.y, q.z, __uint_as_float(i));
+                    a.wl_b[w] = make_float4(best.d, __int_as_float(best.i), __uint_as_float(best.p), __uint_as_float(p));
+                }
+            }
+        }
+        phase_mark(a.phase, it, PH_NN);
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {  // the other parity's counters: idle until the next iteration
+            a.wl_counters[(par ^ 1) * 2] = 0;
+            a.wl_counters[(par ^ 1) * 2 + 1] = 0;
+        }
+        // ---- 2. the queries the first pass could not certify: one per warp, drained by the whole grid
+        {
+            const unsigned int n_slow = __ldcg(wl_count);
+            for (;;) {
+                unsigned int k = 0;
+                if (lane == 0) k = atomicAdd(wl_cursor, 1u);
+                k = __shfl_sync(FULL, k, 0);
+                if (k >= n_slow) break;
+                const float4 qv = __ldcg(a.wl_q + k);
+                const float4 bv = __ldcg(a.wl_b + k);
+                const PairDesc* d = a.pairs + __float_as_uint(bv.w);
+                const uint32_t i = __float_as_uint(qv.w);
+                Best1 best;
+                best.d = bv.x;
+                best.i = __float_as_int(bv.y);
+                best.p = __float_as_uint(bv.z);
+                icp_coop_search(d->grid, qv.x, qv.y, qv.z, best, a.max_corr);
+                if (lane == 0) {
+                    d->idx[i] = best.i;
+                    d->dist[i] = best.d;
+                    d->pos[i] = best.p;
+                }
+            }
+        }
+        __threadfence();
+        grid.sync();
+        phase_mark(a.phase, it, PH_COOP);
+        // ---- 3. factor pass: one correspondence per lane, one partial row per chunk
+        double* part = a.partials + (size_t)par * a.total_chunks * 32;
+        for (uint32_t c = blockIdx.x; c < a.total_chunks; c += gridDim.x) {
+            const uint32_t p = single ? 0u : pair_of_chunk(a, c);
+            const PairDesc* d = a.pairs + p;
+            const RegState* st = d->state;
+            if (!single && __ldcg(&st->stop)) continue;
+            const Xform T = single ? state_xform(&st1) : pose_ldcg(st);
+            const uint32_t i = (c - __ldg(&d->chunk0)) * CHUNK + threadIdx.x;
+            float acc[N_ACC];
+#pragma unroll
+            for (int v = 0; v < N_ACC; ++v) acc[v] = 0.0f;
+            uint32_t inl = 0;
+            if (i < __ldg(&d->ns)) {
+                const float dd = __ldcg(d->dist + i);
+                const int ti = __ldcg(d->idx + i);
+                if (!(dd > a.max_corr_sq || ti < 0)) {  // registration.hpp:584 (+ guard for the -1 fill)
+                    const float4 ps = __ldg(d->src_pts + i);
+                    const float4 pt = __ldg(d->tgt_pts + ti);
+                    const float4* nrm_p = d->tgt_normals;
+                    const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && nrm_p) ? __ldg(nrm_p + ti) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    Mat3 cs, ct;
+                    if (REG == SPX_REG_GICP) cs = load_mat(d->src_cm, i);
+                    if (REG == SPX_REG_GICP || REG == SPX_REG_POINT_TO_DISTRIBUTION) ct = load_mat(d->tgt_cm, (size_t)ti);
+                    accumulate_point<REG>(T, ps, cs, pt, ct, nrm, a.loss, __ldg(&d->scale), acc);
+                    inl = 1;
+                }
+            }
+            for (int v = 0; v < N_ACC; ++v) {
+                const float s = warp_sum(acc[v]);
+                if (lane == 0) red[warp][v] = s;
+            }
+            {
+                const unsigned c1 = __popc(__ballot_sync(FULL, inl != 0));
+                if (lane == 0) red[warp][31] = __uint_as_float(c1);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                double s = 0.0;
+                if (threadIdx.x < N_ACC) {
+                    for (int w = 0; w < LIN_WARPS; ++w) s += (double)red[w][threadIdx.x];
+                } else if (threadIdx.x == S_INL) {
+                    for (int w = 0; w < LIN_WARPS; ++w) s += (double)__float_as_uint(red[w][31]);
+                }
+                __stcg(part + (size_t)c * 32 + threadIdx.x, s);
+            }
+            __syncthreads();
+        }
+        __threadfence();
+        phase_mark(a.phase, it, PH_PART);
+        grid.sync();
+        phase_mark(a.phase, it, PH_SYNC);
+        // ---- 4. fold a pair's rows in chunk order, solve, advance its pose
+        if (single) {
+            const PairDesc* d = a.pairs;
+            {
+                const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
+                double s = 0.0;
+                for (uint32_t b = slice; b < a.total_chunks; b += LIN_WARPS) s += __ldcg(part + (size_t)b * 32 + v);
+                fold[slice][v] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                double t = 0.0;
+                for (int w = 0; w < LIN_WARPS; ++w) t += fold[w][threadIdx.x];
+                fold[0][threadIdx.x] = t;
+            }
+            __syncthreads();
+            phase_mark(a.phase, it, PH_FOLD);
+            if (threadIdx.x == 0)
+                gn_update(&st1, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, it, blockIdx.x == 0 ? d->trace : nullptr);
+            __syncthreads();
+            phase_mark(a.phase, it, PH_SOLVE);
+            if (st1.stop) break;
+        } else {
+            for (uint32_t p = blockIdx.x; p < a.n_pairs; p += gridDim.x) {
+                const PairDesc* d = a.pairs + p;
+                RegState* st = d->state;
+                if (st->stop) continue;  // written by this block only
+                const uint32_t c0 = __ldg(&d->chunk0), nc = __ldg(&d->nchunks);
+                {
+                    const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
+                    double s = 0.0;
+                    for (uint32_t b = slice; b < nc; b += LIN_WARPS) s += __ldcg(part + (size_t)(c0 + b) * 32 + v);
+                    fold[slice][v] = s;
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    double t = 0.0;
+                    for (int w = 0; w < LIN_WARPS; ++w) t += fold[w][threadIdx.x];
+                    fold[0][threadIdx.x] = t;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) gn_update(st, &fold[0][0], a.lambda, a.crit_rot, a.crit_trans, it, d->trace);
+                __syncthreads();
+            }
+            __threadfence();
+            phase_mark(a.phase, it, PH_FOLD);
+            grid.sync();
+            phase_mark(a.phase, it, PH_SOLVE);
+            int active = 0;
+            for (uint32_t p = threadIdx.x; p < a.n_pairs; p += LIN_THREADS)
+                active |= !__ldcg(&a.pairs[p].state->stop);
+            if (!__syncthreads_or(active)) break;
+        }
+    }
+    if (single && blockIdx.x == 0 && threadIdx.x == 0) *a.pairs[0].state = st1;
+}
+
 // error-only pass with frozen neighbours — registration.hpp:678-777; WEIGHTS: per-point robust
 // weights instead of the sum (registration.hpp:412-462)
 template <int REG, bool WEIGHTS>
@@ -875,6 +1146,54 @@ __global__ void __launch_bounds__(128) align_prepare_kernel(PrepArgs p) {
     }
     const Mat3 raw = cov16 ? load_cov16(cov16 + (size_t)i * 16) : mat3_identity();
     store_mat(cm, i, invert ? mat3_inverse(raw) : plane_regularize(raw));  // invert: point-to-distribution
+}
+
+// set-up of the batched align: per pair, the pose-independent matrices of both clouds, the optimiser state and
+// the pair's row of the descriptor table; block (0, 0) also zeroes the work-list counters.  P = 1 receives its
+// PairPrep as a kernel parameter (no H2D copy in front of the align: DESIGN.md §3 K-prep), P > 1 reads a table.
+struct PairPrep {
+    const float* src_cov16;
+    const float* tgt_cov16;
+    uint32_t n_src_m;  // source matrices to prepare (0: none)
+    uint32_t n_tgt_m;  // target matrices to prepare
+    float4* src_cm;
+    float4* tgt_cm;
+    int invert_tgt;
+    int pad;
+    Xform T;
+    PairDesc desc;
+};
+__global__ void __launch_bounds__(128) align_prepare_batch_kernel(const PairPrep* __restrict__ table, const PairPrep one,
+                                                                  PairDesc* descs, uint32_t* chunk_end,
+                                                                  unsigned int* wl_counters) {
+    const PairPrep& pp = table ? table[blockIdx.y] : one;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        RegState s;
+        memset(&s, 0, sizeof(s));
+        const float4 r[4] = {pp.T.r0, pp.T.r1, pp.T.r2, pp.T.r3};
+        for (int i = 0; i < 4; ++i) {
+            s.T[i][0] = r[i].x; s.T[i][1] = r[i].y; s.T[i][2] = r[i].z; s.T[i][3] = r[i].w;
+        }
+        s.error = FLT_MAX;
+        *pp.desc.state = s;
+        descs[blockIdx.y] = pp.desc;
+        chunk_end[blockIdx.y] = pp.desc.chunk0 + pp.desc.nchunks;
+        if (blockIdx.y == 0)
+            for (int i = 0; i < 4; ++i) wl_counters[i] = 0u;
+    }
+    uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    const float* cov16 = pp.src_cov16;
+    float4* cm = pp.src_cm;
+    bool invert = false;
+    if (i >= pp.n_src_m) {
+        i -= pp.n_src_m;
+        if (i >= pp.n_tgt_m) return;
+        cov16 = pp.tgt_cov16;
+        cm = pp.tgt_cm;
+        invert = pp.invert_tgt != 0;
+    }
+    const Mat3 raw = cov16 ? load_cov16(cov16 + (size_t)i * 16) : mat3_identity();
+    store_mat(cm, i, invert ? mat3_inverse(raw) : plane_regularize(raw));
 }
 
 template <int REG, int MODE, bool SOLVE>
@@ -976,6 +1295,17 @@ struct spx_registration_s {
     size_t src_cap = 0;
     float4* tgt_cm = nullptr;
     size_t tgt_cap = 0;
+    // batched Gauss-Newton align (P = 1: the single-pair path)
+    RegState* states = nullptr;   // [pairs_cap] (P > 1; P = 1 uses `state`)
+    PairDesc* descs = nullptr;    // [pairs_cap]
+    uint32_t* chunk_end = nullptr;
+    PairPrep* preps = nullptr;    // [pairs_cap] device copy of the set-up table
+    size_t pairs_cap = 0;
+    float4* wl_q = nullptr;       // [wl_cap]
+    float4* wl_b = nullptr;
+    size_t wl_cap = 0;
+    double* cpartials = nullptr;  // [2][cpart_cap][32]
+    size_t cpart_cap = 0;
     float* trace = nullptr;
     size_t trace_cap = 0;
     size_t nn_n = 0;
@@ -1003,7 +1333,7 @@ void reg_free(spx_registration_t r) {
         p = nullptr;
     };
     f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist); f(r->nn_pos); f(r->worklist); f(r->wl_counters);
-    f(r->src_cm); f(r->tgt_cm); f(r->trace); f(r->phase);
+    f(r->src_cm); f(r->tgt_cm); f(r->states); f(r->descs); f(r->chunk_end); f(r->preps); f(r->wl_q); f(r->wl_b); f(r->cpartials); f(r->trace); f(r->phase);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     r->ev0 = r->ev1 = nullptr;
@@ -1316,6 +1646,252 @@ void launch_align_gn(int reg_type, LinArgs& a, int max_it, spx_queue_t q, spx_re
     SPX_LAUNCH_CHECK();
 }
 
+template <int REG>
+unsigned batch_coop_blocks(int device_sm_count) {
+    static int per_sm = 0;
+    if (per_sm == 0)
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_batch_kernel<REG>, LIN_THREADS, 0));
+    return (unsigned)std::max(per_sm, 1) * (unsigned)device_sm_count;
+}
+
+template <typename T>
+void ensure_n(T*& p, size_t& cap, size_t need, size_t elems_per, cudaStream_t st) {
+    if (need <= cap && p) return;
+    if (p) {
+        SPX_CUDA(cudaStreamSynchronize(st));
+        SPX_CUDA(cudaFree(p));
+        p = nullptr;
+    }
+    const size_t c = std::max<size_t>(need + need / 8, 1024);
+    SPX_CUDA(cudaMalloc(&p, c * elems_per * sizeof(T)));
+    cap = c;
+}
+
+// Gauss-Newton align of P pairs in one cooperative launch (align_batch_kernel).  `pairs` are host structs;
+// results[p] receives pair p's RegistrationResult.  T_trace_host: P == 1 only.  Synchronises once.
+void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs, spx_registration_result* results,
+                    float* T_trace_host) {
+    spx_queue_t q = r->q;
+    cudaStream_t st = q->stream;
+    const spx_registration_params& Pm = r->P;
+    check_reg_loss(Pm.reg_type, Pm.robust_loss, "[Registration::align]");
+    int loss = Pm.robust_loss;
+    if (loss != SPX_LOSS_NONE && Pm.robust_default_scale <= 0.0f) loss = SPX_LOSS_NONE;  // registration.hpp:186-192
+    const bool gicp = Pm.reg_type == SPX_REG_GICP, p2d = Pm.reg_type == SPX_REG_POINT_TO_DISTRIBUTION;
+    const int max_it = Pm.max_iterations;
+    static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+
+    // RegistrationResult defaults — result.hpp:16-25; pairs with an empty source stay at them (registration.hpp:209-211)
+    size_t total_ns = 0, total_nt = 0, total_chunks = 0, n_active = 0;
+    for (size_t p = 0; p < P; ++p) {
+        const spx_align_pair& A = pairs[p];
+        spx_registration_result* R = results + p;
+        std::memset(R, 0, sizeof(*R));
+        const float* T0 = A.T_init_host ? A.T_init_host : I16;
+        std::memcpy(R->T, T0, 64);
+        R->error = FLT_MAX;
+        R->error_raw = FLT_MAX;
+        if (A.ns == 0) continue;
+        SPX_REQUIRE(A.src_points && (A.tgt_points || A.nt == 0), "[Registration::align] null points");
+        SPX_REQUIRE(A.target_index, "[Registration::align] target_knn (spx_index) is null");
+        SPX_REQUIRE(A.target_index->q->device == q->device, "[Registration::align] index lives on another device");
+        SPX_REQUIRE(A.target_index->n_total == A.nt, "[Registration::align] target_knn was built on a different cloud size");
+        SPX_REQUIRE(A.ns < (1ull << 31) && A.nt < (1ull << 31), "[Registration::align] too many points");
+        validate(Pm, A.src_covs, A.tgt_covs, A.tgt_normals);
+        SPX_REQUIRE(!(Pm.reg_type == SPX_REG_POINT_TO_PLANE && !A.tgt_normals) || P == 1,
+                    "[Registration::align_batch] Point-to-Plane needs target normals");
+        total_ns += A.ns;
+        total_nt += A.nt;
+        total_chunks += (size_t)div_up(A.ns, CHUNK);
+        ++n_active;
+    }
+    r->timed = false;
+    r->nn_n = P == 1 ? pairs[0].ns : 0;
+    if (n_active == 0 || max_it <= 0) return;
+    SPX_REQUIRE(total_chunks < (1ull << 31), "[Registration::align_batch] too many points in one batch");
+
+    // scratch
+    {
+        size_t cap = r->nn_cap;
+        ensure(r->nn_idx, cap, total_ns, st);
+        cap = r->nn_cap;
+        ensure(r->nn_pos, cap, total_ns, st);
+        cap = r->nn_cap;
+        ensure(r->worklist, cap, total_ns, st);
+        ensure(r->nn_dist, r->nn_cap, total_ns, st);
+        cap = r->wl_cap;
+        ensure_n(r->wl_q, cap, total_ns, 1, st);
+        ensure_n(r->wl_b, r->wl_cap, total_ns, 1, st);
+        ensure_n(r->cpartials, r->cpart_cap, total_chunks, 64, st);
+        if (gicp) ensure3(r->src_cm, r->src_cap, total_ns, st);
+        if (gicp || p2d) ensure3(r->tgt_cm, r->tgt_cap, total_nt, st);
+        if (n_active > r->pairs_cap) {
+            SPX_CUDA(cudaStreamSynchronize(st));
+            if (r->states) SPX_CUDA(cudaFree(r->states));
+            if (r->descs) SPX_CUDA(cudaFree(r->descs));
+            if (r->chunk_end) SPX_CUDA(cudaFree(r->chunk_end));
+            if (r->preps) SPX_CUDA(cudaFree(r->preps));
+            r->states = nullptr; r->descs = nullptr; r->chunk_end = nullptr; r->preps = nullptr;
+            const size_t c = std::max<size_t>(n_active, 8);
+            SPX_CUDA(cudaMalloc(&r->states, c * sizeof(RegState)));
+            SPX_CUDA(cudaMalloc(&r->descs, c * sizeof(PairDesc)));
+            SPX_CUDA(cudaMalloc(&r->chunk_end, c * sizeof(uint32_t)));
+            SPX_CUDA(cudaMalloc(&r->preps, c * sizeof(PairPrep)));
+            r->pairs_cap = c;
+        }
+        if (T_trace_host && P == 1) {
+            size_t tcap = r->trace_cap;
+            ensure(r->trace, tcap, (size_t)std::max(max_it, 1) * 16, st);
+            r->trace_cap = tcap;
+        }
+    }
+    float4* derived_normals = nullptr;
+    // the set-up table (pinned staging for P > 1)
+    std::vector<PairPrep> table(n_active);
+    std::vector<size_t> slot_of(n_active);
+    size_t so = 0, to = 0, co = 0, k = 0;
+    unsigned prep_blocks = 1;
+    for (size_t p = 0; p < P; ++p) {
+        const spx_align_pair& A = pairs[p];
+        if (A.ns == 0) continue;
+        PairPrep& pp = table[k];
+        std::memset(&pp, 0, sizeof(pp));
+        slot_of[k] = p;
+        pp.src_cov16 = A.src_covs;
+        pp.tgt_cov16 = A.tgt_covs;
+        pp.n_src_m = gicp ? (uint32_t)A.ns : 0u;
+        pp.n_tgt_m = (gicp || p2d) ? (uint32_t)A.nt : 0u;
+        pp.src_cm = gicp ? r->src_cm + 3 * so : nullptr;
+        pp.tgt_cm = (gicp || p2d) ? r->tgt_cm + 3 * to : nullptr;
+        pp.invert_tgt = p2d ? 1 : 0;
+        pp.T = xform_from_colmajor(A.T_init_host ? A.T_init_host : I16);
+        PairDesc& d = pp.desc;
+        d.src_pts = reinterpret_cast<const float4*>(A.src_points);
+        d.src_cm = pp.src_cm;
+        d.tgt_pts = reinterpret_cast<const float4*>(A.tgt_points);
+        d.tgt_cm = pp.tgt_cm;
+        d.tgt_normals = reinterpret_cast<const float4*>(A.tgt_normals);
+        if (Pm.reg_type == SPX_REG_POINT_TO_PLANE && !A.tgt_normals) {
+            // registration.hpp:139-141: normals derived from the pre-computed covariances (P == 1 only, checked above)
+            fprintf(stdout, "[Caution] Normal vectors for Point-to-Plane ICP are not provided. \n"
+                            "          Attempting to derive them from pre-computed covariance matrices.\n");
+            SPX_CUDA(cudaMalloc(&derived_normals, std::max<size_t>(A.nt, 1) * sizeof(float4)));
+            if (spx_normals_from_covs(q, A.tgt_points, A.tgt_covs, A.nt, reinterpret_cast<float*>(derived_normals)) != SPX_OK) {
+                cudaFree(derived_normals);
+                throw Error(SPX_ERR_INTERNAL, spx_last_error());
+            }
+            d.tgt_normals = derived_normals;
+        }
+        d.idx = r->nn_idx + so;
+        d.dist = r->nn_dist + so;
+        d.pos = r->nn_pos + so;
+        d.state = (P == 1) ? r->state : r->states + k;
+        d.trace = (P == 1 && T_trace_host) ? r->trace : nullptr;
+        d.ns = (uint32_t)A.ns;
+        d.chunk0 = (uint32_t)co;
+        d.nchunks = (uint32_t)div_up(A.ns, CHUNK);
+        d.scale = A.robust_scale > 0.0f ? A.robust_scale : Pm.robust_default_scale;  // registration.hpp:217-218
+        d.grid = A.target_index->levels;
+        prep_blocks = std::max(prep_blocks, (unsigned)div_up((size_t)pp.n_src_m + pp.n_tgt_m, 128));
+        so += A.ns;
+        to += A.nt;
+        co += d.nchunks;
+        ++k;
+    }
+    auto free_normals = [&] {
+        if (derived_normals) {
+            cudaStreamSynchronize(st);
+            cudaFree(derived_normals);
+        }
+    };
+    try {
+        if (r->phase) SPX_CUDA(cudaMemsetAsync(r->phase, 0, PH_WORDS * sizeof(unsigned long long), st));
+        if (n_active == 1) {
+            align_prepare_batch_kernel<<<dim3(prep_blocks, 1), 128, 0, st>>>(nullptr, table[0], r->descs, r->chunk_end,
+                                                                            r->wl_counters);
+        } else {
+            PairPrep* pin = static_cast<PairPrep*>(q->pinned_get(n_active * sizeof(PairPrep) + n_active * sizeof(RegState)));
+            std::memcpy(pin, table.data(), n_active * sizeof(PairPrep));
+            SPX_CUDA(cudaMemcpyAsync(r->preps, pin, n_active * sizeof(PairPrep), cudaMemcpyHostToDevice, st));
+            align_prepare_batch_kernel<<<dim3(prep_blocks, (unsigned)n_active), 128, 0, st>>>(r->preps, table[0], r->descs,
+                                                                                             r->chunk_end, r->wl_counters);
+        }
+        SPX_LAUNCH_CHECK();
+
+        BatchArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.pairs = r->descs;
+        a.chunk_end = r->chunk_end;
+        a.n_pairs = (uint32_t)n_active;
+        a.total_chunks = (uint32_t)total_chunks;
+        a.wl_q = r->wl_q;
+        a.wl_b = r->wl_b;
+        a.wl_counters = r->wl_counters;
+        a.partials = r->cpartials;
+        a.max_corr = Pm.max_correspondence_distance;
+        a.max_corr_sq = Pm.max_correspondence_distance * Pm.max_correspondence_distance;
+        a.loss = loss;
+        a.lambda = Pm.gn_lambda;
+        a.crit_rot = Pm.criteria_rotation;
+        a.crit_trans = Pm.criteria_translation;
+        a.phase = r->phase;
+        unsigned resident;
+        const void* fn;
+        switch (Pm.reg_type) {
+            case SPX_REG_POINT_TO_POINT:
+                resident = batch_coop_blocks<SPX_REG_POINT_TO_POINT>(q->sm_count);
+                fn = (const void*)align_batch_kernel<SPX_REG_POINT_TO_POINT>;
+                break;
+            case SPX_REG_POINT_TO_PLANE:
+                resident = batch_coop_blocks<SPX_REG_POINT_TO_PLANE>(q->sm_count);
+                fn = (const void*)align_batch_kernel<SPX_REG_POINT_TO_PLANE>;
+                break;
+            case SPX_REG_POINT_TO_DISTRIBUTION:
+                resident = batch_coop_blocks<SPX_REG_POINT_TO_DISTRIBUTION>(q->sm_count);
+                fn = (const void*)align_batch_kernel<SPX_REG_POINT_TO_DISTRIBUTION>;
+                break;
+            default:
+                resident = batch_coop_blocks<SPX_REG_GICP>(q->sm_count);
+                fn = (const void*)align_batch_kernel<SPX_REG_GICP>;
+                break;
+        }
+        unsigned blocks = std::max(1u, std::min((unsigned)total_chunks, resident));
+        // reserved[0] = cap on the persistent grid (0 = one full wave): lets several aligns share one GPU
+        if (Pm.reserved[0] > 0) blocks = std::min(blocks, (unsigned)Pm.reserved[0]);
+        int mi = max_it;
+        void* args[] = {(void*)&a, (void*)&mi};
+        SPX_CUDA(cudaEventRecord(r->ev0, st));
+        SPX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(LIN_THREADS), args, 0, st));
+        SPX_LAUNCH_CHECK();
+        SPX_CUDA(cudaEventRecord(r->ev1, st));
+
+        RegState* hs = static_cast<RegState*>(q->pinned_get(n_active * sizeof(PairPrep) + n_active * sizeof(RegState)));
+        if (n_active > 1) hs = reinterpret_cast<RegState*>(reinterpret_cast<char*>(hs) + n_active * sizeof(PairPrep));
+        SPX_CUDA(cudaMemcpyAsync(hs, P == 1 ? r->state : r->states, n_active * sizeof(RegState), cudaMemcpyDeviceToHost, st));
+        q->sync();
+        int most = 0;
+        for (size_t j = 0; j < n_active; ++j) {
+            fill_result(hs[j], results + slot_of[j]);
+            most = std::max(most, hs[j].iterations + 1);
+        }
+        r->timed = true;
+        r->last_launches = 1;
+        r->last_iterations = most;
+        if (T_trace_host && P == 1) {
+            // iterations never run (converged earlier) repeat the final pose
+            SPX_CUDA(cudaMemcpyAsync(T_trace_host, r->trace, (size_t)(hs[0].iterations + 1) * 16 * sizeof(float),
+                                     cudaMemcpyDeviceToHost, st));
+            q->sync();
+            for (int it = hs[0].iterations + 1; it < max_it; ++it)
+                std::memcpy(T_trace_host + (size_t)it * 16, T_trace_host + (size_t)hs[0].iterations * 16, 64);
+        }
+    } catch (...) {
+        free_normals();
+        throw;
+    }
+    free_normals();
+}
+
 // generic (caller-supplied correspondences) argument block for spx_linearize / spx_error / weights
 LinArgs generic_args(spx_queue_t q, int loss, const float* src_points, const float* src_covs, size_t ns,
                      const float* tgt_points, const float* tgt_covs, const float* tgt_normals, const int32_t* nn_idx,
@@ -1580,6 +2156,21 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         R->error_raw = FLT_MAX;
         if (ns == 0) return;  // registration.hpp:209-211
         SPX_REQUIRE(src_points && (tgt_points || nt == 0), "[Registration::align] null points");
+        {
+            size_t split_min = 400000;
+            if (const char* e = std::getenv("SPX_SPLIT_MIN")) split_min = (size_t)std::atoll(e);  // tuning aid
+            if (P.optimization_method == SPX_OPT_GAUSS_NEWTON && ns < split_min) {
+                // the cooperative one-launch path: the batched kernel with one pair
+                spx_align_pair one{};
+                one.src_points = src_points; one.src_covs = src_covs; one.ns = ns;
+                one.tgt_points = tgt_points; one.tgt_covs = tgt_covs; one.tgt_normals = tgt_normals; one.nt = nt;
+                one.target_index = target_index;
+                one.T_init_host = T_init_host;
+                one.robust_scale = robust_scale;
+                gn_align_batch(reg, 1, &one, R, T_trace_host);
+                return;
+            }
+        }
         AlignCtx c = align_setup(reg, src_points, src_covs, ns, tgt_points, tgt_covs, tgt_normals, nt, target_index,
                                  T_init_host, robust_scale, &derived_normals);
         LinArgs& a = c.a;
@@ -1597,10 +2188,8 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
             const bool split = ns >= split_min;
             int launches = 0;
             SPX_CUDA(cudaEventRecord(reg->ev0, st));
-            if (max_it > 0 && !split) {
-                launch_align_gn<false>(c.reg, a, max_it, q, reg);
-                launches = 1;
-            } else if (max_it > 0) {
+            if (max_it > 0) {  // split kernels (large clouds); smaller ones took the batched kernel above
+                (void)split;
                 constexpr int SPLIT_POLL = 4;
                 LinArgs f = a;  // factor pass: correspondences given, fused solve
                 f.idx_in = reg->nn_idx;
@@ -1753,6 +2342,26 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         cudaFree(derived_normals);
     }
     return rc;
+}
+
+int spx_registration_align_batch(spx_registration_t reg, size_t n_pairs, const spx_align_pair* pairs_host,
+                                 spx_registration_result* results_host) {
+    return guard([&] {
+        SPX_REQUIRE(reg && (n_pairs == 0 || (pairs_host && results_host)), "[Registration::align_batch] null argument");
+        if (n_pairs == 0) return;
+        DeviceGuard g(reg->q->device);
+        if (reg->P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
+            gn_align_batch(reg, n_pairs, pairs_host, results_host, nullptr);
+            return;
+        }
+        // LM / dog-leg take host decisions per trial step: one pair after the other
+        for (size_t p = 0; p < n_pairs; ++p) {
+            const spx_align_pair& A = pairs_host[p];
+            const int rc = spx_registration_align(reg, A.src_points, A.src_covs, A.ns, A.tgt_points, A.tgt_covs, A.tgt_normals,
+                                                  A.nt, A.target_index, A.T_init_host, A.robust_scale, results_host + p, nullptr);
+            if (rc != SPX_OK) throw Error(rc, spx_last_error());
+        }
+    });
 }
 
 // ------------------------------------------------------------------ sharded building blocks

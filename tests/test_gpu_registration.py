@@ -529,3 +529,81 @@ def test_config2_full_size_pipeline_matches_oracle(spx, q):
     dt, da = pose_delta(ores["T"], res.T)
     assert dt < 1e-5 and da < 1e-5, (dt, da)
     assert res.iterations == ores["iterations"] and res.inlier == ores["inlier"]
+
+
+# ---- batched align (BASELINE config 5 building block): one launch for P pairs
+@pytest.mark.parametrize("reg", ["GICP", "POINT_TO_PLANE", "POINT_TO_POINT", "POINT_TO_DISTRIBUTION"])
+def test_align_batch_equals_single_bit_for_bit(spx, q, pair, reg):
+    """spx_registration_align_batch: every pair's result is bit for bit the single-pair result (the
+    per-pair sums are folded in chunk order, independent of the batch and of the grid), for pairs of
+    different sizes, different initial guesses and different iteration counts, incl. an empty source."""
+    rs = np.random.RandomState(11)
+    tgt, cov_t = clouds_for(spx, q, pair, reg)
+    src_h, cov_s = pair["src_h"], pair["cov_s"]
+    params = spx.RegistrationParams(reg_type=spx.RegType[reg])
+    params.robust.type = spx.RobustLossType.HUBER
+    params.robust.default_scale = 1.0
+    reg_obj = spx.Registration(q, params)
+    pairs = []
+    for j, n in enumerate([len(src_h), 3000, 257, 256, 1, 0, 4500, 1000]):
+        sel = np.sort(rs.choice(len(src_h), n, replace=False)) if n else np.zeros(0, np.int64)
+        s = spx.PointCloudShared(q, src_h[sel], cov_s[sel]) if n else spx.PointCloudShared(q, np.zeros((0, 4), np.float32))
+        T0 = oracle.se3_exp(rs.normal(0, [0.005, 0.005, 0.005, 0.05, 0.05, 0.02]).astype(np.float32)) if j % 2 else None
+        pairs.append((s, tgt, pair["tree"], T0))
+    batch = reg_obj.align_batch(pairs)
+    singles = [reg_obj.align(s, t, k, T0) for s, t, k, T0 in pairs]
+    its = set()
+    for b, s1 in zip(batch, singles):
+        assert np.array_equal(b.T, s1.T) and b.iterations == s1.iterations and b.converged == s1.converged
+        assert np.array_equal(b.H, s1.H) and np.array_equal(b.b, s1.b) and b.error == s1.error and b.inlier == s1.inlier
+        its.add(b.iterations)
+    assert len(its) > 1  # the batch really mixes pairs that stop at different iterations
+    # and the first pair (the whole cloud) against the oracle
+    P = oracle.default_params(reg_type=oracle.REG[reg], loss=1, robust_default_scale=1.0)
+    ores = oracle.align(P, src_h, cov_s, pair["tgt_h"], cov_t, pair["nrm_t"], pair["otree"])
+    dt, da = pose_delta(ores["T"], batch[0].T)
+    assert dt < 1e-5 and da < 1e-5 and batch[0].iterations == ores["iterations"]
+
+
+def test_align_batch_64_pairs_of_60k(spx, q):
+    """config-5 shape: 64 pairs of ~60 k points (voxelised synthetic scans, 4 distinct scenes x 16 random
+    motions), GICP: the batch equals the single-pair path bit for bit and three of them are checked against the
+    oracle at 1e-5."""
+    import synthetic
+    rs = np.random.RandomState(5)
+    vg = spx.VoxelGrid(q, 0.25)
+    scenes = []
+    for seed in range(4):
+        tgt_raw, _, _ = synthetic.kitti_pair(100 + seed, sweeps=8)
+        tgt = vg.downsampling(spx.PointCloudShared(q, tgt_raw))
+        tree = spx.KDTree.build(q, tgt)
+        spx.covariance.estimate(tree.knn_search(tgt, 10), tgt)
+        scenes.append((tgt, tree, tgt_raw))
+    pairs, keep = [], []
+    for j in range(64):
+        tgt, tree, tgt_raw = scenes[j % 4]
+        T_gt = synthetic.random_pose(rs, 0.6, 1.0).astype(np.float32)
+        src_raw = oracle.transform_points(np.linalg.inv(T_gt), tgt_raw[rs.rand(len(tgt_raw)) < 0.9])
+        src = vg.downsampling(spx.PointCloudShared(q, src_raw))
+        ts = spx.KDTree.build(q, src)
+        spx.covariance.estimate(ts.knn_search(src, 10), src)
+        ts.close()
+        pairs.append((src, tgt, tree, None))
+        keep.append(T_gt)
+    assert 40_000 < pairs[0][0].size() < 80_000
+    params = spx.RegistrationParams()
+    params.robust.type = spx.RobustLossType.HUBER
+    reg_obj = spx.Registration(q, params)
+    batch = reg_obj.align_batch(pairs)
+    for j in (0, 17, 63):
+        s1 = reg_obj.align(*pairs[j])
+        assert np.array_equal(batch[j].T, s1.T) and batch[j].iterations == s1.iterations and batch[j].inlier == s1.inlier
+        src, tgt, _, _ = pairs[j]
+        P = oracle.default_params(reg_type=3, loss=1)
+        ores = oracle.align(P, src.points_host(), src.covs_host(), tgt.points_host(), tgt.covs_host(), None,
+                            oracle.KDTree(tgt.points_host()))
+        dt, da = pose_delta(ores["T"], batch[j].T)
+        assert dt < 1e-5 and da < 1e-5 and batch[j].iterations == ores["iterations"], (j, dt, da)
+    for j, r in enumerate(batch):
+        dt, da = pose_delta(keep[j], r.T)
+        assert r.converged and dt < 0.05, (j, dt)
