@@ -240,6 +240,12 @@ SPX_API int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_
 SPX_API int spx_box_filter(spx_queue_t q, const float* points, size_t n, float min_distance, float max_distance,
                    float* out_points, size_t* m_host);
 
+/* The same filter returning the KEPT INDICES (ascending, device int32[<= n]) instead of the points: what
+ * common/filter_by_flags.hpp:29-57 applies to every attribute the cloud carries (covariances, normals, rgb,
+ * intensities, timestamp offsets) — run each through spx_gather.  Synchronises. */
+SPX_API int spx_box_filter_indices(spx_queue_t q, const float* points, size_t n, float min_distance, float max_distance,
+                           int32_t* idx_out, size_t* m_host);
+
 /* PreprocessFilter::random_sampling(source, output, n) — preprocess_operator/random_sampling_operator.hpp:15-58:
  * partial Fisher-Yates over 0..n-1 with a persistent std::mt19937 (seed 1234) and
  * std::uniform_int_distribution<size_t>(i, n-1) (libstdc++), then ORDER-PRESERVING compaction.
@@ -321,6 +327,30 @@ typedef struct spx_align_pair {
 } spx_align_pair;
 SPX_API int spx_registration_align_batch(spx_registration_t reg, size_t n_pairs, const spx_align_pair* pairs_host,
                                  spx_registration_result* results_host);
+/* spx_align_batch — SURVEY.md §8(b), BASELINE config 5 ("batched odometry: independent scan pairs: voxel
+ * downsample + covariance + GICP"): n_pairs RAW scan pairs to registration results in one call.  Per cloud:
+ * VoxelGrid::downsampling(voxel_size) -> KDTree::build -> knn_search(k) -> covariance::estimate
+ * (voxel_downsampling.hpp:50-79, kdtree.hpp:165-224, covariance.hpp:260-311), spread over `lanes` internal queues
+ * (streams) driven by as many host threads; then ONE batched Registration::align for all pairs
+ * (spx_registration_align_batch).  A cloud that appears in several pairs (same pointer and size) is processed once.
+ * lanes <= 0: SPX_BATCH_LANES or 8.  Results are bit for bit those of the single-pair entry points.
+ * n_src_out / n_tgt_out (nullable, HOST uint32[n_pairs]): points after the voxel grid.  Synchronises. */
+typedef struct spx_batch_s* spx_batch_t;
+typedef struct spx_scan_pair {
+    const float* src_raw; /* device float[n_src][4] */
+    size_t n_src;
+    const float* tgt_raw;
+    size_t n_tgt;
+    const float* T_init_host; /* 16 floats column-major, NULL = identity */
+} spx_scan_pair;
+SPX_API int spx_batch_create(spx_queue_t q, const spx_registration_params* params, float voxel_size, int k_correspondences,
+                     int lanes, spx_batch_t* out);
+SPX_API int spx_batch_destroy(spx_batch_t batch);
+SPX_API int spx_batch_set_params(spx_batch_t batch, const spx_registration_params* params);
+SPX_API int spx_align_batch(spx_batch_t batch, size_t n_pairs, const spx_scan_pair* pairs_host,
+                    spx_registration_result* results_host, uint32_t* n_src_out, uint32_t* n_tgt_out);
+/* CUDA-event time of the batched align kernel of the last spx_align_batch and the most iterations any pair ran */
+SPX_API int spx_batch_last_timing(spx_batch_t batch, float* align_ms, int32_t* iterations);
 /* CUDA-event time of the iteration kernels of the last align on this handle (from just before the
  * first iteration launch to just after the last), the number of iteration kernels launched and
  * the number of outer iterations that did work: bench.py's live per-launch duration. */

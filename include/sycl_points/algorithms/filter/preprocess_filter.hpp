@@ -34,8 +34,8 @@ public:
                     float max_distance = std::numeric_limits<float>::max()) {
         this->box_filter(data, data, min_distance, max_distance);
     }
-    /// keep points whose L-infinity range lies in [min_distance, max_distance]; attributes other
-    /// than the points are dropped (the path filters raw scans, which carry none it needs)
+    /// keep points whose L-infinity range lies in [min_distance, max_distance]; every attribute the cloud
+    /// carries is compacted with them (common/filter_by_flags.hpp:29-57), in source order
     void box_filter(const PointCloudShared& source, PointCloudShared& output, float min_distance = 1.0f,
                     float max_distance = std::numeric_limits<float>::max()) {
         const size_t N = source.size();
@@ -43,19 +43,13 @@ public:
             if (&source != &output) output.clear();
             return;
         }
-        PointContainerShared out(N);
+        shared_vector<int32_t> idx(N);
         this->queue_.set_accessed_by_device(source.points_ptr(), N);
-        this->queue_.set_accessed_by_device(out.data(), N);
+        this->queue_.set_accessed_by_device(idx.data(), N);
         size_t m = 0;
-        detail::spx_check(spx_box_filter(this->queue_.handle(), reinterpret_cast<const float*>(source.points_ptr()), N,
-                                         min_distance, max_distance, reinterpret_cast<float*>(out.data()), &m));
-        out.resize(m);
-        output.points->swap(out);
-        output.covs->clear();
-        output.normals->clear();
-        output.rgb->clear();
-        output.intensities->clear();
-        output.timestamp_offsets->clear();
+        detail::spx_check(spx_box_filter_indices(this->queue_.handle(), reinterpret_cast<const float*>(source.points_ptr()),
+                                                 N, min_distance, max_distance, idx.data(), &m));
+        this->gather_all(source, output, idx, m);
     }
 
     /// in place
@@ -64,8 +58,7 @@ public:
         this->random_sampling(data, out, sampling_num);
         data = out;
     }
-    /// partial Fisher-Yates with the persistent mt19937, order-preserving compaction of points,
-    /// covariances, normals and intensities
+    /// partial Fisher-Yates with the persistent mt19937, order-preserving compaction of every attribute
     void random_sampling(const PointCloudShared& source, PointCloudShared& output, size_t sampling_num) {
         const size_t N = source.size();
         if (N <= sampling_num) {  // keep everything (random_sampling_operator.hpp:26-30)
@@ -76,23 +69,32 @@ public:
         this->queue_.set_accessed_by_device(idx.data(), sampling_num);
         size_t m = 0;
         detail::spx_check(spx_random_sampling(this->queue_.handle(), rng_, N, sampling_num, idx.data(), &m));
+        this->gather_all(source, output, idx, m);
+    }
+
+private:
+    /// order-preserving compaction of every per-point attribute through the kept indices
+    void gather_all(const PointCloudShared& source, PointCloudShared& output, const shared_vector<int32_t>& idx, size_t m) {
         PointCloudShared out(this->queue_);
         gather(*source.points, *out.points, idx, m, true);
         gather(*source.covs, *out.covs, idx, m, source.has_cov());
         gather(*source.normals, *out.normals, idx, m, source.has_normal());
+        gather(*source.rgb, *out.rgb, idx, m, source.has_rgb());
         gather(*source.intensities, *out.intensities, idx, m, source.has_intensity());
+        gather(*source.timestamp_offsets, *out.timestamp_offsets, idx, m, source.has_timestamps());
         detail::spx_check(spx_queue_sync(this->queue_.handle()));
         out.start_time_ms = source.start_time_ms;
         out.end_time_ms = source.end_time_ms;
         output.points.swap(out.points);
         output.covs.swap(out.covs);
         output.normals.swap(out.normals);
+        output.rgb.swap(out.rgb);
         output.intensities.swap(out.intensities);
-        output.rgb->clear();
-        output.timestamp_offsets->clear();
+        output.timestamp_offsets.swap(out.timestamp_offsets);
+        output.start_time_ms = out.start_time_ms;
+        output.end_time_ms = out.end_time_ms;
     }
 
-private:
     template <typename V>
     void gather(const V& src, V& dst, const shared_vector<int32_t>& idx, size_t m, bool enable) const {
         dst.resize(enable ? m : 0);

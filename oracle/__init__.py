@@ -28,6 +28,36 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+def use_fast_build() -> str:
+    """Switch this process to the timing build (-O3 -march=native, oracle/Makefile `fast`): bench.py's
+    CPU-baseline legs only.  Must be called before the first oracle call.  The library is named after the
+    host CPU's feature flags, so a copy built on another machine is not loaded."""
+    global _SO, _lib
+    import hashlib
+    if _lib is not None:
+        raise RuntimeError("oracle.use_fast_build() must be called before the oracle library is loaded")
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith(("flags", "model name")):
+                    flags += line
+                if line.startswith("flags"):
+                    break
+    except OSError:
+        pass
+    tag = hashlib.sha1(flags.encode()).hexdigest()[:10]
+    out = os.path.join(_HERE, "_build", f"liborc_fast_{tag}.so")
+    stale = not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in _SRCS)
+    if stale:
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.run(["make", "-C", _HERE, "fast", f"FAST_OUT={out}"], check=True, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT)
+    _SO = out
+    return out
+
+
 class RegParams(C.Structure):
     """Field-for-field mirror of `struct orc_reg_params` (defaults: registration_params.hpp:46-114)."""
     _fields_ = [
@@ -60,7 +90,8 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        build()
+        if "liborc_fast_" not in _SO:
+            build()
         _lib = C.CDLL(_SO)
         L = _lib
         L.orc_num_threads.restype = C.c_int

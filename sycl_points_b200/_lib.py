@@ -58,6 +58,12 @@ class AlignPairC(C.Structure):
     ]
 
 
+class ScanPairC(C.Structure):
+    """struct spx_scan_pair (include/spx.h)."""
+    _fields_ = [("src_raw", C.c_void_p), ("n_src", C.c_size_t), ("tgt_raw", C.c_void_p), ("n_tgt", C.c_size_t),
+                ("T_init_host", C.POINTER(C.c_float))]
+
+
 def declared_symbols() -> list[str]:
     """Every function include/spx.h declares (the exported-symbol test walks this list)."""
     with open(HEADER) as f:
@@ -130,6 +136,7 @@ def lib() -> C.CDLL:
         "spx_voxel_downsample_attrs": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                                  C.POINTER(C.c_size_t)]),
         "spx_box_filter": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, f32p, C.POINTER(C.c_size_t)]),
+        "spx_box_filter_indices": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, i32p, C.POINTER(C.c_size_t)]),
         "spx_linearize": (C.c_int, [vp, C.c_int, C.c_int, f32p, f32p, sz, f32p, f32p, f32p, i32p, f32p, hostf,
                                     C.c_float, C.c_float, hostf, hostf, C.POINTER(C.c_float),
                                     C.POINTER(C.c_uint32)]),
@@ -147,6 +154,11 @@ def lib() -> C.CDLL:
         "spx_registration_align": (C.c_int, [vp, f32p, f32p, sz, f32p, f32p, f32p, sz, vp, hostf, C.c_float,
                                              C.POINTER(RegistrationResultC), hostf]),
         "spx_registration_align_batch": (C.c_int, [vp, sz, C.POINTER(AlignPairC), C.POINTER(RegistrationResultC)]),
+        "spx_batch_create": (C.c_int, [vp, C.POINTER(RegistrationParamsC), C.c_float, C.c_int, C.c_int, C.POINTER(vp)]),
+        "spx_batch_destroy": (C.c_int, [vp]),
+        "spx_batch_set_params": (C.c_int, [vp, C.POINTER(RegistrationParamsC)]),
+        "spx_align_batch": (C.c_int, [vp, sz, C.POINTER(ScanPairC), C.POINTER(RegistrationResultC), u32p, u32p]),
+        "spx_batch_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
         "spx_registration_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                                    C.POINTER(C.c_int32)]),
         "spx_registration_phase_times": (C.c_int, [vp, C.c_int, vp, C.c_int]),

@@ -562,6 +562,27 @@ class PreprocessFilter:
     def set_random_seed(self, seed: int):
         check(_lib.lib().spx_rng_seed(self._rng, int(seed)))
 
+    _ATTRS = ("points", "covs", "normals", "rgb", "intensities", "timestamp_offsets")
+
+    def _gather_all(self, cloud: PointCloudShared, idx: DeviceArray, m: int, output: PointCloudShared | None):
+        """filter_by_flags (common/filter_by_flags.hpp:29-57): every attribute the cloud carries is compacted"""
+        has = (True, cloud.has_cov(), cloud.has_normal(), cloud.has_rgb(), cloud.has_intensity(), cloud.has_timestamps())
+
+        def take(a: DeviceArray | None, enable: bool):
+            if not enable:
+                return None
+            row = int(np.prod(a.shape[1:])) if len(a.shape) > 1 else 1
+            out = DeviceArray(self.queue, (m,) + a.shape[1:], a.dtype)
+            check(_lib.lib().spx_gather(self.queue.handle, a.ptr, row * a.dtype.itemsize, idx.ptr, m, out.ptr))
+            return out
+
+        res = [take(getattr(cloud, name), h) for name, h in zip(self._ATTRS, has)]
+        output = output if output is not None else PointCloudShared(self.queue)
+        for name, a in zip(self._ATTRS, res):
+            setattr(output, name, a)
+        output._n = m
+        return output
+
     def random_sampling(self, cloud: PointCloudShared, sampling_num: int,
                         output: PointCloudShared | None = None) -> PointCloudShared:
         """PreprocessFilter::random_sampling (random_sampling_operator.hpp:24-52): partial Fisher-Yates
@@ -570,46 +591,37 @@ class PreprocessFilter:
         if n <= sampling_num:
             if output is None or output is cloud:
                 return cloud
-            for name in ("points", "covs", "normals", "rgb", "intensities", "timestamp_offsets"):
-                setattr(output, name, getattr(cloud, name))
+            # keep everything: the reference copies the source into the output (random_sampling_operator.hpp:26-30)
+            for name in self._ATTRS:
+                a = getattr(cloud, name)
+                if a is None:
+                    setattr(output, name, None)
+                    continue
+                b = DeviceArray(self.queue, a.shape, a.dtype)
+                if a.nbytes:
+                    check(_lib.lib().spx_memcpy_d2d(self.queue.handle, b.ptr, a.ptr, a.nbytes))
+                setattr(output, name, b)
             output._n = n
             return output
         idx = DeviceArray(self.queue, (sampling_num,), np.int32)
         m = C.c_size_t()
         check(_lib.lib().spx_random_sampling(self.queue.handle, self._rng, n, sampling_num, idx.ptr, C.byref(m)))
-        mm = int(m.value)
-
-        def take(a: DeviceArray | None, enable: bool):
-            if not enable:
-                return None
-            row = int(np.prod(a.shape[1:])) if len(a.shape) > 1 else 1
-            out = DeviceArray(self.queue, (mm,) + a.shape[1:], a.dtype)
-            check(_lib.lib().spx_gather(self.queue.handle, a.ptr, row * a.dtype.itemsize, idx.ptr, mm, out.ptr))
-            return out
-
-        res = (take(cloud.points, True), take(cloud.covs, cloud.has_cov()), take(cloud.normals, cloud.has_normal()),
-               take(cloud.rgb, cloud.has_rgb()), take(cloud.intensities, cloud.has_intensity()),
-               take(cloud.timestamp_offsets, cloud.has_timestamps()))
-        output = output if output is not None else PointCloudShared(self.queue)
-        (output.points, output.covs, output.normals, output.rgb, output.intensities, output.timestamp_offsets) = res
-        output._n = mm
         self._last_indices = idx
-        return output
+        return self._gather_all(cloud, idx, int(m.value), output)
 
     def box_filter(self, cloud: PointCloudShared, min_distance: float = 1.0, max_distance: float = FLT_MAX,
                    output: PointCloudShared | None = None) -> PointCloudShared:
+        """PreprocessFilter::box_filter (box_filter_operator.hpp:19-54): keep points whose L-infinity range lies
+        in [min, max]; every attribute the cloud carries is compacted with them, in source order."""
         output = output if output is not None else cloud
         n = cloud.size()
         if n == 0:
             return output
-        out = DeviceArray(self.queue, (n, 4), np.float32)
+        idx = DeviceArray(self.queue, (n,), np.int32)
         m = C.c_size_t()
-        check(_lib.lib().spx_box_filter(self.queue.handle, cloud.points.ptr, n, min_distance, max_distance, out.ptr,
-                                        C.byref(m)))
-        output.adopt_points(out, int(m.value))
-        output.covs = None
-        output.normals = None
-        return output
+        check(_lib.lib().spx_box_filter_indices(self.queue.handle, cloud.points.ptr, n, min_distance, max_distance, idx.ptr,
+                                                C.byref(m)))
+        return self._gather_all(cloud, idx, int(m.value), output)
 
 
 class transform:  # namespace sycl_points::algorithms::transform (common/transform.hpp:45-136)
@@ -1102,6 +1114,66 @@ class RobustScheduleParams:  # registration_pipeline_params.hpp:18-25
     rotation_init_scale: float = 10.0
     rotation_min_scale: float = 0.5
     auto_scaling_iter: int = 4
+
+
+class BatchAligner:
+    """spx_align_batch (include/spx.h): P RAW scan pairs -> P registration results in one call (BASELINE
+    config 5).  Per cloud voxel grid -> index -> KNN k -> covariances on `lanes` concurrent internal queues, then
+    one batched Registration::align.  Reference semantics per pair: voxel_downsampling.hpp:50-79,
+    covariance.hpp:260-311, registration.hpp:201-276."""
+
+    def __init__(self, queue: DeviceQueue, params: "RegistrationParams | None" = None, voxel_size: float = 0.25,
+                 k_correspondences: int = 10, lanes: int = 0):
+        if voxel_size <= 0.0:
+            raise ValueError("voxel_size must be positive")
+        self.queue = queue
+        self.params = params if params is not None else RegistrationParams()
+        h = C.c_void_p()
+        Pc = self.params.to_c()
+        check(_lib.lib().spx_batch_create(queue.handle, C.byref(Pc), float(voxel_size), int(k_correspondences), int(lanes),
+                                          C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().spx_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align(self, pairs):
+        """pairs: sequence of (source_raw, target_raw[, initial_guess]) with raw clouds as PointCloudShared.
+        Returns (results, n_src_after_voxel, n_tgt_after_voxel)."""
+        pairs = list(pairs)
+        n = len(pairs)
+        if n == 0:
+            return [], np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+        Pc = self.params.to_c()
+        check(_lib.lib().spx_batch_set_params(self._h, C.byref(Pc)))
+        arr = (_lib.ScanPairC * n)()
+        keep = []
+        for j, pr in enumerate(pairs):
+            src, tgt = pr[0], pr[1]
+            T0 = None if len(pr) < 3 or pr[2] is None else _T16(np.asarray(pr[2], np.float32))
+            keep.append(T0)
+            arr[j].src_raw = _addr(src.points.ptr) if src.size() else None
+            arr[j].n_src = src.size()
+            arr[j].tgt_raw = _addr(tgt.points.ptr) if tgt.size() else None
+            arr[j].n_tgt = tgt.size()
+            arr[j].T_init_host = _hostf(T0)
+        R = (RegistrationResultC * n)()
+        ns, nt = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        check(_lib.lib().spx_align_batch(self._h, n, arr, R, ns.ctypes.data_as(C.c_void_p), nt.ctypes.data_as(C.c_void_p)))
+        return [RegistrationResult.from_c(R[j]) for j in range(n)], ns, nt
+
+    def last_timing(self) -> dict:
+        ms, it = C.c_float(), C.c_int32()
+        check(_lib.lib().spx_batch_last_timing(self._h, C.byref(ms), C.byref(it)))
+        return dict(align_ms=ms.value, iterations=it.value)
 
 
 @dataclass

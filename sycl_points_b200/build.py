@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspx.so")
-SOURCES = ["spx_runtime.cu", "spx_knn.cu", "spx_features.cu", "spx_voxel.cu", "spx_registration.cu"]
+SOURCES = ["spx_runtime.cu", "spx_knn.cu", "spx_features.cu", "spx_voxel.cu", "spx_registration.cu", "spx_batch.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--fmad=true", "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-ccbin", host, *ARCH, "-shared", "-o", OUT, *objs, "-Xlinker", "--exclude-libs,ALL"]
+    cmd = [_nvcc(), "-ccbin", host, *ARCH, "-shared", "-o", OUT, *objs, "-Xlinker", "--exclude-libs,ALL", "-lpthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     log.append(r.stdout)
     if r.returncode != 0:

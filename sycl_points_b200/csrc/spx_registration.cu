@@ -736,8 +736,11 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs 
         }
         if (SHARDED) {
             const PeerX& x = a.px;
-            const int par = it & 1;
+            // mailbox rows and flags are double-buffered by the parity of the GLOBAL row sequence number, which
+            // runs on contiguously from one align to the next (the host advances it by the iterations actually
+            // executed): a rank is never more than one exchange ahead of a peer, across aligns too
             const unsigned long long seq = x.seq0 + (unsigned long long)it;
+            const int par = (int)(seq & 1ull);
             if (blockIdx.x == 0) {
                 if (threadIdx.x < 32) {
                     const double v = fold[0][threadIdx.x];
@@ -2464,8 +2467,7 @@ int spx_registration_align_sharded_launch(spx_registration_t reg, spx_comm_t com
         x.ready = reinterpret_cast<unsigned long long*>(comm->local + SPX_MBOX_READY);
         x.error = reinterpret_cast<unsigned int*>(comm->local + SPX_MBOX_ERROR);
         const int max_it = std::max(reg->P.max_iterations, 0);
-        x.seq0 = comm->seq;
-        comm->seq += (unsigned long long)std::max(max_it, 1);
+        x.seq0 = comm->seq;  // advanced by spx_registration_align_sharded_finish, by the iterations that ran
         SPX_CUDA(cudaMemsetAsync(x.error, 0, sizeof(unsigned int), st));
         reg->timed = false;
         SPX_CUDA(cudaEventRecord(reg->ev0, st));
@@ -2496,6 +2498,9 @@ int spx_registration_align_sharded_finish(spx_registration_t reg, spx_registrati
         q->sync();
         if (*herr) throw Error(SPX_ERR_INTERNAL, "[Registration::align_sharded] a peer rank did not answer (timeout)");
         if (reg->shard_max_it > 0) {
+            // every rank ran the same number of exchanges (identical poses -> identical stop): the next align's
+            // first row follows this align's last one in sequence
+            comm->seq += (unsigned long long)(hs->iterations + 1);
             fill_result(*hs, R);
             reg->timed = true;
             reg->last_launches = 1;

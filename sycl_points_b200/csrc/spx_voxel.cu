@@ -707,6 +707,14 @@ __global__ void __launch_bounds__(VX_THREADS) compact_float4_kernel(const float4
     if (flags[i]) out[pos[i]] = in[i];
 }
 
+__global__ void __launch_bounds__(VX_THREADS) compact_index_kernel(const uint32_t* __restrict__ flags,
+                                                                   const uint32_t* __restrict__ pos, uint32_t n,
+                                                                   int32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i]) out[pos[i]] = (int32_t)i;
+}
+
 // box_filter — preprocess_operator/box_filter_operator.hpp:36-44 + common.hpp:15-25
 __global__ void __launch_bounds__(VX_THREADS) box_flag_kernel(const float4* __restrict__ pts, uint32_t n, float mn,
                                                               float mx, uint32_t* __restrict__ flags) {
@@ -1047,6 +1055,36 @@ int spx_box_filter(spx_queue_t q, const float* points, size_t n_in, float min_di
         exclusive_scan_u32(st, flags, pos, n, scan_tmp, total_dev);
         compact_float4_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, flags, pos, n,
                                                                            reinterpret_cast<float4*>(out_points));
+        SPX_LAUNCH_CHECK();
+        uint32_t* htotal = static_cast<uint32_t*>(q->pinned_get(64));
+        SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
+        q->sync();
+        *m_host = *htotal;
+    });
+}
+
+int spx_box_filter_indices(spx_queue_t q, const float* points, size_t n_in, float min_distance, float max_distance,
+                           int32_t* idx_out, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && m_host, "[PreprocessFilter::box_filter] null argument");
+        SPX_REQUIRE(n_in < (1ull << 31), "[PreprocessFilter::box_filter] too many points");
+        *m_host = 0;
+        if (n_in == 0) return;
+        SPX_REQUIRE(points && idx_out, "[PreprocessFilter::box_filter] null pointer");
+        DeviceGuard dg(q->device);
+        cudaStream_t st = q->stream;
+        const uint32_t n = (uint32_t)n_in;
+        q->arena_reset();
+        q->arena_reserve((size_t)n * 8 + scan_scratch_elems(n) * 4 + 4096);
+        uint32_t* flags = q->take<uint32_t>(n);
+        uint32_t* pos = q->take<uint32_t>(n);
+        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(n));
+        uint32_t* total_dev = q->take<uint32_t>(16);
+        box_flag_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(reinterpret_cast<const float4*>(points), n, min_distance,
+                                                                     max_distance, flags);
+        SPX_LAUNCH_CHECK();
+        exclusive_scan_u32(st, flags, pos, n, scan_tmp, total_dev);
+        compact_index_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(flags, pos, n, idx_out);
         SPX_LAUNCH_CHECK();
         uint32_t* htotal = static_cast<uint32_t*>(q->pinned_get(64));
         SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));

@@ -231,3 +231,103 @@ class ShardedRegistration:
 
     def last_timing(self) -> dict:
         return self.reg.last_timing()
+
+
+# ------------------------------------------------------------------ sharded KNN / covariance
+def all_gather_rows(local: np.ndarray, n_total: int, world: int, group=None) -> np.ndarray:
+    """Concatenate the ranks' contiguous ceil(n / world) row shards (shard_bounds order) into the full
+    array on every rank.  Host arrays through the process group's object gather: works on any backend
+    (gloo on CPU, nccl)."""
+    import torch.distributed as dist
+    if world == 1:
+        return local
+    parts = [None] * world
+    dist.all_gather_object(parts, local, group=group)
+    out = np.concatenate([p for p in parts if len(p)], axis=0) if n_total else local[:0]
+    assert len(out) == n_total, (len(out), n_total)
+    return out
+
+
+class ShardedKNN:
+    """KNN with the QUERIES split over the ranks and the targets (+ their index) replicated — independent
+    units, no data-path collective; results stay sharded unless `gather` is asked for.
+    Per-shard contract = the single-GPU searches: knn_search_bruteforce (bruteforce.hpp:24-96) and
+    KNNBase::knn_search (knn.hpp:22-24, kdtree.hpp:203-224): exact, ordered by (dist, index).
+
+    `search(queries_rows, k) -> (idx, dist)` is the per-shard computation; the default runs the CUDA path
+    (method "index" or "bruteforce") on this rank's queue, tests inject the oracle."""
+
+    def __init__(self, rank: int, world: int, group=None, search=None):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("need 0 <= rank < world")
+        self.rank, self.world, self.group = rank, world, group
+        self._search = search
+
+    @classmethod
+    def on_device(cls, queue: DeviceQueue, targets: PointCloudShared, rank: int, world: int, group=None,
+                  method: str = "index") -> "ShardedKNN":
+        from .api import KNNResult, knn_search_bruteforce
+        if method not in ("index", "bruteforce"):
+            raise ValueError("method must be 'index' or 'bruteforce'")
+        tree = KDTree.build(queue, targets) if method == "index" else None
+
+        def search(rows: np.ndarray, k: int):
+            qc = PointCloudShared(queue, rows)
+            res = tree.knn_search(qc, k) if tree is not None else knn_search_bruteforce(queue, qc, targets, k)
+            return res.indices_host(), res.distances_host()
+
+        self = cls(rank, world, group, search)
+        self.queue, self.targets, self.tree, self.method = queue, targets, tree, method
+        return self
+
+    def shard(self, n: int) -> tuple[int, int]:
+        return shard_of(n, self.rank, self.world)
+
+    def knn_search(self, queries: np.ndarray, k: int, gather: bool = False):
+        """queries: the FULL (n, 4) host array, identical on every rank; this rank searches its rows.
+        Returns (idx, dist, (lo, hi)) for the shard, or the gathered full arrays when gather=True."""
+        lo, hi = self.shard(len(queries))
+        idx, dist_ = self._search(np.ascontiguousarray(queries[lo:hi]), k)
+        idx = np.asarray(idx, np.int32).reshape(hi - lo, k)
+        dist_ = np.asarray(dist_, np.float32).reshape(hi - lo, k)
+        if not gather:
+            return idx, dist_, (lo, hi)
+        return (all_gather_rows(idx, len(queries), self.world, self.group),
+                all_gather_rows(dist_, len(queries), self.world, self.group), (0, len(queries)))
+
+
+class ShardedCovariance:
+    """covariance::estimate (covariance.hpp:16-47,260-311) with the POINTS split over the ranks: every rank
+    holds the full cloud (the gathers need it) and its index, computes the k-neighbour covariances of its own
+    contiguous range, and — when the next stage needs them replicated (the target side of GICP) — all-gathers
+    the 64-byte matrices.  `compute(points, lo, hi, k) -> (hi-lo, 4, 4)` is injectable like ShardedKNN.search."""
+
+    def __init__(self, rank: int, world: int, group=None, compute=None):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("need 0 <= rank < world")
+        self.rank, self.world, self.group = rank, world, group
+        self._compute = compute
+
+    @classmethod
+    def on_device(cls, queue: DeviceQueue, rank: int, world: int, group=None) -> "ShardedCovariance":
+        from .api import covariance
+
+        def compute(points: np.ndarray, lo: int, hi: int, k: int):
+            from .api import DeviceArray
+            cloud = PointCloudShared(queue, points)            # the full cloud, replicated: the gathers read it
+            tree = KDTree.build(queue, cloud)
+            nn = tree.knn_search(PointCloudShared(queue, points[lo:hi]), k)  # this rank's rows against the full cloud
+            covs = DeviceArray(queue, (hi - lo, 16), np.float32)
+            if hi > lo:
+                check(_lib.lib().spx_covariance(queue.handle, cloud.points.ptr, hi - lo, nn.indices.ptr, k, covs.ptr))
+            tree.close()
+            return covs.download().reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+        return cls(rank, world, group, compute)
+
+    def estimate(self, points: np.ndarray, k: int, gather: bool = True):
+        lo, hi = shard_of(len(points), self.rank, self.world)
+        covs = np.asarray(self._compute(points, lo, hi, k), np.float32).reshape(hi - lo, 4, 4)
+        if not gather:
+            return covs, (lo, hi)
+        return all_gather_rows(covs, len(points), self.world, self.group), (0, len(points))

@@ -6,7 +6,7 @@ tests: a ground plane, 40 axis-aligned buildings and
 A single revolution of such a sensor fills only ~30 k voxels of 0.25 m (the ground rings are far
 apart), so each cloud is the motion-compensated accumulation of `sweeps` revolutions taken every
 `spacing` metres along the corridor — what a LiDAR-odometry front end hands to scan matching when
-it aligns against a local map.  The default (16 sweeps x 64 beams x 2048 azimuth steps, 8 m apart,
+it aligns against a local map.  The default (16 sweeps x 64 beams x 2048 azimuth steps, 8.3 m apart,
 ~2.05 M raw points) gives the 120 k +- 2 % points after the 0.25 m voxel grid that BASELINE.json
 config 2 names.  Target cloud at the identity pose, source cloud at
 T_gt = trans(0.5, 0.1, -0.02) * Rz(0.7 deg) — the magnitudes of the reference's bundled
@@ -146,7 +146,7 @@ def accumulated_cloud(pose: np.ndarray, boxes, cyl, sweeps: int, beams: int, azi
     return np.concatenate(out)
 
 
-def kitti_pair(seed: int = 42, sweeps: int = 16, beams: int = 64, azimuth_steps: int = 2048, spacing: float = 8.0,
+def kitti_pair(seed: int = 42, sweeps: int = 16, beams: int = 64, azimuth_steps: int = 2048, spacing: float = 8.3,
                T_gt: np.ndarray | None = None):
     """(target_raw, source_raw, T_gt): align(source -> target) should recover T_gt."""
     boxes, cyl = make_scene(seed)

@@ -162,6 +162,46 @@ def test_box_filter(spx, q, bundled):
     assert np.array_equal(cloud.points_host(), oracle.box_filter(raw, 0.5, 50.0))
 
 
+def test_filters_compact_every_attribute(spx, q, bundled):
+    """filter_by_flags (common/filter_by_flags.hpp:29-57): box_filter and random_sampling compact every
+    attribute the cloud carries, in source order; the keep-all branch of random_sampling deep-copies."""
+    raw = bundled["source_raw_head"][:5000].copy()
+    n = len(raw)
+    rs = np.random.RandomState(1)
+    covs = np.zeros((n, 4, 4), np.float32)
+    covs[:, :3, :3] = rs.rand(n, 3, 3)
+    nrm, rgb = rs.rand(n, 4).astype(np.float32), rs.rand(n, 4).astype(np.float32)
+    inten, ts = rs.rand(n).astype(np.float32), rs.rand(n).astype(np.float32)
+
+    def make():
+        c = spx.PointCloudShared(q, raw, covs, nrm)
+        c.set_rgb(rgb)
+        c.set_intensities(inten)
+        c.set_timestamp_offsets(ts)
+        return c
+
+    keep = np.array([np.isfinite(p).all() and 2.0 <= np.abs(p[:3]).max() <= 30.0 for p in raw])
+    pf = spx.PreprocessFilter(q)
+    c = make()
+    pf.box_filter(c, 2.0, 30.0)
+    assert c.size() == keep.sum() and 0 < keep.sum() < n
+    assert np.array_equal(c.points_host(), raw[keep]) and np.array_equal(c.covs_host(), covs[keep])
+    assert np.array_equal(c.normals_host(), nrm[keep]) and c.has_rgb() and c.has_intensity() and c.has_timestamps()
+    assert np.array_equal(c.rgb.download(), rgb[keep]) and np.array_equal(c.intensities.download(), inten[keep])
+    assert np.array_equal(c.timestamp_offsets.download(), ts[keep])
+    c = make()
+    out = pf.random_sampling(c, 700)
+    sel = pf._last_indices.download()
+    assert out.size() == 700 and (np.diff(sel) > 0).all()
+    assert np.array_equal(out.rgb.download(), rgb[sel]) and np.array_equal(out.timestamp_offsets.download(), ts[sel])
+    assert np.array_equal(out.covs_host(), covs[sel])
+    dst = spx.PointCloudShared(q)
+    pf.random_sampling(c, n + 5, output=dst)  # keep-all: a copy, not an alias
+    assert dst.points is not c.points and np.array_equal(dst.points_host(), raw)
+    spx.transform.transform(dst, oracle.se3_exp(np.array([0, 0, 0.1, 1, 0, 0], np.float32)))
+    assert np.array_equal(c.points_host(), raw)
+
+
 def test_voxel_attributes_vs_oracle(spx, q, bundled):
     """Cloud overload (voxel_downsampling.hpp:220-288): mean RGB, MEDIAN intensity, mean timestamp per
     voxel in the stable order — bit-exact vs the oracle, incl. even / odd run lengths and ties."""

@@ -607,3 +607,36 @@ def test_align_batch_64_pairs_of_60k(spx, q):
     for j, r in enumerate(batch):
         dt, da = pose_delta(keep[j], r.T)
         assert r.converged and dt < 0.05, (j, dt)
+
+
+def test_spx_align_batch_raw_pairs_equal_the_single_pair_chain(spx, q):
+    """spx_align_batch (raw clouds in, results out; lanes + one batched align) == the single-pair chain
+    voxel -> index -> KNN -> covariance -> align, bit for bit, incl. a target shared by several pairs."""
+    import synthetic
+    rs = np.random.RandomState(9)
+    raws = []
+    for seed in range(2):
+        tgt_raw, src_raw, _ = synthetic.kitti_pair(200 + seed, sweeps=4)
+        raws.append((spx.PointCloudShared(q, src_raw), spx.PointCloudShared(q, tgt_raw)))
+    pairs = []
+    for j in range(6):
+        s, t = raws[j % 2]
+        T0 = oracle.se3_exp(rs.normal(0, [0.002, 0.002, 0.004, 0.05, 0.05, 0.01]).astype(np.float32)) if j >= 2 else None
+        pairs.append((s, t, T0))
+    params = spx.RegistrationParams()
+    params.robust.type = spx.RobustLossType.HUBER
+    ba = spx.BatchAligner(q, params, 0.25, 10, lanes=3)
+    res, ns, nt = ba.align(pairs)
+    vg = spx.VoxelGrid(q, 0.25)
+    reg_obj = spx.Registration(q, params)
+    for j, (s_raw, t_raw, T0) in enumerate(pairs):
+        src, tgt = vg.downsampling(s_raw), vg.downsampling(t_raw)
+        assert ns[j] == src.size() and nt[j] == tgt.size()
+        ts, tt = spx.KDTree.build(q, src), spx.KDTree.build(q, tgt)
+        spx.covariance.estimate(ts.knn_search(src, 10), src)
+        spx.covariance.estimate(tt.knn_search(tgt, 10), tgt)
+        one = reg_obj.align(src, tgt, tt, T0)
+        assert np.array_equal(res[j].T, one.T) and res[j].iterations == one.iterations and res[j].inlier == one.inlier
+        assert res[j].converged == one.converged and res[j].error == one.error
+    assert ba.last_timing()["iterations"] >= 1
+    ba.close()

@@ -151,3 +151,60 @@ def test_block_cyclic_shards_partition_the_cloud():
             if n >= 8 * 1024 * w:
                 sizes = [len(p) for p in parts]
                 assert max(sizes) - min(sizes) <= 1024
+
+
+WORKER_KNN = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+import oracle
+from sycl_points_b200.multi_gpu import ShardedKNN, ShardedCovariance, shard_of
+
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
+rank, world = dist.get_rank(), dist.get_world_size()
+Q = oracle.Rng(1234).box_points(1001, (-50, -50, -3), (50, 50, 10))   # config-3 distribution, odd count: ragged shards
+T = oracle.Rng(4321).box_points(3000, (-50, -50, -3), (50, 50, 10))
+knn = ShardedKNN(rank, world, search=lambda rows, k: oracle.knn_bruteforce(rows, T, k))
+idx, dst, (lo, hi) = knn.knn_search(Q, 20)
+assert (lo, hi) == shard_of(len(Q), rank, world) and idx.shape == (hi - lo, 20)
+gi, gd, _ = knn.knn_search(Q, 20, gather=True)
+ri, rd = oracle.knn_bruteforce(Q, T, 20)
+ok_knn = bool(np.array_equal(gi, ri) and np.array_equal(gd, rd) and np.array_equal(idx, ri[lo:hi]))
+# covariance: every rank holds the full cloud, computes its rows, all-gathers
+tree = oracle.KDTree(T)
+def compute(points, lo, hi, k):
+    nn, _ = tree.knn(points[lo:hi], k)
+    # rows of the shard against the FULL cloud: estimate() gathers neighbours from `points`
+    full_idx = np.full((len(points), k), -1, np.int32)
+    full_idx[lo:hi] = nn
+    return oracle.covariance(points, full_idx)[lo:hi]
+cov, _ = ShardedCovariance(rank, world, compute=compute).estimate(T, 10)
+ref = oracle.covariance(T, tree.knn(T, 10)[0])
+ok_cov = bool(np.array_equal(cov, ref))
+# an empty query set and more ranks than rows
+e_i, e_d, _ = knn.knn_search(Q[:0], 5, gather=True)
+o_i, o_d, _ = knn.knn_search(Q[:1], 5, gather=True)
+ok_edge = bool(e_i.shape == (0, 5) and np.array_equal(o_i, ri[:1, :5]))
+if rank == 0:
+    print(json.dumps(dict(knn=ok_knn, cov=ok_cov, edge=ok_edge)))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.timeout(300)
+def test_sharded_knn_and_covariance_world2_gloo(tmp_path):
+    """SURVEY §8(e) rows 2-3 on CPU: queries / points split over 2 gloo ranks, per-shard computation injected
+    (oracle); the gathered result equals the unsharded one bit for bit, ragged and empty shards included."""
+    script = tmp_path / "worker_knn.py"
+    script.write_text(WORKER_KNN)
+    port = free_port()
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), "2"], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, env=env) for r in range(2)]
+    outs = [p.communicate(timeout=280) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    import json
+    res = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert res == dict(knn=True, cov=True, edge=True), res
