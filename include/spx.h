@@ -143,6 +143,9 @@ SPX_API int spx_queue_set_blocking_sync(spx_queue_t q, int blocking);
 /* Kernels launched by this library since load (all queues): bench.py's `gpu_launches`. */
 SPX_API uint64_t spx_kernel_launch_count(void);
 
+/* tuning aid: cudaProfilerStart / cudaProfilerStop (ncu --profile-from-start off captures only the range) */
+SPX_API int spx_profiler_range(int start);
+
 /* shared_vector<T> storage — sycl_utils.hpp:630-635 (USM shared -> explicit device memory) */
 SPX_API int spx_malloc(spx_queue_t q, size_t bytes, void** out);
 SPX_API int spx_free(spx_queue_t q, void* ptr);

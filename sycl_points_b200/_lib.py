@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "spx_queue_set_blocking_sync": (C.c_int, [vp, C.c_int]),
         "spx_queue_device": (C.c_int, [vp, C.POINTER(C.c_int)]),
         "spx_kernel_launch_count": (C.c_uint64, []),
+        "spx_profiler_range": (C.c_int, [C.c_int]),
         "spx_malloc": (C.c_int, [vp, sz, C.POINTER(vp)]),
         "spx_free": (C.c_int, [vp, vp]),
         "spx_malloc_host": (C.c_int, [sz, C.POINTER(vp)]),

@@ -6,6 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
+#include <vector>
+
 #include "spx_grid.cuh"
 #include "spx_scan.cuh"
 
@@ -329,9 +332,9 @@ __global__ void occupied_from_start_kernel(const uint32_t* __restrict__ start, s
 // l*n + (position inside the level): the levels' sorted copies are laid out back to back in one
 // array and `start` values index it directly (GridView::pts is the common base pointer).
 struct LevelSet {
-    int n_levels;
-    GridGeom geom[GRID_MAX_LEVELS];
-    uint32_t cell_base[GRID_MAX_LEVELS + 1];
+    int n_levels;  // incl. the extra k-NN grid (always the last entry) when the index has one
+    GridGeom geom[GRID_MAX_LEVELS + 1];
+    uint32_t cell_base[GRID_MAX_LEVELS + 2];
 };
 
 __global__ void levels_count_kernel(const float4* __restrict__ pts, uint32_t n, LevelSet ls, uint32_t* __restrict__ counts) {
@@ -536,7 +539,8 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_first_kernel(const 
                                                                            int32_t* __restrict__ idx, float* __restrict__ dist,
                                                                            uint32_t* __restrict__ worklist,
                                                                            unsigned int* __restrict__ wl_count,
-                                                                           unsigned long long* __restrict__ carry) {
+                                                                           unsigned long long* __restrict__ carry,
+                                                                           unsigned int* __restrict__ wl_count_back) {
     const uint32_t qi = blockIdx.x * GRID_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const float INF = __int_as_float(0x7f800000);
@@ -559,18 +563,31 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_reg_first_kernel(const 
                 }
         }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, pending);
-    if (m) {
+    // wl_count_back != null: queries that do not even HAVE k candidates yet (sparse surroundings: the expensive ones)
+    // are listed from the front, the others from the back of the same array, and the list kernel drains front first
+    // — the long queries start at once instead of forming the kernel's tail
+    const bool sparse = pending && best.key[K - 1] == BestR<K>::EMPTY;
+    const bool to_back = pending && wl_count_back != nullptr && !sparse;
+    const bool to_front = pending && !to_back;
+    const unsigned mf = __ballot_sync(0xffffffffu, to_front), mb = __ballot_sync(0xffffffffu, to_back);
+    unsigned int w = 0;
+    if (mf) {
         unsigned int slot = 0;
-        if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
-        slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
-        if (pending) {
-            // the list kernel resumes from this state instead of repeating the first pass
-            const unsigned int w = slot + __popc(m & ((1u << lane) - 1u));
-            worklist[w] = qi;
+        if (lane == __ffs(mf) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(mf));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(mf) - 1);
+        if (to_front) w = slot + __popc(mf & ((1u << lane) - 1u));
+    }
+    if (mb) {
+        unsigned int slot = 0;
+        if (lane == __ffs(mb) - 1) slot = atomicAdd(wl_count_back, (unsigned int)__popc(mb));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(mb) - 1);
+        if (to_back) w = nq - 1u - (slot + __popc(mb & ((1u << lane) - 1u)));
+    }
+    if (pending) {
+        // the list kernel resumes from this state instead of repeating the first pass
+        worklist[w] = qi;
 #pragma unroll
-            for (int j = 0; j < K; ++j) carry[(size_t)j * nq + w] = best.key[j];
-        }
+        for (int j = 0; j < K; ++j) carry[(size_t)j * nq + w] = best.key[j];
     }
 }
 
@@ -644,9 +661,354 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_far_kernel(const GridLe
     }
 }
 
+// ---- the queries the first pass could not certify, ONE WARP per query, bound-driven.
+// The first pass leaves such a query with the candidates of its 3x3x3 block (its k-th best distance d_k, when it
+// has k of them, is an UPPER bound of the answer's k-th distance).  Instead of walking shell after shell, the warp
+//   * picks the finest (level, ring radius) whose scanned block certifies d_k — every point outside it is farther
+//     than sqrt(d_k) — so that ONE scan finishes the query; a query with fewer than k candidates first grows its
+//     block (ring 2, then the next coarser level's 3x3x3, ...) until it has k;
+//   * looks up the (z, y) rows of that block 32 at a time (rows and x-ranges pruned against d_k, cells a finer ring
+//     of the same level has already covered skipped), and scans their candidates 32 wide, load-balanced by a prefix
+//     sum over the rows' counts;
+//   * keeps a candidate only if (dist, index) sorts before the current k-th entry — few do — in a small
+//     shared-memory buffer, and merges buffer and list by k rounds of a warp-wide minimum (equal (dist, index) keys,
+//     i.e. the same point offered by two levels, leave together: duplicates vanish).
+// The list lives one 64-bit key per lane ((dist bits << 32 | index) + 1, BestR's encoding): lanes K-k .. K-1 hold the k
+// entries in ascending order.  Exactness: the stop test is grid_search's (k-th best strictly inside the scanned
+// block's certified radius, or the whole grid seen), ties resolve by index through the key order.
+constexpr int COOP_BUF = 64;
+constexpr int COOP_U = 2;     // 32-candidate batches in flight per step
+constexpr int COOP_RMAX = 5;  // largest ring radius on a level that is not the coarsest (11 cells < the next level's 12)
+
+template <int K>
+__global__ void __launch_bounds__(GRID_THREADS) grid_knn_coop_list_kernel(const GridLevels gl, const float4* __restrict__ queries,
+                                                                          uint32_t nq, int k, Xform T, int has_T,
+                                                                          int32_t* __restrict__ idx, float* __restrict__ dist,
+                                                                          const uint32_t* __restrict__ worklist,
+                                                                          const unsigned int* __restrict__ wl_count,
+                                                                          unsigned int* __restrict__ wl_cursor,
+                                                                          const unsigned long long* __restrict__ carry,
+                                                                          const unsigned int* __restrict__ wl_count_back,
+                                                                          uint32_t* __restrict__ dbg) {
+    constexpr unsigned long long EMPTY = BestR<K>::EMPTY;
+    const unsigned FULL = 0xffffffffu;
+    const float INF = __int_as_float(0x7f800000);
+    __shared__ unsigned long long sbuf[GRID_THREADS / 32][COOP_BUF];
+    const int lane = threadIdx.x & 31;
+    unsigned long long* buf = sbuf[threadIdx.x >> 5];
+    const unsigned int n_front = *wl_count, n_slow = n_front + *wl_count_back;
+    const int first = K - k;  // lane of the list's smallest entry
+    for (;;) {
+        unsigned int w = 0;
+        if (lane == 0) w = atomicAdd(wl_cursor, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= n_slow) break;
+        if (w >= n_front) w = nq - 1u - (w - n_front);  // the back part of the list
+        const uint32_t qi = worklist[w];
+        float4 q = __ldg(queries + qi);
+        if (has_T) q = transform_point(T, q);
+        unsigned long long mykey = (lane < K) ? carry[(size_t)lane * nq + w] : EMPTY;
+        if (lane < first) mykey = 0ull;
+        int nb = 0;  // accepted candidates waiting in the buffer
+        uint32_t d_cands = 0, d_scans = 0, d_merges = 0, d_last = 0;
+        const long long d_t0 = dbg ? clock64() : 0;
+
+        auto merge = [&]() {
+            // candidates of this lane: its list entry and up to two buffer entries
+            unsigned long long c0 = (lane >= first && lane < K) ? mykey : EMPTY;
+            unsigned long long c1 = lane < nb ? buf[lane] : EMPTY;
+            unsigned long long c2 = lane + 32 < nb ? buf[lane + 32] : EMPTY;
+            unsigned long long out = EMPTY;
+            for (int t = 0; t < k; ++t) {
+                unsigned long long m = c0 < c1 ? c0 : c1;
+                m = c2 < m ? c2 : m;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long v = __shfl_xor_sync(FULL, m, o);
+                    m = v < m ? v : m;
+                }
+                if (m != EMPTY) {  // every copy of this exact (dist, index) leaves
+                    if (c0 == m) c0 = EMPTY;
+                    if (c1 == m) c1 = EMPTY;
+                    if (c2 == m) c2 = EMPTY;
+                }
+                if (lane == first + t) out = m;
+            }
+            mykey = lane < first ? 0ull : (lane < K ? out : EMPTY);
+            nb = 0;
+            ++d_merges;
+            __syncwarp();
+        };
+
+        // scan every cell within Chebyshev radius r of the query's cell on level l that lies farther than r_done
+        // (cells a previous scan of this level has covered; -1: none)
+        auto scan = [&](const GridView& g, int r, int r_done) {
+            const int cx = grid_coord(q.x, g.ox, g.inv, g.dx);
+            const int cy = grid_coord(q.y, g.oy, g.inv, g.dy);
+            const int cz = grid_coord(q.z, g.oz, g.inv, g.dz);
+            const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+            // rows (z, y) in CENTRE-OUT order (ring 0, ring 1, ...): near rows first, so the k-th best tightens early
+            // and the far rows are pruned or rejected by one compare (a sweep from one face of the block offers
+            // candidates in decreasing distance: half of them would enter the list)
+            const int nrows = (2 * r + 1) * (2 * r + 1);
+            for (int base = 0; base < nrows; base += 32) {
+                unsigned long long kth = __shfl_sync(FULL, mykey, K - 1);
+                const float lim2 = kth != EMPTY ? __uint_as_float((uint32_t)((kth - 1ull) >> 32)) : INF;
+                const int t = base + lane;
+                uint32_t sA = 0, eA = 0, sB = 0, eB = 0;
+                int ddz = 0, ddy = 0;
+                if (t > 0 && t < nrows) {
+                    int rr = 1;
+                    while ((2 * rr + 1) * (2 * rr + 1) <= t) ++rr;
+                    const int pp = t - (2 * rr - 1) * (2 * rr - 1), side = 2 * rr, edge = pp / side, o = pp - edge * side;
+                    ddz = edge == 0 ? -rr : (edge == 1 ? -rr + o : (edge == 2 ? rr : rr - o));
+                    ddy = edge == 0 ? -rr + o : (edge == 1 ? rr : (edge == 2 ? rr - o : -rr));
+                }
+                const int zz = cz + ddz, yy = cy + ddy;
+                if (t < nrows && zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy) {
+                    const bool outer = max(abs(zz - cz), abs(yy - cy)) > r_done;  // no cell of this row seen before
+                    int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
+                    bool ok = true;
+                    if (lim2 < 1.0e30f) {
+                        const float gz = axis_gap(q.z, g.oz, g.cell, zz);
+                        const float gy = axis_gap(q.y, g.oy, g.cell, yy);
+                        const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
+                        const float gyz2 = __fmul_rn(gyz, gyz);
+                        ok = gyz2 <= lim2;
+                        const float wd = sqrtf(fmaxf(lim2 - gyz2, 0.0f)) + margin;
+                        xa = max(xa, grid_coord(q.x - wd, g.ox, g.inv, g.dx));
+                        xb = min(xb, grid_coord(q.x + wd, g.ox, g.inv, g.dx));
+                        ok = ok && xa <= xb;
+                    }
+                    if (ok) {
+                        const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
+                        if (outer) {
+                            sA = __ldg(g.start + row + xa);
+                            eA = __ldg(g.start + row + xb + 1);
+                        } else {  // only the cells beyond the ring already covered: two ends of the row
+                            const int la = xa, lb = min(xb, cx - r_done - 1);
+                            const int ra = max(xa, cx + r_done + 1), rb = xb;
+                            if (la <= lb) {
+                                sA = __ldg(g.start + row + la);
+                                eA = __ldg(g.start + row + lb + 1);
+                            }
+                            if (ra <= rb) {
+                                sB = __ldg(g.start + row + ra);
+                                eB = __ldg(g.start + row + rb + 1);
+                            }
+                        }
+                    }
+                }
+                // LONG rows (coarse levels: a row can hold thousands of points) are strided by the whole warp, four
+                // loads per lane in flight, no per-candidate bookkeeping; the others share the prefix-sum path below
+                {
+                    unsigned longm = __ballot_sync(FULL, (eA - sA) + (eB - sB) >= 128u);
+                    while (longm) {
+                        const int src = __ffs(longm) - 1;
+                        longm &= longm - 1;
+#pragma unroll
+                        for (int seg = 0; seg < 2; ++seg) {
+                            const uint32_t a0 = __shfl_sync(FULL, seg ? sB : sA, src), b0 = __shfl_sync(FULL, seg ? eB : eA, src);
+                            d_cands += b0 - a0;
+                            for (uint32_t j = a0 + lane; j < b0 + 96; j += 128) {  // warp-uniform trip count
+                                float4 p4[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    if (j + 32 * u < b0) p4[u] = __ldg(g.pts + j + 32 * u);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (j - lane + 32 * u >= b0) continue;  // warp-uniform
+                                    if (nb > COOP_BUF - 32) merge();
+                                    const unsigned long long kth4 = __shfl_sync(FULL, mykey, K - 1);
+                                    bool take = false;
+                                    unsigned long long c4 = EMPTY;
+                                    if (j + 32 * u < b0) {
+                                        const float ds = dist_sq(q.x, q.y, q.z, p4[u].x, p4[u].y, p4[u].z);
+                                        c4 = (((unsigned long long)__float_as_uint(ds) << 32) |
+                                              (unsigned long long)(uint32_t)__float_as_int(p4[u].w)) + 1ull;
+                                        take = c4 < kth4;
+                                    }
+                                    const unsigned m = __ballot_sync(FULL, take);
+                                    if (take) buf[nb + __popc(m & ((1u << lane) - 1u))] = c4;
+                                    nb += __popc(m);
+                                    __syncwarp();
+                                }
+                            }
+                        }
+                        if (lane == src) sA = eA = sB = eB = 0u;
+                    }
+                }
+                const uint32_t cA = eA - sA, cnt = cA + (eB - sB);
+                uint32_t inc = cnt;  // inclusive prefix sum of the candidate counts over the lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const uint32_t total = __shfl_sync(FULL, inc, 31);
+                d_cands += total;
+                // COOP_U x 32 candidates per step, their loads issued together: a coarse block can hold thousands of
+                // candidates, and one load per step is one L2 round trip per 32 of them
+                for (uint32_t cb = 0; cb < total; cb += 32 * COOP_U) {
+                    unsigned long long ck[COOP_U];
+                    float4 pp[COOP_U];
+                    bool live[COOP_U];
+#pragma unroll
+                    for (int u = 0; u < COOP_U; ++u) {
+                        const uint32_t kk = cb + u * 32 + lane;
+                        live[u] = kk < total;
+                        pp[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (cb + u * 32 >= total) continue;  // warp-uniform
+                        const uint32_t key = live[u] ? kk : 0u;
+                        int owner = 0;  // number of lanes whose inclusive sum is <= key
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) {
+                            const uint32_t v = __shfl_sync(FULL, inc, owner + sft - 1);
+                            if (v <= key) owner += sft;
+                        }
+                        owner = min(owner, 31);
+                        const uint32_t o_inc = __shfl_sync(FULL, inc, owner);
+                        const uint32_t o_cnt = __shfl_sync(FULL, cnt, owner);
+                        const uint32_t o_cA = __shfl_sync(FULL, cA, owner);
+                        const uint32_t o_sA = __shfl_sync(FULL, sA, owner);
+                        const uint32_t o_sB = __shfl_sync(FULL, sB, owner);
+                        if (live[u]) {
+                            const uint32_t jj = key - (o_inc - o_cnt);
+                            const uint32_t pos = jj < o_cA ? o_sA + jj : o_sB + (jj - o_cA);
+                            pp[u] = __ldg(g.pts + pos);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < COOP_U; ++u) {
+                        const float ds = dist_sq(q.x, q.y, q.z, pp[u].x, pp[u].y, pp[u].z);
+                        ck[u] = live[u] ? (((unsigned long long)__float_as_uint(ds) << 32) |
+                                           (unsigned long long)(uint32_t)__float_as_int(pp[u].w)) + 1ull
+                                        : EMPTY;
+                    }
+#pragma unroll
+                    for (int u = 0; u < COOP_U; ++u) {
+                        if (cb + u * 32 >= total) continue;  // warp-uniform
+                        if (nb > COOP_BUF - 32) merge();
+                        kth = __shfl_sync(FULL, mykey, K - 1);
+                        const bool take = ck[u] < kth;
+                        const unsigned m = __ballot_sync(FULL, take);
+                        if (take) buf[nb + __popc(m & ((1u << lane) - 1u))] = ck[u];
+                        nb += __popc(m);
+                        __syncwarp();
+                    }
+                }
+            }
+            if (nb) merge();
+        };
+
+        int l_min = 0;      // never go back to a finer level
+        int r_done = 1;     // level 0: the first pass covered ring 1 completely
+        for (;;) {
+            const unsigned long long kth = __shfl_sync(FULL, mykey, K - 1);
+            const bool full = kth != EMPTY;
+            const float d_k = full ? __uint_as_float((uint32_t)((kth - 1ull) >> 32)) : INF;
+            int L = l_min, R = r_done + 1;
+            bool found = false;
+            if (full) {
+                // the finest block that certifies d_k
+                for (int l = l_min; l < gl.n_levels && !found; ++l) {
+                    const GridView& g = gl.lv[l];
+                    const bool last = l == gl.n_levels - 1;
+                    const int cx = grid_coord(q.x, g.ox, g.inv, g.dx);
+                    const int cy = grid_coord(q.y, g.oy, g.inv, g.dy);
+                    const int cz = grid_coord(q.z, g.oz, g.inv, g.dz);
+                    const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+                    const int r_first = (l == l_min) ? r_done + 1 : 1;
+                    const int r_last = last ? (1 << 20) : COOP_RMAX;
+                    for (int r = r_first; r <= r_last; ++r) {
+                        const float bound = fminf(fminf(shell_bound_axis(q.x, g.ox, g.cell, cx, r, g.dx),
+                                                        shell_bound_axis(q.y, g.oy, g.cell, cy, r, g.dy)),
+                                                  shell_bound_axis(q.z, g.oz, g.cell, cz, r, g.dz));
+                        const float bs = bound - margin;
+                        if (bound == INF || (bs > 0.0f && d_k < __fmul_rn(bs, bs))) {
+                            L = l;
+                            R = r;
+                            found = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            if (!found) {
+                // fewer than k candidates so far: the smallest block of the growth sequence (rings r_done+1 .. COOP_RMAX
+                // of this level, then rings 1 .. COOP_RMAX of the next coarser one, ...; the coarsest level grows until
+                // the grid is covered) that HOLDS at least k points — counted from the rows' cell ranges, one round trip
+                // per 32 rows, nothing scanned: an isolated query crosses empty space without touching a point
+                int l = l_min, r = r_done;
+                for (;;) {
+                    const bool last = l == gl.n_levels - 1;
+                    if (last || r < COOP_RMAX) {
+                        ++r;
+                    } else {
+                        ++l;
+                        r = 1;
+                    }
+                    const GridView& g = gl.lv[l];
+                    const int cx = grid_coord(q.x, g.ox, g.inv, g.dx);
+                    const int cy = grid_coord(q.y, g.oy, g.inv, g.dy);
+                    const int cz = grid_coord(q.z, g.oz, g.inv, g.dz);
+                    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
+                    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
+                    const int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
+                    const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+                    uint32_t c = 0;
+                    for (int t = lane; t < nrows; t += 32) {
+                        const uint32_t row = ((uint32_t)(z0 + t / ny) * (uint32_t)g.dy + (uint32_t)(y0 + t % ny)) * (uint32_t)g.dx;
+                        c += __ldg(g.start + row + xb + 1) - __ldg(g.start + row + xa);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+                    const bool whole = z0 == 0 && y0 == 0 && xa == 0 && z1 == g.dz - 1 && y1 == g.dy - 1 && xb == g.dx - 1;
+                    if (c >= (uint32_t)k || whole) break;
+                }
+                L = l;
+                R = r;
+            }
+            const GridView& g = gl.lv[L];
+            ++d_scans;
+            d_last = (uint32_t)(L * 100 + R) + (full ? 0u : 10000u);
+            scan(g, R, L == l_min ? r_done : -1);
+            l_min = L;
+            r_done = R;
+            // stop test of the block just completed (grid_search's)
+            {
+                const int cx = grid_coord(q.x, g.ox, g.inv, g.dx);
+                const int cy = grid_coord(q.y, g.oy, g.inv, g.dy);
+                const int cz = grid_coord(q.z, g.oz, g.inv, g.dz);
+                const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+                const float bound = fminf(fminf(shell_bound_axis(q.x, g.ox, g.cell, cx, R, g.dx),
+                                                shell_bound_axis(q.y, g.oy, g.cell, cy, R, g.dy)),
+                                          shell_bound_axis(q.z, g.oz, g.cell, cz, R, g.dz));
+                if (bound == INF) break;  // whole grid visited
+                const unsigned long long kth2 = __shfl_sync(FULL, mykey, K - 1);
+                const float bs = bound - margin;
+                if (kth2 != EMPTY && bs > 0.0f && __uint_as_float((uint32_t)((kth2 - 1ull) >> 32)) < __fmul_rn(bs, bs)) break;
+            }
+        }
+        if (dbg && lane == 0) {
+            dbg[(size_t)w * 6 + 0] = d_cands;
+            dbg[(size_t)w * 6 + 1] = d_scans;
+            dbg[(size_t)w * 6 + 2] = d_merges;
+            dbg[(size_t)w * 6 + 3] = (uint32_t)(clock64() - d_t0);
+            dbg[(size_t)w * 6 + 4] = d_last;
+            dbg[(size_t)w * 6 + 5] = qi;
+        }
+        if (lane >= first && lane < K) {
+            idx[(size_t)qi * k + (lane - first)] = (int)(uint32_t)((mykey - 1ull) & 0xffffffffull);
+            dist[(size_t)qi * k + (lane - first)] = __uint_as_float((uint32_t)((mykey - 1ull) >> 32));
+        }
+    }
+}
+
 template <int K>
 void launch_knn_reg(spx_index_t index, spx_queue_t q, const float4* qs, uint32_t nq, int k, const Xform& T, int has_T,
                     int32_t* idx, float* dist) {
+    const GridLevels& levels = index->levels_knn;  // k >= 2: the first level is the k-NN grid
     q->arena_reset();
     q->arena_reserve((size_t)nq * (8 + 8 * K) + 8192);
     uint32_t* worklist = q->take<uint32_t>(nq);
@@ -655,16 +1017,48 @@ void launch_knn_reg(spx_index_t index, spx_queue_t q, const float4* qs, uint32_t
     int list_levels = 2, list_rings0 = GRID_LEVEL_RINGS;  // tuning aids
     if (const char* e = std::getenv("SPX_KNN_LIST_LEVELS")) list_levels = std::atoi(e);
     if (const char* e = std::getenv("SPX_KNN_LIST_RINGS0")) list_rings0 = std::atoi(e);
-    unsigned int* counters = q->take<unsigned int>(16);  // {list count, list cursor, far count, far cursor}
-    SPX_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), q->stream));
-    grid_knn_reg_first_kernel<K><<<div_up(nq, GRID_THREADS), GRID_THREADS, 0, q->stream>>>(index->levels, qs, nq, k, T, has_T, idx,
-                                                                                         dist, worklist, counters, carry);
+    unsigned int* counters = q->take<unsigned int>(16);  // {list count, list cursor, far count, far cursor, back count}
+    SPX_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned int), q->stream));
+    static const bool legacy = std::getenv("SPX_KNN_LEGACY_LIST") != nullptr;  // tuning aid: the per-lane list + far kernels
+    grid_knn_reg_first_kernel<K><<<div_up(nq, GRID_THREADS), GRID_THREADS, 0, q->stream>>>(levels, qs, nq, k, T, has_T, idx,
+                                                                                         dist, worklist, counters, carry, legacy ? nullptr : counters + 4);
     SPX_LAUNCH_CHECK();
+    if (!legacy) {
+        // one warp per unfinished query, bound-driven (resident grid: the warps pull queries off the list)
+        uint32_t* dbg = nullptr;
+        static const bool debug = std::getenv("SPX_KNN_DEBUG") != nullptr;  // tuning aid: per-query work of the list kernel
+        if (debug) {
+            SPX_CUDA(cudaMalloc(&dbg, (size_t)nq * 6 * sizeof(uint32_t)));
+            SPX_CUDA(cudaMemsetAsync(dbg, 0, (size_t)nq * 6 * sizeof(uint32_t), q->stream));
+        }
+        grid_knn_coop_list_kernel<K><<<q->sm_count * 16, GRID_THREADS, 0, q->stream>>>(levels, qs, nq, k, T, has_T, idx, dist,
+                                                                                   worklist, counters, counters + 1, carry, counters + 4, dbg);
+        if (debug) {
+            SPX_LAUNCH_CHECK();
+            std::vector<uint32_t> h((size_t)nq * 6);
+            unsigned int hc[4];
+            SPX_CUDA(cudaMemcpyAsync(h.data(), dbg, h.size() * 4, cudaMemcpyDeviceToHost, q->stream));
+            SPX_CUDA(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, q->stream));
+            SPX_CUDA(cudaStreamSynchronize(q->stream));
+            cudaFree(dbg);
+            std::vector<size_t> order(nq);
+            for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h[a * 6 + 3] > h[b * 6 + 3]; });
+            unsigned long long tc = 0, tcy = 0;
+            for (size_t i = 0; i < order.size(); ++i) { tc += h[i * 6]; tcy += h[i * 6 + 3]; }
+            fprintf(stderr, "[knn debug] nq %u listed %u total cands %llu mean cycles %llu\n", nq, hc[0], tc, order.empty() ? 0ull : tcy / order.size());
+            for (size_t i = 0; i < std::min<size_t>(12, order.size()); ++i) {
+                const uint32_t* e = &h[order[i] * 6];
+                fprintf(stderr, "   q %u: cands %u scans %u merges %u cycles %u last(L*100+R,+10000 notfull) %u\n", e[5], e[0], e[1], e[2], e[3], e[4]);
+            }
+        }
+        return;
+    }
     grid_knn_reg_list_kernel<K><<<q->sm_count * 16, GRID_THREADS, 0, q->stream>>>(
-        index->levels, qs, nq, k, T, has_T, idx, dist, worklist, counters, counters + 1, far_list, counters + 2, carry,
+        levels, qs, nq, k, T, has_T, idx, dist, worklist, counters, counters + 1, far_list, counters + 2, carry,
         list_levels, list_rings0);
     SPX_LAUNCH_CHECK();
-    grid_knn_far_kernel<K><<<q->sm_count, GRID_THREADS, 0, q->stream>>>(index->levels, qs, k, T, has_T, idx, dist, far_list,
+    grid_knn_far_kernel<K><<<q->sm_count, GRID_THREADS, 0, q->stream>>>(levels, qs, k, T, has_T, idx, dist, far_list,
                                                                        counters + 2, counters + 3);
 }
 
@@ -752,6 +1146,7 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         L.lv[0].dx = L.lv[0].dy = L.lv[0].dz = 1;
         L.lv[0].cell = 1.0f;
         L.lv[0].inv = 1.0f;
+        ix->levels_knn = L;
         if (nt == 0) return;  // empty tree: every search returns -1 / FLT_MAX (kdtree.hpp:296-300)
         const float4* pts = reinterpret_cast<const float4*>(targets);
         const uint32_t n = (uint32_t)nt;
@@ -764,12 +1159,12 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         const uint32_t words_per_map = map_bits / 32u;
         q->arena_reset();
         q->arena_reserve(sizeof(BuildHead) + 1024 + (size_t)OCC_CANDS * words_per_map * 4 +
-                         (MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384) * 4 + 8192);
+                         (2 * MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384) * 4 + 8192);
         BuildHead* head = q->take<BuildHead>(1);
         OccPlan* plan = &head->plan;
         unsigned int* ones = head->ones;
         uint32_t* bitmaps = q->take<uint32_t>((size_t)OCC_CANDS * words_per_map);
-        uint32_t* counts = q->take<uint32_t>(MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384);
+        uint32_t* counts = q->take<uint32_t>(2 * MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384);
 
         BuildHead* hhead = static_cast<BuildHead*>(q->pinned_get(1024));
         unsigned int* hones = hhead->ones;
@@ -821,8 +1216,8 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         // LiDAR-shaped clouds for both the k = 10 and the warm-started k = 1 searches: smaller cells
         // send more queries past the first pass, larger ones add candidates to every query), read off
         // the measured occupancy curve by log-log interpolation between the candidates
-        float cell = cell_size;
-        if (adaptive) {
+        // occupancy curve -> cell edge at which an occupied cell holds `want` points
+        auto cell_for = [&](double want) {
             double avg[OCC_CANDS];
             for (int j = 0; j < OCC_CANDS; ++j) {
                 const double zeros = (double)map_bits - (double)hones[j];
@@ -831,8 +1226,6 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
                 avg[j] = (double)bb.finite / std::max(occ, 1.0);
             }
             static const double F[OCC_CANDS] = {0.35, 0.5, 0.7071, 1.0, 1.4142, 2.0, 2.8284, 4.0};
-            double want = 3.0;
-            if (const char* e = std::getenv("SPX_CELL_TARGET")) want = std::max(0.5, std::atof(e));  // tuning aid
             double f = F[OCC_CANDS - 1];
             if (avg[0] >= want) {
                 f = F[0];
@@ -845,8 +1238,22 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
                     }
             }
             if (bb.finite <= 8) f = 1.0;
-            cell = (float)(pl.c0 * f);
-            cell = std::max(cell, 1e-6f * std::max(max_abs, 1.0f));
+            float c = (float)(pl.c0 * f);
+            return std::max(c, 1e-6f * std::max(max_abs, 1.0f));
+        };
+        float cell = cell_size;
+        float cell_knn = 0.0f;  // edge of the extra first-pass grid of the k >= 2 searches (0: none)
+        if (adaptive) {
+            double want = 3.0, want_knn = 5.0;
+            if (const char* e = std::getenv("SPX_CELL_TARGET")) want = std::max(0.5, std::atof(e));          // tuning aids
+            if (const char* e = std::getenv("SPX_KNN_CELL_TARGET")) want_knn = std::max(0.0, std::atof(e));
+            cell = cell_for(want);
+            // A k-nearest-neighbour search (k ~ 10-20: the covariance stage) wants larger cells than the k = 1 search
+            // of the registration loop: with ~3 points per occupied cell a third of the k = 10 queries cannot be
+            // certified from their 3x3x3 block, with ~5 almost all can (measured: 0.19 -> 0.12 ms at 120 k points),
+            // while the registration iteration slows down by 15 % on such cells.  The index therefore carries ONE
+            // more grid, used only as the first level of the k >= 2 searches.
+            if (want_knn > want * 1.05 && bb.finite > 64) cell_knn = cell_for(want_knn);
         }
         int dims[3];
         for (;;) {  // respect the dense-grid budget
@@ -870,18 +1277,29 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
             cell *= (float)GRID_LEVEL_FACTOR;
             dims_for(cell, dims);
         }
-        ls.n_levels = level + 1;
+        const int n_regular = level + 1;
+        ls.n_levels = n_regular;
+        int knn_dims[3] = {0, 0, 0};
+        if (cell_knn > cells[0] * 1.02f && (n_regular < 2 || cell_knn < cells[1] * 0.9f)) {
+            dims_for(cell_knn, knn_dims);
+            ls.geom[n_regular] = GridGeom{lo[0], lo[1], lo[2], 1.0f / cell_knn, knn_dims[0], knn_dims[1], knn_dims[2]};
+            ls.cell_base[n_regular] = (uint32_t)total_cells;
+            total_cells += (size_t)knn_dims[0] * knn_dims[1] * knn_dims[2];
+            ls.n_levels = n_regular + 1;
+        } else {
+            cell_knn = 0.0f;
+        }
         ls.cell_base[ls.n_levels] = (uint32_t)total_cells;
         SPX_REQUIRE((unsigned long long)ls.n_levels * bb.finite < (1ull << 32) && total_cells + 1 < (1ull << 32),
                     "[KDTree::build] cloud too large for 32-bit index positions");
         // (counts / scan scratch were sized for MAX_CELLS of the finest level + the coarser ones: <= 1/63 more)
-        SPX_REQUIRE(total_cells + 1 <= MAX_CELLS + MAX_CELLS / 32 + 64, "[KDTree::build] internal: cell budget exceeded");
+        SPX_REQUIRE(total_cells + 1 <= 2 * MAX_CELLS + MAX_CELLS / 32 + 64, "[KDTree::build] internal: cell budget exceeded");
 
         SPX_CUDA(cudaMallocAsync(&ix->start[0], (total_cells + 1) * 4, st));
         SPX_CUDA(cudaMallocAsync(&ix->sorted[0], (size_t)ls.n_levels * bb.finite * sizeof(float4), st));
         // per-cell counts and, right behind them, the zeroed ticket + status words of the one-launch scan
         const size_t scan_at = align_up(total_cells + 1, 2);
-        SPX_REQUIRE(scan_at + scan_lookback_words(total_cells + 1) <= MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384,
+        SPX_REQUIRE(scan_at + scan_lookback_words(total_cells + 1) <= 2 * MAX_CELLS + MAX_CELLS / 32 + MAX_CELLS / 1024 + 384,
                     "[KDTree::build] internal: count buffer too small");
         SPX_CUDA(cudaMemsetAsync(counts, 0, (scan_at + scan_lookback_words(total_cells + 1)) * 4, st));
         levels_count_kernel<<<div_up(n, 256), 256, 0, st>>>(pts, n, ls, counts);
@@ -892,17 +1310,28 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         // (the points of a cell stay in the order the scatter's atomics handed out: every search orders its
         // candidates by (distance, original index), so no result depends on it)
         for (int l = 0; l < ls.n_levels; ++l) {
-            GridView& v = L.lv[l];
+            const bool extra = l >= n_regular;  // the k-NN first-pass grid
+            GridView knn_view{};
+            GridView& v = extra ? knn_view : L.lv[l];
+            const float cl = extra ? cell_knn : cells[l];
             v.ox = lo[0]; v.oy = lo[1]; v.oz = lo[2];
-            v.cell = cells[l];
+            v.cell = cl;
             v.inv = ls.geom[l].inv;
             v.dx = ls.geom[l].dx; v.dy = ls.geom[l].dy; v.dz = ls.geom[l].dz;
-            v.margin = 1e-3f * cells[l] + 2e-6f * (max_abs + max_ext);
+            v.margin = 1e-3f * cl + 2e-6f * (max_abs + max_ext);
             v.start = ix->start[0] + ls.cell_base[l];
             v.pts = ix->sorted[0];  // common base: `start` values of level l already include l * n
             v.n = bb.finite;
+            if (extra) ix->levels_knn.lv[0] = knn_view;
         }
-        L.n_levels = level + 1;
+        L.n_levels = n_regular;
+        // the level list of the k >= 2 searches: the extra grid first, then the regular levels above the finest
+        if (cell_knn > 0.0f) {
+            ix->levels_knn.n_levels = n_regular;
+            for (int l = 1; l < n_regular; ++l) ix->levels_knn.lv[l] = L.lv[l];
+        } else {
+            ix->levels_knn = L;
+        }
         // no final sync: everything above is ordered on the queue's stream, and so is every search
     });
 }
@@ -1024,7 +1453,7 @@ int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, con
                                               128 * GRID_THREADS * 8));
                 attr_set.fetch_or(bit, std::memory_order_release);
             }
-            grid_knn_kernel<false><<<blocks, GRID_THREADS, smem, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T,
+            grid_knn_kernel<false><<<blocks, GRID_THREADS, smem, q->stream>>>(index->levels_knn, qs, (uint32_t)nq, k, T,
                                                                              has_T, idx, dist);
         }
         SPX_LAUNCH_CHECK();

@@ -9,6 +9,8 @@
 #include <random>
 #include <unordered_map>
 
+#include <cuda_profiler_api.h>
+
 #include "spx_common.cuh"
 
 namespace spx {
@@ -75,6 +77,13 @@ extern "C" {
 const char* spx_last_error(void) { return t_last_error.c_str(); }
 int spx_abi_version(void) { return SPX_ABI_VERSION; }
 uint64_t spx_kernel_launch_count(void) { return g_launches.load(); }
+
+int spx_profiler_range(int start) {
+    return guard([&] {
+        if (start) SPX_CUDA(cudaProfilerStart());
+        else SPX_CUDA(cudaProfilerStop());
+    });
+}
 
 int spx_device_count(int* count) {
     return guard([&] {
