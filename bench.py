@@ -206,9 +206,15 @@ class PairPipeline:
         params.robust.default_scale = 10.0
         self.reg = spx.Registration(q, params)
         self.nn_s, self.nn_t = spx.KNNResult(), spx.KNNResult()
-        self.pool = ThreadPoolExecutor(max_workers=1)
+        self.pool = ThreadPoolExecutor(max_workers=2)
         self.src_done = spx.Event()
         self.last = None
+        # pipelined mode (two pairs in flight): the align of pair s runs on its own queue while both feeder chains
+        # of pair s+1 run on q / q2
+        self.q3 = spx.DeviceQueue(q.device)
+        self.reg3 = spx.Registration(self.q3, params)
+        self.nn_pipe = [(spx.KNNResult(), spx.KNNResult()) for _ in range(2)]
+        self.done_pipe = [(spx.Event(), spx.Event()) for _ in range(2)]
         # resident raw clouds: one (source, target) per rotating pair, sized for the largest
         self.n_src_raw, self.n_tgt_raw = n_src_raw, n_tgt_raw
         self.resident = []
@@ -216,11 +222,15 @@ class PairPipeline:
         # scan pair s+1 overlaps the processing of pair s (what a LiDAR front end does with its frames)
         self.qc = spx.DeviceQueue(q.device)
         self.stream_raw = []
+        self.stream_xyz = []
         for _ in range(2):
             rs, rt = spx.PointCloudShared(self.qc), spx.PointCloudShared(self.qc)
             rs.adopt_points(spx.DeviceArray(self.qc, (max(n_src_raw), 4), np.float32), 0)
             rt.adopt_points(spx.DeviceArray(self.qc, (max(n_tgt_raw), 4), np.float32), 0)
             self.stream_raw.append((rs, rt, spx.Event()))
+            # the host sends packed xyz (12 B per point); the device expands it to xyz1
+            self.stream_xyz.append((spx.DeviceArray(self.qc, (max(n_src_raw), 3), np.float32),
+                                    spx.DeviceArray(self.qc, (max(n_tgt_raw), 3), np.float32)))
 
     def add_resident(self, src_host, tgt_host):
         spx = self.spx
@@ -245,14 +255,17 @@ class PairPipeline:
             done.record(q)  # the other queue waits for this on the device, the host does not
         return cloud, tree
 
-    def stream_upload(self, slot, src_host, tgt_host):
-        """H2D of one pair's raw clouds (pinned source) into buffer set `slot`, on the copy queue"""
+    def stream_upload(self, slot, src_xyz_host, tgt_xyz_host):
+        """H2D of one pair's raw clouds (pinned packed-xyz source) into buffer set `slot`, on the copy queue, and their
+        expansion to xyz1 on the device"""
         spx = self.spx
         rs, rt, ev = self.stream_raw[slot]
+        xs, xt = self.stream_xyz[slot]
         L = spx.lib()
-        spx._lib.check(L.spx_memcpy_h2d(self.qc.handle, rt.points.ptr, tgt_host.ctypes.data, tgt_host.nbytes))
-        spx._lib.check(L.spx_memcpy_h2d(self.qc.handle, rs.points.ptr, src_host.ctypes.data, src_host.nbytes))
-        rs._n, rt._n = len(src_host), len(tgt_host)
+        spx._lib.check(L.spx_memcpy_h2d(self.qc.handle, xt.ptr, tgt_xyz_host.ctypes.data, tgt_xyz_host.nbytes))
+        rt.set_points_xyz(xt, len(tgt_xyz_host))
+        spx._lib.check(L.spx_memcpy_h2d(self.qc.handle, xs.ptr, src_xyz_host.ctypes.data, src_xyz_host.nbytes))
+        rs.set_points_xyz(xs, len(src_xyz_host))
         ev.record(self.qc)
 
     def run_streamed(self, slot):
@@ -265,6 +278,32 @@ class PairPipeline:
         res = self.reg.align(src, tgt, tree_t)
         self.last = (src, tgt, tree_t, res)
         tree_s.close()
+        return res
+
+    def feeders_async(self, which, slot, start_event=None, streamed=False):
+        """both chains of one pair (resident buffer set `which`, or streamed buffer set `which` once its upload has
+        landed) on q / q2, each on its own pool thread; returns the two futures"""
+        if streamed:
+            rs, rt, ev = self.stream_raw[which]
+        else:
+            (rs, rt), ev = self.resident[which], start_event
+        nn_s, nn_t = self.nn_pipe[slot]
+        ds, dt_ = self.done_pipe[slot]
+        return (self.pool.submit(self._chain, self.q2, self.vg2, rs, nn_s, ev, ds),
+                self.pool.submit(self._chain, self.q, self.vg, rt, nn_t, ev, dt_))
+
+    def align_pipelined(self, futs, slot):
+        """align of the pair whose feeders are `futs`, on the third queue (the feeders of the next pair may already
+        be running on q / q2)"""
+        src, tree_s = futs[0].result()
+        tgt, tree_t = futs[1].result()
+        ds, dt_ = self.done_pipe[slot]
+        self.q3.wait_event(ds)
+        self.q3.wait_event(dt_)
+        res = self.reg3.align(src, tgt, tree_t)
+        self.last = (src, tgt, tree_t, res)
+        tree_s.close()
+        tree_t.close()
         return res
 
     def run(self, which, start_event=None):
@@ -366,19 +405,19 @@ def workload_pair(ctx):
     args, spx, q = ctx.args, ctx.spx, ctx.q
     # every rank drives two queues from two host threads; when that oversubscribes the host's cores
     # the queues wait on an OS primitive instead of spinning (SPX_BENCH_SYNC=spin|block overrides)
-    sync_mode = os.environ.get("SPX_BENCH_SYNC", "block" if 2 * ctx.world > (os.cpu_count() or 1) // 2 else "spin")
+    sync_mode = os.environ.get("SPX_BENCH_SYNC", "block" if 3 * ctx.world > (os.cpu_count() or 1) // 2 else "spin")
     pairs = rotating_pairs(ctx.rank)
     pipe = PairPipeline(spx, q, [len(p[1]) for p in pairs], [len(p[0]) for p in pairs])
     if sync_mode == "block":
-        for qq in (q, pipe.q2, pipe.qc):
+        for qq in (q, pipe.q2, pipe.qc, pipe.q3):
             qq.set_blocking_sync(True)
     pins = []
     for tgt_raw, src_raw, _ in pairs:
-        ps, pt = spx.PinnedArray(src_raw.shape), spx.PinnedArray(tgt_raw.shape)
-        ps.array[...] = src_raw
-        pt.array[...] = tgt_raw
+        ps, pt = spx.PinnedArray((len(src_raw), 3)), spx.PinnedArray((len(tgt_raw), 3))
+        ps.array[...] = src_raw[:, :3]
+        pt.array[...] = tgt_raw[:, :3]
         pins.append((ps, pt))
-        pipe.add_resident(ps.array, pt.array)
+        pipe.add_resident(src_raw, tgt_raw)
 
     W = max(args.warmup, N_ROTATE + 1)
     for w in range(W):
@@ -405,10 +444,40 @@ def workload_pair(ctx):
         per_pair[s % N_ROTATE] = (pipe.last[0].size(), pipe.last[1].size(), t["iterations"], res)
     ctx.barrier(pipe.q2, pipe.qc)
     wall = time.perf_counter() - wall0
-    gpu_launches = spx.kernel_launch_count() - launches0
-    clocks = sampler.stop()
+    serial_launches = spx.kernel_launch_count() - launches0
     step_ms = [a.elapsed_ms(b) for a, b in ev]
-    total_ms = float(np.sum(step_ms))
+    serial_ms = float(np.sum(step_ms))
+    # ---------------- throughput: two pairs in flight (the feeders of pair s+1 overlap the align of pair s)
+    def pipelined(n_steps, streamed):
+        a, b = spx.Event(), spx.Event()
+        ctx.barrier(pipe.q2, pipe.qc, pipe.q3)
+        ctx.l2_flush()
+        a.record(q)
+        for qq in (pipe.q2, pipe.qc, pipe.q3):
+            qq.wait_event(a)
+        if streamed:
+            pipe.stream_upload(0, pins[0][0].array, pins[0][1].array)
+        futs = pipe.feeders_async(0, 0, a, streamed)
+        for s in range(n_steps):
+            nxt = None
+            if s + 1 < n_steps:
+                if streamed:
+                    # the buffer set of pair s+1 was last read by the feeders of pair s-1: they are done (their align ran)
+                    pipe.stream_upload((s + 1) % 2, pins[(s + 1) % N_ROTATE][0].array, pins[(s + 1) % N_ROTATE][1].array)
+                    nxt = pipe.feeders_async((s + 1) % 2, (s + 1) % 2, None, True)
+                else:
+                    nxt = pipe.feeders_async((s + 1) % N_ROTATE, (s + 1) % 2, None, False)
+            pipe.align_pipelined(futs, s % 2)
+            futs = nxt
+        b.record(pipe.q3)
+        ctx.barrier(pipe.q2, pipe.qc, pipe.q3)
+        return float(a.elapsed_ms(b))
+
+    pipelined(4, False)
+    launches1 = spx.kernel_launch_count()
+    total_ms = pipelined(args.steps, False)
+    gpu_launches = spx.kernel_launch_count() - launches1
+    clocks = sampler.stop()
     for j in range(N_ROTATE):
         if j not in per_pair:
             res = pipe.run(j)
@@ -417,22 +486,9 @@ def workload_pair(ctx):
     # Every step's inputs are copied from pinned host memory inside the timed region and every
     # step's result struct is read back (align synchronises); one bracket around the K steps because
     # consecutive steps overlap.
-    for j in range(2):
-        pipe.stream_upload(j % 2, pins[j % N_ROTATE][0].array, pins[j % N_ROTATE][1].array)
-        pipe.run_streamed(j % 2)
-    e2e_a, e2e_b = spx.Event(), spx.Event()
-    ctx.barrier(pipe.q2, pipe.qc)
-    ctx.l2_flush()
-    e2e_a.record(q)
-    pipe.qc.wait_event(e2e_a)  # the first upload starts inside the bracket
-    pipe.stream_upload(0, pins[0][0].array, pins[0][1].array)
-    for s in range(args.steps):
-        if s + 1 < args.steps:  # prefetch the next pair
-            pipe.stream_upload((s + 1) % 2, pins[(s + 1) % N_ROTATE][0].array, pins[(s + 1) % N_ROTATE][1].array)
-        pipe.run_streamed(s % 2)
-    e2e_b.record(q)
-    ctx.barrier(pipe.q2, pipe.qc)
-    e2e_ms = float(e2e_a.elapsed_ms(e2e_b))
+    pipelined(4, True)
+    e2e_ms = pipelined(args.steps, True)
+    serial_ms, = ctx.max_over_ranks(serial_ms)
     total_ms, e2e_ms = ctx.max_over_ranks(total_ms, e2e_ms)
     gpu_launches = int(ctx.sum_over_ranks(float(gpu_launches))[0])
 
@@ -458,7 +514,7 @@ def workload_pair(ctx):
     for j in range(N_ROTATE):
         dT = np.linalg.inv(pairs[j][2].astype(np.float64)) @ per_pair[j][3].T.astype(np.float64)
         errs.append(float(np.linalg.norm(dT[:3, 3])))
-    raw_bytes = int(np.mean([p[0].nbytes + p[1].nbytes for p in pairs]))
+    raw_bytes = int(np.mean([ps.array.nbytes + pt.array.nbytes for ps, pt in pins]))
     metric, unit, hib, scaling = METRICS["pair"]
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": ctx.world, "steps": args.steps,
@@ -472,12 +528,16 @@ def workload_pair(ctx):
                     "host_cores": os.cpu_count(), "pose_error_vs_gt_m": errs},
         "ms_per_iter": kern_ms,
         "align_loop_ms": float(np.mean(loop_ms)),
+        "latency_ms_per_pair": serial_ms / args.steps,
+        "pipeline": "value / e2e: two pairs in flight (both feeder chains of pair s+1 on two queues while the align of pair "
+                    "s runs on a third), CUDA events around the K steps; latency_ms_per_pair, ms_per_iter and roofline: one "
+                    "pair at a time, L2 flushed before every step, events around every step / align launch",
         "wall_s": wall,
         "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": raw_bytes,
                 "d2h_bytes_per_step": 428 + 2 * 8 + 4 * 8,
-                "note": "streaming: the H2D of pair s+1 (copy queue, double-buffered) overlaps the processing of "
-                        "pair s; every step copies its own 65 MB of raw points in and reads its result struct, "
-                        "voxel counts and index-build scalars back"},
+                "note": "streaming: the H2D of pair s+1 (copy queue, double-buffered) and its feeder chains overlap the "
+                        "align of pair s; every step copies its own raw points in as packed xyz (12 B per point, ~49 MB, "
+                        "expanded to xyz1 on the device) and reads its result struct, voxel counts and index-build scalars back"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "align_batch_kernel<GICP> (persistent cooperative launch: nearest neighbour + "

@@ -207,6 +207,11 @@ SPX_API int spx_normals(spx_queue_t q, const float* points, size_t n, const int3
 /* covariance::extract_normals_async(points) — covariance.hpp:467-495 */
 SPX_API int spx_normals_from_covs(spx_queue_t q, const float* points, const float* covs, size_t n, float* normals);
 
+/* PointCloudShared(queue, PointCloudCPU) — I/points/point_cloud.hpp:110-198 copies Vector4f points (xyz1, 16 B) to the
+ * device.  A LiDAR driver delivers packed xyz: this expands float[n][3] (device) to float[n][4] with w = 1 on the
+ * device, so that the host-to-device copy of a raw scan carries 12 instead of 16 bytes per point.  Asynchronous. */
+SPX_API int spx_points_from_xyz(spx_queue_t q, const float* xyz, size_t n, float* points);
+
 /* eigen_utils::symmetric_eigen_decomposition_3x3 — I/utils/eigen_utils.hpp:443-562 — applied to the
  * upper-left 3x3 of n stored covariances (which must be symmetric, as covariance::estimate writes
  * them: the upper triangle is read).  evals[n][3] ascending; evecs[n][9] row-major 3x3 whose column

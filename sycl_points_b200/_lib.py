@@ -130,6 +130,7 @@ def lib() -> C.CDLL:
         "spx_covariance": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals_from_covs": (C.c_int, [vp, f32p, f32p, sz, f32p]),
+        "spx_points_from_xyz": (C.c_int, [vp, f32p, sz, f32p]),
         "spx_eigen3": (C.c_int, [vp, f32p, sz, f32p, f32p]),
         "spx_covariance_update_plane": (C.c_int, [vp, f32p, sz]),
         "spx_transform": (C.c_int, [vp, f32p, f32p, f32p, sz, hostf]),

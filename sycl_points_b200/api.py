@@ -289,6 +289,12 @@ class PointCloudShared:
         self.timestamp_offsets = DeviceArray.from_host(self.queue,
                                                        np.ascontiguousarray(v, dtype=np.float32).reshape(-1))
 
+    def set_points_xyz(self, xyz_dev: DeviceArray, n: int):
+        """points <- packed xyz (device float[n][3]) expanded to xyz1 on the device (spx_points_from_xyz); the
+        points array must already be allocated with room for n points.  Asynchronous."""
+        check(_lib.lib().spx_points_from_xyz(self.queue.handle, xyz_dev.ptr, n, self.points.ptr))
+        self._n = n
+
     def adopt_points(self, dev: DeviceArray, n: int):
         self.points = dev
         self._n = n

@@ -1,5 +1,7 @@
 // Per-point covariance and normal estimation from k neighbours
 // (I/algorithms/feature/covariance.hpp:16-74,260-311,417-495).
+#include <algorithm>
+
 #include "spx_math.cuh"
 
 using namespace spx;
@@ -108,6 +110,12 @@ __global__ void __launch_bounds__(FEAT_THREADS) update_plane_kernel(float* __res
     store_cov16(covs + (size_t)i * 16, plane_regularize(load_cov16(covs + (size_t)i * 16)));
 }
 
+// packed xyz (12 B per point, what a LiDAR driver delivers) -> PointType xyz1 (types.hpp:11: Vector4f, w = 1)
+__global__ void __launch_bounds__(256) expand_xyz_kernel(const float* __restrict__ xyz, uint32_t n, float4* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        out[i] = make_float4(__ldg(xyz + 3 * (size_t)i), __ldg(xyz + 3 * (size_t)i + 1), __ldg(xyz + 3 * (size_t)i + 2), 1.0f);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ cloud transform
@@ -208,6 +216,19 @@ int spx_normals_from_covs(spx_queue_t q, const float* points, const float* covs,
         DeviceGuard g(q->device);
         normals_from_covs_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
             reinterpret_cast<const float4*>(points), covs, (uint32_t)n, reinterpret_cast<float4*>(normals));
+        SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_points_from_xyz(spx_queue_t q, const float* xyz, size_t n, float* points) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[PointCloudShared] null queue");
+        SPX_REQUIRE(n < (1ull << 31), "[PointCloudShared] too many points");
+        if (n == 0) return;
+        SPX_REQUIRE(xyz && points, "[PointCloudShared] null pointer");
+        DeviceGuard g(q->device);
+        expand_xyz_kernel<<<std::min(div_up(n, 256), q->sm_count * 16), 256, 0, q->stream>>>(xyz, (uint32_t)n,
+                                                                                       reinterpret_cast<float4*>(points));
         SPX_LAUNCH_CHECK();
     });
 }

@@ -633,131 +633,193 @@ __device__ __forceinline__ int icp_first_pass(const GridView& g, float qx, float
     return ((bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) || bs >= max_radius) ? 1 : 0;
 }
 
-// Warp-cooperative continuation for ONE query (all arguments warp-uniform, every lane calls it):
-// shells r = 2.. on the finest level, then r = 1.. on each coarser level, rows of a shell spread
-// over the lanes, candidates of all rows scanned 32 wide.  `best` is warp-uniform on entry and exit.
+// Warp-cooperative continuation for ONE query (all arguments warp-uniform, every lane calls it).  `best` holds what
+// the per-lane first pass left: usually a real candidate (the warm start or a point of the 3x3x3 block), whose
+// distance bounds the answer.  Instead of walking shell after shell, the warp picks the finest (level, ring radius)
+// whose block CERTIFIES that bound — everything outside is farther than min(best, max_radius) — and finishes the
+// query with ONE scan of it: rows (z, y) spread over the lanes and pruned against the bound, x-ranges trimmed, the
+// ring-1 cells of the finest level (covered by the first pass) skipped, candidates of all rows scanned 32 wide.
+// A query without any candidate and without a radius bound first grows its block until it holds a point (counted
+// from the cell ranges, nothing scanned).  `best` is warp-uniform on entry and exit.
+constexpr int ICP_RMAX = 5;  // largest ring radius on a level that is not the coarsest (11 cells < the next level's 12)
+
 static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float qx, float qy, float qz, Best1& best,
                                                     float max_radius, uint32_t* dbg = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const float INF = __int_as_float(0x7f800000);
-    for (int l = 0; l < gl.n_levels; ++l) {
-        const GridView& g = gl.lv[l];
-        const bool last = (l == gl.n_levels - 1);
+    int l_min = 0, r_done = 1;  // level 0: the first pass covered ring 1
+    for (;;) {
+        int L = l_min, R = r_done + 1;
+        bool found = false;
+        if (best.d < 1.0e30f || max_radius < 1.8e19f) {  // there is something to certify: a candidate or a radius
+            for (int l = l_min; l < gl.n_levels && !found; ++l) {
+                const GridView& g = gl.lv[l];
+                const bool last = l == gl.n_levels - 1;
+                const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
+                const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
+                const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
+                const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+                const int r_first = (l == l_min) ? r_done + 1 : 1;
+                const int r_last = last ? (1 << 20) : ICP_RMAX;
+                for (int r = r_first; r <= r_last; ++r) {
+                    const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, r, g.dx),
+                                                    shell_bound_axis(qy, g.oy, g.cell, cy, r, g.dy)),
+                                              shell_bound_axis(qz, g.oz, g.cell, cz, r, g.dz));
+                    const float bs = bound - margin;
+                    if (bound == INF || (bs > 0.0f && best.d < __fmul_rn(bs, bs)) || bs >= max_radius) {
+                        L = l;
+                        R = r;
+                        found = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (!found) {
+            // no candidate and no radius: the smallest block of the growth sequence that holds a point at all
+            int l = l_min, r = r_done;
+            for (;;) {
+                const bool last = l == gl.n_levels - 1;
+                if (last || r < ICP_RMAX) {
+                    ++r;
+                } else {
+                    ++l;
+                    r = 1;
+                }
+                const GridView& g = gl.lv[l];
+                const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
+                const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
+                const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
+                const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
+                const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
+                const int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
+                const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+                uint32_t c = 0;
+                for (int t = lane; t < nrows; t += 32) {
+                    const uint32_t row = ((uint32_t)(z0 + t / ny) * (uint32_t)g.dy + (uint32_t)(y0 + t % ny)) * (uint32_t)g.dx;
+                    c += __ldg(g.start + row + xb + 1) - __ldg(g.start + row + xa);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+                const bool whole = z0 == 0 && y0 == 0 && xa == 0 && z1 == g.dz - 1 && y1 == g.dy - 1 && xb == g.dx - 1;
+                if (c > 0u || whole) break;
+            }
+            L = l;
+            R = r;
+        }
+        // ---- one scan of block (L, R), cells within ring r_skip of the same level excluded
+        const GridView& g = gl.lv[L];
+        const int r_skip = (L == l_min) ? r_done : -1;
         const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
         const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
         const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
         const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+        // what has to be beaten: the current candidate, or the search radius (+ allowance)
         const float reach = max_radius + margin;
-        const float reach2 = reach < 1.8e19f ? __fmul_rn(reach, reach) : INF;
-        const int r_begin = (l == 0) ? 2 : 1;
-        const int r_max = last ? (1 << 20) : GRID_LEVEL_RINGS;
-        // (Skipping a level whose last shell cannot certify the current candidate was tried and is a
-        // large loss: the candidate is often NOT the answer — a wall one metre away is found by the
-        // next fine shell for a handful of candidates, but costs thousands on the coarser level.)
-        for (int r = r_begin;; ++r) {
-            const bool merged = (r == 1);  // first shell on a coarser level: the whole 3x3x3 block
-            const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
-            const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
-            const int ny = y1 - y0 + 1;
-            const int nrows = (z1 - z0 + 1) * ny;
-            Best1 mine = best;  // per-lane candidate, merged after the shell
-            const float lim2 = fminf(best.d, reach2);
-            if (dbg) {
-                dbg[1] += 1;
-                dbg[2] += (uint32_t)nrows;
-            }
-            for (int base = 0; base < nrows; base += 32) {
-                const int t = base + lane;
-                uint32_t sA = 0, eA = 0, sB = 0, eB = 0;
-                if (t < nrows) {
-                    const int zz = z0 + t / ny, yy = y0 + t % ny;
-                    const bool edge = merged || (zz - cz == r) || (cz - zz == r) || (yy - cy == r) || (cy - yy == r);
-                    int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
-                    bool ok = true;
-                    if (lim2 < 1.0e30f) {
-                        const float gz = axis_gap(qz, g.oz, g.cell, zz);
-                        const float gy = axis_gap(qy, g.oy, g.cell, yy);
-                        const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
-                        const float gyz2 = __fmul_rn(gyz, gyz);
-                        ok = gyz2 <= lim2;
-                        const float w = sqrtf(fmaxf(lim2 - gyz2, 0.0f)) + margin;
-                        xa = max(xa, grid_coord(qx - w, g.ox, g.inv, g.dx));
-                        xb = min(xb, grid_coord(qx + w, g.ox, g.inv, g.dx));
-                        ok = ok && xa <= xb;
-                    }
-                    if (ok) {
-                        const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
-                        if (edge) {
-                            sA = __ldg(g.start + row + xa);
-                            eA = __ldg(g.start + row + xb + 1);
-                        } else {  // interior row of a later shell: only the two end cells are new
-                            if (cx - r >= xa) {
-                                sA = __ldg(g.start + row + (cx - r));
-                                eA = __ldg(g.start + row + (cx - r) + 1);
-                            }
-                            if (cx + r <= xb) {
-                                sB = __ldg(g.start + row + (cx + r));
-                                eB = __ldg(g.start + row + (cx + r) + 1);
-                            }
+        const float lim2 = fminf(best.d, reach < 1.8e19f ? __fmul_rn(reach, reach) : INF);
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
+        const int ny = y1 - y0 + 1;
+        const int nrows = (z1 - z0 + 1) * ny;
+        Best1 mine = best;  // per-lane candidate, merged after the scan
+        if (dbg) {
+            dbg[1] += 1;
+            dbg[2] += (uint32_t)nrows;
+        }
+        for (int base = 0; base < nrows; base += 32) {
+            const int t = base + lane;
+            uint32_t sA = 0, eA = 0, sB = 0, eB = 0;
+            if (t < nrows) {
+                const int zz = z0 + t / ny, yy = y0 + t % ny;
+                const bool outer = max(abs(zz - cz), abs(yy - cy)) > r_skip;
+                int xa = max(cx - R, 0), xb = min(cx + R, g.dx - 1);
+                bool ok = true;
+                if (lim2 < 1.0e30f) {
+                    const float gz = axis_gap(qz, g.oz, g.cell, zz);
+                    const float gy = axis_gap(qy, g.oy, g.cell, yy);
+                    const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
+                    const float gyz2 = __fmul_rn(gyz, gyz);
+                    ok = gyz2 <= lim2;
+                    const float w = sqrtf(fmaxf(lim2 - gyz2, 0.0f)) + margin;
+                    xa = max(xa, grid_coord(qx - w, g.ox, g.inv, g.dx));
+                    xb = min(xb, grid_coord(qx + w, g.ox, g.inv, g.dx));
+                    ok = ok && xa <= xb;
+                }
+                if (ok) {
+                    const uint32_t row = ((uint32_t)zz * (uint32_t)g.dy + (uint32_t)yy) * (uint32_t)g.dx;
+                    if (outer) {
+                        sA = __ldg(g.start + row + xa);
+                        eA = __ldg(g.start + row + xb + 1);
+                    } else {  // only the cells beyond the ring already covered: the two ends of the row
+                        const int la = xa, lb = min(xb, cx - r_skip - 1);
+                        const int ra = max(xa, cx + r_skip + 1), rb = xb;
+                        if (la <= lb) {
+                            sA = __ldg(g.start + row + la);
+                            eA = __ldg(g.start + row + lb + 1);
+                        }
+                        if (ra <= rb) {
+                            sB = __ldg(g.start + row + ra);
+                            eB = __ldg(g.start + row + rb + 1);
                         }
                     }
                 }
-                const uint32_t cA = eA - sA, cnt = cA + (eB - sB);
-                uint32_t inc = cnt;  // inclusive prefix sum of the candidate counts over the lanes
+            }
+            const uint32_t cA = eA - sA, cnt = cA + (eB - sB);
+            uint32_t inc = cnt;  // inclusive prefix sum of the candidate counts over the lanes
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t v = __shfl_up_sync(FULL, inc, o);
-                    if (lane >= o) inc += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const uint32_t total = __shfl_sync(FULL, inc, 31);
+            if (dbg) dbg[3] += total;
+            for (uint32_t cb = 0; cb < total; cb += 32) {
+                const uint32_t kk = cb + lane;
+                const bool live = kk < total;
+                const uint32_t key = live ? kk : 0u;
+                int owner = 0;  // number of lanes whose inclusive sum is <= key
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const uint32_t v = __shfl_sync(FULL, inc, owner + sft - 1);
+                    if (v <= key) owner += sft;
                 }
-                const uint32_t total = __shfl_sync(FULL, inc, 31);
-                if (dbg) dbg[3] += total;
-                for (uint32_t cb = 0; cb < total; cb += 32) {
-                    const uint32_t kk = cb + lane;
-                    const bool live = kk < total;
-                    const uint32_t key = live ? kk : 0u;
-                    int owner = 0;  // number of lanes whose inclusive sum is <= key
-#pragma unroll
-                    for (int sft = 16; sft > 0; sft >>= 1) {
-                        const uint32_t v = __shfl_sync(FULL, inc, owner + sft - 1);
-                        if (v <= key) owner += sft;
-                    }
-                    owner = min(owner, 31);
-                    const uint32_t o_inc = __shfl_sync(FULL, inc, owner);
-                    const uint32_t o_cnt = __shfl_sync(FULL, cnt, owner);
-                    const uint32_t o_cA = __shfl_sync(FULL, cA, owner);
-                    const uint32_t o_sA = __shfl_sync(FULL, sA, owner);
-                    const uint32_t o_sB = __shfl_sync(FULL, sB, owner);
-                    if (live) {
-                        const uint32_t jj = key - (o_inc - o_cnt);
-                        const uint32_t pos = jj < o_cA ? o_sA + jj : o_sB + (jj - o_cA);
-                        const float4 p = __ldg(g.pts + pos);
-                        mine.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), pos);
-                    }
+                owner = min(owner, 31);
+                const uint32_t o_inc = __shfl_sync(FULL, inc, owner);
+                const uint32_t o_cnt = __shfl_sync(FULL, cnt, owner);
+                const uint32_t o_cA = __shfl_sync(FULL, cA, owner);
+                const uint32_t o_sA = __shfl_sync(FULL, sA, owner);
+                const uint32_t o_sB = __shfl_sync(FULL, sB, owner);
+                if (live) {
+                    const uint32_t jj = key - (o_inc - o_cnt);
+                    const uint32_t pos = jj < o_cA ? o_sA + jj : o_sB + (jj - o_cA);
+                    const float4 p = __ldg(g.pts + pos);
+                    mine.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), pos);
                 }
             }
-            // merge the lanes' candidates: minimum by (dist, index)
-            unsigned long long k = best_key(mine.d, mine.i);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long v = __shfl_xor_sync(FULL, k, o);
-                k = v < k ? v : k;
-            }
-            const unsigned win = __ballot_sync(FULL, best_key(mine.d, mine.i) == k);
-            const int wl = __ffs(win) - 1;
-            best.d = __shfl_sync(FULL, mine.d, wl);
-            best.i = __shfl_sync(FULL, mine.i, wl);
-            best.p = __shfl_sync(FULL, mine.p, wl);
-
-            const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, r, g.dx),
-                                            shell_bound_axis(qy, g.oy, g.cell, cy, r, g.dy)),
-                                      shell_bound_axis(qz, g.oz, g.cell, cz, r, g.dz));
-            if (bound == INF) return;  // whole grid visited
-            const float bs = bound - margin;
-            if (bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) return;
-            if (bs >= max_radius) return;  // everything within max_radius has been seen
-            if (r >= r_max) break;         // next (coarser) level
         }
+        // merge the lanes' candidates: minimum by (dist, index)
+        unsigned long long k = best_key(mine.d, mine.i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long v = __shfl_xor_sync(FULL, k, o);
+            k = v < k ? v : k;
+        }
+        const unsigned win = __ballot_sync(FULL, best_key(mine.d, mine.i) == k);
+        const int wl = __ffs(win) - 1;
+        best.d = __shfl_sync(FULL, mine.d, wl);
+        best.i = __shfl_sync(FULL, mine.i, wl);
+        best.p = __shfl_sync(FULL, mine.p, wl);
+        l_min = L;
+        r_done = R;
+        // stop test of the block just completed (grid_search's)
+        const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, R, g.dx),
+                                        shell_bound_axis(qy, g.oy, g.cell, cy, R, g.dy)),
+                                  shell_bound_axis(qz, g.oz, g.cell, cz, R, g.dz));
+        if (bound == INF) return;  // whole grid visited
+        const float bs = bound - margin;
+        if (bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) return;
+        if (bs >= max_radius) return;  // everything within max_radius has been seen
     }
 }
 

@@ -805,6 +805,10 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs 
 // barrier -> factor pass + chunk rows -> barrier -> fold + 6x6 solve (P = 1: every block, redundantly, no
 // further barrier; P > 1: pair p by block p mod gridDim.x, then a barrier).
 constexpr int CHUNK = LIN_THREADS;
+// resident CTAs per SM the persistent kernel is compiled for: the search phases are latency-bound and want warps,
+// the factor pass wants registers.  Measured (B200): one pair of 120 k points 74 / 71 / 69 us per iteration at
+// 2 / 3 / 4 CTAs, a batch of 64 pairs of 66 k points 2.56 / 2.19 / 2.31 ms.
+constexpr int ALIGN_CTAS_SINGLE = 4, ALIGN_CTAS_BATCH = 3;
 
 struct PairDesc {
     const float4* src_pts;
@@ -860,8 +864,8 @@ __device__ __forceinline__ Xform pose_ldcg(const RegState* st) {
     return T;
 }
 
-template <int REG>
-__global__ void __launch_bounds__(LIN_THREADS, 2) align_batch_kernel(const BatchArgs a, int max_iterations) {
+template <int REG, int CTAS>
+__global__ void __launch_bounds__(LIN_THREADS, CTAS) align_batch_kernel(const BatchArgs a, int max_iterations) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double fold[LIN_WARPS][32];
@@ -1649,12 +1653,18 @@ void launch_align_gn(int reg_type, LinArgs& a, int max_it, spx_queue_t q, spx_re
     SPX_LAUNCH_CHECK();
 }
 
-template <int REG>
-unsigned batch_coop_blocks(int device_sm_count) {
+template <int REG, int CTAS>
+unsigned batch_coop_blocks(int device_sm_count, const void** fn) {
     static int per_sm = 0;
     if (per_sm == 0)
-        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_batch_kernel<REG>, LIN_THREADS, 0));
+        SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_batch_kernel<REG, CTAS>, LIN_THREADS, 0));
+    *fn = (const void*)align_batch_kernel<REG, CTAS>;
     return (unsigned)std::max(per_sm, 1) * (unsigned)device_sm_count;
+}
+template <int REG>
+unsigned batch_coop_pick(bool single, int device_sm_count, const void** fn) {
+    return single ? batch_coop_blocks<REG, ALIGN_CTAS_SINGLE>(device_sm_count, fn)
+                  : batch_coop_blocks<REG, ALIGN_CTAS_BATCH>(device_sm_count, fn);
 }
 
 template <typename T>
@@ -1839,24 +1849,13 @@ void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs,
         a.crit_trans = Pm.criteria_translation;
         a.phase = r->phase;
         unsigned resident;
-        const void* fn;
+        const void* fn = nullptr;
+        const bool one = n_active == 1;
         switch (Pm.reg_type) {
-            case SPX_REG_POINT_TO_POINT:
-                resident = batch_coop_blocks<SPX_REG_POINT_TO_POINT>(q->sm_count);
-                fn = (const void*)align_batch_kernel<SPX_REG_POINT_TO_POINT>;
-                break;
-            case SPX_REG_POINT_TO_PLANE:
-                resident = batch_coop_blocks<SPX_REG_POINT_TO_PLANE>(q->sm_count);
-                fn = (const void*)align_batch_kernel<SPX_REG_POINT_TO_PLANE>;
-                break;
-            case SPX_REG_POINT_TO_DISTRIBUTION:
-                resident = batch_coop_blocks<SPX_REG_POINT_TO_DISTRIBUTION>(q->sm_count);
-                fn = (const void*)align_batch_kernel<SPX_REG_POINT_TO_DISTRIBUTION>;
-                break;
-            default:
-                resident = batch_coop_blocks<SPX_REG_GICP>(q->sm_count);
-                fn = (const void*)align_batch_kernel<SPX_REG_GICP>;
-                break;
+            case SPX_REG_POINT_TO_POINT: resident = batch_coop_pick<SPX_REG_POINT_TO_POINT>(one, q->sm_count, &fn); break;
+            case SPX_REG_POINT_TO_PLANE: resident = batch_coop_pick<SPX_REG_POINT_TO_PLANE>(one, q->sm_count, &fn); break;
+            case SPX_REG_POINT_TO_DISTRIBUTION: resident = batch_coop_pick<SPX_REG_POINT_TO_DISTRIBUTION>(one, q->sm_count, &fn); break;
+            default: resident = batch_coop_pick<SPX_REG_GICP>(one, q->sm_count, &fn); break;
         }
         unsigned blocks = std::max(1u, std::min((unsigned)total_chunks, resident));
         // reserved[0] = cap on the persistent grid (0 = one full wave): lets several aligns share one GPU

@@ -306,3 +306,14 @@ def test_queue_with_priority_runs_the_same_path(spx, priority):
     got = spx.VoxelGrid(qp, 0.5).downsampling(spx.PointCloudShared(qp, pts)).points_host()
     assert np.array_equal(got, oracle.voxel_downsample(pts, 0.5))
     qp.close()
+
+
+def test_points_from_packed_xyz(spx, q):
+    rs = np.random.RandomState(2)
+    xyz = rs.normal(0, 30, (10001, 3)).astype(np.float32)
+    d = spx.DeviceArray.from_host(q, xyz)
+    cloud = spx.PointCloudShared(q)
+    cloud.adopt_points(spx.DeviceArray(q, (len(xyz), 4), np.float32), 0)
+    cloud.set_points_xyz(d, len(xyz))
+    got = cloud.points_host()
+    assert np.array_equal(got[:, :3], xyz) and (got[:, 3] == 1.0).all()
