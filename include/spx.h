@@ -54,7 +54,7 @@ typedef enum spx_reg_type {
     SPX_REG_POINT_TO_PLANE = 1,
     SPX_REG_POINT_TO_DISTRIBUTION = 2,
     SPX_REG_GICP = 3,
-    SPX_REG_GENZ = 4 /* not built: SPX_ERR_UNSUPPORTED */
+    SPX_REG_GENZ = 4 /* factor.hpp:378-449: plane factor x alpha / point factor x (1 - alpha), alpha recounted per linearisation */
 } spx_reg_type;
 
 /* I/algorithms/robust/robust.hpp:14-20 */
@@ -101,7 +101,9 @@ typedef struct spx_registration_params {
     float dogleg_eta2;          /* .75 */
     float dogleg_gamma_decrease;/* .25 */
     float dogleg_gamma_increase;/* 2 */
-    int32_t reserved[8];        /* [0]: cap on the align kernel's persistent grid (blocks, 0 = auto); rest must be zero */
+    int32_t max_grid_blocks;    /* cap on the align kernel's persistent grid (blocks, 0 = auto: one full wave) */
+    float genz_planarity_threshold; /* RegistrationParams::genz.planarity_threshold, 0.2 (registration_params.hpp:51-53) */
+    int32_t reserved[6];        /* must be zero */
 } spx_registration_params;
 
 /* RegistrationResult, I/algorithms/registration/result.hpp:13-28.  `iterations` keeps the
@@ -293,6 +295,10 @@ SPX_API int spx_robust_weights(spx_queue_t q, int reg_type, int robust_loss, con
  * of (H + lambda I) delta = -b, fp64 inside), eigen_utils.hpp:909-943 (se3_exp, column-major
  * out), dogleg_step.hpp:34-102. */
 SPX_API void spx_default_registration_params(spx_registration_params* p);
+/* GenZ planarity threshold used by the stateless entry points below and above (spx_linearize, spx_error,
+ * spx_robust_weights), which take no parameter struct; thread-local, default 0.2.  Registration handles use
+ * spx_registration_params::genz_planarity_threshold. */
+SPX_API int spx_set_genz_planarity_threshold(float threshold);
 SPX_API int spx_solve_6x6(const float* H_host, const float* b_host, float lambda, float* delta_host, int* success);
 SPX_API int spx_se3_exp(const float* twist6_host, float* T_host);
 SPX_API int spx_dogleg_step(const float* H_host, const float* g_host, float radius, float* p_host, float* step_norm,

@@ -1,6 +1,6 @@
 // registration::RegType and its string parser — I/algorithms/registration/factor.hpp:18-61.  The
-// factors (:63-484) run inside libspx's kernels; GENZ is not built (spx returns SPX_ERR_UNSUPPORTED,
-// surfaced as std::runtime_error).
+// factors (:63-484) run inside libspx's kernels (point-to-point, point-to-plane, point-to-distribution,
+// GICP and GenZ).
 #pragma once
 
 #include <algorithm>

@@ -155,6 +155,7 @@ private:
         p.dogleg_eta2 = P.dogleg.eta2;
         p.dogleg_gamma_decrease = P.dogleg.gamma_decrease;
         p.dogleg_gamma_increase = P.dogleg.gamma_increase;
+        p.genz_planarity_threshold = P.genz.planarity_threshold;
         return p;
     }
     static void from_c(const spx_registration_result& R, RegistrationResult& out) {
@@ -185,6 +186,19 @@ private:
             throw std::runtime_error(
                 "[Registration::validate_params] Covariance matrices of source and target must be pre-computed "
                 "before performing GICP matching.");
+        if (this->params_.reg_type == RegType::GENZ) {
+            if (!target.has_cov())
+                throw std::runtime_error(
+                    "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
+                    "performing GenZ-ICP matching.");
+            if (!target.has_normal()) {
+                std::cout << "[Caution] Normal vectors for GenZ-ICP are not provided. " << std::endl;
+                std::cout << "          Attempting to derive them from pre-computed covariance matrices." << std::endl;
+                covariance::extract_normals(target);
+            }
+            // the stateless C entry points (linearise / error / weights) read the threshold from a thread-local setting
+            detail::spx_check(spx_set_genz_planarity_threshold(this->params_.genz.planarity_threshold));
+        }
         if (this->params_.reg_type == RegType::POINT_TO_DISTRIBUTION && !target.has_cov())
             throw std::runtime_error(
                 "[Registration::validate_params] Covariance matrices of target must be pre-computed before "

@@ -80,7 +80,7 @@ class RegResult(C.Structure):
     ]
 
 
-REG = {"POINT_TO_POINT": 0, "POINT_TO_PLANE": 1, "POINT_TO_DISTRIBUTION": 2, "GICP": 3}
+REG = {"POINT_TO_POINT": 0, "POINT_TO_PLANE": 1, "POINT_TO_DISTRIBUTION": 2, "GICP": 3, "GENZ": 4}
 LOSS = {"NONE": 0, "HUBER": 1, "TUKEY": 2, "CAUCHY": 3, "GEMAN_MCCLURE": 4}
 OPT = {"GN": 0, "LM": 1, "DOGLEG": 2}
 
@@ -290,6 +290,19 @@ def update_covariance_plane(covs) -> np.ndarray:
     out = np.empty_like(c)
     lib().orc_update_covariance_plane(_f(c), C.c_size_t(len(c)), _f(out))
     return out.reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+
+def set_genz_planarity_threshold(t: float) -> None:
+    """RegistrationParams::genz.planarity_threshold (registration_params.hpp:51-53), default 0.2"""
+    lib().orc_set_genz_planarity_threshold(C.c_float(t))
+
+
+def genz_alpha(tgt_covs, idx, dist, max_corr_sq: float) -> float:
+    """Registration::compute_genz_alpha (registration.hpp:464-511)"""
+    idx = np.ascontiguousarray(idx, np.int32).reshape(-1)
+    dist = np.ascontiguousarray(dist, np.float32).reshape(-1)
+    lib().orc_genz_alpha.restype = C.c_float
+    return float(lib().orc_genz_alpha(_f(_covs_cm(tgt_covs)), C.c_size_t(len(idx)), _i(idx), _f(dist), C.c_float(max_corr_sq)))
 
 
 def robust_weight(loss: int, r: float, s: float) -> float:

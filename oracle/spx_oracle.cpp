@@ -498,6 +498,34 @@ inline PointTerm lin_p2plane(const M4& T, const V4& ps, const V4& pt, const V4& 
 // I/algorithms/common/transform.hpp:14-22
 inline M4 transform_cov(const M4& C, const M4& T) { return mul<4, 4, 4>(T, mul<4, 4, 4>(C, transpose(T))); }
 
+// ---- GenZ (factor.hpp:378-449): a correspondence whose TARGET neighbourhood is planar (PCA normalised curvature
+// l0 / (l0 + l1 + l2) below the threshold) takes the point-to-plane factor weighted by alpha, the others the
+// point-to-point factor weighted by 1 - alpha; alpha = planar inliers / inliers of the current correspondences
+// (registration.hpp:464-511, recomputed at every linearisation :519).
+static float g_genz_planarity_threshold = 0.2f;  // RegistrationParams::genz.planarity_threshold (registration_params.hpp:51-53)
+
+// I/algorithms/registration/factor.hpp:378-385
+inline float genz_curvature(const M4& ct) {
+    V3 ev;
+    M3 evec;
+    eigen3(block3(ct), ev, evec);
+    const float sum = ev(0) + ev(1) + ev(2);
+    return (sum > 1e-12f) ? ev(0) / sum : 1.0f;
+}
+inline bool genz_planar(const M4& ct) { return genz_curvature(ct) < g_genz_planarity_threshold; }  // :391-393
+
+// I/algorithms/registration/registration.hpp:464-511
+inline float genz_alpha_of(const float* tgt_covs, size_t ns, const int32_t* idx, const float* dist, float max_corr_sq) {
+    uint32_t inl = 0, plane = 0;
+    const M4 ident = M4::identity();
+    for (size_t i = 0; i < ns; ++i) {
+        if (dist[i] > max_corr_sq) continue;
+        if (genz_planar(tgt_covs ? load_cov(tgt_covs + 16 * (size_t)idx[i]) : ident)) ++plane;
+        ++inl;
+    }
+    return inl == 0 ? 1.0f : (float)plane / (float)inl;
+}
+
 // I/algorithms/registration/factor.hpp:111-123 + covariance.hpp:136-141
 inline M4 gicp_mahalanobis_inv(const M4& cs_in, const M4& ct_in, const M4& T) {
     M4 cs = cs_in, ct = ct_in;
@@ -552,8 +580,8 @@ inline PointTerm lin_p2d(const M4& T, const V4& ps, const V4& pt, const M4& ct) 
 // I/algorithms/registration/factor.hpp:156-164, 218-230, 287-306, 362-373
 inline float err_only(int reg, const M4& T, const V4& ps, const M4& cs, const V4& pt, const M4& ct, const V4& nrm) {
     const V4 r = residual_of(T, ps, pt);
-    if (reg == R_P2P) return dot<4>(r, r);
-    if (reg == R_P2PLANE) {
+    if (reg == R_P2P || (reg == R_GENZ && !genz_planar(ct))) return dot<4>(r, r);
+    if (reg == R_P2PLANE || reg == R_GENZ) {
         V3 n, r3;
         for (int i = 0; i < 3; ++i) {
             n(i) = nrm(i);
@@ -564,6 +592,20 @@ inline float err_only(int reg, const M4& T, const V4& ps, const M4& cs, const V4
     }
     const M4 Minv = reg == R_P2D ? p2d_mahalanobis(ct) : gicp_mahalanobis_inv(cs, ct, T);
     return dot<4>(r, mul<4, 4>(Minv, r));
+}
+
+// linearize_geometry<GENZ> — factor.hpp:425-443: the selected factor's H, b scaled by the GenZ weight, the residual
+// norm left unweighted; returns the weight
+inline float genz_term(const M4& T, const V4& ps, const V4& pt, const M4& ct, const V4& nrm, float alpha, PointTerm& t) {
+    const bool planar = genz_planar(ct);
+    const float gw = planar ? alpha : (1.0f - alpha);
+    t = planar ? lin_p2plane(T, ps, pt, nrm) : lin_p2p(T, ps, pt);
+    for (int r = 0; r < 6; ++r) {
+        for (int q = 0; q < 6; ++q) t.H(r, q) = t.H(r, q) * gw;
+        t.b(r) = t.b(r) * gw;
+    }
+    t.sq_err = t.sq_err * gw;
+    return gw;
 }
 
 struct Clouds {
@@ -589,6 +631,7 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
                      float max_corr_sq, float scale, int mode) {
     const M4 ident = M4::identity();
     const V4 zero4 = V4::zero();
+    const float alpha = reg == R_GENZ ? genz_alpha_of(c.tgt_covs, c.ns, idx, dist, max_corr_sq) : 1.0f;
     Linearized out;
     if (mode == 0) {
         float H[36] = {0}, b[6] = {0}, err = 0.0f;
@@ -599,12 +642,16 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
             const V4 ps = load_p(c.src_pts + 4 * i);
             const V4 pt = load_p(c.tgt_pts + 4 * (size_t)ti);
             PointTerm t;
+            float gw = 1.0f;  // GenZ weight of this correspondence (1 for every other factor)
             if (reg == R_P2P) {
                 t = lin_p2p(T, ps, pt);
             } else if (reg == R_P2PLANE) {
                 t = lin_p2plane(T, ps, pt, c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
             } else if (reg == R_P2D) {
                 t = lin_p2d(T, ps, pt, c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);
+            } else if (reg == R_GENZ) {
+                gw = genz_term(T, ps, pt, c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident,
+                               c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4, alpha, t);
             } else {
                 t = lin_gicp(T, ps, c.src_covs ? load_cov(c.src_covs + 16 * i) : ident, pt,
                              c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);
@@ -614,7 +661,7 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
                 for (int q = 0; q < 6; ++q) H[r * 6 + q] += w * t.H(r, q);
                 b[r] += w * t.b(r);
             }
-            err += robust_error(loss, t.res_norm, scale);
+            err += gw * robust_error(loss, t.res_norm, scale);
             ++inl;
         }
         std::memcpy(out.H, H, sizeof(H));
@@ -637,12 +684,16 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
             const V4 ps = load_p(c.src_pts + 4 * i);
             const V4 pt = load_p(c.tgt_pts + 4 * (size_t)ti);
             PointTerm t;
+            float gw = 1.0f;  // GenZ weight of this correspondence (1 for every other factor)
             if (reg == R_P2P) {
                 t = lin_p2p(T, ps, pt);
             } else if (reg == R_P2PLANE) {
                 t = lin_p2plane(T, ps, pt, c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
             } else if (reg == R_P2D) {
                 t = lin_p2d(T, ps, pt, c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);
+            } else if (reg == R_GENZ) {
+                gw = genz_term(T, ps, pt, c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident,
+                               c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4, alpha, t);
             } else {
                 t = lin_gicp(T, ps, c.src_covs ? load_cov(c.src_covs + 16 * i) : ident, pt,
                              c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident);
@@ -652,7 +703,7 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
                 for (int q = 0; q < 6; ++q) Hl[r * 6 + q] += (double)(w * t.H(r, q));
                 bl[r] += (double)(w * t.b(r));
             }
-            el += (double)robust_error(loss, t.res_norm, scale);
+            el += (double)(gw * robust_error(loss, t.res_norm, scale));
             ++il;
         }
 #pragma omp critical
@@ -675,6 +726,12 @@ void error_sum(int reg, int loss, const Clouds& c, const int32_t* idx, const flo
                float max_corr_sq, float scale, int mode, float* err_out, uint32_t* inl_out) {
     const M4 ident = M4::identity();
     const V4 zero4 = V4::zero();
+    // GenZ: alpha of the (frozen) correspondences — what the last linearisation on them stored (registration.hpp:370,519)
+    const float alpha = reg == R_GENZ ? genz_alpha_of(c.tgt_covs, c.ns, idx, dist, max_corr_sq) : 1.0f;
+    auto genz_w = [&](int32_t ti) {
+        if (reg != R_GENZ) return 1.0f;
+        return genz_planar(c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident) ? alpha : (1.0f - alpha);
+    };
     if (mode == 0) {
         float err = 0.0f;
         uint32_t inl = 0;
@@ -686,7 +743,7 @@ void error_sum(int reg, int loss, const Clouds& c, const int32_t* idx, const flo
                                       load_p(c.tgt_pts + 4 * (size_t)ti),
                                       c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident,
                                       c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
-            err += robust_error(loss, std::sqrt(e2), scale);
+            err += genz_w(ti) * robust_error(loss, std::sqrt(e2), scale);
             ++inl;
         }
         *err_out = err;
@@ -704,7 +761,7 @@ void error_sum(int reg, int loss, const Clouds& c, const int32_t* idx, const flo
             err_only(reg, T, load_p(c.src_pts + 4 * i), c.src_covs ? load_cov(c.src_covs + 16 * i) : ident,
                      load_p(c.tgt_pts + 4 * (size_t)ti), c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident,
                      c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
-        err += (double)robust_error(loss, std::sqrt(e2), scale);
+        err += (double)(genz_w(ti) * robust_error(loss, std::sqrt(e2), scale));
         ++inl;
     }
     *err_out = (float)err;
@@ -897,7 +954,7 @@ Dogleg dogleg_step(const float* H, const float* g, float radius) {
 extern "C" {
 
 struct orc_reg_params {
-    int32_t reg_type;        // 0 P2P, 1 P2PLANE, 3 GICP   (factor.hpp:18-32)
+    int32_t reg_type;        // 0 P2P, 1 P2PLANE, 2 P2D, 3 GICP, 4 GENZ   (factor.hpp:18-32)
     int32_t loss;            // 0 NONE 1 HUBER 2 TUKEY 3 CAUCHY 4 GEMAN_MCCLURE (robust.hpp:14-20)
     int32_t opt_method;      // 0 GN, 1 LM, 2 dog-leg      (registration_params.hpp:17-21)
     int32_t max_iterations;  // 20
@@ -1123,6 +1180,10 @@ void orc_update_covariance_plane(const float* covs_in, size_t n, float* covs_out
     }
 }
 
+void orc_set_genz_planarity_threshold(float t) { g_genz_planarity_threshold = t; }
+float orc_genz_alpha(const float* tgt_covs, size_t ns, const int32_t* idx, const float* dist, float max_corr_sq) {
+    return genz_alpha_of(tgt_covs, ns, idx, dist, max_corr_sq);
+}
 float orc_robust_weight(int loss, float r, float s) { return robust_weight(loss, r, s); }
 float orc_robust_error(int loss, float r, float s) { return robust_error(loss, r, s); }
 

@@ -752,6 +752,11 @@ class DoglegParams:
 
 
 @dataclass
+class GenZParams:
+    planarity_threshold: float = 0.2  # registration_params.hpp:51-53
+
+
+@dataclass
 class RegistrationParams:
     """RegistrationParams (registration_params.hpp:41-114), same defaults."""
     reg_type: RegType = RegType.GICP
@@ -764,6 +769,7 @@ class RegistrationParams:
     optimization_method: OptimizationMethod = OptimizationMethod.GAUSS_NEWTON
     max_iterations: int = 20
     criteria: Criteria = field(default_factory=Criteria)
+    genz: GenZParams = field(default_factory=GenZParams)
     max_blocks: int = 0  # spx extension: cap on the align kernel's persistent grid (0 = one full wave)
 
     def to_c(self) -> RegistrationParamsC:
@@ -790,7 +796,8 @@ class RegistrationParams:
         P.dogleg_eta2 = self.dogleg.eta2
         P.dogleg_gamma_decrease = self.dogleg.gamma_decrease
         P.dogleg_gamma_increase = self.dogleg.gamma_increase
-        P.reserved[0] = int(self.max_blocks)
+        P.max_grid_blocks = int(self.max_blocks)
+        P.genz_planarity_threshold = self.genz.planarity_threshold
         return P
 
 
@@ -891,6 +898,11 @@ class Registration:
         s = options.robust_scale if options is not None else -1.0
         return s if s > 0.0 else self.params.robust.default_scale  # registration.hpp:217-218
 
+    def _genz(self):
+        """the stateless C entry points take the GenZ planarity threshold from a thread-local setting"""
+        if self.params.reg_type == RegType.GENZ:
+            check(_lib.lib().spx_set_genz_planarity_threshold(float(self.params.genz.planarity_threshold)))
+
     def _loss(self) -> int:
         if self.params.robust.type != RobustLossType.NONE and self.params.robust.default_scale <= 0.0:
             print("[Caution] `robust.default_scale` must be greater than zero. Disable robust loss.")
@@ -906,6 +918,14 @@ class Registration:
             print("[Caution] Normal vectors for Point-to-Plane ICP are not provided. ")
             print("          Attempting to derive them from pre-computed covariance matrices.")
             covariance.extract_normals(target)
+        if self.params.reg_type == RegType.GENZ:
+            if not target.has_cov():
+                raise RuntimeError("[Registration::validate_params] Covariance matrices of target must be pre-computed "
+                                   "before performing GenZ-ICP matching.")
+            if not target.has_normal():
+                print("[Caution] Normal vectors for GenZ-ICP are not provided. ")
+                print("          Attempting to derive them from pre-computed covariance matrices.")
+                covariance.extract_normals(target)
         if self.params.reg_type == RegType.GICP and (not source.has_cov() or not target.has_cov()):
             raise RuntimeError("[Registration::validate_params] Covariance matrices of source and target must be "
                                "pre-computed before performing GICP matching.")
@@ -991,6 +1011,7 @@ class Registration:
         err, inl = C.c_float(), C.c_uint32()
         mc = np.float32(self.params.max_correspondence_distance)
         t16 = _T16(T)
+        self._genz()
         check(_lib.lib().spx_linearize(
             self.queue.handle, int(self.params.reg_type), self._loss(), source.points.ptr,
             _ptr(source.covs) if source.has_cov() else None, source.size(), target.points.ptr,
@@ -1003,6 +1024,7 @@ class Registration:
         err, inl = C.c_float(), C.c_uint32()
         mc = np.float32(self.params.max_correspondence_distance)
         t16 = _T16(T)
+        self._genz()
         check(_lib.lib().spx_error(
             self.queue.handle, int(self.params.reg_type), self._loss(), source.points.ptr,
             _ptr(source.covs) if source.has_cov() else None, source.size(), target.points.ptr,

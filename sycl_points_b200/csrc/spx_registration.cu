@@ -97,6 +97,9 @@ struct LinArgs {
     int iter_index;
     float* trace;  // [max_iterations][16] column-major poses, nullable
     float* weights_out;  // compute_icp_robust_weights
+    // GenZ (factor.hpp:378-449): planarity threshold and the {planar inliers, inliers} counters alpha comes from
+    float genz_threshold;
+    unsigned int* genz_counts;
     PeerX px;            // sharded align only
     // optional phase timestamps (tuning aid, spx_registration_phase_times): [iteration][PH_N] ns,
     // entry p = latest time any block reached phase p of that iteration
@@ -216,46 +219,84 @@ __device__ __forceinline__ Mat3 gicp_minv(const Xform& T, const Mat3& cs, const 
 // the weighted accumulation of registration.hpp:613-626,653-659.  The residual norm and weight are
 // formed first, then every H / b entry is computed and added straight into its accumulator, so no
 // 27-entry temporary is ever live (register pressure, not arithmetic, limits this kernel).
+// point-to-point terms (factor.hpp:130-149).  GW: every H / b entry is first scaled by the GenZ weight gw
+// (linearize_geometry<GENZ>, factor.hpp:436-440: H * w, b * w elementwise) — the other factors never multiply.
+template <bool GW>
+__device__ __forceinline__ void acc_p2p(const Jac& J, float r0, float r1, float r2, int loss, float scale, float gw, float* acc) {
+    const float e2 = chain3(r0, r0, r1, r1, r2, r2);
+    const float rn = __fsqrt_rn(e2);
+    const float w = robust_weight(loss, rn, scale);
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = a; c < 6; ++c, ++t) {
+            float h = chain3(J.j[0][a], J.j[0][c], J.j[1][a], J.j[1][c], J.j[2][a], J.j[2][c]);
+            if (GW) h = __fmul_rn(h, gw);
+            acc[t] = __fadd_rn(acc[t], __fmul_rn(w, h));
+        }
+        float bb = chain3(J.j[0][a], r0, J.j[1][a], r1, J.j[2][a], r2);
+        if (GW) bb = __fmul_rn(bb, gw);
+        acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, bb));
+    }
+    const float rho = robust_error(loss, rn, scale);
+    acc[S_ERR] = __fadd_rn(acc[S_ERR], GW ? __fmul_rn(gw, rho) : rho);
+}
+
+// point-to-plane terms (factor.hpp:172-210)
+template <bool GW>
+__device__ __forceinline__ void acc_p2plane(const Jac& J, float r0, float r1, float r2, const float4 nrm, int loss, float scale,
+                                            float gw, float* acc) {
+    const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
+    const float rn = fabsf(d);
+    const float w = robust_weight(loss, rn, scale);
+    const float n[3] = {nrm.x, nrm.y, nrm.z};
+    float row[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) row[c] = chain3(n[0], J.j[0][c], n[1], J.j[1][c], n[2], J.j[2][c]);
+    const float pe0 = __fmul_rn(n[0], d), pe1 = __fmul_rn(n[1], d), pe2 = __fmul_rn(n[2], d);
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const float ja0 = __fmul_rn(n[0], row[a]), ja1 = __fmul_rn(n[1], row[a]), ja2 = __fmul_rn(n[2], row[a]);
+#pragma unroll
+        for (int c = a; c < 6; ++c, ++t) {
+            float h = chain3(ja0, __fmul_rn(n[0], row[c]), ja1, __fmul_rn(n[1], row[c]), ja2, __fmul_rn(n[2], row[c]));
+            if (GW) h = __fmul_rn(h, gw);
+            acc[t] = __fadd_rn(acc[t], __fmul_rn(w, h));
+        }
+        float bb = chain3(ja0, pe0, ja1, pe1, ja2, pe2);
+        if (GW) bb = __fmul_rn(bb, gw);
+        acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, bb));
+    }
+    const float rho = robust_error(loss, rn, scale);
+    acc[S_ERR] = __fadd_rn(acc[S_ERR], GW ? __fmul_rn(gw, rho) : rho);
+}
+
+// is_genz_planar_correspondence — factor.hpp:378-393: PCA normalised curvature l0 / (l0 + l1 + l2) of the TARGET
+// covariance below the threshold
+__device__ __forceinline__ bool genz_planar(const Mat3& ct, float threshold) {
+    float ev[3], V[3][3];
+    mat3_eigen(ct, ev, V);
+    const float sum = __fadd_rn(__fadd_rn(ev[0], ev[1]), ev[2]);
+    const float curv = sum > 1e-12f ? __fdiv_rn(ev[0], sum) : 1.0f;
+    return curv < threshold;
+}
+
 template <int REG>
 __device__ __forceinline__ void accumulate_point(const Xform& T, const float4 ps, const Mat3& cs, const float4 pt,
                                                  const Mat3& ct, const float4 nrm, int loss, float scale,
-                                                 float* acc) {
+                                                 float* acc, bool planar = false, float gw = 1.0f) {
     const float4 tp = transform_point(T, ps);
     const float r0 = __fsub_rn(pt.x, tp.x), r1 = __fsub_rn(pt.y, tp.y), r2 = __fsub_rn(pt.z, tp.z);
     const Jac J = se3_jacobian(T, ps);
-    if (REG == SPX_REG_POINT_TO_POINT) {  // factor.hpp:130-149
-        const float e2 = chain3(r0, r0, r1, r1, r2, r2);
-        const float rn = __fsqrt_rn(e2);
-        const float w = robust_weight(loss, rn, scale);
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-#pragma unroll
-            for (int c = a; c < 6; ++c, ++t)
-                acc[t] = __fadd_rn(acc[t], __fmul_rn(w, chain3(J.j[0][a], J.j[0][c], J.j[1][a], J.j[1][c], J.j[2][a], J.j[2][c])));
-            acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(J.j[0][a], r0, J.j[1][a], r1, J.j[2][a], r2)));
-        }
-        acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
-    } else if (REG == SPX_REG_POINT_TO_PLANE) {  // factor.hpp:172-210
-        const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
-        const float rn = fabsf(d);
-        const float w = robust_weight(loss, rn, scale);
-        const float n[3] = {nrm.x, nrm.y, nrm.z};
-        float row[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) row[c] = chain3(n[0], J.j[0][c], n[1], J.j[1][c], n[2], J.j[2][c]);
-        const float pe0 = __fmul_rn(n[0], d), pe1 = __fmul_rn(n[1], d), pe2 = __fmul_rn(n[2], d);
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const float ja0 = __fmul_rn(n[0], row[a]), ja1 = __fmul_rn(n[1], row[a]), ja2 = __fmul_rn(n[2], row[a]);
-#pragma unroll
-            for (int c = a; c < 6; ++c, ++t)
-                acc[t] = __fadd_rn(acc[t], __fmul_rn(w, chain3(ja0, __fmul_rn(n[0], row[c]), ja1, __fmul_rn(n[1], row[c]),
-                                                             ja2, __fmul_rn(n[2], row[c]))));
-            acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(w, chain3(ja0, pe0, ja1, pe1, ja2, pe2)));
-        }
-        acc[S_ERR] = __fadd_rn(acc[S_ERR], robust_error(loss, rn, scale));
+    if (REG == SPX_REG_POINT_TO_POINT) {
+        acc_p2p<false>(J, r0, r1, r2, loss, scale, 1.0f, acc);
+    } else if (REG == SPX_REG_POINT_TO_PLANE) {
+        acc_p2plane<false>(J, r0, r1, r2, nrm, loss, scale, 1.0f, acc);
+    } else if (REG == SPX_REG_GENZ) {  // factor.hpp:425-443: plane factor x alpha or point factor x (1 - alpha)
+        if (planar) acc_p2plane<true>(J, r0, r1, r2, nrm, loss, scale, gw, acc);
+        else acc_p2p<true>(J, r0, r1, r2, loss, scale, gw, acc);
     } else {  // GICP, factor.hpp:239-278; point-to-distribution, :326-354 (ct already holds inverse(C_t))
         const Mat3 Mi = (REG == SPX_REG_POINT_TO_DISTRIBUTION) ? ct : gicp_minv(T, cs, ct);
         const float m0 = chain3(Mi.m[0][0], r0, Mi.m[0][1], r1, Mi.m[0][2], r2);  // M^-1 r, rows of the full inverse
@@ -292,11 +333,11 @@ __device__ __forceinline__ void accumulate_point(const Xform& T, const float4 ps
 
 template <int REG>
 __device__ __forceinline__ float point_error(const Xform& T, const float4 ps, const Mat3& cs, const float4 pt,
-                                             const Mat3& ct, const float4 nrm) {
+                                             const Mat3& ct, const float4 nrm, bool planar = false) {
     const float4 tp = transform_point(T, ps);
     const float r0 = __fsub_rn(pt.x, tp.x), r1 = __fsub_rn(pt.y, tp.y), r2 = __fsub_rn(pt.z, tp.z);
-    if (REG == SPX_REG_POINT_TO_POINT) return chain3(r0, r0, r1, r1, r2, r2);  // factor.hpp:156-164
-    if (REG == SPX_REG_POINT_TO_PLANE) {                                       // factor.hpp:218-230
+    if (REG == SPX_REG_POINT_TO_POINT || (REG == SPX_REG_GENZ && !planar)) return chain3(r0, r0, r1, r1, r2, r2);  // factor.hpp:156-164
+    if (REG == SPX_REG_POINT_TO_PLANE || REG == SPX_REG_GENZ) {                // factor.hpp:218-230, :474-478
         const float d = chain3(nrm.x, r0, nrm.y, r1, nrm.z, r2);
         return __fmul_rn(d, d);
     }
@@ -333,6 +374,10 @@ __device__ __forceinline__ void load_covs(const LinArgs& a, uint32_t i, int ti, 
         // factor.hpp:311-317 — the RAW covariance, no plane regularisation); missing -> identity
         if (a.tgt_cm) ct = load_mat(a.tgt_cm, (size_t)ti);
         else ct = mat3_inverse(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity());
+        return;
+    }
+    if (REG == SPX_REG_GENZ) {  // the RAW target covariance decides planar / non-planar; missing -> identity
+        ct = a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity();
         return;
     }
     if (REG != SPX_REG_GICP) return;
@@ -613,21 +658,61 @@ __global__ void __launch_bounds__(NN_THREADS, 8) icp_coop_kernel(const LinArgs a
     }
 }
 
+// Registration::compute_genz_alpha — registration.hpp:464-511: {planar inliers, inliers} of the current
+// correspondences, added to a.genz_counts (zeroed by the host before the launch)
+template <int MODE>
+__device__ __forceinline__ void genz_count(const LinArgs& a) {
+    const int32_t* idx = MODE == 1 ? a.idx_out : a.idx_in;
+    const float* dist = MODE == 1 ? a.dist_out : a.dist_in;
+    unsigned int plane = 0, inl = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x) {
+        const float d = MODE == 1 ? __ldcg(dist + i) : __ldg(dist + i);
+        const int ti = MODE == 1 ? __ldcg(idx + i) : __ldg(idx + i);
+        if (d > a.max_corr_sq || ti < 0) continue;
+        const Mat3 ct = a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity();
+        plane += genz_planar(ct, a.genz_threshold) ? 1u : 0u;
+        ++inl;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        plane += __shfl_xor_sync(0xffffffffu, plane, o);
+        inl += __shfl_xor_sync(0xffffffffu, inl, o);
+    }
+    if ((threadIdx.x & 31) == 0 && inl) {
+        atomicAdd(a.genz_counts, plane);
+        atomicAdd(a.genz_counts + 1, inl);
+    }
+}
+__global__ void __launch_bounds__(LIN_THREADS) genz_count_kernel(const LinArgs a) { genz_count<0>(a); }
+
+__device__ __forceinline__ float genz_alpha(const LinArgs& a) {
+    const unsigned int plane = __ldcg(a.genz_counts), inl = __ldcg(a.genz_counts + 1);
+    return inl == 0u ? 1.0f : __fdiv_rn((float)plane, (float)inl);
+}
+
 template <int REG, int MODE>
 __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Xform& T, float* acc, uint32_t& inl) {
     const int32_t* idx = MODE == 1 ? a.idx_out : a.idx_in;
     const float* dist = MODE == 1 ? a.dist_out : a.dist_in;
+    const float genz_alpha_v = REG == SPX_REG_GENZ ? genz_alpha(a) : 1.0f;
     for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
         const float d = MODE == 1 ? __ldcg(dist + i) : __ldg(dist + i);
         const int ti = MODE == 1 ? __ldcg(idx + i) : __ldg(idx + i);
         if (d > a.max_corr_sq || ti < 0) continue;  // registration.hpp:584 (+ guard for the -1 fill)
         const float4 ps = __ldg(a.src_pts + i);
         const float4 pt = __ldg(a.tgt_pts + ti);
-        const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
-                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 nrm = ((REG == SPX_REG_POINT_TO_PLANE || REG == SPX_REG_GENZ) && a.tgt_normals)
+                               ? __ldg(a.tgt_normals + ti)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
         Mat3 cs, ct;
         load_covs<REG>(a, i, ti, cs, ct);
-        accumulate_point<REG>(T, ps, cs, pt, ct, nrm, a.loss, a.scale, acc);
+        if (REG == SPX_REG_GENZ) {
+            const bool planar = genz_planar(ct, a.genz_threshold);
+            accumulate_point<REG>(T, ps, cs, pt, ct, nrm, a.loss, a.scale, acc, planar,
+                                  planar ? genz_alpha_v : __fsub_rn(1.0f, genz_alpha_v));
+        } else {
+            accumulate_point<REG>(T, ps, cs, pt, ct, nrm, a.loss, a.scale, acc);
+        }
         ++inl;
     }
 }
@@ -646,6 +731,11 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs
     if (MODE == 1) {  // cooperative launch: the correspondence search has grid barriers inside
         cooperative_groups::grid_group grid = cooperative_groups::this_grid();
         nn_search_grid(a, T, a.iter_index, grid);
+        if (REG == SPX_REG_GENZ) {  // alpha of the fresh correspondences, before any factor is evaluated
+            genz_count<1>(a);
+            __threadfence();
+            grid.sync();
+        }
     }
     float acc[N_ACC];
 #pragma unroll
@@ -1076,6 +1166,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) error_kernel(const LinArgs a) 
     const Xform T = a.T;
     float acc[1] = {0.0f};
     uint32_t inl = 0;
+    // GenZ: the error sum weights every term by alpha / 1 - alpha (registration.hpp:749-753); the weights export does not (:449)
+    const float alpha = (REG == SPX_REG_GENZ && !WEIGHTS) ? genz_alpha(a) : 1.0f;
     for (uint32_t i = blockIdx.x * LIN_THREADS + threadIdx.x; i < a.ns; i += gridDim.x * LIN_THREADS) {
         const float d = __ldg(a.dist_in + i);
         const int ti = __ldg(a.idx_in + i);
@@ -1083,15 +1175,18 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) error_kernel(const LinArgs a) 
         if (!(d > a.max_corr_sq || ti < 0)) {
             const float4 ps = __ldg(a.src_pts + i);
             const float4 pt = __ldg(a.tgt_pts + ti);
-            const float4 nrm = (REG == SPX_REG_POINT_TO_PLANE && a.tgt_normals) ? __ldg(a.tgt_normals + ti)
-                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 nrm = ((REG == SPX_REG_POINT_TO_PLANE || REG == SPX_REG_GENZ) && a.tgt_normals)
+                                   ? __ldg(a.tgt_normals + ti)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             Mat3 cs, ct;
             load_covs<REG>(a, i, ti, cs, ct);
-            const float rn = __fsqrt_rn(point_error<REG>(T, ps, cs, pt, ct, nrm));
+            const bool planar = REG == SPX_REG_GENZ ? genz_planar(ct, a.genz_threshold) : false;
+            const float rn = __fsqrt_rn(point_error<REG>(T, ps, cs, pt, ct, nrm, planar));
             if (WEIGHTS) {
                 w = robust_weight(a.loss, rn, a.scale);
             } else {
-                acc[0] = __fadd_rn(acc[0], robust_error(a.loss, rn, a.scale));
+                const float rho = robust_error(a.loss, rn, a.scale);
+                acc[0] = __fadd_rn(acc[0], REG == SPX_REG_GENZ ? __fmul_rn(planar ? alpha : __fsub_rn(1.0f, alpha), rho) : rho);
                 ++inl;
             }
         }
@@ -1227,6 +1322,16 @@ void launch_linearize(int reg, const LinArgs& a, unsigned blocks, cudaStream_t s
         case SPX_REG_POINT_TO_DISTRIBUTION:
             launch_linearize_one<SPX_REG_POINT_TO_DISTRIBUTION, MODE, SOLVE>(a, blocks, st, sm_count);
             break;
+        case SPX_REG_GENZ:
+            // alpha needs the counts of the correspondences: MODE 1 counts inside the kernel (after its search), MODE 0
+            // (correspondences given) by a launch in front
+            SPX_CUDA(cudaMemsetAsync(a.genz_counts, 0, 2 * sizeof(unsigned int), st));
+            if (MODE == 0) {
+                genz_count_kernel<<<blocks, LIN_THREADS, 0, st>>>(a);
+                SPX_LAUNCH_CHECK();
+            }
+            launch_linearize_one<SPX_REG_GENZ, MODE, SOLVE>(a, blocks, st, sm_count);
+            break;
         default: launch_linearize_one<SPX_REG_GICP, MODE, SOLVE>(a, blocks, st, sm_count); break;
     }
     SPX_LAUNCH_CHECK();
@@ -1239,6 +1344,14 @@ void launch_error(int reg, const LinArgs& a, unsigned blocks, cudaStream_t st) {
         case SPX_REG_POINT_TO_PLANE: error_kernel<SPX_REG_POINT_TO_PLANE, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
         case SPX_REG_POINT_TO_DISTRIBUTION:
             error_kernel<SPX_REG_POINT_TO_DISTRIBUTION, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a);
+            break;
+        case SPX_REG_GENZ:
+            if (!WEIGHTS) {  // alpha of the frozen correspondences (what the linearisation on them stored, registration.hpp:370)
+                SPX_CUDA(cudaMemsetAsync(a.genz_counts, 0, 2 * sizeof(unsigned int), st));
+                genz_count_kernel<<<std::min(blocks, 1024u), LIN_THREADS, 0, st>>>(a);
+                SPX_LAUNCH_CHECK();
+            }
+            error_kernel<SPX_REG_GENZ, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a);
             break;
         default: error_kernel<SPX_REG_GICP, WEIGHTS><<<blocks, LIN_THREADS, 0, st>>>(a); break;
     }
@@ -1254,9 +1367,9 @@ unsigned coop_blocks(int device_sm_count) {
 }
 
 void check_reg_loss(int reg, int loss, const char* where) {
-    if (reg == SPX_REG_GENZ) throw Error(SPX_ERR_UNSUPPORTED, std::string(where) + " RegType GENZ is not built");
+    (void)where;
     if (!(reg == SPX_REG_POINT_TO_POINT || reg == SPX_REG_POINT_TO_PLANE || reg == SPX_REG_GICP ||
-          reg == SPX_REG_POINT_TO_DISTRIBUTION))
+          reg == SPX_REG_POINT_TO_DISTRIBUTION || reg == SPX_REG_GENZ))
         throw Error(SPX_ERR_INVALID_ARGUMENT, "[Registration::dispatch] Combination not found in tags!");
     if (loss < SPX_LOSS_NONE || loss > SPX_LOSS_GEMAN_MCCLURE)
         throw Error(SPX_ERR_INVALID_ARGUMENT, "[Registration::dispatch] Combination not found in tags!");
@@ -1383,6 +1496,10 @@ void validate(const spx_registration_params& P, const float* src_covs, const flo
         throw Error(SPX_ERR_INVALID_ARGUMENT,
                     "[Registration::validate_params] Covariance matrices of source and target must be pre-computed "
                     "before performing GICP matching.");
+    if (P.reg_type == SPX_REG_GENZ && !tgt_covs)
+        throw Error(SPX_ERR_INVALID_ARGUMENT,
+                    "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
+                    "performing GenZ-ICP matching.");
     if (P.reg_type == SPX_REG_POINT_TO_DISTRIBUTION && !tgt_covs)
         throw Error(SPX_ERR_INVALID_ARGUMENT,
                     "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
@@ -1458,10 +1575,11 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
         if (gicp) a.src_cm = r->src_cm;
         a.tgt_cm = r->tgt_cm;
     }
-    if (P.reg_type == SPX_REG_POINT_TO_PLANE && !tgt_normals) {
-        // registration.hpp:139-141: normals derived from the pre-computed covariances
-        fprintf(stdout, "[Caution] Normal vectors for Point-to-Plane ICP are not provided. \n"
-                        "          Attempting to derive them from pre-computed covariance matrices.\n");
+    if ((P.reg_type == SPX_REG_POINT_TO_PLANE || P.reg_type == SPX_REG_GENZ) && !tgt_normals) {
+        // registration.hpp:139-141,157-164: normals derived from the pre-computed covariances
+        fprintf(stdout, "[Caution] Normal vectors for %s are not provided. \n"
+                        "          Attempting to derive them from pre-computed covariance matrices.\n",
+                P.reg_type == SPX_REG_GENZ ? "GenZ-ICP" : "Point-to-Plane ICP");
         float4* nrm = nullptr;
         SPX_CUDA(cudaMalloc(&nrm, std::max<size_t>(nt, 1) * sizeof(float4)));
         *derived_normals = nrm;
@@ -1469,6 +1587,9 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
             throw Error(SPX_ERR_INTERNAL, spx_last_error());
         a.tgt_normals = nrm;
     }
+    if (P.reg_type == SPX_REG_GENZ) a.tgt_cov16 = tgt_covs;  // the raw target covariance classifies planar / non-planar
+    a.genz_threshold = P.genz_planarity_threshold > 0.0f ? P.genz_planarity_threshold : 0.2f;
+    a.genz_counts = r->wl_counters + 8;
     a.idx_in = r->nn_idx; a.dist_in = r->nn_dist;
     a.idx_out = r->nn_idx; a.dist_out = r->nn_dist;
     a.pos_out = r->nn_pos;
@@ -1638,9 +1759,9 @@ void launch_align_gn(int reg_type, LinArgs& a, int max_it, spx_queue_t q, spx_re
             break;
     }
     unsigned blocks = std::max(1u, std::min((unsigned)div_up(a.ns, LIN_THREADS), resident));
-    // reserved[0] = cap on the persistent grid (0 = one full wave).  Lets several aligns share one
+    // max_grid_blocks = cap on the persistent grid (0 = one full wave).  Lets several aligns share one
     // GPU (concurrent queues; two ranks of the exchange protocol on one device in the tests).
-    if (reg->P.reserved[0] > 0) blocks = std::min(blocks, (unsigned)reg->P.reserved[0]);
+    if (reg->P.max_grid_blocks > 0) blocks = std::min(blocks, (unsigned)reg->P.max_grid_blocks);
     if (2 * blocks > reg->max_blocks) {
         SPX_CUDA(cudaStreamSynchronize(q->stream));
         if (reg->partials) SPX_CUDA(cudaFree(reg->partials));
@@ -1858,8 +1979,8 @@ void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs,
             default: resident = batch_coop_pick<SPX_REG_GICP>(one, q->sm_count, &fn); break;
         }
         unsigned blocks = std::max(1u, std::min((unsigned)total_chunks, resident));
-        // reserved[0] = cap on the persistent grid (0 = one full wave): lets several aligns share one GPU
-        if (Pm.reserved[0] > 0) blocks = std::min(blocks, (unsigned)Pm.reserved[0]);
+        // max_grid_blocks = cap on the persistent grid (0 = one full wave): lets several aligns share one GPU
+        if (Pm.max_grid_blocks > 0) blocks = std::min(blocks, (unsigned)Pm.max_grid_blocks);
         int mi = max_it;
         void* args[] = {(void*)&a, (void*)&mi};
         SPX_CUDA(cudaEventRecord(r->ev0, st));
@@ -1894,6 +2015,10 @@ void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs,
     free_normals();
 }
 
+// GenZ planarity threshold of the stateless entry points (spx_linearize / spx_error / spx_robust_weights), which take no
+// parameter struct: RegistrationParams::genz.planarity_threshold's default unless spx_set_genz_planarity_threshold changed it
+thread_local float t_genz_planarity_threshold = 0.2f;
+
 // generic (caller-supplied correspondences) argument block for spx_linearize / spx_error / weights
 LinArgs generic_args(spx_queue_t q, int loss, const float* src_points, const float* src_covs, size_t ns,
                      const float* tgt_points, const float* tgt_covs, const float* tgt_normals, const int32_t* nn_idx,
@@ -1918,6 +2043,8 @@ LinArgs generic_args(spx_queue_t q, int loss, const float* src_points, const flo
     a.partials = q->take<double>((size_t)blocks * 32);
     a.sums_out = q->take<double>(32);
     a.ticket = q->take<unsigned int>(16);
+    a.genz_counts = a.ticket + 8;
+    a.genz_threshold = t_genz_planarity_threshold;
     SPX_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), q->stream));
     return a;
 }
@@ -1950,6 +2077,14 @@ void spx_default_registration_params(spx_registration_params* p) {
     p->dogleg_eta2 = 0.75f;
     p->dogleg_gamma_decrease = 0.25f;
     p->dogleg_gamma_increase = 2.0f;
+    p->genz_planarity_threshold = 0.2f;
+}
+
+int spx_set_genz_planarity_threshold(float threshold) {
+    return guard([&] {
+        SPX_REQUIRE(threshold > 0.0f, "[spx_set_genz_planarity_threshold] threshold must be positive");
+        t_genz_planarity_threshold = threshold;
+    });
 }
 
 int spx_solve_6x6(const float* H_host, const float* b_host, float lambda, float* delta_host, int* success) {
@@ -2161,7 +2296,7 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         {
             size_t split_min = 400000;
             if (const char* e = std::getenv("SPX_SPLIT_MIN")) split_min = (size_t)std::atoll(e);  // tuning aid
-            if (P.optimization_method == SPX_OPT_GAUSS_NEWTON && ns < split_min) {
+            if (P.optimization_method == SPX_OPT_GAUSS_NEWTON && ns < split_min && P.reg_type != SPX_REG_GENZ) {
                 // the cooperative one-launch path: the batched kernel with one pair
                 spx_align_pair one{};
                 one.src_points = src_points; one.src_covs = src_covs; one.ns = ns;
@@ -2352,11 +2487,12 @@ int spx_registration_align_batch(spx_registration_t reg, size_t n_pairs, const s
         SPX_REQUIRE(reg && (n_pairs == 0 || (pairs_host && results_host)), "[Registration::align_batch] null argument");
         if (n_pairs == 0) return;
         DeviceGuard g(reg->q->device);
-        if (reg->P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
+        if (reg->P.optimization_method == SPX_OPT_GAUSS_NEWTON && reg->P.reg_type != SPX_REG_GENZ) {
             gn_align_batch(reg, n_pairs, pairs_host, results_host, nullptr);
             return;
         }
-        // LM / dog-leg take host decisions per trial step: one pair after the other
+        // LM / dog-leg take host decisions per trial step, GenZ needs a count reduction in front of every
+        // linearisation: one pair after the other
         for (size_t p = 0; p < n_pairs; ++p) {
             const spx_align_pair& A = pairs_host[p];
             const int rc = spx_registration_align(reg, A.src_points, A.src_covs, A.ns, A.tgt_points, A.tgt_covs, A.tgt_normals,

@@ -640,3 +640,70 @@ def test_spx_align_batch_raw_pairs_equal_the_single_pair_chain(spx, q):
         assert res[j].converged == one.converged and res[j].error == one.error
     assert ba.last_timing()["iterations"] >= 1
     ba.close()
+
+
+# ---- GenZ (factor.hpp:378-449, registration.hpp:464-511)
+@pytest.mark.parametrize("thr", [0.2, 0.02, 0.005])
+@pytest.mark.parametrize("loss", ["NONE", "HUBER"])
+def test_genz_linearize_error_weights_vs_oracle(spx, q, pair, thr, loss):
+    """GenZ: plane factor x alpha for planar correspondences, point factor x (1 - alpha) for the others, alpha =
+    planar inliers / inliers recounted per linearisation.  Thresholds chosen so that the planar share of the
+    bundled pair is ~100 %, ~60 % and ~10 %."""
+    oracle.set_genz_planarity_threshold(thr)
+    try:
+        T = oracle.se3_exp(np.array([0.004, -0.003, 0.012, 0.4, 0.1, -0.02], np.float32))
+        nn_idx, nn_dist = pair["otree"].knn(pair["src_h"], 1, T)
+        alpha = oracle.genz_alpha(pair["cov_t"], nn_idx, nn_dist, 4.0)
+        params = spx.RegistrationParams(reg_type=spx.RegType.GENZ)
+        params.genz.planarity_threshold = thr
+        params.robust.type = spx.RobustLossType[loss]
+        params.robust.default_scale = 0.7
+        reg_obj = spx.Registration(q, params)
+        lin = reg_obj.compute_linearized_result(pair["src"], pair["tgt"], pair["tree"], T)
+        H, b, e, inl = oracle.linearize(4, oracle.LOSS[loss], pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"],
+                                        pair["nrm_t"], nn_idx, nn_dist, T, 4.0, 0.7, mode=1)
+        assert lin.inlier == inl
+        assert rel(lin.H, H) <= 1e-5 and rel(lin.b, b) <= 1e-5 and abs(lin.error - e) <= 1e-5 * abs(e), (alpha, rel(lin.H, H))
+        T2 = (T @ oracle.se3_exp(np.array([1e-3, 2e-3, -1e-3, 0.01, -0.02, 0.005], np.float32))).astype(np.float32)
+        ge, gi = reg_obj.compute_error_frozen(pair["src"], pair["tgt"], T2)
+        oe, oi = oracle.error(4, oracle.LOSS[loss], pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"], pair["nrm_t"],
+                              nn_idx, nn_dist, T2, 4.0, 0.7, mode=1)
+        assert gi == oi and abs(ge - oe) <= 1e-5 * abs(oe)
+        w = reg_obj.compute_icp_robust_weights(pair["src"], pair["tgt"], pair["tree"], T, 0.7)
+        ow = oracle.robust_weights(4, oracle.LOSS[loss], pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"],
+                                   pair["nrm_t"], nn_idx, nn_dist, T, 4.0, 0.7)
+        assert np.abs(w - ow).max() <= 1e-6
+        if thr == 0.02:
+            assert 0.2 < alpha < 0.9, alpha  # a real mix of both factors
+    finally:
+        oracle.set_genz_planarity_threshold(0.2)
+
+
+@pytest.mark.parametrize("opt", ["GN", "LM", "DOGLEG"])
+def test_genz_align_matches_oracle(spx, q, pair, opt):
+    thr = 0.02
+    oracle.set_genz_planarity_threshold(thr)
+    try:
+        iters = 5
+        params = spx.RegistrationParams(reg_type=spx.RegType.GENZ, max_iterations=iters)
+        params.genz.planarity_threshold = thr
+        params.robust.type = spx.RobustLossType.HUBER
+        params.robust.default_scale = 1.0
+        params.optimization_method = spx.OptimizationMethod({"GN": 0, "LM": 1, "DOGLEG": 2}[opt])
+        params.criteria.translation = 0.0
+        params.criteria.rotation = 0.0
+        res = spx.Registration(q, params).align(pair["src"], pair["tgt"], pair["tree"], trace=True)
+        P = oracle.default_params(reg_type=4, loss=1, opt_method=oracle.OPT[opt], max_iterations=iters,
+                                  robust_default_scale=1.0, crit_translation=0.0, crit_rotation=0.0)
+        ores = oracle.align(P, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"], pair["nrm_t"], pair["otree"],
+                            trace=True)
+        for it in range(iters):
+            dt, da = pose_delta(ores["trace"][it], res.trace[it])
+            assert dt < 1e-5 and da < 1e-5, f"iteration {it}: dt={dt:.2e} da={da:.2e}"
+        assert res.inlier == ores["inlier"]
+        # batched entry point with GenZ: one pair after the other, same results
+        reg_obj = spx.Registration(q, params)
+        b = reg_obj.align_batch([(pair["src"], pair["tgt"], pair["tree"], None)] * 2)
+        assert np.array_equal(b[0].T, res.T) and np.array_equal(b[1].T, res.T)
+    finally:
+        oracle.set_genz_planarity_threshold(0.2)
