@@ -103,7 +103,10 @@ typedef struct spx_registration_params {
     float dogleg_gamma_increase;/* 2 */
     int32_t max_grid_blocks;    /* cap on the align kernel's persistent grid (blocks, 0 = auto: one full wave) */
     float genz_planarity_threshold; /* RegistrationParams::genz.planarity_threshold, 0.2 (registration_params.hpp:51-53) */
-    int32_t reserved[6];        /* must be zero */
+    int32_t rotation_constraint_enable;       /* RegistrationParams::rotation_constraint (registration_params.hpp:54-62), off */
+    float rotation_constraint_weight;         /* 1 */
+    float rotation_constraint_robust_scale;   /* 10; a positive ExecutionOptions::rotation_robust_scale goes here (registration.hpp:219-221) */
+    int32_t reserved[3];        /* must be zero */
 } spx_registration_params;
 
 /* RegistrationResult, I/algorithms/registration/result.hpp:13-28.  `iterations` keeps the
@@ -299,6 +302,10 @@ SPX_API void spx_default_registration_params(spx_registration_params* p);
  * spx_robust_weights), which take no parameter struct; thread-local, default 0.2.  Registration handles use
  * spx_registration_params::genz_planarity_threshold. */
 SPX_API int spx_set_genz_planarity_threshold(float threshold);
+/* RegistrationParams::rotation_constraint for the same stateless entry points (thread-local, default off): the
+ * Jensen-Bregman LogDet term of I/algorithms/registration/rotation_constraint.hpp:15-121 added to every correspondence
+ * (registration.hpp:629-649,757-764). */
+SPX_API int spx_set_rotation_constraint(int enable, float weight, float robust_scale);
 SPX_API int spx_solve_6x6(const float* H_host, const float* b_host, float lambda, float* delta_host, int* success);
 SPX_API int spx_se3_exp(const float* twist6_host, float* T_host);
 SPX_API int spx_dogleg_step(const float* H_host, const float* g_host, float radius, float* p_host, float* step_norm,

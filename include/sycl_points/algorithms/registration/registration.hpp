@@ -44,10 +44,10 @@ public:
     /// registration.hpp:105-114
     Registration(const sycl_utils::DeviceQueue& queue, const RegistrationParams& params = RegistrationParams())
         : params_(params), queue_(queue) {
-        if (params.rotation_constraint.enable || params.degenerate_reg.enable || params.map_prior.enable)
+        if (params.degenerate_reg.enable || params.map_prior.enable)
             throw std::runtime_error(
-                "[Registration::Registration] rotation_constraint / degenerate_reg / map_prior are not built in "
-                "libspx (default-off add-ons outside the hot path)");
+                "[Registration::Registration] degenerate_reg / map_prior are not built in libspx (default-off "
+                "add-ons outside the hot path)");
         const spx_registration_params p = to_c(params);
         detail::spx_check(spx_registration_create(queue.handle(), &p, &this->handle_));
     }
@@ -75,7 +75,8 @@ public:
         if (tree == nullptr || tree->handle() == nullptr) return this->align_injected(source, target, target_knn, result, options);
 
         this->prefetch(source, target);
-        const spx_registration_params p = to_c(this->params_);
+        spx_registration_params p = to_c(this->params_);
+        if (options.rotation_robust_scale > 0.0f) p.rotation_constraint_robust_scale = options.rotation_robust_scale;  // :219-221
         detail::spx_check(spx_registration_set_params(this->handle_, &p));
         spx_registration_result R;
         detail::spx_check(spx_registration_align(
@@ -156,6 +157,9 @@ private:
         p.dogleg_gamma_decrease = P.dogleg.gamma_decrease;
         p.dogleg_gamma_increase = P.dogleg.gamma_increase;
         p.genz_planarity_threshold = P.genz.planarity_threshold;
+        p.rotation_constraint_enable = P.rotation_constraint.enable ? 1 : 0;
+        p.rotation_constraint_weight = P.rotation_constraint.weight;
+        p.rotation_constraint_robust_scale = P.rotation_constraint.robust.default_scale;
         return p;
     }
     static void from_c(const spx_registration_result& R, RegistrationResult& out) {
@@ -203,6 +207,20 @@ private:
             throw std::runtime_error(
                 "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
                 "performing Point-to-Distribution ICP matching.");
+        if (this->params_.rotation_constraint.enable) {
+            if (!source.has_cov())
+                throw std::runtime_error(
+                    "[Registration::validate_params] Covariance matrices of source are required for performing "
+                    "rotation constraint matching.");
+            if (!target.has_cov())
+                throw std::runtime_error(
+                    "[Registration::validate_params] Covariance matrices of target are required for performing "
+                    "rotation constraint matching.");
+        }
+        // the stateless C entry points (linearise / error / weights) read this add-on from a thread-local setting
+        detail::spx_check(spx_set_rotation_constraint(this->params_.rotation_constraint.enable ? 1 : 0,
+                                                      this->params_.rotation_constraint.weight,
+                                                      this->params_.rotation_constraint.robust.default_scale));
         if (this->params_.robust.type != robust::RobustLossType::NONE && this->params_.robust.default_scale <= 0.0f) {
             std::cout << "[Caution] `robust.default_scale` must be greater than zero. Disable robust loss." << std::endl;
             this->params_.robust.type = robust::RobustLossType::NONE;

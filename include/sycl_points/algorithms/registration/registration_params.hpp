@@ -1,7 +1,7 @@
 // Registration parameter structs — I/algorithms/registration/registration_params.hpp:17-114, same
-// names and defaults.  The default-off add-ons whose kernels are out of scope (rotation
-// constraint, GenZ, degenerate regularisation, MAP prior: DESIGN.md §7) keep their fields so that
-// configuration code compiles; enabling one makes Registration's constructor throw.
+// names and defaults.  GenZ and the rotation constraint are built; the default-off add-ons whose
+// kernels are out of scope (degenerate regularisation, MAP prior: DESIGN.md §7) keep their fields so
+// that configuration code compiles; enabling one makes Registration's constructor throw.
 #pragma once
 
 #include <algorithm>

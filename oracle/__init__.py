@@ -297,6 +297,11 @@ def set_genz_planarity_threshold(t: float) -> None:
     lib().orc_set_genz_planarity_threshold(C.c_float(t))
 
 
+def set_rotation_constraint(enable: bool, weight: float = 1.0, robust_scale: float = 10.0) -> None:
+    """RegistrationParams::rotation_constraint (registration_params.hpp:54-62); process-wide, default off"""
+    lib().orc_set_rotation_constraint(C.c_int(1 if enable else 0), C.c_float(weight), C.c_float(robust_scale))
+
+
 def genz_alpha(tgt_covs, idx, dist, max_corr_sq: float) -> float:
     """Registration::compute_genz_alpha (registration.hpp:464-511)"""
     idx = np.ascontiguousarray(idx, np.int32).reshape(-1)

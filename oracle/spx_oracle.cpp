@@ -594,6 +594,56 @@ inline float err_only(int reg, const M4& T, const V4& ps, const M4& cs, const V4
     return dot<4>(r, mul<4, 4>(Minv, r));
 }
 
+// ---- rotation constraint (rotation_constraint.hpp:15-121): Jensen-Bregman LogDet divergence between the rotated
+// source covariance and the target covariance, D = log det(0.5 (R Cs R^T + Ct)) - 0.5 (log det Cs + log det Ct),
+// residual r = max(D, 0), Jacobian (rotation block only) g = -R^T vex([Cs', M^-1]); added to every correspondence's
+// H / b / error with weight rotation_constraint.weight x robust weight (registration.hpp:629-649,757-764).
+static int g_rot_enable = 0;
+static float g_rot_weight = 1.0f, g_rot_scale = 10.0f;
+
+inline float rot_logdet(const M3& m) { return cr_log(std::fmax(determinant(m), 1e-10f)); }
+
+struct RotTerm {
+    float D;
+    V3 grad;
+};
+inline RotTerm rot_divergence(const M4& cs4, const M4& ct4, const M4& T) {
+    const M3 R = block3(T), Cs = block3(cs4), Ct = block3(ct4);
+    const M3 Csp = mul<3, 3, 3>(R, mul<3, 3, 3>(Cs, transpose(R)));
+    const M3 M = scale(add(Csp, Ct), 0.5f);
+    const float log_det_M = rot_logdet(M);
+    const float log_det_ref = 0.5f * (rot_logdet(Cs) + rot_logdet(Ct));
+    RotTerm o;
+    o.D = std::fmax(log_det_M - log_det_ref, 0.0f);
+    const M3 Minv = inverse(M);
+    const M3 comm = sub(mul<3, 3, 3>(Csp, Minv), mul<3, 3, 3>(Minv, Csp));
+    V3 g;
+    g(0) = -0.5f * (comm(2, 1) - comm(1, 2));
+    g(1) = -0.5f * (comm(0, 2) - comm(2, 0));
+    g(2) = -0.5f * (comm(1, 0) - comm(0, 1));
+    o.grad = mul<3, 3>(transpose(R), g);
+    return o;
+}
+// linearize_rotation_constraint_logdet — rotation_constraint.hpp:84-105
+inline PointTerm lin_rot(const M4& cs, const M4& ct, const M4& T) {
+    const RotTerm d = rot_divergence(cs, ct, T);
+    PointTerm o;
+    o.H = M6::zero();
+    o.b = V6::zero();
+    for (int i = 0; i < 3; ++i) {
+        o.b(i) = d.D * d.grad(i);
+        for (int j = 0; j < 3; ++j) o.H(i, j) = d.grad(i) * d.grad(j);
+    }
+    o.sq_err = 0.5f * d.D * d.D;
+    o.res_norm = std::sqrt(o.sq_err);
+    return o;
+}
+// calculate_logdet_divergence_squared — rotation_constraint.hpp:15-44
+inline float err_rot(const M4& cs, const M4& ct, const M4& T) {
+    const float D = rot_divergence(cs, ct, T).D;
+    return 0.5f * D * D;
+}
+
 // linearize_geometry<GENZ> — factor.hpp:425-443: the selected factor's H, b scaled by the GenZ weight, the residual
 // norm left unweighted; returns the weight
 inline float genz_term(const M4& T, const V4& ps, const V4& pt, const M4& ct, const V4& nrm, float alpha, PointTerm& t) {
@@ -662,6 +712,16 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
                 b[r] += w * t.b(r);
             }
             err += gw * robust_error(loss, t.res_norm, scale);
+            if (g_rot_enable) {  // registration.hpp:629-649
+                const PointTerm rt = lin_rot(c.src_covs ? load_cov(c.src_covs + 16 * i) : ident,
+                                             c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident, T);
+                const float wr = robust_weight(loss, rt.res_norm, g_rot_scale);
+                for (int r = 0; r < 6; ++r) {
+                    for (int q = 0; q < 6; ++q) H[r * 6 + q] += g_rot_weight * wr * rt.H(r, q);
+                    b[r] += g_rot_weight * wr * rt.b(r);
+                }
+                err += g_rot_weight * robust_error(loss, rt.res_norm, g_rot_scale);
+            }
             ++inl;
         }
         std::memcpy(out.H, H, sizeof(H));
@@ -704,6 +764,16 @@ Linearized linearize(int reg, int loss, const Clouds& c, const int32_t* idx, con
                 bl[r] += (double)(w * t.b(r));
             }
             el += (double)(gw * robust_error(loss, t.res_norm, scale));
+            if (g_rot_enable) {  // registration.hpp:629-649
+                const PointTerm rt = lin_rot(c.src_covs ? load_cov(c.src_covs + 16 * i) : ident,
+                                             c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident, T);
+                const float wr = robust_weight(loss, rt.res_norm, g_rot_scale);
+                for (int r = 0; r < 6; ++r) {
+                    for (int q = 0; q < 6; ++q) Hl[r * 6 + q] += (double)(g_rot_weight * wr * rt.H(r, q));
+                    bl[r] += (double)(g_rot_weight * wr * rt.b(r));
+                }
+                el += (double)(g_rot_weight * robust_error(loss, rt.res_norm, g_rot_scale));
+            }
             ++il;
         }
 #pragma omp critical
@@ -744,6 +814,10 @@ void error_sum(int reg, int loss, const Clouds& c, const int32_t* idx, const flo
                                       c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident,
                                       c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
             err += genz_w(ti) * robust_error(loss, std::sqrt(e2), scale);
+            if (g_rot_enable)
+                err += g_rot_weight * robust_error(loss, std::sqrt(err_rot(c.src_covs ? load_cov(c.src_covs + 16 * i) : ident,
+                                                                           c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident, T)),
+                                                   g_rot_scale);
             ++inl;
         }
         *err_out = err;
@@ -762,6 +836,10 @@ void error_sum(int reg, int loss, const Clouds& c, const int32_t* idx, const flo
                      load_p(c.tgt_pts + 4 * (size_t)ti), c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident,
                      c.tgt_normals ? load_p(c.tgt_normals + 4 * (size_t)ti) : zero4);
         err += (double)(genz_w(ti) * robust_error(loss, std::sqrt(e2), scale));
+        if (g_rot_enable)
+            err += (double)(g_rot_weight * robust_error(loss, std::sqrt(err_rot(c.src_covs ? load_cov(c.src_covs + 16 * i) : ident,
+                                                                               c.tgt_covs ? load_cov(c.tgt_covs + 16 * (size_t)ti) : ident, T)),
+                                                       g_rot_scale));
         ++inl;
     }
     *err_out = (float)err;
@@ -1181,6 +1259,12 @@ void orc_update_covariance_plane(const float* covs_in, size_t n, float* covs_out
 }
 
 void orc_set_genz_planarity_threshold(float t) { g_genz_planarity_threshold = t; }
+// RegistrationParams::rotation_constraint {enable, weight, robust.default_scale} (registration_params.hpp:54-62)
+void orc_set_rotation_constraint(int enable, float weight, float robust_scale) {
+    g_rot_enable = enable;
+    g_rot_weight = weight;
+    g_rot_scale = robust_scale;
+}
 float orc_genz_alpha(const float* tgt_covs, size_t ns, const int32_t* idx, const float* dist, float max_corr_sq) {
     return genz_alpha_of(tgt_covs, ns, idx, dist, max_corr_sq);
 }

@@ -37,7 +37,8 @@ class RegistrationParamsC(C.Structure):
         ("dogleg_initial_trust_region_radius", C.c_float), ("dogleg_min_trust_region_radius", C.c_float),
         ("dogleg_max_trust_region_radius", C.c_float), ("dogleg_eta1", C.c_float), ("dogleg_eta2", C.c_float),
         ("dogleg_gamma_decrease", C.c_float), ("dogleg_gamma_increase", C.c_float), ("max_grid_blocks", C.c_int32),
-        ("genz_planarity_threshold", C.c_float), ("reserved", C.c_int32 * 6),
+        ("genz_planarity_threshold", C.c_float), ("rotation_constraint_enable", C.c_int32),
+        ("rotation_constraint_weight", C.c_float), ("rotation_constraint_robust_scale", C.c_float), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -149,6 +150,7 @@ def lib() -> C.CDLL:
                                          C.c_float, C.c_float, f32p]),
         "spx_default_registration_params": (None, [C.POINTER(RegistrationParamsC)]),
         "spx_set_genz_planarity_threshold": (C.c_int, [C.c_float]),
+        "spx_set_rotation_constraint": (C.c_int, [C.c_int, C.c_float, C.c_float]),
         "spx_solve_6x6": (C.c_int, [hostf, hostf, C.c_float, hostf, C.POINTER(C.c_int)]),
         "spx_se3_exp": (C.c_int, [hostf, hostf]),
         "spx_dogleg_step": (C.c_int, [hostf, hostf, C.c_float, hostf, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -757,6 +757,19 @@ class GenZParams:
 
 
 @dataclass
+class RotationConstraintRobust:
+    default_scale: float = 10.0
+
+
+@dataclass
+class RotationConstraintParams:
+    """RegistrationFactorParams::RotationConstraint (registration_params.hpp:54-62)"""
+    enable: bool = False
+    weight: float = 1.0
+    robust: RotationConstraintRobust = field(default_factory=RotationConstraintRobust)
+
+
+@dataclass
 class RegistrationParams:
     """RegistrationParams (registration_params.hpp:41-114), same defaults."""
     reg_type: RegType = RegType.GICP
@@ -770,6 +783,7 @@ class RegistrationParams:
     max_iterations: int = 20
     criteria: Criteria = field(default_factory=Criteria)
     genz: GenZParams = field(default_factory=GenZParams)
+    rotation_constraint: RotationConstraintParams = field(default_factory=RotationConstraintParams)
     max_blocks: int = 0  # spx extension: cap on the align kernel's persistent grid (0 = one full wave)
 
     def to_c(self) -> RegistrationParamsC:
@@ -798,6 +812,9 @@ class RegistrationParams:
         P.dogleg_gamma_increase = self.dogleg.gamma_increase
         P.max_grid_blocks = int(self.max_blocks)
         P.genz_planarity_threshold = self.genz.planarity_threshold
+        P.rotation_constraint_enable = 1 if self.rotation_constraint.enable else 0
+        P.rotation_constraint_weight = self.rotation_constraint.weight
+        P.rotation_constraint_robust_scale = self.rotation_constraint.robust.default_scale
         return P
 
 
@@ -902,6 +919,8 @@ class Registration:
         """the stateless C entry points take the GenZ planarity threshold from a thread-local setting"""
         if self.params.reg_type == RegType.GENZ:
             check(_lib.lib().spx_set_genz_planarity_threshold(float(self.params.genz.planarity_threshold)))
+        rc = self.params.rotation_constraint
+        check(_lib.lib().spx_set_rotation_constraint(1 if rc.enable else 0, float(rc.weight), float(rc.robust.default_scale)))
 
     def _loss(self) -> int:
         if self.params.robust.type != RobustLossType.NONE and self.params.robust.default_scale <= 0.0:
@@ -926,6 +945,13 @@ class Registration:
                 print("[Caution] Normal vectors for GenZ-ICP are not provided. ")
                 print("          Attempting to derive them from pre-computed covariance matrices.")
                 covariance.extract_normals(target)
+        if self.params.rotation_constraint.enable:
+            if not source.has_cov():
+                raise RuntimeError("[Registration::validate_params] Covariance matrices of source are required for "
+                                   "performing rotation constraint matching.")
+            if not target.has_cov():
+                raise RuntimeError("[Registration::validate_params] Covariance matrices of target are required for "
+                                   "performing rotation constraint matching.")
         if self.params.reg_type == RegType.GICP and (not source.has_cov() or not target.has_cov()):
             raise RuntimeError("[Registration::validate_params] Covariance matrices of source and target must be "
                                "pre-computed before performing GICP matching.")
@@ -944,6 +970,8 @@ class Registration:
         if not isinstance(target_knn, KDTree):
             return self._align_injected_knn(source, target, target_knn, T0, options, trace)
         Pc = self.params.to_c()
+        if options is not None and options.rotation_robust_scale > 0.0:  # registration.hpp:219-221
+            Pc.rotation_constraint_robust_scale = float(options.rotation_robust_scale)
         check(_lib.lib().spx_registration_set_params(self._h, C.byref(Pc)))
         R = RegistrationResultC()
         t16 = _T16(T0)
@@ -1052,6 +1080,7 @@ class Registration:
         w = DeviceArray(self.queue, (n,), np.float32)
         mc = np.float32(self.params.max_correspondence_distance)
         t16 = _T16(pose)
+        self._genz()
         check(_lib.lib().spx_robust_weights(
             self.queue.handle, int(self.params.reg_type), self._loss(), source.points.ptr,
             _ptr(source.covs) if source.has_cov() else None, n, target.points.ptr,

@@ -100,6 +100,9 @@ struct LinArgs {
     // GenZ (factor.hpp:378-449): planarity threshold and the {planar inliers, inliers} counters alpha comes from
     float genz_threshold;
     unsigned int* genz_counts;
+    // rotation constraint (rotation_constraint.hpp:15-121), an extra term per correspondence on the RAW covariances
+    int rot_enable;
+    float rot_weight, rot_scale;
     PeerX px;            // sharded align only
     // optional phase timestamps (tuning aid, spx_registration_phase_times): [iteration][PH_N] ns,
     // entry p = latest time any block reached phase p of that iteration
@@ -658,6 +661,65 @@ __global__ void __launch_bounds__(NN_THREADS, 8) icp_coop_kernel(const LinArgs a
     }
 }
 
+// ---- rotation constraint — rotation_constraint.hpp:15-121: Jensen-Bregman LogDet divergence between the rotated
+// source covariance Cs' = R Cs R^T and the target covariance, D = log det(0.5 (Cs' + Ct)) - 0.5 (log det Cs + log det Ct),
+// residual max(D, 0), Jacobian (rotation block only) g = -R^T vex([Cs', M^-1]).  Full 3x3 arithmetic in the
+// reference's fma order; log correctly rounded (spx_math.cuh cr_logf).
+__device__ __forceinline__ float rot_logdet(const Mat3& m) { return cr_logf(fmaxf(mat3_det(m), 1e-10f)); }
+
+__device__ inline float rot_divergence(const Xform& T, const Mat3& Cs, const Mat3& Ct, float grad[3], bool want_grad) {
+    const float R[3][3] = {{T.r0.x, T.r0.y, T.r0.z}, {T.r1.x, T.r1.y, T.r1.z}, {T.r2.x, T.r2.y, T.r2.z}};
+    float X[3][3];  // Cs R^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) X[i][j] = chain3(Cs.m[i][0], R[j][0], Cs.m[i][1], R[j][1], Cs.m[i][2], R[j][2]);
+    Mat3 Csp, M;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            Csp.m[i][j] = chain3(R[i][0], X[0][j], R[i][1], X[1][j], R[i][2], X[2][j]);
+            M.m[i][j] = __fmul_rn(__fadd_rn(Csp.m[i][j], Ct.m[i][j]), 0.5f);
+        }
+    const float log_det_M = rot_logdet(M);
+    const float log_det_ref = __fmul_rn(0.5f, __fadd_rn(rot_logdet(Cs), rot_logdet(Ct)));
+    const float D = fmaxf(__fsub_rn(log_det_M, log_det_ref), 0.0f);
+    if (!want_grad) return D;
+    const Mat3 Mi = mat3_inverse(M);
+    float comm[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            comm[i][j] = __fsub_rn(chain3(Csp.m[i][0], Mi.m[0][j], Csp.m[i][1], Mi.m[1][j], Csp.m[i][2], Mi.m[2][j]),
+                                   chain3(Mi.m[i][0], Csp.m[0][j], Mi.m[i][1], Csp.m[1][j], Mi.m[i][2], Csp.m[2][j]));
+    const float g0 = __fmul_rn(-0.5f, __fsub_rn(comm[2][1], comm[1][2]));
+    const float g1 = __fmul_rn(-0.5f, __fsub_rn(comm[0][2], comm[2][0]));
+    const float g2 = __fmul_rn(-0.5f, __fsub_rn(comm[1][0], comm[0][1]));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) grad[i] = chain3(R[0][i], g0, R[1][i], g1, R[2][i], g2);  // R^T g
+    return D;
+}
+
+// the term's share of H / b / error, added on top of the factor's (registration.hpp:629-649)
+__device__ __forceinline__ void accumulate_rotation(const Xform& T, const Mat3& Cs, const Mat3& Ct, int loss, float weight,
+                                                    float scale, float* acc) {
+    float g[3];
+    const float D = rot_divergence(T, Cs, Ct, g, true);
+    const float sq = __fmul_rn(__fmul_rn(0.5f, D), D);
+    const float rn = __fsqrt_rn(sq);
+    const float ww = __fmul_rn(weight, robust_weight(loss, rn, scale));
+    constexpr int TIDX[3][3] = {{0, 1, 2}, {1, 6, 7}, {2, 7, 11}};  // packed upper-triangle slot of H(a, c), a, c < 3
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int c = a; c < 3; ++c) acc[TIDX[a][c]] = __fadd_rn(acc[TIDX[a][c]], __fmul_rn(ww, __fmul_rn(g[a], g[c])));
+        acc[S_B + a] = __fadd_rn(acc[S_B + a], __fmul_rn(ww, __fmul_rn(D, g[a])));
+    }
+    acc[S_ERR] = __fadd_rn(acc[S_ERR], __fmul_rn(weight, robust_error(loss, rn, scale)));
+}
+
 // Registration::compute_genz_alpha — registration.hpp:464-511: {planar inliers, inliers} of the current
 // correspondences, added to a.genz_counts (zeroed by the host before the launch)
 template <int MODE>
@@ -713,6 +775,10 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Xform& T,
         } else {
             accumulate_point<REG>(T, ps, cs, pt, ct, nrm, a.loss, a.scale, acc);
         }
+        if (a.rot_enable)  // on the raw covariances; missing -> identity (registration.hpp:589-590)
+            accumulate_rotation(T, a.src_cov16 ? load_cov16(a.src_cov16 + (size_t)i * 16) : mat3_identity(),
+                                a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity(), a.loss, a.rot_weight,
+                                a.rot_scale, acc);
         ++inl;
     }
 }
@@ -762,7 +828,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) linearize_kernel(const LinArgs
 // and converge at the same iteration.  Mailbox rows and flags are double-buffered by iteration
 // parity: a rank can be at most one exchange ahead of the slowest peer.
 template <int REG, bool SHARDED>
-__global__ void __launch_bounds__(LIN_THREADS, 2) align_gn_kernel(const LinArgs a, int max_iterations) {
+__global__ void __launch_bounds__(LIN_THREADS, 3) align_gn_kernel(const LinArgs a, int max_iterations) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double fold[LIN_WARPS][32];
@@ -1187,6 +1253,13 @@ __global__ void __launch_bounds__(LIN_THREADS, 2) error_kernel(const LinArgs a) 
             } else {
                 const float rho = robust_error(a.loss, rn, a.scale);
                 acc[0] = __fadd_rn(acc[0], REG == SPX_REG_GENZ ? __fmul_rn(planar ? alpha : __fsub_rn(1.0f, alpha), rho) : rho);
+                if (a.rot_enable) {  // registration.hpp:757-764
+                    float g[3];
+                    const float D = rot_divergence(T, a.src_cov16 ? load_cov16(a.src_cov16 + (size_t)i * 16) : mat3_identity(),
+                                                   a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity(), g, false);
+                    const float rr = __fsqrt_rn(__fmul_rn(__fmul_rn(0.5f, D), D));
+                    acc[0] = __fadd_rn(acc[0], __fmul_rn(a.rot_weight, robust_error(a.loss, rr, a.rot_scale)));
+                }
                 ++inl;
             }
         }
@@ -1500,6 +1573,14 @@ void validate(const spx_registration_params& P, const float* src_covs, const flo
         throw Error(SPX_ERR_INVALID_ARGUMENT,
                     "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
                     "performing GenZ-ICP matching.");
+    if (P.rotation_constraint_enable && !src_covs)
+        throw Error(SPX_ERR_INVALID_ARGUMENT,
+                    "[Registration::validate_params] Covariance matrices of source are required for performing rotation "
+                    "constraint matching.");
+    if (P.rotation_constraint_enable && !tgt_covs)
+        throw Error(SPX_ERR_INVALID_ARGUMENT,
+                    "[Registration::validate_params] Covariance matrices of target are required for performing rotation "
+                    "constraint matching.");
     if (P.reg_type == SPX_REG_POINT_TO_DISTRIBUTION && !tgt_covs)
         throw Error(SPX_ERR_INVALID_ARGUMENT,
                     "[Registration::validate_params] Covariance matrices of target must be pre-computed before "
@@ -1588,6 +1669,13 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
         a.tgt_normals = nrm;
     }
     if (P.reg_type == SPX_REG_GENZ) a.tgt_cov16 = tgt_covs;  // the raw target covariance classifies planar / non-planar
+    if (P.rotation_constraint_enable) {  // the rotation-constraint term reads the RAW covariances of both clouds
+        a.src_cov16 = src_covs;
+        a.tgt_cov16 = tgt_covs;
+        a.rot_enable = 1;
+        a.rot_weight = P.rotation_constraint_weight;
+        a.rot_scale = P.rotation_constraint_robust_scale > 0.0f ? P.rotation_constraint_robust_scale : 10.0f;
+    }
     a.genz_threshold = P.genz_planarity_threshold > 0.0f ? P.genz_planarity_threshold : 0.2f;
     a.genz_counts = r->wl_counters + 8;
     a.idx_in = r->nn_idx; a.dist_in = r->nn_dist;
@@ -2018,6 +2106,9 @@ void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs,
 // GenZ planarity threshold of the stateless entry points (spx_linearize / spx_error / spx_robust_weights), which take no
 // parameter struct: RegistrationParams::genz.planarity_threshold's default unless spx_set_genz_planarity_threshold changed it
 thread_local float t_genz_planarity_threshold = 0.2f;
+// the same for RegistrationParams::rotation_constraint (spx_set_rotation_constraint)
+thread_local int t_rot_enable = 0;
+thread_local float t_rot_weight = 1.0f, t_rot_scale = 10.0f;
 
 // generic (caller-supplied correspondences) argument block for spx_linearize / spx_error / weights
 LinArgs generic_args(spx_queue_t q, int loss, const float* src_points, const float* src_covs, size_t ns,
@@ -2045,6 +2136,9 @@ LinArgs generic_args(spx_queue_t q, int loss, const float* src_points, const flo
     a.ticket = q->take<unsigned int>(16);
     a.genz_counts = a.ticket + 8;
     a.genz_threshold = t_genz_planarity_threshold;
+    a.rot_enable = t_rot_enable;
+    a.rot_weight = t_rot_weight;
+    a.rot_scale = t_rot_scale;
     SPX_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), q->stream));
     return a;
 }
@@ -2078,6 +2172,18 @@ void spx_default_registration_params(spx_registration_params* p) {
     p->dogleg_gamma_decrease = 0.25f;
     p->dogleg_gamma_increase = 2.0f;
     p->genz_planarity_threshold = 0.2f;
+    p->rotation_constraint_enable = 0;
+    p->rotation_constraint_weight = 1.0f;
+    p->rotation_constraint_robust_scale = 10.0f;
+}
+
+int spx_set_rotation_constraint(int enable, float weight, float robust_scale) {
+    return guard([&] {
+        SPX_REQUIRE(!enable || robust_scale > 0.0f, "[spx_set_rotation_constraint] robust_scale must be positive");
+        t_rot_enable = enable ? 1 : 0;
+        t_rot_weight = weight;
+        t_rot_scale = robust_scale;
+    });
 }
 
 int spx_set_genz_planarity_threshold(float threshold) {
@@ -2296,7 +2402,8 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         {
             size_t split_min = 400000;
             if (const char* e = std::getenv("SPX_SPLIT_MIN")) split_min = (size_t)std::atoll(e);  // tuning aid
-            if (P.optimization_method == SPX_OPT_GAUSS_NEWTON && ns < split_min && P.reg_type != SPX_REG_GENZ) {
+            if (P.optimization_method == SPX_OPT_GAUSS_NEWTON && ns < split_min && P.reg_type != SPX_REG_GENZ &&
+                !P.rotation_constraint_enable) {
                 // the cooperative one-launch path: the batched kernel with one pair
                 spx_align_pair one{};
                 one.src_points = src_points; one.src_covs = src_covs; one.ns = ns;
@@ -2487,7 +2594,8 @@ int spx_registration_align_batch(spx_registration_t reg, size_t n_pairs, const s
         SPX_REQUIRE(reg && (n_pairs == 0 || (pairs_host && results_host)), "[Registration::align_batch] null argument");
         if (n_pairs == 0) return;
         DeviceGuard g(reg->q->device);
-        if (reg->P.optimization_method == SPX_OPT_GAUSS_NEWTON && reg->P.reg_type != SPX_REG_GENZ) {
+        if (reg->P.optimization_method == SPX_OPT_GAUSS_NEWTON && reg->P.reg_type != SPX_REG_GENZ &&
+            !reg->P.rotation_constraint_enable) {
             gn_align_batch(reg, n_pairs, pairs_host, results_host, nullptr);
             return;
         }

@@ -707,3 +707,54 @@ def test_genz_align_matches_oracle(spx, q, pair, opt):
         assert np.array_equal(b[0].T, res.T) and np.array_equal(b[1].T, res.T)
     finally:
         oracle.set_genz_planarity_threshold(0.2)
+
+
+# ---- rotation constraint (rotation_constraint.hpp:15-121; registration.hpp:629-649,757-764)
+@pytest.mark.parametrize("reg", ["GICP", "POINT_TO_PLANE", "GENZ"])
+def test_rotation_constraint_vs_oracle(spx, q, pair, reg):
+    """the Jensen-Bregman LogDet term on the raw covariances, added to every correspondence of any factor:
+    linearise / frozen error <= 1e-5 vs the oracle, and the GN / LM pose traces <= 1e-5."""
+    oracle.set_rotation_constraint(True, 0.5, 3.0)
+    try:
+        T = oracle.se3_exp(np.array([0.02, -0.015, 0.03, 0.4, 0.1, -0.02], np.float32))
+        nn_idx, nn_dist = pair["otree"].knn(pair["src_h"], 1, T)
+        params = spx.RegistrationParams(reg_type=spx.RegType[reg])
+        params.robust.type = spx.RobustLossType.HUBER
+        params.robust.default_scale = 0.7
+        params.rotation_constraint.enable = True
+        params.rotation_constraint.weight = 0.5
+        params.rotation_constraint.robust.default_scale = 3.0
+        reg_obj = spx.Registration(q, params)
+        lin = reg_obj.compute_linearized_result(pair["src"], pair["tgt"], pair["tree"], T)
+        H, b, e, inl = oracle.linearize(oracle.REG[reg], 1, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"],
+                                        pair["nrm_t"], nn_idx, nn_dist, T, 4.0, 0.7, mode=1)
+        assert lin.inlier == inl
+        assert rel(lin.H, H) <= 1e-5 and rel(lin.b, b) <= 1e-5 and abs(lin.error - e) <= 1e-5 * abs(e)
+        # the term is really there
+        oracle.set_rotation_constraint(False)
+        H0, _, e0, _ = oracle.linearize(oracle.REG[reg], 1, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"],
+                                        pair["nrm_t"], nn_idx, nn_dist, T, 4.0, 0.7, mode=1)
+        oracle.set_rotation_constraint(True, 0.5, 3.0)
+        assert rel(H0, H) > 1e-3 and e > e0
+        ge, gi = reg_obj.compute_error_frozen(pair["src"], pair["tgt"], T)
+        oe, oi = oracle.error(oracle.REG[reg], 1, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"], pair["nrm_t"],
+                              nn_idx, nn_dist, T, 4.0, 0.7, mode=1)
+        assert gi == oi and abs(ge - oe) <= 1e-5 * abs(oe)
+        for opt in ("GN", "LM"):
+            iters = 4
+            params.max_iterations = iters
+            params.optimization_method = spx.OptimizationMethod({"GN": 0, "LM": 1}[opt])
+            params.criteria.translation = params.criteria.rotation = 0.0
+            res = spx.Registration(q, params).align(pair["src"], pair["tgt"], pair["tree"], trace=True)
+            P = oracle.default_params(reg_type=oracle.REG[reg], loss=1, opt_method=oracle.OPT[opt], max_iterations=iters,
+                                      robust_default_scale=0.7, crit_translation=0.0, crit_rotation=0.0)
+            ores = oracle.align(P, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"], pair["nrm_t"], pair["otree"],
+                                trace=True)
+            for it in range(iters):
+                dt, da = pose_delta(ores["trace"][it], res.trace[it])
+                assert dt < 1e-5 and da < 1e-5, f"{opt} iteration {it}: dt={dt:.2e} da={da:.2e}"
+    finally:
+        oracle.set_rotation_constraint(False)
+    src_nocov = spx.PointCloudShared(q, pair["src_h"])
+    with pytest.raises(RuntimeError, match="Covariance matrices of source are required"):
+        reg_obj.align(src_nocov, pair["tgt"], pair["tree"])
