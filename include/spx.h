@@ -207,6 +207,12 @@ SPX_API int spx_index_levels(spx_index_t index, int32_t* n_levels);
 /* ------------------------------------------------------------------ features
  * covariance::estimate_async(queue, neighbors, points, covs) — I/algorithms/feature/covariance.hpp:16-47,260-292 */
 SPX_API int spx_covariance(spx_queue_t q, const float* points, size_t n, const int32_t* knn_idx, int k, float* covs);
+/* covariance::estimate_robust_async(queue, neighbors, points, covs, robust_type, mad_scale, min_robust_scale,
+ * robust_max_iterations) — covariance.hpp:97-134,143-250,323-373: M-estimated covariances (weights from the squared
+ * Mahalanobis distances at scale mad_scale x median, floored at min_robust_scale).  robust_loss NONE = the plain
+ * estimate; k <= 64 (the reference's MAX_K).  Reference defaults: CAUCHY, 1.0, 1.0, 1 iteration. */
+SPX_API int spx_covariance_robust(spx_queue_t q, const float* points, size_t n, const int32_t* knn_idx, int k, int robust_loss,
+                          float mad_scale, float min_robust_scale, int robust_max_iterations, float* covs);
 /* covariance::estimate_normals_async(neighbors, points) — covariance.hpp:49-65,417-445 */
 SPX_API int spx_normals(spx_queue_t q, const float* points, size_t n, const int32_t* knn_idx, int k, float* normals);
 /* covariance::extract_normals_async(points) — covariance.hpp:467-495 */

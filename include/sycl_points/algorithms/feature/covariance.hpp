@@ -5,6 +5,7 @@
 #include <stdexcept>
 
 #include "sycl_points/algorithms/knn/knn.hpp"
+#include "sycl_points/algorithms/robust/robust.hpp"
 #include "sycl_points/points/point_cloud.hpp"
 
 namespace sycl_points {
@@ -49,6 +50,56 @@ inline sycl_utils::events estimate_async(const knn::KNNBase& knn, const PointClo
     knn::KNNResult neighbors;
     auto knn_events = knn.knn_search_async(points, k_correspondences, neighbors, depends);
     auto ev = estimate_async(neighbors, points, knn_events.evs);
+    ev.add_resource(neighbors.indices);
+    ev.add_resource(neighbors.distances);
+    return ev;
+}
+
+/// covariance.hpp:323-373 — M-estimated covariances (kernel: covariance.hpp:97-134,143-250)
+inline sycl_utils::events estimate_robust_async(const sycl_utils::DeviceQueue& queue, const knn::KNNResult& neighbors,
+                                                const PointContainerShared& points, CovarianceContainerShared& covs,
+                                                robust::RobustLossType robust_type = robust::RobustLossType::CAUCHY,
+                                                float mad_scale = 1.0f, float min_robust_scale = 1.0f,
+                                                size_t robust_max_iterations = 1,
+                                                const std::vector<sycl::event>& depends = std::vector<sycl::event>()) {
+    if (neighbors.k > 64) throw std::runtime_error("[covariance::estimate_robust_async] neighbor K is too large. MAX_K is 64");
+    const size_t N = points.size();
+    if (covs.size() != N) covs.resize(N);
+    sycl_utils::events events;
+    if (N == 0) return events;
+    detail_spx::wait_all(depends);
+    queue.set_accessed_by_device(points.data(), N);
+    queue.set_accessed_by_device(covs.data(), N);
+    queue.set_accessed_by_device(neighbors.indices->data(), neighbors.indices->size());
+    detail::spx_check(spx_covariance_robust(queue.handle(), reinterpret_cast<const float*>(points.data()), N,
+                                            neighbors.indices->data(), (int)neighbors.k, (int)robust_type, mad_scale,
+                                            min_robust_scale, (int)robust_max_iterations,
+                                            reinterpret_cast<float*>(covs.data())));
+    events += queue.checkpoint();
+    return events;
+}
+
+/// covariance.hpp:383-390
+inline sycl_utils::events estimate_robust_async(const knn::KNNResult& neighbors, const PointCloudShared& points,
+                                                robust::RobustLossType robust_type = robust::RobustLossType::CAUCHY,
+                                                float mad_scale = 1.0f, float min_robust_scale = 1.0f,
+                                                size_t robust_max_iterations = 1,
+                                                const std::vector<sycl::event>& depends = std::vector<sycl::event>()) {
+    return estimate_robust_async(points.queue, neighbors, *points.points, *points.covs, robust_type, mad_scale,
+                                 min_robust_scale, robust_max_iterations, depends);
+}
+
+/// covariance.hpp:400-410
+inline sycl_utils::events estimate_robust_async(const knn::KNNBase& knn, const PointCloudShared& points,
+                                                const size_t k_correspondences,
+                                                robust::RobustLossType robust_type = robust::RobustLossType::CAUCHY,
+                                                float mad_scale = 1.0f, float min_robust_scale = 1.0f,
+                                                size_t robust_max_iterations = 1,
+                                                const std::vector<sycl::event>& depends = std::vector<sycl::event>()) {
+    knn::KNNResult neighbors;
+    auto knn_events = knn.knn_search_async(points, k_correspondences, neighbors, depends);
+    auto ev = estimate_robust_async(neighbors, points, robust_type, mad_scale, min_robust_scale, robust_max_iterations,
+                                    knn_events.evs);
     ev.add_resource(neighbors.indices);
     ev.add_resource(neighbors.distances);
     return ev;

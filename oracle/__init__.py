@@ -262,6 +262,17 @@ def covariance(points, idx) -> np.ndarray:
     return covs.reshape(-1, 4, 4).transpose(0, 2, 1).copy()
 
 
+def covariance_robust(points, idx, loss: int = 3, mad_scale: float = 1.0, min_robust_scale: float = 1.0,
+                      robust_max_iterations: int = 1) -> np.ndarray:
+    """covariance::estimate_robust (covariance.hpp:182-250, 323-373); default loss CAUCHY (3)"""
+    p = _pts(points)
+    idx = np.ascontiguousarray(idx, np.int32)
+    covs = np.empty((len(p), 16), np.float32)
+    lib().orc_covariance_robust(_f(p), C.c_size_t(len(p)), _i(idx), C.c_int(idx.shape[1]), C.c_int(loss),
+                                C.c_float(mad_scale), C.c_float(min_robust_scale), C.c_int(robust_max_iterations), _f(covs))
+    return covs.reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+
 def normals(points, idx) -> np.ndarray:
     p = _pts(points)
     idx = np.ascontiguousarray(idx, np.int32)

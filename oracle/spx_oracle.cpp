@@ -427,6 +427,77 @@ struct PointTerm {
     float res_norm;
 };
 
+// ---- M-estimated covariance — I/algorithms/feature/covariance.hpp:97-134 (estimate_weighted), :143-173
+// (compute_median), :182-222 (estimate_robust)
+inline bool estimate_cov_weighted(const float* pts, int k, const int32_t* idx_row, const float* w, M4& ret, V3& mean) {
+    ret = M4::zero();
+    V3 sp = V3::zero();
+    M3 so = M3::zero();
+    size_t cnt = 0;
+    float tw = 0.0f;
+    for (int j = 0; j < k; ++j) {
+        const int32_t id = idx_row[j];
+        if (id < 0) continue;
+        V3 p;
+        p(0) = pts[4 * (size_t)id + 0];
+        p(1) = pts[4 * (size_t)id + 1];
+        p(2) = pts[4 * (size_t)id + 2];
+        for (int a = 0; a < 3; ++a) sp(a) += p(a) * w[j];
+        const M3 o = outer<3>(p, p);
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) so(r, c) += o(r, c) * w[j];
+        ++cnt;
+        tw += w[j];
+    }
+    if (cnt < 4 || tw < std::numeric_limits<float>::epsilon()) {
+        ret(0, 0) = ret(1, 1) = ret(2, 2) = 1.0f;
+        return false;
+    }
+    mean = scale(sp, 1.0f / tw);
+    const M3 c = ensure_symmetric<3>(sub(scale(so, 1.0f / tw), outer<3>(mean, mean)));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) ret(i, j) = c(i, j);
+    return true;
+}
+
+inline M4 estimate_cov_robust(const float* pts, int k, const int32_t* idx_row, int loss, float mad_scale, float min_scale,
+                              int max_iter) {
+    constexpr int MAX_K = 64;
+    float w[MAX_K], d2[MAX_K];
+    std::fill(w, w + MAX_K, 1.0f);
+    std::fill(d2, d2 + MAX_K, 0.0f);
+    M4 cov;
+    V3 mean = V3::zero();
+    bool ok = estimate_cov_weighted(pts, k, idx_row, w, cov, mean);
+    for (int it = 0; ok && it < max_iter; ++it) {
+        const M3 ci = inverse(block3(cov));
+        for (int j = 0; j < k; ++j) {
+            const int32_t id = idx_row[j];
+            if (id < 0) continue;
+            V3 d;
+            for (int a = 0; a < 3; ++a) d(a) = pts[4 * (size_t)id + a] - mean(a);
+            d2[j] = dot<3>(d, mul<3, 3>(ci, d));  // dot<4> / multiply<4,4> with zero 4th components: the same chain
+        }
+        for (int j = 0; j < k; ++j) w[j] = d2[j];
+        for (int a = 1; a < k; ++a) {  // insertion sort in the weights buffer
+            const float key = w[a];
+            int b = a;
+            while (b > 0 && w[b - 1] > key) {
+                w[b] = w[b - 1];
+                --b;
+            }
+            w[b] = key;
+        }
+        const int mid = k / 2;
+        const float median = (k % 2 == 0) ? (w[mid - 1] + w[mid]) * 0.5f : w[mid];
+        float rs = mad_scale * median;
+        if (rs < min_scale) rs = min_scale;
+        for (int j = 0; j < k; ++j) w[j] = robust_weight(loss, d2[j], rs);
+        ok = estimate_cov_weighted(pts, k, idx_row, w, cov, mean);
+    }
+    return cov;
+}
+
 // I/algorithms/registration/factor.hpp:69-84 (+ :100-104 with identity weight: exact no-op)
 inline Mat<4, 6> se3_jacobian(const M4& T, const V4& p) {
     Mat<4, 6> J = Mat<4, 6>::zero();
@@ -1226,6 +1297,17 @@ void orc_covariance(const float* pts, size_t n, const int32_t* idx, int k, float
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         const M4 c = estimate_cov(pts, k, idx + (size_t)i * k);
+        store_T(c, covs + 16 * (size_t)i);
+    }
+}
+
+// covariance.hpp:323-373
+void orc_covariance_robust(const float* pts, size_t n, const int32_t* idx, int k, int loss, float mad_scale, float min_scale,
+                           int max_iter, float* covs) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        const M4 c = loss == L_NONE ? estimate_cov(pts, k, idx + (size_t)i * k)
+                                    : estimate_cov_robust(pts, k, idx + (size_t)i * k, loss, mad_scale, min_scale, max_iter);
         store_T(c, covs + 16 * (size_t)i);
     }
 }

@@ -130,6 +130,7 @@ def lib() -> C.CDLL:
         "spx_index_nn_stats": (C.c_int, [vp, f32p, sz, hostf, C.c_float, u32p]),
         "spx_index_levels": (C.c_int, [vp, C.POINTER(C.c_int32)]),
         "spx_covariance": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
+        "spx_covariance_robust": (C.c_int, [vp, f32p, sz, i32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, f32p]),
         "spx_normals": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_normals_from_covs": (C.c_int, [vp, f32p, f32p, sz, f32p]),
         "spx_points_from_xyz": (C.c_int, [vp, f32p, sz, f32p]),

@@ -433,6 +433,21 @@ class covariance:  # namespace sycl_points::algorithms::covariance
                                         neighbors.k, points.covs.ptr))
 
     @staticmethod
+    def estimate_robust(neighbors: KNNResult, points: PointCloudShared, robust_type=None, mad_scale: float = 1.0,
+                        min_robust_scale: float = 1.0, robust_max_iterations: int = 1):
+        """covariance::estimate_robust_async(neighbors, points, robust_type, mad_scale, min_robust_scale,
+        robust_max_iterations) (covariance.hpp:323-390); default robust_type CAUCHY"""
+        n = points.size()
+        if neighbors.k > 64:
+            raise RuntimeError("[covariance::estimate_robust_async] neighbor K is too large. MAX_K is 64")
+        if points.covs is None or len(points.covs) != n:
+            points.covs = DeviceArray(points.queue, (n, 16), np.float32)
+        loss = int(RobustLossType.CAUCHY if robust_type is None else robust_type)
+        check(_lib.lib().spx_covariance_robust(points.queue.handle, _ptr(points.points), n, _ptr(neighbors.indices),
+                                               neighbors.k, loss, float(mad_scale), float(min_robust_scale),
+                                               int(robust_max_iterations), points.covs.ptr))
+
+    @staticmethod
     def estimate_knn(knn: KNNBase, points: PointCloudShared, k_correspondences: int):
         """covariance::estimate_async(knn, points, k) (covariance.hpp:304-311)"""
         neighbors = KNNResult()

@@ -71,6 +71,94 @@ __global__ void __launch_bounds__(FEAT_THREADS) covariance_kernel(const float4* 
     store_cov16(covs + (size_t)i * 16, mat3_from_sym(C));
 }
 
+// kernel::estimate_weighted — covariance.hpp:97-134: weighted sums over the valid neighbours in rank order, identity
+// when fewer than 4 of them or no weight; returns success
+__device__ __forceinline__ bool estimate_cov_weighted(const float4* __restrict__ pts, const int32_t* __restrict__ row, int k,
+                                                      const float* w, Mat3& C, float mean[3]) {
+    float sp[3] = {0.f, 0.f, 0.f};
+    float so[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    int cnt = 0;
+    float tw = 0.0f;
+    for (int j = 0; j < k; ++j) {
+        const int id = __ldg(row + j);
+        if (id < 0) continue;
+        const float4 p4 = __ldg(pts + id);
+        const float p[3] = {p4.x, p4.y, p4.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            sp[a] = __fadd_rn(sp[a], __fmul_rn(p[a], w[j]));
+#pragma unroll
+            for (int b = 0; b < 3; ++b) so[a][b] = __fadd_rn(so[a][b], __fmul_rn(__fmul_rn(p[a], p[b]), w[j]));
+        }
+        ++cnt;
+        tw = __fadd_rn(tw, w[j]);
+    }
+    if (cnt < 4 || tw < 1.1920929e-07f) {
+        C = mat3_identity();
+        return false;
+    }
+    const float inv = __fdiv_rn(1.0f, tw);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) mean[a] = __fmul_rn(sp[a], inv);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) C.m[a][b] = __fsub_rn(__fmul_rn(so[a][b], inv), __fmul_rn(mean[a], mean[b]));
+    return true;  // exactly symmetric: ensure_symmetric is the identity on it
+}
+
+// kernel::estimate_robust — covariance.hpp:182-222: M-estimated covariance: weights from the SQUARED Mahalanobis
+// distances (passed to the robust weight as the residual, as the reference does) at scale mad_scale x median
+// (floored at min_robust_scale; the median runs over all k entries, unfilled ones count as 0, :159-173)
+constexpr int ROBUST_MAX_K = 64;
+__global__ void __launch_bounds__(FEAT_THREADS) covariance_robust_kernel(const float4* __restrict__ pts, uint32_t n,
+                                                                         const int32_t* __restrict__ idx, int k, int loss,
+                                                                         float mad_scale, float min_scale, int max_iter,
+                                                                         float* __restrict__ covs) {
+    const uint32_t i = blockIdx.x * FEAT_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* row = idx + (size_t)i * k;
+    float w[ROBUST_MAX_K], d2[ROBUST_MAX_K];
+    for (int j = 0; j < ROBUST_MAX_K; ++j) {
+        w[j] = 1.0f;
+        d2[j] = 0.0f;
+    }
+    Mat3 C;
+    float mean[3] = {0.f, 0.f, 0.f};
+    bool ok = estimate_cov_weighted(pts, row, k, w, C, mean);
+    for (int it = 0; ok && it < max_iter; ++it) {
+        const Mat3 Ci = mat3_inverse(C);
+        for (int j = 0; j < k; ++j) {
+            const int id = __ldg(row + j);
+            if (id < 0) continue;
+            const float4 p = __ldg(pts + id);
+            const float d0 = __fsub_rn(p.x, mean[0]), d1 = __fsub_rn(p.y, mean[1]), dz = __fsub_rn(p.z, mean[2]);
+            const float m0 = __fmaf_rn(Ci.m[0][2], dz, __fmaf_rn(Ci.m[0][1], d1, __fmul_rn(Ci.m[0][0], d0)));
+            const float m1 = __fmaf_rn(Ci.m[1][2], dz, __fmaf_rn(Ci.m[1][1], d1, __fmul_rn(Ci.m[1][0], d0)));
+            const float m2 = __fmaf_rn(Ci.m[2][2], dz, __fmaf_rn(Ci.m[2][1], d1, __fmul_rn(Ci.m[2][0], d0)));
+            d2[j] = __fmaf_rn(dz, m2, __fmaf_rn(d1, m1, __fmul_rn(d0, m0)));
+        }
+        // median by insertion sort in the weights buffer (compute_median, :143-173)
+        for (int j = 0; j < k; ++j) w[j] = d2[j];
+        for (int a = 1; a < k; ++a) {
+            const float key = w[a];
+            int b = a;
+            while (b > 0 && w[b - 1] > key) {
+                w[b] = w[b - 1];
+                --b;
+            }
+            w[b] = key;
+        }
+        const int mid = k / 2;
+        const float median = (k % 2 == 0) ? __fmul_rn(__fadd_rn(w[mid - 1], w[mid]), 0.5f) : w[mid];
+        float scale = __fmul_rn(mad_scale, median);
+        if (scale < min_scale) scale = min_scale;
+        for (int j = 0; j < k; ++j) w[j] = robust_weight(loss, d2[j], scale);
+        ok = estimate_cov_weighted(pts, row, k, w, C, mean);
+    }
+    store_cov16(covs + (size_t)i * 16, C);
+}
+
 __global__ void __launch_bounds__(FEAT_THREADS) normals_kernel(const float4* __restrict__ pts, uint32_t n,
                                                                const int32_t* __restrict__ idx, int k,
                                                                float4* __restrict__ normals) {
@@ -188,6 +276,30 @@ int spx_covariance(spx_queue_t q, const float* points, size_t n, const int32_t* 
         DeviceGuard g(q->device);
         covariance_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
             reinterpret_cast<const float4*>(points), (uint32_t)n, knn_idx, k, covs);
+        SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_covariance_robust(spx_queue_t q, const float* points, size_t n, const int32_t* knn_idx, int k, int robust_loss,
+                          float mad_scale, float min_robust_scale, int robust_max_iterations, float* covs) {
+    return guard([&] {
+        SPX_REQUIRE(q, "[covariance::estimate_robust_async] null queue");
+        SPX_REQUIRE(n < (1ull << 31), "[covariance::estimate_robust_async] too many points");
+        if (k > ROBUST_MAX_K)
+            throw Error(SPX_ERR_INVALID_ARGUMENT, "[covariance::estimate_robust_async] neighbor K is too large. MAX_K is 64");
+        SPX_REQUIRE(robust_loss >= SPX_LOSS_NONE && robust_loss <= SPX_LOSS_GEMAN_MCCLURE,
+                    "[covariance::estimate_robust_async] unknown robust loss");
+        if (n == 0) return;
+        SPX_REQUIRE(points && knn_idx && covs && k >= 1, "[covariance::estimate_robust_async] null pointer or k < 1");
+        DeviceGuard g(q->device);
+        if (robust_loss == SPX_LOSS_NONE) {  // covariance.hpp:241-244: the plain estimate
+            covariance_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
+                reinterpret_cast<const float4*>(points), (uint32_t)n, knn_idx, k, covs);
+        } else {
+            covariance_robust_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
+                reinterpret_cast<const float4*>(points), (uint32_t)n, knn_idx, k, robust_loss, mad_scale, min_robust_scale,
+                std::max(robust_max_iterations, 0), covs);
+        }
         SPX_LAUNCH_CHECK();
     });
 }

@@ -243,6 +243,45 @@ __device__ __forceinline__ void store_cov16(float* __restrict__ out, const Mat3&
 }
 #endif  // __CUDACC__
 
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ robust kernels (robust.hpp:56-114)
+__device__ __forceinline__ float robust_weight(int loss, float r, float s) {
+    if (loss == SPX_LOSS_NONE) return 1.0f;
+    if (r <= 1e-8f) return 1.0f;
+    const float x = __fdiv_rn(r, s);
+    switch (loss) {
+        case SPX_LOSS_HUBER: return fminf(1.0f, __fdiv_rn(1.0f, x));
+        case SPX_LOSS_TUKEY: {
+            if (x >= 1.0f) return 0.0f;
+            const float f = __fsub_rn(1.0f, __fmul_rn(x, x));
+            return __fmul_rn(f, f);
+        }
+        case SPX_LOSS_CAUCHY: return __fdiv_rn(1.0f, __fadd_rn(1.0f, __fmul_rn(x, x)));
+        default: {
+            const float d = __fadd_rn(1.0f, __fmul_rn(x, x));
+            return __fdiv_rn(1.0f, __fmul_rn(d, d));
+        }
+    }
+}
+
+__device__ __forceinline__ float robust_error(int loss, float r, float s) {
+    const float r2 = __fmul_rn(r, r), s2 = __fmul_rn(s, s);
+    switch (loss) {
+        case SPX_LOSS_HUBER:
+            return r <= s ? __fmul_rn(__fmul_rn(0.5f, r), r) : __fmul_rn(s, __fsub_rn(r, __fmul_rn(0.5f, s)));
+        case SPX_LOSS_TUKEY:
+            return r <= s ? __fmul_rn(__fdiv_rn(s2, 6.0f), __fsub_rn(1.0f, cr_cubef(__fsub_rn(1.0f, __fdiv_rn(r2, s2)))))
+                          : __fdiv_rn(s2, 6.0f);
+        case SPX_LOSS_CAUCHY:
+            return __fmul_rn(__fmul_rn(__fmul_rn(0.5f, s), s), cr_logf(__fadd_rn(1.0f, __fdiv_rn(r2, s2))));
+        case SPX_LOSS_GEMAN_MCCLURE:
+            return __fdiv_rn(__fmul_rn(0.5f, __fmul_rn(__fmul_rn(s2, r), r)), __fadd_rn(s2, r2));
+        default: return __fmul_rn(__fmul_rn(0.5f, r), r);
+    }
+}
+
+#endif  // __CUDACC__
+
 // ---------------------------------------------------------------- SE(3) pieces (host + device)
 // lie::se3_exp — eigen_utils.hpp:886-943 (so3_exp -> quaternion -> rotation; V matrix).  Row-major out.
 SPX_HD void se3_exp_rm(const float a[6], float T[4][4]) {

@@ -317,3 +317,25 @@ def test_points_from_packed_xyz(spx, q):
     cloud.set_points_xyz(d, len(xyz))
     got = cloud.points_host()
     assert np.array_equal(got[:, :3], xyz) and (got[:, 3] == 1.0).all()
+
+
+@pytest.mark.parametrize("loss", ["NONE", "HUBER", "TUKEY", "CAUCHY", "GEMAN_MCCLURE"])
+def test_robust_covariance_bit_exact(spx, q, bundled, loss):
+    """covariance::estimate_robust (covariance.hpp:97-134,143-250,323-373): M-estimated covariances, same fp32
+    operations in the same order as the oracle -> bit-exact, on the bundled cloud (tiny determinants: the inverse is
+    the reference's zero matrix) and on a x10 copy (real Mahalanobis weights), k = 10 / 20, 1 and 3 iterations."""
+    for scale_pts, mad, floor_ in ((1.0, 1.0, 1.0), (10.0, 1.5, 1e-3)):
+        tgt = bundled["target_ds"].copy()
+        tgt[:, :3] *= np.float32(scale_pts)
+        cloud = spx.PointCloudShared(q, tgt)
+        tree = spx.KDTree.build(q, cloud)
+        for k, iters in ((10, 1), (20, 3)):
+            nn = tree.knn_search(cloud, k)
+            spx.covariance.estimate_robust(nn, cloud, spx.RobustLossType[loss], mad, floor_, iters)
+            got = cloud.covs_host()
+            want = oracle.covariance_robust(tgt, nn.indices_host(), oracle.LOSS[loss], mad, floor_, iters)
+            assert np.array_equal(got, want), (loss, k, iters, np.abs(got - want).max())
+            if loss != "NONE" and scale_pts > 1:
+                assert not np.array_equal(want, oracle.covariance(tgt, nn.indices_host()))  # the weights did something
+    with pytest.raises(RuntimeError, match="neighbor K is too large"):
+        spx.covariance.estimate_robust(tree.knn_search(cloud, 65), cloud)
