@@ -212,7 +212,12 @@ class PairPipeline:
         # pipelined mode (two pairs in flight): the align of pair s runs on its own queue while both feeder chains
         # of pair s+1 run on q / q2
         self.q3 = spx.DeviceQueue(q.device)
-        self.reg3 = spx.Registration(self.q3, params)
+        # the pipelined align leaves SM resources to the next pair's feeder kernels: its persistent grid is capped at
+        # two CTAs per SM (a full-occupancy cooperative grid can neither start while feeders hold SMs nor share them)
+        import copy
+        params3 = copy.deepcopy(params)
+        params3.max_blocks = int(os.environ.get("SPX_BENCH_ALIGN_BLOCKS", 2 * q.device_info()["sm_count"]))
+        self.reg3 = spx.Registration(self.q3, params3)
         self.nn_pipe = [(spx.KNNResult(), spx.KNNResult()) for _ in range(2)]
         self.done_pipe = [(spx.Event(), spx.Event()) for _ in range(2)]
         # resident raw clouds: one (source, target) per rotating pair, sized for the largest

@@ -188,6 +188,13 @@ SPX_API int spx_knn_bruteforce(spx_queue_t q, const float* queries, size_t nq, c
  * index (uniform cell grid, counting-sorted on device) over `targets`; cell_size <= 0 picks one
  * from the point density.  The index keeps its own sorted copy; `targets` may be freed after. */
 SPX_API int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_size, spx_index_t* out);
+/* The same index from a caller that already knows a box containing the points and the cell edges it wants — e.g. a
+ * cloud that just came out of the voxel grid (spx_voxel_last_box; ~1.85 x voxel_size holds ~3 points per occupied
+ * cell on LiDAR surfaces, ~2.4 x voxel_size ~5 for the k >= 2 first-pass grid).  Skips the build's bounding-box /
+ * occupancy pass and its host round trip: fully asynchronous.  A box that misses points costs speed, never exactness
+ * (cell coordinates clamp into the grid).  knn_cell_size <= cell_size: no extra k-NN grid. */
+SPX_API int spx_index_build_hinted(spx_queue_t q, const float* targets, size_t nt, const float* lo3_host, const float* hi3_host,
+                           float cell_size, float knn_cell_size, spx_index_t* out);
 SPX_API int spx_index_destroy(spx_index_t index);
 /* KNNBase::knn_search_async(queries, k, result, depends, transT) — knn.hpp:22-24,
  * kdtree.hpp:203-224,424-562.  Exact: identical to spx_knn_bruteforce on the same inputs
@@ -246,6 +253,9 @@ SPX_API int spx_transform(spx_queue_t q, float* points, float* covs, float* norm
  * (synchronises).  voxel_size <= 0 -> SPX_ERR_INVALID_ARGUMENT (voxel_downsampling.hpp:23-25). */
 SPX_API int spx_voxel_downsample(spx_queue_t q, const float* points, size_t n, float voxel_size, size_t min_voxel_count,
                          float* out_points, size_t* m_host);
+/* Metric box [lo, hi] that contains every point the LAST spx_voxel_downsample* call on this queue produced (from the
+ * voxel coordinates' bounding box the sort already needed; one voxel of slack): the hint of spx_index_build_hinted. */
+SPX_API int spx_voxel_last_box(spx_queue_t q, float* lo3_host, float* hi3_host, float* voxel_size);
 /* filter::VoxelGrid::downsampling(cloud, result) — voxel_downsampling.hpp:64-79,220-288: the cloud
  * overload also aggregates per-point attributes over each voxel in the same order: mean RGBA
  * (float[n][4]), MEDIAN intensity (float[n], :82-98), mean timestamp offset (float[n]).  Any

@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
         "spx_event_elapsed_ms": (C.c_int, [vp, vp, C.POINTER(C.c_float)]),
         "spx_knn_bruteforce": (C.c_int, [vp, f32p, sz, f32p, sz, C.c_int, hostf, i32p, f32p]),
         "spx_index_build": (C.c_int, [vp, f32p, sz, C.c_float, C.POINTER(vp)]),
+        "spx_index_build_hinted": (C.c_int, [vp, f32p, sz, hostf, hostf, C.c_float, C.c_float, C.POINTER(vp)]),
+        "spx_voxel_last_box": (C.c_int, [vp, hostf, hostf, C.POINTER(C.c_float)]),
         "spx_index_destroy": (C.c_int, [vp]),
         "spx_index_knn": (C.c_int, [vp, f32p, sz, C.c_int, hostf, i32p, f32p]),
         "spx_index_info": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64),

@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -222,9 +223,19 @@ def _addr(p):
 
 
 # ------------------------------------------------------------------ containers
+# A cloud that comes out of the voxel grid carries the box and cell edges KDTree.build needs (index_hint): with ~one
+# point per occupied voxel on LiDAR surfaces, cells of 1.85 voxels hold ~3 points (the k = 1 optimum) and cells of
+# 2.4 voxels ~5 (the k-NN first-pass grid) — what the adaptive build measures on such clouds.  SPX_INDEX_HINT=0 turns
+# the hints off (every build measures its own occupancy curve).
+INDEX_HINTS = os.environ.get("SPX_INDEX_HINT", "1") != "0"
+INDEX_HINT_CELL = float(os.environ.get("SPX_INDEX_HINT_CELL", "1.85"))
+INDEX_HINT_KNN_CELL = float(os.environ.get("SPX_INDEX_HINT_KNN_CELL", "2.4"))
+
+
 class PointCloudShared:
     """PointCloudShared (point_cloud.hpp:73-476): per-attribute arrays on the device.
     points (n,4) xyz1; covs (n,4,4) symmetric, zero 4th row/col; normals (n,4) xyz0."""
+    index_hint = None
 
     def __init__(self, queue: DeviceQueue, points: np.ndarray | None = None, covs: np.ndarray | None = None,
                  normals: np.ndarray | None = None):
@@ -261,6 +272,7 @@ class PointCloudShared:
             raise ValueError("points must be (n, 4) float32 (xyz1)")
         self.points = DeviceArray.from_host(self.queue, p)
         self._n = len(p)
+        self.index_hint = None
 
     def set_covs(self, covs: np.ndarray):
         c = np.asarray(covs, dtype=np.float32).reshape(-1, 4, 4)
@@ -298,6 +310,7 @@ class PointCloudShared:
     def adopt_points(self, dev: DeviceArray, n: int):
         self.points = dev
         self._n = n
+        self.index_hint = None
 
     def points_host(self) -> np.ndarray:
         return self.points.download(self._n) if self._n else np.zeros((0, 4), np.float32)
@@ -377,8 +390,14 @@ class KDTree(KNNBase):
         # leaf_threshold is the reference's KD-tree knob; it has no meaning for the grid (accepted, ignored)
         t = KDTree(queue)
         h = C.c_void_p()
-        check(_lib.lib().spx_index_build(queue.handle, _ptr(cloud.points), cloud.size(), float(cell_size),
-                                         C.byref(h)))
+        hint = getattr(cloud, "index_hint", None)
+        if hint is not None and cell_size <= 0.0 and cloud.size() > 0:
+            lo, hi, cell, cell_knn = hint
+            check(_lib.lib().spx_index_build_hinted(queue.handle, _ptr(cloud.points), cloud.size(), _hostf(lo), _hostf(hi),
+                                                    float(cell), float(cell_knn), C.byref(h)))
+        else:
+            check(_lib.lib().spx_index_build(queue.handle, _ptr(cloud.points), cloud.size(), float(cell_size),
+                                             C.byref(h)))
         t._h = h
         t._n = cloud.size()
         return t
@@ -546,6 +565,13 @@ class VoxelGrid:
                 C.byref(m)))
         mm = int(m.value)
         result.adopt_points(out, mm)
+        # the voxel box of the output, known without touching the points: lets KDTree.build skip its bounding-box /
+        # occupancy pass and the host round trip (spx_index_build_hinted).  Dropped by anything that moves the points.
+        result.index_hint = None
+        if mm > 0 and INDEX_HINTS:
+            lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+            check(_lib.lib().spx_voxel_last_box(self.queue.handle, _hostf(lo), _hostf(hi), None))
+            result.index_hint = (lo, hi, INDEX_HINT_CELL * self._voxel_size, INDEX_HINT_KNN_CELL * self._voxel_size)
         result.covs = None
         result.normals = None
         result.rgb = _trim(o_rgb, mm)
@@ -602,6 +628,8 @@ class PreprocessFilter:
         for name, a in zip(self._ATTRS, res):
             setattr(output, name, a)
         output._n = m
+        if output is not cloud:
+            output.index_hint = getattr(cloud, "index_hint", None)  # a subset stays inside the box
         return output
 
     def random_sampling(self, cloud: PointCloudShared, sampling_num: int,
@@ -655,6 +683,7 @@ class transform:  # namespace sycl_points::algorithms::transform (common/transfo
         check(_lib.lib().spx_transform(cloud.queue.handle, cloud.points.ptr,
                                        _ptr(cloud.covs) if cloud.has_cov() else None,
                                        _ptr(cloud.normals) if cloud.has_normal() else None, cloud.size(), _hostf(t16)))
+        cloud.index_hint = None  # the points moved: the voxel box no longer describes them
 
     transform_async = transform
 

@@ -91,6 +91,14 @@ struct spx_queue_s {
         int mn[3] = {0, 0, 0};
         int mx[3] = {0, 0, 0};
     } voxel_geom;
+    // voxel box of the LAST down-sampled cloud on this queue (its own, not the joined guess): the metric bounding
+    // box of its output follows from it without touching the points (spx_voxel_last_box -> hinted index build)
+    struct {
+        bool valid = false;
+        float voxel = 0.0f;
+        int mn[3] = {0, 0, 0};
+        int mx[3] = {0, 0, 0};
+    } voxel_last;
 
     void arena_reset() { arena_off = 0; }
     // Reserve the total a call needs BEFORE taking pointers: growing invalidates nothing in flight

@@ -55,10 +55,13 @@ __device__ __forceinline__ int grid_coord(float q, float o, float inv, int dim) 
     return (int)g;
 }
 
-// distance from q to the slab of cell index ci on one axis (0 inside), minus nothing; >= 0
-__device__ __forceinline__ float axis_gap(float q, float o, float cell, int ci) {
-    const float lo = __fmaf_rn((float)ci, cell, o);
-    const float hi = __fmaf_rn((float)(ci + 1), cell, o);
+// distance from q to the slab of cell index ci on one axis (0 inside); >= 0.  The two boundary cells of an axis also
+// hold the points that lie BEYOND the grid on their side (cell coordinates clamp), so their slabs extend to
+// infinity outward: a query outside the grid must not be told that the boundary cell is far away.
+__device__ __forceinline__ float axis_gap(float q, float o, float cell, int ci, int dim) {
+    const float INF = __int_as_float(0x7f800000);
+    const float lo = ci > 0 ? __fmaf_rn((float)ci, cell, o) : -INF;
+    const float hi = ci < dim - 1 ? __fmaf_rn((float)(ci + 1), cell, o) : INF;
     return fmaxf(fmaxf(lo - q, q - hi), 0.0f);
 }
 
@@ -257,8 +260,8 @@ __device__ __forceinline__ bool grid_search(const GridView& g, float qx, float q
                 if (lim2 < 1.0e30f) {
                     // prune rows that cannot hold anything better than the current k-th best, and
                     // cells of the row farther along x than sqrt(lim2 - gap^2) (+ allowance)
-                    const float gz = axis_gap(qz, g.oz, g.cell, zz);
-                    const float gy = axis_gap(qy, g.oy, g.cell, yy);
+                    const float gz = axis_gap(qz, g.oz, g.cell, zz, g.dz);
+                    const float gy = axis_gap(qy, g.oy, g.cell, yy, g.dy);
                     const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
                     const float gyz2 = __fmul_rn(gyz, gyz);
                     if (gyz2 > lim2) continue;
@@ -450,8 +453,8 @@ static __device__ __noinline__ void knn_coop_search(const GridLevels& gl, float 
                     int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
                     bool ok = true;
                     if (kth_d < 1.0e30f) {
-                        const float gz = axis_gap(qz, g.oz, g.cell, zz);
-                        const float gy = axis_gap(qy, g.oy, g.cell, yy);
+                        const float gz = axis_gap(qz, g.oz, g.cell, zz, g.dz);
+                        const float gy = axis_gap(qy, g.oy, g.cell, yy, g.dy);
                         const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
                         const float gyz2 = __fmul_rn(gyz, gyz);
                         ok = !(gyz2 > kth_d);
@@ -581,8 +584,8 @@ __device__ __forceinline__ int icp_first_pass(const GridView& g, float qx, float
     float gy2[3], gz2[3];
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-        const float a = prune ? axis_gap(qy, g.oy, g.cell, cy + v - 1) : 0.0f;
-        const float b = prune ? axis_gap(qz, g.oz, g.cell, cz + v - 1) : 0.0f;
+        const float a = prune ? axis_gap(qy, g.oy, g.cell, cy + v - 1, g.dy) : 0.0f;
+        const float b = prune ? axis_gap(qz, g.oz, g.cell, cz + v - 1, g.dz) : 0.0f;
         gy2[v] = __fmul_rn(a, a);
         gz2[v] = __fmul_rn(b, b);
     }
@@ -736,8 +739,8 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
                 int xa = max(cx - R, 0), xb = min(cx + R, g.dx - 1);
                 bool ok = true;
                 if (lim2 < 1.0e30f) {
-                    const float gz = axis_gap(qz, g.oz, g.cell, zz);
-                    const float gy = axis_gap(qy, g.oy, g.cell, yy);
+                    const float gz = axis_gap(qz, g.oz, g.cell, zz, g.dz);
+                    const float gy = axis_gap(qy, g.oy, g.cell, yy, g.dy);
                     const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
                     const float gyz2 = __fmul_rn(gyz, gyz);
                     ok = gyz2 <= lim2;

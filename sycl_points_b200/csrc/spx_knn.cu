@@ -770,8 +770,8 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_coop_list_kernel(const 
                     int xa = max(cx - r, 0), xb = min(cx + r, g.dx - 1);
                     bool ok = true;
                     if (lim2 < 1.0e30f) {
-                        const float gz = axis_gap(q.z, g.oz, g.cell, zz);
-                        const float gy = axis_gap(q.y, g.oy, g.cell, yy);
+                        const float gz = axis_gap(q.z, g.oz, g.cell, zz, g.dz);
+                        const float gy = axis_gap(q.y, g.oy, g.cell, yy, g.dy);
                         const float gyz = fmaxf(sqrtf(__fmaf_rn(gz, gz, __fmul_rn(gy, gy))) - margin, 0.0f);
                         const float gyz2 = __fmul_rn(gyz, gyz);
                         ok = gyz2 <= lim2;
@@ -810,14 +810,15 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_coop_list_kernel(const 
                         for (int seg = 0; seg < 2; ++seg) {
                             const uint32_t a0 = __shfl_sync(FULL, seg ? sB : sA, src), b0 = __shfl_sync(FULL, seg ? eB : eA, src);
                             d_cands += b0 - a0;
-                            for (uint32_t j = a0 + lane; j < b0 + 96; j += 128) {  // warp-uniform trip count
+                            for (uint32_t jb = a0; jb < b0; jb += 128) {  // warp-uniform trip count
+                                const uint32_t j = jb + lane;
                                 float4 p4[4];
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
                                     if (j + 32 * u < b0) p4[u] = __ldg(g.pts + j + 32 * u);
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
-                                    if (j - lane + 32 * u >= b0) continue;  // warp-uniform
+                                    if (jb + 32 * u >= b0) continue;  // warp-uniform
                                     if (nb > COOP_BUF - 32) merge();
                                     const unsigned long long kth4 = __shfl_sync(FULL, mykey, K - 1);
                                     bool take = false;
@@ -1130,7 +1131,44 @@ int spx_knn_bruteforce(spx_queue_t q, const float* queries, size_t nq, const flo
     });
 }
 
+namespace {
+// a caller that already knows a box containing the points (e.g. the voxel box of a down-sampled cloud) and the cell
+// edges it wants skips the build's first phase — bounding box, occupancy curve, and the host round trip that sizes
+// the grid.  A box that misses points is harmless for exactness (cell coordinates clamp into the grid, and every bound
+// of the searches is a lower bound on clamped points), it only costs speed.
+struct BuildHint {
+    float lo[3], hi[3];
+    float cell, cell_knn;
+};
+int index_build_impl(spx_queue_t q, const float* targets, size_t nt, float cell_size, const BuildHint* hint, spx_index_t* out);
+}  // namespace
+
 int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_size, spx_index_t* out) {
+    return index_build_impl(q, targets, nt, cell_size, nullptr, out);
+}
+
+int spx_index_build_hinted(spx_queue_t q, const float* targets, size_t nt, const float* lo3_host, const float* hi3_host,
+                           float cell_size, float knn_cell_size, spx_index_t* out) {
+    if (!lo3_host || !hi3_host || !(cell_size > 0.0f)) {
+        set_last_error("[KDTree::build] hinted build needs a box and a positive cell size");
+        return SPX_ERR_INVALID_ARGUMENT;
+    }
+    BuildHint h;
+    for (int a = 0; a < 3; ++a) {
+        h.lo[a] = lo3_host[a];
+        h.hi[a] = hi3_host[a];
+        if (!(h.hi[a] >= h.lo[a]) || !std::isfinite(h.lo[a]) || !std::isfinite(h.hi[a])) {
+            set_last_error("[KDTree::build] hinted build: the box is empty or not finite");
+            return SPX_ERR_INVALID_ARGUMENT;
+        }
+    }
+    h.cell = cell_size;
+    h.cell_knn = knn_cell_size;
+    return index_build_impl(q, targets, nt, cell_size, &h, out);
+}
+
+namespace {
+int index_build_impl(spx_queue_t q, const float* targets, size_t nt, float cell_size, const BuildHint* hint, spx_index_t* out) {
     return guard([&] {
         SPX_REQUIRE(q && out, "[KDTree::build] null argument");
         SPX_REQUIRE(nt < (1ull << 31), "[KDTree::build] too many points");
@@ -1169,6 +1207,19 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         BuildHead* hhead = static_cast<BuildHead*>(q->pinned_get(1024));
         unsigned int* hones = hhead->ones;
         const bool adaptive = !(cell_size > 0.0f);
+        if (hint) {
+            // everything the first phase would have measured, from the caller's box: no kernel, no round trip
+            std::memset(hhead, 0, sizeof(BuildHead));
+            hhead->acc.finite = n;  // (non-finite points are skipped by the counting kernels; only capacities use this)
+            float max_abs = 0.0f;
+            for (int a = 0; a < 3; ++a) {
+                hhead->plan.lo[a] = hint->lo[a];
+                hhead->plan.ext[a] = hint->hi[a] - hint->lo[a];
+                max_abs = std::max(max_abs, std::max(std::fabs(hint->lo[a]), std::fabs(hint->hi[a])));
+            }
+            hhead->plan.max_abs = max_abs;
+            hhead->plan.c0 = hint->cell;
+        } else {
         // accumulators, ticket and counters start as zero bits: one memset clears them together with the
         // occupancy bitmaps behind them; the bounding-box kernel's last block derives the occupancy plan
         SPX_CUDA(cudaMemsetAsync(head, 0,
@@ -1187,6 +1238,7 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         }
         SPX_CUDA(cudaMemcpyAsync(hhead, head, sizeof(BuildHead), cudaMemcpyDeviceToHost, st));
         q->sync();  // the only host round trip of the build: grid dimensions size the allocations
+        }
         const BBoxAcc bb = hhead->acc;
         const OccPlan pl = hhead->plan;
         ix->n = bb.finite;
@@ -1243,7 +1295,9 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         };
         float cell = cell_size;
         float cell_knn = 0.0f;  // edge of the extra first-pass grid of the k >= 2 searches (0: none)
-        if (adaptive) {
+        if (hint) {
+            cell_knn = hint->cell_knn;
+        } else if (adaptive) {
             double want = 3.0, want_knn = 5.0;
             if (const char* e = std::getenv("SPX_CELL_TARGET")) want = std::max(0.5, std::atof(e));          // tuning aids
             if (const char* e = std::getenv("SPX_KNN_CELL_TARGET")) want_knn = std::max(0.0, std::atof(e));
@@ -1335,6 +1389,7 @@ int spx_index_build(spx_queue_t q, const float* targets, size_t nt, float cell_s
         // no final sync: everything above is ordered on the queue's stream, and so is every search
     });
 }
+}  // namespace
 
 int spx_index_destroy(spx_index_t index) {
     return guard([&] {

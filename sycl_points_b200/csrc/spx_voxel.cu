@@ -882,6 +882,7 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         if (!(voxel_size > 0.0f)) throw Error(SPX_ERR_INVALID_ARGUMENT, "voxel_size must be positive");
         SPX_REQUIRE(n_in < (1ull << 31), "[VoxelGrid::downsampling] too many points");
         *m_host = 0;
+        q->voxel_last.valid = false;
         if (n_in == 0) return;
         SPX_REQUIRE(points && out_points, "[VoxelGrid::downsampling] null pointer");
         SPX_REQUIRE((!rgb || out_rgb) && (!intensity || out_intensity) && (!timestamps || out_timestamps),
@@ -1001,6 +1002,12 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         // hacc holds this cloud's box either way: it is the next call's guess — joined with the previous guess
         // when that costs no radix pass (a queue that alternates between two clouds, source and target of a
         // pair, would otherwise miss on every larger one)
+        q->voxel_last.valid = hacc->valid > 0;
+        q->voxel_last.voxel = voxel_size;
+        for (int a = 0; a < 3; ++a) {
+            q->voxel_last.mn[a] = hacc->mn[a];
+            q->voxel_last.mx[a] = hacc->mx[a];
+        }
         if (hacc->valid > 0) {
             int mn[3], mx[3];
             bool join = cache.valid && cache.voxel == voxel_size;
@@ -1023,6 +1030,21 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         }
         if (guessed && hacc->valid == 0) htotal[0] = 0;
         *m_host = htotal[0];
+    });
+}
+
+int spx_voxel_last_box(spx_queue_t q, float* lo3_host, float* hi3_host, float* voxel_size) {
+    return guard([&] {
+        SPX_REQUIRE(q && lo3_host && hi3_host, "[VoxelGrid::last_box] null argument");
+        SPX_REQUIRE(q->voxel_last.valid, "[VoxelGrid::last_box] no down-sampled cloud on this queue yet");
+        // voxel coordinate c (offset by 2^20, voxel_constants.hpp:36-53) covers [c, c + 1) * voxel in floor(p * (1 / voxel));
+        // one voxel of slack on both sides absorbs the rounding of p * inv against c * voxel
+        const float v = q->voxel_last.voxel;
+        for (int a = 0; a < 3; ++a) {
+            lo3_host[a] = (float)(q->voxel_last.mn[a] - (1 << 20) - 1) * v;
+            hi3_host[a] = (float)(q->voxel_last.mx[a] - (1 << 20) + 2) * v;
+        }
+        if (voxel_size) *voxel_size = v;
     });
 }
 

@@ -213,3 +213,42 @@ def test_self_search_after_the_points_moved(spx, q):
     r = tree.knn_search(cloud, 10)
     want = oracle.knn_bruteforce(moved, pts, 10)
     assert_same((r.indices_host(), r.distances_host()), want)
+
+
+def test_hinted_index_build_is_exact_even_with_a_wrong_box(spx, q, bundled):
+    """spx_index_build_hinted: the voxel grid's box + cell edges replace the build's measuring pass; searches stay
+    bit-exact vs the oracle — also when the box MISSES most of the cloud (cell coordinates clamp into the grid)."""
+    import ctypes as C
+    raw = bundled["source_raw_head"]
+    vg = spx.VoxelGrid(q, 0.25)
+    cloud = vg.downsampling(spx.PointCloudShared(q, raw))
+    assert cloud.index_hint is not None
+    pts = cloud.points_host()
+    lo, hi = cloud.index_hint[0], cloud.index_hint[1]
+    assert (pts[:, :3] >= lo).all() and (pts[:, :3] <= hi).all()
+    tree = spx.KDTree.build(q, cloud)  # hinted
+    oi, od = oracle.knn_bruteforce(pts, pts, 10)
+    r = tree.knn_search(cloud, 10)
+    assert np.array_equal(r.indices_host(), oi) and np.array_equal(r.distances_host(), od)
+    qpts = pts[::3].copy()
+    qpts[:, :3] += np.float32(0.1)
+    o1, d1 = oracle.knn_bruteforce(qpts, pts, 1)
+    qc = spx.PointCloudShared(q, qpts)
+    r1 = tree.knn_search(qc, 1)
+    assert np.array_equal(r1.indices_host(), o1) and np.array_equal(r1.distances_host(), d1)
+    # a box around a corner of the cloud only
+    mid = np.median(pts[:, :3], axis=0).astype(np.float32)
+    lo2, hi2 = (mid - 1.0).astype(np.float32), (mid + 2.0).astype(np.float32)
+    h = C.c_void_p()
+    spx._lib.check(spx.lib().spx_index_build_hinted(q.handle, cloud.points.ptr, cloud.size(),
+                                                    lo2.ctypes.data_as(C.POINTER(C.c_float)),
+                                                    hi2.ctypes.data_as(C.POINTER(C.c_float)), 0.4, 0.6, C.byref(h)))
+    t2 = spx.KDTree(q)
+    t2._h, t2._n = h, cloud.size()
+    r2 = t2.knn_search(cloud, 10)
+    assert np.array_equal(r2.indices_host(), oi) and np.array_equal(r2.distances_host(), od)
+    r3 = t2.knn_search(qc, 1)
+    assert np.array_equal(r3.indices_host(), o1) and np.array_equal(r3.distances_host(), d1)
+    # the hint does not survive a transform
+    spx.transform.transform(cloud, oracle.se3_exp(np.array([0, 0, 0.3, 5, 0, 0], np.float32)))
+    assert cloud.index_hint is None
