@@ -202,6 +202,14 @@ SPX_API int spx_index_destroy(spx_index_t index);
  * 1 <= k <= 128 (the reference throws above 100, kdtree.hpp:221-223).  Asynchronous. */
 SPX_API int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, const float* T_host, int32_t* idx,
                   float* dist);
+/* KDTree::radius_search_async(queries, max_k, radius, result, depends, transT) — kdtree.hpp:226-280,564-720: the
+ * max_k nearest targets within `radius` (dist^2 <= radius^2), ascending by (dist, idx), the rest -1 / FLT_MAX. */
+SPX_API int spx_index_radius(spx_index_t index, const float* queries, size_t nq, int max_k, float radius, const float* T_host,
+                     int32_t* idx, float* dist);
+/* KDTree::remove_nodes_by_flags(flags, indices) — kdtree.hpp:282-284,721-760: points whose flag is not INCLUDE (1) leave
+ * the index, the others are re-numbered new_index[old] (device arrays of n entries; n_kept = number of kept points =
+ * 1 + the largest new index).  The grid is rebuilt over the kept points; searches then report the new numbers. */
+SPX_API int spx_index_remove_by_flags(spx_index_t index, const uint8_t* flags, const int32_t* new_index, size_t n, size_t n_kept);
 /* introspection for tests / DESIGN.md: cell size, grid dims[3], occupied cells, points */
 SPX_API int spx_index_info(spx_index_t index, float* cell_size, int32_t* dims3, int64_t* occupied_cells, int64_t* n_points);
 /* tuning aid: per-query work counters of the k = 1 search, stats4[q] = {segments, candidate points,

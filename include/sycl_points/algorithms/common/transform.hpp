@@ -14,6 +14,7 @@ inline sycl_utils::events transform_async(PointCloudShared& cloud, const Transfo
     const size_t N = cloud.size();
     if (N == 0) return events;
     const auto& q = cloud.queue;
+    cloud.index_hint = PointCloudShared::IndexHint{};  // the points move: the voxel box no longer describes them
     q.set_accessed_by_device(cloud.points_ptr(), N);
     if (cloud.has_cov()) q.set_accessed_by_device(cloud.covs_ptr(), N);
     if (cloud.has_normal()) q.set_accessed_by_device(cloud.normals_ptr(), N);

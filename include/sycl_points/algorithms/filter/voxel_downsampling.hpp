@@ -89,6 +89,15 @@ public:
         result.normals->clear();
         result.start_time_ms = t0;
         result.end_time_ms = t1;
+        // the voxel box of the output: KDTree::build(queue, result) needs no measuring pass (1.85 / 2.4 voxels per
+        // cell hold ~3 / ~5 points per occupied cell on LiDAR surfaces)
+        result.index_hint = PointCloudShared::IndexHint{};
+        if (m > 0 && spx_voxel_last_box(q.handle(), result.index_hint.lo, result.index_hint.hi, nullptr) == SPX_OK) {
+            result.index_hint.data = result.points->data();
+            result.index_hint.n = m;
+            result.index_hint.cell = 1.85f * this->voxel_size_;
+            result.index_hint.knn_cell = 2.4f * this->voxel_size_;
+        }
     }
 
 private:

@@ -8,6 +8,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "spx.h"
@@ -33,6 +34,20 @@ inline void spx_check(int rc) {
 
 namespace sycl {
 
+/// the exception user code catches around device set-up (sycl::exception): CUDA failures surface as
+/// std::runtime_error from the C-ABI, so this type is never thrown — it only has to exist and be catchable
+class exception : public std::runtime_error {
+public:
+    explicit exception(const std::string& what) : std::runtime_error(what) {}
+};
+
+namespace info {
+namespace device {
+struct name {};
+struct vendor {};
+}  // namespace device
+}  // namespace info
+
 /// selects a CUDA ordinal: SPX_DEVICE (env) or 0 — the role ONEAPI_DEVICE_SELECTOR plays for the reference
 struct default_selector_t {
     int operator()() const {
@@ -51,6 +66,12 @@ public:
     template <typename Selector, typename = decltype(std::declval<Selector>()())>
     explicit device(const Selector& s) : ordinal_(s()) {}
     int ordinal() const { return ordinal_; }
+    /// device.get_info<sycl::info::device::name>()
+    template <typename Tag>
+    std::string get_info() const {
+        if constexpr (std::is_same_v<Tag, info::device::vendor>) return "NVIDIA Corporation";
+        else return this->name();
+    }
     bool is_gpu() const { return true; }
     bool is_cpu() const { return false; }
     std::string name() const {

@@ -60,6 +60,19 @@ struct PointCloudShared {
     double start_time_ms = 0.0;
     double end_time_ms = 0.0;
 
+    /// spx extension (not in the reference): a cloud that just came out of VoxelGrid::downsampling carries the box
+    /// and cell edges KDTree::build needs, so the build skips its measuring pass and host round trip
+    /// (spx_index_build_hinted).  Valid only while `data` / `n` still describe *points; transform clears it.  A stale
+    /// hint can cost speed, never exactness.
+    struct IndexHint {
+        const void* data = nullptr;
+        size_t n = 0;
+        float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        float cell = 0.0f, knn_cell = 0.0f;
+        bool matches(const void* d, size_t m) const { return data != nullptr && data == d && n == m && m > 0; }
+    };
+    mutable IndexHint index_hint;
+
     PointCloudShared(const sycl_utils::DeviceQueue& q) : queue(q) { this->make_containers(); }
 
     /// copy a host cloud in (point_cloud.hpp:110-198) and start moving it to the device

@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
         "spx_voxel_last_box": (C.c_int, [vp, hostf, hostf, C.POINTER(C.c_float)]),
         "spx_index_destroy": (C.c_int, [vp]),
         "spx_index_knn": (C.c_int, [vp, f32p, sz, C.c_int, hostf, i32p, f32p]),
+        "spx_index_radius": (C.c_int, [vp, f32p, sz, C.c_int, C.c_float, hostf, i32p, f32p]),
+        "spx_index_remove_by_flags": (C.c_int, [vp, vp, i32p, sz, sz]),
         "spx_index_info": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int64)]),
         "spx_index_nn_stats": (C.c_int, [vp, f32p, sz, hostf, C.c_float, u32p]),

@@ -428,6 +428,40 @@ class KDTree(KNNBase):
         check(_lib.lib().spx_index_knn(self._h, _ptr(queries.points), nq, k, _hostf(t16), result.indices.ptr,
                                        result.distances.ptr))
 
+    def radius_search_async(self, queries: PointCloudShared, max_k: int, radius: float, result: KNNResult,
+                            depends=None, transT=None):
+        """kdtree.hpp:251-280: the max_k nearest targets within `radius` (dist² <= radius²), the remaining slots
+        -1 / FLT_MAX."""
+        if max_k > 100:
+            raise SpxInvalidArgument(-1, "[KDTree::radius_search_async] `max_k` is too large. not support.")
+        nq = queries.size()
+        if nq == 0 or max_k == 0:
+            result.allocate(self.queue, 0, 0)  # kdtree.hpp:580-587
+            return
+        if result.indices is None or result.query_size != nq or result.k != max_k:
+            result.allocate(self.queue, nq, max_k)
+        check(_lib.lib().spx_index_radius(self._h, _ptr(queries.points), nq, max_k, float(radius), _hostf(_T16(transT)),
+                                          result.indices.ptr, result.distances.ptr))
+
+    def radius_search(self, queries: PointCloudShared, max_k: int, radius: float, depends=None, transT=None):
+        result = KNNResult()
+        self.radius_search_async(queries, max_k, radius, result, depends, transT)
+        queries.queue.wait()
+        return result
+
+    def remove_nodes_by_flags(self, flags: "DeviceArray", indices: "DeviceArray"):
+        """kdtree.hpp:282-284: drop the points whose flag is 0 (REMOVE_FLAG) and renumber the kept ones by `indices`
+        (old -> new, -1 where removed: FilterByFlags::calculate_indices)."""
+        if len(flags) != len(indices):
+            raise SpxInvalidArgument(-1, "[KDTree::remove_nodes_by_flags_impl] flags and indices must have the same size.")
+        if self._h is None or len(flags) == 0:
+            return
+        host = indices.download()
+        kept = int(host.max()) + 1 if host.size and host.max() >= 0 else 0
+        check(_lib.lib().spx_index_remove_by_flags(self._h, flags.ptr, indices.ptr, len(flags), kept))
+        self.queue.wait()
+        self._n = kept
+
     def close(self):
         if self._h:
             _lib.lib().spx_index_destroy(self._h)

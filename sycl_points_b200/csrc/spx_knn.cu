@@ -1079,6 +1079,35 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_nn_stats_kernel(const GridL
     stats[qi] = make_uint4(cs.segs, cs.cands, cs.shells, cs.last_level);
 }
 
+// radius search = the max_k nearest within the radius: entries farther than radius^2 become unfilled (-1 / FLT_MAX),
+// kdtree.hpp:564-720 (dist_sq <= radius_sq is kept, :663,678)
+__global__ void __launch_bounds__(256) radius_mask_kernel(int32_t* __restrict__ idx, float* __restrict__ dist, size_t n,
+                                                          float radius_sq) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (!(dist[i] <= radius_sq)) {
+        idx[i] = -1;
+        dist[i] = FLT_MAX;
+    }
+}
+
+// remove_nodes_by_flags — kdtree.hpp:282-284,721-760: the kept points, re-numbered by `new_index`, gathered out of the
+// index's own sorted copy (level 0 holds every finite point once, its original index in w)
+__global__ void __launch_bounds__(256) index_kept_points_kernel(const float4* __restrict__ sorted, uint32_t n,
+                                                                const uint8_t* __restrict__ flags,
+                                                                const int32_t* __restrict__ new_index, size_t n_flags,
+                                                                float4* __restrict__ out) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const float4 p = __ldg(sorted + j);
+    const int orig = __float_as_int(p.w);
+    if (orig < 0 || (size_t)orig >= n_flags) return;
+    if (flags[orig] == 1) {  // filter::INCLUDE_FLAG
+        const int ni = new_index[orig];
+        if (ni >= 0) out[ni] = make_float4(p.x, p.y, p.z, 1.0f);
+    }
+}
+
 void launch_bruteforce(spx_queue_t q, const float4* queries, uint32_t nq, const float4* targets, uint32_t nt, int k,
                        const Xform& T, int has_T, int32_t* idx, float* dist) {
     if (nq == 0) return;
@@ -1455,6 +1484,51 @@ int spx_index_nn_stats(spx_index_t index, const float* queries, size_t nq, const
             index->levels, reinterpret_cast<const float4*>(queries), (uint32_t)nq, T, T_host != nullptr, r,
             reinterpret_cast<uint4*>(stats4));
         SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_index_radius(spx_index_t index, const float* queries, size_t nq, int max_k, float radius, const float* T_host,
+                     int32_t* idx, float* dist) {
+    const int rc = spx_index_knn(index, queries, nq, max_k, T_host, idx, dist);
+    if (rc != SPX_OK || nq == 0) return rc;
+    return guard([&] {
+        spx_queue_t q = index->q;
+        DeviceGuard g(q->device);
+        const size_t n = nq * (size_t)max_k;
+        radius_mask_kernel<<<div_up(n, 256), 256, 0, q->stream>>>(idx, dist, n, radius * radius);
+        SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_index_remove_by_flags(spx_index_t index, const uint8_t* flags, const int32_t* new_index, size_t n, size_t n_kept) {
+    return guard([&] {
+        SPX_REQUIRE(index, "[KDTree::remove_nodes_by_flags] null index");
+        SPX_REQUIRE(flags && new_index, "[KDTree::remove_nodes_by_flags_impl] null flags / indices");
+        spx_queue_t q = index->q;
+        DeviceGuard g(q->device);
+        float4* kept = nullptr;
+        SPX_CUDA(cudaMallocAsync(&kept, std::max<size_t>(n_kept, 1) * sizeof(float4), q->stream));
+        // slots no kept point lands on (indices that skip numbers) hold NaN: the rebuilt index ignores them
+        SPX_CUDA(cudaMemsetAsync(kept, 0xff, std::max<size_t>(n_kept, 1) * sizeof(float4), q->stream));
+        if (index->n > 0) {
+            index_kept_points_kernel<<<div_up(index->n, 256), 256, 0, q->stream>>>(index->sorted[0], index->n, flags, new_index,
+                                                                                 n, kept);
+            SPX_LAUNCH_CHECK();
+        }
+        spx_index_t fresh = nullptr;
+        if (spx_index_build(q, reinterpret_cast<const float*>(kept), n_kept, 0.0f, &fresh) != SPX_OK) {
+            cudaFreeAsync(kept, q->stream);
+            throw Error(SPX_ERR_INTERNAL, spx_last_error());
+        }
+        SPX_CUDA(cudaFreeAsync(kept, q->stream));  // the index keeps its own sorted copy
+        // the handle the caller holds now IS the rebuilt index
+        for (int l = 0; l < GRID_MAX_LEVELS; ++l) {
+            if (index->sorted[l]) cudaFreeAsync(index->sorted[l], q->stream);
+            if (index->start[l]) cudaFreeAsync(index->start[l], q->stream);
+        }
+        if (index->occ_dev) cudaFreeAsync(index->occ_dev, q->stream);
+        *index = *fresh;
+        delete fresh;
     });
 }
 

@@ -3,7 +3,9 @@
 // compiled UNMODIFIED against include/ + libspx.so, so that reference-held assertions run on the CUDA path itself.
 // Not a product file: test infrastructure only.
 #pragma once
+#include <chrono>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <functional>
 #include <iostream>

@@ -91,3 +91,20 @@ def test_example_registration_on_bundled_pair(example_exe, bundled, tmp_path):
     line = [l for l in r.stdout.splitlines() if l.startswith("translation error vs ground truth")][0]
     assert float(line.split(":")[1].split()[0]) < 0.10, r.stdout
     assert "7. Registration" in r.stdout
+
+
+REF_TESTS = ["test_kdtree"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_TESTS)
+def test_reference_gtest_source_passes_on_libspx(name):
+    """The reference's own cpp/tests/<name>.cpp, compiled UNMODIFIED against include/ + libspx.so through
+    tests/cpp/gtest_shim (built by __graft_entry__.build() where /root/reference exists; the binary travels to
+    the GPU box): every reference-held assertion runs on the CUDA path."""
+    exe = os.path.join(BUILD, "ref_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt reference test binary is absent (no /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-4000:], r.stderr[-2000:])
+    assert " 0 failed" in r.stdout and "[  FAILED  ]" not in r.stdout
