@@ -253,6 +253,18 @@ SPX_API int spx_covariance_update_plane(spx_queue_t q, float* covs, size_t n);
  * reference's kernel).  Asynchronous. */
 SPX_API int spx_transform(spx_queue_t q, float* points, float* covs, float* normals, size_t n, const float* T_host);
 
+/* deskew::deskew_point_cloud_constant_velocity (algorithms/deskew/relative_pose_deskew.hpp:36-178): every point is
+ * moved by se3_exp(tau * twist), tau = clamp(timestamp_offset_ms * 1e-3 / scan_duration_s, 0, 1); normals and
+ * covariances (both nullable, in and out together) are rotated by the rotation of that motion.  twist6_host =
+ * se3_log(previous_pose^-1 * current_pose) as [rx ry rz tx ty tz] (spx_se3_log).  Outputs may alias the inputs. */
+SPX_API int spx_deskew_constant_velocity(spx_queue_t q, const float* points, const float* normals, const float* covs,
+                                         const float* timestamp_offsets_ms, size_t n, const float* twist6_host,
+                                         float scan_duration_s, float* points_out, float* normals_out, float* covs_out);
+/* eigen_utils::lie::se3_log (utils/eigen_utils.hpp:991-1034; spx_se3_exp below is its inverse): host arithmetic,
+ * column-major 4x4 -> [rx ry rz tx ty tz].  No device work, no queue. */
+SPX_API int spx_se3_log(const float* T_host, float* twist6_host);
+
+
 /* ------------------------------------------------------------------ filters
  * filter::VoxelGrid::downsampling(points, result) — I/algorithms/filter/voxel_downsampling.hpp:50-62,
  * key = I/algorithms/common/voxel_constants.hpp:36-62.  Device radix sort by (key, index), fp32

@@ -1,7 +1,6 @@
 // registration::RegistrationPipeline — I/algorithms/registration/registration_pipeline.hpp:17-151:
 // optional random subsampling of the source (default ON, 1000 points, persistent mt19937(1234)),
-// then the robust-scale wrapper around Registration::align.  The velocity-update (deskew) wrapper
-// is out of scope and must stay disabled.
+// then the wrapper chain RobustAligner -> VelocityUpdateAligner -> Registration::align (:99-117).
 #pragma once
 
 #include <memory>
@@ -10,6 +9,7 @@
 #include "sycl_points/algorithms/filter/preprocess_filter.hpp"
 #include "sycl_points/algorithms/registration/pipeline/aligner.hpp"
 #include "sycl_points/algorithms/registration/pipeline/robust.hpp"
+#include "sycl_points/algorithms/registration/pipeline/velocity_update.hpp"
 #include "sycl_points/algorithms/registration/registration.hpp"
 #include "sycl_points/algorithms/registration/registration_pipeline_params.hpp"
 
@@ -51,15 +51,19 @@ public:
         if (this->registration_ == nullptr)
             throw std::runtime_error(
                 "[RegistrationPipeline::compute_icp_robust_weights] Registration backend is not available.");
-        if (this->registration_input_pc_ == nullptr)
+        const auto source = this->get_deskewed_point_cloud();
+        if (source == nullptr)
             throw std::runtime_error(
                 "[RegistrationPipeline::compute_icp_robust_weights] Registration input point cloud is not available.");
-        this->registration_->compute_icp_robust_weights(*this->registration_input_pc_, target, target_knn, pose,
-                                                        robust_scale, out);
+        this->registration_->compute_icp_robust_weights(*source, target, target_knn, pose, robust_scale, out);
     }
 
     const PointCloudShared* get_registration_input_point_cloud() const { return this->registration_input_pc_.get(); }
-    const PointCloudShared::Ptr get_deskewed_point_cloud() const { return this->registration_input_pc_; }
+    /// the deskewed source of the most recent align(); the registration input when velocity update is off
+    const PointCloudShared::Ptr get_deskewed_point_cloud() const {
+        if (this->velocity_update_pipeline_ != nullptr) return this->velocity_update_pipeline_->get_deskewed_point_cloud();
+        return this->registration_input_pc_;
+    }
 
     float get_inlier_ratio(const RegistrationResult& result) const {
         const auto* input = this->get_registration_input_point_cloud();
@@ -69,8 +73,12 @@ public:
 
 private:
     void wrap_aligner() {
-        if (this->pipeline_params_.velocity_update.enable)
-            throw std::runtime_error("[RegistrationPipeline] velocity_update (deskew wrapper) is not built in libspx");
+        // for each robust scale: for each deskew update: align(...)   (:99-117)
+        if (this->pipeline_params_.velocity_update.enable) {
+            this->velocity_update_pipeline_ = std::make_shared<pipeline::VelocityUpdateAligner>(
+                this->aligner_, this->pipeline_params_.velocity_update.iter, this->pipeline_params_.registration.verbose);
+            this->aligner_ = this->velocity_update_pipeline_->make_aligner();
+        }
         if (this->pipeline_params_.random_sampling.use_intensities)
             throw std::runtime_error("[RegistrationPipeline] intensity-weighted sampling is not built in libspx");
         if (this->pipeline_params_.robust.auto_scale) {
@@ -96,6 +104,7 @@ private:
     Registration::Ptr registration_;
     RegistrationPipelineParams pipeline_params_;
     pipeline::RobustAligner::Ptr robust_pipeline_ = nullptr;
+    pipeline::VelocityUpdateAligner::Ptr velocity_update_pipeline_ = nullptr;
     pipeline::RegistrationAligner aligner_;
     mutable filter::PreprocessFilter::Ptr preprocess_filter_ = nullptr;
     mutable PointCloudShared::Ptr registration_input_pc_ = nullptr;

@@ -26,7 +26,7 @@ struct RegistrationRobustScheduleParams {
 };
 
 struct RegistrationVelocityUpdateParams {
-    bool enable = false;  // deskew wrapper is out of scope: must stay false
+    bool enable = false;
     size_t iter = 1;
 };
 

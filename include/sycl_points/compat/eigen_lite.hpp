@@ -239,6 +239,18 @@ struct Isometry3f {
     float* data() { return M.data(); }
 };
 
+/// Eigen::Translation3f: only as the left factor of an isometry product
+struct Translation3f {
+    Vector3f t;
+    Translation3f(float x, float y, float z) : t(x, y, z) {}
+    explicit Translation3f(const Vector3f& v) : t(v) {}
+    Isometry3f operator*(const Isometry3f& o) const {
+        Isometry3f r = o;
+        r.set_translation(o.translation() + t);
+        return r;
+    }
+};
+
 template <typename T>
 struct aligned_allocator {
     using value_type = T;

@@ -377,6 +377,25 @@ def robust_weights(reg: int, loss: int, src_pts, src_covs, tgt_pts, tgt_covs, tg
     return w
 
 
+def deskew_constant_velocity(pts, ts_ms, twist, duration, covs=None, normals=None):
+    """deskew::deskew_point_cloud_constant_velocity (relative_pose_deskew.hpp:36-178) with twist =
+    se3_log(prev^-1 * cur) given: returns (points, covs | None, normals | None)."""
+    pts = _pts(pts)
+    n = len(pts)
+    ts = np.ascontiguousarray(ts_ms, np.float32)
+    tw = np.ascontiguousarray(twist, np.float32)
+    cv = None if covs is None else _covs_cm(covs)
+    nr = None if normals is None else _pts(normals)
+    o_p = np.empty_like(pts)
+    o_c = None if cv is None else np.empty((n, 16), np.float32)
+    o_n = None if nr is None else np.empty((n, 4), np.float32)
+    lib().orc_deskew_constant_velocity(_f(pts), _f(nr), _f(cv), _f(ts), C.c_size_t(n), _f(tw), C.c_float(duration),
+                                       _f(o_p), _f(o_n), _f(o_c))
+    if o_c is not None:
+        o_c = np.ascontiguousarray(o_c.reshape(n, 4, 4).transpose(0, 2, 1))
+    return o_p, o_c, o_n
+
+
 def se3_exp(twist) -> np.ndarray:
     tw = np.ascontiguousarray(twist, np.float32)
     out = np.empty(16, np.float32)

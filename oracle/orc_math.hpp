@@ -27,6 +27,7 @@ namespace orc {
 inline float cr_cos(float x) { return (float)std::cos((double)x); }
 inline float cr_sin(float x) { return (float)std::sin((double)x); }
 inline float cr_acos(float x) { return (float)std::acos((double)x); }
+inline float cr_atan2(float y, float x) { return (float)std::atan2((double)y, (double)x); }
 inline float cr_cbrt(float x) { return (float)std::cbrt((double)x); }
 inline float cr_log(float x) { return (float)std::log((double)x); }
 inline float cr_cube(float x) { const double d = (double)x; return (float)(d * d * d); }
@@ -404,7 +405,7 @@ inline V3 so3_log(const V4& quat) {
         const float th = 3.14159265358979323846f;
         return scale(xyz, th / n);
     }
-    const float th = 2.0f * std::atan2(n, std::fabs(w));
+    const float th = 2.0f * cr_atan2(n, std::fabs(w));
     return scale(xyz, th / n);
 }
 
@@ -425,7 +426,7 @@ inline V6 se3_log(const M4& T) {
             for (int j = 0; j < 3; ++j) Vinv(i, j) = Vinv(i, j) - 0.5f * Om(i, j);
     } else {
         const float h = 0.5f * th;
-        const float sh = std::sin(h), ch = std::cos(h);
+        const float sh = cr_sin(h), ch = cr_cos(h);
         const float coeff = (1.0f - th * ch / (2.0f * sh)) / (th * th);
         M3 Om2 = M3::zero();
         for (int i = 0; i < 3; ++i)

@@ -1233,6 +1233,50 @@ void orc_transform_cloud(const float* T16, const float* pts, const float* covs, 
     }
 }
 
+// deskew::deskew_point_cloud_constant_velocity — I/algorithms/deskew/relative_pose_deskew.hpp:121-174: per point
+// tau = clamp(t_ms * 1e-3 / duration, 0, 1), motion = se3_exp(tau * twist) (:140-146), point = motion * p (:149),
+// normal = R n (:155-160), covariance = R (C R^T) (:161-168) with R = quat_to_rot(so3_exp(tau * omega)); a
+// non-finite timestamp copies the element (:127-137).  normals / covs (column-major 4x4) may be NULL.
+void orc_deskew_constant_velocity(const float* pts, const float* normals, const float* covs, const float* ts_ms, size_t n,
+                                  const float* twist6, float duration, float* out_pts, float* out_normals,
+                                  float* out_covs) {
+    for (size_t i = 0; i < n; ++i) {
+        const float t_s = ts_ms[i] * 1e-3f;
+        if (!std::isfinite(t_s)) {
+            for (int a = 0; a < 4; ++a) out_pts[4 * i + a] = pts[4 * i + a];
+            if (normals) for (int a = 0; a < 4; ++a) out_normals[4 * i + a] = normals[4 * i + a];
+            if (covs) for (int a = 0; a < 16; ++a) out_covs[16 * i + a] = covs[16 * i + a];
+            continue;
+        }
+        const float tau = std::fmin(std::fmax(t_s / duration, 0.0f), 1.0f);
+        V6 a;
+        for (int k = 0; k < 6; ++k) a(k) = twist6[k] * tau;
+        const M4 motion = se3_exp(a);
+        const V4 r = mul<4, 4>(motion, load_p(pts + 4 * i));
+        for (int k = 0; k < 4; ++k) out_pts[4 * i + k] = r(k);
+        V3 om; om(0) = a(0); om(1) = a(1); om(2) = a(2);
+        const M3 R = quat_to_rot(so3_exp(om));
+        if (normals) {
+            V3 nv; nv(0) = normals[4 * i]; nv(1) = normals[4 * i + 1]; nv(2) = normals[4 * i + 2];
+            const V3 o = mul<3, 3>(R, nv);
+            out_normals[4 * i] = o(0); out_normals[4 * i + 1] = o(1); out_normals[4 * i + 2] = o(2);
+            out_normals[4 * i + 3] = 0.0f;
+        }
+        if (covs) {
+            M3 Cm, Rt;
+            for (int c = 0; c < 3; ++c)
+                for (int rr = 0; rr < 3; ++rr) {
+                    Cm(rr, c) = covs[16 * i + c * 4 + rr];
+                    Rt(rr, c) = R(c, rr);
+                }
+            const M3 o = mul<3, 3, 3>(R, mul<3, 3, 3>(Cm, Rt));
+            for (int a2 = 0; a2 < 16; ++a2) out_covs[16 * i + a2] = 0.0f;
+            for (int c = 0; c < 3; ++c)
+                for (int rr = 0; rr < 3; ++rr) out_covs[16 * i + c * 4 + rr] = o(rr, c);
+        }
+    }
+}
+
 // I/algorithms/knn/bruteforce.hpp:24-96 with the oracle's fixed distance formula (the
 // reference's sycl::dot leaves contraction to the SYCL implementation):
 // dist = fma(dz,dz,fma(dy,dy,dx*dx)) on the transformed query, order (dist, index).

@@ -133,6 +133,8 @@ def lib() -> C.CDLL:
                                      C.POINTER(C.c_int64)]),
         "spx_index_nn_stats": (C.c_int, [vp, f32p, sz, hostf, C.c_float, u32p]),
         "spx_index_levels": (C.c_int, [vp, C.POINTER(C.c_int32)]),
+        "spx_deskew_constant_velocity": (C.c_int, [vp, f32p, f32p, f32p, f32p, sz, hostf, C.c_float, f32p, f32p, f32p]),
+        "spx_se3_log": (C.c_int, [hostf, hostf]),
         "spx_covariance": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),
         "spx_covariance_robust": (C.c_int, [vp, f32p, sz, i32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, f32p]),
         "spx_normals": (C.c_int, [vp, f32p, sz, i32p, C.c_int, f32p]),

@@ -246,6 +246,8 @@ class PointCloudShared:
         self.rgb: DeviceArray | None = None          # (n, 4) RGBA in [0, 1]  (types.hpp:14-17)
         self.intensities: DeviceArray | None = None  # (n,)
         self.timestamp_offsets: DeviceArray | None = None  # (n,) ms relative to the first measurement
+        self.start_time_ms = 0.0
+        self.end_time_ms = 0.0
         self._n = 0
         if points is not None:
             self.set_points(points)
@@ -744,6 +746,56 @@ class transform:  # namespace sycl_points::algorithms::transform (common/transfo
         return out
 
 
+class deskew:  # namespace sycl_points::algorithms::deskew
+    @staticmethod
+    def deskew_point_cloud_constant_velocity(input_cloud: PointCloudShared, output_cloud: PointCloudShared,
+                                             previous_relative_pose, current_relative_pose,
+                                             inter_scan_duration_seconds: float = -1.0) -> bool:
+        """relative_pose_deskew.hpp:36-178.  False (nothing done) for an empty cloud, a cloud without timestamps
+        or a non-positive duration.  `output_cloud` may be `input_cloud`."""
+        n = input_cloud.size()
+        if n == 0 or not input_cloud.has_timestamps():
+            return False
+        dur = inter_scan_duration_seconds if inter_scan_duration_seconds > 0.0 else \
+            float(np.float32((input_cloud.end_time_ms - input_cloud.start_time_ms) * 1e-3))
+        if dur <= 0.0:
+            return False
+        q = input_cloud.queue
+        if output_cloud is not input_cloud:
+            def dup(a, enable):
+                if not enable:
+                    return None
+                b = DeviceArray(q, a.shape, a.dtype)
+                check(_lib.lib().spx_memcpy_d2d(q.handle, b.ptr, a.ptr, a.nbytes))
+                return b
+            output_cloud.start_time_ms, output_cloud.end_time_ms = input_cloud.start_time_ms, input_cloud.end_time_ms
+            output_cloud.timestamp_offsets = dup(input_cloud.timestamp_offsets, True)
+            output_cloud.points = DeviceArray(q, (n, 4), np.float32)
+            output_cloud._n = n
+            output_cloud.normals = DeviceArray(q, (n, 4), np.float32) if input_cloud.has_normal() else None
+            output_cloud.covs = DeviceArray(q, (n, 4, 4), np.float32) if input_cloud.has_cov() else None
+            output_cloud.rgb = dup(input_cloud.rgb, input_cloud.has_rgb())
+            output_cloud.intensities = dup(input_cloud.intensities, input_cloud.has_intensity())
+        output_cloud.index_hint = None
+        prev = np.asarray(previous_relative_pose, np.float32).reshape(4, 4)
+        cur = np.asarray(current_relative_pose, np.float32).reshape(4, 4)
+        inv = np.eye(4, dtype=np.float32)  # Isometry3f::inverse(): R^T, -R^T t
+        inv[:3, :3] = prev[:3, :3].T
+        inv[:3, 3] = -(prev[:3, :3].T @ prev[:3, 3])
+        delta = np.eye(4, dtype=np.float32)
+        delta[:3, :3] = inv[:3, :3] @ cur[:3, :3]
+        delta[:3, 3] = inv[:3, :3] @ cur[:3, 3] + inv[:3, 3]
+        twist = se3_log(delta)
+        nrm, cov = input_cloud.has_normal(), input_cloud.has_cov()
+        check(_lib.lib().spx_deskew_constant_velocity(
+            q.handle, input_cloud.points.ptr, _ptr(input_cloud.normals) if nrm else None,
+            _ptr(input_cloud.covs) if cov else None, output_cloud.timestamp_offsets.ptr, n, _hostf(twist), float(dur),
+            output_cloud.points.ptr, _ptr(output_cloud.normals) if nrm else None,
+            _ptr(output_cloud.covs) if cov else None))
+        q.wait()
+        return True
+
+
 # ------------------------------------------------------------------ registration
 class RegType(enum.IntEnum):  # factor.hpp:18-32
     POINT_TO_POINT = 0
@@ -946,6 +998,13 @@ def se3_exp(twist) -> np.ndarray:
     out = np.empty(16, np.float32)
     check(_lib.lib().spx_se3_exp(_hostf(tw), _hostf(out)))
     return _T_from16(out)
+
+
+def se3_log(T) -> np.ndarray:
+    """eigen_utils::lie::se3_log (eigen_utils.hpp:991-1034): [rx ry rz tx ty tz]."""
+    out = np.empty(6, np.float32)
+    check(_lib.lib().spx_se3_log(_hostf(_T16(T)), _hostf(out)))
+    return out
 
 
 def solve_6x6(H, b, lam: float):
@@ -1312,10 +1371,46 @@ class BatchAligner:
 
 
 @dataclass
+class VelocityUpdateParams:  # registration_pipeline_params.hpp:27-30
+    enable: bool = False
+    iter: int = 1
+
+
+@dataclass
 class RegistrationPipelineParams:  # registration_pipeline_params.hpp:32-41
     registration: RegistrationParams = field(default_factory=RegistrationParams)
     random_sampling: RandomSamplingParams = field(default_factory=RandomSamplingParams)
     robust: RobustScheduleParams = field(default_factory=RobustScheduleParams)
+    velocity_update: VelocityUpdateParams = field(default_factory=VelocityUpdateParams)
+
+
+class VelocityUpdateAligner:
+    """pipeline::VelocityUpdateAligner (pipeline/velocity_update.hpp:16-104): deskew the source with the current
+    pose estimate under a constant-velocity model (options.prev_pose, options.dt), align, repeat."""
+
+    def __init__(self, aligner, velocity_update_iter: int, verbose: bool = False):
+        self._aligner = aligner.align if isinstance(aligner, Registration) else aligner
+        self.velocity_update_iter = velocity_update_iter
+        self.verbose = verbose
+        self._deskewed = None
+
+    def get_deskewed_point_cloud(self):
+        return self._deskewed
+
+    def align(self, source, target, target_knn, initial_guess=None, options: "ExecutionOptions | None" = None):
+        options = options if options is not None else ExecutionOptions()
+        T0 = np.eye(4, dtype=np.float32) if initial_guess is None else np.asarray(initial_guess, np.float32)
+        result = RegistrationResult(T=T0.copy())
+        if source.size() == 0:
+            return result
+        if not source.has_timestamps():
+            self._deskewed = transform.transform_copy(source, np.eye(4, dtype=np.float32))
+            return self._aligner(self._deskewed, target, target_knn, result.T, options)
+        self._deskewed = PointCloudShared(source.queue)
+        for _ in range(max(1, self.velocity_update_iter)):
+            deskew.deskew_point_cloud_constant_velocity(source, self._deskewed, options.prev_pose, result.T, options.dt)
+            result = self._aligner(self._deskewed, target, target_knn, result.T, options)
+        return result
 
 
 def robust_scale_schedule(init_scale: float, min_scale: float, levels: int) -> list[float]:
@@ -1346,11 +1441,19 @@ class RegistrationPipeline:
         else:
             self.registration = Registration(queue_or_aligner, self.pipeline_params.registration)
             self._aligner = self.registration.align
+        self._velocity = None
+        vu = self.pipeline_params.velocity_update
+        if vu.enable:  # registration_pipeline.hpp:99-110: robust -> velocity update -> base aligner
+            self._velocity = VelocityUpdateAligner(self._aligner, vu.iter, self.pipeline_params.registration.verbose)
+            self._aligner = self._velocity.align
         self._input = None
         self._filter = None
 
     def get_registration_input_point_cloud(self):
         return self._input
+
+    def get_deskewed_point_cloud(self):
+        return self._velocity.get_deskewed_point_cloud() if self._velocity is not None else self._input
 
     def align(self, source, target, target_knn, initial_guess=None, options: ExecutionOptions | None = None):
         rs = self.pipeline_params.random_sampling

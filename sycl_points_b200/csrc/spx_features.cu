@@ -263,6 +263,90 @@ __global__ void __launch_bounds__(FEAT_THREADS) transform_cloud_kernel(float4* _
         o[a] = __fmaf_rn(rows[a].w, p.w, __fmaf_rn(rows[a].z, p.z, __fmaf_rn(rows[a].y, p.y, __fmaf_rn(rows[a].x, p.x, 0.0f))));
     pts[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
+
+// ------------------------------------------------------------------ constant-velocity deskew
+// deskew::deskew_point_cloud_constant_velocity — I/algorithms/deskew/relative_pose_deskew.hpp:121-174.  One
+// thread per point: tau = clamp(t_ms * 1e-3 / duration, 0, 1), M = se3_exp(tau * twist), point = M p; normal =
+// R n and covariance = R (C R^T) with R the rotation of M (quaternion_to_rotation_matrix(so3_exp(tau * omega)),
+// :155-157, is that same matrix); a point whose timestamp is not finite is copied (:127-137).  In place when the
+// output pointers equal the inputs (every thread reads its own element before it writes it).
+struct Twist6 {
+    float a[6];
+};
+__global__ void __launch_bounds__(FEAT_THREADS)
+    deskew_kernel(const float4* __restrict__ pin, const float4* __restrict__ nin, const float* __restrict__ cin,
+                  const float* __restrict__ ts, uint32_t n, Twist6 tw, float duration, float4* pout, float4* nout, float* cout) {
+    const uint32_t i = blockIdx.x * FEAT_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float t_s = __fmul_rn(ts[i], 1e-3f);
+    const float4 p = pin[i];
+    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 c[4];
+    if (nin) nv = nin[i];
+    if (cin)
+        for (int b = 0; b < 4; ++b) c[b] = reinterpret_cast<const float4*>(cin + (size_t)i * 16)[b];
+    if (!isfinite(t_s)) {
+        pout[i] = p;
+        if (nin) nout[i] = nv;
+        if (cin)
+            for (int b = 0; b < 4; ++b) reinterpret_cast<float4*>(cout + (size_t)i * 16)[b] = c[b];
+        return;
+    }
+    const float tau = fminf(fmaxf(__fdiv_rn(t_s, duration), 0.0f), 1.0f);
+    float a[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = __fmul_rn(tw.a[k], tau);
+    float M[4][4];
+    se3_exp_rm(a, M);
+    const float pv[4] = {p.x, p.y, p.z, p.w};
+    float o[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc = __fmaf_rn(M[r][k], pv[k], acc);
+        o[r] = acc;
+    }
+    pout[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (nin) {
+        const float v[3] = {nv.x, nv.y, nv.z};
+        float r3[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc = __fmaf_rn(M[r][k], v[k], acc);
+            r3[r] = acc;
+        }
+        nout[i] = make_float4(r3[0], r3[1], r3[2], 0.0f);
+    }
+    if (cin) {
+        const float Cm[3][3] = {{c[0].x, c[1].x, c[2].x}, {c[0].y, c[1].y, c[2].y}, {c[0].z, c[1].z, c[2].z}};
+        float X[3][3], R[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {  // X = C R^T
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc = __fmaf_rn(Cm[r][k], M[b][k], acc);
+                X[r][b] = acc;
+            }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc = __fmaf_rn(M[r][k], X[k][b], acc);
+                R[r][b] = acc;
+            }
+        float4* co = reinterpret_cast<float4*>(cout + (size_t)i * 16);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) co[b] = make_float4(R[0][b], R[1][b], R[2][b], 0.0f);
+        co[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -380,6 +464,38 @@ int spx_transform(spx_queue_t q, float* points, float* covs, float* normals, siz
             reinterpret_cast<float4*>(points), covs, reinterpret_cast<float4*>(normals), (uint32_t)n,
             xform_from_colmajor(T_host));
         SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_deskew_constant_velocity(spx_queue_t q, const float* points, const float* normals, const float* covs,
+                                 const float* timestamp_offsets_ms, size_t n, const float* twist6_host,
+                                 float scan_duration_s, float* points_out, float* normals_out, float* covs_out) {
+    return guard([&] {
+        SPX_REQUIRE(q && twist6_host, "[deskew_point_cloud_constant_velocity] null argument");
+        SPX_REQUIRE(n < (1ull << 31), "[deskew_point_cloud_constant_velocity] too many points");
+        SPX_REQUIRE(scan_duration_s > 0.0f, "[deskew_point_cloud_constant_velocity] scan duration must be positive");
+        if (n == 0) return;
+        SPX_REQUIRE(points && points_out && timestamp_offsets_ms, "[deskew_point_cloud_constant_velocity] null points or timestamps");
+        SPX_REQUIRE((normals == nullptr) == (normals_out == nullptr) && (covs == nullptr) == (covs_out == nullptr),
+                    "[deskew_point_cloud_constant_velocity] an attribute needs both its input and its output");
+        DeviceGuard g(q->device);
+        Twist6 tw;
+        for (int k = 0; k < 6; ++k) tw.a[k] = twist6_host[k];
+        deskew_kernel<<<div_up(n, FEAT_THREADS), FEAT_THREADS, 0, q->stream>>>(
+            reinterpret_cast<const float4*>(points), reinterpret_cast<const float4*>(normals), covs, timestamp_offsets_ms,
+            (uint32_t)n, tw, scan_duration_s, reinterpret_cast<float4*>(points_out), reinterpret_cast<float4*>(normals_out),
+            covs_out);
+        SPX_LAUNCH_CHECK();
+    });
+}
+
+int spx_se3_log(const float* T_host, float* twist6_host) {
+    return guard([&] {
+        SPX_REQUIRE(T_host && twist6_host, "[lie::se3_log] null argument");
+        float T[4][4];
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) T[r][c] = T_host[c * 4 + r];
+        se3_log_rm(T, twist6_host);
     });
 }
 

@@ -344,6 +344,85 @@ SPX_HD void se3_exp_rm(const float a[6], float T[4][4]) {
     }
 }
 
+// lie::se3_log — eigen_utils.hpp:774-803 (rotation -> quaternion), :948-986 (so3_log), :991-1034.  Host code in
+// the reference too (velocity_update.hpp:71, relative_pose_deskew.hpp:108); atan2 / sin / cos are evaluated in
+// fp64 and cast, like every transcendental of this library.  Row-major 4x4 in, [rx ry rz tx ty tz] out.
+SPX_HD void se3_log_rm(const float T[4][4], float a[6]) {
+    float q[4];
+    const float tr = SPX_ADD(SPX_ADD(T[0][0], T[1][1]), T[2][2]);
+    if (tr > 0.0f) {
+        const float S = SPX_MUL(sqrtf(SPX_ADD(tr, 1.0f)), 2.0f);
+        q[0] = SPX_DIV(SPX_SUB(T[2][1], T[1][2]), S);
+        q[1] = SPX_DIV(SPX_SUB(T[0][2], T[2][0]), S);
+        q[2] = SPX_DIV(SPX_SUB(T[1][0], T[0][1]), S);
+        q[3] = SPX_MUL(0.25f, S);
+    } else if (T[0][0] > T[1][1] && T[0][0] > T[2][2]) {
+        const float S = SPX_MUL(sqrtf(SPX_SUB(SPX_SUB(SPX_ADD(1.0f, T[0][0]), T[1][1]), T[2][2])), 2.0f);
+        q[0] = SPX_MUL(0.25f, S);
+        q[1] = SPX_DIV(SPX_ADD(T[0][1], T[1][0]), S);
+        q[2] = SPX_DIV(SPX_ADD(T[0][2], T[2][0]), S);
+        q[3] = SPX_DIV(SPX_SUB(T[2][1], T[1][2]), S);
+    } else if (T[1][1] > T[2][2]) {
+        const float S = SPX_MUL(sqrtf(SPX_SUB(SPX_SUB(SPX_ADD(1.0f, T[1][1]), T[0][0]), T[2][2])), 2.0f);
+        q[0] = SPX_DIV(SPX_ADD(T[0][1], T[1][0]), S);
+        q[1] = SPX_MUL(0.25f, S);
+        q[2] = SPX_DIV(SPX_ADD(T[1][2], T[2][1]), S);
+        q[3] = SPX_DIV(SPX_SUB(T[0][2], T[2][0]), S);
+    } else {
+        const float S = SPX_MUL(sqrtf(SPX_SUB(SPX_SUB(SPX_ADD(1.0f, T[2][2]), T[0][0]), T[1][1])), 2.0f);
+        q[2] = SPX_MUL(0.25f, S);
+        q[3] = SPX_DIV(SPX_SUB(T[1][0], T[0][1]), S);
+        q[0] = SPX_DIV(SPX_ADD(T[0][2], T[2][0]), S);
+        q[1] = SPX_DIV(SPX_ADD(T[1][2], T[2][1]), S);
+    }
+    // so3_log: normalise, w >= 0, three angle regimes
+    const float nrm = sqrtf(SPX_FMA(q[3], q[3], SPX_FMA(q[2], q[2], SPX_FMA(q[1], q[1], SPX_FMA(q[0], q[0], 0.0f)))));
+    if (nrm < 1e-6f) {
+        q[0] = q[1] = q[2] = q[3] = 0.0f;
+    } else {
+        const float inv = SPX_DIV(1.0f, nrm);
+        for (int i = 0; i < 4; ++i) q[i] = SPX_MUL(q[i], inv);
+    }
+    if (q[3] < 0.0f)
+        for (int i = 0; i < 4; ++i) q[i] = SPX_MUL(q[i], -1.0f);
+    const float w = q[3];
+    const float n = sqrtf(SPX_FMA(q[2], q[2], SPX_FMA(q[1], q[1], SPX_FMA(q[0], q[0], 0.0f))));
+    float sc;
+    if (n < 1e-6f) {
+        sc = SPX_MUL(SPX_DIV(2.0f, w), SPX_ADD(1.0f, SPX_DIV(SPX_MUL(n, n), SPX_MUL(SPX_MUL(6.0f, w), w))));
+    } else if (fabsf(w) < 1e-6f) {
+        sc = SPX_DIV(3.14159265358979323846f, n);
+    } else {
+        sc = SPX_DIV(SPX_MUL(2.0f, (float)atan2((double)n, (double)fabsf(w))), n);
+    }
+    const float om[3] = {SPX_MUL(q[0], sc), SPX_MUL(q[1], sc), SPX_MUL(q[2], sc)};
+    a[0] = om[0];
+    a[1] = om[1];
+    a[2] = om[2];
+    const float th = sqrtf(SPX_FMA(om[2], om[2], SPX_FMA(om[1], om[1], SPX_FMA(om[0], om[0], 0.0f))));
+    const float Om[3][3] = {{0.0f, -om[2], om[1]}, {om[2], 0.0f, -om[0]}, {-om[1], om[0], 0.0f}};
+    float Vinv[3][3];
+    if (th < 1e-6f) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Vinv[i][j] = SPX_SUB((i == j) ? 1.0f : 0.0f, SPX_MUL(0.5f, Om[i][j]));
+    } else {
+        const float h = SPX_MUL(0.5f, th);
+        const float sh = cr_sinf(h), ch = cr_cosf(h);
+        const float coeff = SPX_DIV(SPX_SUB(1.0f, SPX_DIV(SPX_MUL(th, ch), SPX_MUL(2.0f, sh))), SPX_MUL(th, th));
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                float s2 = 0.0f;
+                for (int k = 0; k < 3; ++k) s2 = SPX_ADD(s2, SPX_MUL(Om[i][k], Om[k][j]));
+                Vinv[i][j] = SPX_ADD(SPX_SUB((i == j) ? 1.0f : 0.0f, SPX_MUL(0.5f, Om[i][j])), SPX_MUL(coeff, s2));
+            }
+    }
+    for (int i = 0; i < 3; ++i) {
+        float s = 0.0f;
+        for (int k = 0; k < 3; ++k) s = SPX_ADD(s, SPX_MUL(Vinv[i][k], T[k][3]));
+        a[3 + i] = s;
+    }
+}
+
 // result.T * Isometry3f(se3_exp(delta)) — registration.hpp:814 (Eigen isometry product:
 // linear = L1*L2, translation = L1*t2 + t1).  Row-major 4x4.
 SPX_HD void isometry_mul_rm(const float A[4][4], const float B[4][4], float out[4][4]) {

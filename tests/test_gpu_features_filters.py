@@ -339,3 +339,108 @@ def test_robust_covariance_bit_exact(spx, q, bundled, loss):
                 assert not np.array_equal(want, oracle.covariance(tgt, nn.indices_host()))  # the weights did something
     with pytest.raises(RuntimeError, match="neighbor K is too large"):
         spx.covariance.estimate_robust(tree.knn_search(cloud, 65), cloud)
+
+
+def _deskew_inputs(spx, q, bundled, n=20000):
+    tgt = bundled["target_ds"][:n]
+    cloud = spx.PointCloudShared(q, tgt)
+    nn = spx.KDTree.build(q, cloud).knn_search(cloud, 10)
+    spx.covariance.estimate(nn, cloud)
+    spx.covariance.estimate_normals(nn, cloud)
+    rng = np.random.default_rng(21)
+    ts = rng.uniform(-10, 120, len(tgt)).astype(np.float32)  # ms; some before 0 and past the 100 ms scan
+    ts[::97] = np.nan
+    ts[5::101] = np.inf
+    cloud.set_timestamp_offsets(ts)
+    return tgt, cloud, ts
+
+
+def test_deskew_constant_velocity_vs_oracle(spx, q, bundled):
+    """deskew::deskew_point_cloud_constant_velocity (relative_pose_deskew.hpp:36-178): same fp32 operations as the
+    oracle with correctly rounded sin / cos on both sides -> bit-exact points, normals and covariances; elements
+    with a non-finite timestamp are copied; in place == out of place."""
+    tgt, cloud, ts = _deskew_inputs(spx, q, bundled)
+    covs, nrm = cloud.covs_host(), cloud.normals_host()
+    prev = oracle.se3_exp(np.array([0.01, -0.02, 0.03, 0.2, 0.1, -0.05], np.float32))
+    cur = oracle.se3_exp(np.array([0.03, -0.01, 0.09, 0.9, 0.3, -0.02], np.float32))
+    delta = np.eye(4, dtype=np.float32)
+    Rt = prev[:3, :3].T
+    delta[:3, :3] = Rt @ cur[:3, :3]
+    delta[:3, 3] = Rt @ cur[:3, 3] - Rt @ prev[:3, 3]
+    twist = spx.api.se3_log(delta)
+    assert np.array_equal(twist, oracle.se3_log(delta))
+    o_p, o_c, o_n = oracle.deskew_constant_velocity(tgt, ts, twist, 0.1, covs, nrm)
+    out = spx.PointCloudShared(q)
+    assert spx.deskew.deskew_point_cloud_constant_velocity(cloud, out, prev, cur, 0.1)
+    assert np.array_equal(out.points_host(), o_p)
+    assert np.array_equal(out.normals_host(), o_n)
+    assert np.array_equal(out.covs_host(), o_c)
+    bad = ~np.isfinite(ts)
+    assert bad.sum() > 100 and np.array_equal(out.points_host()[bad], tgt[bad])
+    assert np.array_equal(out.covs_host()[bad], covs[bad])
+    late = ts >= 100.0  # tau clamps to 1: the whole motion
+    whole = oracle.transform_points(oracle.se3_exp(twist), tgt[late])
+    assert np.allclose(out.points_host()[late], whole, rtol=0, atol=1e-5)
+    assert np.array_equal(out.points_host()[ts <= 0.0], tgt[ts <= 0.0])  # tau = 0: identity motion
+    assert np.array_equal(cloud.points_host(), tgt)  # the input was left alone
+    assert spx.deskew.deskew_point_cloud_constant_velocity(cloud, cloud, prev, cur, 0.1)  # in place
+    assert np.array_equal(cloud.points_host(), o_p) and np.array_equal(cloud.covs_host(), o_c)
+
+
+def test_deskew_prerequisites_and_pure_translation(spx, q):
+    """relative_pose_deskew.hpp:50-61 (false without timestamps / duration) and the translation known answer of
+    T/test_relative_pose_deskew.cpp: a point sampled at tau moves by tau x the inter-scan translation."""
+    pts = np.array([[1, 0, 0, 1], [0, 2, 0, 1], [0, 0, 3, 1]], np.float32)
+    cloud, out = spx.PointCloudShared(q, pts), spx.PointCloudShared(q)
+    eye = np.eye(4, dtype=np.float32)
+    cur = eye.copy()
+    cur[:3, 3] = [1.0, -2.0, 0.5]
+    assert not spx.deskew.deskew_point_cloud_constant_velocity(cloud, out, eye, cur, 0.1)  # no timestamps
+    cloud.set_timestamp_offsets(np.array([0.0, 50.0, 100.0], np.float32))
+    assert not spx.deskew.deskew_point_cloud_constant_velocity(cloud, out, eye, cur, -1.0)  # start == end time
+    cloud.start_time_ms, cloud.end_time_ms = 0.0, 100.0
+    assert spx.deskew.deskew_point_cloud_constant_velocity(cloud, out, eye, cur, -1.0)  # duration from the cloud
+    want = pts.copy()
+    want[1, :3] += 0.5 * cur[:3, 3]
+    want[2, :3] += cur[:3, 3]
+    assert np.allclose(out.points_host(), want, rtol=0, atol=1e-6)
+    assert out.has_timestamps() and np.array_equal(out.timestamp_offsets.download(), [0.0, 50.0, 100.0])
+
+
+def test_velocity_update_aligner_and_pipeline(spx, q):
+    """T/test_registration_pipeline.cpp:219-330: accessors before align, the most recent deskewed cloud is a copy
+    with its own storage, the fallback without timestamps, and the RegistrationPipeline wiring."""
+    def cloud_of(n, stamps=True):
+        c = spx.PointCloudShared(q, np.c_[np.arange(n), np.zeros((n, 2)), np.ones(n)].astype(np.float32))
+        c.set_intensities(np.arange(n, dtype=np.float32))
+        if stamps:
+            c.set_timestamp_offsets(np.linspace(0, 100, n).astype(np.float32))
+        return c
+    seen = []
+
+    def aligner(src, tgt, knn, T, options):
+        seen.append((src.size(), src.has_timestamps()))
+        r = spx.RegistrationResult(T=np.eye(4, dtype=np.float32))
+        r.T[0, 3] = 1.0
+        r.inlier = src.size()
+        return r
+
+    vu = spx.VelocityUpdateAligner(aligner, 2)
+    assert vu.get_deskewed_point_cloud() is None
+    src = cloud_of(4)
+    opt = spx.ExecutionOptions(dt=0.1)
+    res = vu.align(src, cloud_of(3), None, np.eye(4, dtype=np.float32), opt)
+    d = vu.get_deskewed_point_cloud()
+    assert res.inlier == 4 and seen == [(4, True), (4, True)]
+    assert d.size() == 4 and d.has_timestamps() and d.points.ptr.value != src.points.ptr.value
+    # second level deskews with T = translate x by 1 over dt: the last point (tau = 1) moved by the full metre
+    assert np.allclose(d.points_host()[:, 0], np.arange(4) + np.linspace(0, 1, 4), atol=1e-6)
+    seen.clear()
+    vu.align(cloud_of(4, stamps=False), cloud_of(3), None, None, opt)
+    assert seen == [(4, False)] and not vu.get_deskewed_point_cloud().has_timestamps()
+    pp = spx.RegistrationPipelineParams()
+    pp.velocity_update.enable, pp.velocity_update.iter = True, 1
+    pipe = spx.RegistrationPipeline(aligner, pp)
+    assert pipe.get_deskewed_point_cloud() is None
+    pipe.align(cloud_of(5), cloud_of(3), None, None, opt)
+    assert pipe.get_deskewed_point_cloud().size() == 5

@@ -257,14 +257,14 @@ def test_hinted_index_build_is_exact_even_with_a_wrong_box(spx, q, bundled):
 def test_radius_search_matches_masked_bruteforce(spx, q):
     """kdtree.hpp:251-280 / test_kdtree.cpp:514: max_k nearest within the radius, the rest -1 / FLT_MAX."""
     rng = np.random.default_rng(5)
-    tgt = rng.uniform(-10, 10, (3000, 3)).astype(np.float32)
-    qry = rng.uniform(-10, 10, (500, 3)).astype(np.float32)
+    tgt = np.c_[rng.uniform(-10, 10, (3000, 3)), np.ones(3000)].astype(np.float32)
+    qry = np.c_[rng.uniform(-10, 10, (500, 3)), np.ones(500)].astype(np.float32)
     t, qc = spx.PointCloudShared(q, tgt), spx.PointCloudShared(q, qry)
     tree = spx.KDTree.build(q, t)
     for max_k, radius in ((8, 1.5), (20, 0.4), (1, 2.0)):
         res = tree.radius_search(qc, max_k, radius)
         idx, dist = res.indices_host(), res.distances_host()
-        d2 = ((qry[:, None, :].astype(np.float64) - tgt[None].astype(np.float64)) ** 2).sum(-1)
+        d2 = ((qry[:, None, :3].astype(np.float64) - tgt[None, :, :3].astype(np.float64)) ** 2).sum(-1)
         order = np.argsort(d2, axis=1)[:, :max_k]
         ref_d = np.take_along_axis(d2, order, 1)
         inside = ref_d <= np.float64(np.float32(radius) * np.float32(radius)) * (1 - 1e-6)
@@ -280,7 +280,7 @@ def test_remove_nodes_by_flags_renumbers_and_stays_exact(spx, q):
     """kdtree.hpp:282-284 / test_kdtree.cpp:459: after the removal the index answers like a fresh one over the
     kept points, in the compacted numbering."""
     rng = np.random.default_rng(6)
-    pts = rng.uniform(-10, 10, (4000, 3)).astype(np.float32)
+    pts = np.c_[rng.uniform(-10, 10, (4000, 3)), np.ones(4000)].astype(np.float32)
     cloud = spx.PointCloudShared(q, pts)
     tree = spx.KDTree.build(q, cloud)
     flags = (rng.random(4000) > 0.35).astype(np.uint8)
