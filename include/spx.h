@@ -284,6 +284,18 @@ SPX_API int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_
                                size_t min_voxel_count, const float* rgb, const float* intensity,
                                const float* timestamps, float* out_points, float* out_rgb, float* out_intensity,
                                float* out_timestamps, size_t* m_host);
+
+/* filter::PolarGrid::downsampling (algorithms/filter/polar_downsampling.hpp:30-108 key, :341-452 aggregation): the
+ * same sort-and-aggregate pass as the voxel grid with cells in (range, elevation, azimuth) — key = range cell
+ * (lowest digits), elevation cell, azimuth cell (highest); points at the origin or on the polar axis are dropped.
+ * Output in ascending key order; attributes as spx_voxel_downsample_attrs. */
+#define SPX_COORD_LIDAR 0  /* x forward, y left, z up    (common/coordinate_system.hpp) */
+#define SPX_COORD_CAMERA 1 /* x right, y down, z forward */
+SPX_API int spx_polar_downsample_attrs(spx_queue_t q, const float* points, size_t n, float distance_voxel_size,
+                                       float elevation_voxel_size, float azimuth_voxel_size, int coordinate_system,
+                                       size_t min_voxel_count, const float* rgb, const float* intensity,
+                                       const float* timestamps, float* out_points, float* out_rgb, float* out_intensity,
+                                       float* out_timestamps, size_t* m_host);
 /* PreprocessFilter::box_filter(cloud, min, max) — preprocess_operator/box_filter_operator.hpp:19-54,
  * common.hpp:15-25, common/filter_by_flags.hpp:43-49 (order-preserving).  Synchronises. */
 SPX_API int spx_box_filter(spx_queue_t q, const float* points, size_t n, float min_distance, float max_distance,

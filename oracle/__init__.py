@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         L.orc_rng_create.argtypes = [C.c_uint32]
         L.orc_kdtree_build.restype = C.c_void_p
         L.orc_kdtree_size.restype = C.c_size_t
+        L.orc_polar_downsample_attrs.restype = C.c_size_t
         L.orc_voxel_downsample.restype = C.c_size_t
         L.orc_voxel_downsample_unstable.restype = C.c_size_t
         L.orc_voxel_downsample_attrs.restype = C.c_size_t
@@ -466,6 +467,25 @@ def voxel_downsample_attrs(points, voxel_size, min_voxel_count, rgb=None, intens
     o_it = None if intensity is None else np.empty(n, np.float32)
     o_ts = None if timestamps is None else np.empty(n, np.float32)
     m = lib().orc_voxel_downsample_attrs(_f(p), C.c_size_t(n), C.c_float(voxel_size), C.c_size_t(min_voxel_count),
+                                         _f(rgb_a), _f(it), _f(ts), _f(out), _f(o_rgb), _f(o_it), _f(o_ts))
+    cut = lambda a: None if a is None else a[:m].copy()
+    return out[:m].copy(), cut(o_rgb), cut(o_it), cut(o_ts)
+
+
+def polar_downsample_attrs(points, dist_size, elev_size, azim_size, coord_system=0, min_voxel_count=1, rgb=None,
+                           intensity=None, timestamps=None):
+    """filter::PolarGrid::downsampling (polar_downsampling.hpp); coord_system 0 LIDAR / 1 CAMERA."""
+    p = _pts(points)
+    n = len(p)
+    out = np.empty_like(p)
+    rgb_a = None if rgb is None else _pts(rgb)
+    it = None if intensity is None else np.ascontiguousarray(intensity, np.float32)
+    ts = None if timestamps is None else np.ascontiguousarray(timestamps, np.float32)
+    o_rgb = None if rgb is None else np.empty((n, 4), np.float32)
+    o_it = None if intensity is None else np.empty(n, np.float32)
+    o_ts = None if timestamps is None else np.empty(n, np.float32)
+    m = lib().orc_polar_downsample_attrs(_f(p), C.c_size_t(n), C.c_float(dist_size), C.c_float(elev_size),
+                                         C.c_float(azim_size), C.c_int(coord_system), C.c_size_t(min_voxel_count),
                                          _f(rgb_a), _f(it), _f(ts), _f(out), _f(o_rgb), _f(o_it), _f(o_ts))
     cut = lambda a: None if a is None else a[:m].copy()
     return out[:m].copy(), cut(o_rgb), cut(o_it), cut(o_ts)

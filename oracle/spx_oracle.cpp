@@ -1548,12 +1548,9 @@ size_t orc_voxel_downsample_unstable(const float* pts, size_t n, float voxel_siz
 // voxel_downsampling.hpp:64-79,220-288 — attribute handling of the cloud overload on the
 // same stable order: mean RGB, median intensity (:82-98), mean timestamp.  Any attribute
 // pointer may be NULL.  Returns the voxel count.
-size_t orc_voxel_downsample_attrs(const float* pts, size_t n, float voxel_size, size_t min_voxel_count,
-                                  const float* rgb, const float* intensity, const float* timestamps, float* out_pts,
-                                  float* out_rgb, float* out_intensity, float* out_timestamps) {
-    const float inv = 1.0f / voxel_size;
-    std::vector<uint64_t> keys(n);
-    for (size_t i = 0; i < n; ++i) keys[i] = orc_voxel_key(pts + 4 * i, inv);
+static size_t aggregate_by_key(const std::vector<uint64_t>& keys, const float* pts, size_t n, size_t min_voxel_count,
+                               const float* rgb, const float* intensity, const float* timestamps, float* out_pts,
+                               float* out_rgb, float* out_intensity, float* out_timestamps) {
     std::vector<size_t> order;
     for (size_t i = 0; i < n; ++i)
         if (keys[i] != std::numeric_limits<uint64_t>::max()) order.push_back(i);
@@ -1600,6 +1597,59 @@ size_t orc_voxel_downsample_attrs(const float* pts, size_t n, float voxel_size, 
         g = e;
     }
     return m;
+}
+
+size_t orc_voxel_downsample_attrs(const float* pts, size_t n, float voxel_size, size_t min_voxel_count,
+                                  const float* rgb, const float* intensity, const float* timestamps, float* out_pts,
+                                  float* out_rgb, float* out_intensity, float* out_timestamps) {
+    const float inv = 1.0f / voxel_size;
+    std::vector<uint64_t> keys(n);
+    for (size_t i = 0; i < n; ++i) keys[i] = orc_voxel_key(pts + 4 * i, inv);
+    return aggregate_by_key(keys, pts, n, min_voxel_count, rgb, intensity, timestamps, out_pts, out_rgb, out_intensity,
+                            out_timestamps);
+}
+
+// I/algorithms/filter/polar_downsampling.hpp:30-108 (coord_system 0 LIDAR, 1 CAMERA).  atan2 correctly rounded
+// (fp64 then cast), squared sums as plain fp32 multiplies and adds.
+uint64_t orc_polar_key(const float* p, float dist_inv, float elev_inv, float azim_inv, int coord_system) {
+    constexpr uint64_t invalid = std::numeric_limits<uint64_t>::max();
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) return invalid;
+    const float xx = p[0] * p[0], yy = p[1] * p[1], zz = p[2] * p[2];
+    const float r = std::sqrt(xx + yy + zz);
+    if (r == 0.0f) return invalid;
+    float azimuth, elevation;
+    if (coord_system == 0) {
+        const float x2y2 = xx + yy;
+        if (x2y2 == 0.0f) return invalid;
+        azimuth = cr_atan2(p[1], p[0]);
+        elevation = cr_atan2(p[2], std::sqrt(x2y2));
+    } else if (coord_system == 1) {
+        const float x2z2 = xx + zz;
+        if (x2z2 == 0.0f) return invalid;
+        azimuth = cr_atan2(p[0], p[2]);
+        elevation = cr_atan2(-p[1], std::sqrt(x2z2));
+    } else {
+        return invalid;
+    }
+    const int64_t off = 1 << 20, mask = (1 << 21) - 1;
+    const float f0 = std::floor(r * dist_inv), f1 = std::floor(elevation * elev_inv), f2 = std::floor(azimuth * azim_inv);
+    if (!(std::fabs(f0) < 4e9f && std::fabs(f1) < 4e9f && std::fabs(f2) < 4e9f)) return invalid;
+    const int64_t c0 = (int64_t)f0 + off, c1 = (int64_t)f1 + off, c2 = (int64_t)f2 + off;
+    if (c0 < 0 || mask < c0 || c1 < 0 || mask < c1 || c2 < 0 || mask < c2) return invalid;
+    return ((uint64_t)(c0 & mask)) | ((uint64_t)(c1 & mask) << 21) | ((uint64_t)(c2 & mask) << 42);
+}
+
+// filter::PolarGrid::downsampling — polar_downsampling.hpp:186-198 (cloud overload), :317-338 (sort), :375-452
+// (aggregation, the same as the voxel grid's).  Stable (key, index) order like the voxel oracle.
+size_t orc_polar_downsample_attrs(const float* pts, size_t n, float dist_size, float elev_size, float azim_size,
+                                  int coord_system, size_t min_voxel_count, const float* rgb, const float* intensity,
+                                  const float* timestamps, float* out_pts, float* out_rgb, float* out_intensity,
+                                  float* out_timestamps) {
+    const float di = 1.0f / dist_size, ei = 1.0f / elev_size, ai = 1.0f / azim_size;
+    std::vector<uint64_t> keys(n);
+    for (size_t i = 0; i < n; ++i) keys[i] = orc_polar_key(pts + 4 * i, di, ei, ai, coord_system);
+    return aggregate_by_key(keys, pts, n, min_voxel_count, rgb, intensity, timestamps, out_pts, out_rgb, out_intensity,
+                            out_timestamps);
 }
 
 // I/algorithms/filter/preprocess_operator/box_filter_operator.hpp:36-44, common.hpp:15-25,

@@ -146,6 +146,8 @@ def lib() -> C.CDLL:
         "spx_voxel_downsample": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, C.POINTER(C.c_size_t)]),
         "spx_voxel_downsample_attrs": (C.c_int, [vp, f32p, sz, C.c_float, sz, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                                  C.POINTER(C.c_size_t)]),
+        "spx_polar_downsample_attrs": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, C.c_float, C.c_int, sz, f32p, f32p, f32p,
+                                                 f32p, f32p, f32p, f32p, C.POINTER(C.c_size_t)]),
         "spx_box_filter": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, f32p, C.POINTER(C.c_size_t)]),
         "spx_box_filter_indices": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, i32p, C.POINTER(C.c_size_t)]),
         "spx_linearize": (C.c_int, [vp, C.c_int, C.c_int, f32p, f32p, sz, f32p, f32p, f32p, i32p, f32p, hostf,

@@ -616,6 +616,62 @@ class VoxelGrid:
         return result
 
 
+class CoordinateSystem(enum.IntEnum):  # common/coordinate_system.hpp:13
+    LIDAR = 0
+    CAMERA = 1
+
+
+class PolarGrid:
+    """filter::PolarGrid (polar_downsampling.hpp:111-452): the grid filter with cells in (range, elevation,
+    azimuth); angles in radians."""
+
+    def __init__(self, queue: DeviceQueue, distance_voxel_size: float, elevation_voxel_size: float,
+                 azimuth_voxel_size: float, coord: CoordinateSystem = CoordinateSystem.LIDAR):
+        if distance_voxel_size <= 0.0 or elevation_voxel_size <= 0.0 or azimuth_voxel_size <= 0.0:
+            raise ValueError("voxel sizes must be positive")  # std::invalid_argument, :129-131
+        self.queue = queue
+        self.distance_voxel_size = float(distance_voxel_size)
+        self.elevation_voxel_size = float(elevation_voxel_size)
+        self.azimuth_voxel_size = float(azimuth_voxel_size)
+        self.coord = CoordinateSystem(coord)
+        self._min_voxel_count = 1
+
+    def set_min_voxel_count(self, n: int):
+        self._min_voxel_count = int(n)
+
+    def set_coordinate_system(self, coord):
+        self.coord = CoordinateSystem(coord)
+
+    def downsampling(self, cloud: PointCloudShared, result: PointCloudShared | None = None) -> PointCloudShared:
+        result = result if result is not None else PointCloudShared(self.queue)
+        n = cloud.size()
+        result.index_hint = None
+        if n == 0:
+            result.adopt_points(DeviceArray(self.queue, (0, 4), np.float32), 0)
+            result.covs = result.normals = result.rgb = result.intensities = result.timestamp_offsets = None
+            return result
+        out = DeviceArray(self.queue, (n, 4), np.float32)
+        m = C.c_size_t()
+        rgb, inten, ts = cloud.has_rgb(), cloud.has_intensity(), cloud.has_timestamps()
+        o_rgb = DeviceArray(self.queue, (n, 4), np.float32) if rgb else None
+        o_int = DeviceArray(self.queue, (n,), np.float32) if inten else None
+        o_ts = DeviceArray(self.queue, (n,), np.float32) if ts else None
+        check(_lib.lib().spx_polar_downsample_attrs(
+            self.queue.handle, cloud.points.ptr, n, self.distance_voxel_size, self.elevation_voxel_size,
+            self.azimuth_voxel_size, int(self.coord), self._min_voxel_count, cloud.rgb.ptr if rgb else None,
+            cloud.intensities.ptr if inten else None, cloud.timestamp_offsets.ptr if ts else None, out.ptr, _ptr(o_rgb),
+            _ptr(o_int), _ptr(o_ts), C.byref(m)))
+        mm = int(m.value)
+        result.adopt_points(out, mm)
+        result.index_hint = None
+        result.covs = None
+        result.normals = None
+        result.rgb = _trim(o_rgb, mm)
+        result.intensities = _trim(o_int, mm)
+        result.timestamp_offsets = _trim(o_ts, mm)
+        return result
+
+
 def _trim(a: DeviceArray | None, m: int):
     """view the first m rows of an over-allocated output array (no copy)"""
     if a is None:

@@ -34,13 +34,46 @@ struct CoordAcc {
     uint32_t pad;
 };
 
-// compute_voxel_bit's coordinate part — voxel_constants.hpp:36-53.  Returns false for the points
-// the reference maps to invalid_coord (non-finite or outside the 21-bit range).
-__device__ __forceinline__ bool voxel_coords(const float4 p, float inv, int c[3]) {
+// How a point becomes three integer grid coordinates (the key's digits, c[2] most significant):
+//   voxel grid  c = floor(p * inv) per axis (compute_voxel_bit, voxel_constants.hpp:36-53);
+//   polar grid  c = floor(range * inv[0]), floor(elevation * inv[1]), floor(azimuth * inv[2])
+//               (compute_polar_bit, filter/polar_downsampling.hpp:30-108; DISTANCE lowest, AZIMUTH highest).
+struct CoordMap {
+    float inv[3];
+    int polar;  // 0 voxel grid, 1 polar LIDAR frame, 2 polar CAMERA frame
+};
+
+// Returns false for the points the reference maps to invalid_coord (non-finite, outside the 21-bit range; for
+// the polar grid also the origin and the points on the polar axis).  atan2 is evaluated in fp64 and cast — the
+// library's rule for transcendentals — and the squared sums are plain fp32 multiplies and adds, left to right.
+template <bool POLAR>
+__device__ __forceinline__ bool voxel_coords(const float4 p, const CoordMap& cm, int c[3]) {
     if (!isfinite(p.x) || !isfinite(p.y) || !isfinite(p.z)) return false;
-    const float fx = floorf(__fmul_rn(p.x, inv));
-    const float fy = floorf(__fmul_rn(p.y, inv));
-    const float fz = floorf(__fmul_rn(p.z, inv));
+    float fx, fy, fz;
+    if constexpr (!POLAR) {
+        fx = floorf(__fmul_rn(p.x, cm.inv[0]));
+        fy = floorf(__fmul_rn(p.y, cm.inv[1]));
+        fz = floorf(__fmul_rn(p.z, cm.inv[2]));
+    } else {
+        const float xx = __fmul_rn(p.x, p.x), yy = __fmul_rn(p.y, p.y), zz = __fmul_rn(p.z, p.z);
+        const float r = sqrtf(__fadd_rn(__fadd_rn(xx, yy), zz));
+        if (r == 0.0f) return false;
+        float azimuth, elevation;
+        if (cm.polar == 1) {
+            const float x2y2 = __fadd_rn(xx, yy);
+            if (x2y2 == 0.0f) return false;
+            azimuth = (float)atan2((double)p.y, (double)p.x);
+            elevation = (float)atan2((double)p.z, (double)sqrtf(x2y2));
+        } else {
+            const float x2z2 = __fadd_rn(xx, zz);
+            if (x2z2 == 0.0f) return false;
+            azimuth = (float)atan2((double)p.x, (double)p.z);
+            elevation = (float)atan2((double)-p.y, (double)sqrtf(x2z2));
+        }
+        fx = floorf(__fmul_rn(r, cm.inv[0]));
+        fy = floorf(__fmul_rn(elevation, cm.inv[1]));
+        fz = floorf(__fmul_rn(azimuth, cm.inv[2]));
+    }
     const float lim = 1048576.0f;  // 2^20: coord + offset must land in [0, 2^21 - 1]
     if (!(fx >= -lim && fx < lim && fy >= -lim && fy < lim && fz >= -lim && fz < lim)) return false;
     c[0] = (int)fx + (1 << 20);
@@ -98,13 +131,14 @@ __device__ __forceinline__ void coord_acc_commit(int mn[3], int mx[3], uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __restrict__ pts, uint32_t n, float inv,
+template <bool POLAR>
+__global__ void __launch_bounds__(VX_THREADS) voxel_bbox_kernel(const float4* __restrict__ pts, uint32_t n, CoordMap cm,
                                                                 CoordAcc* acc) {
     int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
     uint32_t cnt = 0;
     for (uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x; i < n; i += gridDim.x * VX_THREADS) {
         int c[3];
-        if (voxel_coords(__ldg(pts + i), inv, c)) {
+        if (voxel_coords<POLAR>(__ldg(pts + i), cm, c)) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 mn[a] = min(mn[a], c[a]);
@@ -123,14 +157,14 @@ struct KeyGeom {
     unsigned long long invalid;  // key given to dropped points (sorts after every valid key)
 };
 
-template <typename KeyT>
-__global__ void __launch_bounds__(VX_THREADS) voxel_key_kernel(const float4* __restrict__ pts, uint32_t n, float inv,
+template <typename KeyT, bool POLAR>
+__global__ void __launch_bounds__(VX_THREADS) voxel_key_kernel(const float4* __restrict__ pts, uint32_t n, CoordMap cm,
                                                                KeyGeom g, KeyT* __restrict__ keys) {
     const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
     if (i >= n) return;
     int c[3];
     unsigned long long key = g.invalid;
-    if (voxel_coords(__ldg(pts + i), inv, c))
+    if (voxel_coords<POLAR>(__ldg(pts + i), cm, c))
         key = (unsigned long long)(c[2] - g.mn[2]) * g.nxy + (unsigned long long)(c[1] - g.mn[1]) * g.nx +
               (unsigned long long)(c[0] - g.mn[0]);
     keys[i] = (KeyT)key;
@@ -232,9 +266,9 @@ struct OsItems {
     static constexpr int value = sizeof(KeyT) == 4 ? 16 : 8;  // keys per thread (tile staged in 32 / 24 KB of smem)
 };
 
-template <typename KeyT>
+template <typename KeyT, bool POLAR>
 __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4* __restrict__ pts, uint32_t n,
-                                                                    float inv, KeyGeom g, KeyT* __restrict__ keys,
+                                                                    CoordMap cm, KeyGeom g, KeyT* __restrict__ keys,
                                                                     int passes, uint32_t* __restrict__ ghist,
                                                                     uint32_t* __restrict__ outside, CoordAcc* acc) {
     // acc != null (the box in `g` is a guess): this cloud's own box and valid count are accumulated here,
@@ -255,7 +289,7 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_key_hist_kernel(const float4
             if (i >= n) break;
             int c[3];
             unsigned long long key = g.invalid;
-            if (voxel_coords(pt[u], inv, c)) {
+            if (voxel_coords<POLAR>(pt[u], cm, c)) {
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     bmn[a] = min(bmn[a], c[a]);
@@ -771,7 +805,7 @@ template <typename KeyT>
 // guessed: the key geometry comes from the previous call (the bounding box of THIS cloud is still on its
 // way to the host in `hacc`): the number of valid points is read on the device, and a point outside the
 // guessed box raises total_dev[2] — the function then returns false and the caller starts over.
-bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, const KeyGeom& geom, int key_bits,
+bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, const CoordMap& cm, const KeyGeom& geom, int key_bits,
                      uint32_t n_valid, float min_count, float4* out, uint32_t* htotal, const VoxAttrIO& io, bool guessed,
                      CoordAcc* acc, CoordAcc* hacc) {
     cudaStream_t st = q->stream;
@@ -805,8 +839,13 @@ bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     uint32_t* vout = vals_a;
     if (onesweep) {
         // one kernel per digit: histograms of all passes from the key kernel, look-back instead of scans
-        voxel_key_hist_kernel<KeyT><<<std::min(div_up(n, VX_THREADS * 4), q->sm_count * 8), VX_THREADS, 0, st>>>(
-            pts, n, inv, geom, keys_a, passes, os, total_dev + 2, guessed ? acc : nullptr);
+        const int kh_grid = std::min((int)div_up(n, VX_THREADS * 4), q->sm_count * 8);
+        if (cm.polar)
+            voxel_key_hist_kernel<KeyT, true><<<kh_grid, VX_THREADS, 0, st>>>(pts, n, cm, geom, keys_a, passes, os,
+                                                                              total_dev + 2, guessed ? acc : nullptr);
+        else
+            voxel_key_hist_kernel<KeyT, false><<<kh_grid, VX_THREADS, 0, st>>>(pts, n, cm, geom, keys_a, passes, os,
+                                                                               total_dev + 2, guessed ? acc : nullptr);
         SPX_LAUNCH_CHECK();
         for (int p = 0; p < passes; ++p) {
             onesweep_kernel<KeyT><<<os_tiles, RS_THREADS, 0, st>>>(
@@ -821,7 +860,10 @@ bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
         const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
         uint32_t* ghist = q->take<uint32_t>((size_t)RADIX * nblocks + 64);
         uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems((size_t)RADIX * nblocks));
-        voxel_key_kernel<KeyT><<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, inv, geom, keys_a);
+        if (cm.polar)
+            voxel_key_kernel<KeyT, true><<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, cm, geom, keys_a);
+        else
+            voxel_key_kernel<KeyT, false><<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(pts, n, cm, geom, keys_a);
         SPX_LAUNCH_CHECK();
         for (int p = 0; p < passes; ++p) {
             const int shift = p * RADIX_BITS;
@@ -869,17 +911,13 @@ bool sort_and_reduce(spx_queue_t q, const float4* pts, uint32_t n, float inv, co
     return true;
 }
 
-}  // namespace
-
-extern "C" {
-
-int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, float voxel_size,
-                               size_t min_voxel_count, const float* rgb, const float* intensity,
-                               const float* timestamps, float* out_points, float* out_rgb, float* out_intensity,
-                               float* out_timestamps, size_t* m_host) {
-    return guard([&] {
+// The grid filters' common body.  `cm` chooses the grid (voxel or polar); voxel_size is only the tag under which the
+// voxel grid's key box is remembered between calls (0 for the polar grid, which never guesses).
+void grid_downsample(spx_queue_t q, const CoordMap& cm, float voxel_size, const float* points, size_t n_in,
+                     size_t min_voxel_count, const float* rgb, const float* intensity, const float* timestamps,
+                     float* out_points, float* out_rgb, float* out_intensity, float* out_timestamps, size_t* m_host) {
+    {
         SPX_REQUIRE(q && m_host, "[VoxelGrid::downsampling] null argument");
-        if (!(voxel_size > 0.0f)) throw Error(SPX_ERR_INVALID_ARGUMENT, "voxel_size must be positive");
         SPX_REQUIRE(n_in < (1ull << 31), "[VoxelGrid::downsampling] too many points");
         *m_host = 0;
         q->voxel_last.valid = false;
@@ -890,7 +928,6 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         DeviceGuard dg(q->device);
         cudaStream_t st = q->stream;
         const uint32_t n = (uint32_t)n_in;
-        const float inv = 1.0f / voxel_size;  // voxel_downsampling.hpp:27
         const float4* pts = reinterpret_cast<const float4*>(points);
         const uint32_t nblocks = (uint32_t)div_up(n, RS_TILE);
 
@@ -921,14 +958,17 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         // The compact key is order-preserving for any box that contains the points, so the output does
         // not depend on which box was used.
         auto& cache = q->voxel_geom;
-        bool guessed = cache.valid && cache.voxel == voxel_size && n < OS_LOCAL && !std::getenv("SPX_VOXEL_EXACT_BOX");
+        bool guessed = !cm.polar && cache.valid && cache.voxel == voxel_size && n < OS_LOCAL &&
+                       !std::getenv("SPX_VOXEL_EXACT_BOX");
         bool have_box = false;  // a failed guess leaves this cloud's own box in hacc
         for (;;) {
             CoordAcc* acc = nullptr;  // guessed: lives in sort_and_reduce's zeroed scratch, filled by the key kernel
             if (!have_box && !guessed) {
                 acc = q->take<CoordAcc>(1);
                 SPX_CUDA(cudaMemsetAsync(acc, 0, sizeof(CoordAcc), st));
-                voxel_bbox_kernel<<<std::min(div_up(n, VX_THREADS), q->sm_count * 8), VX_THREADS, 0, st>>>(pts, n, inv, acc);
+                const int bb_grid = std::min((int)div_up(n, VX_THREADS), q->sm_count * 8);
+                if (cm.polar) voxel_bbox_kernel<true><<<bb_grid, VX_THREADS, 0, st>>>(pts, n, cm, acc);
+                else voxel_bbox_kernel<false><<<bb_grid, VX_THREADS, 0, st>>>(pts, n, cm, acc);
                 SPX_LAUNCH_CHECK();
             }
             int box_mn[3], box_mx[3];
@@ -988,9 +1028,9 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
             const unsigned long long max_key = dim[0] * dim[1] * dim[2] - 1ull;  // <= 2^63 - 1
             geom.invalid = max_key + 1ull;
             const int key_bits = bits_for(has_invalid ? geom.invalid : max_key);
-            const bool ok = key_bits <= 32 ? sort_and_reduce<uint32_t>(q, pts, n, inv, geom, key_bits, n_valid, min_count, out,
+            const bool ok = key_bits <= 32 ? sort_and_reduce<uint32_t>(q, pts, n, cm, geom, key_bits, n_valid, min_count, out,
                                                                       htotal, io, guessed, acc, hacc)
-                                           : sort_and_reduce<unsigned long long>(q, pts, n, inv, geom, key_bits, n_valid,
+                                           : sort_and_reduce<unsigned long long>(q, pts, n, cm, geom, key_bits, n_valid,
                                                                                 min_count, out, htotal, io, guessed, acc,
                                                                                 hacc);
             if (guessed) coord_acc_decode(hacc);  // this cloud's own box came back with the result
@@ -1002,6 +1042,12 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         // hacc holds this cloud's box either way: it is the next call's guess — joined with the previous guess
         // when that costs no radix pass (a queue that alternates between two clouds, source and target of a
         // pair, would otherwise miss on every larger one)
+        if (cm.polar) {  // polar cells say nothing about a Cartesian box: no hint, no guess for the next call
+            cache.valid = false;
+            if (hacc->valid == 0) htotal[0] = 0;
+            *m_host = htotal[0];
+            return;
+        }
         q->voxel_last.valid = hacc->valid > 0;
         q->voxel_last.voxel = voxel_size;
         for (int a = 0; a < 3; ++a) {
@@ -1030,6 +1076,43 @@ int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, 
         }
         if (guessed && hacc->valid == 0) htotal[0] = 0;
         *m_host = htotal[0];
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int spx_voxel_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, float voxel_size,
+                               size_t min_voxel_count, const float* rgb, const float* intensity,
+                               const float* timestamps, float* out_points, float* out_rgb, float* out_intensity,
+                               float* out_timestamps, size_t* m_host) {
+    return guard([&] {
+        if (!(voxel_size > 0.0f)) throw Error(SPX_ERR_INVALID_ARGUMENT, "voxel_size must be positive");
+        CoordMap cm;
+        cm.inv[0] = cm.inv[1] = cm.inv[2] = 1.0f / voxel_size;  // voxel_downsampling.hpp:27
+        cm.polar = 0;
+        grid_downsample(q, cm, voxel_size, points, n_in, min_voxel_count, rgb, intensity, timestamps, out_points, out_rgb,
+                        out_intensity, out_timestamps, m_host);
+    });
+}
+
+int spx_polar_downsample_attrs(spx_queue_t q, const float* points, size_t n_in, float distance_voxel_size,
+                               float elevation_voxel_size, float azimuth_voxel_size, int coordinate_system,
+                               size_t min_voxel_count, const float* rgb, const float* intensity, const float* timestamps,
+                               float* out_points, float* out_rgb, float* out_intensity, float* out_timestamps,
+                               size_t* m_host) {
+    return guard([&] {
+        if (!(distance_voxel_size > 0.0f && elevation_voxel_size > 0.0f && azimuth_voxel_size > 0.0f))
+            throw Error(SPX_ERR_INVALID_ARGUMENT, "voxel sizes must be positive");  // polar_downsampling.hpp:129-131
+        SPX_REQUIRE(coordinate_system == SPX_COORD_LIDAR || coordinate_system == SPX_COORD_CAMERA,
+                    "[PolarGrid::downsampling] unknown coordinate system");
+        CoordMap cm;
+        cm.inv[0] = 1.0f / distance_voxel_size;  // :133-135
+        cm.inv[1] = 1.0f / elevation_voxel_size;
+        cm.inv[2] = 1.0f / azimuth_voxel_size;
+        cm.polar = coordinate_system == SPX_COORD_LIDAR ? 1 : 2;
+        grid_downsample(q, cm, 0.0f, points, n_in, min_voxel_count, rgb, intensity, timestamps, out_points, out_rgb,
+                        out_intensity, out_timestamps, m_host);
     });
 }
 

@@ -378,7 +378,7 @@ def test_deskew_constant_velocity_vs_oracle(spx, q, bundled):
     bad = ~np.isfinite(ts)
     assert bad.sum() > 100 and np.array_equal(out.points_host()[bad], tgt[bad])
     assert np.array_equal(out.covs_host()[bad], covs[bad])
-    late = ts >= 100.0  # tau clamps to 1: the whole motion
+    late = np.isfinite(ts) & (ts >= 100.0)  # tau clamps to 1: the whole motion
     whole = oracle.transform_points(oracle.se3_exp(twist), tgt[late])
     assert np.allclose(out.points_host()[late], whole, rtol=0, atol=1e-5)
     assert np.array_equal(out.points_host()[ts <= 0.0], tgt[ts <= 0.0])  # tau = 0: identity motion
@@ -444,3 +444,55 @@ def test_velocity_update_aligner_and_pipeline(spx, q):
     assert pipe.get_deskewed_point_cloud() is None
     pipe.align(cloud_of(5), cloud_of(3), None, None, opt)
     assert pipe.get_deskewed_point_cloud().size() == 5
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+def test_polar_grid_vs_oracle(spx, q, bundled, coord):
+    """filter::PolarGrid (polar_downsampling.hpp): same key (correctly rounded atan2 on both sides), same stable
+    order, same running fp32 sums -> bit-exact points and attributes on the raw bundled scan, both frames."""
+    import synthetic
+    boxes, cyl = synthetic.make_scene(3)
+    raw = synthetic.scan(synthetic.ground_truth_pose(), 64, 2048, boxes, cyl, noise_seed=5)[:120000].copy()
+    raw[::1000, :3] = 0.0          # the origin: dropped
+    raw[1::1000, :2] = 0.0         # on the LIDAR polar axis
+    raw[2::1000, 0] = np.nan
+    rng = np.random.default_rng(8)
+    n = len(raw)
+    rgb = rng.uniform(0, 1, (n, 4)).astype(np.float32)
+    inten = rng.uniform(0, 255, n).astype(np.float32)
+    ts = rng.uniform(0, 100, n).astype(np.float32)
+    cloud = spx.PointCloudShared(q, raw)
+    cloud.set_rgb(rgb)
+    cloud.set_intensities(inten)
+    cloud.set_timestamp_offsets(ts)
+    for sizes, minc in (((0.5, 0.02, 0.02), 1), ((2.0, 0.05, 0.1), 3)):
+        grid = spx.PolarGrid(q, *sizes, coord)
+        grid.set_min_voxel_count(minc)
+        out = grid.downsampling(cloud)
+        o_p, o_rgb, o_it, o_ts = oracle.polar_downsample_attrs(raw, *sizes, coord, minc, rgb, inten, ts)
+        assert out.size() == len(o_p) and 0 < len(o_p) < n
+        assert np.array_equal(out.points_host(), o_p)
+        assert np.array_equal(out.rgb.download(), o_rgb)
+        assert np.array_equal(out.intensities.download(), o_it)
+        assert np.array_equal(out.timestamp_offsets.download(), o_ts)
+    bare = spx.PolarGrid(q, 0.5, 0.02, 0.02, coord).downsampling(spx.PointCloudShared(q, raw))
+    assert np.array_equal(bare.points_host(), oracle.polar_downsample_attrs(raw, 0.5, 0.02, 0.02, coord, 1)[0])
+    # a voxel grid call afterwards still finds its own (not the polar) key box
+    v = spx.VoxelGrid(q, 0.25).downsampling(spx.PointCloudShared(q, raw))
+    assert np.array_equal(v.points_host(), oracle.voxel_downsample(raw, 0.25))
+
+
+def test_polar_grid_reference_known_answer(spx, q):
+    # T/test_downsampling_filters.cpp:90-135
+    pts = np.array([[1.1, 0, 0, 1], [1.4, 0, 0, 1], [2.1, 0, 0, 1], [2.3, 0, 0, 1], [2.4, 0, 0, 1]], np.float32)
+    cloud = spx.PointCloudShared(q, pts)
+    cloud.set_intensities(np.array([2, 4, 6, 10, 100], np.float32))
+    grid = spx.PolarGrid(q, 1.0, 3.14159265, 3.14159265, spx.CoordinateSystem.LIDAR)
+    grid.set_min_voxel_count(2)
+    out = grid.downsampling(cloud)
+    assert out.size() == 2 and out.has_intensity()
+    got = sorted(zip(out.points_host()[:, 0].tolist(), out.intensities.download().tolist()))
+    assert abs(got[0][0] - 1.25) < 1e-5 and abs(got[0][1] - 3.0) < 1e-5
+    assert abs(got[1][0] - 2.2666667) < 1e-5 and abs(got[1][1] - 10.0) < 1e-5
+    with pytest.raises(ValueError):
+        spx.PolarGrid(q, 0.0, 1.0, 1.0)
