@@ -463,6 +463,7 @@ def workload_pair(ctx):
         if streamed:
             pipe.stream_upload(0, pins[0][0].array, pins[0][1].array)
         futs = pipe.feeders_async(0, 0, a, streamed)
+        marks = [time.perf_counter()]
         for s in range(n_steps):
             nxt = None
             if s + 1 < n_steps:
@@ -473,10 +474,18 @@ def workload_pair(ctx):
                 else:
                     nxt = pipe.feeders_async((s + 1) % N_ROTATE, (s + 1) % 2, None, False)
             pipe.align_pipelined(futs, s % 2)
+            marks.append(time.perf_counter())  # the align returned: this pair's result is on the host
             futs = nxt
         b.record(pipe.q3)
         ctx.barrier(pipe.q2, pipe.qc, pipe.q3)
+        step_hist.append(np.diff(marks) * 1e3)
         return float(a.elapsed_ms(b))
+
+    step_hist = []
+
+    def spread(ms):
+        """median / worst host-observed step of one pipelined run (the mean is the reported figure)"""
+        return {"median_ms": float(np.median(ms)), "p99_ms": float(np.percentile(ms, 99)), "max_ms": float(np.max(ms))}
 
     pipelined(4, False)
     launches1 = spx.kernel_launch_count()
@@ -491,8 +500,10 @@ def workload_pair(ctx):
     # Every step's inputs are copied from pinned host memory inside the timed region and every
     # step's result struct is read back (align synchronises); one bracket around the K steps because
     # consecutive steps overlap.
+    value_spread = spread(step_hist[-1])
     pipelined(4, True)
     e2e_ms = pipelined(args.steps, True)
+    e2e_spread = spread(step_hist[-1])
     serial_ms, = ctx.max_over_ranks(serial_ms)
     total_ms, e2e_ms = ctx.max_over_ranks(total_ms, e2e_ms)
     gpu_launches = int(ctx.sum_over_ranks(float(gpu_launches))[0])
@@ -534,6 +545,8 @@ def workload_pair(ctx):
         "ms_per_iter": kern_ms,
         "align_loop_ms": float(np.mean(loop_ms)),
         "latency_ms_per_pair": serial_ms / args.steps,
+        "step_spread": {"value": value_spread, "e2e": e2e_spread,
+                        "note": "host-observed time between consecutive results of the pipelined runs"},
         "pipeline": "value / e2e: two pairs in flight (both feeder chains of pair s+1 on two queues while the align of pair "
                     "s runs on a third), CUDA events around the K steps; latency_ms_per_pair, ms_per_iter and roofline: one "
                     "pair at a time, L2 flushed before every step, events around every step / align launch",

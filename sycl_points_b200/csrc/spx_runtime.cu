@@ -133,6 +133,30 @@ static int queue_create(int device, void* stream, bool own, spx_queue_t* out, in
         SPX_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t keep = UINT64_MAX;
         SPX_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        // ... and start the pool with a cushion (once per device): a pool that has to grow in the middle of a
+        // stream of scans — whenever a block freed on one queue is not yet reusable on another — stalls the
+        // allocating host thread for 3-30 ms per growth (measured: profiles/r2_pool_growth_stalls.txt).
+        // SPX_POOL_RESERVE_MB overrides the 2 GiB default; 0 leaves the pool to grow on demand.
+        {
+            static std::mutex mu;
+            static bool grown[64] = {};
+            std::lock_guard<std::mutex> lk(mu);
+            if (device < 64 && !grown[device]) {
+                grown[device] = true;
+                const char* e = std::getenv("SPX_POOL_RESERVE_MB");
+                const size_t mb = e ? (size_t)std::strtoull(e, nullptr, 10) : 2048;
+                size_t free_b = 0, total_b = 0;
+                if (mb && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (mb << 20) < free_b / 2) {
+                    void* cushion = nullptr;
+                    if (cudaMallocAsync(&cushion, mb << 20, q->stream) == cudaSuccess) {
+                        cudaFreeAsync(cushion, q->stream);
+                        cudaStreamSynchronize(q->stream);
+                    } else {
+                        cudaGetLastError();
+                    }
+                }
+            }
+        }
         q->arena_reserve(8 << 20);
         *out = q;
     });
