@@ -52,6 +52,7 @@ import synthetic  # noqa: E402
 VOXEL = 0.25
 K_COV = 10
 N_ROTATE = 4
+STREAM_SLOTS = 3
 TINY = bool(os.environ.get("SPX_BENCH_TINY"))  # CPU tests of the launch logic only
 WORKLOADS = {
     "pair": ("config 2: synthetic KITTI-shaped pair (16 accumulated 64-beam sweeps, ~2.0M raw pts/cloud), 0.25 m voxel "
@@ -223,12 +224,13 @@ class PairPipeline:
         # resident raw clouds: one (source, target) per rotating pair, sized for the largest
         self.n_src_raw, self.n_tgt_raw = n_src_raw, n_tgt_raw
         self.resident = []
-        # end-to-end (streaming) mode: a copy queue and two sets of raw buffers, so that the upload of
-        # scan pair s+1 overlaps the processing of pair s (what a LiDAR front end does with its frames)
+        # end-to-end (streaming) mode: a copy queue and three sets of raw buffers, so that the copy engine
+        # works two pairs ahead of the align (what a LiDAR front end does with its frames): upload of pair s+2 ||
+        # feeder chains of pair s+1 || align of pair s
         self.qc = spx.DeviceQueue(q.device)
         self.stream_raw = []
         self.stream_xyz = []
-        for _ in range(2):
+        for _ in range(STREAM_SLOTS):
             rs, rt = spx.PointCloudShared(self.qc), spx.PointCloudShared(self.qc)
             rs.adopt_points(spx.DeviceArray(self.qc, (max(n_src_raw), 4), np.float32), 0)
             rt.adopt_points(spx.DeviceArray(self.qc, (max(n_tgt_raw), 4), np.float32), 0)
@@ -462,15 +464,19 @@ def workload_pair(ctx):
             qq.wait_event(a)
         if streamed:
             pipe.stream_upload(0, pins[0][0].array, pins[0][1].array)
+            if n_steps > 1:
+                pipe.stream_upload(1, pins[1 % N_ROTATE][0].array, pins[1 % N_ROTATE][1].array)
         futs = pipe.feeders_async(0, 0, a, streamed)
         marks = [time.perf_counter()]
         for s in range(n_steps):
             nxt = None
+            if streamed and s + 2 < n_steps:
+                # buffer set (s+2) % 3 was last read by the feeders of pair s-1: they are done (their align returned)
+                pipe.stream_upload((s + 2) % STREAM_SLOTS, pins[(s + 2) % N_ROTATE][0].array,
+                                   pins[(s + 2) % N_ROTATE][1].array)
             if s + 1 < n_steps:
                 if streamed:
-                    # the buffer set of pair s+1 was last read by the feeders of pair s-1: they are done (their align ran)
-                    pipe.stream_upload((s + 1) % 2, pins[(s + 1) % N_ROTATE][0].array, pins[(s + 1) % N_ROTATE][1].array)
-                    nxt = pipe.feeders_async((s + 1) % 2, (s + 1) % 2, None, True)
+                    nxt = pipe.feeders_async((s + 1) % STREAM_SLOTS, (s + 1) % 2, None, True)
                 else:
                     nxt = pipe.feeders_async((s + 1) % N_ROTATE, (s + 1) % 2, None, False)
             pipe.align_pipelined(futs, s % 2)
@@ -553,8 +559,8 @@ def workload_pair(ctx):
         "wall_s": wall,
         "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": raw_bytes,
                 "d2h_bytes_per_step": 428 + 2 * 8 + 4 * 8,
-                "note": "streaming: the H2D of pair s+1 (copy queue, double-buffered) and its feeder chains overlap the "
-                        "align of pair s; every step copies its own raw points in as packed xyz (12 B per point, ~49 MB, "
+                "note": "streaming: the H2D of pair s+2 (copy queue, three buffer sets) and the feeder chains of pair s+1 "
+                        "overlap the align of pair s; every step copies its own raw points in as packed xyz (12 B per point, ~49 MB, "
                         "expanded to xyz1 on the device) and reads its result struct, voxel counts and index-build scalars back"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,

@@ -47,16 +47,19 @@ def main():
         for qq in (pipe.q2, pipe.qc, pipe.q3):
             qq.wait_event(base)
         t_base = time.perf_counter()
+        S = bench.STREAM_SLOTS
         if streamed:
             pipe.stream_upload(0, pins[0][0].array, pins[0][1].array)
+            pipe.stream_upload(1, pins[1 % NR][0].array, pins[1 % NR][1].array)
         futs = pipe.feeders_async(0, 0, base, streamed)
         for s in range(n_steps):
             h0 = time.perf_counter()
             nxt = None
+            if streamed and s + 2 < n_steps:
+                pipe.stream_upload((s + 2) % S, pins[(s + 2) % NR][0].array, pins[(s + 2) % NR][1].array)
             if s + 1 < n_steps:
                 if streamed:
-                    pipe.stream_upload((s + 1) % 2, pins[(s + 1) % NR][0].array, pins[(s + 1) % NR][1].array)
-                    nxt = pipe.feeders_async((s + 1) % 2, (s + 1) % 2, None, True)
+                    nxt = pipe.feeders_async((s + 1) % S, (s + 1) % 2, None, True)
                 else:
                     nxt = pipe.feeders_async((s + 1) % NR, (s + 1) % 2, None, False)
             h1 = time.perf_counter()
