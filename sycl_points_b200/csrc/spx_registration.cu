@@ -1072,6 +1072,12 @@ __global__ void __launch_bounds__(LIN_THREADS, CTAS) align_batch_kernel(const Ba
                     d->idx[i] = best.i;
                     d->dist[i] = best.d;
                     d->pos[i] = best.p;
+                    // tuning aid: {list size, list queries that end without a neighbour inside max_corr} per iteration
+                    if (a.phase && it < PH_MAX_ITERS) {
+                        unsigned long long* w = a.phase + PH_MAX_ITERS * PH_N + it * 2;
+                        if (k == 0) w[0] = n_slow;
+                        if (!(best.d <= a.max_corr * a.max_corr)) atomicAdd(w + 1, 1ull);
+                    }
                 }
             }
         }

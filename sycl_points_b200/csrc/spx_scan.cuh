@@ -183,22 +183,54 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(cons
     const size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t s = 0;
+    // a thread's 16 items are 64 contiguous bytes: four 16-byte accesses when the tile is whole and the arrays
+    // are 16-byte aligned (the index build's are), scalar otherwise
+    const bool vec = base + SCAN_ITEMS <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) {
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        const size_t j = base + i;
-        v[i] = j < n ? in[j] : 0u;
-        s += v[i];
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+            const uint4 x = __ldg(reinterpret_cast<const uint4*>(in + base) + i);
+            v[4 * i] = x.x;
+            v[4 * i + 1] = x.y;
+            v[4 * i + 2] = x.z;
+            v[4 * i + 3] = x.w;
+        }
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const size_t j = base + i;
+            v[i] = j < n ? in[j] : 0u;
+            s += v[i];
+        }
     }
     uint32_t total;
     uint32_t run = block_exclusive_scan(s, sw, &total);
     lookback_publish(status, tile, total);
     const unsigned long long off = block_lookback(status, tile, total, s_min, &s_sum);
     run += (uint32_t)off;
+    if (vec) {
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        const size_t j = base + i;
-        if (j < n) out[j] = run;
-        run += v[i];
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+            uint4 x;
+            x.x = run;
+            run += v[4 * i];
+            x.y = run;
+            run += v[4 * i + 1];
+            x.z = run;
+            run += v[4 * i + 2];
+            x.w = run;
+            run += v[4 * i + 3];
+            reinterpret_cast<uint4*>(out + base)[i] = x;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const size_t j = base + i;
+            if (j < n) out[j] = run;
+            run += v[i];
+        }
     }
     if (grand_total && (size_t)(tile + 1) * SCAN_TILE >= n && threadIdx.x == 0) *grand_total = (uint32_t)off + total;
 }

@@ -42,15 +42,10 @@ for it in range(iters):
 print("  mean                     " + "  ".join(f"{v:12.1f}" for v in d[1:].mean(0)) + f"   {d[1:].sum(1).mean():6.1f}")
 
 
-# per-warp records of the work-list (cooperative) phase of iteration 2: {ns, queries, slowest query ns, list size}
+# work-list statistics of the batched kernel: {list size, list queries that end without a neighbour inside max_corr}
 full = np.zeros(64 * 8 + 8192 * 5, np.uint64)
 spx._lib.check(spx.lib().spx_registration_phase_times(reg._h, 1, full.ctypes.data_as(C.c_void_p), -1))
-w = full[64 * 8:].reshape(-1, 5).astype(np.int64)
-w = w[w[:, 4] == 1]
-if len(w):
-    print(f"work-list phase, iteration 2: {len(w)} warps, list size {w[0, 3]} queries ({100.0 * w[0, 3] / src.size():.1f} % of the source)")
-    for col, nm, sc in ((0, "warp time us", 1e3), (1, "queries per warp", 1), (2, "slowest query us", 1e3)):
-        v = w[:, col] / sc
-        print(f"  {nm:18s} mean {v.mean():7.2f} p50 {np.percentile(v, 50):7.2f} p90 {np.percentile(v, 90):7.2f} "
-              f"p99 {np.percentile(v, 99):7.2f} max {v.max():7.2f}")
-    print(f"  mean time per query {w[:, 0].sum() / max(w[:, 1].sum(), 1) / 1e3:.2f} us")
+w = full[64 * 8:64 * 8 + 2 * iters].reshape(-1, 2).astype(np.int64)
+for it in range(iters):
+    print(f"  iter {it:2d}: work list {w[it, 0]:7d} queries ({100.0 * w[it, 0] / src.size():5.1f} % of the source), "
+          f"{w[it, 1]:7d} of them end beyond max_corr")
