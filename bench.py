@@ -207,7 +207,12 @@ class PairPipeline:
         params.robust.default_scale = 10.0
         self.reg = spx.Registration(q, params)
         self.nn_s, self.nn_t = spx.KNNResult(), spx.KNNResult()
-        self.pool = ThreadPoolExecutor(max_workers=2)
+        # ONE worker thread per queue: a queue (its scratch arena, its pinned staging block, its voxel-grid state) is
+        # single-threaded by contract (include/spx.h), and in the pipelined mode the chains of pair s+1 are submitted
+        # while those of pair s may still be running — a shared two-worker pool could hand the second chain of a
+        # queue to the idle worker while the first is still inside the library on the same queue.
+        self.pool = ThreadPoolExecutor(max_workers=1)   # drives q2 (source chains)
+        self.pool_t = ThreadPoolExecutor(max_workers=1)  # drives q (target chains) in the pipelined mode
         self.src_done = spx.Event()
         self.last = None
         # pipelined mode (two pairs in flight): the align of pair s runs on its own queue while both feeder chains
@@ -297,7 +302,7 @@ class PairPipeline:
         nn_s, nn_t = self.nn_pipe[slot]
         ds, dt_ = self.done_pipe[slot]
         return (self.pool.submit(self._chain, self.q2, self.vg2, rs, nn_s, ev, ds),
-                self.pool.submit(self._chain, self.q, self.vg, rt, nn_t, ev, dt_))
+                self.pool_t.submit(self._chain, self.q, self.vg, rt, nn_t, ev, dt_))
 
     def align_pipelined(self, futs, slot):
         """align of the pair whose feeders are `futs`, on the third queue (the feeders of the next pair may already

@@ -320,6 +320,50 @@ SPX_API int spx_rng_destroy(spx_rng_t rng);
 SPX_API int spx_random_sampling(spx_queue_t q, spx_rng_t rng, size_t n, size_t sampling_num, int32_t* idx_out, size_t* m_host);
 SPX_API int spx_gather(spx_queue_t q, const void* src, size_t elem_bytes, const int32_t* idx, size_t m, void* dst);
 
+/* ------------------------------------------------------------------ submap: mapping::VoxelHashMap
+ * I/algorithms/mapping/voxel_hash_map.hpp:22-1066 — a device hash table keyed by the voxel key of
+ * voxel_constants.hpp:36-62 (open addressing, double hashing :607-612, <= 100 probes :498, capacities from the
+ * reference's list of primes :481-482).  A slot accumulates sum xyz + count, the sum of the log-Euclidean images
+ * of the covariances rotated into the map frame (:420-476), sum rgba, sum intensity and the call number of its last
+ * update.  The accumulation order inside a call is unspecified (fp32 atomics, as in the reference): sums agree
+ * with a sequential evaluation to rounding.
+ *   create       VoxelHashMap(queue, voxel_size) :29-36; voxel_size <= 0 -> SPX_ERR_INVALID_ARGUMENT (:41-43)
+ *   set_params   set_voxel_size / set_max_staleness (100) / set_remove_old_data_cycle (10) /
+ *                set_rehash_threshold (0.7) / set_min_num_point (1) :40-80
+ *   clear        :83-112
+ *   add          add_point_cloud(cloud, sensor_pose) :117-140: rehash when voxel_num / capacity > threshold, insert the
+ *                points transformed by sensor_pose (column-major 4x4, NULL = identity; covs float[n][16], rgb
+ *                float[n][4], intensities float[n], each nullable), every remove_old_data_cycle-th call drop the
+ *                voxels not updated for more than max_staleness calls, ++call counter.  Synchronises (voxel count).
+ *   remove_old   remove_old_data() :248,794-845
+ *   info         capacity, voxel_num, call counter, which attributes the map holds
+ *   downsample   downsampling(result, center, distance) :146-188,936-1065: voxels with count >= min_num_point whose
+ *                centroid lies in [center - distance, center + distance]^3, in slot order: centroid (w = 1),
+ *                exp(mean log-covariance) as float[16], mean rgba, mean intensity; out_keys (nullable) receives the
+ *                voxel key of every row.  Outputs must hold voxel_num rows (out_capacity); attribute outputs the map
+ *                does not hold are left untouched.  *m_host = rows written.  Synchronises.
+ *   overlap_ratio compute_overlap_ratio(cloud, sensor_pose) :194-246: fraction of the points whose voxel exists with
+ *                count >= min_num_point.  Synchronises. */
+/* eigen_utils::log_spd_3x3(A, min_eigenvalue) / exp_spd_3x3(A) — I/utils/eigen_utils.hpp:646-677 — on n
+ * column-major 3x3 matrices (device or managed float[n][9]); asynchronous. */
+SPX_API int spx_spd_function(spx_queue_t q, const float* mats, size_t n, int is_log, float min_eigenvalue, float* out);
+typedef struct spx_voxelmap_s* spx_voxelmap_t;
+SPX_API int spx_voxelmap_create(spx_queue_t q, float voxel_size, spx_voxelmap_t* out);
+SPX_API int spx_voxelmap_destroy(spx_voxelmap_t m);
+SPX_API int spx_voxelmap_set_params(spx_voxelmap_t m, float voxel_size, uint32_t max_staleness,
+                                    uint32_t remove_old_data_cycle, float rehash_threshold, uint32_t min_num_point);
+SPX_API int spx_voxelmap_clear(spx_voxelmap_t m);
+SPX_API int spx_voxelmap_add(spx_voxelmap_t m, const float* points, const float* covs, const float* rgb,
+                             const float* intensities, size_t n, const float* sensor_pose16);
+SPX_API int spx_voxelmap_remove_old(spx_voxelmap_t m);
+SPX_API int spx_voxelmap_info(spx_voxelmap_t m, uint64_t* capacity, uint64_t* voxel_num, uint32_t* staleness_counter,
+                              int* has_cov, int* has_rgb, int* has_intensity);
+SPX_API int spx_voxelmap_downsample(spx_voxelmap_t m, const float* center3, float distance, float* out_points,
+                                    float* out_covs, float* out_rgb, float* out_intensities, uint64_t* out_keys,
+                                    size_t out_capacity, size_t* m_host);
+SPX_API int spx_voxelmap_overlap_ratio(spx_voxelmap_t m, const float* points, size_t n, const float* sensor_pose16,
+                                       float* ratio);
+
 /* ------------------------------------------------------------------ registration
  * Registration::compute_linearized_result / linearize — registration.hpp:312-331,513-676:
  * per source i: skip if dist[i] > max_corr_sq; factor (factor.hpp:130-278) on

@@ -2,11 +2,24 @@
 // I/algorithms/common/transform.hpp:45-188.  The device path is one libspx kernel (spx_transform).
 #pragma once
 
+#include <array>
+
 #include "sycl_points/points/point_cloud.hpp"
+#include "sycl_points/utils/eigen_utils.hpp"
 
 namespace sycl_points {
 namespace algorithms {
 namespace transform {
+
+namespace kernel {
+/// trans * cov * trans^T on the host (the reference's device helper of the same name, transform.hpp:14-22; the
+/// device side of it lives in csrc/spx_features.cu)
+inline void transform_covs(const Covariance& cov, Covariance& result, const std::array<sycl::float4, 4>& trans) {
+    const Eigen::Matrix4f T = eigen_utils::from_sycl_vec(trans);
+    const Eigen::Matrix4f r = T * (cov * T.transpose());
+    result = r;
+}
+}  // namespace kernel
 
 /// in place: points T p, covariances T C T^T, normals T n (not re-normalised, like the reference's kernel)
 inline sycl_utils::events transform_async(PointCloudShared& cloud, const TransformMatrix& trans) {

@@ -27,6 +27,53 @@
 namespace Eigen {
 
 template <typename T, int R, int C>
+struct Matrix;
+
+/// writable view of a BR x BC block of a matrix (what Eigen's non-const block<>() returns): assignable,
+/// accumulable, and convertible to the block's value
+template <typename T, int R, int C, int BR, int BC>
+struct BlockRef {
+    Matrix<T, R, C>& m;
+    int i0, j0;
+    Matrix<T, BR, BC> eval() const {
+        Matrix<T, BR, BC> r;
+        for (int i = 0; i < BR; ++i)
+            for (int j = 0; j < BC; ++j) r(i, j) = m(i0 + i, j0 + j);
+        return r;
+    }
+    operator Matrix<T, BR, BC>() const { return eval(); }
+    BlockRef& operator=(const Matrix<T, BR, BC>& b) {
+        for (int i = 0; i < BR; ++i)
+            for (int j = 0; j < BC; ++j) m(i0 + i, j0 + j) = b(i, j);
+        return *this;
+    }
+    BlockRef& operator=(const BlockRef& o) { return *this = o.eval(); }
+    BlockRef& operator+=(const Matrix<T, BR, BC>& b) { return *this = eval() + b; }
+    BlockRef& operator-=(const Matrix<T, BR, BC>& b) { return *this = eval() - b; }
+    BlockRef& operator*=(T s) { return *this = eval() * s; }
+    BlockRef& operator/=(T s) { return *this = eval() / s; }
+    T& operator()(int i, int j) { return m(i0 + i, j0 + j); }
+    T operator()(int i, int j) const { return m(i0 + i, j0 + j); }
+    T& operator()(int i) { return BC == 1 ? m(i0 + i, j0) : m(i0, j0 + i); }
+    T& x() { return (*this)(0); }
+    T& y() { return (*this)(1); }
+    T& z() { return (*this)(2); }
+    T norm() const { return eval().norm(); }
+    T squaredNorm() const { return eval().squaredNorm(); }
+    Matrix<T, BC, BR> transpose() const { return eval().transpose(); }
+    void setZero() { *this = Matrix<T, BR, BC>::Zero(); }
+    void setIdentity() { *this = Matrix<T, BR, BC>::Identity(); }
+    Matrix<T, BR, BC> operator+(const Matrix<T, BR, BC>& o) const { return eval() + o; }
+    Matrix<T, BR, BC> operator-(const Matrix<T, BR, BC>& o) const { return eval() - o; }
+    Matrix<T, BR, BC> operator-() const { return -eval(); }
+    Matrix<T, BR, BC> operator*(T s) const { return eval() * s; }
+    template <int K>
+    Matrix<T, BR, K> operator*(const Matrix<T, BC, K>& o) const { return eval() * o; }
+    T dot(const Matrix<T, BR, BC>& o) const { return eval().dot(o); }
+    Matrix<T, BR, BC> normalized() const { return eval().normalized(); }
+};
+
+template <typename T, int R, int C>
 struct Matrix {
     static constexpr int Rows = R, Cols = C, Size = R * C;
     alignas((sizeof(T) * R * C) % 16 == 0 ? 16 : alignof(T)) T m[R * C];
@@ -166,6 +213,26 @@ struct Matrix {
         return r;
     }
     template <int BR, int BC>
+    BlockRef<T, R, C, BR, BC> block(int i0, int j0) {
+        return BlockRef<T, R, C, BR, BC>{*this, i0, j0};
+    }
+    Matrix<T, 1, C> row(int i) const { return block<1, C>(i, 0); }
+    Matrix<T, R, 1> col(int j) const { return block<R, 1>(0, j); }
+    BlockRef<T, R, C, 1, C> row(int i) { return BlockRef<T, R, C, 1, C>{*this, i, 0}; }
+    BlockRef<T, R, C, R, 1> col(int j) { return BlockRef<T, R, C, R, 1>{*this, 0, j}; }
+    static Matrix Unit(int k) {
+        Matrix r = Zero();
+        r.m[k] = T(1);
+        return r;
+    }
+    static Matrix UnitX() { return Unit(0); }
+    static Matrix UnitY() { return Unit(1); }
+    static Matrix UnitZ() { return Unit(2); }
+    Matrix cross(const Matrix& o) const {
+        static_assert(Size == 3, "cross product of 3-vectors");
+        return Matrix(m[1] * o.m[2] - m[2] * o.m[1], m[2] * o.m[0] - m[0] * o.m[2], m[0] * o.m[1] - m[1] * o.m[0]);
+    }
+    template <int BR, int BC>
     void set_block(int i0, int j0, const Matrix<T, BR, BC>& b) {
         for (int i = 0; i < BR; ++i)
             for (int j = 0; j < BC; ++j) (*this)(i0 + i, j0 + j) = b(i, j);
@@ -220,8 +287,10 @@ struct Isometry3f {
     Matrix4f& matrix() { return M; }
     const Matrix4f& matrix() const { return M; }
     Matrix3f linear() const { return M.block<3, 3>(0, 0); }
+    BlockRef<float, 4, 4, 3, 3> linear() { return M.block<3, 3>(0, 0); }
     Matrix3f rotation() const { return linear(); }
     Vector3f translation() const { return Vector3f(M(0, 3), M(1, 3), M(2, 3)); }
+    BlockRef<float, 4, 4, 3, 1> translation() { return M.block<3, 1>(0, 3); }
     void set_translation(const Vector3f& t) {
         for (int i = 0; i < 3; ++i) M(i, 3) = t(i);
     }
@@ -237,6 +306,25 @@ struct Isometry3f {
     }
     const float* data() const { return M.data(); }
     float* data() { return M.data(); }
+};
+
+/// Eigen::AngleAxisf: rotation by `angle` about the unit vector `axis` (Rodrigues)
+struct AngleAxisf {
+    float a;
+    Vector3f ax;
+    AngleAxisf(float angle, const Vector3f& axis) : a(angle), ax(axis) {}
+    float angle() const { return a; }
+    const Vector3f& axis() const { return ax; }
+    Matrix3f toRotationMatrix() const {
+        const float c = std::cos(a), s = std::sin(a), t = 1.0f - c;
+        const float x = ax.x(), y = ax.y(), z = ax.z();
+        Matrix3f R;
+        R(0, 0) = t * x * x + c;     R(0, 1) = t * x * y - s * z; R(0, 2) = t * x * z + s * y;
+        R(1, 0) = t * x * y + s * z; R(1, 1) = t * y * y + c;     R(1, 2) = t * y * z - s * x;
+        R(2, 0) = t * x * z - s * y; R(2, 1) = t * y * z + s * x; R(2, 2) = t * z * z + c;
+        return R;
+    }
+    Matrix3f matrix() const { return toRotationMatrix(); }
 };
 
 /// Eigen::Translation3f: only as the left factor of an isometry product

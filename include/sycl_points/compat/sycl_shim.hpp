@@ -41,6 +41,25 @@ public:
     explicit exception(const std::string& what) : std::runtime_error(what) {}
 };
 
+/// sycl::vec<float, 4> as the reference's host helpers use it (to_sycl_vec / from_sycl_vec): four lanes with accessors
+template <typename T, int N>
+struct vec {
+    T v[N] = {};
+    vec() = default;
+    vec(T a, T b, T c, T d) : v{a, b, c, d} { static_assert(N == 4, "four-lane constructor"); }
+    T& x() { return v[0]; }
+    T& y() { return v[1]; }
+    T& z() { return v[2]; }
+    T& w() { return v[3]; }
+    const T& x() const { return v[0]; }
+    const T& y() const { return v[1]; }
+    const T& z() const { return v[2]; }
+    const T& w() const { return v[3]; }
+    T& operator[](int i) { return v[i]; }
+    const T& operator[](int i) const { return v[i]; }
+};
+using float4 = vec<float, 4>;
+
 namespace info {
 namespace device {
 struct name {};

@@ -105,6 +105,10 @@ def lib() -> C.CDLL:
         L.orc_voxel_downsample_attrs.restype = C.c_size_t
         L.orc_box_filter.restype = C.c_size_t
         L.orc_voxel_key.restype = C.c_uint64
+        L.orc_voxelmap_create.restype = C.c_void_p
+        L.orc_voxelmap_create.argtypes = [C.c_float]
+        L.orc_voxelmap_downsample.restype = C.c_size_t
+        L.orc_voxelmap_overlap_ratio.restype = C.c_float
         L.orc_robust_weight.restype = C.c_float
         L.orc_robust_error.restype = C.c_float
         L.orc_robust_weight.argtypes = [C.c_int, C.c_float, C.c_float]
@@ -454,6 +458,76 @@ def voxel_downsample(points, voxel_size: float, min_voxel_count: int = 1, unstab
     fn = lib().orc_voxel_downsample_unstable if unstable else lib().orc_voxel_downsample
     m = fn(_f(p), C.c_size_t(len(p)), C.c_float(voxel_size), C.c_size_t(min_voxel_count), _f(out))
     return out[:m].copy()
+
+
+class VoxelHashMap:
+    """mapping::VoxelHashMap restated sequentially (voxel_hash_map.hpp:22-1066): points inserted in index order."""
+
+    def __init__(self, voxel_size: float):
+        if voxel_size <= 0:
+            raise ValueError("voxel_size must be positive.")
+        self.h = C.c_void_p(lib().orc_voxelmap_create(C.c_float(voxel_size)))
+        self.voxel_size, self.max_staleness, self.remove_old_data_cycle = voxel_size, 100, 10
+        self.rehash_threshold, self.min_num_point = 0.7, 1
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_voxelmap_destroy(self.h)
+            self.h = None
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            assert hasattr(self, k), k
+            setattr(self, k, v)
+        lib().orc_voxelmap_set_params(self.h, C.c_float(self.voxel_size), C.c_uint32(self.max_staleness),
+                                      C.c_uint32(self.remove_old_data_cycle), C.c_float(self.rehash_threshold),
+                                      C.c_uint32(self.min_num_point))
+
+    def add_point_cloud(self, points, sensor_pose=None, covs=None, rgb=None, intensities=None):
+        p = _pts(points) if len(points) else np.zeros((0, 4), np.float32)
+        T = _T(np.eye(4) if sensor_pose is None else sensor_pose)
+        cv = None if covs is None else np.ascontiguousarray(covs, np.float32).reshape(len(p), 16)
+        cl = None if rgb is None else _pts(rgb)
+        it = None if intensities is None else np.ascontiguousarray(intensities, np.float32)
+        lib().orc_voxelmap_add(self.h, _f(p), _f(cv), _f(cl), _f(it), C.c_size_t(len(p)), _f(T))
+
+    def remove_old_data(self):
+        lib().orc_voxelmap_remove_old(self.h)
+
+    def info(self):
+        cap, vn, st = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        fl = (C.c_int * 3)()
+        lib().orc_voxelmap_info(self.h, C.byref(cap), C.byref(vn), C.byref(st), fl)
+        return {"capacity": cap.value, "voxel_num": vn.value, "staleness_counter": st.value, "has_cov": bool(fl[0]),
+                "has_rgb": bool(fl[1]), "has_intensity": bool(fl[2])}
+
+    def downsampling(self, center=(0, 0, 0), distance=100.0):
+        """-> dict(points, covs | None, rgb | None, intensities | None, keys), rows in slot order"""
+        inf = self.info()
+        n = inf["voxel_num"]
+        pts = np.zeros((n, 4), np.float32)
+        cv = np.zeros((n, 16), np.float32) if inf["has_cov"] else None
+        cl = np.zeros((n, 4), np.float32) if inf["has_rgb"] else None
+        it = np.zeros(n, np.float32) if inf["has_intensity"] else None
+        keys = np.zeros(n, np.uint64)
+        c = np.asarray(center, np.float32)
+        m = lib().orc_voxelmap_downsample(self.h, _f(c), C.c_float(distance), _f(pts), _f(cv), _f(cl), _f(it),
+                                          keys.ctypes.data_as(C.c_void_p)) if n else 0
+        cut = lambda a: None if a is None else a[:m].copy()
+        return {"points": pts[:m].copy(), "covs": cut(cv), "rgb": cut(cl), "intensities": cut(it), "keys": keys[:m].copy()}
+
+    def compute_overlap_ratio(self, points, sensor_pose=None) -> float:
+        p = _pts(points) if len(points) else np.zeros((0, 4), np.float32)
+        T = _T(np.eye(4) if sensor_pose is None else sensor_pose)
+        return float(lib().orc_voxelmap_overlap_ratio(self.h, _f(p), C.c_size_t(len(p)), _f(T)))
+
+
+def spd_function(A, is_log: bool) -> np.ndarray:
+    """log_spd_3x3 / exp_spd_3x3 (eigen_utils.hpp:646-677)"""
+    a = np.ascontiguousarray(A, np.float32).reshape(9)
+    out = np.empty(9, np.float32)
+    lib().orc_spd_function(_f(a), C.c_int(int(is_log)), _f(out))
+    return out.reshape(3, 3)
 
 
 def voxel_downsample_attrs(points, voxel_size, min_voxel_count, rgb=None, intensity=None, timestamps=None):

@@ -30,6 +30,7 @@ inline float cr_acos(float x) { return (float)std::acos((double)x); }
 inline float cr_atan2(float y, float x) { return (float)std::atan2((double)y, (double)x); }
 inline float cr_cbrt(float x) { return (float)std::cbrt((double)x); }
 inline float cr_log(float x) { return (float)std::log((double)x); }
+inline float cr_exp(float x) { return (float)std::exp((double)x); }
 inline float cr_cube(float x) { const double d = (double)x; return (float)(d * d * d); }
 
 template <int M, int N>

@@ -381,6 +381,16 @@ inline void update_covariance_plane(M4& cov) {
         for (int j = 0; j < 3; ++j) cov(i, j) = r(i, j);
 }
 
+// I/utils/eigen_utils.hpp:646-677  log / exp of a symmetric 3x3 through its eigen-decomposition
+inline M3 spd_function(const M3& A, bool is_log) {
+    V3 ev;
+    M3 evec;
+    eigen3(A, ev, evec);
+    M3 D = M3::zero();
+    for (int i = 0; i < 3; ++i) D(i, i) = is_log ? cr_log(std::fmax(ev(i), 1e-6f)) : cr_exp(ev(i));
+    return ensure_symmetric<3>(mul<3, 3, 3>(mul<3, 3, 3>(evec, D), transpose(evec)));
+}
+
 // ------------------------------------------------------------------ robust kernels
 enum Loss { L_NONE = 0, L_HUBER, L_TUKEY, L_CAUCHY, L_GM };
 enum Reg { R_P2P = 0, R_P2PLANE = 1, R_P2D = 2, R_GICP = 3, R_GENZ = 4 };
@@ -1481,6 +1491,98 @@ uint64_t orc_voxel_key(const float* p, float inv) {
     return ((uint64_t)(c0 & mask)) | ((uint64_t)(c1 & mask) << 21) | ((uint64_t)(c2 & mask) << 42);
 }
 
+// ------------------------------------------------------------------ mapping::VoxelHashMap
+// I/algorithms/mapping/voxel_hash_map.hpp:22-1066, restated SEQUENTIALLY: points are inserted in index order (the
+// reference's atomics leave the accumulation order and the winner of a slot race unspecified), every slot
+// accumulates in fp32 in that order.  Same table: double hashing :607-612, 100 probes :498, capacities :481-482.
+struct OrcVoxelMap {
+    static constexpr uint64_t INVALID = std::numeric_limits<uint64_t>::max();
+    float voxel = 0, inv = 0;
+    size_t cap = 30029;
+    std::vector<uint64_t> key;
+    std::vector<float> core;  // sx sy sz
+    std::vector<uint32_t> count;
+    std::vector<float> cov;   // xx xy xz yy yz zz
+    std::vector<float> color, intensity;
+    std::vector<uint32_t> last;
+    uint32_t staleness = 0, max_staleness = 100, cycle = 10, min_num_point = 1;
+    float rehash_threshold = 0.7f;
+    size_t voxel_num = 0;
+    bool has_cov = false, has_rgb = false, has_int = false;
+
+    void alloc(size_t c) {
+        cap = c;
+        key.assign(c, INVALID);
+        core.assign(3 * c, 0.f);
+        count.assign(c, 0u);
+        cov.assign(6 * c, 0.f);
+        color.assign(4 * c, 0.f);
+        intensity.assign(c, 0.f);
+        last.assign(c, 0u);
+    }
+    size_t slot_of(uint64_t k, size_t probe) const {  // :607-612
+        const uint64_t h2 = (cap - 2) - (k % (cap - 2));
+        return (size_t)((k + probe * h2) % cap);
+    }
+    // global_reduction :574-605
+    void insert(uint64_t k, const float* c3, uint32_t n, const float* cv6, const float* rgba, float inten, uint32_t stamp,
+                bool hc, bool hr, bool hi) {
+        if (k == INVALID) return;
+        for (size_t j = 0; j < 100; ++j) {
+            const size_t s = slot_of(k, j);
+            if (key[s] == INVALID) {
+                key[s] = k;
+                ++voxel_num;
+            }
+            if (key[s] == k) {
+                for (int a = 0; a < 3; ++a) core[3 * s + a] += c3[a];
+                count[s] += n;
+                if (hc) for (int a = 0; a < 6; ++a) cov[6 * s + a] += cv6[a];
+                if (hr) for (int a = 0; a < 4; ++a) color[4 * s + a] += rgba[a];
+                if (hi) intensity[s] += inten;
+                last[s] = stamp;
+                return;
+            }
+        }
+    }
+    void remove_old() {  // :794-845
+        if (staleness <= max_staleness) return;
+        const uint32_t rs = staleness - max_staleness;
+        size_t kept = 0;
+        for (size_t i = 0; i < cap; ++i) {
+            if (key[i] == INVALID) continue;
+            if (last[i] >= rs) {
+                ++kept;
+                continue;
+            }
+            key[i] = INVALID;
+            for (int a = 0; a < 3; ++a) core[3 * i + a] = 0;
+            count[i] = 0;
+            for (int a = 0; a < 6; ++a) cov[6 * i + a] = 0;
+            for (int a = 0; a < 4; ++a) color[4 * i + a] = 0;
+            intensity[i] = 0;
+            last[i] = 0;
+        }
+        set_voxel_num(kept);
+    }
+    void set_voxel_num(size_t v) {  // :510-517
+        voxel_num = v;
+        if (v == 0) has_cov = has_rgb = has_int = false;
+    }
+    void rehash(size_t nc) {  // :847-934
+        if (cap >= nc) return;
+        OrcVoxelMap old = *this;
+        alloc(nc);
+        voxel_num = 0;
+        for (size_t i = 0; i < old.cap; ++i) {
+            if (old.key[i] == INVALID) continue;
+            insert(old.key[i], &old.core[3 * i], old.count[i], &old.cov[6 * i], &old.color[4 * i], old.intensity[i],
+                   old.last[i], has_cov, has_rgb, has_int);
+        }
+        set_voxel_num(voxel_num);
+    }
+};
+
 // I/algorithms/filter/voxel_downsampling.hpp:50-62,146-218.  Oracle contract for the order
 // the reference leaves to std::sort: stable (key, original index); fp32 running Vector4f
 // sum in that order, then sum / sum.w.  out must hold n points; returns the voxel count.
@@ -1611,6 +1713,153 @@ size_t orc_voxel_downsample_attrs(const float* pts, size_t n, float voxel_size, 
 
 // I/algorithms/filter/polar_downsampling.hpp:30-108 (coord_system 0 LIDAR, 1 CAMERA).  atan2 correctly rounded
 // (fp64 then cast), squared sums as plain fp32 multiplies and adds.
+void* orc_voxelmap_create(float voxel_size) {
+    auto* m = new OrcVoxelMap;
+    m->voxel = voxel_size;
+    m->inv = 1.0f / voxel_size;
+    m->alloc(30029);
+    return m;
+}
+void orc_voxelmap_destroy(void* h) { delete static_cast<OrcVoxelMap*>(h); }
+void orc_voxelmap_set_params(void* h, float voxel_size, uint32_t max_staleness, uint32_t cycle, float rehash_threshold,
+                             uint32_t min_num_point) {
+    auto* m = static_cast<OrcVoxelMap*>(h);
+    m->voxel = voxel_size;
+    m->inv = 1.0f / voxel_size;
+    m->max_staleness = max_staleness;
+    m->cycle = cycle;
+    m->rehash_threshold = rehash_threshold;
+    m->min_num_point = min_num_point;
+}
+// add_point_cloud :117-140, add_point_cloud_impl :614-792 (load_entry :661-704)
+void orc_voxelmap_add(void* h, const float* pts, const float* covs, const float* rgb, const float* intens, size_t n,
+                      const float* T16) {
+    static const size_t caps[11] = {30029, 60013, 120011, 240007, 480013, 960017, 1920001, 3840007, 7680017, 15360013, 30720007};
+    auto* m = static_cast<OrcVoxelMap*>(h);
+    if (m->rehash_threshold < (float)m->voxel_num / (float)m->cap) {
+        size_t next = m->cap;
+        for (size_t c : caps)
+            if (c > m->cap) {
+                next = c;
+                break;
+            }
+        if (next > m->cap) m->rehash(next);
+    }
+    if (n > 0) {
+        m->has_cov |= covs != nullptr;
+        m->has_rgb |= rgb != nullptr;
+        m->has_int |= intens != nullptr;
+        const M4 T = load_T(T16);
+        for (size_t i = 0; i < n; ++i) {
+            const V4 w = transform_point(T, load_p(pts + 4 * i));
+            const float wp[4] = {w(0), w(1), w(2), w(3)};
+            const uint64_t k = orc_voxel_key(wp, m->inv);
+            float cv[6] = {0, 0, 0, 0, 0, 0};
+            if (covs) {  // rotate_covariance_upper_triangle :420-456, encode_covariance_for_aggregation :458-476
+                const float* c = covs + 16 * i;
+                const float cxx = c[0], cxy = c[4], cxz = c[8], cyy = c[5], cyz = c[9], czz = c[10];
+                const float r00 = T(0, 0), r01 = T(0, 1), r02 = T(0, 2), r10 = T(1, 0), r11 = T(1, 1), r12 = T(1, 2),
+                            r20 = T(2, 0), r21 = T(2, 1), r22 = T(2, 2);
+                const float a00 = std::fma(r02, cxz, std::fma(r01, cxy, r00 * cxx));
+                const float a01 = std::fma(r02, cyz, std::fma(r01, cyy, r00 * cxy));
+                const float a02 = std::fma(r02, czz, std::fma(r01, cyz, r00 * cxz));
+                const float a10 = std::fma(r12, cxz, std::fma(r11, cxy, r10 * cxx));
+                const float a11 = std::fma(r12, cyz, std::fma(r11, cyy, r10 * cxy));
+                const float a12 = std::fma(r12, czz, std::fma(r11, cyz, r10 * cxz));
+                const float a20 = std::fma(r22, cxz, std::fma(r21, cxy, r20 * cxx));
+                const float a21 = std::fma(r22, cyz, std::fma(r21, cyy, r20 * cxy));
+                const float a22 = std::fma(r22, czz, std::fma(r21, cyz, r20 * cxz));
+                M3 S;
+                S(0, 0) = std::fma(a02, r02, std::fma(a01, r01, a00 * r00));
+                S(0, 1) = S(1, 0) = std::fma(a02, r12, std::fma(a01, r11, a00 * r10));
+                S(0, 2) = S(2, 0) = std::fma(a02, r22, std::fma(a01, r21, a00 * r20));
+                S(1, 1) = std::fma(a12, r12, std::fma(a11, r11, a10 * r10));
+                S(1, 2) = S(2, 1) = std::fma(a12, r22, std::fma(a11, r21, a10 * r20));
+                S(2, 2) = std::fma(a22, r22, std::fma(a21, r21, a20 * r20));
+                const M3 L = spd_function(S, true);
+                cv[0] = L(0, 0); cv[1] = L(0, 1); cv[2] = L(0, 2); cv[3] = L(1, 1); cv[4] = L(1, 2); cv[5] = L(2, 2);
+            }
+            const float zero4[4] = {0, 0, 0, 0};
+            m->insert(k, wp, 1u, cv, rgb ? rgb + 4 * i : zero4, intens ? intens[i] : 0.f, m->staleness, covs != nullptr,
+                      rgb != nullptr, intens != nullptr);
+        }
+    }
+    if (m->cycle > 0 && (m->staleness % m->cycle) == 0) m->remove_old();
+    ++m->staleness;
+}
+void orc_voxelmap_remove_old(void* h) { static_cast<OrcVoxelMap*>(h)->remove_old(); }
+void orc_voxelmap_info(void* h, uint64_t* cap, uint64_t* voxel_num, uint32_t* staleness, int* flags3) {
+    auto* m = static_cast<OrcVoxelMap*>(h);
+    *cap = m->cap;
+    *voxel_num = m->voxel_num;
+    *staleness = m->staleness;
+    flags3[0] = m->has_cov; flags3[1] = m->has_rgb; flags3[2] = m->has_int;
+}
+// downsampling :146-188, downsampling_impl :936-1065 (slot order), compute_averaged_attributes :348-393
+size_t orc_voxelmap_downsample(void* h, const float* center3, float distance, float* out_pts, float* out_covs,
+                               float* out_rgb, float* out_int, uint64_t* out_keys) {
+    auto* m = static_cast<OrcVoxelMap*>(h);
+    if (m->voxel_num == 0) return 0;
+    const float lo[3] = {center3[0] - distance, center3[1] - distance, center3[2] - distance};
+    const float hi[3] = {center3[0] + distance, center3[1] + distance, center3[2] + distance};
+    size_t o = 0;
+    for (size_t i = 0; i < m->cap; ++i) {
+        if (m->key[i] == OrcVoxelMap::INVALID || m->count[i] < m->min_num_point || m->count[i] == 0) continue;
+        const float ic = 1.0f / (float)m->count[i];
+        const float c[3] = {m->core[3 * i] * ic, m->core[3 * i + 1] * ic, m->core[3 * i + 2] * ic};
+        if (!(c[0] >= lo[0] && c[0] <= hi[0] && c[1] >= lo[1] && c[1] <= hi[1] && c[2] >= lo[2] && c[2] <= hi[2])) continue;
+        out_pts[4 * o] = c[0]; out_pts[4 * o + 1] = c[1]; out_pts[4 * o + 2] = c[2]; out_pts[4 * o + 3] = 1.0f;
+        if (m->has_cov && out_covs) {
+            const float* v = &m->cov[6 * i];
+            M3 S;
+            S(0, 0) = v[0] * ic; S(0, 1) = S(1, 0) = v[1] * ic; S(0, 2) = S(2, 0) = v[2] * ic;
+            S(1, 1) = v[3] * ic; S(1, 2) = S(2, 1) = v[4] * ic; S(2, 2) = v[5] * ic;
+            const M3 E = spd_function(S, false);
+            float* oc = out_covs + 16 * o;
+            for (int a = 0; a < 16; ++a) oc[a] = 0.f;
+            for (int r = 0; r < 3; ++r)
+                for (int cc = 0; cc < 3; ++cc) oc[cc * 4 + r] = E(r, cc);
+        }
+        if (m->has_rgb && out_rgb)
+            for (int a = 0; a < 4; ++a) out_rgb[4 * o + a] = m->color[4 * i + a] * ic;
+        if (m->has_int && out_int) out_int[o] = m->intensity[i] * ic;
+        if (out_keys) out_keys[o] = m->key[i];
+        ++o;
+    }
+    return o;
+}
+// compute_overlap_ratio :194-246
+float orc_voxelmap_overlap_ratio(void* h, const float* pts, size_t n, const float* T16) {
+    auto* m = static_cast<OrcVoxelMap*>(h);
+    if (n == 0 || m->voxel_num == 0) return 0.0f;
+    const M4 T = load_T(T16);
+    uint32_t hits = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const V4 w = transform_point(T, load_p(pts + 4 * i));
+        const float wp[4] = {w(0), w(1), w(2), w(3)};
+        const uint64_t k = orc_voxel_key(wp, m->inv);
+        if (k == OrcVoxelMap::INVALID) continue;
+        for (size_t j = 0; j < 100; ++j) {
+            const size_t s = m->slot_of(k, j);
+            if (m->key[s] == k) {
+                if (m->count[s] >= m->min_num_point) ++hits;
+                break;
+            }
+            if (m->key[s] == OrcVoxelMap::INVALID) break;
+        }
+    }
+    return (float)hits / (float)n;
+}
+// eigen_utils.hpp:646-677 on row-major 3x3
+void orc_spd_function(const float* A9_rowmajor, int is_log, float* out9_rowmajor) {
+    M3 A;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A(i, j) = A9_rowmajor[3 * i + j];
+    const M3 R = spd_function(A, is_log != 0);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) out9_rowmajor[3 * i + j] = R(i, j);
+}
+
 uint64_t orc_polar_key(const float* p, float dist_inv, float elev_inv, float azim_inv, int coord_system) {
     constexpr uint64_t invalid = std::numeric_limits<uint64_t>::max();
     if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) return invalid;

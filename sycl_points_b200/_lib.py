@@ -149,6 +149,18 @@ def lib() -> C.CDLL:
         "spx_polar_downsample_attrs": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, C.c_float, C.c_int, sz, f32p, f32p, f32p,
                                                  f32p, f32p, f32p, f32p, C.POINTER(C.c_size_t)]),
         "spx_box_filter": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, f32p, C.POINTER(C.c_size_t)]),
+        "spx_spd_function": (C.c_int, [vp, f32p, sz, C.c_int, C.c_float, f32p]),
+        "spx_voxelmap_create": (C.c_int, [vp, C.c_float, C.POINTER(vp)]),
+        "spx_voxelmap_destroy": (C.c_int, [vp]),
+        "spx_voxelmap_set_params": (C.c_int, [vp, C.c_float, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32]),
+        "spx_voxelmap_clear": (C.c_int, [vp]),
+        "spx_voxelmap_add": (C.c_int, [vp, f32p, f32p, f32p, f32p, sz, hostf]),
+        "spx_voxelmap_remove_old": (C.c_int, [vp]),
+        "spx_voxelmap_info": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "spx_voxelmap_downsample": (C.c_int, [vp, hostf, C.c_float, f32p, f32p, f32p, f32p, vp, sz,
+                                              C.POINTER(C.c_size_t)]),
+        "spx_voxelmap_overlap_ratio": (C.c_int, [vp, f32p, sz, hostf, C.POINTER(C.c_float)]),
         "spx_box_filter_indices": (C.c_int, [vp, f32p, sz, C.c_float, C.c_float, i32p, C.POINTER(C.c_size_t)]),
         "spx_linearize": (C.c_int, [vp, C.c_int, C.c_int, f32p, f32p, sz, f32p, f32p, f32p, i32p, f32p, hostf,
                                     C.c_float, C.c_float, hostf, hostf, C.POINTER(C.c_float),

@@ -616,6 +616,134 @@ class VoxelGrid:
         return result
 
 
+class VoxelHashMap:
+    """mapping::VoxelHashMap (algorithms/mapping/voxel_hash_map.hpp:22-1066): the odometry submap — a device hash
+    table of voxels accumulating centroid, log-Euclidean mean covariance, mean colour and mean intensity."""
+
+    def __init__(self, queue: DeviceQueue, voxel_size: float):
+        if voxel_size <= 0.0:
+            raise ValueError("voxel_size must be positive.")  # std::invalid_argument, :41-43
+        self.queue = queue
+        self._voxel_size = float(voxel_size)
+        self._max_staleness, self._remove_old_data_cycle = 100, 10
+        self._rehash_threshold, self._min_num_point = 0.7, 1
+        h = C.c_void_p()
+        check(_lib.lib().spx_voxelmap_create(queue.handle, self._voxel_size, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().spx_voxelmap_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _push(self):
+        check(_lib.lib().spx_voxelmap_set_params(self._h, self._voxel_size, self._max_staleness,
+                                                 self._remove_old_data_cycle, self._rehash_threshold,
+                                                 self._min_num_point))
+
+    def set_voxel_size(self, voxel_size: float):
+        if voxel_size <= 0.0:
+            raise ValueError("voxel_size must be positive.")
+        self._voxel_size = float(voxel_size)
+        self._push()
+
+    def get_voxel_size(self) -> float:
+        return self._voxel_size
+
+    def set_max_staleness(self, v: int):
+        self._max_staleness = int(v)
+        self._push()
+
+    def get_max_staleness(self) -> int:
+        return self._max_staleness
+
+    def set_remove_old_data_cycle(self, v: int):
+        self._remove_old_data_cycle = int(v)
+        self._push()
+
+    def get_remove_old_data_cycle(self) -> int:
+        return self._remove_old_data_cycle
+
+    def set_rehash_threshold(self, v: float):
+        self._rehash_threshold = float(v)
+        self._push()
+
+    def get_rehash_threshold(self) -> float:
+        return self._rehash_threshold
+
+    def set_min_num_point(self, v: int):
+        self._min_num_point = int(v)
+        self._push()
+
+    def get_min_num_point(self) -> int:
+        return self._min_num_point
+
+    def clear(self):
+        check(_lib.lib().spx_voxelmap_clear(self._h))
+
+    def info(self) -> dict:
+        cap, vn, st = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        hc, hr, hi = C.c_int(), C.c_int(), C.c_int()
+        check(_lib.lib().spx_voxelmap_info(self._h, C.byref(cap), C.byref(vn), C.byref(st), C.byref(hc), C.byref(hr),
+                                           C.byref(hi)))
+        return {"capacity": cap.value, "voxel_num": vn.value, "staleness_counter": st.value, "has_cov": bool(hc.value),
+                "has_rgb": bool(hr.value), "has_intensity": bool(hi.value)}
+
+    def add_point_cloud(self, cloud: PointCloudShared, sensor_pose=None):
+        """:117-140 — the cloud is in the sensor frame, sensor_pose (4x4) maps it into the map frame."""
+        n = cloud.size()
+        check(_lib.lib().spx_voxelmap_add(
+            self._h, cloud.points.ptr if n else None, cloud.covs.ptr if n and cloud.has_cov() else None,
+            cloud.rgb.ptr if n and cloud.has_rgb() else None,
+            cloud.intensities.ptr if n and cloud.has_intensity() else None, n, _hostf(_T16(sensor_pose))))
+
+    def remove_old_data(self):
+        check(_lib.lib().spx_voxelmap_remove_old(self._h))
+
+    def downsampling(self, result: PointCloudShared | None = None, center=(0.0, 0.0, 0.0), distance: float = 100.0,
+                     return_keys: bool = False):
+        """:146-188 — the voxels whose centroid lies within `distance` of `center` per axis, as a point cloud (with
+        covariances / rgb / intensities when the map holds them)."""
+        result = result if result is not None else PointCloudShared(self.queue)
+        inf = self.info()
+        n = inf["voxel_num"]
+        result.covs = result.normals = result.rgb = result.intensities = result.timestamp_offsets = None
+        if n == 0:
+            result.adopt_points(DeviceArray(self.queue, (0, 4), np.float32), 0)
+            return (result, np.zeros(0, np.uint64)) if return_keys else result
+        pts = DeviceArray(self.queue, (n, 4), np.float32)
+        covs = DeviceArray(self.queue, (n, 16), np.float32) if inf["has_cov"] else None
+        rgb = DeviceArray(self.queue, (n, 4), np.float32) if inf["has_rgb"] else None
+        inten = DeviceArray(self.queue, (n,), np.float32) if inf["has_intensity"] else None
+        keys = DeviceArray(self.queue, (n,), np.uint64) if return_keys else None
+        c = np.asarray(center, np.float32).reshape(3)
+        m = C.c_size_t()
+        check(_lib.lib().spx_voxelmap_downsample(self._h, _hostf(c), float(distance), pts.ptr, _ptr(covs), _ptr(rgb),
+                                                 _ptr(inten), _ptr(keys), n, C.byref(m)))
+        mm = int(m.value)
+        result.adopt_points(pts, mm)
+        result.covs = _trim(covs, mm)
+        result.rgb = _trim(rgb, mm)
+        result.intensities = _trim(inten, mm)
+        if return_keys:
+            return result, keys.download(mm)
+        return result
+
+    def compute_overlap_ratio(self, cloud: PointCloudShared, sensor_pose=None) -> float:
+        """:194-246"""
+        n = cloud.size()
+        r = C.c_float()
+        check(_lib.lib().spx_voxelmap_overlap_ratio(self._h, cloud.points.ptr if n else None, n,
+                                                    _hostf(_T16(sensor_pose)), C.byref(r)))
+        return float(r.value)
+
+
 class CoordinateSystem(enum.IntEnum):  # common/coordinate_system.hpp:13
     LIDAR = 0
     CAMERA = 1

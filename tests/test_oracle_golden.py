@@ -274,3 +274,61 @@ def test_bundled_pair_lands_near_ground_truth(bundled):
     dT = np.linalg.inv(T_gt.astype(np.float64)) @ r["T"].astype(np.float64)
     ang = np.degrees(np.arccos(np.clip((np.trace(dT[:3, :3]) - 1) / 2, -1, 1)))
     assert np.linalg.norm(dT[:3, 3]) < 0.05 and ang < 0.3
+
+
+# ------------------------------------------------------------------ mapping::VoxelHashMap
+class _OracleMap:
+    """adapter of tests/voxelmap_cases.py over the oracle's sequential restatement"""
+
+    def __init__(self, voxel_size):
+        self.m = oracle.VoxelHashMap(voxel_size)
+
+    def set(self, **kw):
+        self.m.set_params(**kw)
+
+    def add(self, pts, pose=None, covs=None, rgb=None, intensities=None):
+        from voxelmap_cases import xyz1
+        cv = None if covs is None else np.array([np.asarray(c, np.float32).T.reshape(16) for c in covs])
+        self.m.add_point_cloud(xyz1(pts), pose, cv, None if rgb is None else np.asarray(rgb, np.float32), intensities)
+
+    def down(self, center=(0, 0, 0), distance=100.0):
+        r = self.m.downsampling(center, distance)
+        if r["covs"] is not None:
+            r["covs"] = r["covs"].reshape(-1, 4, 4).transpose(0, 2, 1)
+        return r
+
+    def overlap(self, pts, pose=None):
+        from voxelmap_cases import xyz1
+        return self.m.compute_overlap_ratio(xyz1(pts), pose)
+
+    def info(self):
+        return self.m.info()
+
+
+def _voxelmap_cases():
+    import voxelmap_cases
+    return voxelmap_cases.CASES
+
+
+@pytest.mark.parametrize("case", _voxelmap_cases(), ids=lambda c: c.__name__)
+def test_voxel_hash_map_reference_known_answers(case):
+    """T/test_voxel_hash_map.cpp:92-520, every TEST, on the oracle"""
+    case(_OracleMap)
+
+
+def test_voxel_hash_map_rejects_non_positive_voxel_size():  # T/test_voxel_hash_map.cpp:92-99
+    for v in (0.0, -0.1):
+        with pytest.raises(ValueError):
+            oracle.VoxelHashMap(v)
+
+
+def test_spd_log_exp_roundtrip_and_scipy():
+    """eigen_utils.hpp:646-677 vs scipy.linalg.logm / expm"""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        a = rng.normal(size=(3, 3))
+        A = (a @ a.T + 0.05 * np.eye(3)).astype(np.float32)
+        L = oracle.spd_function(A, True)
+        np.testing.assert_allclose(L, sl.logm(A.astype(np.float64)).real, atol=2e-4 * max(1.0, np.abs(L).max()))
+        np.testing.assert_allclose(oracle.spd_function(L, False), A, rtol=0, atol=1e-4 * np.abs(A).max())
