@@ -124,6 +124,26 @@ typedef struct spx_registration_result {
     uint32_t inlier;
 } spx_registration_result;
 
+/* Solver add-ons of Registration (both default-off; host-side 6x6 arithmetic between the device linearisation and the
+ * step, exactly where the reference applies them: registration.hpp:248-253):
+ *   DegenerateRegularizationParams (degenerate_regularization.hpp:35-40): nl-reg — for every eigen-direction of the
+ *     rotation / translation 3x3 block of H whose eigenvalue / inlier is below its threshold, H += lambda v v^T and
+ *     b += lambda v v^T Log(T_initial^-1 T), lambda = base_factor * inlier (:58-112);
+ *   MapPriorParams (map_prior.hpp:15-21): a Gaussian prior around the predicted pose whose information is the previous
+ *     frame's calibrated Hessian inflated by velocity-proportional process noise (:30-117); adds Omega to H,
+ *     Omega Log(T_pred^-1 T) to b and 1/2 e^T Omega e to the error (:119-139). */
+typedef struct spx_registration_addons {
+    int32_t degenerate_type;          /* 0 none, 1 nl_reg */
+    float rot_eigenvalue_threshold;   /* 10 */
+    float trans_eigenvalue_threshold; /* 1 */
+    float base_factor;                /* 1 */
+    int32_t map_prior_enabled;        /* 0 */
+    float rot_vel_sigma;              /* 1 */
+    float trans_vel_sigma;            /* 1 */
+    float rot_base_sigma;             /* 3.16e-2 */
+    float trans_base_sigma;           /* 1e-2 */
+} spx_registration_addons;
+
 /* ------------------------------------------------------------------ runtime (replaces sycl_utils.hpp) */
 SPX_API const char* spx_last_error(void);
 SPX_API int spx_abi_version(void);
@@ -319,6 +339,20 @@ SPX_API int spx_rng_seed(spx_rng_t rng, uint32_t seed);
 SPX_API int spx_rng_destroy(spx_rng_t rng);
 SPX_API int spx_random_sampling(spx_queue_t q, spx_rng_t rng, size_t n, size_t sampling_num, int32_t* idx_out, size_t* m_host);
 SPX_API int spx_gather(spx_queue_t q, const void* src, size_t elem_bytes, const int32_t* idx, size_t m, void* dst);
+/* PreprocessFilter::mixed_random_sampling(source, output, weights, n, weighted_ratio) —
+ * preprocess_operator/mixed_random_sampling_operator.hpp:29-107: floor(n * ratio) points by weighted reservoir keys
+ * log(u) / w (the robust ICP weights of registration.hpp:412-462), the rest uniformly from the remainder; same
+ * persistent mt19937 stream and libstdc++ distributions as the reference.  weights: device float[n].  Kept indices
+ * ascending in idx_out (device int32[min(n, sampling_num)]); apply them with spx_gather.  Synchronises. */
+SPX_API int spx_mixed_random_sampling(spx_queue_t q, spx_rng_t rng, const float* weights, size_t n, size_t sampling_num,
+                                      float weighted_ratio, int32_t* idx_out, size_t* m_host);
+/* PreprocessFilter::angle_incidence_filter(source, output, min_angle, max_angle) —
+ * preprocess_operator/angle_incidence_filter_operator.hpp:23-111: keep the points whose incidence angle (between the
+ * ray from the sensor and the surface normal; normals, or the smallest-eigenvalue direction of covs when normals is
+ * NULL) lies in [min_angle, max_angle] (0 <= min < max <= pi/2, else SPX_ERR_INVALID_ARGUMENT).  Kept indices
+ * ascending in idx_out (device int32[<= n]).  Synchronises. */
+SPX_API int spx_angle_incidence_indices(spx_queue_t q, const float* points, const float* normals, const float* covs,
+                                        size_t n, float min_angle, float max_angle, int32_t* idx_out, size_t* m_host);
 
 /* ------------------------------------------------------------------ submap: mapping::VoxelHashMap
  * I/algorithms/mapping/voxel_hash_map.hpp:22-1066 — a device hash table keyed by the voxel key of
@@ -407,6 +441,19 @@ SPX_API int spx_dogleg_step(const float* H_host, const float* g_host, float radi
 SPX_API int spx_registration_create(spx_queue_t q, const spx_registration_params* params, spx_registration_t* out);
 SPX_API int spx_registration_destroy(spx_registration_t reg);
 SPX_API int spx_registration_set_params(spx_registration_t reg, const spx_registration_params* params);
+/* Registration(queue, params) with params.degenerate_reg / params.map_prior (registration.hpp:112-113); setting them
+ * drops a stored prior (MapPrior::set_params, map_prior.hpp:25-28). */
+SPX_API void spx_default_registration_addons(spx_registration_addons* a);
+SPX_API int spx_registration_set_addons(spx_registration_t reg, const spx_registration_addons* a);
+/* Registration::set_map_prior_state(prev_result, T_pred) — registration.hpp:124-126, MapPrior::update map_prior.hpp:30-117
+ * (T_pred column-major 4x4).  *active_out (nullable): whether a prior is now in force. */
+SPX_API int spx_registration_set_map_prior_state(spx_registration_t reg, const spx_registration_result* prev_result,
+                                                 const float* T_pred16, int* active_out, float* omega36_out);
+/* DegenerateRegularization::regularize on host H (36, symmetric) / b (6) in place — degenerate_regularization.hpp:58-112;
+ * what compute_linearized_result(…, pose, initial_pose, …) applies to its raw result (registration.hpp:312-323). */
+SPX_API int spx_degenerate_regularize(const spx_registration_addons* a, float* H36, float* b6, uint32_t inlier,
+                                      const float* T_current16, const float* T_initial16);
+
 
 /* Registration::align(source, target, target_knn, initial_guess, options) — registration.hpp:201-276
  * with the target's spx_index as the KNNBase.  GN runs as a device-resident loop (nearest

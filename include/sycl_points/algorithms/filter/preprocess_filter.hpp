@@ -5,6 +5,8 @@
 // reference class (polar grid, FPS, angle incidence, intensity ...) are out of scope.
 #pragma once
 
+#include <cmath>
+
 #include <limits>
 #include <memory>
 
@@ -69,6 +71,62 @@ public:
         this->queue_.set_accessed_by_device(idx.data(), sampling_num);
         size_t m = 0;
         detail::spx_check(spx_random_sampling(this->queue_.handle(), rng_, N, sampling_num, idx.data(), &m));
+        this->gather_all(source, output, idx, m);
+    }
+
+    /// mixed_random_sampling_operator.hpp:29-107 (in place / into `output`)
+    void mixed_random_sampling(PointCloudShared& data, const shared_vector<float>& weights, size_t sampling_num,
+                               float weighted_ratio) {
+        PointCloudShared out(this->queue_);
+        this->mixed_random_sampling(data, out, weights, sampling_num, weighted_ratio);
+        data = out;
+    }
+    void mixed_random_sampling(const PointCloudShared& source, PointCloudShared& output,
+                               const shared_vector<float>& weights, size_t sampling_num, float weighted_ratio) {
+        const size_t N = source.size();
+        if (N <= sampling_num) {
+            output = source;
+            return;
+        }
+        if (weights.size() != N)
+            throw std::invalid_argument("[PreprocessFilter::mixed_random_sampling] weights size must match points");
+        if (!std::isfinite(weighted_ratio) || weighted_ratio < 0.0f || weighted_ratio > 1.0f)
+            throw std::invalid_argument("[PreprocessFilter::mixed_random_sampling] weighted_ratio must be within [0.0, 1.0]");
+        for (size_t i = 0; i < N; ++i)
+            if (!std::isfinite(weights[i]) || weights[i] < 0.0f)
+                throw std::invalid_argument(
+                    "[PreprocessFilter::mixed_random_sampling] weights must be finite and non-negative");
+        shared_vector<int32_t> idx(sampling_num);
+        this->queue_.set_accessed_by_device(idx.data(), sampling_num);
+        size_t m = 0;
+        detail::spx_check(spx_mixed_random_sampling(this->queue_.handle(), rng_, weights.data(), N, sampling_num,
+                                                    weighted_ratio, idx.data(), &m));
+        this->gather_all(source, output, idx, m);
+    }
+
+    /// angle_incidence_filter_operator.hpp:23-111
+    void angle_incidence_filter(PointCloudShared& data, float min_angle, float max_angle) {
+        this->angle_incidence_filter(data, data, min_angle, max_angle);
+    }
+    void angle_incidence_filter(const PointCloudShared& source, PointCloudShared& output, float min_angle,
+                                float max_angle) {
+        const size_t N = source.size();
+        if (N == 0) return;
+        if (!source.has_normal() && !source.has_cov())
+            throw std::runtime_error(
+                "[PreprocessFilter::angle_incidence_filter] Normal vector or covariance matrices must be "
+                "pre-computed.");
+        if (min_angle < 0.0f || max_angle > 3.14159265358979323846f * 0.5f || min_angle >= max_angle)
+            throw std::invalid_argument("[PreprocessFilter::angle_incidence_filter] Invalid angle range");
+        shared_vector<int32_t> idx(N);
+        this->queue_.set_accessed_by_device(source.points_ptr(), N);
+        this->queue_.set_accessed_by_device(idx.data(), N);
+        size_t m = 0;
+        detail::spx_check(spx_angle_incidence_indices(
+            this->queue_.handle(), reinterpret_cast<const float*>(source.points_ptr()),
+            source.has_normal() ? reinterpret_cast<const float*>(source.normals_ptr()) : nullptr,
+            source.has_normal() ? nullptr : reinterpret_cast<const float*>(source.covs_ptr()), N, min_angle, max_angle,
+            idx.data(), &m));
         this->gather_all(source, output, idx, m);
     }
 

@@ -171,11 +171,32 @@ class Rng:
         lib().orc_rng_box_points(self._g, C.c_size_t(n), _f(lo), _f(hi), _f(out))
         return out
 
+    def mixed_random_sampling_flags(self, weights, num: int, weighted_ratio: float) -> np.ndarray:
+        w = np.ascontiguousarray(weights, np.float32)
+        flags = np.empty(len(w), np.uint8)
+        lib().orc_mixed_random_sampling_flags(self._g, _f(w), C.c_size_t(len(w)), C.c_size_t(num),
+                                              C.c_float(weighted_ratio), flags.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return flags
+
     def random_sampling_flags(self, n: int, num: int) -> np.ndarray:
         flags = np.empty(n, np.uint8)
         lib().orc_random_sampling_flags(self._g, C.c_size_t(n), C.c_size_t(num),
                                         flags.ctypes.data_as(C.POINTER(C.c_uint8)))
         return flags
+
+
+def angle_incidence_flags(points, min_angle: float, max_angle: float, normals=None, covs=None) -> np.ndarray:
+    """angle_incidence_filter_operator.hpp:57-103; covs (n,16) column-major or (n,4,4) row-major"""
+    p = _pts(points)
+    nr = None if normals is None else _pts(normals)
+    cv = None
+    if covs is not None:
+        cv = np.asarray(covs, np.float32)
+        cv = np.ascontiguousarray(cv.transpose(0, 2, 1)).reshape(-1, 16) if cv.ndim == 3 else np.ascontiguousarray(cv)
+    flags = np.empty(len(p), np.uint8)
+    lib().orc_angle_incidence_flags(_f(p), _f(nr), _f(cv), C.c_size_t(len(p)), C.c_float(min_angle), C.c_float(max_angle),
+                                    flags.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return flags
 
 
 def transform_points(T, pts) -> np.ndarray:
@@ -445,6 +466,46 @@ def dogleg_step(H, g, radius: float):
     pr = C.c_float()
     lib().orc_dogleg_step(_f(H), _f(g), C.c_float(radius), _f(p), C.byref(sn), C.byref(pr))
     return p, float(sn.value), float(pr.value)
+
+
+class Addons(C.Structure):
+    """struct orc_addons: DegenerateRegularizationParams (degenerate_regularization.hpp:35-40) + MapPriorParams
+    (map_prior.hpp:15-21)"""
+    _fields_ = [("degenerate_type", C.c_int32), ("rot_thr", C.c_float), ("trans_thr", C.c_float),
+                ("base_factor", C.c_float), ("map_prior_enabled", C.c_int32), ("rot_vel_sigma", C.c_float),
+                ("trans_vel_sigma", C.c_float), ("rot_base_sigma", C.c_float), ("trans_base_sigma", C.c_float)]
+
+
+def make_addons(nl_reg=False, rot_thr=10.0, trans_thr=1.0, base_factor=1.0, map_prior=False, rot_vel_sigma=1.0,
+                trans_vel_sigma=1.0, rot_base_sigma=3.16e-2, trans_base_sigma=1e-2) -> Addons:
+    return Addons(int(nl_reg), rot_thr, trans_thr, base_factor, int(map_prior), rot_vel_sigma, trans_vel_sigma,
+                  rot_base_sigma, trans_base_sigma)
+
+
+def set_addons(a: "Addons | None" = None):
+    """process-wide add-on state of align() (also clears the stored prior)"""
+    a = a if a is not None else make_addons()
+    lib().orc_set_addons(C.byref(a))
+
+
+def degenerate_regularize(a: Addons, H, b, inlier: int, T_cur, T_init):
+    H = np.ascontiguousarray(H, np.float32).reshape(36).copy()
+    b = np.ascontiguousarray(b, np.float32).reshape(6).copy()
+    lib().orc_degenerate_regularize(C.byref(a), _f(H), _f(b), C.c_uint32(inlier), _f(_T(T_cur)), _f(_T(T_init)))
+    return H.reshape(6, 6), b
+
+
+def set_map_prior_state(prev: dict, T_pred):
+    """MapPrior::update from an align() result dict -> (active, Omega 6x6)"""
+    R = RegResult()
+    R.T[:] = list(_T(prev["T"]))
+    R.H_raw[:] = list(np.asarray(prev["H_raw"], np.float32).reshape(36))
+    R.error_raw = float(prev["error_raw"])
+    R.inlier = int(prev["inlier"])
+    om = np.zeros(36, np.float32)
+    lib().orc_set_map_prior_state.restype = C.c_int
+    act = lib().orc_set_map_prior_state(C.byref(R), _f(_T(T_pred)), _f(om))
+    return bool(act), om.reshape(6, 6)
 
 
 def voxel_key(p, inv: float) -> int:

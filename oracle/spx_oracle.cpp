@@ -21,6 +21,7 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <queue>
 #include <random>
 #include <vector>
 
@@ -1213,6 +1214,75 @@ void orc_random_sampling_flags(void* g, size_t n, size_t num, uint8_t* flags_out
     for (size_t i = 0; i < num; ++i) flags_out[ind[i]] = 1;
 }
 
+// preprocess_operator/mixed_random_sampling_operator.hpp:29-107 (weights already validated by the caller)
+void orc_mixed_random_sampling_flags(void* g, const float* weights, size_t n, size_t sampling_num, float weighted_ratio,
+                                     uint8_t* flags_out) {
+    std::mt19937& gen = *static_cast<std::mt19937*>(g);
+    if (n <= sampling_num) {
+        std::fill(flags_out, flags_out + n, (uint8_t)1);
+        return;
+    }
+    const size_t weighted_target = static_cast<size_t>(std::floor(static_cast<double>(sampling_num) * weighted_ratio));
+    std::fill(flags_out, flags_out + n, (uint8_t)0);
+    using KI = std::pair<float, size_t>;
+    std::priority_queue<KI, std::vector<KI>, std::greater<KI>> selected;
+    std::uniform_real_distribution<float> wd(std::numeric_limits<float>::min(), 1.0f);
+    for (size_t i = 0; i < n; ++i) {
+        const float w = weights[i];
+        if (w <= 0.0f || weighted_target == 0) continue;
+        const float key = std::log(wd(gen)) / w;
+        if (selected.size() < weighted_target) {
+            selected.emplace(key, i);
+            continue;
+        }
+        if (!selected.empty() && selected.top().first < key) {
+            selected.pop();
+            selected.emplace(key, i);
+        }
+    }
+    while (!selected.empty()) {
+        flags_out[selected.top().second] = 1;
+        selected.pop();
+    }
+    std::vector<size_t> rest;
+    size_t cnt = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (flags_out[i]) ++cnt;
+        else rest.push_back(i);
+    }
+    const size_t ut = std::min(sampling_num - cnt, rest.size());
+    for (size_t i = 0; i < ut; ++i) {
+        std::uniform_int_distribution<size_t> d(i, rest.size() - 1);
+        const size_t j = d(gen);
+        std::swap(rest[i], rest[j]);
+        flags_out[rest[i]] = 1;
+    }
+}
+
+// preprocess_operator/angle_incidence_filter_operator.hpp:57-103 (normals, or extract_normal of covs when normals == NULL)
+void orc_angle_incidence_flags(const float* pts, const float* normals, const float* covs, size_t n, float min_angle,
+                               float max_angle, uint8_t* flags_out) {
+    const float max_cos = std::cos(min_angle), min_cos = std::cos(max_angle);
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = pts + 4 * i;
+        flags_out[i] = 0;
+        if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && std::isfinite(p[3]))) continue;
+        V3 nr, pv;
+        if (normals) {
+            for (int a = 0; a < 3; ++a) nr(a) = normals[4 * i + a];
+        } else {
+            const V4 e = extract_normal(p, load_cov(covs + 16 * i));
+            for (int a = 0; a < 3; ++a) nr(a) = e(a);
+        }
+        for (int a = 0; a < 3; ++a) pv(a) = p[a];
+        const float d = dot<3>(pv, nr);
+        const float denom = std::sqrt(dot<3>(pv, pv)) * std::sqrt(dot<3>(nr, nr));
+        if (denom <= 1e-6f) continue;
+        const float ac = std::fabs(d / denom);
+        flags_out[i] = !(ac < min_cos || ac > max_cos);
+    }
+}
+
 void orc_transform_points(const float* T16, const float* pts, size_t n, float* out) {
     const M4 T = load_T(T16);
     for (size_t i = 0; i < n; ++i) {
@@ -1946,11 +2016,99 @@ void orc_default_params(orc_reg_params* p) {
 // :897-964 (dog-leg), :407-410 (convergence).  `tree` is an orc_kdtree built on tgt_pts
 // (ignored for knn_mode 2).  robust_scale <= 0 selects params->robust_default_scale (:217-218).
 // trace_T (nullable): max_iterations*16 floats receiving the pose after every outer iteration.
+// ------------------------------------------------------------------ solver add-ons (default off)
+// DegenerateRegularizationParams degenerate_regularization.hpp:35-40, MapPriorParams map_prior.hpp:15-21
+struct orc_addons {
+    int32_t degenerate_type;  // 0 none, 1 nl_reg
+    float rot_thr, trans_thr, base_factor;
+    int32_t map_prior_enabled;
+    float rot_vel_sigma, trans_vel_sigma, rot_base_sigma, trans_base_sigma;
+};
+static orc_addons g_addons = {0, 10.0f, 1.0f, 1.0f, 0, 1.0f, 1.0f, 3.16e-2f, 1e-2f};
+static bool g_prior_active = false;
+static double g_prior_omega[6][6];
+static M4 g_prior_T_pred_inv;
+
+// symmetric 3x3 eigen-decomposition in fp64 (stands in for Eigen::SelfAdjointEigenSolver<Matrix3f>: third-party,
+// unpinned — SURVEY.md §8(c)); cyclic Jacobi, eigenvectors in the columns of V
+static void orc_jacobi3(const double A[3][3], double ev[3], double V[3][3]) {
+    double a[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            a[i][j] = 0.5 * (A[i][j] + A[j][i]);
+            V[i][j] = i == j;
+        }
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        if (a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2] < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                const double th = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) { const double x = a[k][p], y = a[k][q]; a[k][p] = c * x - sn * y; a[k][q] = sn * x + c * y; }
+                for (int k = 0; k < 3; ++k) { const double x = a[p][k], y = a[q][k]; a[p][k] = c * x - sn * y; a[q][k] = sn * x + c * y; }
+                for (int k = 0; k < 3; ++k) { const double x = V[k][p], y = V[k][q]; V[k][p] = c * x - sn * y; V[k][q] = sn * x + c * y; }
+            }
+    }
+    for (int i = 0; i < 3; ++i) ev[i] = a[i][i];
+}
+
+static M4 isometry_inverse(const M4& T) {
+    M4 r = M4::identity();
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) r(i, j) = T(j, i);
+        r(i, 3) = -(T(0, i) * T(0, 3) + T(1, i) * T(1, 3) + T(2, i) * T(2, 3));
+    }
+    return r;
+}
+
+// degenerate_regularization.hpp:58-112 on row-major H[36], b[6]
+static void orc_nl_reg(const orc_addons& A, float* H, float* b, uint32_t inlier, const M4& T_cur, const M4& T_init) {
+    if (inlier == 0 || A.degenerate_type != 1) return;
+    const float lambda = A.base_factor * (float)inlier;
+    float Hp[36] = {};
+    for (int blk = 0; blk < 2; ++blk) {
+        const float thr = blk == 0 ? A.rot_thr : A.trans_thr;
+        if (!(thr > 0.0f)) continue;
+        double B[3][3], ev[3], V[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) B[i][j] = H[(3 * blk + i) * 6 + 3 * blk + j];
+        orc_jacobi3(B, ev, V);
+        for (int k = 0; k < 3; ++k) {
+            if (!((float)ev[k] / (float)inlier < thr)) continue;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) Hp[(3 * blk + i) * 6 + 3 * blk + j] += lambda * ((float)V[i][k] * (float)V[j][k]);
+        }
+    }
+    const V6 tw = se3_log(isometry_mul(isometry_inverse(T_init), T_cur));
+    for (int i = 0; i < 6; ++i) {
+        float acc = 0.0f;
+        for (int j = 0; j < 6; ++j) acc += Hp[i * 6 + j] * tw(j);
+        b[i] += acc;
+    }
+    for (int i = 0; i < 36; ++i) H[i] += Hp[i];
+}
+
+// map_prior.hpp:119-146
+static float orc_prior_terms(const M4& T, float* omega_e) {
+    const V6 e = se3_log(isometry_mul(g_prior_T_pred_inv, T));
+    float dotv = 0.0f;
+    for (int i = 0; i < 6; ++i) {
+        float acc = 0.0f;
+        for (int j = 0; j < 6; ++j) acc += (float)g_prior_omega[i][j] * e(j);
+        if (omega_e) omega_e[i] = acc;
+        dotv += e(i) * acc;
+    }
+    return 0.5f * dotv;
+}
+
 void orc_align(const orc_reg_params* P, const float* src_pts, const float* src_covs, size_t ns, const float* tgt_pts,
                const float* tgt_covs, const float* tgt_normals, size_t nt, void* tree, const float* T_init16,
                float robust_scale_opt, orc_reg_result* R, float* trace_T) {
     std::memset(R, 0, sizeof(*R));
     M4 T = load_T(T_init16);
+    const M4 T_initial = T;
     store_T(T, R->T);
     R->error = FMAX;
     R->error_raw = FMAX;
@@ -1979,10 +2137,18 @@ void orc_align(const orc_reg_params* P, const float* src_pts, const float* src_c
             orc_knn_bruteforce(src_pts, ns, tgt_pts, nt, 1, T16, idx.data(), dist.data());
         else
             orc_kdtree_knn(tree, src_pts, ns, 1, T16, P->knn_mode, idx.data(), dist.data());
-        const Linearized lin = linearize(P->reg_type, loss, c, idx.data(), dist.data(), T, max2, scale, P->sum_mode);
+        Linearized lin = linearize(P->reg_type, loss, c, idx.data(), dist.data(), T, max2, scale, P->sum_mode);
         std::memcpy(R->H_raw, lin.H, sizeof(lin.H));
         std::memcpy(R->b_raw, lin.b, sizeof(lin.b));
         R->error_raw = lin.error;
+        Linearized& linm = lin;
+        orc_nl_reg(g_addons, linm.H, linm.b, lin.inlier, T, T_initial);  // registration.hpp:249-250
+        if (g_prior_active) {                                            // :253
+            float oe[6];
+            linm.error += orc_prior_terms(T, oe);
+            for (int i = 0; i < 36; ++i) linm.H[i] += (float)g_prior_omega[i / 6][i % 6];
+            for (int i = 0; i < 6; ++i) linm.b[i] += oe[i];
+        }
 
         if (P->opt_method == 0) {  // Gauss-Newton
             float d[6];
@@ -2005,6 +2171,7 @@ void orc_align(const orc_reg_params* P, const float* src_pts, const float* src_c
                 float ne;
                 uint32_t inl;
                 error_sum(P->reg_type, loss, c, idx.data(), dist.data(), Tn, max2, scale, P->sum_mode, &ne, &inl);
+                if (g_prior_active) ne += orc_prior_terms(Tn, nullptr);  // registration.hpp:854
                 if (ne <= cur) {
                     R->converged = converged(d);
                     T = Tn;
@@ -2042,6 +2209,7 @@ void orc_align(const orc_reg_params* P, const float* src_pts, const float* src_c
                 float ne;
                 uint32_t inl;
                 error_sum(P->reg_type, loss, c, idx.data(), dist.data(), Tn, max2, scale, P->sum_mode, &ne, &inl);
+                if (g_prior_active) ne += orc_prior_terms(Tn, nullptr);  // registration.hpp:933
                 const float rho = (lin.error - ne) / dl.predicted_reduction;
                 if (rho < P->dl_eta1) {
                     radius = clampr(radius * P->dl_gamma_dec);
@@ -2058,6 +2226,84 @@ void orc_align(const orc_reg_params* P, const float* src_pts, const float* src_c
         if (trace_T) store_T(T, trace_T + 16 * (size_t)iter);
         if (R->converged) break;
     }
+}
+
+void orc_set_addons(const orc_addons* a) {
+    g_addons = *a;
+    g_prior_active = false;  // MapPrior::set_params, map_prior.hpp:25-28
+}
+void orc_degenerate_regularize(const orc_addons* a, float* H36, float* b6, uint32_t inlier, const float* T_cur16,
+                               const float* T_init16) {
+    orc_nl_reg(*a, H36, b6, inlier, load_T(T_cur16), load_T(T_init16));
+}
+// MapPrior::update — map_prior.hpp:30-117 (6x6 algebra in fp64; Eigen::LDLT of H + R restated as an exact solve)
+int orc_set_map_prior_state(const orc_reg_result* prev, const float* T_pred16, float* omega36_out) {
+    g_prior_active = false;
+    const orc_addons& A = g_addons;
+    if (!A.map_prior_enabled) return 0;
+    const float dof = 3.0f * (float)prev->inlier - 6.0f;
+    if (dof <= 0.0f) return 0;
+    if (!std::isfinite(prev->error_raw) || prev->error_raw < 0.0f) return 0;
+    const float s_sq = std::max(1.0f, 2.0f * prev->error_raw / dof);
+    const M4 Tp = load_T(T_pred16), To = load_T(prev->T);
+    M4 Rrel = M4::identity();
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Rrel(i, j) = To(0, i) * Tp(0, j) + To(1, i) * Tp(1, j) + To(2, i) * Tp(2, j);
+    const V6 tw = se3_log(Rrel);
+    float dt[3], dtb[3];
+    for (int i = 0; i < 3; ++i) dt[i] = Tp(i, 3) - To(i, 3);
+    for (int i = 0; i < 3; ++i) dtb[i] = Tp(0, i) * dt[0] + Tp(1, i) * dt[1] + Tp(2, i) * dt[2];
+    double q[6];
+    for (int i = 0; i < 3; ++i) {
+        q[i] = std::fabs(tw(i)) * A.rot_vel_sigma * A.rot_vel_sigma + A.rot_base_sigma * A.rot_base_sigma;
+        q[3 + i] = std::fabs(dtb[i]) * A.trans_vel_sigma * A.trans_vel_sigma + A.trans_base_sigma * A.trans_base_sigma;
+    }
+    double Ad[6][6] = {}, Hs[6][6], HA[6][6], Hc[6][6];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Ad[i][j] = Ad[3 + i][3 + j] = Rrel(i, j);
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) Hs[i][j] = (double)prev->H_raw[i * 6 + j] / s_sq;
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 6; ++k) acc += Hs[i][k] * Ad[k][j];
+            HA[i][j] = acc;
+        }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 6; ++k) acc += Ad[k][i] * HA[k][j];
+            Hc[i][j] = acc;
+        }
+    // X = (H + R)^-1 R by Gaussian elimination with partial pivoting
+    double M[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            M[i][j] = Hc[i][j] + (i == j ? 1.0 / q[i] : 0.0);
+            M[i][6 + j] = i == j ? 1.0 / q[i] : 0.0;
+        }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+        if (!(std::fabs(M[piv][c]) > 1e-300)) return 0;
+        for (int k = 0; k < 12; ++k) std::swap(M[c][k], M[piv][k]);
+        const double inv = 1.0 / M[c][c];
+        for (int k = 0; k < 12; ++k) M[c][k] *= inv;
+        for (int r = 0; r < 6; ++r)
+            if (r != c) {
+                const double f = M[r][c];
+                for (int k = 0; k < 12; ++k) M[r][k] -= f * M[c][k];
+            }
+    }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            g_prior_omega[i][j] = (double)(float)((i == j ? 1.0 / q[i] : 0.0) - (1.0 / q[i]) * M[i][6 + j]);
+            if (omega36_out) omega36_out[i * 6 + j] = (float)g_prior_omega[i][j];
+        }
+    g_prior_T_pred_inv = isometry_inverse(Tp);
+    g_prior_active = true;
+    return 1;
 }
 
 // I/algorithms/registration/pipeline/robust.hpp:84-87,106-110 — geometric robust-scale schedule

@@ -51,6 +51,14 @@ class RegistrationResultC(C.Structure):
     ]
 
 
+class RegistrationAddonsC(C.Structure):
+    """struct spx_registration_addons (include/spx.h)."""
+    _fields_ = [("degenerate_type", C.c_int32), ("rot_eigenvalue_threshold", C.c_float),
+                ("trans_eigenvalue_threshold", C.c_float), ("base_factor", C.c_float), ("map_prior_enabled", C.c_int32),
+                ("rot_vel_sigma", C.c_float), ("trans_vel_sigma", C.c_float), ("rot_base_sigma", C.c_float),
+                ("trans_base_sigma", C.c_float)]
+
+
 class AlignPairC(C.Structure):
     """struct spx_align_pair (include/spx.h)."""
     _fields_ = [
@@ -178,6 +186,11 @@ def lib() -> C.CDLL:
         "spx_registration_create": (C.c_int, [vp, C.POINTER(RegistrationParamsC), C.POINTER(vp)]),
         "spx_registration_destroy": (C.c_int, [vp]),
         "spx_registration_set_params": (C.c_int, [vp, C.POINTER(RegistrationParamsC)]),
+        "spx_default_registration_addons": (None, [C.POINTER(RegistrationAddonsC)]),
+        "spx_registration_set_addons": (C.c_int, [vp, C.POINTER(RegistrationAddonsC)]),
+        "spx_registration_set_map_prior_state": (C.c_int, [vp, C.POINTER(RegistrationResultC), hostf, C.POINTER(C.c_int),
+                                                           hostf]),
+        "spx_degenerate_regularize": (C.c_int, [C.POINTER(RegistrationAddonsC), hostf, hostf, C.c_uint32, hostf, hostf]),
         "spx_registration_align": (C.c_int, [vp, f32p, f32p, sz, f32p, f32p, f32p, sz, vp, hostf, C.c_float,
                                              C.POINTER(RegistrationResultC), hostf]),
         "spx_registration_align_batch": (C.c_int, [vp, sz, C.POINTER(AlignPairC), C.POINTER(RegistrationResultC)]),
@@ -203,6 +216,9 @@ def lib() -> C.CDLL:
         "spx_rng_destroy": (C.c_int, [vp]),
         "spx_random_sampling": (C.c_int, [vp, vp, sz, sz, i32p, C.POINTER(C.c_size_t)]),
         "spx_gather": (C.c_int, [vp, vp, sz, i32p, sz, vp]),
+        "spx_mixed_random_sampling": (C.c_int, [vp, vp, f32p, sz, sz, C.c_float, i32p, C.POINTER(C.c_size_t)]),
+        "spx_angle_incidence_indices": (C.c_int, [vp, f32p, f32p, f32p, sz, C.c_float, C.c_float, i32p,
+                                                  C.POINTER(C.c_size_t)]),
         "spx_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
         "spx_comm_destroy": (C.c_int, [vp]),
         "spx_comm_ipc_handle": (C.c_int, [vp, C.c_char_p]),

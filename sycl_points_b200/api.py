@@ -19,7 +19,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import RegistrationParamsC, RegistrationResultC, SpxError, SpxInvalidArgument, check
+from ._lib import (RegistrationAddonsC, RegistrationParamsC, RegistrationResultC, SpxError, SpxInvalidArgument,
+                   check)
 
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -878,6 +879,48 @@ class PreprocessFilter:
         self._last_indices = idx
         return self._gather_all(cloud, idx, int(m.value), output)
 
+    def mixed_random_sampling(self, cloud: PointCloudShared, weights, sampling_num: int, weighted_ratio: float,
+                              output: PointCloudShared | None = None) -> PointCloudShared:
+        """PreprocessFilter::mixed_random_sampling (mixed_random_sampling_operator.hpp:29-107): floor(num * ratio)
+        points by weighted reservoir keys (weights: DeviceArray or host array of n floats), the rest uniformly."""
+        n = cloud.size()
+        if n <= sampling_num:
+            return self.random_sampling(cloud, sampling_num, output)  # keep-all branch: copy, no draw
+        w = weights if isinstance(weights, DeviceArray) else DeviceArray.from_host(self.queue,
+                                                                                  np.ascontiguousarray(weights, np.float32))
+        if len(w) != n:
+            raise ValueError("[PreprocessFilter::mixed_random_sampling] weights size must match points")
+        idx = DeviceArray(self.queue, (sampling_num,), np.int32)
+        m = C.c_size_t()
+        try:
+            check(_lib.lib().spx_mixed_random_sampling(self.queue.handle, self._rng, w.ptr, n, sampling_num,
+                                                       float(weighted_ratio), idx.ptr, C.byref(m)))
+        except SpxInvalidArgument as e:
+            raise ValueError(str(e)) from e
+        self._last_indices = idx
+        return self._gather_all(cloud, idx, int(m.value), output)
+
+    def angle_incidence_filter(self, cloud: PointCloudShared, min_angle: float, max_angle: float,
+                               output: PointCloudShared | None = None) -> PointCloudShared:
+        """PreprocessFilter::angle_incidence_filter (angle_incidence_filter_operator.hpp:23-111)."""
+        output = output if output is not None else cloud
+        n = cloud.size()
+        if n == 0:
+            return output
+        if not cloud.has_normal() and not cloud.has_cov():
+            raise RuntimeError("[PreprocessFilter::angle_incidence_filter] Normal vector or covariance matrices must be "
+                               "pre-computed.")
+        idx = DeviceArray(self.queue, (n,), np.int32)
+        m = C.c_size_t()
+        try:
+            check(_lib.lib().spx_angle_incidence_indices(
+                self.queue.handle, cloud.points.ptr, cloud.normals.ptr if cloud.has_normal() else None,
+                None if cloud.has_normal() else cloud.covs.ptr, n, float(min_angle), float(max_angle), idx.ptr,
+                C.byref(m)))
+        except SpxInvalidArgument as e:
+            raise ValueError(str(e)) from e
+        return self._gather_all(cloud, idx, int(m.value), output)
+
     def box_filter(self, cloud: PointCloudShared, min_distance: float = 1.0, max_distance: float = FLT_MAX,
                    output: PointCloudShared | None = None) -> PointCloudShared:
         """PreprocessFilter::box_filter (box_filter_operator.hpp:19-54): keep points whose L-infinity range lies
@@ -1083,6 +1126,37 @@ class RotationConstraintParams:
     robust: RotationConstraintRobust = field(default_factory=RotationConstraintRobust)
 
 
+class DegenerateRegularizationType(enum.IntEnum):  # degenerate_regularization.hpp:14-17
+    none = 0
+    nl_reg = 1
+
+
+def DegenerateRegularizationType_from_string(s: str) -> DegenerateRegularizationType:  # :19-33
+    u = s.upper()
+    if u == "NONE":
+        return DegenerateRegularizationType.none
+    if u in ("NL-REG", "NL_REG"):
+        return DegenerateRegularizationType.nl_reg
+    raise RuntimeError(f"[DegenerateRegularizationType_from_string] Invalid DegenerateRegularizationType str [{s}]")
+
+
+@dataclass
+class DegenerateRegularizationParams:  # degenerate_regularization.hpp:35-40
+    type: DegenerateRegularizationType = DegenerateRegularizationType.none
+    rot_eigenvalue_threshold: float = 10.0
+    trans_eigenvalue_threshold: float = 1.0
+    base_factor: float = 1.0
+
+
+@dataclass
+class MapPriorParams:  # map_prior.hpp:15-21
+    enabled: bool = False
+    rot_vel_sigma: float = 1.0
+    trans_vel_sigma: float = 1.0
+    rot_base_sigma: float = 3.16e-2
+    trans_base_sigma: float = 1e-2
+
+
 @dataclass
 class RegistrationParams:
     """RegistrationParams (registration_params.hpp:41-114), same defaults."""
@@ -1098,7 +1172,15 @@ class RegistrationParams:
     criteria: Criteria = field(default_factory=Criteria)
     genz: GenZParams = field(default_factory=GenZParams)
     rotation_constraint: RotationConstraintParams = field(default_factory=RotationConstraintParams)
+    degenerate_reg: DegenerateRegularizationParams = field(default_factory=DegenerateRegularizationParams)
+    map_prior: MapPriorParams = field(default_factory=MapPriorParams)
     max_blocks: int = 0  # spx extension: cap on the align kernel's persistent grid (0 = one full wave)
+
+    def addons_c(self) -> RegistrationAddonsC:
+        d, m = self.degenerate_reg, self.map_prior
+        return RegistrationAddonsC(int(d.type), d.rot_eigenvalue_threshold, d.trans_eigenvalue_threshold, d.base_factor,
+                                   int(bool(m.enabled)), m.rot_vel_sigma, m.trans_vel_sigma, m.rot_base_sigma,
+                                   m.trans_base_sigma)
 
     def to_c(self) -> RegistrationParamsC:
         P = RegistrationParamsC()
@@ -1220,6 +1302,32 @@ class Registration:
         check(_lib.lib().spx_registration_create(queue.handle, C.byref(Pc), C.byref(h)))
         self._h = h
         self._neighbors = KNNResult()  # registration.hpp:365 (used with injected KNNs)
+        a = self.params.addons_c()
+        check(_lib.lib().spx_registration_set_addons(self._h, C.byref(a)))  # registration.hpp:112-113
+        self._addons_key = bytes(a)
+
+    def set_map_prior_state(self, prev_result: "RegistrationResult", T_pred) -> bool:
+        """Registration::set_map_prior_state (registration.hpp:124-126): arms the MAP prior of the next align from
+        the previous result and the predicted pose; returns whether a prior is now in force."""
+        self._sync_addons()
+        R = RegistrationResultC()
+        R.T[:] = list(_T16(prev_result.T))
+        R.H_raw[:] = list(np.asarray(prev_result.H_raw, np.float32).reshape(36))
+        R.error_raw = float(prev_result.error_raw)
+        R.inlier = int(prev_result.inlier)
+        act = C.c_int()
+        self._prior_omega = np.zeros(36, np.float32)
+        check(_lib.lib().spx_registration_set_map_prior_state(self._h, C.byref(R), _hostf(_T16(T_pred)), C.byref(act),
+                                                              _hostf(self._prior_omega)))
+        return bool(act.value)
+
+    def _sync_addons(self):
+        """params.degenerate_reg / params.map_prior edited after construction: pushed (and the prior dropped, as
+        MapPrior::set_params does) only when they changed"""
+        a = self.params.addons_c()
+        if bytes(a) != self._addons_key:
+            check(_lib.lib().spx_registration_set_addons(self._h, C.byref(a)))
+            self._addons_key = bytes(a)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -1294,6 +1402,7 @@ class Registration:
         if options is not None and options.rotation_robust_scale > 0.0:  # registration.hpp:219-221
             Pc.rotation_constraint_robust_scale = float(options.rotation_robust_scale)
         check(_lib.lib().spx_registration_set_params(self._h, C.byref(Pc)))
+        self._sync_addons()
         R = RegistrationResultC()
         t16 = _T16(T0)
         tr = np.zeros((max(self.params.max_iterations, 1), 16), np.float32) if trace else None
@@ -1383,10 +1492,19 @@ class Registration:
         return err.value, inl.value
 
     def compute_linearized_result(self, source, target, target_knn: KNNBase, pose,
-                                  options: ExecutionOptions | None = None) -> LinearizedResult:
-        """Registration::compute_linearized_result (registration.hpp:312-331)."""
+                                  options: ExecutionOptions | None = None, initial_pose=None) -> LinearizedResult:
+        """Registration::compute_linearized_result (registration.hpp:312-331); with `initial_pose` the overload
+        that applies the degenerate regularisation relative to it (:312-323)."""
         target_knn.nearest_neighbor_search_async(source, self._neighbors, None, pose)
-        return self._linearize(source, target, self._neighbors, pose, self._scale(options))
+        lin = self._linearize(source, target, self._neighbors, pose, self._scale(options))
+        if initial_pose is not None and self.params.degenerate_reg.type != DegenerateRegularizationType.none:
+            a = self.params.addons_c()
+            H = np.ascontiguousarray(lin.H, np.float32).reshape(36).copy()
+            b = np.ascontiguousarray(lin.b, np.float32).reshape(6).copy()
+            check(_lib.lib().spx_degenerate_regularize(C.byref(a), _hostf(H), _hostf(b), int(lin.inlier),
+                                                       _hostf(_T16(pose)), _hostf(_T16(initial_pose))))
+            lin.H, lin.b = H.reshape(6, 6), b
+        return lin
 
     def compute_error_frozen(self, source, target, pose, options: ExecutionOptions | None = None):
         """Registration::compute_error_frozen (registration.hpp:350-359)."""

@@ -1481,6 +1481,11 @@ struct spx_registration_s {
     spx_comm_t shard_comm = nullptr;  // fused (mailbox) sharded align in flight
     float4* shard_derived_normals = nullptr;
     int shard_max_it = 0;
+    // solver add-ons (host side): nl-reg parameters and the MAP prior of the next align
+    spx_registration_addons addons{0, 10.0f, 1.0f, 1.0f, 0, 1.0f, 1.0f, 3.16e-2f, 1e-2f};
+    bool prior_active = false;
+    float prior_omega[36] = {};
+    float prior_T_pred_inv[4][4] = {};
     // live timing of the iteration kernels (bench.py roofline)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0;
@@ -2297,6 +2302,224 @@ int spx_registration_destroy(spx_registration_t reg) {
     });
 }
 
+}  // extern "C"
+
+namespace {
+
+// eigen-decomposition of a symmetric 3x3 by cyclic Jacobi rotations in fp64 (the reference calls
+// Eigen::SelfAdjointEigenSolver<Matrix3f>, third-party and unpinned: any backward-stable solver agrees with it to
+// fp32 rounding).  evec columns = eigenvectors.
+void jacobi3(const float A[3][3], double ev[3], double V[3][3]) {
+    double a[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            a[i][j] = 0.5 * ((double)A[i][j] + (double)A[j][i]);
+            V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 32; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s_ = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s_ * akq;
+                    a[k][q] = s_ * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s_ * aqk;
+                    a[q][k] = s_ * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s_ * vkq;
+                    V[k][q] = s_ * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) ev[i] = a[i][i];
+}
+
+void colmajor_to_rm(const float* T16, float T[4][4]) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) T[i][j] = T16[j * 4 + i];
+}
+void isometry_inverse_rm(const float T[4][4], float out[4][4]) {
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) out[i][j] = T[j][i];
+        out[i][3] = -(T[0][i] * T[0][3] + T[1][i] * T[1][3] + T[2][i] * T[2][3]);
+        out[3][i] = 0.0f;
+    }
+    out[3][3] = 1.0f;
+}
+
+// DegenerateRegularization::regularize_impl — degenerate_regularization.hpp:58-112.  H row-major 6x6 (symmetric).
+void nl_reg_apply(const spx_registration_addons& A, float* H, float* b, uint32_t inlier, const float T_cur[4][4],
+                  const float T_init[4][4]) {
+    if (inlier == 0 || A.degenerate_type != 1) return;
+    const float lambda = A.base_factor * (float)inlier;
+    float Hp[36] = {};
+    for (int blk = 0; blk < 2; ++blk) {
+        const float thr = blk == 0 ? A.rot_eigenvalue_threshold : A.trans_eigenvalue_threshold;
+        if (!(thr > 0.0f)) continue;
+        float B[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) B[i][j] = H[(3 * blk + i) * 6 + 3 * blk + j];
+        double ev[3], V[3][3];
+        jacobi3(B, ev, V);
+        for (int k = 0; k < 3; ++k) {
+            const float val = (float)ev[k] / (float)inlier;
+            if (!(val < thr)) continue;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    Hp[(3 * blk + i) * 6 + 3 * blk + j] += lambda * ((float)V[i][k] * (float)V[j][k]);
+        }
+    }
+    float Ti[4][4], D[4][4], tw[6];
+    isometry_inverse_rm(T_init, Ti);
+    isometry_mul_rm(Ti, T_cur, D);
+    se3_log_rm(D, tw);
+    for (int i = 0; i < 6; ++i) {
+        float acc = 0.0f;
+        for (int j = 0; j < 6; ++j) acc += Hp[i * 6 + j] * tw[j];
+        b[i] += acc;
+    }
+    for (int i = 0; i < 36; ++i) H[i] += Hp[i];
+}
+
+// MapPrior::update — map_prior.hpp:30-117
+void map_prior_update(spx_registration_t reg, const spx_registration_result& prev, const float* T_pred16) {
+    reg->prior_active = false;
+    const spx_registration_addons& A = reg->addons;
+    if (!A.map_prior_enabled) return;
+    const float dof = 3.0f * (float)prev.inlier - 6.0f;
+    if (dof <= 0.0f) return;
+    if (!std::isfinite(prev.error_raw) || prev.error_raw < 0.0f) return;
+    const float s_sq = std::max(1.0f, 2.0f * prev.error_raw / dof);
+    float Tp[4][4], To[4][4];
+    colmajor_to_rm(T_pred16, Tp);
+    colmajor_to_rm(prev.T, To);
+    float Rrel[4][4] = {};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Rrel[i][j] = To[0][i] * Tp[0][j] + To[1][i] * Tp[1][j] + To[2][i] * Tp[2][j];
+    Rrel[3][3] = 1.0f;
+    float tw[6];
+    se3_log_rm(Rrel, tw);  // rotation vector = axis * angle (translation part zero)
+    const float dt[3] = {Tp[0][3] - To[0][3], Tp[1][3] - To[1][3], Tp[2][3] - To[2][3]};
+    float dtb[3];
+    for (int i = 0; i < 3; ++i) dtb[i] = Tp[0][i] * dt[0] + Tp[1][i] * dt[1] + Tp[2][i] * dt[2];
+    double q[6];
+    for (int i = 0; i < 3; ++i) {
+        q[i] = std::fabs(tw[i]) * A.rot_vel_sigma * A.rot_vel_sigma + A.rot_base_sigma * A.rot_base_sigma;
+        q[3 + i] = std::fabs(dtb[i]) * A.trans_vel_sigma * A.trans_vel_sigma + A.trans_base_sigma * A.trans_base_sigma;
+    }
+    // H_curr = Ad^T (H_raw / s^2) Ad, Ad = blockdiag(R_rel, R_rel)
+    double Hc[6][6], tmp[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 3; ++k) acc += (double)prev.H_raw[i * 6 + (j / 3) * 3 + k] / s_sq * Rrel[k][j % 3];
+            tmp[i][j] = acc;  // (H Ad)
+        }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 3; ++k) acc += (double)Rrel[k][i % 3] * tmp[(i / 3) * 3 + k][j];
+            Hc[i][j] = acc;  // Ad^T (H Ad)
+        }
+    // Omega = R - R (H + R)^-1 R with R = diag(1 / q): Gauss-Jordan with partial pivoting in fp64 (H + R is PD)
+    double M[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            M[i][j] = Hc[i][j] + (i == j ? 1.0 / q[i] : 0.0);
+            M[i][6 + j] = i == j ? 1.0 / q[i] : 0.0;  // right-hand sides: R
+        }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+        if (!(std::fabs(M[piv][c]) > 1e-300) || !std::isfinite(M[piv][c])) return;
+        if (piv != c)
+            for (int k = 0; k < 12; ++k) std::swap(M[c][k], M[piv][k]);
+        const double inv = 1.0 / M[c][c];
+        for (int k = 0; k < 12; ++k) M[c][k] *= inv;
+        for (int r = 0; r < 6; ++r) {
+            if (r == c) continue;
+            const double f = M[r][c];
+            if (f != 0.0)
+                for (int k = 0; k < 12; ++k) M[r][k] -= f * M[c][k];
+        }
+    }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            const double v = (i == j ? 1.0 / q[i] : 0.0) - (1.0 / q[i]) * M[i][6 + j];
+            if (!std::isfinite(v)) return;
+            reg->prior_omega[i * 6 + j] = (float)v;
+        }
+    isometry_inverse_rm(Tp, reg->prior_T_pred_inv);
+    reg->prior_active = true;
+}
+
+// e = Log(T_pred^-1 T), Omega e, 1/2 e^T Omega e — map_prior.hpp:119-146
+float map_prior_terms(const spx_registration_t reg, const float T[4][4], float* omega_e) {
+    float D[4][4], e[6];
+    isometry_mul_rm(reg->prior_T_pred_inv, T, D);
+    se3_log_rm(D, e);
+    float oe[6], dot = 0.0f;
+    for (int i = 0; i < 6; ++i) {
+        float acc = 0.0f;
+        for (int j = 0; j < 6; ++j) acc += reg->prior_omega[i * 6 + j] * e[j];
+        oe[i] = acc;
+        dot += e[i] * acc;
+    }
+    if (omega_e) std::memcpy(omega_e, oe, sizeof(oe));
+    return 0.5f * dot;
+}
+
+}  // namespace
+
+extern "C" {
+
+void spx_default_registration_addons(spx_registration_addons* a) {
+    if (!a) return;
+    *a = spx_registration_addons{0, 10.0f, 1.0f, 1.0f, 0, 1.0f, 1.0f, 3.16e-2f, 1e-2f};
+}
+
+int spx_registration_set_addons(spx_registration_t reg, const spx_registration_addons* a) {
+    return guard([&] {
+        SPX_REQUIRE(reg && a, "[Registration::set_params] null argument");
+        SPX_REQUIRE(a->degenerate_type == 0 || a->degenerate_type == 1, "[Registration::set_params] unknown degenerate regularization type");
+        reg->addons = *a;
+        reg->prior_active = false;
+    });
+}
+
+int spx_registration_set_map_prior_state(spx_registration_t reg, const spx_registration_result* prev_result,
+                                         const float* T_pred16, int* active_out, float* omega36_out) {
+    return guard([&] {
+        SPX_REQUIRE(reg && prev_result && T_pred16, "[Registration::set_map_prior_state] null argument");
+        map_prior_update(reg, *prev_result, T_pred16);
+        if (active_out) *active_out = reg->prior_active ? 1 : 0;
+        if (omega36_out && reg->prior_active) std::memcpy(omega36_out, reg->prior_omega, sizeof(reg->prior_omega));
+    });
+}
+
+int spx_degenerate_regularize(const spx_registration_addons* a, float* H36, float* b6, uint32_t inlier,
+                              const float* T_current16, const float* T_initial16) {
+    return guard([&] {
+        SPX_REQUIRE(a && H36 && b6 && T_current16 && T_initial16, "[DegenerateRegularization::regularize] null argument");
+        float Tc[4][4], Ti[4][4];
+        colmajor_to_rm(T_current16, Tc);
+        colmajor_to_rm(T_initial16, Ti);
+        nl_reg_apply(*a, H36, b6, inlier, Tc, Ti);
+    });
+}
+
 int spx_registration_set_params(spx_registration_t reg, const spx_registration_params* params) {
     return guard([&] {
         SPX_REQUIRE(reg && params, "[Registration::set_params] null argument");
@@ -2369,11 +2592,14 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         R->error_raw = FLT_MAX;
         if (ns == 0) return;  // registration.hpp:209-211
         SPX_REQUIRE(src_points && (tgt_points || nt == 0), "[Registration::align] null points");
+        // nl-reg / MAP prior sit between the linearisation and the step (registration.hpp:248-253): with either in
+        // force every method runs as the host-decided loop below (one 32-double read-back per iteration)
+        const bool addons_active = reg->addons.degenerate_type == 1 || reg->prior_active;
         {
             size_t split_min = 400000;
             if (const char* e = std::getenv("SPX_SPLIT_MIN")) split_min = (size_t)std::atoll(e);  // tuning aid
             if (P.optimization_method == SPX_OPT_GAUSS_NEWTON && ns < split_min && P.reg_type != SPX_REG_GENZ &&
-                !P.rotation_constraint_enable) {
+                !P.rotation_constraint_enable && !addons_active) {
                 // the cooperative one-launch path: the batched kernel with one pair
                 spx_align_pair one{};
                 one.src_points = src_points; one.src_covs = src_covs; one.ns = ns;
@@ -2393,7 +2619,7 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         const int max_it = P.max_iterations;
 
         reg->timed = false;
-        if (P.optimization_method == SPX_OPT_GAUSS_NEWTON) {
+        if (P.optimization_method == SPX_OPT_GAUSS_NEWTON && !addons_active) {
             // small clouds: one cooperative launch for the whole loop.  Large clouds: three ordinary
             // launches per iteration (search kernels with their own register budget), converged-state
             // polled every SPLIT_POLL iterations; launches after convergence return immediately.
@@ -2442,9 +2668,9 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
         }
 
         // LM / dog-leg: one host decision per trial step (registration.hpp:830-964)
-        float T[4][4];
+        float T[4][4], T_initial[4][4];
         for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 4; ++j) T[i][j] = R->T[j * 4 + i];
+            for (int j = 0; j < 4; ++j) T[i][j] = T_initial[i][j] = R->T[j * 4 + i];
         float lambda = P.lm_init_lambda;
         float radius = P.dogleg_initial_trust_region_radius;
         a.use_state = 0;
@@ -2460,6 +2686,7 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
             q->sync();
             *err = (float)hsums[S_ERR];
             *inl = (uint32_t)(hsums[S_INL] + 0.5);
+            if (reg->prior_active) *err += map_prior_terms(reg, Tn, nullptr);  // registration.hpp:854,933
         };
         auto clampf = [](float v, float lo, float hi) { return std::min(std::max(v, lo), hi); };
         for (int it = 0; it < max_it; ++it) {
@@ -2475,7 +2702,27 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
             std::memcpy(R->H_raw, H, sizeof(H));
             std::memcpy(R->b_raw, b, sizeof(b));
             R->error_raw = err;
-            if (P.optimization_method == SPX_OPT_LEVENBERG_MARQUARDT) {
+            nl_reg_apply(reg->addons, H, b, inl, T, T_initial);  // registration.hpp:249-250
+            if (reg->prior_active) {                             // :253, map_prior.hpp:119-132
+                float oe[6];
+                err += map_prior_terms(reg, T, oe);
+                for (int i = 0; i < 36; ++i) H[i] += reg->prior_omega[i];
+                for (int i = 0; i < 6; ++i) b[i] += oe[i];
+            }
+            if (P.optimization_method == SPX_OPT_GAUSS_NEWTON) {  // optimize_gauss_newton, registration.hpp:803-828
+                float d[6];
+                const bool ok = solve_damped6(H, b, P.gn_lambda, d);
+                R->converged = ok ? converged(d) : 0;
+                float E[4][4], Tn[4][4];
+                se3_exp_rm(d, E);
+                isometry_mul_rm(T, E, Tn);
+                std::memcpy(T, Tn, sizeof(T));
+                R->iterations = it;
+                std::memcpy(R->H, H, sizeof(H));
+                std::memcpy(R->b, b, sizeof(b));
+                R->error = err;
+                R->inlier = inl;
+            } else if (P.optimization_method == SPX_OPT_LEVENBERG_MARQUARDT) {
                 float last = FLT_MAX, d[6];
                 for (int in = 0; in < P.lm_max_inner_iterations; ++in) {
                     const bool ok = solve_damped6(H, b, lambda, d);

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <numeric>
+#include <queue>
 #include <random>
 #include <unordered_map>
 
@@ -457,6 +458,78 @@ int spx_random_sampling(spx_queue_t q, spx_rng_t rng, size_t n, size_t sampling_
         std::memcpy(pin, sel.data(), sel.size() * sizeof(int32_t));
         SPX_CUDA(cudaMemcpyAsync(idx_out, pin, sel.size() * sizeof(int32_t), cudaMemcpyDefault, q->stream));
         q->sync();  // the pinned staging block is reused by the next call
+    });
+}
+
+// mixed_random_sampling_operator.hpp:29-107: the first floor(sampling_num * weighted_ratio) points by weighted
+// reservoir keys log(u) / w (u ~ uniform_real_distribution<float>(FLT_MIN, 1), one draw per positive weight, the
+// smallest key evicted first: std::priority_queue with std::greater on (key, index)), the rest by a partial
+// Fisher-Yates over the not yet selected indices; the persistent mt19937 advances exactly as in the reference.
+int spx_mixed_random_sampling(spx_queue_t q, spx_rng_t rng, const float* weights, size_t n, size_t sampling_num,
+                              float weighted_ratio, int32_t* idx_out, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && rng && m_host, "[PreprocessFilter::mixed_random_sampling] null argument");
+        SPX_REQUIRE(n < (1ull << 31), "[PreprocessFilter::mixed_random_sampling] too many points");
+        DeviceGuard g(q->device);
+        std::vector<int32_t> sel;
+        if (n <= sampling_num) {
+            sel.resize(n);
+            std::iota(sel.begin(), sel.end(), 0);
+        } else {
+            SPX_REQUIRE(weights, "[PreprocessFilter::mixed_random_sampling] weights size must match points");
+            SPX_REQUIRE(std::isfinite(weighted_ratio) && weighted_ratio >= 0.0f && weighted_ratio <= 1.0f,
+                        "[PreprocessFilter::mixed_random_sampling] weighted_ratio must be within [0.0, 1.0]");
+            std::vector<float> w(n);
+            SPX_CUDA(cudaMemcpyAsync(w.data(), weights, n * sizeof(float), cudaMemcpyDefault, q->stream));
+            q->sync();
+            const size_t weighted_target = static_cast<size_t>(std::floor(static_cast<double>(sampling_num) * weighted_ratio));
+            std::vector<uint8_t> flags(n, 0);
+            using KeyIndexPair = std::pair<float, size_t>;
+            std::priority_queue<KeyIndexPair, std::vector<KeyIndexPair>, std::greater<KeyIndexPair>> selected;
+            std::uniform_real_distribution<float> weighted_dist(std::numeric_limits<float>::min(), 1.0f);
+            for (size_t i = 0; i < n; ++i) {
+                const float weight = w[i];
+                SPX_REQUIRE(std::isfinite(weight) && weight >= 0.0f,
+                            "[PreprocessFilter::mixed_random_sampling] weights must be finite and non-negative");
+                if (weight <= 0.0f || weighted_target == 0) continue;
+                const float key = std::log(weighted_dist(rng->mt)) / weight;
+                if (selected.size() < weighted_target) {
+                    selected.emplace(key, i);
+                    continue;
+                }
+                if (!selected.empty() && selected.top().first < key) {
+                    selected.pop();
+                    selected.emplace(key, i);
+                }
+            }
+            while (!selected.empty()) {
+                flags[selected.top().second] = 1;
+                selected.pop();
+            }
+            std::vector<size_t> remaining;
+            remaining.reserve(n);
+            size_t selected_count = 0;
+            for (size_t i = 0; i < n; ++i) {
+                if (flags[i]) ++selected_count;
+                else remaining.push_back(i);
+            }
+            const size_t uniform_target = std::min(sampling_num - selected_count, remaining.size());
+            for (size_t i = 0; i < uniform_target; ++i) {
+                std::uniform_int_distribution<size_t> uniform_dist(i, remaining.size() - 1);
+                const size_t j = uniform_dist(rng->mt);
+                std::swap(remaining[i], remaining[j]);
+                flags[remaining[i]] = 1;
+            }
+            for (size_t i = 0; i < n; ++i)
+                if (flags[i]) sel.push_back((int32_t)i);
+        }
+        *m_host = sel.size();
+        if (sel.empty()) return;
+        SPX_REQUIRE(idx_out, "[PreprocessFilter::mixed_random_sampling] null output");
+        int32_t* pin = static_cast<int32_t*>(q->pinned_get(sel.size() * sizeof(int32_t)));
+        std::memcpy(pin, sel.data(), sel.size() * sizeof(int32_t));
+        SPX_CUDA(cudaMemcpyAsync(idx_out, pin, sel.size() * sizeof(int32_t), cudaMemcpyDefault, q->stream));
+        q->sync();
     });
 }
 

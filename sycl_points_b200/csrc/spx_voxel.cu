@@ -14,6 +14,7 @@
 #include <cmath>
 
 #include "spx_scan.cuh"
+#include "spx_math.cuh"
 
 using namespace spx;
 
@@ -763,6 +764,40 @@ __global__ void __launch_bounds__(VX_THREADS) box_flag_kernel(const float4* __re
     flags[i] = keep;
 }
 
+// angle_incidence_filter — preprocess_operator/angle_incidence_filter_operator.hpp:57-103: keep a point when the
+// |cosine| between its direction from the sensor and its surface normal lies in [cos(max_angle), cos(min_angle)];
+// the normal is the stored one, or extract_normal of the covariance (covariance.hpp:49-65: eigenvector of the
+// smallest eigenvalue; the sign does not matter under the absolute value).  Non-finite points and degenerate
+// directions (|p| |n| <= 1e-6) are removed.
+__global__ void __launch_bounds__(VX_THREADS) angle_flag_kernel(const float4* __restrict__ pts, const float4* __restrict__ normals,
+                                                                const float* __restrict__ covs, uint32_t n, float min_cos,
+                                                                float max_cos, uint32_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pts + i);
+    uint32_t keep = 0;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(p.w)) {
+        float nx, ny, nz;
+        if (normals) {
+            const float4 nr = __ldg(normals + i);
+            nx = nr.x; ny = nr.y; nz = nr.z;
+        } else {
+            float ev[3], V[3][3];
+            mat3_eigen(load_cov16(covs + (size_t)i * 16), ev, V);
+            nx = V[0][0]; ny = V[1][0]; nz = V[2][0];
+        }
+        const float dot = __fmaf_rn(p.z, nz, __fmaf_rn(p.y, ny, __fmul_rn(p.x, nx)));
+        const float pn = __fsqrt_rn(__fmaf_rn(p.z, p.z, __fmaf_rn(p.y, p.y, __fmul_rn(p.x, p.x))));
+        const float nn = __fsqrt_rn(__fmaf_rn(nz, nz, __fmaf_rn(ny, ny, __fmul_rn(nx, nx))));
+        const float denom = __fmul_rn(pn, nn);
+        if (denom > 1e-6f) {
+            const float abs_cos = fabsf(__fdiv_rn(dot, denom));
+            keep = !(abs_cos < min_cos || abs_cos > max_cos);
+        }
+    }
+    flags[i] = keep;
+}
+
 // order given by idx: dst[j] = src[idx[j]], in 4-byte words (points 4 words, covariances 16)
 __global__ void __launch_bounds__(VX_THREADS) gather_words_kernel(const uint32_t* __restrict__ src, int words,
                                                                   const int32_t* __restrict__ idx, size_t total,
@@ -1187,6 +1222,44 @@ int spx_box_filter_indices(spx_queue_t q, const float* points, size_t n_in, floa
         uint32_t* total_dev = q->take<uint32_t>(16);
         box_flag_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(reinterpret_cast<const float4*>(points), n, min_distance,
                                                                      max_distance, flags);
+        SPX_LAUNCH_CHECK();
+        exclusive_scan_u32(st, flags, pos, n, scan_tmp, total_dev);
+        compact_index_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(flags, pos, n, idx_out);
+        SPX_LAUNCH_CHECK();
+        uint32_t* htotal = static_cast<uint32_t*>(q->pinned_get(64));
+        SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
+        q->sync();
+        *m_host = *htotal;
+    });
+}
+
+int spx_angle_incidence_indices(spx_queue_t q, const float* points, const float* normals, const float* covs, size_t n_in,
+                                float min_angle, float max_angle, int32_t* idx_out, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && m_host, "[PreprocessFilter::angle_incidence_filter] null argument");
+        SPX_REQUIRE(n_in < (1ull << 31), "[PreprocessFilter::angle_incidence_filter] too many points");
+        *m_host = 0;
+        if (n_in == 0) return;
+        if (!normals && !covs)
+            throw Error(SPX_ERR_INVALID_ARGUMENT,
+                        "[PreprocessFilter::angle_incidence_filter] Normal vector or covariance matrices must be pre-computed.");
+        SPX_REQUIRE(!(min_angle < 0.0f || max_angle > 3.14159265358979323846f * 0.5f || min_angle >= max_angle),
+                    "[PreprocessFilter::angle_incidence_filter] Invalid angle range");
+        SPX_REQUIRE(points && idx_out, "[PreprocessFilter::angle_incidence_filter] null pointer");
+        DeviceGuard dg(q->device);
+        cudaStream_t st = q->stream;
+        const uint32_t n = (uint32_t)n_in;
+        q->arena_reset();
+        q->arena_reserve((size_t)n * 8 + scan_scratch_elems(n) * 4 + 4096);
+        uint32_t* flags = q->take<uint32_t>(n);
+        uint32_t* pos = q->take<uint32_t>(n);
+        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(n));
+        uint32_t* total_dev = q->take<uint32_t>(16);
+        // std::cos of the host, as the reference evaluates the two bounds before the launch (:68-69)
+        const float max_cos = std::cos(min_angle), min_cos = std::cos(max_angle);
+        angle_flag_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(reinterpret_cast<const float4*>(points),
+                                                                       reinterpret_cast<const float4*>(normals), covs, n,
+                                                                       min_cos, max_cos, flags);
         SPX_LAUNCH_CHECK();
         exclusive_scan_u32(st, flags, pos, n, scan_tmp, total_dev);
         compact_index_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(flags, pos, n, idx_out);

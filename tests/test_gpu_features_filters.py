@@ -496,3 +496,59 @@ def test_polar_grid_reference_known_answer(spx, q):
     assert abs(got[1][0] - 2.2666667) < 1e-5 and abs(got[1][1] - 10.0) < 1e-5
     with pytest.raises(ValueError):
         spx.PolarGrid(q, 0.0, 1.0, 1.0)
+
+
+def test_mixed_random_sampling_matches_reference_rng_stream(spx, q, bundled):
+    """PreprocessFilter::mixed_random_sampling (mixed_random_sampling_operator.hpp:29-107): weighted reservoir keys
+    for floor(num * ratio) points + partial Fisher-Yates for the rest, the same mt19937 stream as the oracle
+    (libstdc++ distributions on both sides), order-preserving compaction of every attribute."""
+    pts = bundled["source_ds"]
+    n = len(pts)
+    rs = np.random.default_rng(8)
+    w = rs.uniform(0, 1, n).astype(np.float32)
+    w[rs.integers(0, n, 200)] = 0.0  # zero weights never enter the weighted part
+    cloud = spx.PointCloudShared(q, pts)
+    cloud.set_intensities(np.arange(n, dtype=np.float32))
+    f, rng = spx.PreprocessFilter(q), oracle.Rng(1234)
+    for num, ratio in ((512, 0.8), (512, 0.8), (100, 0.0), (100, 1.0), (333, 0.5)):
+        out = f.mixed_random_sampling(cloud, w, num, ratio)
+        keep = rng.mixed_random_sampling_flags(w, num, ratio).astype(bool)
+        assert out.size() == keep.sum() == num
+        assert np.array_equal(out.points_host(), pts[keep])
+        assert np.array_equal(out.intensities.download(), np.arange(n, dtype=np.float32)[keep])
+    # the uniform sampler shares nothing with it (separate generators in the reference, one per operator)
+    assert f.mixed_random_sampling(cloud, w, n + 1, 0.5) is cloud
+    with pytest.raises(ValueError):
+        f.mixed_random_sampling(cloud, w, 10, 1.5)
+    with pytest.raises(ValueError):
+        f.mixed_random_sampling(cloud, np.where(np.arange(n) == 3, -1.0, w).astype(np.float32), 10, 0.5)
+    with pytest.raises(ValueError):
+        f.mixed_random_sampling(cloud, w[:-1], 10, 0.5)
+
+
+def test_angle_incidence_filter_matches_oracle(spx, q, bundled):
+    """PreprocessFilter::angle_incidence_filter (angle_incidence_filter_operator.hpp:23-111) from covariances and
+    from stored normals: the kept set equals the oracle's, attributes follow."""
+    tgt = bundled["target_ds"].copy()
+    tgt[5, 0] = np.nan
+    cloud = spx.PointCloudShared(q, tgt)
+    nn = spx.KDTree.build(q, cloud).knn_search(cloud, 10)
+    spx.covariance.estimate(nn, cloud)
+    covs = cloud.covs_host()
+    f = spx.PreprocessFilter(q)
+    lo, hi = 0.0, np.float32(80.0 * np.pi / 180.0)
+    out = f.angle_incidence_filter(cloud, lo, hi, spx.PointCloudShared(q))
+    keep = oracle.angle_incidence_flags(tgt, lo, hi, covs=covs).astype(bool)
+    assert 0 < keep.sum() < len(tgt) and not keep[5]
+    assert np.array_equal(out.points_host(), tgt[keep])
+    assert np.array_equal(out.covs_host(), covs[keep])
+    spx.covariance.estimate_normals(nn, cloud)
+    nrm = cloud.normals_host()
+    out2 = f.angle_incidence_filter(cloud, np.float32(0.2), np.float32(1.2), spx.PointCloudShared(q))
+    keep2 = oracle.angle_incidence_flags(tgt, np.float32(0.2), np.float32(1.2), normals=nrm).astype(bool)
+    assert np.array_equal(out2.points_host(), tgt[keep2])
+    assert np.array_equal(out2.normals_host(), nrm[keep2])
+    with pytest.raises(ValueError):
+        f.angle_incidence_filter(cloud, 0.5, 0.4)
+    with pytest.raises(RuntimeError):
+        f.angle_incidence_filter(spx.PointCloudShared(q, tgt), 0.0, 1.0)

@@ -758,3 +758,101 @@ def test_rotation_constraint_vs_oracle(spx, q, pair, reg):
     src_nocov = spx.PointCloudShared(q, pair["src_h"])
     with pytest.raises(RuntimeError, match="Covariance matrices of source are required"):
         reg_obj.align(src_nocov, pair["tgt"], pair["tree"])
+
+
+# ------------------------------------------------------------------ solver add-ons: nl-reg and MAP prior
+@pytest.mark.parametrize("opt", ["GN", "LM", "DOGLEG"])
+@pytest.mark.parametrize("addon", ["nl_reg", "map_prior", "both"])
+def test_align_with_addons_matches_oracle(spx, q, pair, opt, addon):
+    """Degenerate regularisation (degenerate_regularization.hpp:58-112) and the MAP prior (map_prior.hpp:30-146)
+    between the linearisation and the step (registration.hpp:248-253): pose after every iteration within 1e-5 of
+    the oracle's restatement, H/b/error as returned (regularised) and H_raw/b_raw (raw) both checked.
+    Thresholds are set so that nl-reg really fires (every rotation eigen-direction of this pair is 'degenerate'
+    under a threshold of 1e9) and the prior comes from a real previous align."""
+    iters = 5
+    reg = "GICP"
+    params = spx.RegistrationParams(reg_type=spx.RegType[reg], max_iterations=iters)
+    params.robust.type = spx.RobustLossType.HUBER
+    params.robust.default_scale = 1.0
+    params.optimization_method = spx.OptimizationMethod({"GN": 0, "LM": 1, "DOGLEG": 2}[opt])
+    params.criteria.translation = params.criteria.rotation = 0.0
+    nl, mp = addon in ("nl_reg", "both"), addon in ("map_prior", "both")
+    if nl:
+        params.degenerate_reg.type = spx.DegenerateRegularizationType.nl_reg
+        params.degenerate_reg.rot_eigenvalue_threshold = 1e9
+        params.degenerate_reg.trans_eigenvalue_threshold = 0.5
+        params.degenerate_reg.base_factor = 20.0
+    params.map_prior.enabled = mp
+    robj = spx.Registration(q, params)
+    P = oracle.default_params(reg_type=oracle.REG[reg], loss=1, opt_method=oracle.OPT[opt], max_iterations=iters,
+                              robust_default_scale=1.0, crit_translation=0.0, crit_rotation=0.0)
+    oracle.set_addons(oracle.make_addons(nl_reg=nl, rot_thr=1e9, trans_thr=0.5, base_factor=20.0, map_prior=mp))
+    try:
+        T0 = oracle.se3_exp(np.array([0.002, -0.004, 0.006, 0.1, -0.05, 0.02], np.float32))
+        if mp:
+            # the "previous frame": a plain GN align without add-ons on both sides, then a predicted pose
+            oracle.set_addons(oracle.make_addons())
+            Pp = oracle.default_params(reg_type=oracle.REG[reg], loss=1, opt_method=0, max_iterations=4,
+                                       robust_default_scale=1.0)
+            oprev = oracle.align(Pp, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"], pair["nrm_t"],
+                                 pair["otree"])
+            pp = spx.RegistrationParams(reg_type=spx.RegType[reg], max_iterations=4)
+            pp.robust.type = spx.RobustLossType.HUBER
+            pp.robust.default_scale = 1.0
+            gprev = spx.Registration(q, pp).align(pair["src"], pair["tgt"], pair["tree"])
+            oracle.set_addons(oracle.make_addons(nl_reg=nl, rot_thr=1e9, trans_thr=0.5, base_factor=20.0, map_prior=True))
+            T_pred = (gprev.T @ oracle.se3_exp(np.array([0.01, 0.0, -0.02, 0.3, 0.1, 0.0], np.float32))).astype(np.float32)
+            act_o, om_o = oracle.set_map_prior_state(oprev, T_pred)
+            assert robj.set_map_prior_state(gprev, T_pred) and act_o
+            om_g = robj._prior_omega.reshape(6, 6)
+            assert rel(om_g, om_o) <= 1e-4  # built from each side's own H_raw (1e-5 apart) through a 6x6 inverse
+            T0 = T_pred
+        res = robj.align(pair["src"], pair["tgt"], pair["tree"], T0, trace=True)
+        ores = oracle.align(P, pair["src_h"], pair["cov_s"], pair["tgt_h"], pair["cov_t"], pair["nrm_t"], pair["otree"],
+                            T_init=T0, trace=True)
+    finally:
+        oracle.set_addons(oracle.make_addons())
+    tol = 2e-5 if mp else 1e-5  # the prior's information matrix differs by the two previous aligns' rounding
+    for it in range(iters):
+        dt, da = pose_delta(ores["trace"][it], res.trace[it])
+        assert dt < tol and da < tol, f"iteration {it}: dt={dt:.2e} da={da:.2e}"
+    assert res.iterations == ores["iterations"] == iters - 1
+    assert res.inlier == ores["inlier"]
+    assert rel(res.H_raw, ores["H_raw"]) <= 1e-5
+    assert rel(res.H, ores["H"]) <= (1e-4 if mp else 1e-5)
+    assert rel(res.H, res.H_raw) > 1e-4  # the add-on really changed the system (H of GICP is ~1e6-1e7 here)
+    assert abs(res.error - ores["error"]) <= 2e-5 * abs(ores["error"])
+    # with the add-ons cleared the same handle is back on the one-launch path and equals a fresh plain align
+    params.degenerate_reg.type = spx.DegenerateRegularizationType.none
+    params.map_prior.enabled = False
+    plain = robj.align(pair["src"], pair["tgt"], pair["tree"], T0)
+    params2 = spx.RegistrationParams(reg_type=spx.RegType[reg], max_iterations=iters)
+    params2.robust.type = spx.RobustLossType.HUBER
+    params2.robust.default_scale = 1.0
+    params2.optimization_method = params.optimization_method
+    params2.criteria.translation = params2.criteria.rotation = 0.0
+    fresh = spx.Registration(q, params2).align(pair["src"], pair["tgt"], pair["tree"], T0)
+    assert np.array_equal(plain.T, fresh.T)
+
+
+def test_degenerate_regularize_entry_point_vs_oracle(spx, q, pair):
+    """compute_linearized_result(..., initial_pose) (registration.hpp:312-323) and the host entry point
+    spx_degenerate_regularize against the oracle, including the no-op cases (type none, zero inliers)."""
+    T = oracle.se3_exp(np.array([0.004, -0.003, 0.012, 0.4, 0.1, -0.02], np.float32))
+    T0 = np.eye(4, dtype=np.float32)
+    params = spx.RegistrationParams(reg_type=spx.RegType.GICP)
+    params.degenerate_reg.type = spx.DegenerateRegularizationType.nl_reg
+    params.degenerate_reg.rot_eigenvalue_threshold = 1e9
+    params.degenerate_reg.trans_eigenvalue_threshold = 1e9
+    robj = spx.Registration(q, params)
+    raw = robj.compute_linearized_result(pair["src"], pair["tgt"], pair["tree"], T)
+    regd = robj.compute_linearized_result(pair["src"], pair["tgt"], pair["tree"], T, initial_pose=T0)
+    Ho, bo = oracle.degenerate_regularize(oracle.make_addons(nl_reg=True, rot_thr=1e9, trans_thr=1e9), raw.H, raw.b,
+                                          raw.inlier, T, T0)
+    assert rel(regd.H, Ho) <= 1e-6 and rel(regd.b, bo) <= 1e-5
+    # every direction penalised with lambda = inlier: H grows by lambda * I on both diagonal blocks
+    lam = float(raw.inlier)
+    np.testing.assert_allclose(regd.H - raw.H, lam * np.eye(6), atol=2e-4 * lam)
+    params.degenerate_reg.type = spx.DegenerateRegularizationType.none
+    same = robj.compute_linearized_result(pair["src"], pair["tgt"], pair["tree"], T, initial_pose=T0)
+    assert np.array_equal(same.H, raw.H) and np.array_equal(same.b, raw.b)

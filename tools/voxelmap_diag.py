@@ -1,5 +1,7 @@
 """Diagnostic: where do the voxel map's covariances differ from the sequential oracle?  (GPU box)"""
 import ctypes as C
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import oracle, synthetic
 import sycl_points_b200 as spx
