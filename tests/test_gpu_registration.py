@@ -820,7 +820,7 @@ def test_align_with_addons_matches_oracle(spx, q, pair, opt, addon):
     assert res.inlier == ores["inlier"]
     assert rel(res.H_raw, ores["H_raw"]) <= 1e-5
     assert rel(res.H, ores["H"]) <= (1e-4 if mp else 1e-5)
-    assert rel(res.H, res.H_raw) > 1e-4  # the add-on really changed the system (H of GICP is ~1e6-1e7 here)
+    assert rel(res.H, res.H_raw) > 1e-5  # the add-on really changed the system (H of GICP is ~1e6-1e7 here, the prior ~1e2-1e4)
     assert abs(res.error - ores["error"]) <= 2e-5 * abs(ores["error"])
     # with the add-ons cleared the same handle is back on the one-launch path and equals a fresh plain align
     params.degenerate_reg.type = spx.DegenerateRegularizationType.none
