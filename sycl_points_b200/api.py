@@ -202,6 +202,8 @@ class DeviceArray:
 
     def free(self):
         if getattr(self, "_p", None) and self._p:
+            # (a queue already closed — members of a reference cycle are finalised in no particular order — passes
+            # NULL: the library then frees synchronously)
             _lib.lib().spx_free(self.queue.handle, self._p)
             self._p = None
 

@@ -45,6 +45,7 @@ inline int guard(F&& f) {
         return SPX_OK;
     } catch (const Error& e) {
         set_last_error(e.what());
+        if (e.code == SPX_ERR_CUDA) (void)cudaGetLastError();  // reported once: do not leave it pending for the next launch check
         return e.code;
     } catch (const std::exception& e) {
         set_last_error(e.what());
@@ -142,6 +143,11 @@ struct spx_comm_s {
 };
 
 namespace spx {
+
+// Handles (device arrays, indices, registrations, voxel maps) outlive their queue in garbage-collected callers
+// (Python finalises the members of a reference cycle in no particular order): every path that releases memory
+// checks that its queue still exists and falls back to a synchronous cudaFree when it does not.
+bool queue_is_live(spx_queue_t q);
 
 struct DeviceGuard {
     int prev = 0;

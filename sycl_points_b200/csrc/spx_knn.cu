@@ -1423,12 +1423,20 @@ int index_build_impl(spx_queue_t q, const float* targets, size_t nt, float cell_
 int spx_index_destroy(spx_index_t index) {
     return guard([&] {
         if (!index) return;
-        DeviceGuard g(index->q->device);
-        for (int l = 0; l < GRID_MAX_LEVELS; ++l) {
-            if (index->sorted[l]) cudaFreeAsync(index->sorted[l], index->q->stream);
-            if (index->start[l]) cudaFreeAsync(index->start[l], index->q->stream);
+        if (queue_is_live(index->q)) {
+            DeviceGuard g(index->q->device);
+            for (int l = 0; l < GRID_MAX_LEVELS; ++l) {
+                if (index->sorted[l]) cudaFreeAsync(index->sorted[l], index->q->stream);
+                if (index->start[l]) cudaFreeAsync(index->start[l], index->q->stream);
+            }
+            if (index->occ_dev) cudaFreeAsync(index->occ_dev, index->q->stream);
+        } else {  // the queue was destroyed first: synchronous frees
+            for (int l = 0; l < GRID_MAX_LEVELS; ++l) {
+                if (index->sorted[l]) cudaFree(index->sorted[l]);
+                if (index->start[l]) cudaFree(index->start[l]);
+            }
+            if (index->occ_dev) cudaFree(index->occ_dev);
         }
-        if (index->occ_dev) cudaFreeAsync(index->occ_dev, index->q->stream);
         delete index;
     });
 }

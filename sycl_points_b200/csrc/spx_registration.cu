@@ -2295,9 +2295,14 @@ int spx_registration_create(spx_queue_t q, const spx_registration_params* params
 int spx_registration_destroy(spx_registration_t reg) {
     return guard([&] {
         if (!reg) return;
-        DeviceGuard g(reg->q->device);
-        cudaStreamSynchronize(reg->q->stream);
-        reg_free(reg);
+        if (queue_is_live(reg->q)) {
+            DeviceGuard g(reg->q->device);
+            cudaStreamSynchronize(reg->q->stream);
+            reg_free(reg);
+        } else {
+            cudaDeviceSynchronize();
+            reg_free(reg);
+        }
         delete reg;
     });
 }

@@ -9,6 +9,7 @@
 #include <queue>
 #include <random>
 #include <unordered_map>
+#include <unordered_set>
 
 #include <cuda_profiler_api.h>
 
@@ -72,6 +73,23 @@ void spx_queue_s::sync() {
     for (void* p : retired) cudaFree(p);
     retired.clear();
 }
+
+namespace spx {
+namespace {
+std::mutex g_queues_mu;
+std::unordered_set<spx_queue_t> g_queues;
+}  // namespace
+bool queue_is_live(spx_queue_t q) {
+    if (!q) return false;
+    std::lock_guard<std::mutex> lk(g_queues_mu);
+    return g_queues.count(q) != 0;
+}
+static void queue_register(spx_queue_t q, bool live) {
+    std::lock_guard<std::mutex> lk(g_queues_mu);
+    if (live) g_queues.insert(q);
+    else g_queues.erase(q);
+}
+}  // namespace spx
 
 extern "C" {
 
@@ -159,6 +177,7 @@ static int queue_create(int device, void* stream, bool own, spx_queue_t* out, in
             }
         }
         q->arena_reserve(8 << 20);
+        queue_register(q, true);
         *out = q;
     });
 }
@@ -173,7 +192,8 @@ int spx_queue_create_on_stream(int device, void* cuda_stream, spx_queue_t* out) 
 
 int spx_queue_destroy(spx_queue_t q) {
     return guard([&] {
-        if (!q) return;
+        if (!q || !queue_is_live(q)) return;  // (a second destroy of the same handle is ignored)
+        queue_register(q, false);
         DeviceGuard g(q->device);
         cudaStreamSynchronize(q->stream);
         for (void* p : q->retired) cudaFree(p);
@@ -224,8 +244,11 @@ int spx_malloc(spx_queue_t q, size_t bytes, void** out) {
 
 int spx_free(spx_queue_t q, void* ptr) {
     return guard([&] {
-        SPX_REQUIRE(q, "[spx_free] null queue");
         if (!ptr) return;
+        if (!queue_is_live(q)) {  // the queue is gone (or NULL): nothing to order against, free synchronously
+            SPX_CUDA(cudaFree(ptr));
+            return;
+        }
         DeviceGuard g(q->device);
         SPX_CUDA(cudaFreeAsync(ptr, q->stream));  // ordered after everything already enqueued
     });
@@ -563,8 +586,12 @@ int spx_comm_create(spx_queue_t q, int rank, int world, spx_comm_t* out) {
 int spx_comm_destroy(spx_comm_t c) {
     return guard([&] {
         if (!c) return;
-        DeviceGuard g(c->q->device);
-        cudaStreamSynchronize(c->q->stream);
+        if (queue_is_live(c->q)) {
+            DeviceGuard g(c->q->device);
+            cudaStreamSynchronize(c->q->stream);
+        } else {
+            cudaDeviceSynchronize();
+        }
         for (int r = 0; r < c->world; ++r)
             if (c->ipc_opened[r] && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
         if (c->local) cudaFree(c->local);

@@ -425,8 +425,12 @@ int spx_voxelmap_create(spx_queue_t q, float voxel_size, spx_voxelmap_t* out) {
 int spx_voxelmap_destroy(spx_voxelmap_t m) {
     return guard([&] {
         if (!m) return;
-        DeviceGuard dg(m->q->device);
-        cudaStreamSynchronize(m->q->stream);
+        if (queue_is_live(m->q)) {
+            DeviceGuard dg(m->q->device);
+            cudaStreamSynchronize(m->q->stream);
+        } else {
+            cudaDeviceSynchronize();
+        }
         vm_free_table(m->t);
         cudaFree(m->counter);
         delete m;

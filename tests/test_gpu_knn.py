@@ -292,3 +292,32 @@ def test_remove_nodes_by_flags_renumbers_and_stays_exact(spx, q):
     np.testing.assert_array_equal(got.distances_host(), want.distances_host())
     assert np.array_equal(got.indices_host()[:, 0], np.arange(kept.size()))
     assert tree.info()["n_points"] == kept.size()
+
+
+def test_handles_may_outlive_their_queue(spx):
+    """Garbage-collected callers finalise the members of a reference cycle in no particular order, so a device array,
+    an index, a registration or a voxel map can be released AFTER its queue: every release path checks that the queue
+    still exists (frees synchronously otherwise) and leaves no pending CUDA error behind for the next launch."""
+    q2 = spx.DeviceQueue(0)
+    pts = np.random.default_rng(0).uniform(-5, 5, (2000, 4)).astype(np.float32)
+    pts[:, 3] = 1
+    cloud = spx.PointCloudShared(q2, pts)
+    tree = spx.KDTree.build(q2, cloud)
+    nn = tree.knn_search(cloud, 5)
+    reg = spx.Registration(q2)
+    vmap = spx.VoxelHashMap(q2, 0.5)
+    vmap.add_point_cloud(cloud)
+    q2.wait()
+    q2.close()          # the queue goes first ...
+    q2.close()          # (twice is harmless)
+    tree.close()        # ... then everything that was created on it
+    reg.close()
+    vmap.close()
+    cloud.points.free()
+    nn.indices.free()
+    nn.distances.free()
+    # the library is still healthy: a fresh queue computes and no stale error surfaces at its first launch check
+    q3 = spx.DeviceQueue(0)
+    c3 = spx.PointCloudShared(q3, pts)
+    got = spx.KDTree.build(q3, c3).knn_search(c3, 3).indices_host()
+    assert (got[:, 0] == np.arange(len(pts))).all()
