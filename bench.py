@@ -920,7 +920,7 @@ def main():
             "e2e": {"value": r.get("e2e_mqueries_per_s"), "unit": "Mqueries/s", "h2d_bytes_per_step": r.get("e2e_h2d_bytes"),
                     "d2h_bytes_per_step": r.get("e2e_d2h_bytes")},
             "gpu_launches": int(r["gpu_launches_per_search"] * steps),
-            "roofline": {"bound": "hbm", "kernel": "grid_knn_reg_*<20>" if method == "index" else "knn_bruteforce_kernel<4,packed>",
+            "roofline": {"bound": "hbm", "kernel": "grid_knn_reg_*<20>" if method == "index" else "knn_bruteforce_kernel<2,packed,TMA-staged,batch 2>",
                          "achieved": r["algorithmic_gbs"], "peak": ctx.peak_hbm * ctx.world, "unit": "GB/s",
                          "frac": r["algorithmic_gbs"] / (ctx.peak_hbm * ctx.world), "traffic": None,
                          "note": "the brute force is FP32-issue bound and the index L2-latency bound (SURVEY.md §8(d)); see details"},

@@ -875,6 +875,8 @@ struct spx_index_s {
     uint32_t* start[spx::GRID_MAX_LEVELS] = {};
     size_t ncells[spx::GRID_MAX_LEVELS] = {};
     unsigned long long* occ_dev = nullptr;  // occupied cells of the finest level (device counter)
+    cudaEvent_t ready = nullptr;            // recorded on q's stream when the build's last kernel is queued: users on
+                                            // OTHER queues wait on it (KDTree::build is synchronous in the reference)
     spx::GridLevels levels{};      // k = 1 searches and the registration kernels
     spx::GridLevels levels_knn{};  // k >= 2 searches: an extra, coarser first grid + the regular levels above the finest
 };

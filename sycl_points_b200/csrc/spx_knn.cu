@@ -53,14 +53,50 @@ __device__ __forceinline__ unsigned long long dist_sq2(unsigned long long qx, un
     return r;
 }
 
-template <int QPT, bool PACKED>
+// ---- target tiles through the TMA engine: 1-D bulk copies (cp.async.bulk, completion counted in bytes on an
+// mbarrier) into a double-buffered shared-memory tile, issued by one thread a whole tile ahead of the compute, so the
+// global-load latency of the staging (the long-scoreboard + barrier stalls of the synchronous version:
+// profiles/r2g_ncu_bf_p4.txt) hides behind the distance evaluations of the previous tile.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Measured and rejected (r2h): a persistent grid whose warps take their queries by ticket, against the tail of the
+// 2.2-wave grid — 13 % SLOWER: blocks that start every pass together stay in lockstep, so nothing overlaps their
+// staging phases, while the hardware's own block scheduler already fills the tail.
+template <int QPT, bool PACKED, bool TMA, int BATCH = BF_BATCH>
 __global__ void __launch_bounds__(BF_THREADS) knn_bruteforce_kernel(const float4* __restrict__ queries, uint32_t nq,
                                                                     const float4* __restrict__ targets, uint32_t nt,
                                                                     int k, Xform T, int has_T,
                                                                     int32_t* __restrict__ idx,
                                                                     float* __restrict__ dist) {
     static_assert(!PACKED || QPT % 2 == 0, "packed variant pairs queries");
-    __shared__ float4 tile[BF_TILE];
+    // (static shared memory: 2 x 16 KB with TMA staging, 1 x 32 KB without)
+    constexpr int TILE = TMA ? BF_TILE / 2 : BF_TILE;
+    __shared__ __align__(128) float4 tiles[TMA ? 2 : 1][TILE];
+    __shared__ __align__(8) unsigned long long bars[2];
     const uint32_t first = (blockIdx.x * BF_THREADS + threadIdx.x) * QPT;
 
     float qx[QPT], qy[QPT], qz[QPT], wd[QPT];
@@ -92,23 +128,55 @@ __global__ void __launch_bounds__(BF_THREADS) knn_bruteforce_kernel(const float4
         }
     }
 
-    for (uint32_t base = 0; base < nt; base += BF_TILE) {
-        __syncthreads();
-#pragma unroll
-        for (int t = threadIdx.x; t < BF_TILE; t += BF_THREADS) {
-            const uint32_t j = base + t;
-            // sentinel beyond the end: squares overflow to +inf, never below any k-th best
-            tile[t] = j < nt ? __ldg(targets + j) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 1.0f);
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        const int lim = min((uint32_t)BF_TILE, nt - base);
-        const int limb = (lim + BF_BATCH - 1) / BF_BATCH * BF_BATCH;  // sentinels cover the padding
+        if (threadIdx.x == 0 && nt > 0) {
+            const uint32_t bytes = min((uint32_t)TILE, nt) * (uint32_t)sizeof(float4);
+            mbar_expect_tx(&bars[0], bytes);
+            bulk_g2s(&tiles[0][0], targets, bytes, &bars[0]);
+        }
+    }
+    uint32_t it = 0;
+    for (uint32_t base = 0; base < nt; base += TILE, ++it) {
+        const int lim = min((uint32_t)TILE, nt - base);
+        const int limb = (lim + BATCH - 1) / BATCH * BATCH;  // sentinels cover the padding
+        const float4* tile;
+        if (TMA) {
+            const uint32_t buf = it & 1u;
+            // the other buffer was read in the previous iteration, which ended in a block barrier: refill it now
+            if (threadIdx.x == 0 && base + TILE < nt) {
+                const uint32_t bytes = min((uint32_t)TILE, nt - base - TILE) * (uint32_t)sizeof(float4);
+                mbar_expect_tx(&bars[buf ^ 1u], bytes);
+                bulk_g2s(&tiles[buf ^ 1u][0], targets + base + TILE, bytes, &bars[buf ^ 1u]);
+            }
+            mbar_wait(&bars[buf], (it >> 1) & 1u);
+            if (lim < limb) {  // (last tile only) sentinels beyond the end: squares overflow to +inf, never a k-th best
+                if (threadIdx.x < (unsigned)(limb - lim))
+                    tiles[buf][lim + threadIdx.x] = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 1.0f);
+                __syncthreads();
+            }
+            tile = tiles[buf];
+        } else {
+            __syncthreads();
+#pragma unroll
+            for (int t = threadIdx.x; t < TILE; t += BF_THREADS) {
+                const uint32_t j = base + t;
+                tiles[0][t] = j < nt ? __ldg(targets + j) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 1.0f);
+            }
+            __syncthreads();
+            tile = tiles[0];
+        }
 #pragma unroll 2
-        for (int t = 0; t < limb; t += BF_BATCH) {
-            float ds[BF_BATCH][QPT];
+        for (int t = 0; t < limb; t += BATCH) {
+            float ds[BATCH][QPT];
             bool any = false;
 #pragma unroll
-            for (int v = 0; v < BF_BATCH; ++v) {
+            for (int v = 0; v < BATCH; ++v) {
                 const float4 p = tile[t + v];
                 if (PACKED) {
 #pragma unroll
@@ -121,29 +189,63 @@ __global__ void __launch_bounds__(BF_THREADS) knn_bruteforce_kernel(const float4
 #pragma unroll
                 for (int u = 0; u < QPT; ++u) any |= ds[v][u] < wd[u];
             }
-            if (any) {
+            // A target that beats some query's k-th best is rare (k (1 + ln(N / k)) of N per query) but divergent:
+            // handled per lane, the sorted insertion — a chain of dependent loads and stores on the query's result
+            // row — ran with one lane in 32 and took a quarter of the kernel's issue slots (24 of 32 lanes active on
+            // average, profiles/r2g_ncu_bf_p4.txt).  Here the WARP inserts for the lane: each lane holds one slot of
+            // the row (k <= 128: up to four), the position is a ballot count, the shift one coalesced load and store.
+            if (__any_sync(0xffffffffu, any)) {
+                const int lane = threadIdx.x & 31;
 #pragma unroll
                 for (int u = 0; u < QPT; ++u) {
 #pragma unroll
-                    for (int v = 0; v < BF_BATCH; ++v) {
+                    for (int v = 0; v < BATCH; ++v) {
                         const float d1 = ds[v][u];
-                        if (d1 < wd[u]) {
-                            float* d = drow[u];
-                            int32_t* id = irow[u];
-                            int pos = k - 1;
-                            while (pos > 0 && d1 < d[pos - 1]) {
-                                d[pos] = d[pos - 1];
-                                id[pos] = id[pos - 1];
-                                --pos;
+                        unsigned m = __ballot_sync(0xffffffffu, d1 < wd[u]);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float dd = __shfl_sync(0xffffffffu, d1, src);
+                            const uint32_t qi = first + (uint32_t)((src - lane) * QPT + u);  // src's query (a live one)
+                            float* d = dist + (size_t)qi * k;
+                            int32_t* id = idx + (size_t)qi * k;
+                            // pos = entries with dist <= dd (strict '<' insertion: behind its equals, bruteforce.hpp:71-83)
+                            int pos = 0;
+                            float pd[4];
+                            int32_t pi[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = e * 32 + lane;
+                                pd[e] = 0.f;
+                                pi[e] = 0;
+                                if (e * 32 < k) {
+                                    const bool in = j < k;
+                                    const float cd = in ? d[j] : FLT_MAX;
+                                    pos += __popc(__ballot_sync(0xffffffffu, in && cd <= dd));
+                                    if (in && j > 0) {
+                                        pd[e] = d[j - 1];
+                                        pi[e] = id[j - 1];
+                                    }
+                                }
                             }
-                            d[pos] = d1;
-                            id[pos] = (int)(base + t + v);
-                            wd[u] = d[k - 1];
+                            const float tail = k >= 2 ? d[k - 2] : dd;  // (same address in every lane)
+                            __syncwarp();  // every load of the old row is done before any slot is overwritten
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = e * 32 + lane;
+                                if (e * 32 < k && j < k && j >= pos) {
+                                    d[j] = j == pos ? dd : pd[e];
+                                    id[j] = j == pos ? (int)(base + t + v) : pi[e];
+                                }
+                            }
+                            __syncwarp();  // the row is consistent before the next insertion reads it
+                            if (lane == src) wd[u] = pos == k - 1 ? dd : tail;
                         }
                     }
                 }
             }
         }
+        if (TMA) __syncthreads();  // every thread is done with this buffer before the next iteration refills it
     }
 }
 
@@ -1111,23 +1213,52 @@ __global__ void __launch_bounds__(256) index_kept_points_kernel(const float4* __
 void launch_bruteforce(spx_queue_t q, const float4* queries, uint32_t nq, const float4* targets, uint32_t nt, int k,
                        const Xform& T, int has_T, int32_t* idx, float* dist) {
     if (nq == 0) return;
-    // more queries per thread = fewer shared-memory reads per pair; small batches keep 1 so the grid
-    // still covers the SMs.  SPX_BF_VARIANT (tuning): "q1", "q2", "q4", "p2", "p4" force a variant.
-    int qpt = nq >= (uint32_t)q->sm_count * BF_THREADS * 8 ? 4 : (nq >= (uint32_t)q->sm_count * BF_THREADS * 4 ? 2 : 1);
+    // Two queries per thread as ONE packed-FP32 stream, the k-th-best test every two targets: measured best on
+    // 1 M x 1 M, k = 20 (profiles/r2k_bf_variants.txt, r2l: p2/batch 2 257 ms; p4/batch 2 305; p2/batch 4 278;
+    // p4/batch 4 404; scalar q2 343, q1 359) — more queries per thread or a longer batch make the (rare, but
+    // warp-wide) insertion path fire more often than the saved shared-memory reads are worth.  Small query sets keep
+    // one query per thread so the grid still covers the SMs.  SPX_BF_VARIANT (tuning): "q1", "q2", "q4", "q8", "p2",
+    // "p4", "p8" force a variant, SPX_BF_BATCH the number of targets per k-th-best test.
+    int qpt = nq >= (uint32_t)q->sm_count * BF_THREADS * 4 ? 2 : 1;
     bool packed = qpt >= 2;
     if (const char* e = std::getenv("SPX_BF_VARIANT")) {
         packed = e[0] == 'p';
-        qpt = e[1] == '4' ? 4 : (e[1] == '2' ? 2 : 1);
+        qpt = e[1] == '8' ? 8 : (e[1] == '4' ? 4 : (e[1] == '2' ? 2 : 1));
         if (qpt == 1) packed = false;
     }
     const unsigned blocks = (unsigned)div_up(nq, (size_t)BF_THREADS * qpt);
-#define SPX_BF_LAUNCH(Q, P) \
-    knn_bruteforce_kernel<Q, P><<<blocks, BF_THREADS, 0, q->stream>>>(queries, nq, targets, nt, k, T, has_T, idx, dist)
-    if (qpt == 4 && packed) SPX_BF_LAUNCH(4, true);
+    // TMA-staged, double-buffered tiles (2 x 1024 targets of shared memory per block) whenever the targets are 16-byte aligned
+    // — every cudaMalloc'ed cloud is; SPX_BF_TMA=0 keeps the synchronous staging (tuning aid)
+    static const bool allow_tma = !(std::getenv("SPX_BF_TMA") && std::getenv("SPX_BF_TMA")[0] == '0');
+    const bool tma = allow_tma && (reinterpret_cast<uintptr_t>(targets) % 16 == 0);
+#define SPX_BF_LAUNCH(Q, P)                                                                                              \
+    do {                                                                                                                 \
+        if (tma)                                                                                                         \
+            knn_bruteforce_kernel<Q, P, true><<<blocks, BF_THREADS, 0, q->stream>>>(queries, nq, targets, nt, k, T, has_T, \
+                                                                                    idx, dist);                         \
+        else                                                                                                             \
+            knn_bruteforce_kernel<Q, P, false><<<blocks, BF_THREADS, 0, q->stream>>>(queries, nq, targets, nt, k, T,      \
+                                                                                     has_T, idx, dist);                 \
+    } while (0)
+    int batch = (packed && qpt == 2) ? 2 : BF_BATCH;
+    if (const char* e = std::getenv("SPX_BF_BATCH")) batch = std::atoi(e);  // tuning aid (packed TMA variants only)
+#define SPX_BF_LAUNCH_B(Q, B)                                                                                        \
+    knn_bruteforce_kernel<Q, true, true, B><<<blocks, BF_THREADS, 0, q->stream>>>(queries, nq, targets, nt, k, T, has_T, \
+                                                                                  idx, dist)
+    if (tma && packed && qpt == 2 && batch == 1) SPX_BF_LAUNCH_B(2, 1);
+    else if (tma && packed && qpt == 4 && batch == 1) SPX_BF_LAUNCH_B(4, 1);
+    else if (tma && packed && qpt == 2 && batch == 2) SPX_BF_LAUNCH_B(2, 2);
+    else if (tma && packed && qpt == 2 && batch == 8) SPX_BF_LAUNCH_B(2, 8);
+    else if (tma && packed && qpt == 4 && batch == 2) SPX_BF_LAUNCH_B(4, 2);
+    else if (tma && packed && qpt == 4 && batch == 8) SPX_BF_LAUNCH_B(4, 8);
+    else if (qpt == 8 && packed) SPX_BF_LAUNCH(8, true);
+    else if (qpt == 8) SPX_BF_LAUNCH(8, false);
+    else if (qpt == 4 && packed) SPX_BF_LAUNCH(4, true);
     else if (qpt == 4) SPX_BF_LAUNCH(4, false);
     else if (qpt == 2 && packed) SPX_BF_LAUNCH(2, true);
     else if (qpt == 2) SPX_BF_LAUNCH(2, false);
     else SPX_BF_LAUNCH(1, false);
+#undef SPX_BF_LAUNCH_B
 #undef SPX_BF_LAUNCH
     SPX_LAUNCH_CHECK();
 }
@@ -1198,15 +1329,37 @@ int spx_index_build_hinted(spx_queue_t q, const float* targets, size_t nt, const
 
 namespace {
 int index_build_impl(spx_queue_t q, const float* targets, size_t nt, float cell_size, const BuildHint* hint, spx_index_t* out) {
+    if (out) *out = nullptr;
     return guard([&] {
         SPX_REQUIRE(q && out, "[KDTree::build] null argument");
         SPX_REQUIRE(nt < (1ull << 31), "[KDTree::build] too many points");
         SPX_REQUIRE(targets || nt == 0, "[KDTree::build] null points");
         DeviceGuard dg(q->device);
+        // the handle reaches the caller only when the build succeeded: a throw below (budget checks, allocation
+        // failures) releases what was allocated so far instead of leaking a half-built index
+        struct Holder {
+            spx_index_s* p;
+            spx_index_t* out;
+            bool done = false;
+            ~Holder() {
+                if (done) {
+                    if (!p->ready) cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming);
+                    if (p->ready) cudaEventRecord(p->ready, p->q->stream);
+                    *out = p;
+                    return;
+                }
+                for (int l = 0; l < GRID_MAX_LEVELS; ++l) {
+                    if (p->sorted[l]) cudaFreeAsync(p->sorted[l], p->q->stream);
+                    if (p->start[l]) cudaFreeAsync(p->start[l], p->q->stream);
+                }
+                if (p->occ_dev) cudaFreeAsync(p->occ_dev, p->q->stream);
+                delete p;
+            }
+        };
         auto* ix = new spx_index_s();
         ix->q = q;
         ix->n_total = nt;
-        *out = ix;
+        Holder holder{ix, out};
         GridLevels& L = ix->levels;
         L = GridLevels{};
         L.n_levels = 1;
@@ -1214,7 +1367,10 @@ int index_build_impl(spx_queue_t q, const float* targets, size_t nt, float cell_
         L.lv[0].cell = 1.0f;
         L.lv[0].inv = 1.0f;
         ix->levels_knn = L;
-        if (nt == 0) return;  // empty tree: every search returns -1 / FLT_MAX (kdtree.hpp:296-300)
+        if (nt == 0) {  // empty tree: every search returns -1 / FLT_MAX (kdtree.hpp:296-300)
+            holder.done = true;
+            return;
+        }
         const float4* pts = reinterpret_cast<const float4*>(targets);
         const uint32_t n = (uint32_t)nt;
         cudaStream_t st = q->stream;
@@ -1272,7 +1428,10 @@ int index_build_impl(spx_queue_t q, const float* targets, size_t nt, float cell_
         const OccPlan pl = hhead->plan;
         ix->n = bb.finite;
         L.lv[0].n = bb.finite;
-        if (bb.finite == 0) return;
+        if (bb.finite == 0) {
+            holder.done = true;
+            return;
+        }
 
         float lo[3], ext[3];
         float max_ext = 0.0f;
@@ -1415,7 +1574,9 @@ int index_build_impl(spx_queue_t q, const float* targets, size_t nt, float cell_
         } else {
             ix->levels_knn = L;
         }
-        // no final sync: everything above is ordered on the queue's stream, and so is every search
+        // no final sync: everything above is ordered on the queue's stream, and so is every search on it; users on
+        // other queues wait on `ready` (recorded by the holder)
+        holder.done = true;
     });
 }
 }  // namespace
@@ -1437,6 +1598,7 @@ int spx_index_destroy(spx_index_t index) {
             }
             if (index->occ_dev) cudaFree(index->occ_dev);
         }
+        if (index->ready) cudaEventDestroy(index->ready);
         delete index;
     });
 }
@@ -1535,6 +1697,7 @@ int spx_index_remove_by_flags(spx_index_t index, const uint8_t* flags, const int
             if (index->start[l]) cudaFreeAsync(index->start[l], q->stream);
         }
         if (index->occ_dev) cudaFreeAsync(index->occ_dev, q->stream);
+        if (index->ready) cudaEventDestroy(index->ready);  // (the rebuilt index brings its own)
         *index = *fresh;
         delete fresh;
     });

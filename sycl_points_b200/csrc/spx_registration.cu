@@ -1578,6 +1578,7 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     SPX_REQUIRE(index, "[Registration::align] target_knn (spx_index) is null");
     SPX_REQUIRE(index->q->device == q->device, "[Registration::align] index lives on another device");
     SPX_REQUIRE(index->n_total == nt, "[Registration::align] target_knn was built on a different cloud size");
+    if (index->q != q && index->ready) SPX_CUDA(cudaStreamWaitEvent(st, index->ready, 0));  // built on another queue
     SPX_REQUIRE(ns < (1ull << 31) && nt < (1ull << 31), "[Registration::align] too many points");
     check_reg_loss(P.reg_type, P.robust_loss, "[Registration::align]");
     validate(P, src_covs, tgt_covs, tgt_normals);
@@ -1892,6 +1893,8 @@ void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs,
         SPX_REQUIRE(A.src_points && (A.tgt_points || A.nt == 0), "[Registration::align] null points");
         SPX_REQUIRE(A.target_index, "[Registration::align] target_knn (spx_index) is null");
         SPX_REQUIRE(A.target_index->q->device == q->device, "[Registration::align] index lives on another device");
+        if (A.target_index->q != q && A.target_index->ready)  // built on another queue: ordered behind its build
+            SPX_CUDA(cudaStreamWaitEvent(q->stream, A.target_index->ready, 0));
         SPX_REQUIRE(A.target_index->n_total == A.nt, "[Registration::align] target_knn was built on a different cloud size");
         SPX_REQUIRE(A.ns < (1ull << 31) && A.nt < (1ull << 31), "[Registration::align] too many points");
         validate(Pm, A.src_covs, A.tgt_covs, A.tgt_normals);
