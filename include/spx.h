@@ -346,6 +346,20 @@ SPX_API int spx_gather(spx_queue_t q, const void* src, size_t elem_bytes, const 
  * ascending in idx_out (device int32[min(n, sampling_num)]); apply them with spx_gather.  Synchronises. */
 SPX_API int spx_mixed_random_sampling(spx_queue_t q, spx_rng_t rng, const float* weights, size_t n, size_t sampling_num,
                                       float weighted_ratio, int32_t* idx_out, size_t* m_host);
+/* PreprocessFilter::weighted_random_sampling(source, output, weights, n) —
+ * preprocess_operator/weighted_sampling_operator.hpp:29-96: n points by weighted reservoir keys over the points of
+ * positive weight; SPX_ERR_INVALID_ARGUMENT for negative / non-finite weights, no positive weight, or n larger than
+ * the number of positive weights.  Kept indices ascending.  Synchronises. */
+SPX_API int spx_weighted_random_sampling(spx_queue_t q, spx_rng_t rng, const float* weights, size_t n, size_t sampling_num,
+                                         int32_t* idx_out, size_t* m_host);
+/* PreprocessFilter::farthest_point_sampling(source, output, n) —
+ * preprocess_operator/farthest_point_sampling_operator.hpp:27-94: starting from `first_index` (the reference draws it
+ * with uniform_int_distribution<size_t>(0, N-1) on the operator's mt19937: spx_rng_uniform_index), repeatedly takes the
+ * point farthest from everything selected so far (squared distance over xyzw, ties to the lower index).  One cooperative
+ * launch for the whole selection.  Kept indices ascending (device int32[min(n, sampling_num)]).  Synchronises. */
+SPX_API int spx_rng_uniform_index(spx_rng_t rng, size_t n, size_t* out);
+SPX_API int spx_farthest_point_sampling(spx_queue_t q, const float* points, size_t n, size_t sampling_num,
+                                        size_t first_index, int32_t* idx_out, size_t* m_host);
 /* PreprocessFilter::angle_incidence_filter(source, output, min_angle, max_angle) —
  * preprocess_operator/angle_incidence_filter_operator.hpp:23-111: keep the points whose incidence angle (between the
  * ray from the sensor and the surface normal; normals, or the smallest-eigenvalue direction of covs when normals is

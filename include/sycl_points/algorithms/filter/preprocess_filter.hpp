@@ -1,8 +1,8 @@
-// filter::PreprocessFilter — the two operators that feed the registration path:
-//   box_filter       I/algorithms/filter/preprocess_operator/box_filter_operator.hpp:19-54 (+ common.hpp:15-25)
-//   random_sampling  I/algorithms/filter/preprocess_operator/random_sampling_operator.hpp:15-58
-// Both compact on the device and preserve source order.  The sensor-specific operators of the
-// reference class (polar grid, FPS, angle incidence, intensity ...) are out of scope.
+// filter::PreprocessFilter — I/algorithms/filter/preprocess_filter.hpp and its operators
+// (I/algorithms/filter/preprocess_operator/*.hpp): box filter, uniform / weighted / mixed random sampling, farthest
+// point sampling, angle-of-incidence filter.  Every operator produces the kept indices (libspx) and compacts every
+// attribute the cloud carries on the device, in source order (common/filter_by_flags.hpp:29-57).  As in the reference
+// each sampling operator owns its std::mt19937 (seed 1234; set_random_seed re-seeds all of them).
 #pragma once
 
 #include <cmath>
@@ -21,15 +21,20 @@ public:
     using Ptr = std::shared_ptr<PreprocessFilter>;
 
     PreprocessFilter(const sycl_utils::DeviceQueue& queue) : queue_(queue) {
-        detail::spx_check(spx_rng_create(1234u, &rng_));  // random_sampling_operator.hpp:20
+        for (spx_rng_t* r : {&rng_, &rng_weighted_, &rng_mixed_, &rng_fps_})
+            detail::spx_check(spx_rng_create(1234u, r));  // random_sampling_operator.hpp:20 and siblings
     }
     ~PreprocessFilter() {
-        if (rng_) spx_rng_destroy(rng_);
+        for (spx_rng_t r : {rng_, rng_weighted_, rng_mixed_, rng_fps_})
+            if (r) spx_rng_destroy(r);
     }
     PreprocessFilter(const PreprocessFilter&) = delete;
     PreprocessFilter& operator=(const PreprocessFilter&) = delete;
 
-    void set_random_seed(uint_fast32_t seed) { detail::spx_check(spx_rng_seed(rng_, (uint32_t)seed)); }
+    /// preprocess_filter.hpp:46-51
+    void set_random_seed(uint_fast32_t seed) {
+        for (spx_rng_t r : {rng_, rng_weighted_, rng_mixed_, rng_fps_}) detail::spx_check(spx_rng_seed(r, (uint32_t)seed));
+    }
 
     /// in place
     void box_filter(PointCloudShared& data, float min_distance = 1.0f,
@@ -74,6 +79,65 @@ public:
         this->gather_all(source, output, idx, m);
     }
 
+    /// weighted_sampling_operator.hpp:29-96 (in place / into `output`)
+    void weighted_random_sampling(PointCloudShared& data, const shared_vector<float>& weights, size_t sampling_num) {
+        PointCloudShared out(this->queue_);
+        this->weighted_random_sampling(data, out, weights, sampling_num);
+        data = out;
+    }
+    void weighted_random_sampling(const PointCloudShared& source, PointCloudShared& output,
+                                  const shared_vector<float>& weights, size_t sampling_num) {
+        const size_t N = source.size();
+        if (N <= sampling_num) {
+            output = source;
+            return;
+        }
+        if (weights.size() != N)
+            throw std::invalid_argument("[PreprocessFilter::weighted_random_sampling] weights size must match points");
+        size_t positive = 0;
+        for (size_t i = 0; i < N; ++i) {
+            if (!std::isfinite(weights[i]) || weights[i] < 0.0f)
+                throw std::invalid_argument(
+                    "[PreprocessFilter::weighted_random_sampling] weights must be finite and non-negative");
+            if (weights[i] > 0.0f) ++positive;
+        }
+        if (positive == 0)
+            throw std::invalid_argument("[PreprocessFilter::weighted_random_sampling] at least one weight must be positive");
+        if (sampling_num > positive)
+            throw std::invalid_argument(
+                "[PreprocessFilter::weighted_random_sampling] sampling_num exceeds positive-weight points");
+        shared_vector<int32_t> idx(sampling_num);
+        this->queue_.set_accessed_by_device(idx.data(), sampling_num);
+        size_t m = 0;
+        detail::spx_check(spx_weighted_random_sampling(this->queue_.handle(), rng_weighted_, weights.data(), N, sampling_num,
+                                                       idx.data(), &m));
+        this->gather_all(source, output, idx, m);
+    }
+
+    /// farthest_point_sampling_operator.hpp:27-94 (in place / into `output`)
+    void farthest_point_sampling(PointCloudShared& data, size_t sampling_num) {
+        PointCloudShared out(this->queue_);
+        this->farthest_point_sampling(data, out, sampling_num);
+        data = out;
+    }
+    void farthest_point_sampling(const PointCloudShared& source, PointCloudShared& output, size_t sampling_num) {
+        const size_t N = source.size();
+        if (N <= sampling_num) {
+            output = source;
+            return;
+        }
+        size_t first = 0;
+        detail::spx_check(spx_rng_uniform_index(rng_fps_, N, &first));
+        shared_vector<int32_t> idx(sampling_num);
+        this->queue_.set_accessed_by_device(source.points_ptr(), N);
+        this->queue_.set_accessed_by_device(idx.data(), sampling_num);
+        size_t m = 0;
+        detail::spx_check(spx_farthest_point_sampling(this->queue_.handle(),
+                                                      reinterpret_cast<const float*>(source.points_ptr()), N, sampling_num,
+                                                      first, idx.data(), &m));
+        this->gather_all(source, output, idx, m);
+    }
+
     /// mixed_random_sampling_operator.hpp:29-107 (in place / into `output`)
     void mixed_random_sampling(PointCloudShared& data, const shared_vector<float>& weights, size_t sampling_num,
                                float weighted_ratio) {
@@ -99,7 +163,7 @@ public:
         shared_vector<int32_t> idx(sampling_num);
         this->queue_.set_accessed_by_device(idx.data(), sampling_num);
         size_t m = 0;
-        detail::spx_check(spx_mixed_random_sampling(this->queue_.handle(), rng_, weights.data(), N, sampling_num,
+        detail::spx_check(spx_mixed_random_sampling(this->queue_.handle(), rng_mixed_, weights.data(), N, sampling_num,
                                                     weighted_ratio, idx.data(), &m));
         this->gather_all(source, output, idx, m);
     }
@@ -164,7 +228,7 @@ private:
     }
 
     sycl_utils::DeviceQueue queue_;
-    spx_rng_t rng_ = nullptr;
+    spx_rng_t rng_ = nullptr, rng_weighted_ = nullptr, rng_mixed_ = nullptr, rng_fps_ = nullptr;
 };
 
 }  // namespace filter

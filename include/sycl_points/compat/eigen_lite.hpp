@@ -73,6 +73,33 @@ struct BlockRef {
     Matrix<T, BR, BC> normalized() const { return eval().normalized(); }
 };
 
+/// `m << a, b, c, ...;` — coefficients in row-major order, as Eigen's comma initialiser
+template <typename T, int R, int C>
+struct CommaInit {
+    Matrix<T, R, C>& m;
+    int n;
+    CommaInit& operator,(T v) {
+        if (n < R * C) m(n / C, n % C) = v;
+        ++n;
+        return *this;
+    }
+};
+/// writable view of the main diagonal
+template <typename T, int R, int C>
+struct DiagRef {
+    Matrix<T, R, C>& m;
+    static constexpr int N = R < C ? R : C;
+    DiagRef& operator=(const Matrix<T, N, 1>& v) {
+        for (int i = 0; i < N; ++i) m(i, i) = v(i);
+        return *this;
+    }
+    operator Matrix<T, N, 1>() const {
+        Matrix<T, N, 1> r;
+        for (int i = 0; i < N; ++i) r(i) = m(i, i);
+        return r;
+    }
+};
+
 template <typename T, int R, int C>
 struct Matrix {
     static constexpr int Rows = R, Cols = C, Size = R * C;
@@ -216,6 +243,26 @@ struct Matrix {
     BlockRef<T, R, C, BR, BC> block(int i0, int j0) {
         return BlockRef<T, R, C, BR, BC>{*this, i0, j0};
     }
+    template <int BR, int BC>
+    Matrix<T, BR, BC> topLeftCorner() const { return block<BR, BC>(0, 0); }
+    template <int BR, int BC>
+    BlockRef<T, R, C, BR, BC> topLeftCorner() { return block<BR, BC>(0, 0); }
+    CommaInit<T, R, C> operator<<(T v) {
+        (*this)(0, 0) = v;
+        return CommaInit<T, R, C>{*this, 1};
+    }
+    DiagRef<T, R, C> diagonal() { return DiagRef<T, R, C>{*this}; }
+    Matrix<T, (R < C ? R : C), 1> diagonal() const {
+        Matrix<T, (R < C ? R : C), 1> r;
+        for (int i = 0; i < (R < C ? R : C); ++i) r(i) = (*this)(i, i);
+        return r;
+    }
+    Matrix eval() const { return *this; }
+    template <int N>
+    BlockRef<T, R, C, N, 1> head() {
+        static_assert(C == 1, "head<N>() of a column vector");
+        return BlockRef<T, R, C, N, 1>{*this, 0, 0};
+    }
     Matrix<T, 1, C> row(int i) const { return block<1, C>(i, 0); }
     Matrix<T, R, 1> col(int j) const { return block<R, 1>(0, j); }
     BlockRef<T, R, C, 1, C> row(int i) { return BlockRef<T, R, C, 1, C>{*this, i, 0}; }
@@ -296,6 +343,7 @@ struct Isometry3f {
     }
     void set_linear(const Matrix3f& R) { M.set_block<3, 3>(0, 0, R); }
     Isometry3f operator*(const Isometry3f& o) const { return Isometry3f(M * o.M); }
+    Matrix4f operator*(const Matrix4f& o) const { return M * o; }
     Vector3f operator*(const Vector3f& p) const { return linear() * p + translation(); }
     Isometry3f inverse() const {
         const Matrix3f Rt = linear().transpose();
@@ -307,6 +355,11 @@ struct Isometry3f {
     const float* data() const { return M.data(); }
     float* data() { return M.data(); }
 };
+
+/// Eigen::Transform<float, 3, Eigen::Isometry>: the only transform the path uses
+template <typename T, int Dim, int Mode, int Options = 0>
+using Transform = Isometry3f;
+constexpr int Isometry = 1;
 
 /// Eigen::AngleAxisf: rotation by `angle` about the unit vector `axis` (Rodrigues)
 struct AngleAxisf {

@@ -43,6 +43,16 @@ struct PointCloudCPU {
     bool has_timestamps() const {
         return this->timestamp_offsets != nullptr && this->timestamp_offsets->size() == this->points->size();
     }
+
+    /// point_cloud.hpp:61-69
+    void update_end_time() {
+        if (this->timestamp_offsets && !this->timestamp_offsets->empty()) {
+            const auto max_offset = *std::max_element(this->timestamp_offsets->begin(), this->timestamp_offsets->end());
+            this->end_time_ms = this->start_time_ms + static_cast<double>(max_offset);
+        } else {
+            this->end_time_ms = this->start_time_ms;
+        }
+    }
 };
 
 /// point_cloud.hpp:73-476

@@ -171,6 +171,20 @@ class Rng:
         lib().orc_rng_box_points(self._g, C.c_size_t(n), _f(lo), _f(hi), _f(out))
         return out
 
+    def weighted_random_sampling_flags(self, weights, num: int) -> np.ndarray:
+        w = np.ascontiguousarray(weights, np.float32)
+        flags = np.empty(len(w), np.uint8)
+        lib().orc_weighted_random_sampling_flags(self._g, _f(w), C.c_size_t(len(w)), C.c_size_t(num),
+                                                 flags.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return flags
+
+    def farthest_point_sampling_flags(self, points, num: int) -> np.ndarray:
+        p = _pts(points)
+        flags = np.empty(len(p), np.uint8)
+        lib().orc_farthest_point_sampling_flags(self._g, _f(p), C.c_size_t(len(p)), C.c_size_t(num),
+                                                flags.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return flags
+
     def mixed_random_sampling_flags(self, weights, num: int, weighted_ratio: float) -> np.ndarray:
         w = np.ascontiguousarray(weights, np.float32)
         flags = np.empty(len(w), np.uint8)

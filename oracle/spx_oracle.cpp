@@ -1259,6 +1259,60 @@ void orc_mixed_random_sampling_flags(void* g, const float* weights, size_t n, si
     }
 }
 
+// preprocess_operator/weighted_sampling_operator.hpp:29-96 (weights already validated by the caller)
+void orc_weighted_random_sampling_flags(void* g, const float* weights, size_t n, size_t sampling_num, uint8_t* flags_out) {
+    std::mt19937& gen = *static_cast<std::mt19937*>(g);
+    if (n <= sampling_num) {
+        std::fill(flags_out, flags_out + n, (uint8_t)1);
+        return;
+    }
+    std::fill(flags_out, flags_out + n, (uint8_t)0);
+    using KI = std::pair<float, size_t>;
+    std::priority_queue<KI, std::vector<KI>, std::greater<KI>> selected;
+    std::uniform_real_distribution<float> wd(std::numeric_limits<float>::min(), 1.0f);
+    for (size_t i = 0; i < n; ++i) {
+        if (weights[i] <= 0.0f) continue;
+        const float key = std::log(wd(gen)) / weights[i];
+        if (selected.size() < sampling_num) {
+            selected.emplace(key, i);
+            continue;
+        }
+        if (selected.top().first < key) {
+            selected.pop();
+            selected.emplace(key, i);
+        }
+    }
+    while (!selected.empty()) {
+        flags_out[selected.top().second] = 1;
+        selected.pop();
+    }
+}
+
+// preprocess_operator/farthest_point_sampling_operator.hpp:27-94
+void orc_farthest_point_sampling_flags(void* g, const float* pts, size_t n, size_t sampling_num, uint8_t* flags_out) {
+    std::mt19937& gen = *static_cast<std::mt19937*>(g);
+    if (n <= sampling_num) {
+        std::fill(flags_out, flags_out + n, (uint8_t)1);
+        return;
+    }
+    std::fill(flags_out, flags_out + n, (uint8_t)0);
+    std::vector<float> dist(n, FMAX);
+    std::uniform_int_distribution<size_t> d0(0, n - 1);
+    size_t sel = d0(gen);
+    flags_out[sel] = 1;
+    for (size_t it = 1; it < sampling_num; ++it) {
+        const float* c = pts + 4 * sel;
+        for (size_t i = 0; i < n; ++i) {
+            const float* p = pts + 4 * i;
+            const float dx = p[0] - c[0], dy = p[1] - c[1], dz = p[2] - c[2], dw = p[3] - c[3];
+            const float d = std::fma(dw, dw, std::fma(dz, dz, std::fma(dy, dy, dx * dx)));
+            dist[i] = std::fmin(dist[i], d);
+        }
+        sel = (size_t)(std::max_element(dist.begin(), dist.end()) - dist.begin());
+        flags_out[sel] = 1;
+    }
+}
+
 // preprocess_operator/angle_incidence_filter_operator.hpp:57-103 (normals, or extract_normal of covs when normals == NULL)
 void orc_angle_incidence_flags(const float* pts, const float* normals, const float* covs, size_t n, float min_angle,
                                float max_angle, uint8_t* flags_out) {

@@ -216,6 +216,9 @@ def lib() -> C.CDLL:
         "spx_rng_destroy": (C.c_int, [vp]),
         "spx_random_sampling": (C.c_int, [vp, vp, sz, sz, i32p, C.POINTER(C.c_size_t)]),
         "spx_gather": (C.c_int, [vp, vp, sz, i32p, sz, vp]),
+        "spx_weighted_random_sampling": (C.c_int, [vp, vp, f32p, sz, sz, i32p, C.POINTER(C.c_size_t)]),
+        "spx_rng_uniform_index": (C.c_int, [vp, sz, C.POINTER(C.c_size_t)]),
+        "spx_farthest_point_sampling": (C.c_int, [vp, f32p, sz, sz, sz, i32p, C.POINTER(C.c_size_t)]),
         "spx_mixed_random_sampling": (C.c_int, [vp, vp, f32p, sz, sz, C.c_float, i32p, C.POINTER(C.c_size_t)]),
         "spx_angle_incidence_indices": (C.c_int, [vp, f32p, f32p, f32p, sz, C.c_float, C.c_float, i32p,
                                                   C.POINTER(C.c_size_t)]),

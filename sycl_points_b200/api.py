@@ -813,24 +813,31 @@ def _trim(a: DeviceArray | None, m: int):
 
 
 class PreprocessFilter:
-    """filter::PreprocessFilter — only box_filter is on the path (preprocess_filter.hpp, box_filter_operator.hpp)."""
+    """filter::PreprocessFilter (preprocess_filter.hpp + preprocess_operator/*.hpp): box filter, uniform / weighted /
+    mixed random sampling, farthest point sampling, angle-of-incidence filter.  As in the reference every sampling
+    operator owns its std::mt19937 (seed 1234); set_random_seed re-seeds all of them (preprocess_filter.hpp:46-51)."""
+
+    _RNGS = ("_rng", "_rng_weighted", "_rng_mixed", "_rng_fps")
 
     def __init__(self, queue: DeviceQueue):
         self.queue = queue
-        h = C.c_void_p()
-        check(_lib.lib().spx_rng_create(1234, C.byref(h)))  # random_sampling_operator.hpp:20
-        self._rng = h
+        for name in self._RNGS:
+            h = C.c_void_p()
+            check(_lib.lib().spx_rng_create(1234, C.byref(h)))  # random_sampling_operator.hpp:20 and siblings
+            setattr(self, name, h)
 
     def __del__(self):
         try:
-            if getattr(self, "_rng", None):
-                _lib.lib().spx_rng_destroy(self._rng)
-                self._rng = None
+            for name in self._RNGS:
+                if getattr(self, name, None):
+                    _lib.lib().spx_rng_destroy(getattr(self, name))
+                    setattr(self, name, None)
         except Exception:
             pass
 
     def set_random_seed(self, seed: int):
-        check(_lib.lib().spx_rng_seed(self._rng, int(seed)))
+        for name in self._RNGS:
+            check(_lib.lib().spx_rng_seed(getattr(self, name), int(seed)))
 
     _ATTRS = ("points", "covs", "normals", "rgb", "intensities", "timestamp_offsets")
 
@@ -895,11 +902,45 @@ class PreprocessFilter:
         idx = DeviceArray(self.queue, (sampling_num,), np.int32)
         m = C.c_size_t()
         try:
-            check(_lib.lib().spx_mixed_random_sampling(self.queue.handle, self._rng, w.ptr, n, sampling_num,
+            check(_lib.lib().spx_mixed_random_sampling(self.queue.handle, self._rng_mixed, w.ptr, n, sampling_num,
                                                        float(weighted_ratio), idx.ptr, C.byref(m)))
         except SpxInvalidArgument as e:
             raise ValueError(str(e)) from e
         self._last_indices = idx
+        return self._gather_all(cloud, idx, int(m.value), output)
+
+    def weighted_random_sampling(self, cloud: PointCloudShared, weights, sampling_num: int,
+                                 output: PointCloudShared | None = None) -> PointCloudShared:
+        """PreprocessFilter::weighted_random_sampling (weighted_sampling_operator.hpp:29-96)."""
+        n = cloud.size()
+        if n <= sampling_num:
+            return self.random_sampling(cloud, sampling_num, output)  # keep-all branch: copy, no draw
+        w = weights if isinstance(weights, DeviceArray) else DeviceArray.from_host(self.queue,
+                                                                                  np.ascontiguousarray(weights, np.float32))
+        if len(w) != n:
+            raise ValueError("[PreprocessFilter::weighted_random_sampling] weights size must match points")
+        idx = DeviceArray(self.queue, (sampling_num,), np.int32)
+        m = C.c_size_t()
+        try:
+            check(_lib.lib().spx_weighted_random_sampling(self.queue.handle, self._rng_weighted, w.ptr, n, sampling_num,
+                                                          idx.ptr, C.byref(m)))
+        except SpxInvalidArgument as e:
+            raise ValueError(str(e)) from e
+        return self._gather_all(cloud, idx, int(m.value), output)
+
+    def farthest_point_sampling(self, cloud: PointCloudShared, sampling_num: int,
+                                output: PointCloudShared | None = None) -> PointCloudShared:
+        """PreprocessFilter::farthest_point_sampling (farthest_point_sampling_operator.hpp:27-94): one cooperative
+        launch for the whole selection."""
+        n = cloud.size()
+        if n <= sampling_num:
+            return self.random_sampling(cloud, sampling_num, output)
+        first = C.c_size_t()
+        check(_lib.lib().spx_rng_uniform_index(self._rng_fps, n, C.byref(first)))
+        idx = DeviceArray(self.queue, (sampling_num,), np.int32)
+        m = C.c_size_t()
+        check(_lib.lib().spx_farthest_point_sampling(self.queue.handle, cloud.points.ptr, n, sampling_num, first.value,
+                                                     idx.ptr, C.byref(m)))
         return self._gather_all(cloud, idx, int(m.value), output)
 
     def angle_incidence_filter(self, cloud: PointCloudShared, min_angle: float, max_angle: float,

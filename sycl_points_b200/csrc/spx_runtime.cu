@@ -556,6 +556,73 @@ int spx_mixed_random_sampling(spx_queue_t q, spx_rng_t rng, const float* weights
     });
 }
 
+// weighted_sampling_operator.hpp:29-96: sampling_num points by weighted reservoir keys log(u) / w over the points of
+// positive weight (std::priority_queue with std::greater on (key, index), the smallest key evicted first).
+int spx_weighted_random_sampling(spx_queue_t q, spx_rng_t rng, const float* weights, size_t n, size_t sampling_num,
+                                 int32_t* idx_out, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && rng && m_host, "[PreprocessFilter::weighted_random_sampling] null argument");
+        SPX_REQUIRE(n < (1ull << 31), "[PreprocessFilter::weighted_random_sampling] too many points");
+        DeviceGuard g(q->device);
+        std::vector<int32_t> sel;
+        if (n <= sampling_num) {
+            sel.resize(n);
+            std::iota(sel.begin(), sel.end(), 0);
+        } else {
+            SPX_REQUIRE(weights, "[PreprocessFilter::weighted_random_sampling] weights size must match points");
+            std::vector<float> w(n);
+            SPX_CUDA(cudaMemcpyAsync(w.data(), weights, n * sizeof(float), cudaMemcpyDefault, q->stream));
+            q->sync();
+            size_t positive = 0;
+            for (size_t i = 0; i < n; ++i) {
+                SPX_REQUIRE(std::isfinite(w[i]) && w[i] >= 0.0f,
+                            "[PreprocessFilter::weighted_random_sampling] weights must be finite and non-negative");
+                if (w[i] > 0.0f) ++positive;
+            }
+            SPX_REQUIRE(positive > 0, "[PreprocessFilter::weighted_random_sampling] at least one weight must be positive");
+            SPX_REQUIRE(sampling_num <= positive,
+                        "[PreprocessFilter::weighted_random_sampling] sampling_num exceeds positive-weight points");
+            using KeyIndexPair = std::pair<float, size_t>;
+            std::priority_queue<KeyIndexPair, std::vector<KeyIndexPair>, std::greater<KeyIndexPair>> selected;
+            std::uniform_real_distribution<float> dist(std::numeric_limits<float>::min(), 1.0f);
+            for (size_t i = 0; i < n; ++i) {
+                if (w[i] <= 0.0f) continue;
+                const float key = std::log(dist(rng->mt)) / w[i];
+                if (selected.size() < sampling_num) {
+                    selected.emplace(key, i);
+                    continue;
+                }
+                if (selected.top().first < key) {
+                    selected.pop();
+                    selected.emplace(key, i);
+                }
+            }
+            while (!selected.empty()) {
+                sel.push_back((int32_t)selected.top().second);
+                selected.pop();
+            }
+            std::sort(sel.begin(), sel.end());
+        }
+        *m_host = sel.size();
+        if (sel.empty()) return;
+        SPX_REQUIRE(idx_out, "[PreprocessFilter::weighted_random_sampling] null output");
+        int32_t* pin = static_cast<int32_t*>(q->pinned_get(sel.size() * sizeof(int32_t)));
+        std::memcpy(pin, sel.data(), sel.size() * sizeof(int32_t));
+        SPX_CUDA(cudaMemcpyAsync(idx_out, pin, sel.size() * sizeof(int32_t), cudaMemcpyDefault, q->stream));
+        q->sync();
+    });
+}
+
+// the first point of farthest_point_sampling: uniform_int_distribution<size_t>(0, N - 1) on the operator's mt19937
+// (farthest_point_sampling_operator.hpp:51-53)
+int spx_rng_uniform_index(spx_rng_t rng, size_t n, size_t* out) {
+    return guard([&] {
+        SPX_REQUIRE(rng && out && n > 0, "[spx_rng_uniform_index] bad argument");
+        std::uniform_int_distribution<size_t> dist(0, n - 1);
+        *out = dist(rng->mt);
+    });
+}
+
 // ------------------------------------------------------------------ multi-GPU mailboxes
 int spx_comm_create(spx_queue_t q, int rank, int world, spx_comm_t* out) {
     return guard([&] {

@@ -13,6 +13,8 @@
 //      sum.w < min_voxel_count (:204), stream-compact to ascending-key output.
 #include <cmath>
 
+#include <cooperative_groups.h>
+
 #include "spx_scan.cuh"
 #include "spx_math.cuh"
 
@@ -798,6 +800,77 @@ __global__ void __launch_bounds__(VX_THREADS) angle_flag_kernel(const float4* __
     flags[i] = keep;
 }
 
+// farthest_point_sampling — preprocess_operator/farthest_point_sampling_operator.hpp:27-94.  The reference runs one
+// kernel (min-distance update) and one host std::max_element per selected point; here the whole selection is ONE
+// cooperative launch: per round every block updates its slice against the point selected last, reduces
+// (distance, lowest index) to a 64-bit key, the grid meets once and every block reads the blocks' keys to agree on
+// the next point.  Same arithmetic (dot<4> fma chain over the xyzw difference, eigen_utils.hpp:245-253,333-335) and
+// the same tie rule (std::max_element: the first of equal maxima), so the selected set is the reference's.
+constexpr int FPS_THREADS = 256;
+__global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float4* __restrict__ pts, uint32_t n, uint32_t first,
+                                                          uint32_t rounds, float* __restrict__ dist_sq,
+                                                          uint32_t* __restrict__ flags,
+                                                          unsigned long long* __restrict__ block_keys /*[2][gridDim.x]*/) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long s_key[FPS_THREADS / 32];
+    __shared__ uint32_t s_sel;
+    const uint32_t stride = gridDim.x * FPS_THREADS;
+    for (uint32_t i = blockIdx.x * FPS_THREADS + threadIdx.x; i < n; i += stride) {
+        dist_sq[i] = FLT_MAX;
+        flags[i] = 0u;
+    }
+    uint32_t sel = first;
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[sel] = 1u;  // (each thread initialises only its own slots above;
+    grid.sync();                                               //  the selected flag is re-asserted after the barrier)
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[sel] = 1u;
+    for (uint32_t it = 1; it < rounds; ++it) {
+        const float4 c = __ldg(pts + sel);
+        unsigned long long best = 0ull;
+        for (uint32_t i = blockIdx.x * FPS_THREADS + threadIdx.x; i < n; i += stride) {
+            const float4 p = __ldg(pts + i);
+            const float dx = __fsub_rn(p.x, c.x), dy = __fsub_rn(p.y, c.y), dz = __fsub_rn(p.z, c.z), dw = __fsub_rn(p.w, c.w);
+            const float d = __fmaf_rn(dw, dw, __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+            const float m = fminf(dist_sq[i], d);
+            dist_sq[i] = m;
+            // larger distance first, then the LOWER index: key = dist bits (non-negative floats order as integers;
+            // a NaN distance — from a non-finite point — never wins, as in std::max_element's operator<) | ~index
+            const unsigned long long key = ((unsigned long long)__float_as_uint(m == m ? m : 0.0f) << 32) | (0xffffffffu - i);
+            best = key > best ? key : best;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = best;
+        __syncthreads();
+        unsigned long long* keys = block_keys + (size_t)(it & 1u) * gridDim.x;
+        if (threadIdx.x == 0) {
+            unsigned long long b = s_key[0];
+            for (int w = 1; w < FPS_THREADS / 32; ++w) b = s_key[w] > b ? s_key[w] : b;
+            keys[blockIdx.x] = b;
+        }
+        grid.sync();
+        if (threadIdx.x < 32) {
+            unsigned long long b = 0ull;
+            for (uint32_t j = threadIdx.x; j < gridDim.x; j += 32) {
+                const unsigned long long kj = keys[j];
+                b = kj > b ? kj : b;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+                b = other > b ? other : b;
+            }
+            if (threadIdx.x == 0) s_sel = 0xffffffffu - (uint32_t)(b & 0xffffffffull);
+        }
+        __syncthreads();
+        sel = s_sel;
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[sel] = 1u;
+    }
+}
+
 // order given by idx: dst[j] = src[idx[j]], in 4-byte words (points 4 words, covariances 16)
 __global__ void __launch_bounds__(VX_THREADS) gather_words_kernel(const uint32_t* __restrict__ src, int words,
                                                                   const int32_t* __restrict__ idx, size_t total,
@@ -1261,6 +1334,46 @@ int spx_angle_incidence_indices(spx_queue_t q, const float* points, const float*
                                                                        reinterpret_cast<const float4*>(normals), covs, n,
                                                                        min_cos, max_cos, flags);
         SPX_LAUNCH_CHECK();
+        exclusive_scan_u32(st, flags, pos, n, scan_tmp, total_dev);
+        compact_index_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(flags, pos, n, idx_out);
+        SPX_LAUNCH_CHECK();
+        uint32_t* htotal = static_cast<uint32_t*>(q->pinned_get(64));
+        SPX_CUDA(cudaMemcpyAsync(htotal, total_dev, 4, cudaMemcpyDeviceToHost, st));
+        q->sync();
+        *m_host = *htotal;
+    });
+}
+
+int spx_farthest_point_sampling(spx_queue_t q, const float* points, size_t n_in, size_t sampling_num, size_t first_index,
+                                int32_t* idx_out, size_t* m_host) {
+    return guard([&] {
+        SPX_REQUIRE(q && m_host, "[PreprocessFilter::farthest_point_sampling] null argument");
+        SPX_REQUIRE(n_in < (1ull << 31), "[PreprocessFilter::farthest_point_sampling] too many points");
+        *m_host = 0;
+        if (n_in == 0 || sampling_num == 0) return;
+        SPX_REQUIRE(points && idx_out, "[PreprocessFilter::farthest_point_sampling] null pointer");
+        SPX_REQUIRE(first_index < n_in, "[PreprocessFilter::farthest_point_sampling] first index out of range");
+        DeviceGuard dg(q->device);
+        cudaStream_t st = q->stream;
+        const uint32_t n = (uint32_t)n_in;
+        static int per_sm = 0;
+        if (!per_sm) SPX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fps_kernel, FPS_THREADS, 0));
+        const unsigned blocks = (unsigned)std::min<size_t>(div_up(n, FPS_THREADS), (size_t)std::max(per_sm, 1) * q->sm_count);
+        q->arena_reset();
+        q->arena_reserve((size_t)n * 12 + scan_scratch_elems(n) * 4 + (size_t)blocks * 16 + 8192);
+        float* dist_sq = q->take<float>(n);
+        uint32_t* flags = q->take<uint32_t>(n);
+        uint32_t* pos = q->take<uint32_t>(n);
+        uint32_t* scan_tmp = q->take<uint32_t>(scan_scratch_elems(n));
+        unsigned long long* block_keys = q->take<unsigned long long>((size_t)blocks * 2);
+        uint32_t* total_dev = q->take<uint32_t>(16);
+        const float4* pts = reinterpret_cast<const float4*>(points);
+        uint32_t first = (uint32_t)first_index, rounds = (uint32_t)std::min<size_t>(sampling_num, n_in);
+        uint32_t nn = n;
+        void* args[] = {(void*)&pts, (void*)&nn, (void*)&first, (void*)&rounds, (void*)&dist_sq, (void*)&flags,
+                        (void*)&block_keys};
+        SPX_CUDA(cudaLaunchCooperativeKernel((const void*)fps_kernel, dim3(blocks), dim3(FPS_THREADS), args, 0, st));
+        count_launch();
         exclusive_scan_u32(st, flags, pos, n, scan_tmp, total_dev);
         compact_index_kernel<<<div_up(n, VX_THREADS), VX_THREADS, 0, st>>>(flags, pos, n, idx_out);
         SPX_LAUNCH_CHECK();

@@ -93,7 +93,7 @@ def test_example_registration_on_bundled_pair(example_exe, bundled, tmp_path):
     assert "7. Registration" in r.stdout
 
 
-REF_TESTS = ["test_kdtree", "test_registration_pipeline", "test_downsampling_filters", "test_voxel_hash_map"]
+REF_TESTS = ["test_kdtree", "test_registration_pipeline", "test_downsampling_filters", "test_voxel_hash_map", "test_relative_pose_deskew", "test_preprocess_filter"]
 
 
 @pytest.mark.gpu

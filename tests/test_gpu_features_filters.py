@@ -552,3 +552,40 @@ def test_angle_incidence_filter_matches_oracle(spx, q, bundled):
         f.angle_incidence_filter(cloud, 0.5, 0.4)
     with pytest.raises(RuntimeError):
         f.angle_incidence_filter(spx.PointCloudShared(q, tgt), 0.0, 1.0)
+
+
+def test_weighted_sampling_and_fps_match_oracle(spx, q, bundled):
+    """weighted_random_sampling (weighted_sampling_operator.hpp:29-96) and farthest_point_sampling
+    (farthest_point_sampling_operator.hpp:27-94; ONE cooperative launch here, a kernel + a host max_element per point
+    in the reference): the selected sets equal the oracle's, each operator on its own mt19937(1234) stream."""
+    pts = bundled["source_ds"]
+    n = len(pts)
+    cloud = spx.PointCloudShared(q, pts)
+    cloud.set_intensities(np.arange(n, dtype=np.float32))
+    f = spx.PreprocessFilter(q)
+    w = np.random.default_rng(4).uniform(0, 1, n).astype(np.float32)
+    w[::7] = 0.0
+    rw, rf, ru = oracle.Rng(1234), oracle.Rng(1234), oracle.Rng(1234)
+    for num in (700, 700, 33):
+        out = f.weighted_random_sampling(cloud, w, num)
+        keep = rw.weighted_random_sampling_flags(w, num).astype(bool)
+        assert keep.sum() == num and not keep[::7].any()
+        assert np.array_equal(out.points_host(), pts[keep])
+    for num in (256, 40):
+        out = f.farthest_point_sampling(cloud, num)
+        keep = rf.farthest_point_sampling_flags(pts, num).astype(bool)
+        assert out.size() == keep.sum() == num
+        assert np.array_equal(out.points_host(), pts[keep])
+        assert np.array_equal(out.intensities.download(), np.arange(n, dtype=np.float32)[keep])
+    # the uniform sampler's stream was not touched by the other operators
+    assert np.array_equal(f.random_sampling(cloud, 100).points_host(), pts[ru.random_sampling_flags(n, 100).astype(bool)])
+    # duplicates: once every distinct point is taken the maximum distance is 0 and nothing new is added
+    dup = np.repeat(pts[:5], 4, axis=0)
+    dcloud = spx.PointCloudShared(q, dup)
+    got = spx.PreprocessFilter(q).farthest_point_sampling(dcloud, 12)
+    want = oracle.Rng(1234).farthest_point_sampling_flags(dup, 12).astype(bool)
+    assert np.array_equal(got.points_host(), dup[want]) and got.size() == want.sum() <= 12
+    with pytest.raises(ValueError):
+        f.weighted_random_sampling(cloud, np.zeros(n, np.float32), 10)
+    with pytest.raises(ValueError):
+        f.weighted_random_sampling(cloud, np.where(np.arange(n) < 5, 1.0, 0.0).astype(np.float32), 10)
