@@ -11,7 +11,7 @@ REF_TESTS = "/root/reference/cpp/tests"
 BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
 LIBDIR = os.path.join(ROOT, "sycl_points_b200")
 # the reference test files whose whole API surface is inside this repo's scope
-SOURCES = ["test_kdtree", "test_registration_pipeline", "test_downsampling_filters", "test_voxel_hash_map", "test_relative_pose_deskew", "test_preprocess_filter"]
+SOURCES = ["test_kdtree", "test_registration_pipeline", "test_downsampling_filters", "test_voxel_hash_map", "test_relative_pose_deskew", "test_preprocess_filter", "test_octree"]
 
 
 def exe_path(name):

@@ -93,18 +93,23 @@ def test_example_registration_on_bundled_pair(example_exe, bundled, tmp_path):
     assert "7. Registration" in r.stdout
 
 
-REF_TESTS = ["test_kdtree", "test_registration_pipeline", "test_downsampling_filters", "test_voxel_hash_map", "test_relative_pose_deskew", "test_preprocess_filter"]
+REF_TESTS = ["test_kdtree", "test_registration_pipeline", "test_downsampling_filters", "test_voxel_hash_map", "test_relative_pose_deskew", "test_preprocess_filter", "test_octree"]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", REF_TESTS)
-def test_reference_gtest_source_passes_on_libspx(name):
+def test_reference_gtest_source_passes_on_libspx(name, bundled, tmp_path):
     """The reference's own cpp/tests/<name>.cpp, compiled UNMODIFIED against include/ + libspx.so through
     tests/cpp/gtest_shim (built by __graft_entry__.build() where /root/reference exists; the binary travels to
     the GPU box): every reference-held assertion runs on the CUDA path."""
     exe = os.path.join(BUILD, "ref_" + name)
     if not os.path.exists(exe):
         pytest.skip("prebuilt reference test binary is absent (no /root/reference at build time)")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    # test_octree.cpp looks for data/target.ply and data/source.ply relative to its working directory (the reference's
+    # bundled scans; /root/reference does not exist on the GPU box): it gets the committed fixture clouds there
+    (tmp_path / "data").mkdir()
+    write_ply(tmp_path / "data" / "target.ply", bundled["target_ds"])
+    write_ply(tmp_path / "data" / "source.ply", bundled["source_ds"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0, (r.stdout[-4000:], r.stderr[-2000:])
     assert " 0 failed" in r.stdout and "[  FAILED  ]" not in r.stdout
