@@ -44,12 +44,20 @@ public:
     /// registration.hpp:105-114
     Registration(const sycl_utils::DeviceQueue& queue, const RegistrationParams& params = RegistrationParams())
         : params_(params), queue_(queue) {
-        if (params.degenerate_reg.enable || params.map_prior.enable)
-            throw std::runtime_error(
-                "[Registration::Registration] degenerate_reg / map_prior are not built in libspx (default-off "
-                "add-ons outside the hot path)");
         const spx_registration_params p = to_c(params);
         detail::spx_check(spx_registration_create(queue.handle(), &p, &this->handle_));
+        const spx_registration_addons a = addons_of(params);  // registration.hpp:112-113
+        detail::spx_check(spx_registration_set_addons(this->handle_, &a));
+    }
+
+    /// registration.hpp:124-126: arms the MAP prior of the next align from the previous result and the predicted pose
+    void set_map_prior_state(const RegistrationResult& prev_result, const Eigen::Isometry3f& T_pred) {
+        spx_registration_result R{};
+        for (int i = 0; i < 16; ++i) R.T[i] = prev_result.T.matrix().data()[i];
+        for (int i = 0; i < 36; ++i) R.H_raw[i] = prev_result.H_raw.data()[i];
+        R.error_raw = prev_result.error_raw;
+        R.inlier = prev_result.inlier;
+        detail::spx_check(spx_registration_set_map_prior_state(this->handle_, &R, T_pred.matrix().data(), nullptr, nullptr));
     }
     Registration(const sycl_utils::DeviceQueue& queue, const RegistrationFactorParams& params)
         : Registration(queue, RegistrationParams(params)) {}
@@ -108,13 +116,19 @@ public:
         detail::spx_check(spx_queue_sync(this->queue_.handle()));
     }
 
-    /// registration.hpp:312-331 (degenerate regularisation is not built: both overloads are raw)
+    /// registration.hpp:312-323: the raw linearisation, degenerate-regularised relative to `initial_pose`
     LinearizedResult compute_linearized_result(const PointCloudShared& source, const PointCloudShared& target,
                                                const knn::KNNBase& target_knn, const TransformMatrix& pose,
-                                               const TransformMatrix& /*initial_pose*/,
+                                               const TransformMatrix& initial_pose,
                                                const ExecutionOptions& options = ExecutionOptions()) {
         target_knn.nearest_neighbor_search_async(source, this->neighbors_, {}, pose).wait_and_throw();
-        return this->linearize(source, target, pose, this->scale_of(options));
+        LinearizedResult lin = this->linearize(source, target, pose, this->scale_of(options));
+        if (this->params_.degenerate_reg.type != DegenerateRegularizationType::none) {
+            const spx_registration_addons a = addons_of(this->params_);
+            detail::spx_check(spx_degenerate_regularize(&a, lin.H.data(), lin.b.data(), lin.inlier, pose.data(),
+                                                        initial_pose.data()));
+        }
+        return lin;
     }
     LinearizedResult compute_linearized_result(const PointCloudShared& source, const PointCloudShared& target,
                                                const knn::KNNBase& target_knn, const TransformMatrix& pose,
@@ -131,6 +145,21 @@ public:
 
 private:
     static const float* fptr(const void* p) { return static_cast<const float*>(p); }
+
+    static spx_registration_addons addons_of(const RegistrationParams& P) {
+        spx_registration_addons a;
+        spx_default_registration_addons(&a);
+        a.degenerate_type = P.degenerate_reg.type == DegenerateRegularizationType::nl_reg ? 1 : 0;
+        a.rot_eigenvalue_threshold = P.degenerate_reg.rot_eigenvalue_threshold;
+        a.trans_eigenvalue_threshold = P.degenerate_reg.trans_eigenvalue_threshold;
+        a.base_factor = P.degenerate_reg.base_factor;
+        a.map_prior_enabled = P.map_prior.enabled ? 1 : 0;
+        a.rot_vel_sigma = P.map_prior.rot_vel_sigma;
+        a.trans_vel_sigma = P.map_prior.trans_vel_sigma;
+        a.rot_base_sigma = P.map_prior.rot_base_sigma;
+        a.trans_base_sigma = P.map_prior.trans_base_sigma;
+        return a;
+    }
 
     static spx_registration_params to_c(const RegistrationParams& P) {
         spx_registration_params p;

@@ -1,7 +1,6 @@
 // Registration parameter structs — I/algorithms/registration/registration_params.hpp:17-114, same
-// names and defaults.  GenZ and the rotation constraint are built; the default-off add-ons whose
-// kernels are out of scope (degenerate regularisation, MAP prior: DESIGN.md §7) keep their fields so
-// that configuration code compiles; enabling one makes Registration's constructor throw.
+// names and defaults, including the solver add-ons' parameter structs (degenerate_regularization.hpp:14-40,
+// map_prior.hpp:15-21), which the reference declares in their own headers.
 #pragma once
 
 #include <algorithm>
@@ -33,11 +32,30 @@ struct RegistrationConvergenceCriteria {
     float rotation = 1e-3f;     // [rad]
 };
 
-struct DegenerateRegularizationParams {  // degenerate_regularization.hpp:40 (default off)
-    bool enable = false;
+enum class DegenerateRegularizationType { none = 0, nl_reg };  // degenerate_regularization.hpp:14-17
+
+inline DegenerateRegularizationType DegenerateRegularizationType_from_string(const std::string& str) {  // :19-33
+    std::string upper(str.size(), '\0');
+    std::transform(str.begin(), str.end(), upper.begin(), [](unsigned char c) { return std::toupper(c); });
+    if (upper == "NONE") return DegenerateRegularizationType::none;
+    if (upper == "NL-REG" || upper == "NL_REG") return DegenerateRegularizationType::nl_reg;
+    throw std::runtime_error("[DegenerateRegularizationType_from_string] Invalid DegenerateRegularizationType str [" + str +
+                             "]");
+}
+
+struct DegenerateRegularizationParams {  // degenerate_regularization.hpp:35-40
+    DegenerateRegularizationType type = DegenerateRegularizationType::none;
+    float rot_eigenvalue_threshold = 10.0f;
+    float trans_eigenvalue_threshold = 1.0f;
+    float base_factor = 1.0f;
 };
-struct MapPriorParams {  // map_prior.hpp:15 (default off)
-    bool enable = false;
+
+struct MapPriorParams {  // map_prior.hpp:15-21
+    bool enabled = false;
+    float rot_vel_sigma = 1.0f;
+    float trans_vel_sigma = 1.0f;
+    float rot_base_sigma = 3.16e-2f;
+    float trans_base_sigma = 1e-2f;
 };
 
 struct RegistrationFactorParams {

@@ -365,7 +365,28 @@ constexpr int Isometry = 1;
 struct AngleAxisf {
     float a;
     Vector3f ax;
+    AngleAxisf() : a(0.0f), ax(1.0f, 0.0f, 0.0f) {}
     AngleAxisf(float angle, const Vector3f& axis) : a(angle), ax(axis) {}
+    /// from a rotation matrix: angle in [0, pi]
+    explicit AngleAxisf(const Matrix3f& R) {
+        const float c = std::fmin(1.0f, std::fmax(-1.0f, 0.5f * (R(0, 0) + R(1, 1) + R(2, 2) - 1.0f)));
+        Vector3f v(R(2, 1) - R(1, 2), R(0, 2) - R(2, 0), R(1, 0) - R(0, 1));
+        const float s = 0.5f * v.norm();
+        a = std::atan2(s, c);
+        if (s > 1e-6f) {
+            ax = v / (2.0f * s);
+        } else if (c > 0.0f) {
+            a = 0.0f;
+            ax = Vector3f(1.0f, 0.0f, 0.0f);
+        } else {  // angle ~ pi: the axis is the dominant column of (R + I) / 2
+            int k = 0;
+            if (R(1, 1) > R(k, k)) k = 1;
+            if (R(2, 2) > R(k, k)) k = 2;
+            Vector3f col(R(0, k) + (k == 0 ? 1.0f : 0.0f), R(1, k) + (k == 1 ? 1.0f : 0.0f), R(2, k) + (k == 2 ? 1.0f : 0.0f));
+            ax = col.normalized();
+        }
+    }
+    static AngleAxisf Identity() { return AngleAxisf(); }
     float angle() const { return a; }
     const Vector3f& axis() const { return ax; }
     Matrix3f toRotationMatrix() const {

@@ -113,3 +113,43 @@ def test_reference_gtest_source_passes_on_libspx(name, bundled, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0, (r.stdout[-4000:], r.stderr[-2000:])
     assert " 0 failed" in r.stdout and "[  FAILED  ]" not in r.stdout
+
+
+@pytest.fixture(scope="module")
+def odometry_exe():
+    return compile_cpp("examples/example_lidar_odometry.cpp", "example_lidar_odometry")
+
+
+def test_odometry_example_compiles(odometry_exe):
+    assert os.access(odometry_exe, os.X_OK)
+
+
+@pytest.mark.gpu
+def test_cpp_lidar_odometry_pipeline_tracks_the_drive_like_the_python_mirror(odometry_exe, tmp_path):
+    """pipeline::lidar_odometry::LiDAROdometryPipeline (include/sycl_points/pipeline/*.hpp; reference:
+    pipeline/lidar_odometry.hpp:115-298) on the synthetic drive of tests/test_gpu_odometry.py: every pose within 5 cm of
+    the ground truth and within 2 mm of what the Python mirror computes on the same scans (same kernels, same RNG
+    streams; the two hosts differ in the rounding of the motion prediction and in the order of the submap's atomics)."""
+    import sycl_points_b200 as spx
+    from sycl_points_b200 import pipeline as pl
+    from test_gpu_odometry import drive, make_params, pose_err
+    n = 8
+    poses, scans = drive(n)
+    for k, s in enumerate(scans):
+        write_ply(tmp_path / f"scan_{k:03d}.ply", s)
+    np.savetxt(tmp_path / "pose0.txt", poses[0])
+    r = subprocess.run([odometry_exe, str(tmp_path), str(n), "0.1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    got = [np.array(l.split("pose")[1].split(), np.float64).reshape(4, 4) for l in r.stdout.splitlines() if l.startswith("frame")]
+    assert len(got) == n
+    q = spx.DeviceQueue(0)
+    P = make_params(pl, spx)
+    P.initial_pose = poses[0]
+    pipe = pl.LiDAROdometryPipeline(P, q)
+    for k in range(n):
+        pipe.process(spx.PointCloudShared(q, scans[k]), 0.1 * k)
+        dt, da = pose_err(poses[k], got[k].astype(np.float32))
+        assert dt < 0.05 and da < 0.005, f"frame {k}: C++ pose {dt:.3f} m / {da:.4f} rad off the ground truth"
+        dt2, da2 = pose_err(pipe.get_odom(), got[k].astype(np.float32))
+        assert dt2 < 2e-3 and da2 < 2e-4, f"frame {k}: C++ vs Python mirror {dt2:.2e} m / {da2:.2e} rad"
+    assert "keyframes" in r.stdout
