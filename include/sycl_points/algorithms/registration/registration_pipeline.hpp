@@ -79,8 +79,6 @@ private:
                 this->aligner_, this->pipeline_params_.velocity_update.iter, this->pipeline_params_.registration.verbose);
             this->aligner_ = this->velocity_update_pipeline_->make_aligner();
         }
-        if (this->pipeline_params_.random_sampling.use_intensities)
-            throw std::runtime_error("[RegistrationPipeline] intensity-weighted sampling is not built in libspx");
         if (this->pipeline_params_.robust.auto_scale) {
             this->robust_pipeline_ = std::make_shared<pipeline::RobustAligner>(this->aligner_, this->pipeline_params_);
             this->aligner_ = this->robust_pipeline_->make_aligner();
@@ -95,7 +93,12 @@ private:
         }
         const auto& rs = this->pipeline_params_.random_sampling;
         if (rs.enable && source.size() > rs.num) {
-            this->preprocess_filter_->random_sampling(source, *this->registration_input_pc_, rs.num);
+            if (rs.use_intensities && source.has_intensity()) {
+                this->preprocess_filter_->mixed_random_sampling(source, *this->registration_input_pc_,
+                                                                *source.intensities, rs.num, rs.weighted_ratio);
+            } else {
+                this->preprocess_filter_->random_sampling(source, *this->registration_input_pc_, rs.num);
+            }
         } else {
             *this->registration_input_pc_ = source;
         }

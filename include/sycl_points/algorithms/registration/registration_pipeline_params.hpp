@@ -12,7 +12,7 @@ namespace registration {
 struct RegistrationRandomSamplingParams {
     bool enable = true;
     size_t num = 1000;
-    bool use_intensities = false;  // mixed (intensity-weighted) sampling is out of scope: must stay false
+    bool use_intensities = false;  // intensity-weighted mixed sampling of the source (registration_pipeline.hpp:131-134)
     float weighted_ratio = 0.8f;
 };
 

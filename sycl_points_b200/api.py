@@ -1803,11 +1803,13 @@ class RegistrationPipeline:
     def align(self, source, target, target_knn, initial_guess=None, options: ExecutionOptions | None = None):
         rs = self.pipeline_params.random_sampling
         if rs.enable and source.size() > rs.num:
-            if rs.use_intensities:
-                raise SpxError(-3, "[RegistrationPipeline::align] intensity-weighted sampling is not built")
             if self._filter is None:
                 self._filter = PreprocessFilter(source.queue)
-            source = self._filter.random_sampling(source, rs.num, PointCloudShared(source.queue))
+            if rs.use_intensities and source.has_intensity():  # registration_pipeline.hpp:131-134
+                source = self._filter.mixed_random_sampling(source, source.intensities, rs.num, rs.weighted_ratio,
+                                                            PointCloudShared(source.queue))
+            else:
+                source = self._filter.random_sampling(source, rs.num, PointCloudShared(source.queue))
         self._input = source
         options = options if options is not None else ExecutionOptions()
         T0 = np.eye(4, dtype=np.float32) if initial_guess is None else np.asarray(initial_guess, np.float32)

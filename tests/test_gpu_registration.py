@@ -856,3 +856,23 @@ def test_degenerate_regularize_entry_point_vs_oracle(spx, q, pair):
     params.degenerate_reg.type = spx.DegenerateRegularizationType.none
     same = robj.compute_linearized_result(pair["src"], pair["tgt"], pair["tree"], T, initial_pose=T0)
     assert np.array_equal(same.H, raw.H) and np.array_equal(same.b, raw.b)
+
+
+def test_pipeline_intensity_weighted_sampling(spx, q, pair):
+    """RegistrationPipeline with random_sampling.use_intensities (registration_pipeline.hpp:131-134): the source is
+    drawn by mixed_random_sampling with the intensities as weights — the registration input equals the oracle's
+    selection from the same mt19937(1234) stream, and the align runs on it."""
+    n = len(pair["src_h"])
+    inten = np.random.default_rng(12).uniform(0.0, 1.0, n).astype(np.float32)
+    src = spx.PointCloudShared(q, pair["src_h"], pair["cov_s"])
+    src.set_intensities(inten)
+    pp = spx.RegistrationPipelineParams()
+    pp.random_sampling.num = 1500
+    pp.random_sampling.use_intensities = True
+    pp.random_sampling.weighted_ratio = 0.6
+    pipe = spx.RegistrationPipeline(q, pp)
+    res = pipe.align(src, pair["tgt"], pair["tree"])
+    used = pipe.get_registration_input_point_cloud()
+    keep = oracle.Rng(1234).mixed_random_sampling_flags(inten, 1500, 0.6).astype(bool)
+    assert used.size() == 1500 and np.array_equal(used.points_host(), pair["src_h"][keep])
+    assert res.inlier > 1000
