@@ -101,7 +101,20 @@ struct spx_queue_s {
         int mx[3] = {0, 0, 0};
     } voxel_last;
 
-    void arena_reset() { arena_off = 0; }
+    // the host thread whose API call owns the arena right now (0: none yet).  A queue — its arena, its pinned staging
+    // block, its voxel-grid state — is single-threaded by contract; a second thread that enters the library on the
+    // same queue while a call is still carving its scratch is caught at the next take instead of silently handing
+    // two calls the same memory (what an illegal address in a kernel much later would otherwise be the only sign of).
+    unsigned long long arena_owner = 0;
+    static unsigned long long this_thread_tag() {
+        static std::atomic<unsigned long long> next{1};
+        static thread_local unsigned long long tag = next.fetch_add(1, std::memory_order_relaxed);
+        return tag;
+    }
+    void arena_reset() {
+        arena_off = 0;
+        arena_owner = this_thread_tag();
+    }
     // Reserve the total a call needs BEFORE taking pointers: growing invalidates nothing in flight
     // (the old block is retired, not freed) but earlier pointers of this call would go stale.
     void arena_reserve(size_t bytes);

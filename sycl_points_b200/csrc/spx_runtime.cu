@@ -39,6 +39,10 @@ void spx_queue_s::arena_reserve(size_t bytes) {
 }
 
 void* spx_queue_s::arena_take(size_t bytes) {
+    if (arena_owner != 0 && arena_owner != this_thread_tag())
+        throw Error(SPX_ERR_INVALID_ARGUMENT,
+                    "[spx] this queue is being used by two host threads at once (a queue and everything created on it "
+                    "is single-threaded: drive each queue from one thread at a time)");
     const size_t off = align_up(arena_off, 256);
     if (off + bytes > arena_cap)
         throw Error(SPX_ERR_INTERNAL, "[spx] scratch arena overflow (arena_reserve under-estimated)");
