@@ -14,6 +14,11 @@ LIBDIR = os.path.join(ROOT, "sycl_points_b200")
 SOURCES = ["test_kdtree", "test_registration_pipeline", "test_downsampling_filters", "test_voxel_hash_map", "test_relative_pose_deskew", "test_preprocess_filter", "test_octree"]
 
 
+# the reference's own example programs whose API surface is inside the scope: compiled the same way (no gtest)
+REF_EXAMPLES = "/root/reference/cpp/examples"
+EXAMPLES = ["example_registration", "example_point_cloud"]
+
+
 def exe_path(name):
     return os.path.join(BUILD, "ref_" + name)
 
@@ -35,6 +40,19 @@ def build(verbose=False):
         if not (os.path.exists(exe) and os.path.getmtime(exe) > max(newest, os.path.getmtime(src))):
             cmd = [gxx, "-std=c++20", "-O1", "-I" + shim, "-I" + os.path.join(ROOT, "include"), src,
                    os.path.join(shim, "gtest_main.cpp"), "-L" + LIBDIR, "-lspx", "-Wl,-rpath," + LIBDIR, "-o", exe]
+            env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+            r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            if r.returncode != 0:
+                raise RuntimeError(f"{name}: {r.stderr[-3000:]}")
+            if verbose:
+                print("built", exe)
+        out.append(exe)
+    for name in EXAMPLES:
+        src = os.path.join(REF_EXAMPLES, name + ".cpp")
+        exe = exe_path(name)
+        if not (os.path.exists(exe) and os.path.getmtime(exe) > max(newest, os.path.getmtime(src))):
+            cmd = [gxx, "-std=c++20", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-L" + LIBDIR, "-lspx",
+                   "-Wl,-rpath," + LIBDIR, "-o", exe]
             env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
             r = subprocess.run(cmd, capture_output=True, text=True, env=env)
             if r.returncode != 0:

@@ -153,3 +153,23 @@ def test_cpp_lidar_odometry_pipeline_tracks_the_drive_like_the_python_mirror(odo
         dt2, da2 = pose_err(pipe.get_odom(), got[k].astype(np.float32))
         assert dt2 < 2e-3 and da2 < 2e-4, f"frame {k}: C++ vs Python mirror {dt2:.2e} m / {da2:.2e} rad"
     assert "keyframes" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["example_registration", "example_point_cloud"])
+def test_reference_example_source_runs_on_libspx(name, bundled, tmp_path):
+    """The reference's own cpp/examples/<name>.cpp, compiled UNMODIFIED against include/ + libspx.so (binary built where
+    /root/reference exists), run from a build-like directory next to data/source.ply and data/target.ply."""
+    exe = os.path.join(BUILD, "ref_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt reference example binary is absent (no /root/reference at build time)")
+    (tmp_path / "data").mkdir()
+    (tmp_path / "build").mkdir()
+    write_ply(tmp_path / "data" / "target.ply", bundled["target_ds"])
+    write_ply(tmp_path / "data" / "source.ply", bundled["source_ds"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, cwd=str(tmp_path / "build"))
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+    if name == "example_registration":
+        assert "Registration" in r.stdout, r.stdout[-2000:]
+    else:
+        assert "Voxel downsampling" in r.stdout and "Compute covariances" in r.stdout, r.stdout[-2000:]
