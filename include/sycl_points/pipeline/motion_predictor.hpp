@@ -18,20 +18,28 @@ namespace lidar_odometry {
 
 enum class MotionPredictionMode { LIDAR_CV = 0, GYRO_LIDAR_CV, IMU_SE3 };
 
+namespace detail {
+struct ModeName {
+    MotionPredictionMode mode;
+    const char* name;
+};
+inline constexpr ModeName kModeNames[] = {{MotionPredictionMode::LIDAR_CV, "LIDAR_CV"},
+                                          {MotionPredictionMode::GYRO_LIDAR_CV, "GYRO_LIDAR_CV"},
+                                          {MotionPredictionMode::IMU_SE3, "IMU_SE3"}};
+}  // namespace detail
+
+/// case-insensitive; throws std::runtime_error for an unknown name (motion_predictor.hpp:26-33)
 inline MotionPredictionMode MotionPredictionMode_from_string(const std::string& str) {
-    std::string upper(str.size(), '\0');
-    std::transform(str.begin(), str.end(), upper.begin(), [](unsigned char c) { return std::toupper(c); });
-    if (upper == "LIDAR_CV") return MotionPredictionMode::LIDAR_CV;
-    if (upper == "GYRO_LIDAR_CV") return MotionPredictionMode::GYRO_LIDAR_CV;
-    if (upper == "IMU_SE3") return MotionPredictionMode::IMU_SE3;
+    std::string upper(str);
+    for (char& c : upper) c = (char)std::toupper((unsigned char)c);
+    for (const auto& m : detail::kModeNames)
+        if (upper == m.name) return m.mode;
     throw std::runtime_error("[MotionPredictionMode_from_string] Invalid motion prediction mode '" + str + "'");
 }
+/// motion_predictor.hpp:35-45
 inline std::string MotionPredictionMode_to_string(const MotionPredictionMode mode) {
-    switch (mode) {
-        case MotionPredictionMode::LIDAR_CV: return "LIDAR_CV";
-        case MotionPredictionMode::GYRO_LIDAR_CV: return "GYRO_LIDAR_CV";
-        case MotionPredictionMode::IMU_SE3: return "IMU_SE3";
-    }
+    for (const auto& m : detail::kModeNames)
+        if (mode == m.mode) return m.name;
     throw std::runtime_error("[MotionPredictionMode_to_string] Invalid motion prediction mode");
 }
 

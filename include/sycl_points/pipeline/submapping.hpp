@@ -100,70 +100,71 @@ private:
     PointCloudShared::Ptr submap_pc_ptr_ = nullptr;     // odom / world frame
     PointCloudShared::Ptr submap_pc_tmp_ = nullptr;
 
-    bool is_keyframe(const algorithms::registration::RegistrationResult& reg_result, double timestamp) const {  // :157-175
-        const Eigen::Isometry3f delta_pose = this->last_keyframe_pose_.inverse() * reg_result.T;
-        const float distance = delta_pose.translation().norm();
-        const float angle = std::fabs(Eigen::AngleAxisf(delta_pose.rotation()).angle()) * (180.0f / 3.14159265358979323846f);
-        const double delta_time = this->last_keyframe_time_ > 0.0 ? timestamp - this->last_keyframe_time_
-                                                                  : std::numeric_limits<double>::max();
-        return distance >= this->submap_params_.keyframe.distance_threshold ||
-               angle >= this->submap_params_.keyframe.angle_threshold_degrees ||
-               delta_time >= this->submap_params_.keyframe.time_threshold_seconds;
+    /// :157-175 — far enough, turned enough, or long enough since the last keyframe
+    bool is_keyframe(const algorithms::registration::RegistrationResult& reg_result, double timestamp) const {
+        const auto& k = this->submap_params_.keyframe;
+        const Eigen::Isometry3f moved = this->last_keyframe_pose_.inverse() * reg_result.T;
+        if (moved.translation().norm() >= k.distance_threshold) return true;
+        constexpr float kRadToDeg = 180.0f / 3.14159265358979323846f;
+        if (std::fabs(Eigen::AngleAxisf(moved.rotation()).angle()) * kRadToDeg >= k.angle_threshold_degrees) return true;
+        // (no keyframe time yet: the reference treats the elapsed time as unbounded)
+        return !(this->last_keyframe_time_ > 0.0) || timestamp - this->last_keyframe_time_ >= k.time_threshold_seconds;
     }
 
+    /// :177-212 — keyframe cloud (sampled) -> voxel map -> boxed export -> target index + what the factor needs
     void build_submap(const PointCloudShared& cloud, const Eigen::Isometry3f& current_pose, bool is_first_frame,
-                      shared_vector_ptr<float> random_sampling_weights = nullptr) {  // :177-212
-        if (random_sampling_weights && random_sampling_weights->size() == cloud.size()) {
-            this->preprocess_filter_->mixed_random_sampling(cloud, *this->last_keyframe_pc_, *random_sampling_weights,
-                                                            this->submap_params_.point_random_sampling_num,
-                                                            this->submap_params_.weighted_sampling_ratio);
-        } else {
-            this->preprocess_filter_->random_sampling(cloud, *this->last_keyframe_pc_,
-                                                      this->submap_params_.point_random_sampling_num);
-        }
+                      shared_vector_ptr<float> random_sampling_weights = nullptr) {
+        this->sample_keyframe_cloud(cloud, random_sampling_weights);
         this->submap_voxel_->add_point_cloud(*this->last_keyframe_pc_, current_pose);
         this->submap_voxel_->downsampling(*this->submap_pc_tmp_, current_pose.translation(),
                                           this->submap_params_.max_distance_range);
         if (is_first_frame) {
+            // the first target is the whole preprocessed scan in the odom frame, not its voxel-map image
             *this->submap_pc_ptr_ = algorithms::transform::transform_copy(cloud, current_pose.matrix());
         } else if (this->submap_pc_tmp_->size() >= this->reg_params_.min_num_points) {
-            std::swap(this->submap_pc_ptr_, this->submap_pc_tmp_);
+            this->submap_pc_ptr_.swap(this->submap_pc_tmp_);
         }
         this->submap_tree_ = algorithms::knn::KDTree::build(this->queue_, *this->submap_pc_ptr_);
-        this->compute_covariances();
+        this->prepare_target_attributes();
     }
 
-    void compute_covariances() {  // :214-247
+    /// robust-ICP-weighted mixed sampling when the caller brought weights for exactly this cloud, uniform otherwise
+    void sample_keyframe_cloud(const PointCloudShared& cloud, const shared_vector_ptr<float>& weights) {
+        const size_t num = this->submap_params_.point_random_sampling_num;
+        if (weights != nullptr && weights->size() == cloud.size()) {
+            this->preprocess_filter_->mixed_random_sampling(cloud, *this->last_keyframe_pc_, *weights, num,
+                                                            this->submap_params_.weighted_sampling_ratio);
+            return;
+        }
+        this->preprocess_filter_->random_sampling(cloud, *this->last_keyframe_pc_, num);
+    }
+
+    /// :214-247 — normals and / or covariances of the submap, whichever the registration factor reads; the k-NN search
+    /// runs at most once and only when something needs it
+    void prepare_target_attributes() {
         using algorithms::registration::RegType;
-        bool knn_ready = false;
-        sycl_utils::events knn_events;
-        auto ensure_knn = [&]() {
-            if (!knn_ready) {
-                knn_events = this->submap_tree_->knn_search_async(*this->submap_pc_ptr_, this->cov_params_.neighbor_num,
-                                                                  this->knn_result_);
-                knn_ready = true;
+        const RegType factor = this->reg_params_.factor.reg_type;
+        const bool wants_normals = factor == RegType::POINT_TO_PLANE || factor == RegType::GENZ;
+        const bool wants_covs = factor == RegType::GICP || factor == RegType::POINT_TO_DISTRIBUTION ||
+                                factor == RegType::GENZ || this->reg_params_.factor.rotation_constraint.enable;
+        PointCloudShared& target = *this->submap_pc_ptr_;
+        const bool has_covs = target.has_cov();  // (the voxel map exports them when the keyframes carried them)
+        sycl_utils::events knn_done, pending;
+        bool searched = false;
+        const auto neighbours = [&]() -> const std::vector<sycl::event>& {
+            if (!searched) {
+                knn_done = this->submap_tree_->knn_search_async(target, this->cov_params_.neighbor_num, this->knn_result_);
+                searched = true;
             }
+            return knn_done.evs;
         };
-        sycl_utils::events cov_events;
-        const auto reg_type = this->reg_params_.factor.reg_type;
-        const bool need_covariances = reg_type == RegType::GICP || reg_type == RegType::POINT_TO_DISTRIBUTION ||
-                                      reg_type == RegType::GENZ || this->reg_params_.factor.rotation_constraint.enable;
-        const bool need_normals = reg_type == RegType::POINT_TO_PLANE || reg_type == RegType::GENZ;
-        const bool submap_has_cov = this->submap_pc_ptr_->has_cov();
-        if (need_normals) {
-            ensure_knn();
-            if (submap_has_cov) {
-                cov_events += algorithms::covariance::extract_normals_async(*this->submap_pc_ptr_, knn_events.evs);
-            } else {
-                cov_events +=
-                    algorithms::covariance::estimate_normals_async(this->knn_result_, *this->submap_pc_ptr_, knn_events.evs);
-            }
+        if (wants_normals) {
+            const auto& deps = neighbours();
+            pending += has_covs ? algorithms::covariance::extract_normals_async(target, deps)
+                                : algorithms::covariance::estimate_normals_async(this->knn_result_, target, deps);
         }
-        if (need_covariances && !submap_has_cov) {
-            ensure_knn();
-            cov_events += algorithms::covariance::estimate_async(this->knn_result_, *this->submap_pc_ptr_, knn_events.evs);
-        }
-        cov_events.wait_and_throw();
+        if (wants_covs && !has_covs) pending += algorithms::covariance::estimate_async(this->knn_result_, target, neighbours());
+        pending.wait_and_throw();
     }
 };
 
