@@ -23,7 +23,8 @@
     `cpu_baseline` = the oracle port of the reference's CPU path (-O3 -march=native build) on the same pairs;
     `extras`     = quick runs of the other configurations in the same job: config 3 (KNN Mqueries/s, index and
                    brute force, queries sharded over the ranks), config 4 (dense pair, source sharded, ms/iter with
-                   the in-kernel NVLink exchange), config 5 (batched pairs inside one GPU, pairs/s).
+                   the in-kernel NVLink exchange), config 5 (batched pairs inside one GPU, pairs/s), and the odometry
+                   loop that calls the path in production (LiDAROdometryPipeline on a synthetic drive, frames/s).
     N > 1: every rank aligns its own independent pairs on its own GPU (no data-path collective: weak scaling of
     batched pairs); max over ranks of the device time.
 
@@ -626,6 +627,58 @@ def make_batch_inputs(ctx, P, scenes=4):
     return host
 
 
+def odometry_params(pl, spx):
+    """settings of the odometry extra (and of tests/test_gpu_odometry.py): 0.4 m voxel grid -> 8000 points, GICP + Huber
+    against a 0.5 m VoxelHashMap submap, 3000-point registration sampling"""
+    P = pl.Parameters()
+    P.submap.map_type = pl.SubmapMapType.VOXEL_HASH_MAP
+    P.submap.voxel_size = 0.5
+    P.submap.point_random_sampling_num = 6000
+    P.submap.max_distance_range = 60.0
+    P.submap.keyframe.distance_threshold = 0.3
+    P.scan.downsampling.polar.enable = False
+    P.scan.downsampling.voxel.enable = True
+    P.scan.downsampling.voxel.size = 0.4
+    P.scan.downsampling.random.num = 8000
+    P.scan.preprocess.box_filter.min = 1.0
+    P.scan.preprocess.box_filter.max = 80.0
+    P.registration.factor.robust.type = spx.RobustLossType.HUBER
+    P.registration.factor.robust.default_scale = 1.0
+    P.registration_sampling.num = 3000
+    return P
+
+
+def workload_odometry(ctx, frames=30, warm=5):
+    """SURVEY.md §8(f) rank 2, the production caller of the path: LiDAROdometryPipeline::process on a synthetic drive
+    (one 64 x 1024 revolution per frame; raw scans resident, as a driver would have uploaded them).  frames/s over the
+    frames after `warm`, host clock around the loop (every process() ends with its result on the host)."""
+    from sycl_points_b200 import pipeline as pl
+    spx, q = ctx.spx, ctx.q
+    poses, scans = synthetic.drive(frames if not TINY else 4, azimuth_steps=1024 if not TINY else 256)
+    P = odometry_params(pl, spx)
+    P.initial_pose = poses[0]
+    pipe = pl.LiDAROdometryPipeline(P, q)
+    clouds = [spx.PointCloudShared(q, s) for s in scans]
+    q.wait()
+    worst, t0 = 0.0, None
+    warm = min(warm, len(scans) - 1)
+    for k in range(len(scans)):
+        if k == warm:
+            q.wait()
+            t0 = time.perf_counter()
+        rc = pipe.process(clouds[k], 0.1 * k)
+        if rc not in (pl.ResultType.first_frame, pl.ResultType.success):
+            raise RuntimeError(f"odometry frame {k}: {pipe.get_error_message()}")
+        worst = max(worst, float(np.linalg.norm(pipe.get_odom()[:3, 3] - poses[k][:3, 3])))
+    q.wait()
+    dt = time.perf_counter() - t0
+    n = len(scans) - warm
+    med = {name: float(np.median(v[warm:])) for name, v in pipe.get_total_processing_times().items() if len(v) > warm}
+    return {"frames_per_s": n / dt, "ms_per_frame": 1e3 * dt / n, "frames_timed": n, "points_per_scan": int(len(scans[0])),
+            "worst_position_error_m": worst, "keyframes": len(pipe.get_keyframe_poses()),
+            "submap_points": int(pipe.get_submap_point_cloud().size()), "stage_median_ms": med}
+
+
 def workload_batch(ctx, steps, warmup, P=64, e2e_steps=None, lanes=0):
     spx, q = ctx.spx, ctx.q
     host = make_batch_inputs(ctx, P)
@@ -896,6 +949,8 @@ def main():
                 extras["config3_knn_bruteforce"] = workload_knn(ctx, 1, 1, "bruteforce")
                 extras["config5_batch"] = workload_batch(ctx, 3, 1, P=64, lanes=args.lanes)
                 extras["config4_align_sharded"] = workload_align_sharded(ctx, 3)
+                if ctx.rank == 0:
+                    extras["odometry_loop"] = workload_odometry(ctx)
             except Exception as e:  # the headline line must go out whatever happens to an extra
                 extras["error"] = repr(e)
             extras["seconds"] = time.perf_counter() - t0

@@ -156,6 +156,26 @@ def kitti_pair(seed: int = 42, sweeps: int = 16, beams: int = 64, azimuth_steps:
     return tgt, src, T_gt.astype(np.float32)
 
 
+def drive(n_frames: int, step: float = 0.45, yaw_deg: float = 0.4, seed: int = 42, beams: int = 64,
+          azimuth_steps: int = 1024, start_x: float = -20.0):
+    """A vehicle driving along the street corridor of scene `seed`: (poses, scans) — the sensor pose of every frame
+    (4x4 float32, world frame) and ONE revolution per frame in the sensor frame (~64 k points at 64 x 1024).  The
+    input of the odometry loop (bench.py extras, tools/run_odometry.py, tests/test_gpu_odometry.py)."""
+    boxes, cyl = make_scene(seed)
+    poses, scans = [], []
+    T = np.eye(4)
+    T[0, 3] = start_x
+    a = np.deg2rad(yaw_deg)
+    D = np.eye(4)
+    D[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+    D[0, 3] = step
+    for k in range(n_frames):
+        poses.append(T.astype(np.float32))
+        scans.append(scan(T, beams, azimuth_steps, boxes, cyl, 900 + k))
+        T = T @ D
+    return poses, scans
+
+
 def dense_pair(seed: int = 42, n_points: int = 2_000_000):
     """BASELINE config 4 shape: a dense scan pair (8 sweeps x 256 beams x 4096 azimuth steps, ~8.2 M raw
     points per cloud) meant for a 0.05 m voxel grid, which leaves ~1.9 M points per cloud; callers trim

@@ -19,38 +19,12 @@ def q(spx):
 
 def drive(n_frames, step=0.45, yaw_deg=0.4):
     """sensor poses along the street corridor of the synthetic scene + one revolution per pose (sensor frame)"""
-    boxes, cyl = synthetic.make_scene(42)
-    poses, scans = [], []
-    T = np.eye(4)
-    T[0, 3] = -20.0
-    for k in range(n_frames):
-        poses.append(T.astype(np.float32))
-        scans.append(synthetic.scan(T, 64, 1024, boxes, cyl, 900 + k))
-        a = np.deg2rad(yaw_deg)
-        D = np.eye(4)
-        D[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
-        D[0, 3] = step
-        T = T @ D
-    return poses, scans
+    return synthetic.drive(n_frames, step, yaw_deg)
 
 
 def make_params(pl, spx):
-    P = pl.Parameters()
-    P.submap.map_type = pl.SubmapMapType.VOXEL_HASH_MAP
-    P.submap.voxel_size = 0.5
-    P.submap.point_random_sampling_num = 6000
-    P.submap.max_distance_range = 60.0
-    P.submap.keyframe.distance_threshold = 0.3
-    P.scan.downsampling.polar.enable = False
-    P.scan.downsampling.voxel.enable = True
-    P.scan.downsampling.voxel.size = 0.4
-    P.scan.downsampling.random.num = 8000
-    P.scan.preprocess.box_filter.min = 1.0
-    P.scan.preprocess.box_filter.max = 80.0
-    P.registration.factor.robust.type = spx.RobustLossType.HUBER
-    P.registration.factor.robust.default_scale = 1.0
-    P.registration_sampling.num = 3000
-    return P
+    import bench
+    return bench.odometry_params(pl, spx)
 
 
 def pose_err(Ta, Tb):
