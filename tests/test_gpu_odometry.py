@@ -39,6 +39,12 @@ def test_odometry_drive_tracks_ground_truth_and_every_registration_matches_oracl
     poses, scans = drive(n_frames)
     P = make_params(pl, spx)
     P.initial_pose = poses[0]
+    # a fixed number of iterations (criteria off): the submap differs in its last bits from run to run (the voxel map's
+    # atomics), so a step norm that lands within 1e-5 of the 1e-3 criterion could otherwise end the GPU's and the
+    # oracle's loops one iteration apart
+    P.lo.registration.criteria.translation = 0.0
+    P.lo.registration.criteria.rotation = 0.0
+    P.lo.registration.max_iterations = 6
     pipe = pl.LiDAROdometryPipeline(P, q)
     # record what every registration was given (host copies taken before the submap moves on)
     calls = []
@@ -63,8 +69,8 @@ def test_odometry_drive_tracks_ground_truth_and_every_registration_matches_oracl
     assert pipe.get_submap_point_cloud().size() > 2000 and pipe.get_submap_point_cloud().has_cov()
     assert set(pipe.get_current_processing_time()) == set(pipe._NAMES)
     # the registration of every frame, re-run by the oracle on the same inputs
-    OP = oracle.default_params(reg_type=oracle.REG["GICP"], loss=oracle.LOSS["HUBER"], opt_method=0, max_iterations=20,
-                               robust_default_scale=1.0)
+    OP = oracle.default_params(reg_type=oracle.REG["GICP"], loss=oracle.LOSS["HUBER"], opt_method=0, max_iterations=6,
+                               robust_default_scale=1.0, crit_translation=0.0, crit_rotation=0.0)
     for k, c in enumerate(calls):
         assert len(c["src"]) == 3000  # registration_sampling.num of the ~8000 preprocessed points
         o = oracle.align(OP, c["src"], c["cov_s"], c["tgt"], c["cov_t"], None, oracle.KDTree(c["tgt"]), T_init=c["T0"])
