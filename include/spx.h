@@ -529,6 +529,12 @@ SPX_API int spx_batch_last_timing(spx_batch_t batch, float* align_ms, int32_t* i
  * first iteration launch to just after the last), the number of iteration kernels launched and
  * the number of outer iterations that did work: bench.py's live per-launch duration. */
 SPX_API int spx_registration_last_timing(spx_registration_t reg, float* loop_ms, int32_t* launches, int32_t* iterations);
+/* Tuning aid: correspondences of the last align that were KEPT without a search, summed over its iterations.  The
+ * split-kernel Gauss-Newton loop (large clouds) keeps a query's nearest neighbour while the query has moved less than
+ * half the margin its last search certified between the nearest and every other target point — the same index and
+ * the same distance find_correspondences (registration.hpp:576-604 -> kdtree.hpp:463-553) would return.
+ * SPX_KEEP_FRAC < 0 in the environment searches every query in every iteration. */
+SPX_API int spx_registration_kept_correspondences(spx_registration_t reg, uint64_t* kept);
 /* tuning aid: per-iteration phase timestamps of the cooperative align kernel (globaltimer ns, latest
  * block to reach each phase): times_host[it][8] = {start, first-pass search done, cooperative search done,
  * accumulate done, partials written, grid barrier passed, fold done, solve done}.  enable != 0 allocates the buffer (affects later

@@ -199,6 +199,7 @@ def lib() -> C.CDLL:
         "spx_batch_set_params": (C.c_int, [vp, C.POINTER(RegistrationParamsC)]),
         "spx_align_batch": (C.c_int, [vp, sz, C.POINTER(ScanPairC), C.POINTER(RegistrationResultC), u32p, u32p]),
         "spx_batch_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+        "spx_registration_kept_correspondences": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         "spx_registration_last_timing": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                                    C.POINTER(C.c_int32)]),
         "spx_registration_phase_times": (C.c_int, [vp, C.c_int, vp, C.c_int]),

@@ -1505,6 +1505,12 @@ class Registration:
         check(_lib.lib().spx_registration_last_timing(self._h, C.byref(ms), C.byref(launches), C.byref(iters)))
         return dict(loop_ms=ms.value, launches=launches.value, iterations=iters.value)
 
+    def kept_correspondences(self) -> int:
+        """Correspondences the last align kept without a search, summed over its iterations (split-kernel loop)."""
+        kept = C.c_uint64()
+        check(_lib.lib().spx_registration_kept_correspondences(self._h, C.byref(kept)))
+        return int(kept.value)
+
     # -- pieces usable with any KNNBase (the reference's tests inject host KNNs)
     def _linearize(self, source, target, nn: KNNResult, T, scale) -> LinearizedResult:
         H = np.empty(36, np.float32)

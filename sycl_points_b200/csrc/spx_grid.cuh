@@ -76,6 +76,7 @@ __device__ __forceinline__ float shell_bound_axis(float q, float o, float cell, 
 // One candidate list per thread.  K1: a register pair.  General k: the thread's row of the output
 // arrays (global memory, L1/L2-resident; touched only on insertion, which is rare once warm).
 struct Best1 {
+    static constexpr bool MARGIN = false;
     float d;
     int i;      // original index
     uint32_t p; // sorted position (for gathers in fused kernels)
@@ -83,6 +84,30 @@ struct Best1 {
     __device__ __forceinline__ float worst() const { return d; }
     __device__ __forceinline__ void offer(float ds, int idx, uint32_t pos) {
         if (ds < d || (ds == d && (i < 0 || idx < i))) { d = ds; i = idx; p = pos; }
+    }
+};
+
+// Best1 + what the ICP loop's keep test needs (spx_registration.cu): a lower bound on the distance of every OTHER
+// target point.  d2 = smallest squared distance among the other points the search looked at and among the pruning
+// bounds it applied (a cell or row left out because it lies beyond sqrt(lim2) counts as a point at lim2); u = the
+// radius (metres) the last block scanned certifies — nothing unseen lies closer.  min(sqrt(d2), u) - sqrt(d) is how
+// far apart the nearest and the second nearest are at least: a query that moves by less than half of that keeps its
+// correspondence, bit for bit what a new search would return.  A point met twice (the warm start inside the block,
+// or on two levels) is recognised by its index.
+struct Best1M {
+    static constexpr bool MARGIN = true;
+    float d;
+    int i;
+    float d2;
+    float u;
+    __device__ __forceinline__ void init() { d = FLT_MAX; i = -1; d2 = FLT_MAX; u = 0.0f; }
+    __device__ __forceinline__ float worst() const { return d; }
+    __device__ __forceinline__ void offer(float ds, int idx, uint32_t) {
+        const bool other = idx != i;
+        const bool better = other && (ds < d || (ds == d && (i < 0 || idx < i)));
+        d2 = better ? d : (other ? fminf(d2, ds) : d2);
+        d = better ? ds : d;
+        i = better ? idx : i;
     }
 };
 
@@ -563,8 +588,11 @@ __device__ __forceinline__ unsigned long long best_key(float d, int i) {
 // indexes all points): afterwards every point closer than min(bound, current best) has been seen.
 // Returns 1 when `best` is final, 0 when not proven, -1 when the rows hold more than max_cands
 // candidates (nothing scanned: the caller leaves dense blocks to the cooperative search).
-__device__ __forceinline__ int icp_first_pass(const GridView& g, float qx, float qy, float qz, Best1& best,
-                                              float max_radius, uint32_t max_cands = 0xffffffffu) {
+// B = Best1M: the pruning bound is the candidate's distance PLUS `infl` metres, so that the pass also proves how far
+// away everything else is (see Best1M).
+template <class B>
+__device__ __forceinline__ int icp_first_pass(const GridView& g, float qx, float qy, float qz, B& best,
+                                              float max_radius, uint32_t max_cands = 0xffffffffu, float infl = 0.0f) {
     const int cx = grid_coord(qx, g.ox, g.inv, g.dx);
     const int cy = grid_coord(qy, g.oy, g.inv, g.dy);
     const int cz = grid_coord(qz, g.oz, g.inv, g.dz);
@@ -572,7 +600,13 @@ __device__ __forceinline__ int icp_first_pass(const GridView& g, float qx, float
     const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
     const float reach = max_radius + margin;
     const float reach2 = reach < 1.8e19f ? __fmul_rn(reach, reach) : INF;
-    const float lim2 = fminf(best.d, reach2);
+    float lim2 = fminf(best.d, reach2);
+    if constexpr (B::MARGIN) {
+        if (best.d < reach2) {
+            const float r = sqrtf(best.d) + infl;
+            lim2 = fminf(fmaxf(__fmul_rn(r, r), best.d), reach2);
+        }
+    }
     // Row (y, z) can hold something better than the bound only if its distance g_yz to the query
     // satisfies g_yz <= sqrt(lim2) + margin =: L, and then only in cells within
     // w = sqrt(L^2 - g_yz^2) + margin of the query along x (w is never smaller than grid_search's
@@ -631,6 +665,10 @@ __device__ __forceinline__ int icp_first_pass(const GridView& g, float qx, float
     const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, 1, g.dx),
                                     shell_bound_axis(qy, g.oy, g.cell, cy, 1, g.dy)),
                               shell_bound_axis(qz, g.oz, g.cell, cz, 1, g.dz));
+    if constexpr (B::MARGIN) {
+        if (prune) best.d2 = fminf(best.d2, lim2);
+        best.u = bound == INF ? INF : fmaxf(bound - margin, 0.0f);
+    }
     if (bound == INF) return 1;
     const float bs = bound - margin;
     return ((bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) || bs >= max_radius) ? 1 : 0;
@@ -654,8 +692,11 @@ constexpr int ICP_RMAX = 5;  // growth sequence: largest ring radius on a level 
 #endif
 constexpr int ICP_RMAX_CERT = SPX_ICP_RMAX_CERT;
 
-static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float qx, float qy, float qz, Best1& best,
-                                                    float max_radius, uint32_t* dbg = nullptr) {
+// B = Best1M: the block has to certify the candidate's distance plus `infl` metres, and rows / cells are pruned
+// against that inflated bound (see Best1M); the stop test stays the plain one.
+template <class B>
+static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float qx, float qy, float qz, B& best,
+                                                    float max_radius, uint32_t* dbg = nullptr, float infl = 0.0f) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const float INF = __int_as_float(0x7f800000);
@@ -667,6 +708,13 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
         // holds a point (or has covered max_radius): certifying the bare radius instead would scan every point
         // within max_radius of each such query — in the first iteration of a dense, misaligned pair that is a quarter
         // of the source at thousands of candidates each (8 ms instead of 0.5 at 1.6 M points).
+        float cert_d = best.d;  // squared distance the block has to certify
+        if constexpr (B::MARGIN) {
+            if (best.d < 1.0e30f) {
+                const float r = sqrtf(best.d) + infl;
+                cert_d = fmaxf(__fmul_rn(r, r), best.d);
+            }
+        }
         if (best.d < 1.0e30f) {
             for (int l = l_min; l < gl.n_levels && !found; ++l) {
                 const GridView& g = gl.lv[l];
@@ -682,7 +730,7 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
                                                     shell_bound_axis(qy, g.oy, g.cell, cy, r, g.dy)),
                                               shell_bound_axis(qz, g.oz, g.cell, cz, r, g.dz));
                     const float bs = bound - margin;
-                    if (bound == INF || (bs > 0.0f && best.d < __fmul_rn(bs, bs)) || bs >= max_radius) {
+                    if (bound == INF || (bs > 0.0f && cert_d < __fmul_rn(bs, bs)) || bs >= max_radius) {
                         L = l;
                         R = r;
                         found = true;
@@ -739,12 +787,12 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
         const float margin = g.margin + 1e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
         // what has to be beaten: the current candidate, or the search radius (+ allowance)
         const float reach = max_radius + margin;
-        const float lim2 = fminf(best.d, reach < 1.8e19f ? __fmul_rn(reach, reach) : INF);
+        const float lim2 = fminf(cert_d, reach < 1.8e19f ? __fmul_rn(reach, reach) : INF);
         const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
         const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
         const int ny = y1 - y0 + 1;
         const int nrows = (z1 - z0 + 1) * ny;
-        Best1 mine = best;  // per-lane candidate, merged after the scan
+        B mine = best;  // per-lane candidate, merged after the scan
         if (dbg) {
             dbg[1] += 1;
             dbg[2] += (uint32_t)nrows;
@@ -831,13 +879,21 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
         const int wl = __ffs(win) - 1;
         best.d = __shfl_sync(FULL, mine.d, wl);
         best.i = __shfl_sync(FULL, mine.i, wl);
-        best.p = __shfl_sync(FULL, mine.p, wl);
+        if constexpr (!B::MARGIN) best.p = __shfl_sync(FULL, mine.p, wl);
         l_min = L;
         r_done = R;
         // stop test of the block just completed (grid_search's)
         const float bound = fminf(fminf(shell_bound_axis(qx, g.ox, g.cell, cx, R, g.dx),
                                         shell_bound_axis(qy, g.oy, g.cell, cy, R, g.dy)),
                                   shell_bound_axis(qz, g.oz, g.cell, cz, R, g.dz));
+        if constexpr (B::MARGIN) {
+            // every point but the winner: a lane whose candidate IS the winner contributes its runner-up
+            float o = mine.i == best.i ? mine.d2 : mine.d;
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) o = fminf(o, __shfl_xor_sync(FULL, o, sft));
+            best.d2 = lim2 < 1.0e30f ? fminf(o, lim2) : o;
+            best.u = bound == INF ? INF : fmaxf(bound - margin, 0.0f);
+        }
         if (bound == INF) return;  // whole grid visited
         const float bs = bound - margin;
         if (bs > 0.0f && best.worst() < __fmul_rn(bs, bs)) return;
@@ -845,21 +901,32 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
     }
 }
 
-// Per-lane part of the search: warm start (warm_pos != 0xffffffff offers that sorted position
-// first) + pruned first pass.  Returns true when `best` is final; otherwise `best` holds the bound
-// reached so far and the query goes to the cooperative continuation.
-__device__ __forceinline__ bool icp_fast(const GridLevels& gl, float qx, float qy, float qz, uint32_t warm_pos,
-                                         float max_radius, Best1& best) {
+// Per-lane part of the search: warm start (warm_idx >= 0 offers that target point first, read from the target cloud
+// in its original order — a correspondence found on a coarser level has no position in the finest level's array) +
+// pruned first pass.  Returns true when `best` is final; otherwise `best` holds the bound reached so far and the query
+// goes to the cooperative continuation.
+template <class B>
+__device__ __forceinline__ bool icp_fast(const GridLevels& gl, float qx, float qy, float qz, int warm_idx,
+                                         const float4* __restrict__ tgt_pts, float max_radius, B& best, float infl = 0.0f) {
     const GridView& g = gl.lv[0];
     best.init();
-    if (warm_pos != 0xffffffffu) {
-        const float4 p = __ldg(g.pts + warm_pos);
-        best.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), warm_pos);
+    if (warm_idx >= 0) {
+        const float4 p = __ldg(tgt_pts + warm_idx);
+        best.offer(dist_sq(qx, qy, qz, p.x, p.y, p.z), warm_idx, 0u);
     }
     // (A per-lane pass on the next coarser level for the unproven, sparse-neighbourhood queries was
     // measured: it halves the cooperative phase but doubles this one — those queries cluster in the
     // same warps — for a net loss; icp_first_pass keeps its max_cands hook for that experiment.)
-    return icp_first_pass(g, qx, qy, qz, best, max_radius) == 1;
+    return icp_first_pass(g, qx, qy, qz, best, max_radius, 0xffffffffu, infl) == 1;
+}
+
+// What a finished search leaves for the keep test: metres the query may still move (summed over the iterations) before
+// its correspondence has to be searched again; 0 = search every time.  The allowance covers the rounding of the fp32
+// distances the search compares (1e-7 relative on coordinates of magnitude qinf).
+__device__ __forceinline__ float icp_keep_slack(const Best1M& b, float qinf, float max_corr_sq) {
+    if (b.i < 0 || !(b.d <= max_corr_sq)) return 0.0f;
+    const float m = fminf(sqrtf(b.d2), b.u) - sqrtf(b.d);
+    return fmaxf(m - (1.0e-3f + 1.0e-5f * qinf), 0.0f);
 }
 
 #endif  // __CUDACC__

@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_nn1_fast_kernel(const GridL
         Best1 best;
         best.init();
         if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && g.lv[0].n > 0)
-            pending = !icp_fast(g, q.x, q.y, q.z, 0xffffffffu, max_radius, best);
+            pending = !icp_fast(g, q.x, q.y, q.z, -1, nullptr, max_radius, best);
         idx[qi] = best.i;
         dist[qi] = best.d;
         pos[qi] = best.p;

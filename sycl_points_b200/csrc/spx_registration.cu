@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "spx_grid.cuh"
 #include "spx_math.cuh"
@@ -45,6 +46,7 @@ struct RegState {
     uint32_t inlier;
     float delta[6];
     float pad[2];
+    float Tp[4][4];  // pose of the previous iteration (keep test of the split search kernels, icp_keep)
 };
 
 // view of the NVLink mailboxes handed to the sharded align kernel (spx_comm_s)
@@ -74,8 +76,10 @@ struct LinArgs {
     const float* dist_in;
     int32_t* idx_out;
     float* dist_out;
-    uint32_t* pos_out;   // sorted position of the correspondence in the index: next iteration's warm start
-    int warm_start;      // idx_out / pos_out hold a previous iteration's result (per-launch kernels)
+    float* slack_out;    // keep test (icp_keep): metres each query may still move before it is searched again
+    float keep_infl;     // most metres a margin-tracking search adds to a candidate's distance when it prunes / certifies
+    int keep_last;       // the previous iteration's search tracked margins: slack_out is valid
+    int warm_start;      // idx_out holds a previous iteration's result (per-launch kernels)
     uint32_t* worklist;          // [ns] source indices whose search the first pass could not finish
     unsigned int* wl_counters;   // [2 parities][count, cursor]
     GridLevels grid;
@@ -354,6 +358,57 @@ __device__ __forceinline__ void load_covs(const LinArgs& a, uint32_t i, int ti, 
     else ct = plane_regularize(a.tgt_cov16 ? load_cov16(a.tgt_cov16 + (size_t)ti * 16) : mat3_identity());
 }
 
+}  // namespace
+
+// SPX_KEEP_FRAC (tuning aid): inflation of the search bound in finest cells, default 0.2; negative = search every
+// query in every iteration.  Results do not depend on it.
+static float keep_fraction() {
+    const char* e = std::getenv("SPX_KEEP_FRAC");
+    return e ? (float)std::atof(e) : 0.2f;
+}
+
+namespace {
+
+__device__ __forceinline__ Xform state_xform_prev(const RegState* s) {
+    Xform T;
+    T.r0 = make_float4(s->Tp[0][0], s->Tp[0][1], s->Tp[0][2], s->Tp[0][3]);
+    T.r1 = make_float4(s->Tp[1][0], s->Tp[1][1], s->Tp[1][2], s->Tp[1][3]);
+    T.r2 = make_float4(s->Tp[2][0], s->Tp[2][1], s->Tp[2][2], s->Tp[2][3]);
+    T.r3 = make_float4(s->Tp[3][0], s->Tp[3][1], s->Tp[3][2], s->Tp[3][3]);
+    return T;
+}
+
+// Keep test of the ICP loop (DESIGN.md §3 K-align): a finished search leaves, per query, how far the query may still
+// move before another target point can become the nearest (icp_keep_slack, spx_grid.cuh).  An iteration moves query
+// i by delta_i = |T p_i - T_prev p_i|; while the allowance lasts the correspondence is kept and only its distance
+// is recomputed — the same index and the same fp32 distance a new search would return.  A kept correspondence that
+// leaves max_correspondence_distance is searched again, so that rejected entries match a search's as well.
+// Returns true when the query needs a search.
+__device__ __forceinline__ bool icp_keep(const Xform& T, const Xform& Tp, const float4 ps, const float4 q, int prev_i,
+                                         float slack, const float4* __restrict__ tgt_pts, float max_corr_sq,
+                                         float* dist_i, float* slack_i) {
+    if (prev_i < 0 || !(slack > 0.0f)) return true;
+    const float4 qp = transform_point(Tp, ps);
+    const float moved = sqrtf(dist_sq(q.x, q.y, q.z, qp.x, qp.y, qp.z));
+    const float left = __fmaf_rn(-2.0002f, moved, slack);
+    if (!(left > 0.0f)) return true;
+    const float4 pt = __ldg(tgt_pts + prev_i);
+    const float dn = dist_sq(q.x, q.y, q.z, pt.x, pt.y, pt.z);
+    if (!(dn <= max_corr_sq)) return true;
+    *dist_i = dn;
+    *slack_i = left;
+    return false;
+}
+
+// How far a search inflates its bound for a query that moved `moved` metres in the last step: three such steps (the
+// iteration contracts) plus the rounding allowance of icp_keep_slack; nothing when that exceeds infl_max — the
+// query would be searched again anyway, and an inflated bound costs candidates.
+__device__ __forceinline__ float icp_keep_infl(const Xform& T, const Xform& Tp, const float4 ps, float qinf, float infl_max) {
+    const float4 q = transform_point(T, ps), qp = transform_point(Tp, ps);
+    const float want = __fmaf_rn(3.0f, sqrtf(dist_sq(q.x, q.y, q.z, qp.x, qp.y, qp.z)), 2.0e-3f + 2.0e-5f * qinf);
+    return want <= infl_max ? want : 0.0f;
+}
+
 __device__ __forceinline__ Xform state_xform(const RegState* s) {
     Xform T;
     T.r0 = make_float4(s->T[0][0], s->T[0][1], s->T[0][2], s->T[0][3]);
@@ -382,7 +437,10 @@ __device__ void gn_update(RegState* st, const double* sums, float lambda, float 
     se3_exp_rm(delta, E);
     isometry_mul_rm(st->T, E, Tn);
     for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) st->T[i][j] = Tn[i][j];
+        for (int j = 0; j < 4; ++j) {
+            st->Tp[i][j] = st->T[i][j];
+            st->T[i][j] = Tn[i][j];
+        }
     st->iterations = iter_index;
     st->converged = conv ? 1 : 0;
     st->stop = conv ? 1 : 0;
@@ -489,13 +547,11 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
             // the three loads are independent: issued together, one round trip instead of three
             const float4 ps = __ldg(a.src_pts + i);
             const int prev_i = warm ? __ldcg(a.idx_out + i) : -1;
-            const uint32_t prev_p = warm ? __ldcg(a.pos_out + i) : 0xffffffffu;
             const float4 q = transform_point(T, ps);
             if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
-                pending = !icp_fast(a.grid, q.x, q.y, q.z, prev_i >= 0 ? prev_p : 0xffffffffu, a.max_corr, best);
+                pending = !icp_fast(a.grid, q.x, q.y, q.z, prev_i, a.tgt_pts, a.max_corr, best);
             a.idx_out[i] = best.i;
             a.dist_out[i] = best.d;
-            a.pos_out[i] = best.p;
         }
         // warp-aggregated append
         const unsigned m = __ballot_sync(FULL, pending);
@@ -530,12 +586,11 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
         Best1 best;
         best.i = __ldcg(a.idx_out + i);
         best.d = __ldcg(a.dist_out + i);
-        best.p = __ldcg(a.pos_out + i);
+        best.p = 0u;
         icp_coop_search(a.grid, q.x, q.y, q.z, best, a.max_corr);
         if (lane == 0) {
             a.idx_out[i] = best.i;
             a.dist_out[i] = best.d;
-            a.pos_out[i] = best.p;
         }
         if (rec) {
             t_worst = max(t_worst, global_ns() - t_q);
@@ -560,29 +615,64 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
 // thousand source points launch overhead no longer matters, so the search gets kernels of its own
 // (64 registers -> 4x the resident warps) and the factor pass runs as linearize_kernel<REG, 0, SOLVE>.
 constexpr int NN_THREADS = 128;
+constexpr int WL_KEPT = 12;  // wl_counters[WL_KEPT]: correspondences kept without a search, summed over the align's iterations
 
+// M: the search tracks margins (Best1M) and, from the second such iteration on, keeps what cannot have changed.
+template <bool M>
 __global__ void __launch_bounds__(NN_THREADS, 8) icp_fast_kernel(const LinArgs a) {
     if (a.state->stop) return;
+    using BestT = typename std::conditional<M, Best1M, Best1>::type;
+    __shared__ unsigned short redo[NN_THREADS];
+    __shared__ unsigned int n_redo;
     const Xform T = state_xform(a.state);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool warm = a.iter_index > 0 || a.warm_start;
     const int par = a.iter_index & 1;
     unsigned int* wl_count = a.wl_counters + par * 2;
-    const uint32_t i = blockIdx.x * NN_THREADS + threadIdx.x;
+    const uint32_t base = blockIdx.x * NN_THREADS;
+    uint32_t i = base + threadIdx.x;
+    bool search = i < a.ns;
+    if (M && a.keep_last) {  // keep what cannot have changed; the rest is searched by the first lanes of the block
+        if (threadIdx.x == 0) n_redo = 0;
+        __syncthreads();
+        if (search) {
+            const Xform Tp = state_xform_prev(a.state);
+            const float4 ps = __ldg(a.src_pts + i);
+            search = icp_keep(T, Tp, ps, transform_point(T, ps), a.idx_out[i], a.slack_out[i], a.tgt_pts, a.max_corr_sq,
+                              a.dist_out + i, a.slack_out + i);
+        }
+        const unsigned m = __ballot_sync(FULL, search);
+        if (lane == 0) {
+            const unsigned live = min(32u, a.ns > (base + (threadIdx.x & ~31u)) ? a.ns - (base + (threadIdx.x & ~31u)) : 0u);
+            if (live > (unsigned)__popc(m)) atomicAdd(a.wl_counters + WL_KEPT, live - (unsigned)__popc(m));
+        }
+        if (m) {
+            unsigned int slot = 0;
+            if (lane == __ffs(m) - 1) slot = atomicAdd(&n_redo, (unsigned int)__popc(m));
+            slot = __shfl_sync(FULL, slot, __ffs(m) - 1);
+            if (search) redo[slot + __popc(m & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
+        }
+        __syncthreads();
+        search = threadIdx.x < n_redo;
+        if (search) i = base + redo[threadIdx.x];
+    }
     bool pending = false;
-    if (i < a.ns) {
-        Best1 best;
+    if (search) {
+        BestT best;
         best.init();
         const float4 ps = __ldg(a.src_pts + i);
         const int prev_i = warm ? a.idx_out[i] : -1;
-        const uint32_t prev_p = warm ? a.pos_out[i] : 0xffffffffu;
         const float4 q = transform_point(T, ps);
-        if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
-            pending = !icp_fast(a.grid, q.x, q.y, q.z, prev_i >= 0 ? prev_p : 0xffffffffu, a.max_corr, best);
+        const float qinf = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+        if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
+            const float infl = M ? icp_keep_infl(T, state_xform_prev(a.state), ps, qinf, a.keep_infl) : 0.0f;
+            pending = !icp_fast(a.grid, q.x, q.y, q.z, prev_i, a.tgt_pts, a.max_corr, best, infl);
+        }
         a.idx_out[i] = best.i;
         a.dist_out[i] = best.d;
-        a.pos_out[i] = best.p;
+        // unfinished: the runner-up bound travels to the cooperative kernel in the allowance's slot
+        if constexpr (M) a.slack_out[i] = pending ? best.d2 : icp_keep_slack(best, qinf, a.max_corr_sq);
     }
     const unsigned m = __ballot_sync(FULL, pending);
     if (m) {
@@ -593,8 +683,10 @@ __global__ void __launch_bounds__(NN_THREADS, 8) icp_fast_kernel(const LinArgs a
     }
 }
 
+template <bool M>
 __global__ void __launch_bounds__(NN_THREADS, 8) icp_coop_kernel(const LinArgs a) {
     if (a.state->stop) return;
+    using BestT = typename std::conditional<M, Best1M, Best1>::type;
     const Xform T = state_xform(a.state);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -611,16 +703,23 @@ __global__ void __launch_bounds__(NN_THREADS, 8) icp_coop_kernel(const LinArgs a
         k = __shfl_sync(FULL, k, 0);
         if (k >= n_slow) break;
         const uint32_t i = a.worklist[k];
-        const float4 q = transform_point(T, __ldg(a.src_pts + i));
-        Best1 best;
+        const float4 ps = __ldg(a.src_pts + i);
+        const float4 q = transform_point(T, ps);
+        const float qinf = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+        BestT best;
+        best.init();
         best.i = a.idx_out[i];
         best.d = a.dist_out[i];
-        best.p = a.pos_out[i];
-        icp_coop_search(a.grid, q.x, q.y, q.z, best, a.max_corr);
+        float infl = 0.0f;
+        if constexpr (M) {
+            best.d2 = a.slack_out[i];
+            infl = icp_keep_infl(T, state_xform_prev(a.state), ps, qinf, a.keep_infl);
+        }
+        icp_coop_search(a.grid, q.x, q.y, q.z, best, a.max_corr, nullptr, infl);
         if (lane == 0) {
             a.idx_out[i] = best.i;
             a.dist_out[i] = best.d;
-            a.pos_out[i] = best.p;
+            if constexpr (M) a.slack_out[i] = icp_keep_slack(best, qinf, a.max_corr_sq);
         }
     }
 }
@@ -938,7 +1037,6 @@ struct PairDesc {
     const float4* tgt_normals;
     int32_t* idx;          // [ns] correspondences of the current iteration (and the next one's warm start)
     float* dist;
-    uint32_t* pos;
     RegState* state;
     float* trace;          // [max_iterations][16] column-major poses, nullable
     uint32_t ns;
@@ -953,7 +1051,7 @@ struct BatchArgs {
     const uint32_t* chunk_end;  // [n_pairs] chunk0 + nchunks, ascending: chunk -> pair lookup
     uint32_t n_pairs, total_chunks;
     float4* wl_q;               // work list: transformed query xyz, w = bits of the source index
-    float4* wl_b;               //            best so far {dist, idx bits, pos bits}, w = bits of the pair id
+    float4* wl_b;               //            best so far {dist, idx bits, -}, w = bits of the pair id
     unsigned int* wl_counters;  // [2 parities][count, cursor]
     double* partials;           // [2 parities][total_chunks][32]
     float max_corr, max_corr_sq;
@@ -1020,17 +1118,14 @@ __global__ void __launch_bounds__(LIN_THREADS, CTAS) align_batch_kernel(const Ba
             if (i < ns) {
                 int32_t* idx = d->idx;
                 float* dist = d->dist;
-                uint32_t* pos = d->pos;
-                // the three loads are independent: issued together, one round trip instead of three
+                // the two loads are independent: issued together, one round trip instead of two
                 const float4 ps = __ldg(d->src_pts + i);
                 const int prev_i = warm ? __ldcg(idx + i) : -1;
-                const uint32_t prev_p = warm ? __ldcg(pos + i) : 0xffffffffu;
                 q = transform_point(T, ps);
                 if (__ldg(&d->grid.lv[0].n) > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
-                    pending = !icp_fast(d->grid, q.x, q.y, q.z, prev_i >= 0 ? prev_p : 0xffffffffu, a.max_corr, best);
+                    pending = !icp_fast(d->grid, q.x, q.y, q.z, prev_i, d->tgt_pts, a.max_corr, best);
                 idx[i] = best.i;
                 dist[i] = best.d;
-                pos[i] = best.p;
             }
             const unsigned m = __ballot_sync(FULL, pending);  // warp-aggregated append
             if (m) {
@@ -1071,7 +1166,6 @@ __global__ void __launch_bounds__(LIN_THREADS, CTAS) align_batch_kernel(const Ba
                 if (lane == 0) {
                     d->idx[i] = best.i;
                     d->dist[i] = best.d;
-                    d->pos[i] = best.p;
                     // tuning aid: {list size, list queries that end without a neighbour inside max_corr} per iteration
                     if (a.phase && it < PH_MAX_ITERS) {
                         unsigned long long* w = a.phase + PH_MAX_ITERS * PH_N + it * 2;
@@ -1276,6 +1370,7 @@ __global__ void __launch_bounds__(128) align_prepare_kernel(PrepArgs p) {
         s.error = FLT_MAX;
         *p.state = s;
         for (int i = 0; i < 4; ++i) p.wl_counters[i] = 0u;
+        p.wl_counters[WL_KEPT] = 0u;
         *p.ticket = 0u;
     }
     uint32_t i = blockIdx.x * 128 + threadIdx.x;
@@ -1656,7 +1751,9 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     a.genz_counts = r->wl_counters + 8;
     a.idx_in = r->nn_idx; a.dist_in = r->nn_dist;
     a.idx_out = r->nn_idx; a.dist_out = r->nn_dist;
-    a.pos_out = r->nn_pos;
+    a.slack_out = reinterpret_cast<float*>(r->nn_pos);
+    a.keep_infl = 0.0f;
+    a.keep_last = 0;
     a.warm_start = 0;
     a.worklist = r->worklist;
     a.wl_counters = r->wl_counters;
@@ -1984,7 +2081,6 @@ void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs,
         }
         d.idx = r->nn_idx + so;
         d.dist = r->nn_dist + so;
-        d.pos = r->nn_pos + so;
         d.state = (P == 1) ? r->state : r->states + k;
         d.trace = (P == 1 && T_trace_host) ? r->trace : nullptr;
         d.ns = (uint32_t)A.ns;
@@ -2535,6 +2631,19 @@ int spx_registration_set_params(spx_registration_t reg, const spx_registration_p
     });
 }
 
+int spx_registration_kept_correspondences(spx_registration_t reg, uint64_t* kept) {
+    return guard([&] {
+        SPX_REQUIRE(reg && kept, "[Registration::kept_correspondences] null argument");
+        DeviceGuard g(reg->q->device);
+        *kept = 0;
+        if (!reg->wl_counters) return;
+        unsigned int v = 0;
+        SPX_CUDA(cudaMemcpyAsync(&v, reg->wl_counters + WL_KEPT, sizeof(v), cudaMemcpyDeviceToHost, reg->q->stream));
+        reg->q->sync();
+        *kept = v;
+    });
+}
+
 int spx_registration_last_timing(spx_registration_t reg, float* loop_ms, int32_t* launches, int32_t* iterations) {
     return guard([&] {
         SPX_REQUIRE(reg, "[Registration::last_timing] null handle");
@@ -2639,14 +2748,26 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
             if (max_it > 0) {  // split kernels (large clouds); smaller ones took the batched kernel above
                 (void)split;
                 constexpr int SPLIT_POLL = 4;
+                // the first search has no previous pose to measure a query's step against: plain; from then on the
+                // searches track margins, and from the third iteration on correspondences can be kept (icp_keep)
+                const float keep_frac = keep_fraction();
+                const bool keep = keep_frac >= 0.0f;
+                a.keep_infl = keep ? keep_frac * a.grid.lv[0].cell : 0.0f;
                 LinArgs f = a;  // factor pass: correspondences given, fused solve
                 f.idx_in = reg->nn_idx;
                 f.dist_in = reg->nn_dist;
                 for (int it = 0; it < max_it; ++it) {
                     a.iter_index = f.iter_index = it;
-                    icp_fast_kernel<<<div_up(ns, NN_THREADS), NN_THREADS, 0, st>>>(a);
-                    SPX_LAUNCH_CHECK();
-                    icp_coop_kernel<<<q->sm_count * 16, NN_THREADS, 0, st>>>(a);
+                    a.keep_last = keep && it >= 2;
+                    if (keep && it >= 1) {
+                        icp_fast_kernel<true><<<div_up(ns, NN_THREADS), NN_THREADS, 0, st>>>(a);
+                        SPX_LAUNCH_CHECK();
+                        icp_coop_kernel<true><<<q->sm_count * 16, NN_THREADS, 0, st>>>(a);
+                    } else {
+                        icp_fast_kernel<false><<<div_up(ns, NN_THREADS), NN_THREADS, 0, st>>>(a);
+                        SPX_LAUNCH_CHECK();
+                        icp_coop_kernel<false><<<q->sm_count * 16, NN_THREADS, 0, st>>>(a);
+                    }
                     SPX_LAUNCH_CHECK();
                     launch_linearize<0, true>(c.reg, f, c.blocks, st, q->sm_count);
                     launches += 3;

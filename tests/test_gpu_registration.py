@@ -487,6 +487,44 @@ def test_split_kernel_path_equals_fused(spx, q, pair, reg, monkeypatch):
     assert np.array_equal(split.trace, fused.trace) and np.array_equal(split.T, fused.T)
 
 
+@pytest.mark.parametrize("reg", ["GICP", "POINT_TO_POINT"])
+def test_kept_correspondences_equal_a_search(spx, q, pair, reg, monkeypatch):
+    """The split-kernel loop keeps a query's correspondence while the query has moved less than half the margin its
+    last search certified (icp_keep, spx_registration.cu).  15 forced iterations from an offset start: the pose after
+    EVERY iteration, the final neighbour indices and their distances must equal, bit for bit, those of a loop that
+    searches every query every time — and most late-iteration correspondences must actually have been kept."""
+    import ctypes as C
+    params = spx.RegistrationParams(reg_type=spx.RegType[reg], max_iterations=15)
+    params.robust.type = spx.RobustLossType.HUBER
+    params.criteria.translation = params.criteria.rotation = 0.0
+    T0 = np.eye(4, dtype=np.float32)
+    T0[:3, 3] = [0.3, -0.2, 0.05]
+    tgt, _ = clouds_for(spx, q, pair, reg)
+    monkeypatch.setenv("SPX_SPLIT_MIN", "0")
+
+    def run():
+        r = spx.Registration(q, params)
+        res = r.align(pair["src"], tgt, pair["tree"], T0, trace=True)
+        ip, dp, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        spx._lib.check(spx.lib().spx_registration_neighbors(r._h, C.byref(ip), C.byref(dp), C.byref(n)))
+        idx, dist = np.empty(n.value, np.int32), np.empty(n.value, np.float32)
+        spx._lib.check(spx.lib().spx_memcpy_d2h(q.handle, idx.ctypes.data_as(C.c_void_p), ip, idx.nbytes))
+        spx._lib.check(spx.lib().spx_memcpy_d2h(q.handle, dist.ctypes.data_as(C.c_void_p), dp, dist.nbytes))
+        q.wait()
+        return res, idx, dist, r.kept_correspondences()
+
+    monkeypatch.setenv("SPX_KEEP_FRAC", "-1")
+    every, idx_e, dist_e, kept_e = run()
+    assert kept_e == 0
+    monkeypatch.delenv("SPX_KEEP_FRAC")
+    keep, idx_k, dist_k, kept_k = run()
+    n = pair["src"].size()
+    assert kept_k > 5 * n, f"only {kept_k} of {15 * n} correspondences kept"
+    assert np.array_equal(keep.trace, every.trace) and np.array_equal(keep.T, every.T)
+    assert keep.inlier == every.inlier and keep.error == every.error
+    assert np.array_equal(idx_k, idx_e) and np.array_equal(dist_k, dist_e)
+
+
 def test_config2_full_size_pipeline_matches_oracle(spx, q):
     """BASELINE config 2 at FULL size (2.0 M raw points per cloud -> ~120 k after the 0.25 m voxel grid):
     every stage of the hot path against the oracle on the same synthetic pair — voxel output and k = 10
