@@ -79,6 +79,7 @@ struct LinArgs {
     float* slack_out;    // keep test (icp_keep): metres each query may still move before it is searched again
     float keep_infl;     // most metres a margin-tracking search adds to a candidate's distance when it prunes / certifies
     int keep_last;       // the previous iteration's search tracked margins: slack_out is valid
+    uint32_t* redo;      // [ns] queries the keep pass could not keep (count: wl_counters[WL_REDO + parity])
     int warm_start;      // idx_out holds a previous iteration's result (per-launch kernels)
     uint32_t* worklist;          // [ns] source indices whose search the first pass could not finish
     unsigned int* wl_counters;   // [2 parities][count, cursor]
@@ -615,47 +616,64 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
 // thousand source points launch overhead no longer matters, so the search gets kernels of its own
 // (64 registers -> 4x the resident warps) and the factor pass runs as linearize_kernel<REG, 0, SOLVE>.
 constexpr int NN_THREADS = 128;
+constexpr int WL_REDO = 4;   // wl_counters[WL_REDO + parity]: length of the keep pass's redo list
 constexpr int WL_KEPT = 12;  // wl_counters[WL_KEPT]: correspondences kept without a search, summed over the align's iterations
 
-// M: the search tracks margins (Best1M) and, from the second such iteration on, keeps what cannot have changed.
+// Keep pass (icp_keep) of an iteration whose predecessor tracked margins: one lane per source point, streaming.  A
+// kept correspondence gets its new distance and the rest of its allowance; the others go to the redo list that
+// icp_fast_kernel<true> searches densely (left in place they would keep every warp on the search path).
+constexpr int KEEP_THREADS = 512;
+__global__ void __launch_bounds__(KEEP_THREADS) icp_keep_kernel(const LinArgs a) {
+    if (a.state->stop) return;
+    __shared__ unsigned int warp_redo[KEEP_THREADS / 32];
+    __shared__ unsigned int block_slot;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * KEEP_THREADS + threadIdx.x;
+    bool search = i < a.ns;
+    if (search) {
+        const Xform T = state_xform(a.state), Tp = state_xform_prev(a.state);
+        const float4 ps = __ldg(a.src_pts + i);
+        search = icp_keep(T, Tp, ps, transform_point(T, ps), a.idx_out[i], a.slack_out[i], a.tgt_pts, a.max_corr_sq,
+                          a.dist_out + i, a.slack_out + i);
+    }
+    // block-aggregated append: same-address atomics serialise, one per warp would cost more than the pass itself
+    const unsigned m = __ballot_sync(FULL, search);
+    if (lane == 0) warp_redo[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int total = 0;
+        for (int w = 0; w < KEEP_THREADS / 32; ++w) {
+            const unsigned int c = warp_redo[w];
+            warp_redo[w] = total;
+            total += c;
+        }
+        const unsigned int live = min((unsigned int)KEEP_THREADS, a.ns - blockIdx.x * KEEP_THREADS);
+        if (live > total) atomicAdd(a.wl_counters + WL_KEPT, live - total);
+        block_slot = total ? atomicAdd(a.wl_counters + WL_REDO + (a.iter_index & 1), total) : 0u;
+    }
+    __syncthreads();
+    if (search) a.redo[block_slot + warp_redo[warp] + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+// M: the search tracks margins (Best1M); with a.keep_last it searches the keep pass's redo list only.
 template <bool M>
 __global__ void __launch_bounds__(NN_THREADS, 8) icp_fast_kernel(const LinArgs a) {
     if (a.state->stop) return;
     using BestT = typename std::conditional<M, Best1M, Best1>::type;
-    __shared__ unsigned short redo[NN_THREADS];
-    __shared__ unsigned int n_redo;
     const Xform T = state_xform(a.state);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool warm = a.iter_index > 0 || a.warm_start;
     const int par = a.iter_index & 1;
     unsigned int* wl_count = a.wl_counters + par * 2;
-    const uint32_t base = blockIdx.x * NN_THREADS;
-    uint32_t i = base + threadIdx.x;
+    uint32_t i = blockIdx.x * NN_THREADS + threadIdx.x;
     bool search = i < a.ns;
-    if (M && a.keep_last) {  // keep what cannot have changed; the rest is searched by the first lanes of the block
-        if (threadIdx.x == 0) n_redo = 0;
-        __syncthreads();
-        if (search) {
-            const Xform Tp = state_xform_prev(a.state);
-            const float4 ps = __ldg(a.src_pts + i);
-            search = icp_keep(T, Tp, ps, transform_point(T, ps), a.idx_out[i], a.slack_out[i], a.tgt_pts, a.max_corr_sq,
-                              a.dist_out + i, a.slack_out + i);
-        }
-        const unsigned m = __ballot_sync(FULL, search);
-        if (lane == 0) {
-            const unsigned live = min(32u, a.ns > (base + (threadIdx.x & ~31u)) ? a.ns - (base + (threadIdx.x & ~31u)) : 0u);
-            if (live > (unsigned)__popc(m)) atomicAdd(a.wl_counters + WL_KEPT, live - (unsigned)__popc(m));
-        }
-        if (m) {
-            unsigned int slot = 0;
-            if (lane == __ffs(m) - 1) slot = atomicAdd(&n_redo, (unsigned int)__popc(m));
-            slot = __shfl_sync(FULL, slot, __ffs(m) - 1);
-            if (search) redo[slot + __popc(m & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
-        }
-        __syncthreads();
-        search = threadIdx.x < n_redo;
-        if (search) i = base + redo[threadIdx.x];
+    if (M && a.keep_last) {
+        const unsigned int n_redo = a.wl_counters[WL_REDO + par];
+        if (blockIdx.x * NN_THREADS >= n_redo) return;
+        search = i < n_redo;
+        if (search) i = a.redo[i];
     }
     bool pending = false;
     if (search) {
@@ -696,6 +714,7 @@ __global__ void __launch_bounds__(NN_THREADS, 8) icp_coop_kernel(const LinArgs a
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // next iteration's counters (idle during this launch)
         a.wl_counters[(par ^ 1) * 2] = 0;
         a.wl_counters[(par ^ 1) * 2 + 1] = 0;
+        a.wl_counters[WL_REDO + (par ^ 1)] = 0;
     }
     for (;;) {
         unsigned int k = 0;
@@ -1369,7 +1388,7 @@ __global__ void __launch_bounds__(128) align_prepare_kernel(PrepArgs p) {
         }
         s.error = FLT_MAX;
         *p.state = s;
-        for (int i = 0; i < 4; ++i) p.wl_counters[i] = 0u;
+        for (int i = 0; i < 6; ++i) p.wl_counters[i] = 0u;
         p.wl_counters[WL_KEPT] = 0u;
         *p.ticket = 0u;
     }
@@ -1545,8 +1564,9 @@ struct spx_registration_s {
     double* sums = nullptr;          // device [32]
     int32_t* nn_idx = nullptr;
     float* nn_dist = nullptr;
-    uint32_t* nn_pos = nullptr;
     uint32_t* worklist = nullptr;
+    uint32_t* keep_buf = nullptr;  // split-kernel loop: [ns] allowances (float) + [ns] redo list
+    size_t keep_cap = 0;
     unsigned int* wl_counters = nullptr;
     size_t nn_cap = 0;
     float4* src_cm = nullptr;  // [3 * src_cap]
@@ -1595,7 +1615,7 @@ void reg_free(spx_registration_t r) {
         if (p) cudaFree(p);
         p = nullptr;
     };
-    f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist); f(r->nn_pos); f(r->worklist); f(r->wl_counters);
+    f(r->state); f(r->partials); f(r->ticket); f(r->sums); f(r->nn_idx); f(r->nn_dist); f(r->worklist); f(r->keep_buf); f(r->wl_counters);
     f(r->src_cm); f(r->tgt_cm); f(r->states); f(r->descs); f(r->chunk_end); f(r->preps); f(r->wl_q); f(r->wl_b); f(r->cpartials); f(r->trace); f(r->phase);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -1683,8 +1703,6 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     size_t cap_dummy = r->nn_cap;
     ensure(r->nn_idx, cap_dummy, ns, st);
     cap_dummy = r->nn_cap;
-    ensure(r->nn_pos, cap_dummy, ns, st);
-    cap_dummy = r->nn_cap;
     ensure(r->worklist, cap_dummy, ns, st);
     ensure(r->nn_dist, r->nn_cap, ns, st);
     r->nn_n = ns;
@@ -1751,7 +1769,8 @@ AlignCtx align_setup(spx_registration_t r, const float* src_points, const float*
     a.genz_counts = r->wl_counters + 8;
     a.idx_in = r->nn_idx; a.dist_in = r->nn_dist;
     a.idx_out = r->nn_idx; a.dist_out = r->nn_dist;
-    a.slack_out = reinterpret_cast<float*>(r->nn_pos);
+    a.slack_out = nullptr;
+    a.redo = nullptr;
     a.keep_infl = 0.0f;
     a.keep_last = 0;
     a.warm_start = 0;
@@ -2011,8 +2030,6 @@ void gn_align_batch(spx_registration_t r, size_t P, const spx_align_pair* pairs,
     {
         size_t cap = r->nn_cap;
         ensure(r->nn_idx, cap, total_ns, st);
-        cap = r->nn_cap;
-        ensure(r->nn_pos, cap, total_ns, st);
         cap = r->nn_cap;
         ensure(r->worklist, cap, total_ns, st);
         ensure(r->nn_dist, r->nn_cap, total_ns, st);
@@ -2753,12 +2770,22 @@ int spx_registration_align(spx_registration_t reg, const float* src_points, cons
                 const float keep_frac = keep_fraction();
                 const bool keep = keep_frac >= 0.0f;
                 a.keep_infl = keep ? keep_frac * a.grid.lv[0].cell : 0.0f;
+                if (keep) {  // allowances + redo list
+                    ensure(reg->keep_buf, reg->keep_cap, 2 * ns, st);
+                    a.slack_out = reinterpret_cast<float*>(reg->keep_buf);
+                    a.redo = reg->keep_buf + ns;
+                }
                 LinArgs f = a;  // factor pass: correspondences given, fused solve
                 f.idx_in = reg->nn_idx;
                 f.dist_in = reg->nn_dist;
                 for (int it = 0; it < max_it; ++it) {
                     a.iter_index = f.iter_index = it;
                     a.keep_last = keep && it >= 2;
+                    if (a.keep_last) {
+                        icp_keep_kernel<<<div_up(ns, KEEP_THREADS), KEEP_THREADS, 0, st>>>(a);
+                        SPX_LAUNCH_CHECK();
+                        ++launches;
+                    }
                     if (keep && it >= 1) {
                         icp_fast_kernel<true><<<div_up(ns, NN_THREADS), NN_THREADS, 0, st>>>(a);
                         SPX_LAUNCH_CHECK();

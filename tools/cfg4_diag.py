@@ -1,5 +1,5 @@
 """Config 4 (dense pair) diagnostics: correspondence-distance distribution after one iteration and the align's time
-per iteration for a few index cell targets.  usage: python tools/cfg4_diag.py"""
+per iteration for a few iteration counts.  usage: python tools/cfg4_diag.py [iters,iters,...]"""
 import ctypes as C
 import os
 import sys
@@ -22,7 +22,8 @@ ts, tt = spx.KDTree.build(q, src), spx.KDTree.build(q, tgt)
 print("target index", tt.info())
 spx.covariance.estimate(ts.knn_search(src, 10), src)
 spx.covariance.estimate(tt.knn_search(tgt, 10), tgt)
-for iters in (1, 2, 20):
+ITERS = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 2, 3, 5, 10, 20, 40]
+for iters in ITERS:
     p = spx.RegistrationParams(reg_type=spx.RegType.GICP, max_iterations=iters)
     p.robust.type = spx.RobustLossType.HUBER
     p.criteria.translation = p.criteria.rotation = 0.0
@@ -30,7 +31,8 @@ for iters in (1, 2, 20):
     reg.align(src, tgt, tt)
     reg.align(src, tgt, tt)
     t = reg.last_timing()
-    print(f"{iters} iterations: loop {t['loop_ms']:.3f} ms -> {t['loop_ms'] / iters:.3f} ms/iter")
+    print(f"{iters} iterations: loop {t['loop_ms']:.3f} ms -> {t['loop_ms'] / iters:.3f} ms/iter; "
+          f"kept without a search {reg.kept_correspondences()} of {iters * src.size()} correspondences")
     idx_p, dist_p, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
     spx._lib.check(spx.lib().spx_registration_neighbors(reg._h, C.byref(idx_p), C.byref(dist_p), C.byref(n)))
     d = np.empty(n.value, np.float32)
