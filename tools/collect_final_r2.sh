@@ -15,7 +15,17 @@ for t in test_kdtree test_registration_pipeline test_downsampling_filters test_v
   (cd /tmp/refdata && $OLDPWD/tests/cpp/_build/ref_$t) > gpurun_out/${T}_reference_${t}_on_libspx.txt 2>&1; echo "$t rc=$? $(tail -n 1 gpurun_out/${T}_reference_${t}_on_libspx.txt)"
 done
 python tools/run_odometry.py 45 > gpurun_out/${T}_odometry.txt 2>&1; tail -n 5 gpurun_out/${T}_odometry.txt
+python tools/cfg4_diag.py 2,5,20,40 > gpurun_out/${T}_cfg4_diag.txt 2>&1; grep iterations gpurun_out/${T}_cfg4_diag.txt | cut -c1-120
 bash tools/collect_profiles_r2.sh $T > gpurun_out/${T}_collect.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"icp_keep|icp_fast|icp_coop|linearize" -c 200 --csv --log-file gpurun_out/${T}_cfg4_launches.csv python tools/cfg4_diag.py 12 > /dev/null 2>&1
+python - <<PY
+import csv
+rows = [r for r in csv.reader(open("gpurun_out/${T}_cfg4_launches.csv")) if len(r) > 10 and r[0].isdigit()]
+with open("gpurun_out/${T}_cfg4_launches.txt", "w") as f:
+    f.write("config 4 (1.64 M x 1.54 M, GICP), second 12-iteration align: ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised launches)\n")
+    for r in rows[-47:]:
+        f.write(f"{r[4][:60]:60s} {int(float(r[-1])) / 1e3:9.1f} us\n")
+PY
 bash tools/collect_ncu_full_r2.sh $T > gpurun_out/${T}_collect_full.log 2>&1
 python - <<PY
 import json
