@@ -114,6 +114,8 @@ struct LinArgs {
     unsigned long long* phase;
 };
 constexpr int PH_START = 0, PH_NN = 1, PH_COOP = 2, PH_ACC = 3, PH_PART = 4, PH_SYNC = 5, PH_FOLD = 6, PH_SOLVE = 7, PH_N = 8;
+constexpr int WL_REDO = 4;   // wl_counters[WL_REDO + parity]: length of the keep pass's redo list
+constexpr int WL_KEPT = 12;  // wl_counters[WL_KEPT]: correspondences kept without a search, summed over the align's iterations
 constexpr int PH_MAX_ITERS = 64;
 constexpr int PH_MAX_WARPS = 8192;
 constexpr size_t PH_WORDS = (size_t)PH_MAX_ITERS * PH_N + (size_t)PH_MAX_WARPS * 5;
@@ -610,14 +612,125 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
     grid.sync();
 }
 
+// nn_search_grid with the keep test (icp_keep) for the sharded one-launch align, whose shards of a dense cloud run many
+// iterations: from the third iteration on a streaming keep pass carries over every correspondence whose allowance
+// outlasts the query's step and lists the others (block-aggregated append); one more grid barrier, then the first
+// pass runs densely over that redo list.  Searches track margins (Best1M) from the first iteration on.  a.keep_infl
+// < 0: every query is searched in every iteration (results are the same either way).
+__device__ __forceinline__ void nn_search_grid_keep(const LinArgs& a, const Xform& T, const Xform& Tp, int it,
+                                                    cooperative_groups::grid_group& grid) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool warm = it > 0;
+    const bool keep_it = it >= 2 && a.keep_infl >= 0.0f;
+    const float infl_max = fmaxf(a.keep_infl, 0.0f);
+    const int par = it & 1;
+    unsigned int* wl_count = a.wl_counters + par * 2;
+    unsigned int* wl_cursor = a.wl_counters + par * 2 + 1;
+    unsigned int* redo_count = a.wl_counters + WL_REDO + par;
+    __shared__ unsigned int warp_redo[LIN_WARPS];
+    __shared__ unsigned int block_slot;
+    if (keep_it) {
+        for (uint32_t base = blockIdx.x * LIN_THREADS; base < a.ns; base += gridDim.x * LIN_THREADS) {
+            const uint32_t i = base + threadIdx.x;
+            bool search = i < a.ns;
+            if (search) {
+                const float4 ps = __ldg(a.src_pts + i);
+                search = icp_keep(T, Tp, ps, transform_point(T, ps), __ldcg(a.idx_out + i), __ldcg(a.slack_out + i), a.tgt_pts,
+                                  a.max_corr_sq, a.dist_out + i, a.slack_out + i);
+            }
+            const unsigned m = __ballot_sync(FULL, search);
+            if (lane == 0) warp_redo[warp] = __popc(m);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int total = 0;
+                for (int w = 0; w < LIN_WARPS; ++w) {
+                    const unsigned int c = warp_redo[w];
+                    warp_redo[w] = total;
+                    total += c;
+                }
+                const unsigned int live = min((unsigned int)LIN_THREADS, a.ns - base);
+                if (live > total) atomicAdd(a.wl_counters + WL_KEPT, live - total);
+                block_slot = total ? atomicAdd(redo_count, total) : 0u;
+            }
+            __syncthreads();
+            if (search) a.redo[block_slot + warp_redo[warp] + __popc(m & ((1u << lane) - 1u))] = i;
+            __syncthreads();
+        }
+        __threadfence();
+        grid.sync();
+    }
+    const uint32_t n_first = keep_it ? __ldcg(redo_count) : a.ns;
+    for (uint32_t base = blockIdx.x * LIN_THREADS; base < n_first; base += gridDim.x * LIN_THREADS) {
+        const uint32_t k = base + threadIdx.x;
+        bool pending = false;
+        uint32_t i = k;
+        if (k < n_first) {
+            if (keep_it) i = __ldcg(a.redo + k);
+            Best1M best;
+            best.init();
+            const float4 ps = __ldg(a.src_pts + i);
+            const int prev_i = warm ? __ldcg(a.idx_out + i) : -1;
+            const float4 q = transform_point(T, ps);
+            const float qinf = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+            if (a.grid.lv[0].n > 0 && isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) {
+                const float infl = warm && a.keep_infl >= 0.0f ? icp_keep_infl(T, Tp, ps, qinf, infl_max) : 0.0f;
+                pending = !icp_fast(a.grid, q.x, q.y, q.z, prev_i, a.tgt_pts, a.max_corr, best, infl);
+            }
+            a.idx_out[i] = best.i;
+            a.dist_out[i] = best.d;
+            // unfinished: the runner-up bound travels to the cooperative phase in the allowance's slot
+            a.slack_out[i] = pending ? best.d2 : icp_keep_slack(best, qinf, a.max_corr_sq);
+        }
+        const unsigned m = __ballot_sync(FULL, pending);
+        if (m) {
+            unsigned int slot = 0;
+            if (lane == __ffs(m) - 1) slot = atomicAdd(wl_count, (unsigned int)__popc(m));
+            slot = __shfl_sync(FULL, slot, __ffs(m) - 1);
+            if (pending) a.worklist[slot + __popc(m & ((1u << lane) - 1u))] = i;
+        }
+    }
+    phase_mark(a.phase, it, PH_NN);
+    __threadfence();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the other parity's counters: idle until the next iteration
+        a.wl_counters[(par ^ 1) * 2] = 0;
+        a.wl_counters[(par ^ 1) * 2 + 1] = 0;
+        a.wl_counters[WL_REDO + (par ^ 1)] = 0;
+    }
+    const unsigned int n_slow = __ldcg(wl_count);
+    for (;;) {
+        unsigned int k = 0;
+        if (lane == 0) k = atomicAdd(wl_cursor, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_slow) break;
+        const uint32_t i = __ldcg(a.worklist + k);
+        const float4 ps = __ldg(a.src_pts + i);
+        const float4 q = transform_point(T, ps);
+        const float qinf = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+        Best1M best;
+        best.init();
+        best.i = __ldcg(a.idx_out + i);
+        best.d = __ldcg(a.dist_out + i);
+        best.d2 = __ldcg(a.slack_out + i);
+        const float infl = warm && a.keep_infl >= 0.0f ? icp_keep_infl(T, Tp, ps, qinf, infl_max) : 0.0f;
+        icp_coop_search(a.grid, q.x, q.y, q.z, best, a.max_corr, nullptr, infl);
+        if (lane == 0) {
+            a.idx_out[i] = best.i;
+            a.dist_out[i] = best.d;
+            a.slack_out[i] = icp_keep_slack(best, qinf, a.max_corr_sq);
+        }
+    }
+    __threadfence();
+    grid.sync();
+}
+
 // ---- the same search as three ordinary launches per iteration (large clouds)
 // The cooperative kernels carry the factor arithmetic's register budget (128/thread -> 16 warps per
 // SM) through the search, which is latency-bound and wants warps in flight.  Above a few hundred
 // thousand source points launch overhead no longer matters, so the search gets kernels of its own
 // (64 registers -> 4x the resident warps) and the factor pass runs as linearize_kernel<REG, 0, SOLVE>.
 constexpr int NN_THREADS = 128;
-constexpr int WL_REDO = 4;   // wl_counters[WL_REDO + parity]: length of the keep pass's redo list
-constexpr int WL_KEPT = 12;  // wl_counters[WL_KEPT]: correspondences kept without a search, summed over the align's iterations
 
 // Keep pass (icp_keep) of an iteration whose predecessor tracked margins: one lane per source point, streaming.  A
 // kept correspondence gets its new distance and the rest of its allowance; the others go to the redo list that
@@ -926,7 +1039,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) align_gn_kernel(const LinArgs 
         for (int v = 0; v < N_ACC; ++v) acc[v] = 0.0f;
         uint32_t inl = 0;
         phase_mark(a.phase, it, PH_START);
-        nn_search_grid(a, T, it, grid);
+        if constexpr (SHARDED) nn_search_grid_keep(a, T, state_xform_prev(&st), it, grid);
+        else nn_search_grid(a, T, it, grid);
         phase_mark(a.phase, it, PH_COOP);
         lin_accumulate<REG, 1>(a, T, acc, inl);
         if (a.phase) {
@@ -3083,6 +3197,13 @@ int spx_registration_align_sharded_launch(spx_registration_t reg, spx_comm_t com
         x.ready = reinterpret_cast<unsigned long long*>(comm->local + SPX_MBOX_READY);
         x.error = reinterpret_cast<unsigned int*>(comm->local + SPX_MBOX_ERROR);
         const int max_it = std::max(reg->P.max_iterations, 0);
+        {  // keep test of the search (nn_search_grid_keep): allowances + redo list
+            const float keep_frac = keep_fraction();
+            ensure(reg->keep_buf, reg->keep_cap, 2 * std::max<size_t>(ns, 1), st);
+            a.slack_out = reinterpret_cast<float*>(reg->keep_buf);
+            a.redo = reg->keep_buf + std::max<size_t>(ns, 1);
+            a.keep_infl = keep_frac >= 0.0f ? keep_frac * a.grid.lv[0].cell : -1.0f;
+        }
         x.seq0 = comm->seq;  // advanced by spx_registration_align_sharded_finish, by the iterations that ran
         SPX_CUDA(cudaMemsetAsync(x.error, 0, sizeof(unsigned int), st));
         reg->timed = false;
