@@ -530,9 +530,10 @@ SPX_API int spx_batch_last_timing(spx_batch_t batch, float* align_ms, int32_t* i
  * the number of outer iterations that did work: bench.py's live per-launch duration. */
 SPX_API int spx_registration_last_timing(spx_registration_t reg, float* loop_ms, int32_t* launches, int32_t* iterations);
 /* Tuning aid: correspondences of the last align that were KEPT without a search, summed over its iterations.  The
- * split-kernel Gauss-Newton loop (large clouds) keeps a query's nearest neighbour while the query has moved less than
- * half the margin its last search certified between the nearest and every other target point — the same index and
- * the same distance find_correspondences (registration.hpp:576-604 -> kdtree.hpp:463-553) would return.
+ * split-kernel Gauss-Newton loop (large clouds) and the sharded one-launch align keep a query's nearest neighbour
+ * while the query has moved less than half the margin its last search certified between the nearest and every other
+ * target point — the same index and the same distance find_correspondences (registration.hpp:576-604 ->
+ * kdtree.hpp:463-553) would return.
  * SPX_KEEP_FRAC < 0 in the environment searches every query in every iteration. */
 SPX_API int spx_registration_kept_correspondences(spx_registration_t reg, uint64_t* kept);
 /* tuning aid: per-iteration phase timestamps of the cooperative align kernel (globaltimer ns, latest
