@@ -417,9 +417,10 @@ def run_reference(ctx):
 
 def workload_pair(ctx):
     args, spx, q = ctx.args, ctx.spx, ctx.q
-    # every rank drives two queues from two host threads; when that oversubscribes the host's cores
-    # the queues wait on an OS primitive instead of spinning (SPX_BENCH_SYNC=spin|block overrides)
-    sync_mode = os.environ.get("SPX_BENCH_SYNC", "block" if 3 * ctx.world > (os.cpu_count() or 1) // 2 else "spin")
+    # every rank drives its queues from three host threads; only when those outnumber the host's cores do the queues wait
+    # on an OS primitive instead of spinning (SPX_BENCH_SYNC=spin|block overrides).  Measured, 8 ranks on 32 cores:
+    # spinning 8302 pairs/s (0.964 ms/step), blocking 6567 (1.218) — profiles/r2r_bench_8gpu*.json
+    sync_mode = os.environ.get("SPX_BENCH_SYNC", "block" if 3 * ctx.world > (os.cpu_count() or 1) else "spin")
     pairs = rotating_pairs(ctx.rank)
     pipe = PairPipeline(spx, q, [len(p[1]) for p in pairs], [len(p[0]) for p in pairs])
     if sync_mode == "block":
