@@ -79,11 +79,10 @@ struct Best1 {
     static constexpr bool MARGIN = false;
     float d;
     int i;      // original index
-    uint32_t p; // sorted position (for gathers in fused kernels)
-    __device__ __forceinline__ void init() { d = FLT_MAX; i = -1; p = 0; }
+    __device__ __forceinline__ void init() { d = FLT_MAX; i = -1; }
     __device__ __forceinline__ float worst() const { return d; }
-    __device__ __forceinline__ void offer(float ds, int idx, uint32_t pos) {
-        if (ds < d || (ds == d && (i < 0 || idx < i))) { d = ds; i = idx; p = pos; }
+    __device__ __forceinline__ void offer(float ds, int idx, uint32_t) {
+        if (ds < d || (ds == d && (i < 0 || idx < i))) { d = ds; i = idx; }
     }
 };
 
@@ -879,7 +878,6 @@ static __device__ __noinline__ void icp_coop_search(const GridLevels& gl, float 
         const int wl = __ffs(win) - 1;
         best.d = __shfl_sync(FULL, mine.d, wl);
         best.i = __shfl_sync(FULL, mine.i, wl);
-        if constexpr (!B::MARGIN) best.p = __shfl_sync(FULL, mine.p, wl);
         l_min = L;
         r_done = R;
         // stop test of the block just completed (grid_search's)

@@ -538,7 +538,6 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_knn_kernel(const GridLevels
 __global__ void __launch_bounds__(GRID_THREADS) grid_nn1_fast_kernel(const GridLevels g, const float4* __restrict__ queries,
                                                                      uint32_t nq, Xform T, int has_T, float max_radius,
                                                                      int32_t* __restrict__ idx, float* __restrict__ dist,
-                                                                     uint32_t* __restrict__ pos,
                                                                      uint32_t* __restrict__ worklist,
                                                                      unsigned int* __restrict__ wl_count) {
     const uint32_t qi = blockIdx.x * GRID_THREADS + threadIdx.x;
@@ -553,7 +552,6 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_nn1_fast_kernel(const GridL
             pending = !icp_fast(g, q.x, q.y, q.z, -1, nullptr, max_radius, best);
         idx[qi] = best.i;
         dist[qi] = best.d;
-        pos[qi] = best.p;
     }
     const unsigned m = __ballot_sync(0xffffffffu, pending);
     if (m) {
@@ -567,7 +565,6 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_nn1_fast_kernel(const GridL
 __global__ void __launch_bounds__(GRID_THREADS) grid_nn1_coop_kernel(const GridLevels g, const float4* __restrict__ queries,
                                                                      Xform T, int has_T, float max_radius,
                                                                      int32_t* __restrict__ idx, float* __restrict__ dist,
-                                                                     const uint32_t* __restrict__ pos,
                                                                      const uint32_t* __restrict__ worklist,
                                                                      const unsigned int* __restrict__ wl_count,
                                                                      unsigned int* __restrict__ wl_cursor) {
@@ -584,7 +581,6 @@ __global__ void __launch_bounds__(GRID_THREADS) grid_nn1_coop_kernel(const GridL
         Best1 best;
         best.i = idx[qi];
         best.d = dist[qi];
-        best.p = pos[qi];
         icp_coop_search(g, q.x, q.y, q.z, best, max_radius);
         if (lane == 0) {
             idx[qi] = best.i;
@@ -1719,17 +1715,16 @@ int spx_index_knn(spx_index_t index, const float* queries, size_t nq, int k, con
         const float4* qs = reinterpret_cast<const float4*>(queries);
         if (k == 1) {
             q->arena_reset();
-            q->arena_reserve(nq * 8 + 4096);
-            uint32_t* pos = q->take<uint32_t>(nq);
+            q->arena_reserve(nq * 4 + 4096);
             uint32_t* worklist = q->take<uint32_t>(nq);
             unsigned int* counters = q->take<unsigned int>(16);
             SPX_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), q->stream));
             grid_nn1_fast_kernel<<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, T, has_T, INFINITY,
-                                                                        idx, dist, pos, worklist, counters);
+                                                                        idx, dist, worklist, counters);
             SPX_LAUNCH_CHECK();
             // the drain kernel sizes itself to the device, not to the (unknown on the host) list length
             grid_nn1_coop_kernel<<<q->sm_count * 8, GRID_THREADS, 0, q->stream>>>(index->levels, qs, T, has_T, INFINITY, idx,
-                                                                                 dist, pos, worklist, counters, counters + 1);
+                                                                                 dist, worklist, counters, counters + 1);
         } else if (k <= 20 && std::getenv("SPX_KNN_ONEPASS")) {  // tuning aid: the single-launch variant
             if (k <= 5)
                 grid_knn_reg_kernel<5><<<blocks, GRID_THREADS, 0, q->stream>>>(index->levels, qs, (uint32_t)nq, k, T, has_T, idx, dist);

@@ -547,7 +547,7 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
         if (i < a.ns) {
             Best1 best;
             best.init();
-            // the three loads are independent: issued together, one round trip instead of three
+            // the two loads are independent: issued together, one round trip instead of two
             const float4 ps = __ldg(a.src_pts + i);
             const int prev_i = warm ? __ldcg(a.idx_out + i) : -1;
             const float4 q = transform_point(T, ps);
@@ -589,7 +589,6 @@ __device__ __forceinline__ void nn_search_grid(const LinArgs& a, const Xform& T,
         Best1 best;
         best.i = __ldcg(a.idx_out + i);
         best.d = __ldcg(a.dist_out + i);
-        best.p = 0u;
         icp_coop_search(a.grid, q.x, q.y, q.z, best, a.max_corr);
         if (lane == 0) {
             a.idx_out[i] = best.i;
@@ -1268,7 +1267,7 @@ __global__ void __launch_bounds__(LIN_THREADS, CTAS) align_batch_kernel(const Ba
                 if (pending) {
                     const unsigned int w = slot + __popc(m & ((1u << lane) - 1u));
                     a.wl_q[w] = make_float4(q.x, q.y, q.z, __uint_as_float(i));
-                    a.wl_b[w] = make_float4(best.d, __int_as_float(best.i), __uint_as_float(best.p), __uint_as_float(p));
+                    a.wl_b[w] = make_float4(best.d, __int_as_float(best.i), 0.0f, __uint_as_float(p));
                 }
             }
         }
@@ -1294,7 +1293,6 @@ __global__ void __launch_bounds__(LIN_THREADS, CTAS) align_batch_kernel(const Ba
                 Best1 best;
                 best.d = bv.x;
                 best.i = __float_as_int(bv.y);
-                best.p = __float_as_uint(bv.z);
                 icp_coop_search(d->grid, qv.x, qv.y, qv.z, best, a.max_corr);
                 if (lane == 0) {
                     d->idx[i] = best.i;
