@@ -343,6 +343,31 @@ def test_fused_exchange_world1_equals_plain_align(spx, q, pair):
     comms.close()
 
 
+def test_fused_exchange_keeps_correspondences_bit_exactly(spx, q, pair):
+    """The sharded one-launch kernel carries correspondences over from one iteration to the next when their certified
+    margin outlasts the query's motion (nn_search_grid_keep).  15 forced iterations from an offset start, single rank:
+    H, b, the pose and the inlier count equal the plain cooperative align's (which searches every query every time),
+    and a good part of the correspondences was in fact kept."""
+    from sycl_points_b200.multi_gpu import LocalCommunicators
+    params = spx.RegistrationParams(max_iterations=15)
+    params.robust.type = spx.RobustLossType.HUBER
+    params.criteria.translation = params.criteria.rotation = 0.0
+    T0 = np.eye(4, dtype=np.float32)
+    T0[:3, 3] = [0.3, -0.2, 0.05]
+    ref = spx.Registration(q, params).align(pair["src"], pair["tgt"], pair["tree"], T0)
+    comms = LocalCommunicators([q])
+    reg = spx.Registration(q, params)
+    spx._lib.check(spx.lib().spx_registration_set_params(reg._h, params.to_c()))
+    t16 = np.ascontiguousarray(T0.T).reshape(16)
+    _sharded_launch(spx, reg, comms.handles[0], pair["src"], pair["tgt"], pair["tree"], t16)
+    out = _sharded_finish(spx, reg)
+    assert np.array_equal(out.T, ref.T) and out.iterations == ref.iterations == 14
+    assert out.inlier == ref.inlier and np.array_equal(out.H, ref.H) and np.array_equal(out.b, ref.b)
+    kept = reg.kept_correspondences()
+    assert kept > 5 * pair["src"].size(), f"only {kept} of {15 * pair['src'].size()} correspondences kept"
+    comms.close()
+
+
 @pytest.mark.parametrize("split", ["half", "empty_tail"])
 def test_fused_exchange_two_ranks_on_one_gpu(spx, pair, split):
     """Two ranks of the exchange protocol co-resident on ONE device (two queues, the persistent
